@@ -1,0 +1,721 @@
+// grb_post.cu -- HDR post chain (bloom threshold / pyramid / luminance / tonemap) and post-AA
+// (FXAA, TAA resolve) as sm_100a kernels.  Compiled with -fmad=false: every multiply/add is a
+// separate IEEE op in source order, so results are comparable bit-for-bit with the CPU oracle
+// except where a transcendental (log2f, exp2f, powf) is involved.
+//
+// What each kernel replaces in the reference is cited at its entry point.  None of these is a
+// translation of the GLSL: a pass here is one CUDA grid over OUTPUT texels (optionally only the
+// rows of one screen-row shard), reading packed texels straight from HBM/L2 with 4/8-byte
+// coalesced accesses; the small pyramid levels live entirely in the 126 MB L2.
+#include "grb_common.cuh"
+
+namespace grb
+{
+namespace
+{
+constexpr int kBlockX = 32;
+constexpr int kBlockY = 8;
+
+inline dim3 grid_for(int w, int rows) { return dim3((w + kBlockX - 1) / kBlockX, (rows + kBlockY - 1) / kBlockY, 1); }
+
+// ------------------------------------------------------------------------------- K7
+// bloom_threshold: out(x,y) = f(bilinear HDR at the output texel centre).
+template <bool DynamicExposure>
+__global__ void __launch_bounds__(kBlockX *kBlockY) bloom_threshold_kernel(View<const uint32_t> hdr, const float *__restrict__ lum,
+                                                                          View<uint2> out, int y0, int y1, float inv_w, float inv_h)
+{
+	int x = blockIdx.x * kBlockX + threadIdx.x;
+	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x >= out.w || y >= y1)
+		return;
+	float u = ((float)x + 0.5f) * inv_w;
+	float v = ((float)y + 0.5f) * inv_h;
+	Bilin s = bilin_setup(u, v, hdr.w, hdr.h);
+	float3 t00 = unpack_r11g11b10(__ldg(&hdr.at(s.x0, s.y0)));
+	float3 t10 = unpack_r11g11b10(__ldg(&hdr.at(s.x1, s.y0)));
+	float3 t01 = unpack_r11g11b10(__ldg(&hdr.at(s.x0, s.y1)));
+	float3 t11 = unpack_r11g11b10(__ldg(&hdr.at(s.x1, s.y1)));
+	float3 c = make_float3(bilin_mix(t00.x, t10.x, t01.x, t11.x, s.a, s.b), bilin_mix(t00.y, t10.y, t01.y, t11.y, s.a, s.b),
+	                       bilin_mix(t00.z, t10.z, t01.z, t11.z, s.a, s.b));
+	float luminance = fmax_(fmax_(c.x, c.y), c.z) + 0.0001f;
+	float loglum = log2f(luminance);
+	c.x = c.x / luminance;
+	c.y = c.y / luminance;
+	c.z = c.z / luminance;
+	if (DynamicExposure)
+		luminance -= 8.0f * __ldg(&lum[1]);
+	else
+		luminance -= 8.0f;
+	out.at(x, y) = pack_rgba16f(make_float4(fmax_(c.x * luminance, 0.0f), fmax_(c.y * luminance, 0.0f), fmax_(c.z * luminance, 0.0f), loglum));
+}
+
+// ------------------------------------------------------------------------------- K8 / K9
+// 9-tap tent over a LinearClamp source; tap order and weights are the contract (fp32 sums are
+// order-sensitive): centre 1/4, then (-,+) (0,+) (+,+) (-,0) (+,0) (-,-) (0,-) (+,-).
+__device__ __forceinline__ float4 tent9(const View<const uint2> &src, float u, float v, float off, float inv_in_w, float inv_in_h)
+{
+	const float du = off * inv_in_w, dv = off * inv_in_h;
+	const float um = u + (-du), up = u + du;
+	const float vm = v + (-dv), vp = v + dv;
+	float4 s = sample_rgba16f(src, u, v);
+	float4 acc = make_float4(0.25f * s.x, 0.25f * s.y, 0.25f * s.z, 0.25f * s.w);
+#define GRB_TAP(W, U, V)                     \
+	s = sample_rgba16f(src, (U), (V));       \
+	acc.x += (W)*s.x;                        \
+	acc.y += (W)*s.y;                        \
+	acc.z += (W)*s.z;                        \
+	acc.w += (W)*s.w;
+	GRB_TAP(0.0625f, um, vp)
+	GRB_TAP(0.125f, u, vp)
+	GRB_TAP(0.0625f, up, vp)
+	GRB_TAP(0.125f, um, v)
+	GRB_TAP(0.125f, up, v)
+	GRB_TAP(0.0625f, um, vm)
+	GRB_TAP(0.125f, u, vm)
+	GRB_TAP(0.0625f, up, vm)
+#undef GRB_TAP
+	return acc;
+}
+
+template <bool Feedback>
+__global__ void __launch_bounds__(kBlockX *kBlockY) bloom_downsample_kernel(View<const uint2> src, View<const uint2> history, float lerp,
+                                                                           View<uint2> out, int y0, int y1, float inv_w, float inv_h,
+                                                                           float inv_in_w, float inv_in_h)
+{
+	int x = blockIdx.x * kBlockX + threadIdx.x;
+	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x >= out.w || y >= y1)
+		return;
+	float u = ((float)x + 0.5f) * inv_w;
+	float v = ((float)y + 0.5f) * inv_h;
+	float4 value = tent9(src, u, v, 1.75f, inv_in_w, inv_in_h);
+	if (Feedback)
+	{
+		float4 hs = unpack_rgba16f(__ldg(&history.at(x, y)));
+		value = make_float4(fmix(hs.x, value.x, lerp), fmix(hs.y, value.y, lerp), fmix(hs.z, value.z, lerp), fmix(hs.w, value.w, 1.0f));
+	}
+	out.at(x, y) = pack_rgba16f(value);
+}
+
+__global__ void __launch_bounds__(kBlockX *kBlockY) bloom_upsample_kernel(View<const uint2> src, View<uint2> out, int y0, int y1, float inv_w,
+                                                                         float inv_h, float inv_in_w, float inv_in_h)
+{
+	int x = blockIdx.x * kBlockX + threadIdx.x;
+	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x >= out.w || y >= y1)
+		return;
+	float u = ((float)x + 0.5f) * inv_w;
+	float v = ((float)y + 0.5f) * inv_h;
+	out.at(x, y) = pack_rgba16f(tent9(src, u, v, 0.875f, inv_in_w, inv_in_h));
+}
+
+// ------------------------------------------------------------------------------- K10
+// Average log-luminance.  The reference sums with one 8x8 workgroup: each invocation adds its
+// strided samples in (y-iter, x-iter) order, then a shared-memory tree 32,16,8,4,2 and a final
+// s[0]+s[1].  fp32 addition is not associative, so the same association is kept here: the
+// strided partials are per-thread, and the tree is five xor-free shuffle-down steps over two
+// warps' worth of values held in shared memory.
+__device__ __forceinline__ float luminance_sample(const View<const uint2> &d3, int sx, int sy, float inv_sx, float inv_sy)
+{
+	return sample_rgba16f(d3, ((float)sx + 0.5f) * inv_sx, ((float)sy + 0.5f) * inv_sy).w;
+}
+
+__device__ __forceinline__ void luminance_tail(float *s, int tid, int size_x, int size_y, float inv_sx, float inv_sy, float *lum, float lerp,
+                                              float lo, float hi)
+{
+	// s[0..63] holds the 64 strided partials (index = ly * 8 + lx).
+	__syncthreads();
+	if (tid < 32)
+	{
+		float a = s[tid] + s[tid + 32];                     // STEP(32)
+		a = a + __shfl_down_sync(0xffffffffu, a, 16);       // STEP(16): lanes 0..15 valid
+		a = a + __shfl_down_sync(0xffffffffu, a, 8);        // STEP(8)
+		a = a + __shfl_down_sync(0xffffffffu, a, 4);        // STEP(4)
+		a = a + __shfl_down_sync(0xffffffffu, a, 2);        // STEP(2): lanes 0,1 valid
+		float b = __shfl_down_sync(0xffffffffu, a, 1);
+		if (tid == 0)
+		{
+			float loglum = a + b;
+			loglum *= inv_sx * inv_sy;
+			loglum = fclamp(loglum, lo, hi);
+			float new_log = fmix(lum[0], loglum, lerp);
+			lum[0] = new_log;
+			lum[1] = exp2f(new_log);
+			lum[2] = exp2f(-new_log);
+		}
+	}
+	(void)size_x;
+	(void)size_y;
+}
+
+__global__ void __launch_bounds__(64) luminance_kernel(View<const uint2> d3, float *lum, float lerp, float lo, float hi)
+{
+	__shared__ float s[64];
+	const int size_x = d3.w / 2, size_y = d3.h / 2;
+	const int iter_y = (size_y + 7) >> 3, iter_x = (size_x + 7) >> 3;
+	const float inv_sx = 1.0f / (float)size_x, inv_sy = 1.0f / (float)size_y;
+	const int lx = threadIdx.x & 7, ly = threadIdx.x >> 3;
+	float total = 0.0f;
+	for (int y = 0; y < iter_y; y++)
+		for (int x = 0; x < iter_x; x++)
+		{
+			int sx = x * 8 + lx, sy = y * 8 + ly;
+			if (sx < size_x && sy < size_y)
+				total += luminance_sample(d3, sx, sy, inv_sx, inv_sy);
+		}
+	s[threadIdx.x] = total;
+	luminance_tail(s, threadIdx.x, size_x, size_y, inv_sx, inv_sy, lum, lerp, lo, hi);
+}
+
+// Sharded form, step 1: every thread samples one grid texel of the rows this rank owns.
+__global__ void __launch_bounds__(kBlockX *kBlockY) luminance_grid_kernel(View<const uint2> d3, float *grid, int y0, int y1)
+{
+	const int size_x = d3.w / 2, size_y = d3.h / 2;
+	int x = blockIdx.x * kBlockX + threadIdx.x;
+	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x >= size_x || y >= y1 || y >= size_y)
+		return;
+	grid[y * size_x + x] = luminance_sample(d3, x, y, 1.0f / (float)size_x, 1.0f / (float)size_y);
+}
+
+// step 2: identical association order to luminance_kernel, reading the assembled grid.
+__global__ void __launch_bounds__(64) luminance_finalize_kernel(const float *__restrict__ grid, int size_x, int size_y, float *lum, float lerp,
+                                                               float lo, float hi)
+{
+	__shared__ float s[64];
+	const int iter_y = (size_y + 7) >> 3, iter_x = (size_x + 7) >> 3;
+	const int lx = threadIdx.x & 7, ly = threadIdx.x >> 3;
+	float total = 0.0f;
+	for (int y = 0; y < iter_y; y++)
+		for (int x = 0; x < iter_x; x++)
+		{
+			int sx = x * 8 + lx, sy = y * 8 + ly;
+			if (sx < size_x && sy < size_y)
+				total += grid[sy * size_x + sx];
+		}
+	s[threadIdx.x] = total;
+	luminance_tail(s, threadIdx.x, size_x, size_y, 1.0f / (float)size_x, 1.0f / (float)size_y, lum, lerp, lo, hi);
+}
+
+// ------------------------------------------------------------------------------- K11
+__device__ __forceinline__ float uncharted2(float x)
+{
+	const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+	return ((x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F)) - E / F;
+}
+
+template <bool DynamicExposure, bool SrgbTarget>
+__global__ void __launch_bounds__(kBlockX *kBlockY) tonemap_kernel(View<const uint32_t> hdr, View<const uint2> bloom, const float *__restrict__ lum,
+                                                                  float exposure, View<uint32_t> out, int y0, int y1, float inv_w, float inv_h)
+{
+	int x = blockIdx.x * kBlockX + threadIdx.x;
+	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x >= out.w || y >= y1)
+		return;
+	float3 c = unpack_r11g11b10(__ldg(&hdr.at(x, y)));
+	float u = ((float)x + 0.5f) * inv_w;
+	float v = ((float)y + 0.5f) * inv_h;
+	float4 b = sample_rgba16f(bloom, u, v);
+	const float white_scale = 1.0f / uncharted2(11.2f);
+	const float k = DynamicExposure ? (__ldg(&lum[2]) * exposure) : exposure;
+	float r = uncharted2((c.x + b.x) * k) * white_scale;
+	float g = uncharted2((c.y + b.y) * k) * white_scale;
+	float bl = uncharted2((c.z + b.z) * k) * white_scale;
+	uint32_t px;
+	if (SrgbTarget)
+		px = linear_to_srgb8(r) | (linear_to_srgb8(g) << 8) | (linear_to_srgb8(bl) << 16) | 0xff000000u;
+	else
+		px = float_to_unorm8(r) | (float_to_unorm8(g) << 8) | (float_to_unorm8(bl) << 16) | 0xff000000u;
+	out.at(x, y) = px;
+}
+
+// ------------------------------------------------------------------------------- K12
+__device__ __forceinline__ float3 unorm8_rgb(uint32_t p)
+{
+	return make_float3((float)(p & 0xffu) / 255.0f, (float)((p >> 8) & 0xffu) / 255.0f, (float)((p >> 16) & 0xffu) / 255.0f);
+}
+
+__device__ __forceinline__ float3 fetch_unorm8(const View<const uint32_t> &im, int x, int y)
+{
+	return unorm8_rgb(__ldg(&im.at(iclamp(x, 0, im.w - 1), iclamp(y, 0, im.h - 1))));
+}
+
+__device__ __forceinline__ float3 sample_unorm8(const View<const uint32_t> &im, float u, float v)
+{
+	Bilin s = bilin_setup(u, v, im.w, im.h);
+	float3 t00 = unorm8_rgb(__ldg(&im.at(s.x0, s.y0))), t10 = unorm8_rgb(__ldg(&im.at(s.x1, s.y0)));
+	float3 t01 = unorm8_rgb(__ldg(&im.at(s.x0, s.y1))), t11 = unorm8_rgb(__ldg(&im.at(s.x1, s.y1)));
+	return make_float3(bilin_mix(t00.x, t10.x, t01.x, t11.x, s.a, s.b), bilin_mix(t00.y, t10.y, t01.y, t11.y, s.a, s.b),
+	                   bilin_mix(t00.z, t10.z, t01.z, t11.z, s.a, s.b));
+}
+
+__device__ __forceinline__ float luma_of(float3 c) { return c.x * 0.299f + c.y * 0.587f + c.z * 0.114f; }
+
+__device__ __forceinline__ float decode_srgb1(float c)
+{
+	float small_side = c / 12.92f;
+	float pow_side = powf((c + 0.055f) / 1.055f, 2.4f);
+	return fclamp(c <= 0.0404482362771082f ? small_side : pow_side, 0.0f, 1.0f);
+}
+
+template <bool SrgbTarget>
+__global__ void __launch_bounds__(kBlockX *kBlockY) fxaa_kernel(View<const uint32_t> in, View<uint32_t> out, int y0, int y1, float inv_w, float inv_h)
+{
+	int x = blockIdx.x * kBlockX + threadIdx.x;
+	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x >= out.w || y >= y1)
+		return;
+	const float FXAA_REDUCE_MIN = 1.0f / 128.0f, FXAA_REDUCE_MUL = 1.0f / 8.0f, FXAA_SPAN_MAX = 8.0f;
+	float u = ((float)x + 0.5f) * inv_w, v = ((float)y + 0.5f) * inv_h;
+	float lumaNW = luma_of(fetch_unorm8(in, x - 1, y - 1));
+	float lumaNE = luma_of(fetch_unorm8(in, x + 1, y - 1));
+	float lumaSW = luma_of(fetch_unorm8(in, x - 1, y + 1));
+	float lumaSE = luma_of(fetch_unorm8(in, x + 1, y + 1));
+	float lumaM = luma_of(fetch_unorm8(in, x, y));
+	float lumaMin = fmin_(lumaM, fmin_(fmin_(lumaNW, lumaNE), fmin_(lumaSW, lumaSE)));
+	float lumaMax = fmax_(lumaM, fmax_(fmax_(lumaNW, lumaNE), fmax_(lumaSW, lumaSE)));
+	float dx = -((lumaNW + lumaNE) - (lumaSW + lumaSE));
+	float dy = ((lumaNW + lumaSW) - (lumaNE + lumaSE));
+	float dirReduce = fmax_((lumaNW + lumaNE + lumaSW + lumaSE) * (0.25f * FXAA_REDUCE_MUL), FXAA_REDUCE_MIN);
+	float rcpDirMin = 1.0f / (fmin_(fabsf(dx), fabsf(dy)) + dirReduce);
+	dx = fclamp(dx * rcpDirMin, -FXAA_SPAN_MAX, FXAA_SPAN_MAX) * inv_w;
+	dy = fclamp(dy * rcpDirMin, -FXAA_SPAN_MAX, FXAA_SPAN_MAX) * inv_h;
+	const float k0 = 1.0f / 3.0f - 0.5f, k1 = 2.0f / 3.0f - 0.5f;
+	float3 a0 = sample_unorm8(in, u + dx * k0, v + dy * k0);
+	float3 a1 = sample_unorm8(in, u + dx * k1, v + dy * k1);
+	float3 rgbA = make_float3(0.5f * (a0.x + a1.x), 0.5f * (a0.y + a1.y), 0.5f * (a0.z + a1.z));
+	float3 b0 = sample_unorm8(in, u + dx * -0.5f, v + dy * -0.5f);
+	float3 b1 = sample_unorm8(in, u + dx * 0.5f, v + dy * 0.5f);
+	float3 rgbB = make_float3(rgbA.x * 0.5f + 0.25f * (b0.x + b1.x), rgbA.y * 0.5f + 0.25f * (b0.y + b1.y), rgbA.z * 0.5f + 0.25f * (b0.z + b1.z));
+	float lumaB = luma_of(rgbB);
+	float3 c = ((lumaB < lumaMin) || (lumaB > lumaMax)) ? rgbA : rgbB;
+	uint32_t px;
+	if (SrgbTarget)
+		px = linear_to_srgb8(decode_srgb1(c.x)) | (linear_to_srgb8(decode_srgb1(c.y)) << 8) | (linear_to_srgb8(decode_srgb1(c.z)) << 16);
+	else
+		px = float_to_unorm8(c.x) | (float_to_unorm8(c.y) << 8) | (float_to_unorm8(c.z) << 16);
+	out.at(x, y) = px | 0xff000000u;
+}
+
+// ------------------------------------------------------------------------------- K13
+__device__ __forceinline__ float3 hdr_to_taa(float3 c)
+{
+	c = make_float3(c.x * 8.0f, c.y * 8.0f, c.z * 8.0f);
+	float r = 1.0f / (fmax_(c.x, fmax_(c.y, c.z)) + 1.0f);
+	c = make_float3(c.x * r, c.y * r, c.z * r);
+	return make_float3(0.25f * c.x + 0.5f * c.y + 0.25f * c.z, 0.5f * c.y - 0.25f * c.x - 0.25f * c.z, 0.5f * c.x - 0.5f * c.z);
+}
+
+__device__ __forceinline__ float3 taa_to_hdr(float3 c)
+{
+	float tmp = c.x - c.y;
+	float3 rgb = make_float3(fclamp(tmp + c.z, 0.0f, 0.999f), fclamp(c.x + c.y, 0.0f, 0.999f), fclamp(tmp - c.z, 0.0f, 0.999f));
+	float r = 1.0f / (1.0f - fmax_(rgb.x, fmax_(rgb.y, rgb.z)));
+	return make_float3((1.0f / 8.0f) * rgb.x * r, (1.0f / 8.0f) * rgb.y * r, (1.0f / 8.0f) * rgb.z * r);
+}
+
+__device__ __forceinline__ float3 min3(float3 a, float3 b) { return make_float3(fmin_(a.x, b.x), fmin_(a.y, b.y), fmin_(a.z, b.z)); }
+__device__ __forceinline__ float3 max3(float3 a, float3 b) { return make_float3(fmax_(a.x, b.x), fmax_(a.y, b.y), fmax_(a.z, b.z)); }
+
+template <bool Aabb>
+__device__ __forceinline__ float3 clamp_box(float3 color, float3 lo, float3 hi)
+{
+	if (!Aabb)
+		return make_float3(fclamp(color.x, lo.x, hi.x), fclamp(color.y, lo.y, hi.y), fclamp(color.z, lo.z, hi.z));
+	float3 center = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+	float3 radius = make_float3(fmax_(0.5f * (hi.x - lo.x), 0.0001f), fmax_(0.5f * (hi.y - lo.y), 0.0001f), fmax_(0.5f * (hi.z - lo.z), 0.0001f));
+	float3 v = make_float3(color.x - center.x, color.y - center.y, color.z - center.z);
+	float3 units = make_float3(v.x / radius.x, v.y / radius.y, v.z / radius.z);
+	float max_unit = fmax_(fmax_(fabsf(units.x), fabsf(units.y)), fabsf(units.z));
+	if (max_unit > 1.0f)
+		return make_float3(center.x + v.x / max_unit, center.y + v.y / max_unit, center.z + v.z / max_unit);
+	return color;
+}
+
+struct TaaInputs
+{
+	View<const uint32_t> hdr;
+	View<const float> depth;
+	View<const uint32_t> mv; // RG16F packed
+	View<const uint2> history;
+};
+
+__device__ __forceinline__ float3 sample_rgb16f(const View<const uint2> &im, float u, float v)
+{
+	float4 s = sample_rgba16f(im, u, v);
+	return make_float3(s.x, s.y, s.z);
+}
+
+__device__ __forceinline__ float3 sample_catmull_rom(const View<const uint2> &tex, float u, float v, float4 rt)
+{
+	float spx = u * rt.z, spy = v * rt.w;
+	float t1x = floorf(spx - 0.5f) + 0.5f, t1y = floorf(spy - 0.5f) + 0.5f;
+	float fx = spx - t1x, fy = spy - t1y;
+#define GRB_W0(f) ((f) * (-0.5f + (f) * (1.0f - 0.5f * (f))))
+#define GRB_W1(f) (1.0f + (f) * (f) * (-2.5f + 1.5f * (f)))
+#define GRB_W2(f) ((f) * (0.5f + (f) * (2.0f - 1.5f * (f))))
+#define GRB_W3(f) ((f) * (f) * (-0.5f + 0.5f * (f)))
+	float w0x = GRB_W0(fx), w1x = GRB_W1(fx), w2x = GRB_W2(fx), w3x = GRB_W3(fx);
+	float w0y = GRB_W0(fy), w1y = GRB_W1(fy), w2y = GRB_W2(fy), w3y = GRB_W3(fy);
+#undef GRB_W0
+#undef GRB_W1
+#undef GRB_W2
+#undef GRB_W3
+	float w12x = w1x + w2x, w12y = w1y + w2y;
+	float o12x = w2x / (w1x + w2x), o12y = w2y / (w1y + w2y);
+	float t0x = (t1x - 1.0f) * rt.x, t0y = (t1y - 1.0f) * rt.y;
+	float t3x = (t1x + 2.0f) * rt.x, t3y = (t1y + 2.0f) * rt.y;
+	float t12x = (t1x + o12x) * rt.x, t12y = (t1y + o12y) * rt.y;
+	float3 result = make_float3(0.0f, 0.0f, 0.0f);
+#define GRB_ACC(UU, VV, WA, WB)                      \
+	{                                                \
+		float3 s = sample_rgb16f(tex, (UU), (VV));   \
+		result.x += s.x * (WA) * (WB);               \
+		result.y += s.y * (WA) * (WB);               \
+		result.z += s.z * (WA) * (WB);               \
+	}
+	GRB_ACC(t0x, t0y, w0x, w0y)
+	GRB_ACC(t12x, t0y, w12x, w0y)
+	GRB_ACC(t3x, t0y, w3x, w0y)
+	GRB_ACC(t0x, t12y, w0x, w12y)
+	GRB_ACC(t12x, t12y, w12x, w12y)
+	GRB_ACC(t3x, t12y, w3x, w12y)
+	GRB_ACC(t0x, t3y, w0x, w3y)
+	GRB_ACC(t12x, t3y, w12x, w3y)
+	GRB_ACC(t3x, t3y, w3x, w3y)
+#undef GRB_ACC
+	return result;
+}
+
+struct Mat4
+{
+	float m[16];
+};
+
+template <int Quality, bool History>
+__global__ void __launch_bounds__(kBlockX *kBlockY) taa_kernel(TaaInputs in, Mat4 reproj, View<uint32_t> out_color, View<uint2> out_history, int y0,
+                                                              int y1, float4 rt)
+{
+	int x = blockIdx.x * kBlockX + threadIdx.x;
+	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x >= out_color.w || y >= y1)
+		return;
+	const int w = in.hdr.w, h = in.hdr.h;
+#define GRB_CUR(DX, DY) hdr_to_taa(fetch_hdr_clamped(in.hdr, x + (DX), y + (DY)))
+	float3 current = GRB_CUR(0, 0);
+	float3 out_c = current;
+	if (History)
+	{
+		float u = ((float)x + 0.5f) * rt.x, v = ((float)y + 0.5f) * rt.y;
+		// sample_nearest_velocity: the closest (largest reverse-Z) depth in the footprint picks the MV
+		float d;
+		uint32_t mvp;
+#define GRB_TRY(PX, PY)                                                 \
+	{                                                                   \
+		int qx = iclamp((PX), 0, w - 1), qy = iclamp((PY), 0, h - 1);   \
+		float dd = __ldg(&in.depth.at(qx, qy));                         \
+		if (dd > d)                                                     \
+		{                                                               \
+			d = dd;                                                     \
+			mvp = __ldg(&in.mv.at(qx, qy));                             \
+		}                                                               \
+	}
+		if (Quality == 2)
+		{
+			int qx = iclamp(x + 1, 0, w - 1), qy = iclamp(y + 1, 0, h - 1);
+			d = __ldg(&in.depth.at(qx, qy));
+			mvp = __ldg(&in.mv.at(qx, qy));
+			GRB_TRY(x - 1, y) GRB_TRY(x, y) GRB_TRY(x, y - 1) GRB_TRY(x - 1, y - 1)
+			GRB_TRY(x + 1, y) GRB_TRY(x + 1, y - 1)
+			GRB_TRY(x - 1, y + 1) GRB_TRY(x, y + 1)
+		}
+		else
+		{
+			int qx = iclamp(x - 1, 0, w - 1);
+			d = __ldg(&in.depth.at(qx, y));
+			mvp = __ldg(&in.mv.at(qx, y));
+			GRB_TRY(x, y) GRB_TRY(x, y - 1) GRB_TRY(x, y + 1) GRB_TRY(x + 1, y)
+		}
+#undef GRB_TRY
+		float mvx = h2f((uint16_t)(mvp & 0xffffu)), mvy = h2f((uint16_t)(mvp >> 16));
+		float old_u, old_v;
+		if (mvx == 0.0f && mvy == 0.0f)
+		{
+			float cx = 2.0f * u - 1.0f, cy = 2.0f * v - 1.0f;
+			const float *m = reproj.m;
+			float px = m[0] * cx + m[4] * cy + m[8] * d + m[12] * 1.0f;
+			float py = m[1] * cx + m[5] * cy + m[9] * d + m[13] * 1.0f;
+			float pw = m[3] * cx + m[7] * cy + m[11] * d + m[15] * 1.0f;
+			old_u = px / pw;
+			old_v = py / pw;
+			mvx = u - old_u;
+			mvy = v - old_v;
+		}
+		else
+		{
+			old_u = u - mvx;
+			old_v = v - mvy;
+		}
+		float3 hist = Quality == 2 ? sample_catmull_rom(in.history, old_u, old_v, rt) : sample_rgb16f(in.history, old_u, old_v);
+		float mv_len = sqrtf(mvx * mvx + mvy * mvy);
+		float mv_fast = fmin_(mv_len * 50.0f, 1.0f);
+		float gamma = fmix(1.5f, 0.5f, mv_fast);
+		hist = make_float3(fclamp(hist.x, 0.0f, 1.0f), fclamp(hist.y, -1.0f, 1.0f), fclamp(hist.z, -1.0f, 1.0f));
+		float lerp_factor = (1.0f + 2.0f * mv_fast) / 16.0f;
+
+		float3 c11 = current;
+		float3 c01 = GRB_CUR(-1, 0), c21 = GRB_CUR(+1, 0), c10 = GRB_CUR(0, -1), c12 = GRB_CUR(0, +1);
+		float3 lo = c11, hi = c11;
+		if (Quality == 0 || Quality == 1)
+		{
+			lo = min3(lo, c01); lo = min3(lo, c21); lo = min3(lo, c10); lo = min3(lo, c12);
+			hi = max3(hi, c01); hi = max3(hi, c21); hi = max3(hi, c10); hi = max3(hi, c12);
+		}
+		if (Quality >= 1)
+		{
+			float3 corner_lo = lo, corner_hi = hi;
+			float3 c00 = GRB_CUR(-1, -1), c22 = GRB_CUR(+1, +1), c02 = GRB_CUR(-1, +1), c20 = GRB_CUR(+1, -1);
+			if (Quality == 1)
+			{
+				lo = min3(lo, c00); lo = min3(lo, c22); lo = min3(lo, c02); lo = min3(lo, c20);
+				hi = max3(hi, c00); hi = max3(hi, c22); hi = max3(hi, c02); hi = max3(hi, c20);
+				lo = make_float3(0.5f * (corner_lo.x + lo.x), 0.5f * (corner_lo.y + lo.y), 0.5f * (corner_lo.z + lo.z));
+				hi = make_float3(0.5f * (corner_hi.x + hi.x), 0.5f * (corner_hi.y + hi.y), 0.5f * (corner_hi.z + hi.z));
+			}
+			else
+			{
+#define GRB_M1(C) ((c00.C + 2.0f * c01.C + c02.C + 2.0f * c10.C + 4.0f * c11.C + 2.0f * c12.C + c20.C + 2.0f * c21.C + c22.C) / 16.0f)
+#define GRB_M2(C)                                                                                                                            \
+	(c00.C * c00.C + 2.0f * c01.C * c01.C + c02.C * c02.C + 2.0f * c10.C * c10.C + 4.0f * c11.C * c11.C + 2.0f * c12.C * c12.C + c20.C * c20.C + \
+	 2.0f * c21.C * c21.C + c22.C * c22.C)
+				float3 m1 = make_float3(GRB_M1(x), GRB_M1(y), GRB_M1(z));
+				float3 m2 = make_float3(GRB_M2(x), GRB_M2(y), GRB_M2(z));
+#undef GRB_M1
+#undef GRB_M2
+				float3 sigma = make_float3(sqrtf(fmax_(m2.x / 16.0f - m1.x * m1.x, 0.0f)), sqrtf(fmax_(m2.y / 16.0f - m1.y * m1.y, 0.0f)),
+				                           sqrtf(fmax_(m2.z / 16.0f - m1.z * m1.z, 0.0f)));
+				lo = make_float3(m1.x - gamma * sigma.x, m1.y - gamma * sigma.y, m1.z - gamma * sigma.z);
+				hi = make_float3(m1.x + gamma * sigma.x, m1.y + gamma * sigma.y, m1.z + gamma * sigma.z);
+			}
+		}
+		hist = clamp_box<Quality != 0>(hist, lo, hi);
+		out_c = make_float3(fmix(hist.x, current.x, lerp_factor), fmix(hist.y, current.y, lerp_factor), fmix(hist.z, current.z, lerp_factor));
+	}
+#undef GRB_CUR
+	float3 color = taa_to_hdr(out_c);
+	out_color.at(x, y) = pack_r11g11b10(color.x, color.y, color.z);
+	out_history.at(x, y) = pack_rgba16f(make_float4(out_c.x, out_c.y, out_c.z, 1.0f));
+}
+} // namespace
+} // namespace grb
+
+using namespace grb;
+
+extern "C" int32_t grb_bloom_threshold(const GrbImage *hdr, const float *luminance, const GrbImage *out, GrbRows rows, void *stream)
+{
+	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !image_ok(out, GRB_FORMAT_R16G16B16A16_SFLOAT, 8))
+	{
+		set_last_error("grb_bloom_threshold: hdr must be B10G11R11_UFLOAT and out R16G16B16A16_SFLOAT");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
+	rows = full_rows(rows, out->height);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	auto o = view_of<uint2>(out);
+	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
+	float inv_w = 1.0f / (float)out->width, inv_h = 1.0f / (float)out->height; // hdr.cpp:140-141
+	if (luminance)
+		bloom_threshold_kernel<true><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint32_t>(hdr), luminance, o, rows.y0, rows.y1, inv_w, inv_h);
+	else
+		bloom_threshold_kernel<false><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint32_t>(hdr), nullptr, o, rows.y0, rows.y1, inv_w, inv_h);
+	return check_launch("grb_bloom_threshold");
+}
+
+extern "C" int32_t grb_bloom_downsample(const GrbImage *in, const GrbImage *history, float lerp, const GrbImage *out, GrbRows rows, void *stream)
+{
+	if (!image_ok(in, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || !image_ok(out, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) ||
+	    (history && (!image_ok(history, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || history->width != out->width || history->height != out->height)))
+	{
+		set_last_error("grb_bloom_downsample: images must be R16G16B16A16_SFLOAT and history must match out");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
+	if (history && history->data == out->data)
+	{
+		set_last_error("grb_bloom_downsample: history must not alias the output");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	rows = full_rows(rows, out->height);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
+	float inv_w = 1.0f / (float)out->width, inv_h = 1.0f / (float)out->height;   // hdr.cpp:178-179
+	float inv_in_w = 1.0f / (float)in->width, inv_in_h = 1.0f / (float)in->height; // hdr.cpp:180-181
+	if (history)
+		bloom_downsample_kernel<true><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint2>(in), view_of<const uint2>(history), lerp,
+		                                                                      view_of<uint2>(out), rows.y0, rows.y1, inv_w, inv_h, inv_in_w, inv_in_h);
+	else
+		bloom_downsample_kernel<false><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint2>(in), View<const uint2>{}, lerp, view_of<uint2>(out),
+		                                                                       rows.y0, rows.y1, inv_w, inv_h, inv_in_w, inv_in_h);
+	return check_launch("grb_bloom_downsample");
+}
+
+extern "C" int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream)
+{
+	if (!image_ok(in, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || !image_ok(out, GRB_FORMAT_R16G16B16A16_SFLOAT, 8))
+	{
+		set_last_error("grb_bloom_upsample: images must be R16G16B16A16_SFLOAT");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
+	rows = full_rows(rows, out->height);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
+	bloom_upsample_kernel<<<grid, block, 0, as_stream(stream)>>>(view_of<const uint2>(in), view_of<uint2>(out), rows.y0, rows.y1,
+	                                                              1.0f / (float)out->width, 1.0f / (float)out->height, 1.0f / (float)in->width,
+	                                                              1.0f / (float)in->height);
+	return check_launch("grb_bloom_upsample");
+}
+
+extern "C" int32_t grb_luminance(const GrbImage *d3, float *luminance, float lerp, float min_loglum, float max_loglum, void *stream)
+{
+	if (!image_ok(d3, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || !luminance || d3->width < 2 || d3->height < 2)
+	{
+		set_last_error("grb_luminance: d3 must be R16G16B16A16_SFLOAT (>= 2x2) and luminance non-null");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	luminance_kernel<<<1, 64, 0, as_stream(stream)>>>(view_of<const uint2>(d3), luminance, lerp, min_loglum, max_loglum);
+	return check_launch("grb_luminance");
+}
+
+extern "C" int32_t grb_luminance_grid(const GrbImage *d3, float *grid, GrbRows rows, void *stream)
+{
+	if (!image_ok(d3, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || !grid || d3->width < 2 || d3->height < 2)
+	{
+		set_last_error("grb_luminance_grid: d3 must be R16G16B16A16_SFLOAT (>= 2x2) and grid non-null");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	rows = full_rows(rows, d3->height / 2);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	dim3 grid_dim = grid_for(d3->width / 2, rows.y1 - rows.y0), block(kBlockX, kBlockY);
+	luminance_grid_kernel<<<grid_dim, block, 0, as_stream(stream)>>>(view_of<const uint2>(d3), grid, rows.y0, rows.y1);
+	return check_launch("grb_luminance_grid");
+}
+
+extern "C" int32_t grb_luminance_finalize(const float *grid, int32_t size_x, int32_t size_y, float *luminance, float lerp, float min_loglum,
+                                          float max_loglum, void *stream)
+{
+	if (!grid || !luminance || size_x <= 0 || size_y <= 0)
+	{
+		set_last_error("grb_luminance_finalize: null grid/luminance or empty size");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	luminance_finalize_kernel<<<1, 64, 0, as_stream(stream)>>>(grid, size_x, size_y, luminance, lerp, min_loglum, max_loglum);
+	return check_launch("grb_luminance_finalize");
+}
+
+extern "C" int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const float *luminance, float dynamic_exposure, const GrbImage *out,
+                               GrbRows rows, void *stream)
+{
+	bool srgb = out && out->format == GRB_FORMAT_R8G8B8A8_SRGB;
+	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !image_ok(bloom, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) ||
+	    !(image_ok(out, GRB_FORMAT_R8G8B8A8_SRGB, 4) || image_ok(out, GRB_FORMAT_R8G8B8A8_UNORM, 4)) || out->width != hdr->width ||
+	    out->height != hdr->height)
+	{
+		set_last_error("grb_tonemap: hdr B10G11R11_UFLOAT, bloom R16G16B16A16_SFLOAT, out R8G8B8A8_{SRGB,UNORM} of hdr's size");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
+	rows = full_rows(rows, out->height);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
+	float inv_w = 1.0f / (float)out->width, inv_h = 1.0f / (float)out->height;
+	auto h = view_of<const uint32_t>(hdr);
+	auto b = view_of<const uint2>(bloom);
+	auto o = view_of<uint32_t>(out);
+	cudaStream_t s = as_stream(stream);
+	if (luminance && srgb)
+		tonemap_kernel<true, true><<<grid, block, 0, s>>>(h, b, luminance, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+	else if (luminance)
+		tonemap_kernel<true, false><<<grid, block, 0, s>>>(h, b, luminance, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+	else if (srgb)
+		tonemap_kernel<false, true><<<grid, block, 0, s>>>(h, b, nullptr, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+	else
+		tonemap_kernel<false, false><<<grid, block, 0, s>>>(h, b, nullptr, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+	return check_launch("grb_tonemap");
+}
+
+extern "C" int32_t grb_fxaa(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream)
+{
+	auto is8 = [](const GrbImage *im) { return image_ok(im, GRB_FORMAT_R8G8B8A8_SRGB, 4) || image_ok(im, GRB_FORMAT_R8G8B8A8_UNORM, 4); };
+	if (!is8(in) || !is8(out) || in->width != out->width || in->height != out->height || in->data == out->data)
+	{
+		set_last_error("grb_fxaa: in/out must be distinct R8G8B8A8 images of equal size");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
+	rows = full_rows(rows, out->height);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
+	float inv_w = 1.0f / (float)in->width, inv_h = 1.0f / (float)in->height; // fxaa.cpp:45-46
+	if (out->format == GRB_FORMAT_R8G8B8A8_SRGB)
+		fxaa_kernel<true><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint32_t>(in), view_of<uint32_t>(out), rows.y0, rows.y1, inv_w, inv_h);
+	else
+		fxaa_kernel<false><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint32_t>(in), view_of<uint32_t>(out), rows.y0, rows.y1, inv_w, inv_h);
+	return check_launch("grb_fxaa");
+}
+
+extern "C" int32_t grb_taa_resolve(const GrbImage *hdr, const GrbImage *depth, const GrbImage *mv, const GrbImage *history, const float *reproj16,
+                                   int32_t quality, const GrbImage *out_color, const GrbImage *out_history, GrbRows rows, void *stream)
+{
+	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !image_ok(out_color, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) ||
+	    !image_ok(out_history, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || out_color->width != hdr->width || out_color->height != hdr->height ||
+	    out_history->width != hdr->width || out_history->height != hdr->height)
+	{
+		set_last_error("grb_taa_resolve: hdr/out_color B10G11R11_UFLOAT, out_history R16G16B16A16_SFLOAT, equal sizes");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
+	if (history && (!image_ok(history, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || !image_ok(depth, GRB_FORMAT_D32_SFLOAT, 4) ||
+	                !image_ok(mv, GRB_FORMAT_R16G16_SFLOAT, 4) || !reproj16 || history->width != hdr->width || history->height != hdr->height ||
+	                depth->width != hdr->width || depth->height != hdr->height || mv->width != hdr->width || mv->height != hdr->height ||
+	                history->data == out_history->data))
+	{
+		set_last_error("grb_taa_resolve: with history, depth (D32_SFLOAT), mv (R16G16_SFLOAT), reproj and a distinct history image are required");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	if (quality < 0 || quality > 2)
+	{
+		set_last_error("grb_taa_resolve: quality must be 0..2");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	rows = full_rows(rows, hdr->height);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	TaaInputs in{};
+	in.hdr = view_of<const uint32_t>(hdr);
+	Mat4 m{};
+	if (history)
+	{
+		in.depth = view_of<const float>(depth);
+		in.mv = view_of<const uint32_t>(mv);
+		in.history = view_of<const uint2>(history);
+		for (int i = 0; i < 16; i++)
+			m.m[i] = reproj16[i];
+	}
+	auto oc = view_of<uint32_t>(out_color);
+	auto oh = view_of<uint2>(out_history);
+	float4 rt = make_float4(1.0f / (float)hdr->width, 1.0f / (float)hdr->height, (float)hdr->width, (float)hdr->height); // temporal.cpp:245-248
+	dim3 grid = grid_for(hdr->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
+	cudaStream_t s = as_stream(stream);
+#define GRB_LAUNCH(Q, H) taa_kernel<Q, H><<<grid, block, 0, s>>>(in, m, oc, oh, rows.y0, rows.y1, rt)
+	if (!history)
+		GRB_LAUNCH(0, false);
+	else if (quality == 0)
+		GRB_LAUNCH(0, true);
+	else if (quality == 1)
+		GRB_LAUNCH(1, true);
+	else
+		GRB_LAUNCH(2, true);
+#undef GRB_LAUNCH
+	return check_launch("grb_taa_resolve");
+}

@@ -1,0 +1,223 @@
+/*
+ * granite_b200.h -- C ABI of the B200-native executor for Granite's clustered deferred
+ * lighting + HDR post chain (libgranite_b200.so).
+ *
+ * This is the drop-in boundary: every entry point replaces one shader dispatch / draw that
+ * the reference's pass builders record into a Vulkan::CommandBuffer.  The reference has no
+ * FFI for this path (the "binding" is set_program + push_constants + dispatch on GLSL), so
+ * each declaration cites the builder code (file:line, relative to the Granite tree at
+ * 7c59ad8089) whose push-constant block and bindings it mirrors.  INTEGRATION.md shows the
+ * build_render_pass lambdas a maintainer would write against these.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers owned by the caller (the render
+ *     graph owns every image/buffer, renderer/render_graph.hpp:988-992); nothing here
+ *     allocates, frees or synchronises the device;
+ *   - `stream` is a cudaStream_t passed as void*; the caller has made the right device
+ *     current (the reference records on whatever queue the graph picked);
+ *   - every function returns 0 (GRB_OK) or a negative GrbResult; the CUDA error text of the
+ *     last failure on the calling thread is available from grb_last_error_string();
+ *   - re-entrant and thread-safe for distinct streams (callbacks run on arbitrary worker
+ *     threads, renderer/render_graph.cpp:2384-2397);
+ *   - matrices are column-major float[16] exactly as muglm::mat4 lays them out;
+ *   - images are row-major, `row_pitch` in BYTES (multiple of the texel size);
+ *   - `rows` selects the OUTPUT rows [y0, y1) a call produces -- the screen-row shard of a
+ *     multi-GPU frame; {0, 0} means the whole image.
+ */
+#ifndef GRANITE_B200_H_
+#define GRANITE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRB_ABI_VERSION 1
+
+typedef enum GrbResult
+{
+	GRB_OK = 0,
+	GRB_ERR_INVALID_ARGUMENT = -1,
+	GRB_ERR_UNSUPPORTED_FORMAT = -2,
+	GRB_ERR_CUDA = -3,
+	GRB_ERR_NOT_INITIALIZED = -4
+} GrbResult;
+
+/* VkFormat values the path uses, kept numerically identical to Vulkan's so the graph layer
+ * can pass AttachmentInfo::format straight through (renderer/render_graph.hpp:154-167). */
+typedef enum GrbFormat
+{
+	GRB_FORMAT_UNDEFINED = 0,
+	GRB_FORMAT_R8G8_UNORM = 16,
+	GRB_FORMAT_R8G8B8A8_UNORM = 37,
+	GRB_FORMAT_R8G8B8A8_SRGB = 43,
+	GRB_FORMAT_A2B10G10R10_UNORM_PACK32 = 64,
+	GRB_FORMAT_R16G16_SFLOAT = 83,
+	GRB_FORMAT_R16G16B16A16_SFLOAT = 97,
+	GRB_FORMAT_B10G11R11_UFLOAT_PACK32 = 122,
+	GRB_FORMAT_D32_SFLOAT = 126
+} GrbFormat;
+
+typedef struct GrbImage
+{
+	void *data;
+	int32_t width;
+	int32_t height;
+	int32_t row_pitch; /* bytes */
+	int32_t format;    /* GrbFormat */
+} GrbImage;
+
+typedef struct GrbRows
+{
+	int32_t y0, y1;
+} GrbRows;
+
+/* renderer/lights/light_info.hpp:35-44 PositionalFragmentInfo == GLSL PositionalLightInfo
+ * (assets/shaders/lights/clusterer_data.h:10-18). 48 bytes. */
+typedef struct GrbPositionalLight
+{
+	float color[3];
+	uint16_t spot_scale_bias[2]; /* fp16 x2 */
+	float position[3];
+	uint16_t offset_radius[2];   /* fp16 x2 */
+	float direction[3];
+	float inv_radius;
+} GrbPositionalLight;
+
+/* math/render_parameters.hpp:90-108 ClustererParametersBindless (fields the path reads). */
+typedef struct GrbClusterParameters
+{
+	float transform[16];
+	float clip_scale[4];
+	float camera_base[3];
+	float camera_front[3];
+	float xy_scale[2];
+	int32_t resolution_xy[2];
+	float inv_resolution_xy[2];
+	int32_t num_lights;
+	int32_t num_lights_32;
+	int32_t z_max_index;
+	float z_scale;
+} GrbClusterParameters;
+
+/* Camera block: the RenderParameters fields (math/render_parameters.hpp:37-59) that
+ * clusterer.cpp:1469-1509 and renderer.cpp:1073-1121 push to the shaders. */
+typedef struct GrbCamera
+{
+	float view[16];
+	float view_projection[16];
+	float inv_view_projection[16];
+	float camera_position[3];
+	float camera_front[3];
+	float z_near;
+	float z_far;
+} GrbCamera;
+
+/* The light-cluster structure ("cluster-bitmask", "cluster-range", "cluster-transforms",
+ * "cluster-cull-setup", "cluster-transformed-spot": renderer/lights/clusterer.cpp:1575-1613).
+ * `lights`, `model`, `type_mask` are the three members of ClustererBindlessTransforms the
+ * path reads (math/render_parameters.hpp:155-162), passed as separate device arrays. */
+typedef struct GrbClusterBuffers
+{
+	const GrbPositionalLight *lights; /* num_lights */
+	const float *model;               /* num_lights x 12: mat_affine rows */
+	const uint32_t *type_mask;        /* num_lights_32 words, bit = 1 => point light */
+	const uint32_t *z_ranges;         /* max(num_lights,1) x uvec2, host-computed (clusterer.cpp:1322-1346) */
+	float *transformed_spots;         /* num_lights x 6 vec4 */
+	float *cull_setup;                /* num_lights x 32 vec4 */
+	uint32_t *bitmask;                /* res_x * res_y * num_lights_32 */
+	uint32_t *cluster_range;          /* res_z x uvec2 */
+	int32_t resolution_z;
+} GrbClusterBuffers;
+
+/* ---- library ---- */
+int32_t grb_abi_version(void);
+/* Uploads the constant tables (sRGB decode LUT) to the CURRENT device. Call once per device
+ * before any other entry point; idempotent and thread-safe. */
+int32_t grb_init(void);
+const char *grb_last_error_string(void);
+
+/* ---- clusterer: replaces LightClusterer::build_cluster_bindless_gpu
+ * (renderer/lights/clusterer.cpp:1463-1573) ---- */
+/* K1 clusterer_bindless_spot_transform.comp; push block clusterer.cpp:1477-1493. */
+int32_t grb_cluster_spot_transform(const GrbCamera *cam, const GrbClusterParameters *params,
+                                   const GrbClusterBuffers *buf, void *stream);
+/* K2 clusterer_bindless_setup.comp; push block clusterer.cpp:1502-1509. */
+int32_t grb_cluster_cull_setup(const GrbCamera *cam, const GrbClusterParameters *params,
+                               const GrbClusterBuffers *buf, void *stream);
+/* K3 clusterer_bindless_binning.comp (SUBGROUPS=1, 32-wide: clusterer.cpp:1519-1561). */
+int32_t grb_cluster_binning(const GrbClusterParameters *params, const GrbClusterBuffers *buf, void *stream);
+/* K4 clusterer_bindless_z_range[_opt].comp; push block clusterer.cpp:1291-1300. */
+int32_t grb_cluster_z_range(const GrbClusterBuffers *buf, int32_t num_ranges, void *stream);
+/* All four in the order build_cluster_bindless_gpu records them. */
+int32_t grb_cluster_build(const GrbCamera *cam, const GrbClusterParameters *params,
+                          const GrbClusterBuffers *buf, void *stream);
+
+/* ---- deferred lighting: replaces DeferredLightRenderer::render_light
+ * (renderer/renderer.cpp:1004-1156): directional.frag + clustering.frag, both additively
+ * blended into HDR-main, sky (depth == 0) skipped. ---- */
+typedef struct GrbGBuffer
+{
+	GrbImage albedo;   /* R8G8B8A8_SRGB       (scene_viewer_application.cpp:880-900) */
+	GrbImage normal;   /* A2B10G10R10_UNORM */
+	GrbImage pbr;      /* R8G8_UNORM */
+	GrbImage depth;    /* D32_SFLOAT, reverse-Z, 0 = far */
+	float directional_color[3];     /* DirectionalLightPush, renderer.cpp:1073-1103 */
+	float directional_direction[3];
+} GrbGBuffer;
+
+/* hdr: B10G11R11_UFLOAT, read-modify-write ("HDR-main" aliases "emissive",
+ * scene_viewer_application.cpp:956-963). */
+int32_t grb_deferred_lighting(const GrbGBuffer *gbuffer, const GrbCamera *cam,
+                              const GrbClusterParameters *params, const GrbClusterBuffers *buf,
+                              const GrbImage *hdr, GrbRows rows, void *stream);
+
+/* Diagnostic: the (tile index, Z slice) the lighting kernel addresses for every pixel, -1 for sky
+ * (clusterer_bindless.h:39-47).  Same device function as grb_deferred_lighting uses; exists so
+ * the "bit-exact cluster indices" contract can be checked directly. */
+int32_t grb_debug_cluster_indices(const GrbImage *depth, const GrbCamera *cam, const GrbClusterParameters *params,
+                                  int32_t *out_tile, int32_t *out_z, GrbRows rows, void *stream);
+
+/* ---- HDR post chain: replaces the "bloom-compute" and "tonemap" passes
+ * (renderer/post/hdr.cpp:308-400) ---- */
+/* K7 bloom_threshold.comp; hdr.cpp:115-144. luminance: device float[3] {avg_log, avg_lin,
+ * avg_inv_lin} or NULL for DYNAMIC_EXPOSURE=0. */
+int32_t grb_bloom_threshold(const GrbImage *hdr, const float *luminance, const GrbImage *out,
+                            GrbRows rows, void *stream);
+/* K8 bloom_downsample.comp; hdr.cpp:146-187. history (NULL => FEEDBACK=0) is last frame's
+ * image of the same size; lerp = 1 - 0.001^frame_time. */
+int32_t grb_bloom_downsample(const GrbImage *in, const GrbImage *history, float lerp,
+                             const GrbImage *out, GrbRows rows, void *stream);
+/* K9 bloom_upsample.comp; hdr.cpp:189-216. */
+int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream);
+/* K10 luminance.comp; hdr.cpp:68-98 (size = d3 / 2, lerp = 1 - 0.5^frame_time, clamp [-3,2]).
+ * Single-device form: reads d3, updates luminance[3] in place. */
+int32_t grb_luminance(const GrbImage *d3, float *luminance, float lerp, float min_loglum,
+                      float max_loglum, void *stream);
+/* Sharded form of K10 for row-sharded frames: step 1 samples the (w/2 x h/2) grid rows
+ * [rows.y0, rows.y1) into `grid` (float, size_x*size_y, other rows untouched -- zero them
+ * once so an all-reduce(sum) across ranks assembles the grid exactly); step 2 reduces a
+ * complete grid in the shader's association order and updates luminance[3]. */
+int32_t grb_luminance_grid(const GrbImage *d3, float *grid, GrbRows rows, void *stream);
+int32_t grb_luminance_finalize(const float *grid, int32_t size_x, int32_t size_y, float *luminance,
+                               float lerp, float min_loglum, float max_loglum, void *stream);
+/* K11 tonemap.frag; hdr.cpp:283-306. out: R8G8B8A8_SRGB (or _UNORM: stores linear). */
+int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const float *luminance,
+                    float dynamic_exposure, const GrbImage *out, GrbRows rows, void *stream);
+
+/* ---- post AA ---- */
+/* K12 fxaa.frag; renderer/post/fxaa.cpp:41-55. in: 8-bit image viewed as UNORM; if out's
+ * format is *_SRGB the shader's FXAA_TARGET_SRGB path applies. */
+int32_t grb_fxaa(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream);
+/* K13 taa_resolve.frag; renderer/post/temporal.cpp:226-265. history NULL on the first
+ * frame (REPROJECTION_HISTORY=0). quality 0..2 = TAAQuality. mv: R16G16_SFLOAT.
+ * out_color: B10G11R11_UFLOAT; out_history: R16G16B16A16_SFLOAT. */
+int32_t grb_taa_resolve(const GrbImage *hdr, const GrbImage *depth, const GrbImage *mv,
+                        const GrbImage *history, const float *reproj16, int32_t quality,
+                        const GrbImage *out_color, const GrbImage *out_history, GrbRows rows, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

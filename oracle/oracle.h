@@ -1,0 +1,151 @@
+/*
+ * oracle.h -- TEST INFRASTRUCTURE ONLY (see oracle_math.h header for the rules).
+ *
+ * Public entry points of the CPU oracle (liboracle.so, plain C ABI so the
+ * Python tests can call it through ctypes on numpy buffers).  Every function
+ * cites the reference file:line it restates (paths relative to the Granite
+ * tree, commit 7c59ad8089).  "parity unpinned": see oracle_math.h.
+ */
+#ifndef ORACLE_H_
+#define ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* renderer/lights/light_info.hpp:35-44 == assets/shaders/lights/clusterer_data.h:10-18 */
+typedef struct
+{
+	float color[3];
+	uint16_t spot_scale_bias[2];
+	float position[3];
+	uint16_t offset_radius[2];
+	float direction[3];
+	float inv_radius;
+} orc_light_t;
+
+/* Subset of math/render_parameters.hpp:90-108 that the light path reads. */
+typedef struct
+{
+	float transform[16];
+	float clip_scale[4];
+	float camera_base[3];
+	float camera_front[3];
+	float xy_scale[2];
+	int32_t resolution_xy[2];
+	float inv_resolution_xy[2];
+	int32_t num_lights;
+	int32_t num_lights_32;
+	int32_t z_max_index;
+	float z_scale;
+} orc_cluster_params_t;
+
+/* Subset of math/render_parameters.hpp:37-59 (RenderParameters). Column-major mat4. */
+typedef struct
+{
+	float projection[16];
+	float view[16];
+	float view_projection[16];
+	float inv_projection[16];
+	float inv_view[16];
+	float inv_view_projection[16];
+	float camera_position[3];
+	float camera_front[3];
+	float z_near;
+	float z_far;
+} orc_camera_t;
+
+/* ---- host math (checked against oracle/_ref = the reference's math/muglm) ---- */
+void orc_perspective(float fovy, float aspect, float z_near, float z_far, float *out16);  /* math/muglm/muglm.cpp:319-345 */
+void orc_mat4_mul(const float *a, const float *b, float *out16);
+void orc_mat4_inverse(const float *m, float *out16);                                      /* math/muglm/muglm.cpp inverse(mat4) */
+uint16_t orc_float_to_half(float v);                                                      /* math/muglm/muglm_impl.hpp:860-907 */
+void orc_camera_setup(const float *projection, const float *view, orc_camera_t *out);     /* renderer/render_context.cpp:54-87 */
+
+/* ---- host light prep ---- */
+/* renderer/lights/lights.cpp:63-70,203-220 (PointLight, unit node scale). */
+void orc_point_light_info(const float *color, const float *position, float cutoff_range, orc_light_t *out);
+/* renderer/lights/lights.cpp:77-146 (SpotLight): also returns the model matrix rows (3 x vec4). */
+void orc_spot_light_info(const float *color, const float *position, const float *rot_cols9,
+                         float inner_cone, float outer_cone, float cutoff_range,
+                         orc_light_t *out, float *model_rows12);
+/* renderer/lights/clusterer.cpp:803-826. resolution (128,64,4096) for the viewer. */
+void orc_cluster_params(const orc_camera_t *cam, int num_lights, int res_x, int res_y, int res_z,
+                        orc_cluster_params_t *out);
+/* renderer/lights/clusterer.cpp:1265-1275,1322-1346 + lights.cpp:330-370.
+ * z_ranges: max(num_lights,1) uvec2 entries. */
+void orc_light_z_ranges(const orc_camera_t *cam, const orc_light_t *lights, const float *model_rows,
+                        const uint32_t *type_mask, int num_lights, int res_z, uint32_t *z_ranges);
+
+/* ---- clusterer kernels ---- */
+/* K1 clusterer_bindless_spot_transform.comp:33-73. out: 6 vec4 per light. */
+void orc_spot_transform(const orc_camera_t *cam, const float *model_rows, int num_lights, float *transformed_spots);
+/* K2 clusterer_bindless_setup.comp:252-322. out: 32 vec4 per light (zero-initialised by the graph). */
+void orc_cull_setup(const orc_camera_t *cam, const orc_cluster_params_t *p, const orc_light_t *lights,
+                    const uint32_t *type_mask, const float *transformed_spots, float *cull_setup);
+/* K3 clusterer_bindless_binning.comp:125-179 (SUBGROUPS=1, subgroup size 32 => 8x4 coarse tile).
+ * bitmask: res_x*res_y*num_lights_32 words.  Bits >= num_lights are defined 0. */
+void orc_binning(const orc_cluster_params_t *p, const uint32_t *type_mask, const float *cull_setup, uint32_t *bitmask);
+/* K4 clusterer_bindless_z_range.comp:20-51. out: res_z uvec2. */
+void orc_z_range(const uint32_t *z_ranges, int num_ranges, int res_z, uint32_t *cluster_range);
+
+/* ---- deferred lighting (K6 directional + K5 clustered, two additive blends) ---- */
+typedef struct
+{
+	int width, height;
+	const uint32_t *albedo;   /* R8G8B8A8_SRGB */
+	const uint32_t *normal;   /* A2B10G10R10_UNORM */
+	const uint16_t *pbr;      /* R8G8_UNORM */
+	const float *depth;       /* D32_SFLOAT, reverse-Z, 0 = sky */
+	const uint32_t *emissive; /* B10G11R11_UFLOAT (HDR-main aliases emissive) */
+	float dir_color[3];
+	float dir_direction[3];
+} orc_gbuffer_t;
+
+/* renderer/renderer.cpp:1004-1156; directional.frag:40-65; clustering.frag:29-44;
+ * clusterer_bindless.h:29-84; point.h; spot.h; pbr.h; lighting.h.
+ * out_tile_index / out_z_index (optional, may be NULL): per-pixel cluster indices (bit-exact contract).
+ * out_light_count (optional): lights evaluated per pixel. */
+void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
+                           const orc_light_t *lights, const uint32_t *type_mask,
+                           const uint32_t *bitmask, const uint32_t *cluster_range,
+                           uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
+                           int32_t *out_light_count, int y0, int y1);
+
+/* ---- HDR chain ---- */
+/* K7 bloom_threshold.comp:23-45.  lum3: {avg_log, avg_lin, avg_inv_lin} or NULL (DYNAMIC_EXPOSURE=0). */
+void orc_bloom_threshold(const uint32_t *hdr, int w_in, int h_in, const float *lum3,
+                         uint16_t *out, int w, int h);
+/* K8 bloom_downsample.comp:21-42.  history may be NULL (FEEDBACK=0). */
+void orc_bloom_downsample(const uint16_t *in, int w_in, int h_in, const uint16_t *history, float lerp,
+                          uint16_t *out, int w, int h);
+/* K9 bloom_upsample.comp:15-33 */
+void orc_bloom_upsample(const uint16_t *in, int w_in, int h_in, uint16_t *out, int w, int h);
+/* K10 luminance.comp:23-68 + hdr.cpp:68-98.  lum3 in/out.  grid (optional): size_x*size_y sampled values. */
+void orc_luminance(const uint16_t *d3, int w, int h, float lerp, float min_loglum, float max_loglum,
+                   float *lum3, float *grid);
+/* K11 tonemap.frag:55-66 + hdr.cpp:283-306.  lum3 NULL => DYNAMIC_EXPOSURE=0. out RGBA8 sRGB-encoded. */
+void orc_tonemap(const uint32_t *hdr, int w, int h, const uint16_t *bloom, int bw, int bh,
+                 const float *lum3, float exposure, uint32_t *out, int y0, int y1);
+/* K12 fxaa.frag:20-67 + fxaa.cpp:28-56. in: RGBA8 read as UNORM. target_srgb => decode_srgb before store. */
+void orc_fxaa(const uint32_t *in, int w, int h, int target_srgb, uint32_t *out, int y0, int y1);
+/* K13 taa_resolve.frag:43-83 + reprojection.h.  history may be NULL (REPROJECTION_HISTORY=0).
+ * mv: RG16F. out_color: B10G11R11. out_history: RGBA16F (alpha written as 1.0... see .c). */
+void orc_taa_resolve(const uint32_t *hdr, const float *depth, const uint16_t *mv, const uint16_t *history,
+                     int w, int h, const float *reproj16, int quality,
+                     uint32_t *out_color, uint16_t *out_history, int y0, int y1);
+
+/* ---- format helpers exported for tests ---- */
+uint32_t orc_pack_r11g11b10(float r, float g, float b);
+void orc_unpack_r11g11b10(uint32_t p, float *rgb);
+uint16_t orc_f32_to_f16(float f);
+float orc_f16_to_f32(uint16_t h);
+uint32_t orc_linear_to_srgb8(float c);
+float orc_srgb8_to_linear(uint32_t v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

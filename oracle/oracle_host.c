@@ -1,0 +1,370 @@
+/*
+ * oracle_host.c -- TEST INFRASTRUCTURE ONLY.  Host-side math and light preparation of the
+ * reference, restated in plain C.  See oracle_math.h for the arithmetic contract.
+ */
+#include "oracle.h"
+#include "oracle_math.h"
+
+#include <float.h>
+
+/* math/muglm/muglm.cpp:319-345 perspective(): reverse-Z, Y-flipped, infinite far when
+ * far == InfiniteFarPlane (= FLT_MAX, math/muglm/matrix_helper.hpp:44). */
+void orc_perspective(float fovy, float aspect, float z_near, float z_far, float *m)
+{
+	float tan_half = tanf(fovy / 2.0f);
+	for (int i = 0; i < 16; i++)
+		m[i] = 0.0f;
+	m[0] = 1.0f / (aspect * tan_half);
+	m[5] = 1.0f / (tan_half);
+	if (z_far == FLT_MAX)
+		m[14] = z_near; /* result[3][2] */
+	else
+	{
+		m[10] = -1.0f - z_far / (z_near - z_far);
+		m[14] = -(z_far * z_near) / (z_near - z_far);
+	}
+	m[11] = -1.0f; /* result[2][3] */
+	m[1] *= -1.0f;
+	m[5] *= -1.0f;
+	m[9] *= -1.0f;
+	m[13] *= -1.0f;
+}
+
+/* math/muglm/muglm_impl.hpp:609-627: a*b = (a*b[0], a*b[1], a*b[2], a*b[3]),
+ * a*v = ((a0*v.x + a1*v.y) + a2*v.z) + a3*v.w */
+void orc_mat4_mul(const float *a, const float *b, float *out)
+{
+	float r[16];
+	for (int c = 0; c < 4; c++)
+	{
+		vec4 v = m4_mul_v4(a, v4(b[c * 4 + 0], b[c * 4 + 1], b[c * 4 + 2], b[c * 4 + 3]));
+		r[c * 4 + 0] = v.x; r[c * 4 + 1] = v.y; r[c * 4 + 2] = v.z; r[c * 4 + 3] = v.w;
+	}
+	memcpy(out, r, sizeof(r));
+}
+
+/* math/muglm/muglm.cpp:146-200 inverse(mat4): cofactor expansion, same association order. */
+#define M(c, r) m[(c) * 4 + (r)]
+void orc_mat4_inverse(const float *m, float *out)
+{
+	float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3);
+	float c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3);
+	float c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+	float c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3);
+	float c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3);
+	float c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+	float c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2);
+	float c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2);
+	float c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+	float c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3);
+	float c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3);
+	float c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+	float c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2);
+	float c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2);
+	float c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+	float c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1);
+	float c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1);
+	float c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+
+	float fac0[4] = { c00, c00, c02, c03 };
+	float fac1[4] = { c04, c04, c06, c07 };
+	float fac2[4] = { c08, c08, c10, c11 };
+	float fac3[4] = { c12, c12, c14, c15 };
+	float fac4[4] = { c16, c16, c18, c19 };
+	float fac5[4] = { c20, c20, c22, c23 };
+	float vec0[4] = { M(1, 0), M(0, 0), M(0, 0), M(0, 0) };
+	float vec1[4] = { M(1, 1), M(0, 1), M(0, 1), M(0, 1) };
+	float vec2_[4] = { M(1, 2), M(0, 2), M(0, 2), M(0, 2) };
+	float vec3_[4] = { M(1, 3), M(0, 3), M(0, 3), M(0, 3) };
+	static const float sign_a[4] = { +1, -1, +1, -1 };
+	static const float sign_b[4] = { -1, +1, -1, +1 };
+	float inv[16];
+	for (int i = 0; i < 4; i++)
+	{
+		float i0 = vec1[i] * fac0[i] - vec2_[i] * fac1[i] + vec3_[i] * fac2[i];
+		float i1 = vec0[i] * fac0[i] - vec2_[i] * fac3[i] + vec3_[i] * fac4[i];
+		float i2 = vec0[i] * fac1[i] - vec1[i] * fac3[i] + vec3_[i] * fac5[i];
+		float i3 = vec0[i] * fac2[i] - vec1[i] * fac4[i] + vec2_[i] * fac5[i];
+		inv[0 * 4 + i] = i0 * sign_a[i];
+		inv[1 * 4 + i] = i1 * sign_b[i];
+		inv[2 * 4 + i] = i2 * sign_a[i];
+		inv[3 * 4 + i] = i3 * sign_b[i];
+	}
+	float d0x = M(0, 0) * inv[0 * 4 + 0];
+	float d0y = M(0, 1) * inv[1 * 4 + 0];
+	float d0z = M(0, 2) * inv[2 * 4 + 0];
+	float d0w = M(0, 3) * inv[3 * 4 + 0];
+	float dot1 = (d0x + d0y) + (d0z + d0w);
+	float ood = 1.0f / dot1;
+	for (int i = 0; i < 16; i++)
+		out[i] = inv[i] * ood;
+}
+#undef M
+
+/* math/muglm/muglm_impl.hpp:860-907 floatToHalf(float): rounds half UP on magnitude (not RNE). */
+uint16_t orc_float_to_half(float v)
+{
+	int i = (int)f_bits(v);
+	int s = (i >> 16) & 0x00008000;
+	int e = ((i >> 23) & 0x000000ff) - (127 - 15);
+	int m = i & 0x007fffff;
+
+	if (e <= 0)
+	{
+		if (e < -10)
+			return (uint16_t)s;
+		m = (m | 0x00800000) >> (1 - e);
+		if (m & 0x00001000)
+			m += 0x00002000;
+		return (uint16_t)(s | (m >> 13));
+	}
+	else if (e == 0xff - (127 - 15))
+	{
+		if (m == 0)
+			return (uint16_t)(s | 0x7c00);
+		m >>= 13;
+		return (uint16_t)(s | 0x7c00 | m | (m == 0));
+	}
+	else
+	{
+		if (m & 0x00001000)
+		{
+			m += 0x00002000;
+			if (m & 0x00800000)
+			{
+				m = 0;
+				e += 1;
+			}
+		}
+		if (e > 30)
+			return (uint16_t)(s | 0x7c00);
+		return (uint16_t)(s | (e << 10) | (m >> 13));
+	}
+}
+
+/* renderer/render_context.cpp:54-87 RenderContext::set_camera */
+void orc_camera_setup(const float *projection, const float *view, orc_camera_t *c)
+{
+	memcpy(c->projection, projection, 64);
+	memcpy(c->view, view, 64);
+	orc_mat4_mul(projection, view, c->view_projection);
+	orc_mat4_inverse(projection, c->inv_projection);
+	orc_mat4_inverse(view, c->inv_view);
+	orc_mat4_inverse(c->view_projection, c->inv_view_projection);
+	for (int i = 0; i < 3; i++)
+	{
+		c->camera_position[i] = c->inv_view[12 + i];
+		c->camera_front[i] = -c->inv_view[8 + i];
+	}
+	/* mat2 inv_zw(inv_projection[2].zw, inv_projection[3].zw); project(zw) = -zw.x / zw.y */
+	const float *ip = c->inv_projection;
+	float a = ip[2 * 4 + 2], b = ip[2 * 4 + 3]; /* column 0 of inv_zw */
+	float cc = ip[3 * 4 + 2], d = ip[3 * 4 + 3]; /* column 1 */
+	int infinite_z = c->inv_view_projection[15] == 0.0f;
+	{
+		float zx = a * 1.0f + cc * 1.0f, zy = b * 1.0f + d * 1.0f;
+		c->z_near = -zx / zy;
+	}
+	{
+		float f = infinite_z ? 1e-10f : 0.0f;
+		float zx = a * f + cc * 1.0f, zy = b * f + d * 1.0f;
+		c->z_far = -zx / zy;
+	}
+}
+
+/* renderer/lights/lights.cpp:63-70 recompute_range + :203-220 PointLight::get_shader_info
+ * with a unit-scale node transform (scale_factor == 1). */
+void orc_point_light_info(const float *color, const float *position, float cutoff_range, orc_light_t *out)
+{
+	const float target_atten = 0.1f;
+	float max_color = f_max(f_max(color[0], color[1]), color[2]);
+	float falloff_range = sqrtf(max_color / target_atten);
+	float max_range = f_min(falloff_range, cutoff_range) * 1.0f;
+	memset(out, 0, sizeof(*out));
+	for (int i = 0; i < 3; i++)
+	{
+		out->color[i] = color[i] * (1.0f * 1.0f);
+		out->position[i] = position[i];
+	}
+	out->spot_scale_bias[0] = 0;
+	out->spot_scale_bias[1] = 0;
+	out->offset_radius[0] = orc_float_to_half(0.0f);
+	out->offset_radius[1] = orc_float_to_half(max_range);
+	/* transform.get_forward() of an identity-rotation node: (0,0,-1). "This shouldn't matter". */
+	out->direction[0] = 0.0f; out->direction[1] = 0.0f; out->direction[2] = -1.0f;
+	out->inv_radius = 1.0f / max_range;
+}
+
+/* renderer/lights/lights.cpp:71-146: set_spot_parameters, set_range, build_model_matrix,
+ * SpotLight::get_shader_info.  rot_cols9 = orthonormal node rotation, column-major 3x3. */
+void orc_spot_light_info(const float *color, const float *position, const float *rot,
+                         float inner_cone_, float outer_cone_, float cutoff_range,
+                         orc_light_t *out, float *model_rows)
+{
+	float inner_cone = f_clamp(inner_cone_, 0.001f, 1.0f);
+	float outer_cone = f_clamp(outer_cone_, 0.001f, 1.0f);
+	const float target_atten = 0.1f;
+	float max_color = f_max(f_max(color[0], color[1]), color[2]);
+	float falloff_range = sqrtf(max_color / target_atten);
+	float max_range0 = f_min(falloff_range, cutoff_range);
+	float xy_range = sqrtf(1.0f - outer_cone * outer_cone) / outer_cone;
+
+	/* build_model_matrix: transform * scale_affine(xy_range*R, xy_range*R, R) */
+	float sx = xy_range * max_range0, sy = xy_range * max_range0, sz = max_range0;
+	for (int r = 0; r < 3; r++)
+	{
+		model_rows[r * 4 + 0] = rot[0 * 3 + r] * sx;
+		model_rows[r * 4 + 1] = rot[1 * 3 + r] * sy;
+		model_rows[r * 4 + 2] = rot[2 * 3 + r] * sz;
+		model_rows[r * 4 + 3] = position[r];
+	}
+
+	float scale_factor = 1.0f;
+	float max_range = max_range0 * scale_factor;
+	float spot_scale = 1.0f / f_max(0.001f, inner_cone - outer_cone);
+	float spot_bias = -outer_cone * spot_scale;
+	float tan2 = (1.0f - outer_cone * outer_cone) / (outer_cone * outer_cone);
+	float center_distance = ((tan2 + 1.0f) * max_range) * 0.5f;
+	float spot_offset, spot_radius;
+	if (center_distance < max_range)
+	{
+		spot_offset = center_distance;
+		spot_radius = center_distance;
+	}
+	else
+	{
+		spot_offset = max_range;
+		spot_radius = sqrtf(tan2) * max_range;
+	}
+	memset(out, 0, sizeof(*out));
+	for (int i = 0; i < 3; i++)
+	{
+		out->color[i] = color[i] * (scale_factor * scale_factor);
+		out->position[i] = position[i];
+	}
+	out->spot_scale_bias[0] = orc_float_to_half(spot_scale);
+	out->spot_scale_bias[1] = orc_float_to_half(spot_bias);
+	out->offset_radius[0] = orc_float_to_half(spot_offset);
+	out->offset_radius[1] = orc_float_to_half(spot_radius);
+	/* normalize(transform.get_forward()), forward = -column 2 */
+	vec3 fwd = v3_normalize(v3(-rot[6], -rot[7], -rot[8]));
+	out->direction[0] = fwd.x; out->direction[1] = fwd.y; out->direction[2] = fwd.z;
+	out->inv_radius = 1.0f / max_range;
+}
+
+/* renderer/lights/clusterer.cpp:700-703 get_z_slice_extent */
+static float z_slice_extent(const orc_camera_t *cam, int res_z)
+{
+	return f_min(0.5f, cam->z_far / (float)res_z);
+}
+
+/* renderer/lights/clusterer.cpp:803-826 */
+void orc_cluster_params(const orc_camera_t *cam, int num_lights, int res_x, int res_y, int res_z,
+                        orc_cluster_params_t *p)
+{
+	memset(p, 0, sizeof(*p));
+	p->num_lights = num_lights;
+	p->num_lights_32 = (num_lights + 31) / 32;
+	p->clip_scale[0] = cam->projection[0];
+	p->clip_scale[1] = -cam->projection[5];
+	p->clip_scale[2] = cam->inv_projection[0];
+	p->clip_scale[3] = -cam->inv_projection[5];
+	/* translate(.5,.5,0) * scale(.5,.5,1) * view_projection */
+	float t[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0.5f, 0.5f, 0.0f, 1 };
+	float s[16] = { 0.5f, 0, 0, 0, 0, 0.5f, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+	float ts[16];
+	orc_mat4_mul(t, s, ts);
+	orc_mat4_mul(ts, cam->view_projection, p->transform);
+	for (int i = 0; i < 3; i++)
+	{
+		p->camera_front[i] = cam->camera_front[i];
+		p->camera_base[i] = cam->camera_position[i];
+	}
+	p->xy_scale[0] = (float)res_x;
+	p->xy_scale[1] = (float)res_y;
+	p->resolution_xy[0] = res_x;
+	p->resolution_xy[1] = res_y;
+	p->inv_resolution_xy[0] = 1.0f / (float)res_x;
+	p->inv_resolution_xy[1] = 1.0f / (float)res_y;
+	p->z_scale = 1.0f / z_slice_extent(cam, res_z);
+	p->z_max_index = res_z - 1;
+}
+
+/* renderer/lights/clusterer.cpp:1265-1275 compute_uint_range */
+static void compute_uint_range(float lo, float hi, float extent, int res_z, uint32_t *out)
+{
+	lo = lo / extent;
+	hi = hi / extent;
+	if (hi < 0.0f)
+	{
+		out[0] = 0xffffffffu;
+		out[1] = 0u;
+		return;
+	}
+	lo = f_max(lo, 0.0f);
+	/* uvec2(vec2): C++ float -> uint32 conversion (truncation). Values here are < 2^32. */
+	uint32_t ux = (uint32_t)lo;
+	uint32_t uy = (uint32_t)hi;
+	if (uy > (uint32_t)(res_z - 1))
+		uy = (uint32_t)(res_z - 1);
+	out[0] = ux;
+	out[1] = uy;
+}
+
+/* renderer/lights/clusterer.cpp:1322-1346 + renderer/lights/lights.cpp:330-370 */
+void orc_light_z_ranges(const orc_camera_t *cam, const orc_light_t *lights, const float *model_rows,
+                        const uint32_t *type_mask, int num_lights, int res_z, uint32_t *z_ranges)
+{
+	float extent = z_slice_extent(cam, res_z);
+	vec3 pos = v3(cam->camera_position[0], cam->camera_position[1], cam->camera_position[2]);
+	vec3 front = v3(cam->camera_front[0], cam->camera_front[1], cam->camera_front[2]);
+	for (int i = 0; i < num_lights; i++)
+	{
+		float lo, hi;
+		if (type_mask[i >> 5] & (1u << (i & 31)))
+		{
+			/* point_light_z_range(center, 1/inv_radius) */
+			vec3 c = v3(lights[i].position[0], lights[i].position[1], lights[i].position[2]);
+			float radius = 1.0f / lights[i].inv_radius;
+			float z = v3_dot(v3_sub(c, pos), front);
+			lo = z - radius;
+			hi = z + radius;
+		}
+		else
+		{
+			const float *m = model_rows + (size_t)i * 12;
+			vec3 base = v3(m[3], m[7], m[11]);
+			vec3 x_off = v3(m[0], m[4], m[8]);
+			vec3 y_off = v3(m[1], m[5], m[9]);
+			vec3 z_off = v3(-m[2], -m[6], -m[10]);
+			vec3 z_base = v3_add(base, z_off);
+			vec3 wp[5];
+			wp[0] = base;
+			wp[1] = v3_add(v3_add(z_base, x_off), y_off);
+			wp[2] = v3_add(v3_sub(z_base, x_off), y_off);
+			wp[3] = v3_sub(v3_add(z_base, x_off), y_off);
+			wp[4] = v3_sub(v3_sub(z_base, x_off), y_off);
+			lo = INFINITY;
+			hi = -INFINITY;
+			for (int k = 0; k < 5; k++)
+			{
+				float z = v3_dot(v3_sub(wp[k], pos), front);
+				lo = f_min(z, lo);
+				hi = f_max(z, hi);
+			}
+		}
+		compute_uint_range(lo, hi, extent, res_z, z_ranges + 2 * (size_t)i);
+	}
+	if (num_lights == 0)
+	{
+		z_ranges[0] = 0xffffffffu;
+		z_ranges[1] = 0u;
+	}
+}
+
+uint32_t orc_pack_r11g11b10(float r, float g, float b) { return pack_r11g11b10(v3(r, g, b)); }
+void orc_unpack_r11g11b10(uint32_t p, float *rgb) { vec3 c = unpack_r11g11b10(p); rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z; }
+uint16_t orc_f32_to_f16(float f) { return f32_to_f16_rne(f); }
+float orc_f16_to_f32(uint16_t h) { return f16_to_f32(h); }
+uint32_t orc_linear_to_srgb8(float c) { return linear_to_srgb8(c); }
+float orc_srgb8_to_linear(uint32_t v) { return srgb8_to_linear(v); }

@@ -1,0 +1,264 @@
+/*
+ * oracle_lighting.c -- TEST INFRASTRUCTURE ONLY.  Deferred lighting pass (K6 directional +
+ * K5 clustered) restated from the reference GLSL.  See oracle_math.h for arithmetic rules.
+ *
+ * Reference: renderer/renderer.cpp:1004-1156 (DeferredLightRenderer::render_light) issues two
+ * full-screen draws with additive ONE/ONE blending into "HDR-main" (which aliases the
+ * emissive attachment, B10G11R11_UFLOAT), depth test NOT_EQUAL against the quad's z=0 so sky
+ * pixels (depth == 0) are untouched.  Each blend is dst = quantise(src + decode(dst)).
+ */
+#include "oracle.h"
+#include "oracle_math.h"
+
+#define PI_GRANITE 3.1415628f /* assets/shaders/lights/pbr.h:5 (sic) */
+
+/* pbr.h:8-26 */
+static float D_GGX(float roughness, vec3 N, vec3 H)
+{
+	float NoH = f_clamp(v3_dot(N, H), 0.0001f, 1.0f);
+	float m = roughness * roughness;
+	float m2 = m * m;
+	float d = (NoH * m2 - NoH) * NoH + 1.0f;
+	return m2 / (PI_GRANITE * d * d);
+}
+
+/* pbr.h:28-35 */
+static float G_schlick(float roughness, float NoV, float NoL)
+{
+	float r = roughness + 1.0f;
+	float k = r * r * (1.0f / 8.0f);
+	float V = NoV * (1.0f - k) + k;
+	float L = NoL * (1.0f - k) + k;
+	return 0.25f / f_max(V * L, 0.001f);
+}
+
+/* pbr.h:44-47: mix(F0, vec3(1.0), pow(1.0 - HoV, 5.0)) */
+static vec3 fresnel(vec3 F0, float HoV)
+{
+	float t = powf(1.0f - HoV, 5.0f);
+	return v3(f_mix(F0.x, 1.0f, t), f_mix(F0.y, 1.0f, t), f_mix(F0.z, 1.0f, t));
+}
+
+/* pbr.h:54-57 */
+static vec3 compute_F0(vec3 base_color, float metallic)
+{
+	return v3(f_mix(0.04f, base_color.x, metallic), f_mix(0.04f, base_color.y, metallic), f_mix(0.04f, base_color.z, metallic));
+}
+
+/* Shared tail of point.h:121-141 / spot.h:124-144 / lighting.h:26-46: Cook-Torrance BRDF.
+ * Returns (reflected + diffuse) WITHOUT the light colour factor when prefactor == NULL,
+ * otherwise follows lighting.h where light_color * NoL * shadow_term leads the products. */
+static vec3 brdf_terms(vec3 base_color, vec3 N, float metallic, float material_roughness,
+                       vec3 L, vec3 V, const vec3 *light_color_dir)
+{
+	float roughness = material_roughness * 0.75f + 0.25f;
+	vec3 H = v3_normalize(v3_add(V, L));
+	float NoV = f_clamp(v3_dot(N, V), 0.001f, 1.0f);
+	float NoL = f_clamp(v3_dot(N, L), 0.001f, 1.0f);
+	float HoV = f_clamp(v3_dot(H, V), 0.001f, 1.0f);
+	vec3 F0 = compute_F0(base_color, metallic);
+	vec3 F = fresnel(F0, HoV);
+	/* cook_torrance_specular: specular * G * D */
+	float D = D_GGX(roughness, N, H);
+	float G = G_schlick(roughness, NoV, NoL);
+	vec3 ct = v3_scale(v3_scale(F, G), D);
+	vec3 specref, diffref;
+	if (light_color_dir)
+	{
+		/* lighting.h:41-42: light_color * NoL * shadow_term(1.0) * X */
+		vec3 lc = v3_scale(v3_scale(*light_color_dir, NoL), 1.0f);
+		specref = v3_mul(lc, ct);
+		diffref = v3_scale(v3_mul(lc, v3(1.0f - F.x, 1.0f - F.y, 1.0f - F.z)), 1.0f / PI_GRANITE);
+	}
+	else
+	{
+		/* point.h:136-137: NoL * cook_torrance ; NoL * (1 - F) * (1/PI) */
+		specref = v3_scale(ct, NoL);
+		diffref = v3_scale(v3(NoL * (1.0f - F.x), NoL * (1.0f - F.y), NoL * (1.0f - F.z)), 1.0f / PI_GRANITE);
+	}
+	/* diffuse_light = diffref * base_color * (1 - metallic) */
+	vec3 diffuse = v3_scale(v3_mul(diffref, base_color), 1.0f - metallic);
+	return v3_add(specref, diffuse);
+}
+
+/* point.h:33-81 compute_point_color (POSITIONAL_LIGHTS_SHADOW undefined => shadow_falloff = 1) */
+static vec3 compute_point_color(const orc_light_t *pt, vec3 world_pos, vec3 *light_dir)
+{
+	vec3 light_pos = v3(pt->position[0], pt->position[1], pt->position[2]);
+	vec3 full = v3_sub(world_pos, light_pos);
+	*light_dir = v3_normalize(v3_neg(full));
+	float light_dist = f_max(0.1f, v3_length(full));
+	float static_falloff = 1.0f - f_smoothstep(0.9f, 1.0f, light_dist * pt->inv_radius);
+	if (static_falloff > 0.0f)
+	{
+		const float shadow_falloff = 1.0f;
+		float s = (shadow_falloff * static_falloff);
+		float d2 = (light_dist * light_dist);
+		/* point.color * (shadow*static) / (dist*dist): left-to-right */
+		return v3(pt->color[0] * s / d2, pt->color[1] * s / d2, pt->color[2] * s / d2);
+	}
+	return v3(0.0f, 0.0f, 0.0f);
+}
+
+/* spot.h:34-84 compute_spot_color */
+static vec3 compute_spot_color(const orc_light_t *sp, vec3 world_pos, vec3 *light_dir)
+{
+	vec3 light_pos = v3(sp->position[0], sp->position[1], sp->position[2]);
+	vec3 primary = v3(sp->direction[0], sp->direction[1], sp->direction[2]);
+	vec3 full = v3_sub(light_pos, world_pos);
+	*light_dir = v3_normalize(full);
+	float light_dist = f_max(0.1f, v3_length(full));
+	float cone_angle = v3_dot(v3_normalize(v3_sub(world_pos, light_pos)), primary);
+	float scale = f16_to_f32(sp->spot_scale_bias[0]); /* unpackHalf2x16 */
+	float bias = f16_to_f32(sp->spot_scale_bias[1]);
+	float cone_falloff = f_clamp(cone_angle * scale + bias, 0.0f, 1.0f);
+	cone_falloff *= cone_falloff;
+	cone_falloff *= 1.0f - f_smoothstep(0.9f, 1.0f, light_dist * sp->inv_radius);
+	if (cone_falloff > 0.0f)
+	{
+		const float shadow_falloff = 1.0f;
+		float k = (cone_falloff * shadow_falloff) / (light_dist * light_dist);
+		return v3(sp->color[0] * k, sp->color[1] * k, sp->color[2] * k);
+	}
+	return v3(0.0f, 0.0f, 0.0f);
+}
+
+/* point.h:103-142 / spot.h:106-145 */
+static vec3 compute_positional_light(const orc_light_t *l, int is_point, vec3 base_color, vec3 N,
+                                     float metallic, float roughness, vec3 world_pos, vec3 camera_pos)
+{
+	vec3 light_dir;
+	vec3 color = is_point ? compute_point_color(l, world_pos, &light_dir) : compute_spot_color(l, world_pos, &light_dir);
+	if (color.x == 0.0f && color.y == 0.0f && color.z == 0.0f)
+		return v3(0.0f, 0.0f, 0.0f);
+	vec3 V = v3_normalize(v3_sub(camera_pos, world_pos));
+	vec3 terms = brdf_terms(base_color, N, metallic, roughness, light_dir, V, 0);
+	return v3_mul(color, terms);
+}
+
+/* clusterer_bindless_buffers.h:17-27 */
+static uint32_t cluster_mask_range(uint32_t mask, uint32_t rx, uint32_t ry, uint32_t start_index)
+{
+	uint32_t lo = start_index, hi = start_index + 32u;
+	rx = rx < lo ? lo : (rx > hi ? hi : rx);
+	uint32_t ry1 = ry + 1u;
+	ry1 = ry1 < rx ? rx : (ry1 > hi ? hi : ry1);
+	uint32_t num_bits = ry1 - rx;
+	uint32_t range_mask = num_bits == 32u ? 0xffffffffu : ((1u << num_bits) - 1u) << (rx - start_index);
+	return mask & range_mask;
+}
+
+void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
+                           const orc_light_t *lights, const uint32_t *type_mask,
+                           const uint32_t *bitmask, const uint32_t *cluster_range,
+                           uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
+                           int32_t *out_light_count, int y0, int y1)
+{
+	const int W = g->width, H = g->height;
+	const float *ivp = cam->inv_view_projection;
+	const vec3 camera_pos = v3(cam->camera_position[0], cam->camera_position[1], cam->camera_position[2]);
+	const vec3 dir_color = v3(g->dir_color[0], g->dir_color[1], g->dir_color[2]);
+	const vec3 dir_dir = v3(g->dir_direction[0], g->dir_direction[1], g->dir_direction[2]);
+	/* push.inv_resolution = 1 / viewport (renderer.cpp:1101-1102, 1120) */
+	const float inv_res_x = 1.0f / (float)W, inv_res_y = 1.0f / (float)H;
+
+#pragma omp parallel for schedule(dynamic, 4)
+	for (int y = y0; y < y1; y++)
+	{
+		for (int x = 0; x < W; x++)
+		{
+			size_t idx = (size_t)y * W + x;
+			float depth = g->depth[idx];
+			uint32_t dst = g->emissive[idx];
+			if (out_tile_index) out_tile_index[idx] = -1;
+			if (out_z_index) out_z_index[idx] = -1;
+			if (out_light_count) out_light_count[idx] = 0;
+			if (depth == 0.0f)
+			{
+				hdr_out[idx] = dst; /* depth test NOT_EQUAL fails: sky keeps the attachment value */
+				continue;
+			}
+
+			/* G-buffer decode (clustering.frag:32-35) */
+			uint32_t a8 = g->albedo[idx];
+			vec3 base_color = v3(srgb8_to_linear(a8 & 0xffu), srgb8_to_linear((a8 >> 8) & 0xffu), srgb8_to_linear((a8 >> 16) & 0xffu));
+			float ambient_a = (float)(a8 >> 24) / 255.0f;
+			uint32_t n10 = g->normal[idx];
+			vec3 N = v3((float)(n10 & 0x3ffu) / 1023.0f * 2.0f - 1.0f,
+			            (float)((n10 >> 10) & 0x3ffu) / 1023.0f * 2.0f - 1.0f,
+			            (float)((n10 >> 20) & 0x3ffu) / 1023.0f * 2.0f - 1.0f);
+			uint16_t mr = g->pbr[idx];
+			float metallic = (float)(mr & 0xffu) / 255.0f;
+			float roughness = (float)(mr >> 8) / 255.0f;
+
+			/* clustering.vert:10-14 + quad: vClip = invVP * (ndc.xy, 0, 1), interpolated at the
+			 * pixel centre; ndc = 2 * (frag + 0.5) / size - 1.  Evaluated per pixel as
+			 * ((col0*ndc.x + col1*ndc.y) + col3)  (col2 * 0 dropped). */
+			float ndc_x = 2.0f * ((float)x + 0.5f) * inv_res_x - 1.0f;
+			float ndc_y = 2.0f * ((float)y + 0.5f) * inv_res_y - 1.0f;
+			vec4 vclip = v4(ivp[0] * ndc_x + ivp[4] * ndc_y + ivp[12],
+			                ivp[1] * ndc_x + ivp[5] * ndc_y + ivp[13],
+			                ivp[2] * ndc_x + ivp[6] * ndc_y + ivp[14],
+			                ivp[3] * ndc_x + ivp[7] * ndc_y + ivp[15]);
+			/* clustering.frag:38-39 */
+			vec4 clip = v4(vclip.x + depth * ivp[8], vclip.y + depth * ivp[9], vclip.z + depth * ivp[10], vclip.w + depth * ivp[11]);
+			vec3 pos = v3(clip.x / clip.w, clip.y / clip.w, clip.z / clip.w);
+
+			/* ---- draw 1: directional.frag:40-65 (LIGHTING_NO_AMBIENT, no SHADOWS,
+			 * VOLUMETRIC_DIFFUSE_FALLBACK, no AMBIENT_OCCLUSION => base_ambient = 1) ---- */
+			vec3 V = v3_normalize(v3_sub(camera_pos, pos));
+			vec3 lit = brdf_terms(base_color, N, metallic, roughness, dir_dir, V, &dir_color);
+			const float base_ambient = 1.0f;
+			(void)ambient_a; /* material_ambient_factor only feeds the !LIGHTING_NO_AMBIENT branch */
+			lit = v3_add(lit, v3(base_ambient * base_color.x * 0.05f, base_ambient * base_color.y * 0.05f, base_ambient * base_color.z * 0.05f));
+			vec3 d = unpack_r11g11b10(dst);
+			dst = pack_r11g11b10(v3_add(lit, d));
+
+			/* ---- draw 2: clustering.frag + clusterer_bindless.h:29-84 ---- */
+			vec3 result = v3(0.0f, 0.0f, 0.0f);
+			/* gl_FragCoord.xy * inv_resolution * cluster.xy_scale */
+			int cx = (int)(((float)x + 0.5f) * inv_res_x * p->xy_scale[0]);
+			int cy = (int)(((float)y + 0.5f) * inv_res_y * p->xy_scale[1]);
+			cx = cx < 0 ? 0 : (cx > p->resolution_xy[0] - 1 ? p->resolution_xy[0] - 1 : cx);
+			cy = cy < 0 ? 0 : (cy > p->resolution_xy[1] - 1 ? p->resolution_xy[1] - 1 : cy);
+			int cluster_index = cy * p->resolution_xy[0] + cx;
+			int cluster_base = cluster_index * p->num_lights_32;
+
+			vec3 cbase = v3(p->camera_base[0], p->camera_base[1], p->camera_base[2]);
+			vec3 cfront = v3(p->camera_front[0], p->camera_front[1], p->camera_front[2]);
+			float z = v3_dot(v3_sub(pos, cbase), cfront);
+			float zs = z * p->z_scale;
+			/* int(float): truncation; saturate like the hardware F2I so huge/NaN values stay defined */
+			int z_index = zs >= 2147483520.0f ? 2147483647 : (zs <= -2147483648.0f ? (-2147483647 - 1) : (zs != zs ? 0 : (int)zs));
+			z_index = z_index < 0 ? 0 : (z_index > p->z_max_index ? p->z_max_index : z_index);
+			uint32_t rx = cluster_range[2 * z_index], ry = cluster_range[2 * z_index + 1];
+			if (out_tile_index) out_tile_index[idx] = cluster_index;
+			if (out_z_index) out_z_index[idx] = z_index;
+
+			/* The reference widens [z_start, z_end] and ORs masks across the subgroup purely for
+			 * scalarisation; a light outside this pixel's own mask lies outside its radius and
+			 * contributes exactly +0, so the per-pixel form below is the same function. */
+			int z_start = (int)(rx >> 5u);
+			int z_end = (int)(ry >> 5u);
+			int count = 0;
+			for (int i = z_start; i <= z_end && i < p->num_lights_32; i++)
+			{
+				uint32_t mask = bitmask[cluster_base + i];
+				mask = cluster_mask_range(mask, rx, ry, 32u * (uint32_t)i);
+				uint32_t tm = type_mask[i];
+				while (mask != 0u)
+				{
+					int bit = __builtin_ctz(mask);
+					int index = 32 * i + bit;
+					vec3 c = compute_positional_light(&lights[index], (tm >> bit) & 1u, base_color, N, metallic, roughness, pos, camera_pos);
+					result = v3_add(result, c);
+					count++;
+					mask &= ~(1u << bit);
+				}
+			}
+			if (out_light_count) out_light_count[idx] = count;
+			d = unpack_r11g11b10(dst);
+			hdr_out[idx] = pack_r11g11b10(v3_add(result, d));
+		}
+	}
+}

@@ -1,0 +1,296 @@
+"""ctypes binding of the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may
+import this module.  The product package granite_b200 must never import it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from types import SimpleNamespace
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_REF_PATH = os.path.join(_HERE, "_ref", "libgranite_refmath.so")
+
+
+def build(ref: bool = True) -> None:
+    """Compile liboracle.so (always) and oracle/_ref (only where /root/reference exists)."""
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    if ref and os.path.isdir("/root/reference/math"):
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+class Light(C.Structure):
+    _fields_ = [("color", C.c_float * 3), ("spot_scale_bias", C.c_uint16 * 2),
+                ("position", C.c_float * 3), ("offset_radius", C.c_uint16 * 2),
+                ("direction", C.c_float * 3), ("inv_radius", C.c_float)]
+
+
+LIGHT_DTYPE = np.dtype([("color", "<f4", 3), ("spot_scale_bias", "<u2", 2), ("position", "<f4", 3),
+                        ("offset_radius", "<u2", 2), ("direction", "<f4", 3), ("inv_radius", "<f4")])
+assert LIGHT_DTYPE.itemsize == 48 and C.sizeof(Light) == 48
+
+
+class ClusterParams(C.Structure):
+    _fields_ = [("transform", C.c_float * 16), ("clip_scale", C.c_float * 4),
+                ("camera_base", C.c_float * 3), ("camera_front", C.c_float * 3),
+                ("xy_scale", C.c_float * 2), ("resolution_xy", C.c_int32 * 2),
+                ("inv_resolution_xy", C.c_float * 2), ("num_lights", C.c_int32),
+                ("num_lights_32", C.c_int32), ("z_max_index", C.c_int32), ("z_scale", C.c_float)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("projection", C.c_float * 16), ("view", C.c_float * 16),
+                ("view_projection", C.c_float * 16), ("inv_projection", C.c_float * 16),
+                ("inv_view", C.c_float * 16), ("inv_view_projection", C.c_float * 16),
+                ("camera_position", C.c_float * 3), ("camera_front", C.c_float * 3),
+                ("z_near", C.c_float), ("z_far", C.c_float)]
+
+
+class GBuffer(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("albedo", C.c_void_p), ("normal", C.c_void_p),
+                ("pbr", C.c_void_p), ("depth", C.c_void_p), ("emissive", C.c_void_p),
+                ("dir_color", C.c_float * 3), ("dir_direction", C.c_float * 3)]
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build(ref=False)
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_float_to_half.restype = C.c_uint16
+        _lib.orc_float_to_half.argtypes = [C.c_float]
+        _lib.orc_pack_r11g11b10.restype = C.c_uint32
+        _lib.orc_pack_r11g11b10.argtypes = [C.c_float] * 3
+        _lib.orc_f32_to_f16.restype = C.c_uint16
+        _lib.orc_f32_to_f16.argtypes = [C.c_float]
+        _lib.orc_f16_to_f32.restype = C.c_float
+        _lib.orc_f16_to_f32.argtypes = [C.c_uint16]
+        _lib.orc_linear_to_srgb8.restype = C.c_uint32
+        _lib.orc_linear_to_srgb8.argtypes = [C.c_float]
+        _lib.orc_srgb8_to_linear.restype = C.c_float
+        _lib.orc_srgb8_to_linear.argtypes = [C.c_uint32]
+    return _lib
+
+
+def ref():
+    """The reference's own math/ compiled into oracle/_ref (None when it was not built)."""
+    global _ref
+    if _ref is None and os.path.exists(_REF_PATH):
+        _ref = C.CDLL(_REF_PATH)
+        _ref.ref_float_to_half.restype = C.c_uint16
+        _ref.ref_float_to_half.argtypes = [C.c_float]
+        _ref.ref_infinite_far_plane.restype = C.c_float
+    return _ref
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(x):
+    return C.c_float(float(x))
+
+
+def _c(a, dtype):
+    if a is None:
+        return None
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+# ---------------- host math ----------------
+def perspective(fovy, aspect, near, far):
+    out = np.zeros(16, np.float32)
+    lib().orc_perspective(_f(fovy), _f(aspect), _f(near), _f(far), _p(out))
+    return out.reshape(4, 4)
+
+
+def mat4_inverse(m):
+    m = _c(m, np.float32)
+    out = np.zeros(16, np.float32)
+    lib().orc_mat4_inverse(_p(m), _p(out))
+    return out.reshape(4, 4)
+
+
+def mat4_mul(a, b):
+    a = _c(a, np.float32); b = _c(b, np.float32)
+    out = np.zeros(16, np.float32)
+    lib().orc_mat4_mul(_p(a), _p(b), _p(out))
+    return out.reshape(4, 4)
+
+
+def camera_setup(projection, view) -> Camera:
+    cam = Camera()
+    pr = _c(projection, np.float32); vw = _c(view, np.float32)
+    lib().orc_camera_setup(_p(pr), _p(vw), C.byref(cam))
+    return cam
+
+
+# ---------------- light prep ----------------
+def prepare_lights(cam: Camera, lights, res=(128, 64, 4096), cutoff=1e10):
+    """Host prep: records (sorted order as given), model rows, type mask, cluster params, z ranges."""
+    n = len(lights.color)
+    n32 = (n + 31) // 32
+    recs = np.zeros(max(n, 1), LIGHT_DTYPE)
+    model = np.zeros((max(n, 1), 12), np.float32)
+    type_mask = np.zeros(max(n32, 1), np.uint32)
+    L = lib()
+    for i in range(n):
+        col = _c(lights.color[i], np.float32); pos = _c(lights.position[i], np.float32)
+        rec = Light()
+        if lights.is_point[i]:
+            L.orc_point_light_info(_p(col), _p(pos), _f(cutoff), C.byref(rec))
+            type_mask[i >> 5] |= np.uint32(1 << (i & 31))
+            model[i, 0:3] = pos
+            model[i, 3] = np.float32(1.0) / np.float32(rec.inv_radius)  # clusterer.cpp:647-650
+        else:
+            rot = _c(lights.rot[i], np.float32)
+            rows = np.zeros(12, np.float32)
+            L.orc_spot_light_info(_p(col), _p(pos), _p(rot), _f(lights.inner_cone[i]), _f(lights.outer_cone[i]),
+                                  _f(cutoff), C.byref(rec), _p(rows))
+            model[i] = rows
+        recs[i:i + 1] = np.frombuffer(bytes(rec), LIGHT_DTYPE)
+    params = ClusterParams()
+    L.orc_cluster_params(C.byref(cam), n, res[0], res[1], res[2], C.byref(params))
+    z_ranges = np.zeros((max(n, 1), 2), np.uint32)
+    L.orc_light_z_ranges(C.byref(cam), _p(recs), _p(model), _p(type_mask), n, res[2], _p(z_ranges))
+    return SimpleNamespace(n=n, n32=n32, records=recs, model=model, type_mask=type_mask, params=params,
+                           z_ranges=z_ranges, res=res)
+
+
+def cluster_build(cam: Camera, prep):
+    """K1..K4. Returns transformed_spots, cull_setup, bitmask, cluster_range."""
+    L = lib()
+    n, n32 = prep.n, prep.n32
+    rx, ry, rz = prep.res
+    spots = np.zeros((max(n, 1), 24), np.float32)
+    L.orc_spot_transform(C.byref(cam), _p(prep.model), n, _p(spots))
+    cull = np.zeros((max(n, 1), 128), np.float32)
+    L.orc_cull_setup(C.byref(cam), C.byref(prep.params), _p(prep.records), _p(prep.type_mask), _p(spots), _p(cull))
+    bitmask = np.zeros((ry, rx, max(n32, 1)), np.uint32)
+    if n:
+        L.orc_binning(C.byref(prep.params), _p(prep.type_mask), _p(cull), _p(bitmask))
+    crange = np.zeros((rz, 2), np.uint32)
+    L.orc_z_range(_p(prep.z_ranges), max(n, 1), rz, _p(crange))
+    return SimpleNamespace(spots=spots, cull=cull, bitmask=bitmask, range=crange)
+
+
+def deferred_lighting(scene, cam: Camera, prep, clus, rows=None, want_indices=False):
+    H, W = scene.depth.shape
+    g = GBuffer()
+    g.width, g.height = W, H
+    keep = [_c(scene.albedo, np.uint32), _c(scene.normal, np.uint32), _c(scene.pbr, np.uint16),
+            _c(scene.depth, np.float32), _c(scene.emissive, np.uint32)]
+    g.albedo, g.normal, g.pbr, g.depth, g.emissive = [k.ctypes.data for k in keep]
+    g.dir_color = (C.c_float * 3)(*scene.dir_color)
+    g.dir_direction = (C.c_float * 3)(*scene.dir_direction)
+    hdr = np.zeros((H, W), np.uint32)
+    tile = np.zeros((H, W), np.int32) if want_indices else None
+    zidx = np.zeros((H, W), np.int32) if want_indices else None
+    cnt = np.zeros((H, W), np.int32) if want_indices else None
+    y0, y1 = rows if rows else (0, H)
+    lib().orc_deferred_lighting(C.byref(g), C.byref(cam), C.byref(prep.params), _p(prep.records),
+                                _p(prep.type_mask), _p(clus.bitmask), _p(clus.range), _p(hdr),
+                                _p(tile), _p(zidx), _p(cnt), y0, y1)
+    if want_indices:
+        return hdr, tile, zidx, cnt
+    return hdr
+
+
+# ---------------- HDR chain ----------------
+def bloom_threshold(hdr, lum3, out_wh):
+    h_in, w_in = hdr.shape
+    w, h = out_wh
+    out = np.zeros((h, w, 4), np.uint16)
+    l3 = None if lum3 is None else _c(lum3, np.float32)
+    lib().orc_bloom_threshold(_p(_c(hdr, np.uint32)), w_in, h_in, _p(l3), _p(out), w, h)
+    return out
+
+
+def bloom_downsample(src, out_wh, history=None, lerp=0.0):
+    h_in, w_in = src.shape[:2]
+    w, h = out_wh
+    out = np.zeros((h, w, 4), np.uint16)
+    hist = None if history is None else _c(history, np.uint16)
+    lib().orc_bloom_downsample(_p(_c(src, np.uint16)), w_in, h_in, _p(hist), _f(lerp), _p(out), w, h)
+    return out
+
+
+def bloom_upsample(src, out_wh):
+    h_in, w_in = src.shape[:2]
+    w, h = out_wh
+    out = np.zeros((h, w, 4), np.uint16)
+    lib().orc_bloom_upsample(_p(_c(src, np.uint16)), w_in, h_in, _p(out), w, h)
+    return out
+
+
+def luminance(d3, lum3, lerp, lo=-3.0, hi=2.0, want_grid=False):
+    h, w = d3.shape[:2]
+    l3 = _c(lum3, np.float32).copy()
+    grid = np.zeros((h // 2, w // 2), np.float32) if want_grid else None
+    lib().orc_luminance(_p(_c(d3, np.uint16)), w, h, _f(lerp), _f(lo), _f(hi), _p(l3), _p(grid))
+    return (l3, grid) if want_grid else l3
+
+
+def tonemap(hdr, bloom, lum3, exposure=1.0, rows=None):
+    h, w = hdr.shape
+    bh, bw = bloom.shape[:2]
+    out = np.zeros((h, w), np.uint32)
+    l3 = None if lum3 is None else _c(lum3, np.float32)
+    y0, y1 = rows if rows else (0, h)
+    lib().orc_tonemap(_p(_c(hdr, np.uint32)), w, h, _p(_c(bloom, np.uint16)), bw, bh, _p(l3), _f(exposure), _p(out), y0, y1)
+    return out
+
+
+def fxaa(img, target_srgb=True, rows=None):
+    h, w = img.shape
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    lib().orc_fxaa(_p(_c(img, np.uint32)), w, h, int(target_srgb), _p(out), y0, y1)
+    return out
+
+
+def taa_resolve(hdr, depth, mv, history, reproj, quality=2, rows=None):
+    h, w = hdr.shape
+    out_c = np.zeros((h, w), np.uint32)
+    out_h = np.zeros((h, w, 4), np.uint16)
+    hist = None if history is None else _c(history, np.uint16)
+    y0, y1 = rows if rows else (0, h)
+    lib().orc_taa_resolve(_p(_c(hdr, np.uint32)), _p(_c(depth, np.float32)), _p(_c(mv, np.uint16)), _p(hist), w, h,
+                          _p(_c(reproj, np.float32)), int(quality), _p(out_c), _p(out_h), y0, y1)
+    return out_c, out_h
+
+
+def pyramid_sizes(w, h):
+    """ceil(parent * scale), renderer/render_graph.cpp:3160-3171; scales 1/2 .. 1/32 of the HDR input."""
+    import math
+    return [(int(math.ceil(w * s)), int(math.ceil(h * s))) for s in (0.5, 0.25, 0.125, 0.0625, 0.03125)]
+
+
+def hdr_chain(hdr, lum3, d3_history, frame_time=1.0 / 60.0, exposure=1.0, dynamic_exposure=True):
+    """One frame of setup_hdr_postprocess_compute (renderer/post/hdr.cpp:354-379) + tonemap."""
+    h, w = hdr.shape
+    sz = pyramid_sizes(w, h)
+    lerp_d3 = np.float32(1.0 - 0.001 ** frame_time)   # hdr.cpp:182 (double math, then float)
+    lerp_lum = np.float32(1.0 - 0.5 ** frame_time)    # hdr.cpp:93
+    lum_in = _c(lum3, np.float32) if dynamic_exposure else None
+    t = bloom_threshold(hdr, lum_in, sz[0])
+    d0 = bloom_downsample(t, sz[1])
+    d1 = bloom_downsample(d0, sz[2])
+    d2 = bloom_downsample(d1, sz[3])
+    d3 = bloom_downsample(d2, sz[4], d3_history, lerp_d3)
+    lum_out = luminance(d3, lum3, lerp_lum) if dynamic_exposure else None
+    u2 = bloom_upsample(d3, sz[3])
+    u1 = bloom_upsample(u2, sz[2])
+    u0 = bloom_upsample(u1, sz[1])
+    ldr = tonemap(hdr, u0, lum_out, exposure)
+    return SimpleNamespace(t=t, d0=d0, d1=d1, d2=d2, d3=d3, u2=u2, u1=u1, u0=u0, lum=lum_out, ldr=ldr)

@@ -1,0 +1,56 @@
+// ref_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+// Thin extern "C" exports over the REFERENCE's own host math (math/muglm, math/transforms),
+// compiled from the sources where they lie under /root/reference into oracle/_ref/
+// (see oracle/Makefile target `ref`).  Used only to pin oracle_host.c's restatements
+// (perspective, inverse, mat4 multiply, floatToHalf, camera look_at) bit-for-bit.
+// No reference source is copied into this repository.
+#include "muglm/muglm_impl.hpp"
+#include "muglm/matrix_helper.hpp"
+#include "transforms.hpp"
+#include <cstring>
+
+using namespace muglm;
+
+extern "C" {
+void ref_perspective(float fovy, float aspect, float z_near, float z_far, float *out16)
+{
+	mat4 m = perspective(fovy, aspect, z_near, z_far);
+	memcpy(out16, &m, 64);
+}
+
+void ref_mat4_inverse(const float *in16, float *out16)
+{
+	mat4 m;
+	memcpy(&m, in16, 64);
+	mat4 r = inverse(m);
+	memcpy(out16, &r, 64);
+}
+
+void ref_mat4_mul(const float *a16, const float *b16, float *out16)
+{
+	mat4 a, b;
+	memcpy(&a, a16, 64);
+	memcpy(&b, b16, 64);
+	mat4 r = a * b;
+	memcpy(out16, &r, 64);
+}
+
+uint16_t ref_float_to_half(float v)
+{
+	return floatToHalf(v);
+}
+
+// renderer/camera.cpp:61-64,76-80: view = mat4_cast(look_at(at - eye, up)) * translate(-eye)
+void ref_camera_view(const float *eye, const float *at, const float *up, float *out16)
+{
+	vec3 e(eye[0], eye[1], eye[2]), a(at[0], at[1], at[2]), u(up[0], up[1], up[2]);
+	quat rot = Granite::look_at(a - e, u);
+	mat4 view = mat4_cast(rot) * translate(-e);
+	memcpy(out16, &view, 64);
+}
+
+float ref_infinite_far_plane(void)
+{
+	return InfiniteFarPlane;
+}
+}

@@ -1,0 +1,70 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+from __future__ import annotations
+
+import numpy as np
+
+from granite_b200 import synth
+
+
+def build_case(oracle, width, height, n_lights, spot_fraction=0.0):
+    """Scene + oracle host prep (camera, light records, cluster params) for one config."""
+    scene = synth.make_scene(width, height)
+    cam = oracle.camera_setup(scene.projection, scene.view)
+    lights = synth.make_lights(n_lights, spot_fraction=spot_fraction, aspect=width / height)
+    prep = oracle.prepare_lights(cam, lights, res=synth.CLUSTER_RES)
+    return scene, cam, lights, prep
+
+
+def build_lights_case(oracle, aspect, n_lights, spot_fraction=0.0):
+    """Camera + lights + oracle host prep only (no G-buffer)."""
+    import math
+
+    proj = synth.perspective_inf(math.pi / 4.0, aspect, 1.0 / 16.0)
+    view = synth.look_at_view((0.0, 0.0, 8.0), (0.0, 0.0, 0.0))
+    cam = oracle.camera_setup(proj, view)
+    lights = synth.make_lights(n_lights, spot_fraction=spot_fraction, aspect=aspect)
+    prep = oracle.prepare_lights(cam, lights, res=synth.CLUSTER_RES)
+    return cam, lights, prep
+
+
+def r11g11b10_codes(p: np.ndarray):
+    """Split packed B10G11R11 into per-channel integer codes (monotone in the decoded value)."""
+    p = p.astype(np.uint32)
+    return (p & 0x7FF).astype(np.int64), ((p >> 11) & 0x7FF).astype(np.int64), (p >> 22).astype(np.int64)
+
+
+def max_code_diff_r11g11b10(a, b):
+    return max(int(np.abs(x - y).max()) for x, y in zip(r11g11b10_codes(a), r11g11b10_codes(b)))
+
+
+def f16_ulp_diff(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """ULP distance between two fp16 bit patterns (sign-magnitude -> monotone integer)."""
+    def key(u):
+        u = u.astype(np.int32)
+        return np.where(u & 0x8000, -(u & 0x7FFF), u & 0x7FFF)
+    return np.abs(key(a.view(np.uint16)) - key(b.view(np.uint16)))
+
+
+def f32_ulp_diff(a, b):
+    def key(f):
+        u = np.asarray(f, np.float32).view(np.int32).astype(np.int64)
+        return np.where(u < 0, -(u & 0x7FFFFFFF), u)
+    return np.abs(key(a) - key(b))
+
+
+def rgba8_channel_diff(a, b):
+    a = np.ascontiguousarray(a).view(np.uint8).astype(np.int32)
+    b = np.ascontiguousarray(b).view(np.uint8).astype(np.int32)
+    return np.abs(a - b)
+
+
+def random_hdr(rng, w, h, scale=4.0, hot=0.002):
+    """Random B10G11R11 image with a few very bright texels (drives bloom)."""
+    rgb = (rng.random((h, w, 3)) ** 3 * scale).astype(np.float32)
+    m = rng.random((h, w)) < hot
+    rgb[m] = rng.uniform(10.0, 200.0, size=(int(m.sum()), 3)).astype(np.float32)
+    return synth.pack_r11g11b10(rgb)
+
+
+def random_rgba16f(rng, w, h, lo=-2.0, hi=8.0):
+    return rng.uniform(lo, hi, size=(h, w, 4)).astype(np.float16).view(np.uint16)

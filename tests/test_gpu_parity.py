@@ -1,0 +1,262 @@
+"""GPU parity: every C-ABI entry point against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): bit-exact for cluster bitmasks / ranges / indices; <= 1 ULP of
+the STORED format per channel elsewhere (B10G11R11 code, fp16 ulp, 8-bit LSB).  Kernels with no
+transcendental in them are additionally required to be bit-exact.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [
+    pytest.param(256, 256, 16, 0.0, id="C1-256x256-16pt"),
+    pytest.param(640, 360, 300, 0.25, id="small-300-25pct-spots"),
+    pytest.param(1920, 1080, 1024, 0.0, id="C2-1080p-1024pt"),
+]
+
+
+def _cluster(cuda, oracle, cam, prep):
+    from granite_b200 import harness
+
+    dev = harness.ClusterDevice(prep.records, prep.model, prep.type_mask, prep.z_ranges, prep.params, prep.res)
+    gcam = harness.camera_struct(cam)
+    dev.build(gcam)
+    torch.cuda.synchronize()
+    return dev, gcam
+
+
+@pytest.mark.parametrize("w,h,n,spots", CONFIGS + [pytest.param(3840, 2160, 4096, 0.25, id="C3-4096-25pct-spots")])
+def test_cluster_build_bit_exact(cuda, oracle, w, h, n, spots):
+    cam, lights, prep = common.build_lights_case(oracle, w / h, n, spots)  # the clusterer does not read the G-buffer
+    ref = oracle.cluster_build(cam, prep)
+    dev, _ = _cluster(cuda, oracle, cam, prep)
+    got = dev.download()
+    is_point = np.array([(prep.type_mask[i >> 5] >> (i & 31)) & 1 for i in range(n)], bool)
+    # K1: spot hull (only spot entries are consumed)
+    assert np.array_equal(got.spots[:n][~is_point].view(np.uint32), ref.spots[:n][~is_point].view(np.uint32))
+    # K2: point lights use data[0..3]; spots use 4 vec4 per emitted triangle (+ count in data[0].w)
+    assert np.array_equal(got.cull[:n][is_point][:, :16].view(np.uint32), ref.cull[:n][is_point][:, :16].view(np.uint32))
+    for i in np.nonzero(~is_point)[0]:
+        cnt = int(ref.cull[i].view(np.uint32)[3])
+        assert int(got.cull[i].view(np.uint32)[3]) == cnt
+        used = 16 * min(cnt, 8) if cnt <= 8 else 0
+        a, b = got.cull[i][:used].view(np.uint32).copy(), ref.cull[i][:used].view(np.uint32).copy()
+        if used:
+            a[3] = b[3] = 0
+        assert np.array_equal(a, b), f"spot {i}"
+    # K3 / K4: the integer contract
+    assert np.array_equal(got.bitmask, ref.bitmask)
+    assert np.array_equal(got.range, ref.range)
+    # bits >= num_lights are zero
+    if n % 32:
+        assert not (got.bitmask[..., -1] >> np.uint32(n % 32)).any()
+
+
+@pytest.mark.parametrize("w,h,n,spots", CONFIGS)
+def test_cluster_indices_bit_exact(cuda, oracle, w, h, n, spots):
+    from granite_b200 import capi, harness
+
+    scene, cam, lights, prep = common.build_case(oracle, w, h, n, spots)
+    clus = oracle.cluster_build(cam, prep)
+    _, tile, zi, _ = oracle.deferred_lighting(scene, cam, prep, clus, want_indices=True)
+    depth = harness.to_dev(scene.depth)
+    out_t = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    out_z = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    img = capi.image(depth, capi.FORMAT_D32_SFLOAT)
+    gcam = harness.camera_struct(cam)
+    params = harness.params_struct(prep.params)
+    capi.check(capi.lib().grb_debug_cluster_indices(C.byref(img), C.byref(gcam), C.byref(params), C.c_void_p(out_t.data_ptr()),
+                                                    C.c_void_p(out_z.data_ptr()), capi.rows(), capi.stream_ptr()))
+    assert np.array_equal(out_t.cpu().numpy(), tile)
+    assert np.array_equal(out_z.cpu().numpy(), zi)
+
+
+@pytest.mark.parametrize("w,h,n,spots", CONFIGS)
+def test_deferred_lighting_parity(cuda, oracle, w, h, n, spots):
+    from granite_b200 import harness
+
+    scene, cam, lights, prep = common.build_case(oracle, w, h, n, spots)
+    clus = oracle.cluster_build(cam, prep)
+    ref = oracle.deferred_lighting(scene, cam, prep, clus)
+    dev, gcam = _cluster(cuda, oracle, cam, prep)
+    gb = harness.GBufferDevice(scene)
+    hdr = gb.emissive.clone()
+    harness.deferred_lighting(gb, gcam, dev, hdr)
+    got = harness.to_host(hdr, np.uint32)
+    sky = scene.depth == 0
+    assert np.array_equal(got[sky], scene.emissive[sky]), "sky pixels must keep the attachment value"
+    assert common.max_code_diff_r11g11b10(got, ref) <= 1
+    exact = float((got == ref).mean())
+    print(f"lighting exact-match fraction: {exact:.5f}")
+    assert exact > 0.97
+    # row sharding is bit-invariant
+    hdr2 = gb.emissive.clone()
+    cut = (h // 3) & ~3
+    harness.deferred_lighting(gb, gcam, dev, hdr2, rows=(0, cut))
+    harness.deferred_lighting(gb, gcam, dev, hdr2, rows=(cut, h))
+    assert torch.equal(hdr, hdr2)
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (1920, 1080), (1001, 517)])
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_bloom_threshold(cuda, oracle, w, h, dynamic):
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w * 7 + h)
+    hdr = common.random_hdr(rng, w, h)
+    ow, oh = oracle.pyramid_sizes(w, h)[0]
+    lum = np.array([0.3, 2.0 ** 0.3, 2.0 ** -0.3], np.float32) if dynamic else None
+    ref = oracle.bloom_threshold(hdr, lum, (ow, oh))
+    out = harness.new_rgba16f(ow, oh)
+    harness.bloom_threshold(harness.to_dev(hdr), harness.to_dev(lum) if dynamic else None, out)
+    got = harness.to_host(out, np.uint16)
+    assert np.array_equal(got[..., :3], ref[..., :3]), "rgb has no transcendental: must be bit-exact"
+    assert common.f16_ulp_diff(got[..., 3], ref[..., 3]).max() <= 1  # log2
+
+
+@pytest.mark.parametrize("w_in,h_in,w,h", [(128, 128, 64, 64), (960, 540, 480, 270), (240, 135, 120, 68), (33, 17, 17, 9)])
+@pytest.mark.parametrize("feedback", [False, True])
+def test_bloom_downsample_bit_exact(cuda, oracle, w_in, h_in, w, h, feedback):
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w_in + 3 * h_in + feedback)
+    src = common.random_rgba16f(rng, w_in, h_in)
+    hist = common.random_rgba16f(rng, w, h) if feedback else None
+    lerp = float(np.float32(1.0 - 0.001 ** (1 / 60)))
+    ref = oracle.bloom_downsample(src, (w, h), hist, lerp)
+    out = harness.new_rgba16f(w, h)
+    harness.bloom_downsample(harness.to_dev(src), out, harness.to_dev(hist) if feedback else None, lerp)
+    assert np.array_equal(harness.to_host(out, np.uint16), ref)
+
+
+@pytest.mark.parametrize("w_in,h_in,w,h", [(8, 8, 16, 16), (120, 68, 240, 135), (480, 270, 960, 540), (9, 5, 17, 9)])
+def test_bloom_upsample_bit_exact(cuda, oracle, w_in, h_in, w, h):
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w_in * 5 + h_in)
+    src = common.random_rgba16f(rng, w_in, h_in)
+    ref = oracle.bloom_upsample(src, (w, h))
+    out = harness.new_rgba16f(w, h)
+    harness.bloom_upsample(harness.to_dev(src), out)
+    assert np.array_equal(harness.to_host(out, np.uint16), ref)
+
+
+@pytest.mark.parametrize("w,h", [(8, 8), (60, 34), (120, 68), (61, 35)])
+def test_luminance(cuda, oracle, w, h):
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w + h)
+    d3 = common.random_rgba16f(rng, w, h, -6.0, 6.0)
+    lum0 = np.array([0.25, 2.0 ** 0.25, 2.0 ** -0.25], np.float32)
+    lerp = float(np.float32(1.0 - 0.5 ** (1 / 60)))
+    ref, grid = oracle.luminance(d3, lum0, lerp, want_grid=True)
+    d3_t = harness.to_dev(d3)
+    lum_t = harness.to_dev(lum0.copy())
+    harness.luminance(d3_t, lum_t, lerp)
+    got = lum_t.cpu().numpy()
+    assert got[0].view(np.uint32) == ref[0].view(np.uint32), "average log luminance (pure add/mul) must be bit-exact"
+    assert common.f32_ulp_diff(got[1:], ref[1:]).max() <= 4  # exp2
+    # sharded form: grid rows from two "ranks", summed (x + 0 is exact), then finalised
+    sx, sy = w // 2, h // 2
+    g0 = torch.zeros(sy * sx, dtype=torch.float32, device="cuda")
+    g1 = torch.zeros(sy * sx, dtype=torch.float32, device="cuda")
+    cut = sy // 2
+    harness.luminance_grid(d3_t, g0, rows=(0, cut))
+    harness.luminance_grid(d3_t, g1, rows=(cut, sy))
+    gsum = g0 + g1
+    assert np.array_equal(gsum.cpu().numpy().reshape(sy, sx).view(np.uint32), grid.view(np.uint32))
+    lum_t2 = harness.to_dev(lum0.copy())
+    harness.luminance_finalize(gsum, sx, sy, lum_t2, lerp)
+    assert torch.equal(lum_t, lum_t2)
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (1920, 1080), (1001, 517)])
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_tonemap(cuda, oracle, w, h, dynamic):
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w + 11 * h)
+    hdr = common.random_hdr(rng, w, h)
+    bw, bh = oracle.pyramid_sizes(w, h)[1]
+    bloom = common.random_rgba16f(rng, bw, bh, 0.0, 0.5)
+    lum = np.array([-0.7, 2.0 ** -0.7, 2.0 ** 0.7], np.float32) if dynamic else None
+    ref = oracle.tonemap(hdr, bloom, lum, 1.25)
+    out = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    harness.tonemap(harness.to_dev(hdr), harness.to_dev(bloom), harness.to_dev(lum) if dynamic else None, out, exposure=1.25)
+    got = harness.to_host(out, np.uint32)
+    d = common.rgba8_channel_diff(got, ref)
+    assert d.max() <= 1
+    print(f"tonemap exact fraction {float((got == ref).mean()):.6f}")
+    assert (got == ref).mean() > 0.999
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (1280, 720), (333, 177)])
+@pytest.mark.parametrize("srgb", [True, False])
+def test_fxaa(cuda, oracle, w, h, srgb):
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w - h)
+    # blocky image with edges so the directional taps are exercised
+    base = rng.integers(0, 256, size=(h // 8 + 1, w // 8 + 1, 4), dtype=np.uint8)
+    img = np.kron(base, np.ones((8, 8, 1), np.uint8))[:h, :w].copy()
+    img = (img.astype(np.int32) + rng.integers(-6, 7, size=img.shape)).clip(0, 255).astype(np.uint8)
+    img32 = np.ascontiguousarray(img).view(np.uint32)[..., 0]
+    ref = oracle.fxaa(img32, srgb)
+    out = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    harness.fxaa(harness.to_dev(img32), out, target_srgb=srgb)
+    got = harness.to_host(out, np.uint32)
+    d = common.rgba8_channel_diff(got, ref)
+    assert d.max() <= 1
+    if not srgb:
+        assert np.array_equal(got, ref), "UNORM target has no transcendental: must be bit-exact"
+
+
+def _taa_inputs(rng, w, h):
+    hdr = common.random_hdr(rng, w, h, scale=2.0)
+    depth = rng.uniform(0.0005, 0.03, size=(h, w)).astype(np.float32)
+    depth[rng.random((h, w)) < 0.1] = 0.0
+    mv = np.zeros((h, w, 2), np.float16)
+    m = rng.random((h, w)) < 0.1
+    mv[m] = (rng.uniform(-2.0, 2.0, size=(int(m.sum()), 2)) / np.array([w, h])).astype(np.float16)
+    hist = np.concatenate([rng.uniform(0, 1, (h, w, 1)), rng.uniform(-0.5, 0.5, (h, w, 2)), np.ones((h, w, 1))], -1).astype(np.float16)
+    # reproj = T*S*VP_prev*invVP_cur for a slightly moved camera: near-identity in UV space
+    reproj = np.array([[0.5, 0, 0, 0], [0, 0.5, 0, 0], [0.3, -0.2, 1, 0], [0.5 + 0.4 / w, 0.5 - 0.3 / h, 0, 1]], np.float32)
+    return hdr, depth, mv.view(np.uint16), hist.view(np.uint16), reproj
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (1280, 720), (333, 177)])
+@pytest.mark.parametrize("quality", [0, 1, 2])
+def test_taa_resolve_bit_exact(cuda, oracle, w, h, quality):
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w * 3 + h + quality)
+    hdr, depth, mv, hist, reproj = _taa_inputs(rng, w, h)
+    hdr_t = harness.to_dev(hdr)
+    oc = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    oh = harness.new_rgba16f(w, h)
+    # first frame: no history
+    ref_c, ref_h = oracle.taa_resolve(hdr, depth, mv, None, reproj, quality)
+    harness.taa_resolve(hdr_t, None, None, None, None, quality, oc, oh)
+    assert np.array_equal(harness.to_host(oc, np.uint32), ref_c)
+    assert np.array_equal(harness.to_host(oh, np.uint16), ref_h)
+    # steady state
+    ref_c, ref_h = oracle.taa_resolve(hdr, depth, mv, hist, reproj, quality)
+    harness.taa_resolve(hdr_t, harness.to_dev(depth), harness.to_dev(mv.reshape(h, w, 2)).view(torch.int32).reshape(h, w),
+                        harness.to_dev(hist), reproj, quality, oc, oh)
+    assert np.array_equal(harness.to_host(oc, np.uint32), ref_c)
+    assert np.array_equal(harness.to_host(oh, np.uint16), ref_h)
+
+
+def test_error_reporting(cuda):
+    from granite_b200 import capi
+
+    bad = capi.GrbImage(None, 0, 0, 0, 0)
+    rc = capi.lib().grb_bloom_upsample(C.byref(bad), C.byref(bad), capi.rows(), capi.stream_ptr())
+    assert rc == -2
+    assert b"R16G16B16A16_SFLOAT" in capi.lib().grb_last_error_string()
