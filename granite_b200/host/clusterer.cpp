@@ -1,0 +1,294 @@
+#include "clusterer.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+namespace Granite
+{
+LightClusterer::LightClusterer() = default;
+
+LightClusterer::~LightClusterer()
+{
+	if (staging)
+		cudaFreeHost(staging);
+}
+
+void LightClusterer::set_resolution(unsigned x, unsigned y, unsigned z)
+{
+	// the binning kernel works on 8x4-tile blocks (clusterer.cpp:1516-1517 asserts & 7)
+	if ((x & 7) || (y & 7) || (z & 63))
+		throw std::logic_error("LightClusterer: resolution must be a multiple of (8, 8, 64).");
+	resolution_x = x;
+	resolution_y = y;
+	resolution_z = z;
+}
+
+size_t LightClusterer::transforms_offset_model() const { return sizeof(PositionalFragmentInfo) * ClustererMaxLightsBindless; }
+size_t LightClusterer::transforms_offset_type_mask() const { return transforms_offset_model() + sizeof(mat_affine) * ClustererMaxLightsBindless; }
+size_t LightClusterer::transforms_size() const { return transforms_offset_type_mask() + sizeof(uint32_t) * (ClustererMaxLightsBindless / 32); }
+
+void LightClusterer::add_render_passes(RenderGraph &graph)
+{
+	add_render_passes_bindless(graph);
+}
+
+// renderer/lights/clusterer.cpp:1575-1613
+void LightClusterer::add_render_passes_bindless(RenderGraph &graph)
+{
+	BufferInfo att;
+	att.usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;
+
+	auto &pass = graph.add_pass("clustering-bindless", RENDER_GRAPH_QUEUE_COMPUTE_BIT);
+	att.size = resolution_x * resolution_y * (ClustererMaxLightsBindless / 8);
+	res_bitmask = &pass.add_storage_output("cluster-bitmask", att);
+	att.size = resolution_z * sizeof(ivec2);
+	res_range = &pass.add_storage_output("cluster-range", att);
+	att.size = transforms_size();
+	res_transforms = &pass.add_transfer_output("cluster-transforms", att);
+	att.size = sizeof(vec4) * 4 * 8 * ClustererMaxLightsBindless;
+	res_cull = &pass.add_storage_output("cluster-cull-setup", att);
+	att.size = sizeof(vec4) * 6 * ClustererMaxLightsBindless;
+	res_spots = &pass.add_storage_output("cluster-transformed-spot", att);
+	// per-light Z slice ranges: a transient host-visible buffer in the reference
+	// (clusterer.cpp:1280-1284), a persistent graph buffer here
+	att.size = sizeof(uvec2) * ClustererMaxLightsBindless;
+	res_zranges = &pass.add_transfer_output("cluster-light-z-ranges", att);
+
+	pass.set_build_render_pass([this](Vulkan::CommandBuffer &cmd) { build_cluster_bindless_gpu(cmd); });
+}
+
+// renderer/lights/clusterer.cpp:83-93
+void LightClusterer::setup_render_pass_dependencies(RenderGraph &, RenderPass &target)
+{
+	target.add_storage_read_only_input("cluster-bitmask");
+	target.add_storage_read_only_input("cluster-range");
+	target.add_storage_read_only_input("cluster-transforms");
+}
+
+// renderer/lights/clusterer.cpp:107-116
+void LightClusterer::setup_render_pass_resources(RenderGraph &graph)
+{
+	bitmask_buffer = graph.maybe_get_physical_buffer_resource(res_bitmask);
+	range_buffer = graph.maybe_get_physical_buffer_resource(res_range);
+	transforms_buffer = graph.maybe_get_physical_buffer_resource(res_transforms);
+	cull_buffer = graph.maybe_get_physical_buffer_resource(res_cull);
+	spot_buffer = graph.maybe_get_physical_buffer_resource(res_spots);
+	zrange_buffer = graph.maybe_get_physical_buffer_resource(res_zranges);
+}
+
+GrbClusterBuffers LightClusterer::get_cluster_buffers() const
+{
+	GrbClusterBuffers b = {};
+	if (!transforms_buffer || !bitmask_buffer || !range_buffer || !cull_buffer || !spot_buffer || !zrange_buffer)
+		return b;
+	auto *base = transforms_buffer->get<uint8_t>();
+	b.lights = reinterpret_cast<const GrbPositionalLight *>(base);
+	b.model = reinterpret_cast<const float *>(base + transforms_offset_model());
+	b.type_mask = reinterpret_cast<const uint32_t *>(base + transforms_offset_type_mask());
+	b.z_ranges = zrange_buffer->get<uint32_t>();
+	b.transformed_spots = spot_buffer->get<float>();
+	b.cull_setup = cull_buffer->get<float>();
+	b.bitmask = bitmask_buffer->get<uint32_t>();
+	b.cluster_range = range_buffer->get<uint32_t>();
+	b.resolution_z = (int32_t)resolution_z;
+	return b;
+}
+
+// renderer/lights/clusterer.cpp:700-703
+float LightClusterer::get_z_slice_extent(const RenderContext &ctx) const
+{
+	return min(0.5f, ctx.get_render_parameters().z_far / float(resolution_z));
+}
+
+// renderer/lights/clusterer.cpp:1265-1275
+uvec2 LightClusterer::compute_uint_range(vec2 range) const
+{
+	float extent = get_z_slice_extent(*context);
+	range.x = range.x / extent;
+	range.y = range.y / extent;
+	if (range.y < 0.0f)
+		return uvec2(0xffffffffu, 0u);
+	range.x = max(range.x, 0.0f);
+	uvec2 urange((uint32_t)range.x, (uint32_t)range.y);
+	urange.y = std::min<uint32_t>(urange.y, resolution_z - 1);
+	return urange;
+}
+
+void LightClusterer::refresh(const RenderContext &ctx)
+{
+	context = &ctx;
+	refresh_bindless_prepare(ctx);
+}
+
+// renderer/threaded_scene.cpp:137-150 (front-to-back order), clusterer.cpp:656-698 (scan),
+// :803-826 (parameters), :1322-1346 (per-light Z ranges).
+void LightClusterer::refresh_bindless_prepare(const RenderContext &ctx)
+{
+	const auto &rp = ctx.get_render_parameters();
+	lights.clear();
+	model.clear();
+	volume_index_range.clear();
+	type_mask.assign(ClustererMaxLightsBindless / 32, 0u);
+
+	// Sort key: view depth of the light centre.  (The reference's key reads one vec4 past the
+	// end of the node transform -- SURVEY.md §7 -- the intended key is this one.)  stable_sort
+	// keeps input order on ties so the light order, hence bit positions and fp accumulation
+	// order, is deterministic.
+	std::vector<unsigned> order;
+	if (scene_lights)
+	{
+		order.resize(scene_lights->size());
+		std::iota(order.begin(), order.end(), 0u);
+		std::vector<float> keys(order.size());
+		for (size_t i = 0; i < keys.size(); i++)
+			keys[i] = dot((*scene_lights)[i].transform.get_translation(), rp.camera_front);
+		std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return keys[a] < keys[b]; });
+	}
+
+	unsigned index = 0;
+	for (unsigned src : order)
+	{
+		if (index >= ClustererMaxLightsBindless)
+			break;
+		auto &l = (*scene_lights)[src];
+		if (l.light->get_type() == PositionalLight::Type::Spot)
+		{
+			auto &spot = static_cast<SpotLight &>(*l.light);
+			lights.push_back(spot.get_shader_info(l.transform));
+			model.push_back(spot.build_model_matrix(l.transform));
+		}
+		else
+		{
+			auto &point = static_cast<PointLight &>(*l.light);
+			lights.push_back(point.get_shader_info(l.transform));
+			// set_point_model_transform (clusterer.cpp:647-650): row 0 = (position, radius)
+			mat_affine m(vec4(0.0f), vec4(0.0f), vec4(0.0f));
+			m[0] = vec4(lights.back().position, 1.0f / lights.back().inv_radius);
+			model.push_back(m);
+			type_mask[index >> 5] |= 1u << (index & 31u);
+		}
+		index++;
+	}
+
+	std::memset(&parameters, 0, sizeof(parameters));
+	parameters.num_lights = (int32_t)index;
+	parameters.num_lights_32 = (int32_t)((index + 31) / 32);
+	float z_slice_size = get_z_slice_extent(ctx);
+	parameters.clip_scale[0] = rp.projection[0][0];
+	parameters.clip_scale[1] = -rp.projection[1][1];
+	parameters.clip_scale[2] = rp.inv_projection[0][0];
+	parameters.clip_scale[3] = -rp.inv_projection[1][1];
+	mat4 transform = translate(vec3(0.5f, 0.5f, 0.0f)) * scale(vec3(0.5f, 0.5f, 1.0f)) * rp.view_projection;
+	std::memcpy(parameters.transform, transform.data(), sizeof(parameters.transform));
+	for (int i = 0; i < 3; i++)
+	{
+		parameters.camera_front[i] = rp.camera_front[i];
+		parameters.camera_base[i] = rp.camera_position[i];
+	}
+	parameters.xy_scale[0] = float(resolution_x);
+	parameters.xy_scale[1] = float(resolution_y);
+	parameters.resolution_xy[0] = (int32_t)resolution_x;
+	parameters.resolution_xy[1] = (int32_t)resolution_y;
+	parameters.inv_resolution_xy[0] = 1.0f / float(resolution_x);
+	parameters.inv_resolution_xy[1] = 1.0f / float(resolution_y);
+	parameters.z_scale = 1.0f / z_slice_size;
+	parameters.z_max_index = (int32_t)resolution_z - 1;
+
+	// update_bindless_range_buffer_gpu: per-light slice range on the host
+	volume_index_range.resize(index);
+	for (unsigned i = 0; i < index; i++)
+	{
+		vec2 range;
+		if (type_mask[i >> 5] & (1u << (i & 31)))
+			range = point_light_z_range(ctx, lights[i].position, 1.0f / lights[i].inv_radius);
+		else
+			range = spot_light_z_range(ctx, model[i]);
+		volume_index_range[i] = compute_uint_range(range);
+	}
+	// still run the Z-range kernel with one empty entry so the range buffer is cleared
+	if (volume_index_range.empty())
+		volume_index_range.push_back(uvec2(~0u, 0u));
+}
+
+// renderer/lights/clusterer.cpp:1564-1573: update_bindless_data (upload), then the kernels.
+void LightClusterer::build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd)
+{
+	if (!context || !transforms_buffer)
+	{
+		Vulkan::log_error("LightClusterer: refresh() / setup_render_pass_resources() must run before the clustering pass.\n");
+		return;
+	}
+	const unsigned n = (unsigned)parameters.num_lights;
+	const size_t lights_bytes = n * sizeof(PositionalFragmentInfo);
+	const size_t model_bytes = n * sizeof(mat_affine);
+	const size_t mask_bytes = sizeof(uint32_t) * (ClustererMaxLightsBindless / 32);
+	const size_t range_bytes = volume_index_range.size() * sizeof(uvec2);
+	const size_t need = lights_bytes + model_bytes + mask_bytes + range_bytes;
+	auto stream = reinterpret_cast<cudaStream_t>(cmd.get_stream());
+	// Two pinned staging slots used alternately; a slot is reused only after the copies that
+	// read it have completed (its event), so frames pipeline without a host-device sync.
+	const size_t slot_size = ClustererMaxLightsBindless * (sizeof(PositionalFragmentInfo) + sizeof(mat_affine) + sizeof(uvec2)) + mask_bytes;
+	if (!staging)
+	{
+		if (!Vulkan::cuda_ok(cudaMallocHost(&staging, slot_size * 2), "cudaMallocHost"))
+		{
+			staging = nullptr;
+			return;
+		}
+		staging_size = slot_size * 2;
+		for (auto &e : staging_events)
+		{
+			cudaEvent_t ev;
+			cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+			e = ev;
+		}
+	}
+	if (need > slot_size)
+		return;
+	const unsigned slot = staging_slot;
+	staging_slot ^= 1u;
+	if (staging_event_pending[slot])
+		cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(staging_events[slot]));
+	auto *s = static_cast<uint8_t *>(staging) + slot * slot_size;
+	std::memcpy(s, lights.data(), lights_bytes);
+	std::memcpy(s + lights_bytes, model.data(), model_bytes);
+	std::memcpy(s + lights_bytes + model_bytes, type_mask.data(), mask_bytes);
+	std::memcpy(s + lights_bytes + model_bytes + mask_bytes, volume_index_range.data(), range_bytes);
+
+	auto *base = transforms_buffer->get<uint8_t>();
+	if (lights_bytes)
+	{
+		cudaMemcpyAsync(base, s, lights_bytes, cudaMemcpyHostToDevice, stream);
+		cudaMemcpyAsync(base + transforms_offset_model(), s + lights_bytes, model_bytes, cudaMemcpyHostToDevice, stream);
+	}
+	cudaMemcpyAsync(base + transforms_offset_type_mask(), s + lights_bytes + model_bytes, mask_bytes, cudaMemcpyHostToDevice, stream);
+	cudaMemcpyAsync(zrange_buffer->get_device_pointer(), s + lights_bytes + model_bytes + mask_bytes, range_bytes, cudaMemcpyHostToDevice, stream);
+	cudaEventRecord(reinterpret_cast<cudaEvent_t>(staging_events[slot]), stream);
+	staging_event_pending[slot] = true;
+
+	const auto &rp = context->get_render_parameters();
+	GrbCamera cam = {};
+	std::memcpy(cam.view, rp.view.data(), 64);
+	std::memcpy(cam.view_projection, rp.view_projection.data(), 64);
+	std::memcpy(cam.inv_view_projection, rp.inv_view_projection.data(), 64);
+	for (int i = 0; i < 3; i++)
+	{
+		cam.camera_position[i] = rp.camera_position[i];
+		cam.camera_front[i] = rp.camera_front[i];
+	}
+	cam.z_near = rp.z_near;
+	cam.z_far = rp.z_far;
+	GrbClusterBuffers buf = get_cluster_buffers();
+
+	// update_bindless_mask_buffer_gpu: K1 -> K2 -> K3 (stream order replaces the barriers)
+	cmd.check(grb_cluster_spot_transform(&cam, &parameters, &buf, cmd.get_stream_handle()), "grb_cluster_spot_transform");
+	cmd.check(grb_cluster_cull_setup(&cam, &parameters, &buf, cmd.get_stream_handle()), "grb_cluster_cull_setup");
+	cmd.check(grb_cluster_binning(&parameters, &buf, cmd.get_stream_handle()), "grb_cluster_binning");
+	// update_bindless_range_buffer_gpu: K4
+	cmd.check(grb_cluster_z_range(&buf, (int32_t)volume_index_range.size(), cmd.get_stream_handle()), "grb_cluster_z_range");
+}
+} // namespace Granite

@@ -1,0 +1,98 @@
+// clusterer.hpp -- LightClusterer for the bindless path (renderer/lights/clusterer.hpp:38-107):
+// gathers the visible positional lights front-to-back, fills the parameter/transform blocks,
+// declares the "clustering-bindless" pass and, in its callback, uploads the per-frame light
+// data and launches the four clusterer kernels through the C ABI.  Shadow-map rendering,
+// decals, volumetrics of the reference's class are outside the hot path.
+#pragma once
+
+#include <memory>
+#include <vector>
+
+#include "lights.hpp"
+#include "render_graph.hpp"
+
+namespace Granite
+{
+// math/render_parameters.hpp:146-148
+enum
+{
+	ClustererMaxLightsBindless = 4096
+};
+
+struct PositionalLightInfo
+{
+	PositionalLight *light;
+	mat_affine transform; // node world transform
+};
+using PositionalLightList = std::vector<PositionalLightInfo>;
+
+class LightClusterer
+{
+public:
+	LightClusterer();
+	~LightClusterer();
+
+	void set_resolution(unsigned x, unsigned y, unsigned z);
+	void set_enable_clustering(bool enable) { enable_clustering = enable; }
+	void set_max_spot_lights(unsigned) {}
+	void set_max_point_lights(unsigned) {}
+
+	// The scene's positional lights (replaces the ECS gather in renderer/threaded_scene.cpp:112-153).
+	void set_scene_lights(const PositionalLightList *lights) { scene_lights = lights; }
+
+	// RenderPassCreator surface
+	void add_render_passes(RenderGraph &graph);
+	void setup_render_pass_dependencies(RenderGraph &graph, RenderPass &target);
+	void setup_render_pass_resources(RenderGraph &graph);
+	void set_base_render_context(const RenderContext *context_) { context = context_; }
+
+	// PerFrameRefreshable: sort + scan lights, fill parameters (clusterer.cpp:1133-1176, 781-889).
+	void refresh(const RenderContext &context);
+
+	const GrbClusterParameters &get_cluster_parameters_bindless() const { return parameters; }
+	const Vulkan::Buffer *get_cluster_transform_buffer() const { return transforms_buffer; }
+	const Vulkan::Buffer *get_cluster_bitmask_buffer() const { return bitmask_buffer; }
+	const Vulkan::Buffer *get_cluster_range_buffer() const { return range_buffer; }
+	// The C-ABI view of the graph-owned cluster buffers (valid after setup_render_pass_resources).
+	GrbClusterBuffers get_cluster_buffers() const;
+	unsigned get_active_light_count() const { return (unsigned)parameters.num_lights; }
+
+	// CPU copies of what is uploaded each frame (exposed for the parity tests).
+	const std::vector<PositionalFragmentInfo> &get_light_records() const { return lights; }
+	const std::vector<mat_affine> &get_model_transforms() const { return model; }
+	const std::vector<uint32_t> &get_type_mask() const { return type_mask; }
+	const std::vector<uvec2> &get_z_ranges() const { return volume_index_range; }
+
+private:
+	const RenderContext *context = nullptr;
+	const PositionalLightList *scene_lights = nullptr;
+	unsigned resolution_x = 64, resolution_y = 32, resolution_z = 16;
+	bool enable_clustering = true;
+
+	GrbClusterParameters parameters = {};
+	std::vector<PositionalFragmentInfo> lights;
+	std::vector<mat_affine> model;
+	std::vector<uint32_t> type_mask;
+	std::vector<uvec2> volume_index_range;
+	// pinned staging copy of {lights, model, type_mask, z ranges} for the async upload
+	void *staging = nullptr;
+	size_t staging_size = 0;
+	void *staging_events[2] = { nullptr, nullptr };
+	bool staging_event_pending[2] = { false, false };
+	unsigned staging_slot = 0;
+
+	RenderBufferResource *res_bitmask = nullptr, *res_range = nullptr, *res_transforms = nullptr;
+	RenderBufferResource *res_cull = nullptr, *res_spots = nullptr, *res_zranges = nullptr;
+	const Vulkan::Buffer *bitmask_buffer = nullptr, *range_buffer = nullptr, *transforms_buffer = nullptr;
+	const Vulkan::Buffer *cull_buffer = nullptr, *spot_buffer = nullptr, *zrange_buffer = nullptr;
+
+	float get_z_slice_extent(const RenderContext &ctx) const;
+	uvec2 compute_uint_range(vec2 range) const;
+	void refresh_bindless_prepare(const RenderContext &ctx);
+	void build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd);
+	void add_render_passes_bindless(RenderGraph &graph);
+	size_t transforms_offset_model() const;
+	size_t transforms_offset_type_mask() const;
+	size_t transforms_size() const;
+};
+} // namespace Granite

@@ -1,0 +1,208 @@
+#include "cuda_backend.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <stdexcept>
+
+namespace Granite
+{
+namespace CUDA
+{
+void log_error(const char *fmt, ...)
+{
+	va_list va;
+	va_start(va, fmt);
+	std::fprintf(stderr, "[granite_b200 ERROR] ");
+	std::vfprintf(stderr, fmt, va);
+	va_end(va);
+}
+
+void log_info(const char *fmt, ...)
+{
+	va_list va;
+	va_start(va, fmt);
+	std::fprintf(stderr, "[granite_b200] ");
+	std::vfprintf(stderr, fmt, va);
+	va_end(va);
+}
+
+bool cuda_ok(int err, const char *what)
+{
+	if (err == cudaSuccess)
+		return true;
+	log_error("%s: %s\n", what, cudaGetErrorString((cudaError_t)err));
+	return false;
+}
+
+Device::Device(int cuda_device_index, Stream stream_) : index(cuda_device_index), stream(stream_)
+{
+	if (!cuda_ok(cudaSetDevice(index), "cudaSetDevice"))
+		throw std::runtime_error("granite_b200: cannot select the CUDA device");
+	if (!stream)
+	{
+		cudaStream_t s;
+		if (!cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate"))
+			throw std::runtime_error("granite_b200: cannot create a stream");
+		stream = s;
+		owns_stream = true;
+	}
+	if (grb_init() != GRB_OK)
+		throw std::runtime_error(std::string("granite_b200: grb_init failed: ") + grb_last_error_string());
+}
+
+Device::~Device()
+{
+	cudaSetDevice(index);
+	cudaStreamSynchronize(stream);
+	for (auto &iv : intervals)
+	{
+		event_pool.push_back(iv.begin);
+		event_pool.push_back(iv.end);
+	}
+	for (auto e : event_pool)
+		cudaEventDestroy(e);
+	if (owns_stream)
+		cudaStreamDestroy(stream);
+}
+
+void *Device::allocate(size_t size)
+{
+	void *p = nullptr;
+	if (size == 0)
+		size = 16;
+	if (!cuda_ok(cudaMalloc(&p, size), "cudaMalloc"))
+		throw std::runtime_error("granite_b200: out of device memory");
+	// zero-initialised like the graph's buffers (render_graph.cpp:2587); ordered on the graph stream
+	cuda_ok(cudaMemsetAsync(p, 0, size, stream), "cudaMemsetAsync");
+	return p;
+}
+
+void Device::free(void *ptr)
+{
+	if (ptr)
+	{
+		cudaStreamSynchronize(stream);
+		cudaFree(ptr);
+	}
+}
+
+void Device::wait_idle()
+{
+	cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+}
+
+ImageHandle Device::create_image(const ImageCreateInfo &info)
+{
+	return std::make_shared<Image>(*this, info);
+}
+
+BufferHandle Device::create_buffer(const BufferCreateInfo &info)
+{
+	return std::make_shared<Buffer>(*this, info);
+}
+
+Event Device::request_event()
+{
+	std::lock_guard<std::mutex> hold(lock);
+	if (!event_pool.empty())
+	{
+		Event e = event_pool.back();
+		event_pool.pop_back();
+		return e;
+	}
+	cudaEvent_t e;
+	cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
+	return e;
+}
+
+void Device::record_event(Event e)
+{
+	cuda_ok(cudaEventRecord(e, stream), "cudaEventRecord");
+}
+
+void Device::register_time_interval(const std::string &tag, Event begin, Event end)
+{
+	std::lock_guard<std::mutex> hold(lock);
+	intervals.push_back({ tag, begin, end });
+}
+
+std::vector<std::pair<std::string, float>> Device::collect_time_intervals()
+{
+	std::vector<TimeInterval> local;
+	{
+		std::lock_guard<std::mutex> hold(lock);
+		local.swap(intervals);
+	}
+	std::vector<std::pair<std::string, float>> out;
+	for (auto &iv : local)
+	{
+		float ms = 0.0f;
+		cudaEventSynchronize(iv.end);
+		cudaEventElapsedTime(&ms, iv.begin, iv.end);
+		out.emplace_back(iv.tag, ms);
+		std::lock_guard<std::mutex> hold(lock);
+		event_pool.push_back(iv.begin);
+		event_pool.push_back(iv.end);
+	}
+	return out;
+}
+
+Image::Image(Device &device_, const ImageCreateInfo &info_) : device(device_), info(info_)
+{
+	unsigned texel = format_texel_size(info.format);
+	if (!texel || !info.width || !info.height)
+		throw std::logic_error("granite_b200: unsupported image format or empty extent");
+	row_pitch = info.width * texel;
+	size = (size_t)row_pitch * info.height;
+	data = device.allocate(size);
+}
+
+Image::~Image()
+{
+	device.free(data);
+}
+
+Buffer::Buffer(Device &device_, const BufferCreateInfo &info_) : device(device_), info(info_)
+{
+	data = device.allocate(info.size);
+}
+
+Buffer::~Buffer()
+{
+	device.free(data);
+}
+
+GrbImage ImageView::as_grb() const
+{
+	GrbImage g;
+	g.data = image->get_device_pointer();
+	g.width = (int32_t)image->get_width();
+	g.height = (int32_t)image->get_height();
+	g.row_pitch = (int32_t)image->get_row_pitch();
+	g.format = image->get_format();
+	return g;
+}
+
+GrbImage ImageView::as_grb_unorm() const
+{
+	GrbImage g = as_grb();
+	if (g.format == VK_FORMAT_R8G8B8A8_SRGB)
+		g.format = VK_FORMAT_R8G8B8A8_UNORM;
+	return g;
+}
+
+bool CommandBuffer::check(int32_t result, const char *what)
+{
+	if (result == GRB_OK)
+		return true;
+	errors++;
+	log_error("%s failed (%d): %s\n", what, result, grb_last_error_string());
+	return false;
+}
+
+void CommandBuffer::begin_region(const char *) {}
+void CommandBuffer::end_region() {}
+} // namespace CUDA
+} // namespace Granite

@@ -1,0 +1,586 @@
+#include "render_graph.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+
+namespace Granite
+{
+// ---------------------------------------------------------------- RenderPassInterface defaults
+bool RenderPassInterface::get_clear_depth_stencil(VkClearDepthStencilValue *value) const
+{
+	if (value)
+		*value = { 1.0f, 0u };
+	return true;
+}
+
+bool RenderPassInterface::get_clear_color(unsigned, VkClearColorValue *value) const
+{
+	if (value)
+		*value = {};
+	return true;
+}
+
+void RenderPassInterface::setup_dependencies(RenderPass &, RenderGraph &) {}
+void RenderPassInterface::setup(Vulkan::Device &) {}
+void RenderPassInterface::enqueue_prepare_render_pass(RenderGraph &, TaskComposer &) {}
+void RenderPassInterface::build_render_pass(Vulkan::CommandBuffer &) {}
+void RenderPassInterface::build_render_pass_separate_layer(Vulkan::CommandBuffer &, unsigned) {}
+
+// ---------------------------------------------------------------- RenderPass declarators
+bool RenderPass::get_clear_color(unsigned attachment, VkClearColorValue *value) const
+{
+	if (render_pass_handle)
+		return render_pass_handle->get_clear_color(attachment, value);
+	if (get_clear_color_cb)
+		return get_clear_color_cb(attachment, value);
+	return false;
+}
+
+bool RenderPass::get_clear_depth_stencil(VkClearDepthStencilValue *value) const
+{
+	if (render_pass_handle)
+		return render_pass_handle->get_clear_depth_stencil(value);
+	if (get_clear_depth_stencil_cb)
+		return get_clear_depth_stencil_cb(value);
+	return false;
+}
+
+RenderTextureResource &RenderPass::set_depth_stencil_input(const std::string &name)
+{
+	auto &res = graph.get_or_create_texture(name);
+	res.read_in_pass(index);
+	depth_stencil_input = &res;
+	reads.push_back(&res);
+	return res;
+}
+
+RenderTextureResource &RenderPass::set_depth_stencil_output(const std::string &name, const AttachmentInfo &info)
+{
+	auto &res = graph.get_or_create_texture(name);
+	res.written_in_pass(index);
+	res.set_attachment_info(info);
+	depth_stencil_output = &res;
+	writes.push_back(&res);
+	return res;
+}
+
+RenderTextureResource &RenderPass::add_color_output(const std::string &name, const AttachmentInfo &info, const std::string &input)
+{
+	auto &res = graph.get_or_create_texture(name);
+	res.written_in_pass(index);
+	res.set_attachment_info(info);
+	color_outputs.push_back(&res);
+	writes.push_back(&res);
+	if (!input.empty())
+	{
+		auto &input_res = graph.get_or_create_texture(input);
+		input_res.read_in_pass(index);
+		color_inputs.push_back(&input_res);
+		reads.push_back(&input_res);
+		rmw_aliases.emplace_back(&res, &input_res);
+	}
+	else
+		color_inputs.push_back(nullptr);
+	return res;
+}
+
+RenderTextureResource &RenderPass::add_attachment_input(const std::string &name)
+{
+	auto &res = graph.get_or_create_texture(name);
+	res.read_in_pass(index);
+	attachments_inputs.push_back(&res);
+	reads.push_back(&res);
+	return res;
+}
+
+RenderTextureResource &RenderPass::add_history_input(const std::string &name)
+{
+	auto &res = graph.get_or_create_texture(name);
+	// History inputs are not used in any particular pass, but next frame.
+	history_inputs.push_back(&res);
+	return res;
+}
+
+RenderTextureResource &RenderPass::add_texture_input(const std::string &name, VkPipelineStageFlags2)
+{
+	auto &res = graph.get_or_create_texture(name);
+	res.read_in_pass(index);
+	texture_inputs.push_back(&res);
+	reads.push_back(&res);
+	return res;
+}
+
+RenderBufferResource &RenderPass::add_uniform_input(const std::string &name, VkPipelineStageFlags2)
+{
+	auto &res = graph.get_or_create_buffer(name);
+	res.read_in_pass(index);
+	buffer_inputs.push_back(&res);
+	reads.push_back(&res);
+	return res;
+}
+
+RenderBufferResource &RenderPass::add_storage_read_only_input(const std::string &name, VkPipelineStageFlags2 stages)
+{
+	return add_uniform_input(name, stages);
+}
+
+RenderBufferResource &RenderPass::add_storage_output(const std::string &name, const BufferInfo &info, const std::string &input)
+{
+	auto &res = graph.get_or_create_buffer(name);
+	res.set_buffer_info(info);
+	res.written_in_pass(index);
+	storage_outputs.push_back(&res);
+	writes.push_back(&res);
+	if (!input.empty())
+	{
+		auto &input_res = graph.get_or_create_buffer(input);
+		input_res.read_in_pass(index);
+		reads.push_back(&input_res);
+		rmw_aliases.emplace_back(&res, &input_res);
+	}
+	return res;
+}
+
+RenderBufferResource &RenderPass::add_transfer_output(const std::string &name, const BufferInfo &info)
+{
+	auto &res = graph.get_or_create_buffer(name);
+	res.set_buffer_info(info);
+	res.written_in_pass(index);
+	transfer_outputs.push_back(&res);
+	writes.push_back(&res);
+	return res;
+}
+
+RenderTextureResource &RenderPass::add_storage_texture_output(const std::string &name, const AttachmentInfo &info, const std::string &input)
+{
+	auto &res = graph.get_or_create_texture(name);
+	res.written_in_pass(index);
+	res.set_attachment_info(info);
+	storage_texture_outputs.push_back(&res);
+	writes.push_back(&res);
+	if (!input.empty())
+	{
+		auto &input_res = graph.get_or_create_texture(input);
+		input_res.read_in_pass(index);
+		reads.push_back(&input_res);
+		rmw_aliases.emplace_back(&res, &input_res);
+	}
+	return res;
+}
+
+void RenderPass::add_fake_resource_write_alias(const std::string &from, const std::string &to)
+{
+	auto &from_res = graph.get_or_create_texture(from);
+	auto &to_res = graph.get_or_create_texture(to);
+	to_res.set_attachment_info(from_res.get_attachment_info());
+	to_res.written_in_pass(index);
+	from_res.read_in_pass(index);
+	reads.push_back(&from_res);
+	writes.push_back(&to_res);
+	rmw_aliases.emplace_back(&to_res, &from_res);
+}
+
+// ---------------------------------------------------------------- RenderGraph
+Vulkan::Device &RenderGraph::get_device()
+{
+	if (!device)
+		throw std::logic_error("RenderGraph: no device set.");
+	return *device;
+}
+
+RenderTextureResource &RenderGraph::get_or_create_texture(const std::string &name)
+{
+	auto itr = resource_to_index.find(name);
+	if (itr != resource_to_index.end())
+	{
+		if (resources[itr->second]->get_type() != RenderResource::Type::Texture)
+			throw std::logic_error("Resource '" + name + "' is not a texture.");
+		return static_cast<RenderTextureResource &>(*resources[itr->second]);
+	}
+	unsigned index = (unsigned)resources.size();
+	resources.emplace_back(new RenderTextureResource(index));
+	resources.back()->set_name(name);
+	resource_to_index[name] = index;
+	return static_cast<RenderTextureResource &>(*resources.back());
+}
+
+RenderBufferResource &RenderGraph::get_or_create_buffer(const std::string &name)
+{
+	auto itr = resource_to_index.find(name);
+	if (itr != resource_to_index.end())
+	{
+		if (resources[itr->second]->get_type() != RenderResource::Type::Buffer)
+			throw std::logic_error("Resource '" + name + "' is not a buffer.");
+		return static_cast<RenderBufferResource &>(*resources[itr->second]);
+	}
+	unsigned index = (unsigned)resources.size();
+	resources.emplace_back(new RenderBufferResource(index));
+	resources.back()->set_name(name);
+	resource_to_index[name] = index;
+	return static_cast<RenderBufferResource &>(*resources.back());
+}
+
+RenderTextureResource &RenderGraph::get_texture_resource(const std::string &name) { return get_or_create_texture(name); }
+RenderBufferResource &RenderGraph::get_buffer_resource(const std::string &name) { return get_or_create_buffer(name); }
+
+RenderPass &RenderGraph::add_pass(const std::string &name, RenderGraphQueueFlagBits queue)
+{
+	auto itr = pass_to_index.find(name);
+	if (itr != pass_to_index.end())
+		return *passes[itr->second];
+	unsigned index = (unsigned)passes.size();
+	passes.emplace_back(new RenderPass(*this, index, queue));
+	passes.back()->set_name(name);
+	pass_to_index[name] = index;
+	return *passes.back();
+}
+
+RenderPass *RenderGraph::find_pass(const std::string &name)
+{
+	auto itr = pass_to_index.find(name);
+	return itr != pass_to_index.end() ? passes[itr->second].get() : nullptr;
+}
+
+void RenderGraph::set_backbuffer_source(const std::string &name) { backbuffer_source = name; }
+
+void RenderGraph::reset()
+{
+	passes.clear();
+	resources.clear();
+	pass_to_index.clear();
+	resource_to_index.clear();
+	pass_stack.clear();
+	physical_dimensions.clear();
+	physical_has_history.clear();
+	physical_attachments.clear();
+	physical_history_attachments.clear();
+	physical_history_spare.clear();
+	physical_buffers.clear();
+	backbuffer_physical = RenderResource::Unused;
+	baked = false;
+}
+
+void RenderGraph::traverse_dependencies(unsigned pass_index, std::vector<uint8_t> &state)
+{
+	// state: 0 = unvisited, 1 = on the stack, 2 = done
+	if (state[pass_index] == 2)
+		return;
+	if (state[pass_index] == 1)
+		throw std::logic_error("Cycle detected in render graph at pass '" + passes[pass_index]->get_name() + "'.");
+	state[pass_index] = 1;
+	auto &pass = *passes[pass_index];
+	for (auto *res : pass.get_all_reads())
+	{
+		if (res->get_write_passes().empty())
+			throw std::logic_error("No pass exists which writes to resource '" + res->get_name() + "'.");
+		// deterministic order: ascending pass index
+		std::vector<unsigned> writers(res->get_write_passes().begin(), res->get_write_passes().end());
+		std::sort(writers.begin(), writers.end());
+		for (unsigned w : writers)
+			if (w != pass_index)
+				traverse_dependencies(w, state);
+	}
+	state[pass_index] = 2;
+	pass_stack.push_back(pass_index);
+}
+
+void RenderGraph::bake()
+{
+	for (auto &pass : passes)
+		pass->setup_dependencies();
+
+	auto itr = resource_to_index.find(backbuffer_source);
+	if (itr == resource_to_index.end())
+		throw std::logic_error("Backbuffer source does not exist.");
+	auto &bb = *resources[itr->second];
+	if (bb.get_write_passes().empty())
+		throw std::logic_error("No pass exists which writes to resource.");
+
+	for (auto &pass : passes)
+	{
+		for (auto &alias : pass->get_write_aliases())
+		{
+			if (alias.first->get_type() != alias.second->get_type())
+				throw std::logic_error("Read-modify-write alias between a texture and a buffer.");
+		}
+		if (pass->get_color_inputs().size() != pass->get_color_outputs().size())
+			throw std::logic_error("Size of color inputs must match color outputs.");
+	}
+
+	pass_stack.clear();
+	std::vector<uint8_t> state(passes.size(), 0);
+	std::vector<unsigned> writers(bb.get_write_passes().begin(), bb.get_write_passes().end());
+	std::sort(writers.begin(), writers.end());
+	for (unsigned w : writers)
+		traverse_dependencies(w, state);
+
+	build_physical_resources();
+	baked = true;
+
+	if (device)
+		for (unsigned p : pass_stack)
+			passes[p]->setup(*device);
+}
+
+ResourceDimensions RenderGraph::get_resource_dimensions(const RenderBufferResource &resource) const
+{
+	ResourceDimensions dim;
+	dim.buffer_info = resource.get_buffer_info();
+	dim.flags = resource.get_buffer_info().flags;
+	dim.name = resource.get_name();
+	return dim;
+}
+
+ResourceDimensions RenderGraph::get_resource_dimensions(const RenderTextureResource &resource) const
+{
+	ResourceDimensions dim;
+	auto &info = resource.get_attachment_info();
+	dim.format = info.format;
+	dim.flags = info.flags;
+	dim.name = resource.get_name();
+	// renderer/render_graph.cpp:3160-3171: every relative size is ceil(parent * scale)
+	switch (info.size_class)
+	{
+	case SizeClass::SwapchainRelative:
+		dim.width = std::max(unsigned(std::ceil(info.size_x * swapchain_dimensions.width)), 1u);
+		dim.height = std::max(unsigned(std::ceil(info.size_y * swapchain_dimensions.height)), 1u);
+		break;
+	case SizeClass::Absolute:
+		dim.width = std::max(unsigned(info.size_x), 1u);
+		dim.height = std::max(unsigned(info.size_y), 1u);
+		break;
+	case SizeClass::InputRelative:
+	{
+		auto itr = resource_to_index.find(info.size_relative_name);
+		if (itr == resource_to_index.end())
+			throw std::logic_error("Resource does not exist.");
+		auto &input = static_cast<const RenderTextureResource &>(*resources[itr->second]);
+		auto input_dim = get_resource_dimensions(input);
+		dim.width = std::max(unsigned(std::ceil(input_dim.width * info.size_x)), 1u);
+		dim.height = std::max(unsigned(std::ceil(input_dim.height * info.size_y)), 1u);
+		break;
+	}
+	}
+	if (dim.format == VK_FORMAT_UNDEFINED)
+		dim.format = swapchain_dimensions.format;
+	return dim;
+}
+
+void RenderGraph::build_physical_resources()
+{
+	physical_dimensions.clear();
+	physical_has_history.clear();
+	for (auto &res : resources)
+		res->set_physical_index(RenderResource::Unused);
+
+	auto assign = [&](RenderResource *res) {
+		if (res->get_physical_index() != RenderResource::Unused)
+			return;
+		unsigned phys = (unsigned)physical_dimensions.size();
+		if (res->get_type() == RenderResource::Type::Texture)
+			physical_dimensions.push_back(get_resource_dimensions(static_cast<RenderTextureResource &>(*res)));
+		else
+			physical_dimensions.push_back(get_resource_dimensions(static_cast<RenderBufferResource &>(*res)));
+		physical_has_history.push_back(false);
+		res->set_physical_index(phys);
+	};
+
+	for (unsigned p : pass_stack)
+	{
+		auto &pass = *passes[p];
+		for (auto *res : pass.get_all_reads())
+			assign(res);
+		// in-place outputs share the physical resource of the input they modify
+		for (auto &alias : pass.get_write_aliases())
+		{
+			assign(alias.second);
+			if (alias.first->get_physical_index() == RenderResource::Unused)
+				alias.first->set_physical_index(alias.second->get_physical_index());
+			else if (alias.first->get_physical_index() != alias.second->get_physical_index())
+				throw std::logic_error("Cannot alias resources. Index already claimed.");
+		}
+		for (auto *res : pass.get_all_writes())
+			assign(res);
+	}
+	for (unsigned p : pass_stack)
+		for (auto *res : passes[p]->get_history_inputs())
+		{
+			if (res->get_physical_index() == RenderResource::Unused)
+				throw std::logic_error("History input is used, but it was never written to.");
+			physical_has_history[res->get_physical_index()] = true;
+		}
+
+	backbuffer_physical = resources[resource_to_index[backbuffer_source]]->get_physical_index();
+	physical_attachments.clear();
+	physical_attachments.resize(physical_dimensions.size());
+	physical_history_attachments.clear();
+	physical_history_attachments.resize(physical_dimensions.size());
+	physical_buffers.resize(physical_dimensions.size());
+}
+
+void RenderGraph::setup_attachments(Vulkan::Device &dev, Vulkan::ImageView *swapchain)
+{
+	if (!baked)
+		throw std::logic_error("setup_attachments() before bake().");
+	device = &dev;
+	for (unsigned i = 0; i < physical_dimensions.size(); i++)
+	{
+		auto &dim = physical_dimensions[i];
+		if (dim.buffer_info.size != 0)
+		{
+			// persistent across frames (and re-bakes via install_physical_buffers)
+			if (!physical_buffers[i] || physical_buffers[i]->get_create_info().size != dim.buffer_info.size)
+			{
+				Vulkan::BufferCreateInfo info;
+				info.size = (size_t)dim.buffer_info.size;
+				physical_buffers[i] = dev.create_buffer(info);
+			}
+			continue;
+		}
+		if (dim.width == 0)
+			continue;
+		if (i == backbuffer_physical && swapchain)
+		{
+			if (swapchain->get_view_width() != dim.width || swapchain->get_view_height() != dim.height)
+				throw std::logic_error("Swapchain image does not match the backbuffer dimensions.");
+			physical_attachments[i].reset(new Vulkan::ImageView(swapchain->get_image_handle()));
+			continue;
+		}
+		// history <-> current swap, renderer/render_graph.cpp:2706-2710
+		if (physical_has_history[i])
+			std::swap(physical_history_attachments[i], physical_attachments[i]);
+		auto &att = physical_attachments[i];
+		if (!att || att->get_view_width() != dim.width || att->get_view_height() != dim.height || att->get_format() != dim.format)
+		{
+			Vulkan::ImageCreateInfo info;
+			info.width = dim.width;
+			info.height = dim.height;
+			info.format = dim.format;
+			att.reset(new Vulkan::ImageView(dev.create_image(info)));
+		}
+	}
+}
+
+void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &composer)
+{
+	if (!baked)
+		throw std::logic_error("enqueue_render_passes() before bake().");
+	Vulkan::CommandBuffer cmd(dev, dev.get_stream());
+	for (unsigned p : pass_stack)
+	{
+		auto &pass = *passes[p];
+		pass.prepare_render_pass(composer);
+		if (!pass.need_render_pass())
+			continue;
+		Vulkan::Event begin = nullptr, end = nullptr;
+		if (timestamps)
+		{
+			begin = dev.request_event();
+			end = dev.request_event();
+			dev.record_event(begin);
+		}
+		cmd.begin_region(pass.get_name().c_str());
+		pass.build_render_pass(cmd, 0);
+		cmd.end_region();
+		if (timestamps)
+		{
+			dev.record_event(end);
+			dev.register_time_interval(pass.get_name(), begin, end);
+		}
+	}
+	if (cmd.get_error_count())
+		Vulkan::log_error("%u pass callback(s) reported errors this frame.\n", cmd.get_error_count());
+}
+
+Vulkan::ImageView &RenderGraph::get_physical_texture_resource(unsigned index)
+{
+	if (index == RenderResource::Unused || index >= physical_attachments.size() || !physical_attachments[index])
+		throw std::logic_error("Physical texture resource is not available (pass culled, or setup_attachments not called).");
+	return *physical_attachments[index];
+}
+
+Vulkan::ImageView *RenderGraph::get_physical_history_texture_resource(unsigned index)
+{
+	if (index == RenderResource::Unused || index >= physical_history_attachments.size())
+		throw std::logic_error("Invalid physical index.");
+	return physical_history_attachments[index].get();
+}
+
+Vulkan::Buffer &RenderGraph::get_physical_buffer_resource(unsigned index)
+{
+	if (index == RenderResource::Unused || index >= physical_buffers.size() || !physical_buffers[index])
+		throw std::logic_error("Physical buffer resource is not available.");
+	return *physical_buffers[index];
+}
+
+Vulkan::ImageView *RenderGraph::maybe_get_physical_texture_resource(RenderTextureResource *resource)
+{
+	if (resource && resource->get_physical_index() != RenderResource::Unused && physical_attachments[resource->get_physical_index()])
+		return physical_attachments[resource->get_physical_index()].get();
+	return nullptr;
+}
+
+Vulkan::Buffer *RenderGraph::maybe_get_physical_buffer_resource(RenderBufferResource *resource)
+{
+	if (resource && resource->get_physical_index() != RenderResource::Unused && physical_buffers[resource->get_physical_index()])
+		return physical_buffers[resource->get_physical_index()].get();
+	return nullptr;
+}
+
+std::vector<Vulkan::BufferHandle> RenderGraph::consume_physical_buffers() const { return physical_buffers; }
+
+void RenderGraph::install_physical_buffers(std::vector<Vulkan::BufferHandle> buffers)
+{
+	// keep a feed-back buffer only where the new bake has a buffer of the same size at that slot
+	for (size_t i = 0; i < buffers.size() && i < physical_buffers.size(); i++)
+		if (buffers[i] && physical_dimensions[i].buffer_info.size == buffers[i]->get_create_info().size)
+			physical_buffers[i] = std::move(buffers[i]);
+}
+
+std::vector<std::string> RenderGraph::get_baked_pass_names() const
+{
+	std::vector<std::string> names;
+	for (unsigned p : pass_stack)
+		names.push_back(passes[p]->get_name());
+	return names;
+}
+
+void RenderGraph::log()
+{
+	for (unsigned p : pass_stack)
+	{
+		auto &pass = *passes[p];
+		Vulkan::log_info("Pass: %s\n", pass.get_name().c_str());
+		for (auto *r : pass.get_all_reads())
+			Vulkan::log_info("  reads  %s (phys %u)\n", r->get_name().c_str(), r->get_physical_index());
+		for (auto *w : pass.get_all_writes())
+			Vulkan::log_info("  writes %s (phys %u)\n", w->get_name().c_str(), w->get_physical_index());
+	}
+}
+
+void RenderGraph::set_row_shard(unsigned y0, unsigned y1, unsigned halo_rows)
+{
+	shard_y0 = y0;
+	shard_y1 = y1;
+	shard_halo = halo_rows;
+}
+
+GrbRows RenderGraph::shard_rows_for(unsigned resource_height, unsigned extra_halo) const
+{
+	GrbRows r = { 0, 0 };
+	if (!is_sharded())
+		return r;
+	const unsigned H = swapchain_dimensions.height;
+	// rows of a (possibly smaller) resource that cover the shard's backbuffer rows
+	uint64_t lo = (uint64_t)shard_y0 * resource_height / H;
+	uint64_t hi = ((uint64_t)shard_y1 * resource_height + H - 1) / H;
+	int y0 = (int)lo - (int)(shard_halo + extra_halo);
+	int y1 = (int)hi + (int)(shard_halo + extra_halo);
+	r.y0 = std::max(y0, 0);
+	r.y1 = std::min(y1, (int)resource_height);
+	if (r.y0 == 0 && r.y1 == 0)
+		r.y1 = 1; // {0,0} means "all rows" in the C ABI; never produce it for a shard
+	return r;
+}
+} // namespace Granite

@@ -1,0 +1,367 @@
+// render_graph.hpp -- Granite's RenderGraph declaration / callback surface
+// (renderer/render_graph.hpp:48-73, 154-186, 488-516, 685-716, 793-866) over a CUDA executor.
+//
+// What is kept: the names, signatures and semantics a pass builder sees -- add_pass (idempotent
+// by name), the resource declarators, AttachmentInfo/BufferInfo/SizeClass, set_build_render_pass,
+// RenderPassInterface with its virtuals, bake(), setup_attachments(), enqueue_render_passes(),
+// get_physical_{texture,buffer,history_texture}_resource, persistent-buffer consume/install,
+// history images that swap every frame and are null on the first one, std::logic_error on
+// graph misuse.
+//
+// What is new: everything below that surface.  There are no barriers, layouts, queues or
+// semaphores to plan -- a baked graph is a topologically ordered list of passes recorded on one
+// CUDA stream per device (stream order IS the dependency), physical images are plain device
+// allocations (no aliasing: 180 GB of HBM3e makes the reference's transient aliasing pointless),
+// and per-pass GPU timestamps are CUDA events.
+#pragma once
+
+#include <functional>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "cuda_backend.hpp"
+
+namespace Granite
+{
+class RenderGraph;
+class RenderPass;
+
+// Stand-in for threading/task_composer.hpp: callbacks that receive it run inline on the
+// recording thread.
+class TaskComposer
+{
+};
+
+class RenderPassInterface
+{
+public:
+	virtual ~RenderPassInterface() = default;
+	// This information must remain fixed.
+	virtual bool render_pass_is_conditional() const { return false; }
+	virtual bool render_pass_is_separate_layered() const { return false; }
+	// Can change per frame.
+	virtual bool need_render_pass() const { return true; }
+	virtual bool get_clear_depth_stencil(VkClearDepthStencilValue *value) const;
+	virtual bool get_clear_color(unsigned attachment, VkClearColorValue *value) const;
+	// Called once before bake().
+	virtual void setup_dependencies(RenderPass &self, RenderGraph &graph);
+	// Called once after bake().
+	virtual void setup(Vulkan::Device &device);
+	// Called every frame, before build_render_pass.
+	virtual void enqueue_prepare_render_pass(RenderGraph &graph, TaskComposer &composer);
+	virtual void build_render_pass(Vulkan::CommandBuffer &cmd);
+	virtual void build_render_pass_separate_layer(Vulkan::CommandBuffer &cmd, unsigned layer);
+};
+using RenderPassInterfaceHandle = std::shared_ptr<RenderPassInterface>;
+
+enum SizeClass
+{
+	Absolute,
+	SwapchainRelative,
+	InputRelative
+};
+
+enum RenderGraphQueueFlagBits
+{
+	RENDER_GRAPH_QUEUE_GRAPHICS_BIT = 1 << 0,
+	RENDER_GRAPH_QUEUE_COMPUTE_BIT = 1 << 1,
+	RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT = 1 << 2
+};
+using RenderGraphQueueFlags = uint32_t;
+
+enum AttachmentInfoFlagBits
+{
+	ATTACHMENT_INFO_PERSISTENT_BIT = 1 << 0,
+	ATTACHMENT_INFO_UNORM_SRGB_ALIAS_BIT = 1 << 1,
+	ATTACHMENT_INFO_SUPPORTS_PREROTATE_BIT = 1 << 2,
+	ATTACHMENT_INFO_MIPGEN_BIT = 1 << 3
+};
+using AttachmentInfoFlags = uint32_t;
+
+struct AttachmentInfo
+{
+	SizeClass size_class = SizeClass::SwapchainRelative;
+	float size_x = 1.0f;
+	float size_y = 1.0f;
+	float size_z = 0.0f;
+	VkFormat format = VK_FORMAT_UNDEFINED;
+	std::string size_relative_name;
+	unsigned samples = 1;
+	unsigned levels = 1;
+	unsigned layers = 1;
+	VkImageUsageFlags aux_usage = 0;
+	AttachmentInfoFlags flags = ATTACHMENT_INFO_PERSISTENT_BIT;
+};
+
+struct BufferInfo
+{
+	VkDeviceSize size = 0;
+	VkBufferUsageFlags usage = 0;
+	AttachmentInfoFlags flags = ATTACHMENT_INFO_PERSISTENT_BIT;
+	bool operator==(const BufferInfo &other) const { return size == other.size && usage == other.usage && flags == other.flags; }
+	bool operator!=(const BufferInfo &other) const { return !(*this == other); }
+};
+
+struct ResourceDimensions
+{
+	VkFormat format = VK_FORMAT_UNDEFINED;
+	BufferInfo buffer_info;
+	unsigned width = 0;
+	unsigned height = 0;
+	unsigned depth = 1;
+	unsigned layers = 1;
+	unsigned levels = 1;
+	unsigned samples = 1;
+	AttachmentInfoFlags flags = ATTACHMENT_INFO_PERSISTENT_BIT;
+	RenderGraphQueueFlags queues = 0;
+	std::string name;
+};
+
+class RenderResource
+{
+public:
+	enum class Type
+	{
+		Buffer,
+		Texture
+	};
+	enum { Unused = ~0u };
+
+	RenderResource(Type type_, unsigned index_) : resource_type(type_), index(index_) {}
+	virtual ~RenderResource() = default;
+	Type get_type() const { return resource_type; }
+	void written_in_pass(unsigned pass) { written_in_passes.insert(pass); }
+	void read_in_pass(unsigned pass) { read_in_passes.insert(pass); }
+	const std::unordered_set<unsigned> &get_read_passes() const { return read_in_passes; }
+	const std::unordered_set<unsigned> &get_write_passes() const { return written_in_passes; }
+	unsigned get_index() const { return index; }
+	void set_physical_index(unsigned index_) { physical_index = index_; }
+	unsigned get_physical_index() const { return physical_index; }
+	void set_name(const std::string &name_) { name = name_; }
+	const std::string &get_name() const { return name; }
+
+private:
+	Type resource_type;
+	unsigned index;
+	unsigned physical_index = Unused;
+	std::unordered_set<unsigned> written_in_passes;
+	std::unordered_set<unsigned> read_in_passes;
+	std::string name;
+};
+
+class RenderBufferResource : public RenderResource
+{
+public:
+	explicit RenderBufferResource(unsigned index_) : RenderResource(RenderResource::Type::Buffer, index_) {}
+	void set_buffer_info(const BufferInfo &info_) { info = info_; }
+	const BufferInfo &get_buffer_info() const { return info; }
+
+private:
+	BufferInfo info;
+};
+
+class RenderTextureResource : public RenderResource
+{
+public:
+	explicit RenderTextureResource(unsigned index_) : RenderResource(RenderResource::Type::Texture, index_) {}
+	void set_attachment_info(const AttachmentInfo &info_) { info = info_; }
+	const AttachmentInfo &get_attachment_info() const { return info; }
+	AttachmentInfo &get_attachment_info() { return info; }
+
+private:
+	AttachmentInfo info;
+};
+
+class RenderPass
+{
+public:
+	RenderPass(RenderGraph &graph_, unsigned index_, RenderGraphQueueFlagBits queue_) : graph(graph_), index(index_), queue(queue_) {}
+
+	RenderGraphQueueFlagBits get_queue() const { return queue; }
+	RenderGraph &get_graph() { return graph; }
+	unsigned get_index() const { return index; }
+
+	RenderTextureResource &set_depth_stencil_input(const std::string &name);
+	RenderTextureResource &set_depth_stencil_output(const std::string &name, const AttachmentInfo &info);
+	RenderTextureResource &add_color_output(const std::string &name, const AttachmentInfo &info, const std::string &input = "");
+	RenderTextureResource &add_attachment_input(const std::string &name);
+	RenderTextureResource &add_history_input(const std::string &name);
+	RenderTextureResource &add_texture_input(const std::string &name, VkPipelineStageFlags2 stages = 0);
+	RenderBufferResource &add_uniform_input(const std::string &name, VkPipelineStageFlags2 stages = 0);
+	RenderBufferResource &add_storage_read_only_input(const std::string &name, VkPipelineStageFlags2 stages = 0);
+	RenderBufferResource &add_storage_output(const std::string &name, const BufferInfo &info, const std::string &input = "");
+	RenderBufferResource &add_transfer_output(const std::string &name, const BufferInfo &info);
+	RenderTextureResource &add_storage_texture_output(const std::string &name, const AttachmentInfo &info, const std::string &input = "");
+	void add_fake_resource_write_alias(const std::string &from, const std::string &to);
+
+	const std::vector<RenderTextureResource *> &get_color_outputs() const { return color_outputs; }
+	const std::vector<RenderTextureResource *> &get_color_inputs() const { return color_inputs; }
+	const std::vector<RenderTextureResource *> &get_storage_texture_outputs() const { return storage_texture_outputs; }
+	const std::vector<RenderTextureResource *> &get_attachment_inputs() const { return attachments_inputs; }
+	const std::vector<RenderTextureResource *> &get_history_inputs() const { return history_inputs; }
+	const std::vector<RenderTextureResource *> &get_texture_inputs() const { return texture_inputs; }
+	const std::vector<RenderBufferResource *> &get_storage_outputs() const { return storage_outputs; }
+	const std::vector<RenderBufferResource *> &get_transfer_outputs() const { return transfer_outputs; }
+	const std::vector<RenderBufferResource *> &get_buffer_inputs() const { return buffer_inputs; }
+	RenderTextureResource *get_depth_stencil_input() const { return depth_stencil_input; }
+	RenderTextureResource *get_depth_stencil_output() const { return depth_stencil_output; }
+
+	bool need_render_pass() const { return render_pass_handle ? render_pass_handle->need_render_pass() : true; }
+	bool get_clear_color(unsigned attachment, VkClearColorValue *value = nullptr) const;
+	bool get_clear_depth_stencil(VkClearDepthStencilValue *value = nullptr) const;
+
+	void prepare_render_pass(TaskComposer &composer)
+	{
+		if (render_pass_handle)
+			render_pass_handle->enqueue_prepare_render_pass(graph, composer);
+	}
+
+	void setup(Vulkan::Device &device)
+	{
+		if (render_pass_handle)
+			render_pass_handle->setup(device);
+	}
+
+	void setup_dependencies()
+	{
+		if (render_pass_handle)
+			render_pass_handle->setup_dependencies(*this, graph);
+	}
+
+	// Dispatch rule of renderer/render_graph.hpp:685-696.
+	void build_render_pass(Vulkan::CommandBuffer &cmd, unsigned layer)
+	{
+		if (render_pass_handle)
+		{
+			if (render_pass_handle->render_pass_is_separate_layered())
+				render_pass_handle->build_render_pass_separate_layer(cmd, layer);
+			else
+				render_pass_handle->build_render_pass(cmd);
+		}
+		else if (build_render_pass_cb)
+			build_render_pass_cb(cmd);
+	}
+
+	void set_render_pass_interface(RenderPassInterfaceHandle handle) { render_pass_handle = std::move(handle); }
+	void set_build_render_pass(std::function<void(Vulkan::CommandBuffer &)> func) { build_render_pass_cb = std::move(func); }
+	void set_get_clear_depth_stencil(std::function<bool(VkClearDepthStencilValue *)> func) { get_clear_depth_stencil_cb = std::move(func); }
+	void set_get_clear_color(std::function<bool(unsigned, VkClearColorValue *)> func) { get_clear_color_cb = std::move(func); }
+	void set_name(const std::string &name) { pass_name = name; }
+	const std::string &get_name() const { return pass_name; }
+
+	// dependency bookkeeping used by bake()
+	const std::vector<RenderResource *> &get_all_reads() const { return reads; }
+	const std::vector<RenderResource *> &get_all_writes() const { return writes; }
+	const std::vector<std::pair<RenderResource *, RenderResource *>> &get_write_aliases() const { return rmw_aliases; }
+
+private:
+	RenderGraph &graph;
+	unsigned index;
+	RenderGraphQueueFlagBits queue;
+	RenderPassInterfaceHandle render_pass_handle;
+	std::function<void(Vulkan::CommandBuffer &)> build_render_pass_cb;
+	std::function<bool(VkClearDepthStencilValue *)> get_clear_depth_stencil_cb;
+	std::function<bool(unsigned, VkClearColorValue *)> get_clear_color_cb;
+	std::string pass_name;
+
+	std::vector<RenderTextureResource *> color_outputs, color_inputs, storage_texture_outputs, attachments_inputs, history_inputs, texture_inputs;
+	std::vector<RenderBufferResource *> storage_outputs, transfer_outputs, buffer_inputs;
+	RenderTextureResource *depth_stencil_input = nullptr;
+	RenderTextureResource *depth_stencil_output = nullptr;
+	std::vector<RenderResource *> reads, writes;
+	std::vector<std::pair<RenderResource *, RenderResource *>> rmw_aliases; // (output, input it modifies in place)
+	std::vector<std::pair<RenderResource *, RenderResource *>> fake_aliases;
+	friend class RenderGraph;
+};
+
+class RenderGraph
+{
+public:
+	RenderGraph() = default;
+	~RenderGraph() = default;
+	RenderGraph(const RenderGraph &) = delete;
+	void operator=(const RenderGraph &) = delete;
+
+	void set_device(Vulkan::Device *device_) { device = device_; }
+	Vulkan::Device &get_device();
+
+	RenderPass &add_pass(const std::string &name, RenderGraphQueueFlagBits queue);
+	RenderPass *find_pass(const std::string &name);
+	void set_backbuffer_source(const std::string &name);
+	void set_backbuffer_dimensions(const ResourceDimensions &dim) { swapchain_dimensions = dim; }
+	const ResourceDimensions &get_backbuffer_dimensions() const { return swapchain_dimensions; }
+
+	ResourceDimensions get_resource_dimensions(const RenderBufferResource &resource) const;
+	ResourceDimensions get_resource_dimensions(const RenderTextureResource &resource) const;
+
+	void enable_timestamps(bool enable) { timestamps = enable; }
+	// Misconfiguration throws std::logic_error, as in the reference (render_graph.cpp:568-619, 3003).
+	void bake();
+	void reset();
+	void log();
+	// Allocates / reuses physical images and buffers, swaps history <-> current
+	// (render_graph.cpp:2686-2765).  `swapchain` may be null: the backbuffer source is then a
+	// graph-owned image of the backbuffer dimensions.
+	void setup_attachments(Vulkan::Device &device, Vulkan::ImageView *swapchain);
+	// Records every baked pass, in order, on the device's stream.
+	void enqueue_render_passes(Vulkan::Device &device, TaskComposer &composer);
+
+	RenderTextureResource &get_texture_resource(const std::string &name);
+	RenderBufferResource &get_buffer_resource(const std::string &name);
+	bool has_texture_resource(const std::string &name) const { return resource_to_index.count(name) != 0; }
+
+	Vulkan::ImageView &get_physical_texture_resource(unsigned index);
+	Vulkan::ImageView *get_physical_history_texture_resource(unsigned index);
+	Vulkan::Buffer &get_physical_buffer_resource(unsigned index);
+	Vulkan::ImageView &get_physical_texture_resource(const RenderTextureResource &resource) { return get_physical_texture_resource(resource.get_physical_index()); }
+	Vulkan::ImageView *maybe_get_physical_texture_resource(RenderTextureResource *resource);
+	Vulkan::ImageView *get_physical_history_texture_resource(const RenderTextureResource &resource) { return get_physical_history_texture_resource(resource.get_physical_index()); }
+	Vulkan::Buffer &get_physical_buffer_resource(const RenderBufferResource &resource) { return get_physical_buffer_resource(resource.get_physical_index()); }
+	Vulkan::Buffer *maybe_get_physical_buffer_resource(RenderBufferResource *resource);
+
+	// For keeping feed-back resources alive during rebaking (scene_viewer_application.cpp:1169,1315).
+	std::vector<Vulkan::BufferHandle> consume_physical_buffers() const;
+	void install_physical_buffers(std::vector<Vulkan::BufferHandle> buffers);
+
+	static RenderGraphQueueFlagBits get_default_post_graphics_queue() { return RENDER_GRAPH_QUEUE_GRAPHICS_BIT; }
+	static RenderGraphQueueFlagBits get_default_compute_queue() { return RENDER_GRAPH_QUEUE_COMPUTE_BIT; }
+
+	// Execution order decided by bake(): names of the passes that will run.
+	std::vector<std::string> get_baked_pass_names() const;
+	// Row shard of this device for row-sharded frames (multi-GPU): output rows [y0, y1) of the
+	// BACKBUFFER; {0,0} = whole frame.  Builders scale it per resource with shard_rows_for().
+	void set_row_shard(unsigned y0, unsigned y1, unsigned halo_rows = 0);
+	GrbRows shard_rows_for(unsigned resource_height, unsigned extra_halo = 0) const;
+	bool is_sharded() const { return shard_y1 != 0; }
+
+private:
+	Vulkan::Device *device = nullptr;
+	std::vector<std::unique_ptr<RenderPass>> passes;
+	std::vector<std::unique_ptr<RenderResource>> resources;
+	std::unordered_map<std::string, unsigned> pass_to_index;
+	std::unordered_map<std::string, unsigned> resource_to_index;
+	std::string backbuffer_source;
+	ResourceDimensions swapchain_dimensions;
+	bool timestamps = false;
+
+	std::vector<unsigned> pass_stack; // baked order
+	std::vector<ResourceDimensions> physical_dimensions;
+	std::vector<bool> physical_has_history;
+	std::vector<std::unique_ptr<Vulkan::ImageView>> physical_attachments;
+	std::vector<std::unique_ptr<Vulkan::ImageView>> physical_history_attachments; // previous frame (may be null)
+	std::vector<std::unique_ptr<Vulkan::ImageView>> physical_history_spare;       // image to become "current" next frame
+	std::vector<Vulkan::BufferHandle> physical_buffers;
+	unsigned backbuffer_physical = RenderResource::Unused;
+	bool baked = false;
+	unsigned shard_y0 = 0, shard_y1 = 0, shard_halo = 0;
+
+	RenderTextureResource &get_or_create_texture(const std::string &name);
+	RenderBufferResource &get_or_create_buffer(const std::string &name);
+	void traverse_dependencies(unsigned pass_index, std::vector<uint8_t> &state);
+	void build_physical_resources();
+	friend class RenderPass;
+};
+} // namespace Granite

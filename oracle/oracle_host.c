@@ -191,7 +191,7 @@ void orc_point_light_info(const float *color, const float *position, float cutof
 	out->offset_radius[0] = orc_float_to_half(0.0f);
 	out->offset_radius[1] = orc_float_to_half(max_range);
 	/* transform.get_forward() of an identity-rotation node: (0,0,-1). "This shouldn't matter". */
-	out->direction[0] = 0.0f; out->direction[1] = 0.0f; out->direction[2] = -1.0f;
+	out->direction[0] = -0.0f; out->direction[1] = -0.0f; out->direction[2] = -1.0f; /* -(row.z) of identity */
 	out->inv_radius = 1.0f / max_range;
 }
 
@@ -219,7 +219,9 @@ void orc_spot_light_info(const float *color, const float *position, const float 
 		model_rows[r * 4 + 3] = position[r];
 	}
 
-	float scale_factor = 1.0f;
+	/* transform.get_uniform_scale() == length(vec[0].xyz()): ROW 0 of the node transform
+	 * (math/muglm/muglm.cpp:434-437); ~1 for a rotation, but not bit-exactly 1. */
+	float scale_factor = sqrtf(rot[0] * rot[0] + rot[3] * rot[3] + rot[6] * rot[6]);
 	float max_range = max_range0 * scale_factor;
 	float spot_scale = 1.0f / f_max(0.001f, inner_cone - outer_cone);
 	float spot_bias = -outer_cone * spot_scale;
