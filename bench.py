@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/sec (+ HBM GB/s of the dominant kernel) of the clustered deferred
+lighting + HDR post chain on a 3840x2160 synthetic G-buffer with 4096 lights (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores
+                                                           # (CPU oracle; the reference has no CPU path
+                                                           #  and no Vulkan device exists here)
+Prints ONE JSON line on rank 0.  A "step" is one frame.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOADS = {
+    # name: (width, height, lights, post_aa, description)
+    "c3": (3840, 2160, 4096, "none", "3840x2160 G-buffer, 4096 clustered point lights + directional, bloom + luminance + tonemap"),
+    "c2": (1920, 1080, 1024, "none", "1920x1080 G-buffer, 1024 clustered lights, full bloom/tonemap chain"),
+    "c5": (3840, 2160, 4096, "taa+fxaa", "3840x2160 TAA(q2) + FXAA post-AA with history buffer"),
+}
+LIGHTING_BYTES_PER_PIXEL = 22  # 4 albedo + 4 normal + 2 pbr + 4 depth + 4 emissive read, 4 HDR write
+
+
+def algorithmic_bytes(w, h, aa):
+    """Compulsory HBM traffic per frame, unfused pass-by-pass accounting of SURVEY.md §8d."""
+    px = w * h
+    sz = [(math.ceil(w * s), math.ceil(h * s)) for s in (0.5, 0.25, 0.125, 0.0625, 0.03125)]
+    t, d0, d1, d2, d3 = [a * b for a, b in sz]
+    lighting = px * LIGHTING_BYTES_PER_PIXEL
+    chain = (px * 4 + t * 8) + (t * 8 + d0 * 8) + (d0 * 8 + d1 * 8) + (d1 * 8 + d2 * 8) + (d2 * 8 + d3 * 8 + d3 * 8) \
+        + d3 * 8 // 4 + (d3 * 8 + d2 * 8) + (d2 * 8 + d1 * 8) + (d1 * 8 + d0 * 8) + (px * 4 + d0 * 8 + px * 4)
+    total = lighting + chain
+    if aa == "taa+fxaa":
+        total += px * 32 + px * 8
+    return lighting, chain, total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        for t, line in self.samples:
+            if t < t0 - 0.05 or t > t1 + 0.05:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the lighting kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "lighting_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_frame_time(w, h, n_lights, aa, steps, warmup, budget_s=150.0):
+    """Times the CPU oracle (the reference's algorithm restated in C, OpenMP over rows) on a bounded
+    sample of the frame: the cluster build and the pyramid tail in full, the per-pixel passes on a
+    band of rows, scaled to the whole frame."""
+    from granite_b200 import synth
+    from oracle import pyoracle as oracle
+
+    oracle.build(ref=False)
+    cores = os.cpu_count() or 1
+    scene = synth.make_scene(w, h)
+    cam = oracle.camera_setup(scene.projection, scene.view)
+    lights = synth.make_lights(n_lights, aspect=w / h)
+    prep = oracle.prepare_lights(cam, lights, res=synth.CLUSTER_RES)
+    sz = oracle.pyramid_sizes(w, h)
+
+    def frame(rows):
+        """One frame with the per-pixel passes restricted to full-res rows [0, rows)."""
+        t0 = time.perf_counter()
+        clus = oracle.cluster_build(cam, prep)
+        t1 = time.perf_counter()
+        hdr = oracle.deferred_lighting(scene, cam, prep, clus, rows=(0, rows))
+        t2 = time.perf_counter()
+        hs = hdr[:rows]
+        psz = oracle.pyramid_sizes(w, rows)
+        t = oracle.bloom_threshold(hs, np.zeros(3, np.float32), psz[0])
+        d0 = oracle.bloom_downsample(t, psz[1])
+        t3 = time.perf_counter()
+        # pyramid tail at FULL frame size (it is tiny): d1..d3, luminance, u2, u1
+        full_d0 = np.zeros((sz[1][1], sz[1][0], 4), np.uint16)
+        d1 = oracle.bloom_downsample(full_d0, sz[2])
+        d2 = oracle.bloom_downsample(d1, sz[3])
+        d3 = oracle.bloom_downsample(d2, sz[4], d2[: sz[4][1], : sz[4][0]].copy(), 0.1)
+        lum = oracle.luminance(d3, np.zeros(3, np.float32), 0.01)
+        u2 = oracle.bloom_upsample(d3, sz[3])
+        u1 = oracle.bloom_upsample(u2, sz[2])
+        t4 = time.perf_counter()
+        u0 = oracle.bloom_upsample(u1[: psz[2][1]], psz[1])
+        ldr = oracle.tonemap(hs, u0, lum, 1.0)
+        extra = 0.0
+        if aa == "taa+fxaa":
+            ta = time.perf_counter()
+            mv = np.zeros((rows, w, 2), np.uint16)
+            hist = np.zeros((rows, w, 4), np.uint16)
+            oracle.taa_resolve(hs, scene.depth[:rows], mv, hist, np.eye(4, dtype=np.float32), 2)
+            oracle.fxaa(ldr, True)
+            extra = time.perf_counter() - ta
+        t5 = time.perf_counter()
+        band = (t2 - t1) + (t3 - t2) + (t5 - t4)  # scales with rows
+        fixed = (t1 - t0) + (t4 - t3)             # cluster build + pyramid tail
+        return band, fixed, extra
+
+    # calibrate on one 64-row band, then pick the largest band that fits the budget
+    band, fixed, _ = frame(64)
+    est_full = band * (h / 64.0) + fixed
+    frac = min(1.0, budget_s / max(est_full * (steps + warmup), 1e-9))
+    rows = int(max(64, min(h, (int(h * frac) // 64) * 64)))
+    for _ in range(warmup):
+        frame(rows)
+    times = []
+    for _ in range(steps):
+        b, f, _ = frame(rows)
+        times.append(b * (h / rows) + f)
+    sec = float(np.mean(times))
+    return sec, cores, f"per step: cluster build + pyramid tail in full, per-pixel passes on rows [0,{rows}) of {h} scaled x{h / rows:.2f}"
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    w, h, n_lights, aa, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    lighting_b, chain_b, total_b = algorithmic_bytes(w, h, aa)
+    config = {"workload": f"{args.workload}: {desc}", "width": w, "height": h, "lights": n_lights, "cluster_grid": "128x64x4096",
+              "sharding": f"{world} row band(s), 64-row aligned" if world > 1 else "none",
+              "l2": "per-frame inputs (182 MB G-buffer at 4K) exceed the 126 MB L2; no explicit flush",
+              "algorithmic_mb_per_frame": round(total_b / 1e6, 2)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = min(args.steps, 5)  # each CPU step is seconds long; bounded so the run stays within minutes
+        sec, cores, sample = oracle_frame_time(w, h, n_lights, aa, steps, min(args.warmup, 1))
+        fps = 1.0 / sec
+        line = {"impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "the reference has no CPU path for these passes and cannot run here (no Vulkan device); this is its algorithm restated in C (oracle/), all host threads"}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from granite_b200 import synth, viewer
+
+    scene = synth.make_scene(w, h)
+    lights = synth.make_lights(n_lights, aspect=w / h)
+    post = {"none": viewer.AA_NONE, "taa+fxaa": viewer.AA_TAA_HIGH_PLUS_FXAA}[aa]
+    stream = torch.cuda.current_stream()
+
+    def make_viewer(timestamps):
+        v = viewer.Viewer(w, h, post_aa=post, cuda_device=local_rank, timestamps=timestamps, stream=stream.cuda_stream)
+        v.set_camera(scene.projection, scene.view)
+        v.set_directional(scene.dir_color, scene.dir_direction)
+        v.set_lights(lights)
+        if world > 1:
+            if aa != "none":
+                raise SystemExit("row-sharded TAA is not supported")
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(viewer.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            v.init_collectives(bytes(uid.cpu().numpy().tobytes()), rank, world)
+            v.set_row_shards(viewer.band_partition(h, world), rank)
+        v.bake()
+        return v
+
+    v = make_viewer(False)
+    bands = viewer.band_partition(h, world) if world > 1 else [(0, h)]
+    own = bands[rank]
+    halo = 8
+    in_rows = (max(own[0] - halo, 0), min(own[1] + halo, h)) if world > 1 else (0, h)
+
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32 if a.dtype == np.uint32 else (np.int16 if a.dtype == np.uint16 else a.dtype))).pin_memory()
+    mv = None
+    if aa == "taa+fxaa":
+        rng = np.random.default_rng(5)
+        mvf = np.zeros((h, w, 2), np.float16)
+        m = rng.random((h, w)) < 0.1
+        mvf[m] = (rng.uniform(-2, 2, size=(int(m.sum()), 2)) / np.array([w, h])).astype(np.float16)
+        mv = pin(np.ascontiguousarray(mvf).view(np.uint32)[..., 0])
+    host = [pin(scene.albedo), pin(scene.normal), pin(scene.pbr), pin(scene.depth), pin(scene.emissive)]
+    gb = viewer.Viewer.host_gbuffer(*host, mv)
+    out = torch.zeros((h, w), dtype=torch.int32).pin_memory()
+    h2d = (in_rows[1] - in_rows[0]) * w * (LIGHTING_BYTES_PER_PIXEL - 4 + (4 if mv is not None else 0))
+    d2h = (own[1] - own[0]) * w * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # warm-up: uploads the G-buffer, builds the history images, adapts the luminance
+    for _ in range(args.warmup):
+        v.render_frame(gb)
+        v.read_output(out)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- timed region 1: device-resident inputs (value) ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        v.render_frame(None)
+    e1.record(stream)
+    barrier()
+    ms_resident = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- timed region 2: end to end through the host API (H2D of the step's inputs, D2H of its result) ----
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    f0.record(stream)
+    for _ in range(args.steps):
+        v.render_frame(gb)
+        v.read_output(out)
+    f1.record(stream)
+    barrier()
+    w1 = time.perf_counter()
+    t_end = time.time()
+    ms_e2e = max_over_ranks(max(f0.elapsed_time(f1), (w1 - w0) * 1e3))
+    if rank == 0:
+        sampler.stop()
+    clocks = sampler.summary(t_begin, t_end) if rank == 0 else None
+    v.close()
+
+    # ---- per-pass GPU time (CUDA events around each pass), outside the timed regions ----
+    vt = make_viewer(True)
+    for _ in range(3):
+        vt.render_frame(gb)
+    vt.sync()
+    vt.collect_timings()
+    n_t = min(args.steps, 50)
+    for _ in range(n_t):
+        vt.render_frame(None)
+    vt.sync()
+    timings = {k: ms / max(c, 1) for k, (ms, c) in vt.collect_timings().items()}
+    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 10 + (2 if world > 1 else 0), "tonemap": 1, "taa-resolve": 1, "fxaa": 1,
+                "gbuffer": 0, "mv": 0}
+    launches_per_frame = sum(n_launch.get(p, 0) for p in vt.pass_names())
+    vt.close()
+
+    peak, peak_kind = measured_peak()
+    light_ms = timings.get("lighting")
+    light_rows = (in_rows[1] - in_rows[0])
+    achieved = (light_rows * w * LIGHTING_BYTES_PER_PIXEL) / (light_ms * 1e-3) / 1e9 if light_ms else None
+    fps = args.steps / (ms_resident * 1e-3)
+    line = {
+        "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+        "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_frame * args.steps,
+        "hbm_gbs_whole_frame": total_b / (ms_resident / args.steps * 1e-3) / 1e9 / 1.0,
+        "roofline": {"kernel": "deferred_lighting_kernel (pass 'lighting')", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(), "peak_source": f"of {peak_kind}",
+                     "bytes_per_pixel": LIGHTING_BYTES_PER_PIXEL, "note": "ALU-bound at this light density: see DESIGN.md"},
+        "pass_ms": {k: round(val, 4) for k, val in timings.items()},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores, sample = oracle_frame_time(w, h, n_lights, aa, steps=1, warmup=0, budget_s=25.0)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -71,7 +71,7 @@ class GrbClusterBuffers(C.Structure):
 
 class GrbGBuffer(C.Structure):
     _fields_ = [("albedo", GrbImage), ("normal", GrbImage), ("pbr", GrbImage), ("depth", GrbImage),
-                ("directional_color", C.c_float * 3), ("directional_direction", C.c_float * 3)]
+                ("directional_color", C.c_float * 3), ("directional_direction", C.c_float * 3), ("emissive", GrbImage)]
 
 
 ENTRY_POINTS = [

@@ -38,6 +38,7 @@ struct LightingParams
 	View<const uint16_t> pbr;
 	View<const float> depth;
 	View<uint32_t> hdr;
+	View<const uint32_t> emissive; // blend destination's initial contents (may be the hdr image itself)
 	float ivp[16];
 	float3 camera_pos;
 	float3 dir_color, dir_dir;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		const uint32_t a8 = __ldg(&p.albedo.at(x, y));
 		const uint32_t n10 = __ldg(&p.normal.at(x, y));
 		const uint32_t mr = __ldg(&p.pbr.at(x, y));
-		dst = p.hdr.at(x, y);
+		dst = __ldg(&p.emissive.at(x, y));
 
 		base_color = make_float3(s_srgb[a8 & 0xffu], s_srgb[(a8 >> 8) & 0xffu], s_srgb[(a8 >> 16) & 0xffu]);
 		s.N = make_float3(fsub(fmul(fdiv((float)(n10 & 0x3ffu), 1023.0f), 2.0f), 1.0f), fsub(fmul(fdiv((float)((n10 >> 10) & 0x3ffu), 1023.0f), 2.0f), 1.0f),
@@ -262,6 +263,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		float3 e = unpack_r11g11b10(dst);
 		p.hdr.at(x, y) = pack_r11g11b10(e.x + acc.x, e.y + acc.y, e.z + acc.z);
 	}
+	else if (inside && p.emissive.p != p.hdr.p)
+		p.hdr.at(x, y) = __ldg(&p.emissive.at(x, y)); // sky keeps the attachment value
 }
 } // namespace
 
@@ -321,6 +324,17 @@ extern "C" int32_t grb_deferred_lighting(const GrbGBuffer *g, const GrbCamera *c
 	p.pbr = view_of<const uint16_t>(&g->pbr);
 	p.depth = view_of<const float>(&g->depth);
 	p.hdr = view_of<uint32_t>(hdr);
+	if (g->emissive.data)
+	{
+		if (!image_ok(&g->emissive, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || g->emissive.width != w || g->emissive.height != h)
+		{
+			set_last_error("grb_deferred_lighting: emissive must be B10G11R11_UFLOAT of the G-buffer's size");
+			return GRB_ERR_UNSUPPORTED_FORMAT;
+		}
+		p.emissive = view_of<const uint32_t>(&g->emissive);
+	}
+	else
+		p.emissive = view_of<const uint32_t>(hdr);
 	for (int i = 0; i < 16; i++)
 		p.ivp[i] = cam->inv_view_projection[i];
 	p.camera_pos = make_float3(cam->camera_position[0], cam->camera_position[1], cam->camera_position[2]);

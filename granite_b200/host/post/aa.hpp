@@ -1,0 +1,38 @@
+// aa.hpp -- PostAAType and the two hooks the application calls around the HDR chain
+// (renderer/post/aa.hpp:33-63).  FXAA and the three TAA qualities are on the hot path; the
+// stale FXAA_2Phase / SMAA_T2X resolves and SMAA are not built.
+#pragma once
+
+#include <string>
+
+#include "temporal.hpp"
+
+namespace Granite
+{
+enum class PostAAType
+{
+	None,
+	FXAA,
+	FXAA_2Phase,
+	SMAA_Low,
+	SMAA_Medium,
+	SMAA_High,
+	SMAA_Ultra,
+	SMAA_Ultra_T2X,
+	TAA_Low,
+	TAA_Medium,
+	TAA_High
+};
+
+constexpr bool post_aa_type_is_supported(PostAAType type)
+{
+	return type == PostAAType::None || type == PostAAType::FXAA || type == PostAAType::TAA_Low || type == PostAAType::TAA_Medium ||
+	       type == PostAAType::TAA_High;
+}
+
+// Returns true when a pass was added (the chain input then becomes `output`).
+bool setup_before_post_chain_antialiasing(PostAAType type, RenderGraph &graph, TemporalJitter &jitter, float scaling_factor, const std::string &input,
+                                          const std::string &input_depth, const std::string &input_mv, const std::string &output);
+bool setup_after_post_chain_antialiasing(PostAAType type, RenderGraph &graph, TemporalJitter &jitter, float scaling_factor, const std::string &input,
+                                         const std::string &input_depth, const std::string &output);
+} // namespace Granite

@@ -1,0 +1,186 @@
+// hdr.cpp -- "bloom-compute" + "tonemap" pass builders (renderer/post/hdr.cpp:35-400), recording
+// C-ABI kernel launches on the graph's CUDA stream instead of Vulkan dispatches.  Push-constant
+// values (inverse sizes, lerp factors) are computed by the kernels' launchers exactly as the
+// reference's builders compute them; the formulas that live on this side are the frame-time
+// dependent ones.
+//
+// Row-sharded frames: levels t (1/2) and d0 (1/4) -- 95 % of the bloom bytes -- are produced for
+// the rank's own band only; d0 bands are all-gathered, the pyramid tail (d1..d3, u2, u1: < 1.5 MB
+// in total at 4K) is computed redundantly on every rank, the average-luminance grid is summed
+// across ranks, u0 and the tonemap are again band-only.  Every texel any rank computes is
+// computed from the same inputs by the same kernel, so the frame is bit-identical for any
+// number of ranks.
+#include "hdr.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+
+namespace Granite
+{
+namespace
+{
+struct BloomResources
+{
+	RenderTextureResource *t, *d0, *u0, *d1, *u1, *d2, *u2, *d3, *hdr;
+	const RenderBufferResource *lum;
+	const RenderBufferResource *lum_grid;
+};
+
+GrbRows all_rows() { return GrbRows{ 0, 0 }; }
+
+void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const FrameParameters &frame, const BloomResources &r)
+{
+	void *stream = cmd.get_stream_handle();
+	auto img = [&](RenderTextureResource *res) { return graph.get_physical_texture_resource(*res).as_grb(); };
+	float *lum = r.lum ? graph.get_physical_buffer_resource(*r.lum).get<float>() : nullptr;
+
+	GrbImage hdr = img(r.hdr), t = img(r.t), d0 = img(r.d0), d1 = img(r.d1), d2 = img(r.d2), d3 = img(r.d3);
+	GrbImage u2 = img(r.u2), u1 = img(r.u1), u0 = img(r.u0);
+	const bool sharded = graph.is_sharded() && graph.get_shard_count() > 1;
+
+	// Rows of each band-only level (shard_plan.hpp derives them from the rows this rank owns).
+	const ShardPlan plan = graph.get_shard_plan();
+	GrbRows d0_rows = sharded ? plan.downsample0 : all_rows();
+	GrbRows t_rows = sharded ? plan.threshold : all_rows();
+
+	// bloom_threshold_build_compute: uses LAST frame's average luminance (hdr.cpp:355)
+	cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
+	cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, stream), "grb_bloom_downsample(d0)");
+
+	if (sharded)
+	{
+		std::vector<GrbRows> bands;
+		for (unsigned rank = 0; rank < graph.get_shard_count(); rank++)
+			bands.push_back(graph.get_shard_plan(rank).downsample0);
+		graph.get_collectives()->all_gather_rows(cmd, graph.get_physical_texture_resource(*r.d0), bands);
+	}
+
+	cmd.check(grb_bloom_downsample(&d0, nullptr, 0.0f, &d1, all_rows(), stream), "grb_bloom_downsample(d1)");
+	cmd.check(grb_bloom_downsample(&d1, nullptr, 0.0f, &d2, all_rows(), stream), "grb_bloom_downsample(d2)");
+
+	// d3 blends with its own previous frame (hdr.cpp:156-167, 182): lerp = 1 - 0.001^frame_time
+	auto *history = graph.get_physical_history_texture_resource(*r.d3);
+	GrbImage hist;
+	if (history)
+		hist = history->as_grb();
+	float lerp_d3 = float(1.0 - std::pow(0.001, frame.frame_time));
+	cmd.check(grb_bloom_downsample(&d2, history ? &hist : nullptr, lerp_d3, &d3, all_rows(), stream), "grb_bloom_downsample(d3)");
+
+	if (lum)
+	{
+		// luminance_build_compute (hdr.cpp:68-98): size = d3 / 2, lerp = 1 - 0.5^frame_time, clamp [-3, 2]
+		float lerp_lum = float(1.0 - std::pow(0.5, frame.frame_time));
+		if (sharded && r.lum_grid)
+		{
+			// each rank samples the grid rows of its own band; the sum over ranks of (value or 0)
+			// reassembles the grid exactly, then every rank reduces it in the shader's order
+			float *grid = graph.get_physical_buffer_resource(*r.lum_grid).get<float>();
+			const int size_x = d3.width / 2, size_y = d3.height / 2;
+			cudaMemsetAsync(grid, 0, sizeof(float) * size_x * size_y, reinterpret_cast<cudaStream_t>(cmd.get_stream()));
+			GrbRows grid_rows = plan.lum_grid;
+			if (grid_rows.y1 > grid_rows.y0)
+				cmd.check(grb_luminance_grid(&d3, grid, grid_rows, stream), "grb_luminance_grid");
+			graph.get_collectives()->all_reduce_sum(cmd, grid, (size_t)size_x * size_y);
+			cmd.check(grb_luminance_finalize(grid, size_x, size_y, lum, lerp_lum, -3.0f, 2.0f, stream), "grb_luminance_finalize");
+		}
+		else
+			cmd.check(grb_luminance(&d3, lum, lerp_lum, -3.0f, 2.0f, stream), "grb_luminance");
+	}
+
+	cmd.check(grb_bloom_upsample(&d3, &u2, all_rows(), stream), "grb_bloom_upsample(u2)");
+	cmd.check(grb_bloom_upsample(&u2, &u1, all_rows(), stream), "grb_bloom_upsample(u1)");
+	// u0 feeds the tonemap's bilinear bloom tap: own band (+ the tonemap halo FXAA needs) at 1/4 res
+	GrbRows u0_rows = sharded ? plan.upsample0 : all_rows();
+	cmd.check(grb_bloom_upsample(&u1, &u0, u0_rows, stream), "grb_bloom_upsample(u0)");
+}
+
+void tonemap_build_render_pass(RenderPass &pass, Vulkan::CommandBuffer &cmd, const RenderTextureResource &hdr_res,
+                               const RenderTextureResource &bloom_res, const RenderBufferResource *ubo_res, const HDRDynamicExposureInterface *iface,
+                               unsigned)
+{
+	auto &graph = pass.get_graph();
+	GrbImage hdr = graph.get_physical_texture_resource(hdr_res).as_grb();
+	GrbImage bloom = graph.get_physical_texture_resource(bloom_res).as_grb();
+	const float *lum = ubo_res ? graph.get_physical_buffer_resource(*ubo_res).get<float>() : nullptr;
+	auto &out_view = graph.get_physical_texture_resource(*pass.get_color_outputs()[0]);
+	GrbImage out = out_view.as_grb();
+	float exposure = iface ? iface->get_exposure() : 1.0f; // hdr.cpp:301
+	GrbRows rows = graph.is_sharded() ? graph.get_shard_plan().tonemap : GrbRows{ 0, 0 };
+	cmd.check(grb_tonemap(&hdr, &bloom, lum, exposure, &out, rows, cmd.get_stream_handle()), "grb_tonemap");
+}
+} // namespace
+
+void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &frame, const std::string &input, const std::string &output,
+                                   const HDROptions &options, const HDRDynamicExposureInterface *iface)
+{
+	BufferInfo buffer_info;
+	buffer_info.size = 3 * sizeof(float);
+	buffer_info.usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT;
+
+	AttachmentInfo downsample_info;
+	downsample_info.format = VK_FORMAT_R16G16B16A16_SFLOAT;
+	downsample_info.size_x = 0.5f;
+	downsample_info.size_y = 0.5f;
+	downsample_info.size_class = SizeClass::InputRelative;
+	downsample_info.size_relative_name = input;
+	downsample_info.aux_usage = VK_IMAGE_USAGE_SAMPLED_BIT;
+	auto level = [&](float s) {
+		auto info = downsample_info;
+		info.size_x = s;
+		info.size_y = s;
+		return info;
+	};
+
+	auto &bloom_pass = graph.add_pass("bloom-compute", RenderGraph::get_default_compute_queue());
+	auto res = std::make_shared<BloomResources>();
+	res->t = &bloom_pass.add_storage_texture_output("threshold", downsample_info);
+	res->d0 = &bloom_pass.add_storage_texture_output("downsample-0", level(0.25f));
+	res->u0 = &bloom_pass.add_storage_texture_output("upsample-0", level(0.25f));
+	res->d1 = &bloom_pass.add_storage_texture_output("downsample-1", level(0.125f));
+	res->u1 = &bloom_pass.add_storage_texture_output("upsample-1", level(0.125f));
+	res->d2 = &bloom_pass.add_storage_texture_output("downsample-2", level(0.0625f));
+	res->u2 = &bloom_pass.add_storage_texture_output("upsample-2", level(0.0625f));
+	res->d3 = &bloom_pass.add_storage_texture_output("downsample-3", level(0.03125f));
+	res->lum = nullptr;
+	res->lum_grid = nullptr;
+	if (options.dynamic_exposure)
+	{
+		res->lum = &bloom_pass.add_storage_output("average-luminance", buffer_info);
+		// scratch for the row-sharded luminance sum: the (d3/2) sample grid; 64 KiB covers 16K frames
+		BufferInfo grid_info;
+		grid_info.size = 64 * 1024;
+		grid_info.usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT;
+		res->lum_grid = &bloom_pass.add_storage_output("average-luminance-grid", grid_info);
+	}
+	res->hdr = &bloom_pass.add_texture_input(input);
+	bloom_pass.add_history_input("downsample-3");
+	bloom_pass.set_build_render_pass([&graph, &frame, res](Vulkan::CommandBuffer &cmd) { bloom_build_compute(cmd, graph, frame, *res); });
+
+	{
+		AttachmentInfo tonemap_info;
+		tonemap_info.flags |= ATTACHMENT_INFO_SUPPORTS_PREROTATE_BIT;
+		tonemap_info.size_class = SizeClass::InputRelative;
+		tonemap_info.size_relative_name = input;
+		auto &tonemap = graph.add_pass("tonemap", RenderGraph::get_default_post_graphics_queue());
+		tonemap.add_color_output(output, tonemap_info);
+		auto &hdr_res = tonemap.add_texture_input(input);
+		auto &bloom_res = tonemap.add_texture_input("upsample-0");
+		const RenderBufferResource *ubo_res = nullptr;
+		if (options.dynamic_exposure)
+			ubo_res = &tonemap.add_uniform_input("average-luminance");
+		tonemap.set_build_render_pass([&tonemap, &hdr_res, &bloom_res, ubo_res, iface, &graph](Vulkan::CommandBuffer &cmd) {
+			// FXAA downstream reads +-9 rows around a band: tonemap that halo too when a consumer declared it
+			unsigned halo = graph.find_pass("fxaa") ? 12u : 0u;
+			tonemap_build_render_pass(tonemap, cmd, hdr_res, bloom_res, ubo_res, iface, halo);
+		});
+	}
+}
+
+void setup_hdr_postprocess(RenderGraph &graph, const FrameParameters &frame, const std::string &input, const std::string &output,
+                           const HDROptions &options, const HDRDynamicExposureInterface *iface)
+{
+	setup_hdr_postprocess_compute(graph, frame, input, output, options, iface);
+}
+} // namespace Granite

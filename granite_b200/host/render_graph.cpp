@@ -559,28 +559,47 @@ void RenderGraph::log()
 	}
 }
 
-void RenderGraph::set_row_shard(unsigned y0, unsigned y1, unsigned halo_rows)
+void RenderGraph::set_row_shards(const std::vector<GrbRows> &bands, unsigned rank, RenderGraphCollectives *collectives_, bool fxaa_downstream)
 {
-	shard_y0 = y0;
-	shard_y1 = y1;
-	shard_halo = halo_rows;
+	shard_fxaa = fxaa_downstream;
+	if (!bands.empty())
+	{
+		if (rank >= bands.size())
+			throw std::logic_error("set_row_shards: rank out of range.");
+		int expect = 0;
+		for (auto &b : bands)
+		{
+			if (b.y0 != expect || b.y1 <= b.y0)
+				throw std::logic_error("set_row_shards: bands must tile the frame in order.");
+			expect = b.y1;
+		}
+		if (bands.size() > 1 && !collectives_)
+			throw std::logic_error("set_row_shards: more than one band needs a collectives implementation.");
+	}
+	shard_bands = bands;
+	shard_rank = rank;
+	collectives = collectives_;
 }
 
-GrbRows RenderGraph::shard_rows_for(unsigned resource_height, unsigned extra_halo) const
+GrbRows RenderGraph::shard_rows_for_rank(unsigned rank, unsigned resource_height, unsigned halo_rows) const
 {
 	GrbRows r = { 0, 0 };
 	if (!is_sharded())
 		return r;
 	const unsigned H = swapchain_dimensions.height;
-	// rows of a (possibly smaller) resource that cover the shard's backbuffer rows
-	uint64_t lo = (uint64_t)shard_y0 * resource_height / H;
-	uint64_t hi = ((uint64_t)shard_y1 * resource_height + H - 1) / H;
-	int y0 = (int)lo - (int)(shard_halo + extra_halo);
-	int y1 = (int)hi + (int)(shard_halo + extra_halo);
-	r.y0 = std::max(y0, 0);
-	r.y1 = std::min(y1, (int)resource_height);
-	if (r.y0 == 0 && r.y1 == 0)
-		r.y1 = 1; // {0,0} means "all rows" in the C ABI; never produce it for a shard
+	const auto &band = shard_bands[rank];
+	// rows of a (possibly smaller) resource that cover the band's backbuffer rows
+	uint64_t lo = (uint64_t)band.y0 * resource_height / H;
+	uint64_t hi = ((uint64_t)band.y1 * resource_height + H - 1) / H;
+	r.y0 = std::max((int)lo - (int)halo_rows, 0);
+	r.y1 = std::min((int)hi + (int)halo_rows, (int)resource_height);
+	if (r.y1 <= r.y0)
+		r.y1 = r.y0 + 1; // never the {0,0} "all rows" value for a shard
 	return r;
+}
+
+GrbRows RenderGraph::shard_rows_for(unsigned resource_height, unsigned halo_rows) const
+{
+	return shard_rows_for_rank(shard_rank, resource_height, halo_rows);
 }
 } // namespace Granite

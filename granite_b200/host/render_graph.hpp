@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "cuda_backend.hpp"
+#include "shard_plan.hpp"
 
 namespace Granite
 {
@@ -33,6 +34,19 @@ class RenderPass;
 // recording thread.
 class TaskComposer
 {
+};
+
+// Exchange steps of a row-sharded frame.  The reference has no counterpart (single GPU); the
+// implementation shipped with the host library runs them with NCCL on the graph's stream.
+class RenderGraphCollectives
+{
+public:
+	virtual ~RenderGraphCollectives() = default;
+	virtual unsigned get_rank() const = 0;
+	virtual unsigned get_world_size() const = 0;
+	// Every rank contributes rows [rows[r].y0, rows[r].y1) of an image all ranks hold at full size.
+	virtual bool all_gather_rows(Vulkan::CommandBuffer &cmd, Vulkan::ImageView &image, const std::vector<GrbRows> &rows) = 0;
+	virtual bool all_reduce_sum(Vulkan::CommandBuffer &cmd, float *data, size_t count) = 0;
 };
 
 class RenderPassInterface
@@ -331,11 +345,22 @@ public:
 
 	// Execution order decided by bake(): names of the passes that will run.
 	std::vector<std::string> get_baked_pass_names() const;
-	// Row shard of this device for row-sharded frames (multi-GPU): output rows [y0, y1) of the
-	// BACKBUFFER; {0,0} = whole frame.  Builders scale it per resource with shard_rows_for().
-	void set_row_shard(unsigned y0, unsigned y1, unsigned halo_rows = 0);
-	GrbRows shard_rows_for(unsigned resource_height, unsigned extra_halo = 0) const;
-	bool is_sharded() const { return shard_y1 != 0; }
+	// Row-sharded frames (multi-GPU, one graph per device/process): `bands[r]` = backbuffer rows
+	// [y0, y1) owned by rank r; they must tile the frame.  Builders scale the local band per
+	// resource with shard_rows_for(); an unsharded graph returns {0,0} (= all rows).
+	void set_row_shards(const std::vector<GrbRows> &bands, unsigned rank, RenderGraphCollectives *collectives, bool fxaa_downstream = false);
+	// Rows of every stage for `rank` (this rank by default); whole images when unsharded.
+	ShardPlan get_shard_plan() const { return get_shard_plan(shard_rank); }
+	ShardPlan get_shard_plan(unsigned rank) const
+	{
+		return compute_shard_plan(swapchain_dimensions.width, swapchain_dimensions.height, shard_bands, rank, shard_fxaa);
+	}
+	GrbRows shard_rows_for(unsigned resource_height, unsigned halo_rows = 0) const;
+	GrbRows shard_rows_for_rank(unsigned rank, unsigned resource_height, unsigned halo_rows = 0) const;
+	bool is_sharded() const { return !shard_bands.empty(); }
+	unsigned get_shard_rank() const { return shard_rank; }
+	unsigned get_shard_count() const { return (unsigned)shard_bands.size(); }
+	RenderGraphCollectives *get_collectives() const { return collectives; }
 
 private:
 	Vulkan::Device *device = nullptr;
@@ -356,7 +381,10 @@ private:
 	std::vector<Vulkan::BufferHandle> physical_buffers;
 	unsigned backbuffer_physical = RenderResource::Unused;
 	bool baked = false;
-	unsigned shard_y0 = 0, shard_y1 = 0, shard_halo = 0;
+	std::vector<GrbRows> shard_bands;
+	unsigned shard_rank = 0;
+	bool shard_fxaa = false;
+	RenderGraphCollectives *collectives = nullptr;
 
 	RenderTextureResource &get_or_create_texture(const std::string &name);
 	RenderBufferResource &get_or_create_buffer(const std::string &name);

@@ -1,0 +1,614 @@
+// scene_viewer.cpp -- application-side harness + its C API (include/granite_b200_host.h).
+// Mirrors the parts of SceneViewerApplication that assemble and drive the hot path:
+// add_main_pass_deferred (application/scene_viewer_application.cpp:876-991), bake_render_graph
+// (:1167-1318), render_frame (:1540-1611).  The G-buffer (and motion vectors) the reference
+// rasterises are uploaded from host memory by the "gbuffer" pass at the head of the graph.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/granite_b200_host.h"
+#include "clusterer.hpp"
+#include "nccl_collectives.hpp"
+#include "post/aa.hpp"
+#include "post/fxaa.hpp"
+#include "post/hdr.hpp"
+#include "renderer.hpp"
+
+using namespace Granite;
+
+namespace
+{
+thread_local std::string t_error;
+
+int32_t fail(const std::string &msg)
+{
+	t_error = msg;
+	return -1;
+}
+
+struct FixedExposure : HDRDynamicExposureInterface
+{
+	float exposure = 1.0f;
+	float get_exposure() const override { return exposure; }
+};
+} // namespace
+
+struct GrbhViewer
+{
+	GrbhViewerConfig config;
+	std::unique_ptr<Vulkan::Device> device;
+	RenderGraph graph;
+	RenderContext context;
+	LightingParameters lighting;
+	LightClusterer cluster;
+	TemporalJitter jitter;
+	FixedExposure exposure;
+	TaskComposer composer;
+	std::unique_ptr<NcclCollectives> collectives;
+	std::vector<GrbRows> bands;
+	unsigned rank = 0;
+
+	std::vector<std::unique_ptr<PositionalLight>> light_storage;
+	PositionalLightList scene_lights;
+
+	mat4 projection = mat4(1.0f), view = mat4(1.0f);
+	bool baked = false;
+	std::string output_name;
+	const GrbhHostGBuffer *pending_upload = nullptr;
+	std::map<std::string, std::pair<double, int>> timings;
+
+	RenderTextureResource *res_emissive = nullptr, *res_albedo = nullptr, *res_normal = nullptr, *res_pbr = nullptr, *res_depth = nullptr,
+	                      *res_mv = nullptr;
+
+	bool uses_taa() const
+	{
+		return config.post_aa == GRBH_AA_TAA_LOW || config.post_aa == GRBH_AA_TAA_MEDIUM || config.post_aa == GRBH_AA_TAA_HIGH ||
+		       config.post_aa == GRBH_AA_TAA_HIGH_PLUS_FXAA;
+	}
+	bool uses_fxaa() const { return config.post_aa == GRBH_AA_FXAA || config.post_aa == GRBH_AA_TAA_HIGH_PLUS_FXAA; }
+
+	// rows of the full-resolution inputs this rank must hold: its band + the halo the bloom
+	// threshold (and FXAA through the tonemap) reaches into
+	GrbRows input_rows() const
+	{
+		return compute_shard_plan((unsigned)config.width, (unsigned)config.height, bands, rank, uses_fxaa()).lighting;
+	}
+
+	void upload_rows(Vulkan::CommandBuffer &cmd, RenderTextureResource *res, const void *host, unsigned texel)
+	{
+		if (!res || !host)
+			return;
+		auto &view_ = graph.get_physical_texture_resource(*res);
+		GrbRows r = input_rows();
+		size_t pitch = (size_t)config.width * texel;
+		auto *dst = static_cast<uint8_t *>(view_.get_image().get_device_pointer()) + (size_t)r.y0 * pitch;
+		auto *src = static_cast<const uint8_t *>(host) + (size_t)r.y0 * pitch;
+		Vulkan::cuda_ok(cudaMemcpyAsync(dst, src, pitch * (size_t)(r.y1 - r.y0), cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(cmd.get_stream())),
+		                "G-buffer upload");
+	}
+
+	void bake_render_graph();
+	void render_frame(const GrbhHostGBuffer *host, double frame_time);
+};
+
+void GrbhViewer::bake_render_graph()
+{
+	auto physical_buffers = graph.consume_physical_buffers();
+	graph.reset();
+	graph.set_device(device.get());
+	graph.enable_timestamps(config.timestamps != 0);
+
+	ResourceDimensions dim;
+	dim.width = (unsigned)config.width;
+	dim.height = (unsigned)config.height;
+	dim.format = VK_FORMAT_R8G8B8A8_SRGB; // headless swapchain format (application_headless.cpp:207)
+	graph.set_backbuffer_dimensions(dim);
+	if (!bands.empty())
+		graph.set_row_shards(bands, rank, collectives.get(), uses_fxaa());
+
+	// scene.add_render_passes(graph) -> LightClusterer::add_render_passes
+	cluster.set_resolution((unsigned)config.cluster_res[0], (unsigned)config.cluster_res[1], (unsigned)config.cluster_res[2]);
+	cluster.set_scene_lights(&scene_lights);
+	cluster.set_base_render_context(&context);
+	cluster.add_render_passes(graph);
+	lighting.cluster = &cluster;
+	context.set_lighting_parameters(&lighting);
+
+	// ---- add_main_pass_deferred ----
+	AttachmentInfo emissive, albedo, normal, pbr, depth;
+	emissive.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+	albedo.format = VK_FORMAT_R8G8B8A8_SRGB;
+	normal.format = VK_FORMAT_A2B10G10R10_UNORM_PACK32;
+	pbr.format = VK_FORMAT_R8G8_UNORM;
+	depth.format = VK_FORMAT_D32_SFLOAT;
+
+	auto &gbuffer = graph.add_pass("gbuffer", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+	res_emissive = &gbuffer.add_color_output("emissive", emissive);
+	res_albedo = &gbuffer.add_color_output("albedo", albedo);
+	res_normal = &gbuffer.add_color_output("normal", normal);
+	res_pbr = &gbuffer.add_color_output("pbr", pbr);
+	res_depth = &gbuffer.set_depth_stencil_output("depth-transient", depth);
+	gbuffer.set_build_render_pass([this](Vulkan::CommandBuffer &cmd) {
+		if (!pending_upload)
+			return; // inputs already resident from an earlier frame
+		upload_rows(cmd, res_emissive, pending_upload->emissive, 4);
+		upload_rows(cmd, res_albedo, pending_upload->albedo, 4);
+		upload_rows(cmd, res_normal, pending_upload->normal, 4);
+		upload_rows(cmd, res_pbr, pending_upload->pbr, 2);
+		upload_rows(cmd, res_depth, pending_upload->depth, 4);
+	});
+
+	auto &lighting_pass = graph.add_pass("lighting", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+	// The reference lets HDR-main alias emissive (add_color_output(..., "emissive")) and blends in
+	// place.  Here HDR-main is its own image and emissive a read-only input: same bytes moved,
+	// and the uploaded G-buffer stays intact, so a resident G-buffer can be lit again next frame.
+	auto &hdr_main = lighting_pass.add_color_output("HDR-main", emissive);
+	auto &in_emissive = lighting_pass.add_attachment_input("emissive");
+	auto &in_albedo = lighting_pass.add_attachment_input("albedo");
+	auto &in_normal = lighting_pass.add_attachment_input("normal");
+	auto &in_pbr = lighting_pass.add_attachment_input("pbr");
+	auto &in_depth = lighting_pass.add_attachment_input("depth-transient");
+	lighting_pass.set_depth_stencil_input("depth-transient");
+	auto light_iface = std::make_shared<DeferredLightingPass>(context, &cluster);
+	light_iface->set_resources(graph, in_albedo, in_normal, in_pbr, in_depth, hdr_main, &in_emissive);
+	light_iface->set_shard_halo(uses_fxaa() ? 12u : 8u);
+	lighting_pass.set_render_pass_interface(light_iface);
+
+	std::string light_output = "HDR-main";
+
+	// ---- AA before the post chain (TAA) ----
+	PostAAType before = PostAAType::None;
+	switch (config.post_aa)
+	{
+	case GRBH_AA_TAA_LOW: before = PostAAType::TAA_Low; break;
+	case GRBH_AA_TAA_MEDIUM: before = PostAAType::TAA_Medium; break;
+	case GRBH_AA_TAA_HIGH:
+	case GRBH_AA_TAA_HIGH_PLUS_FXAA: before = PostAAType::TAA_High; break;
+	default: break;
+	}
+	res_mv = nullptr;
+	if (uses_taa())
+	{
+		// add_mv_pass: the motion-vector image is an input of this path
+		AttachmentInfo mv;
+		mv.format = VK_FORMAT_R16G16_SFLOAT;
+		auto &mv_pass = graph.add_pass("mv", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+		res_mv = &mv_pass.add_color_output("mv-main", mv);
+		mv_pass.set_build_render_pass([this](Vulkan::CommandBuffer &cmd) {
+			if (pending_upload)
+				upload_rows(cmd, res_mv, pending_upload->mv, 4);
+		});
+	}
+	bool resolved = setup_before_post_chain_antialiasing(before, graph, jitter, 1.0f, light_output, "depth-transient", "mv-main", "HDR-resolved");
+
+	// ---- HDR chain ----
+	std::string chain_input = resolved ? "HDR-resolved" : light_output;
+	HDROptions opts;
+	opts.dynamic_exposure = config.dynamic_exposure != 0;
+	if (config.hdr_bloom)
+		setup_hdr_postprocess_compute(graph, context.get_frame_parameters(), chain_input, "tonemapped", opts, &exposure);
+	else
+	{
+		// BASELINE config 1: a single tonemap pass.  tonemap.frag always samples uBloom; with
+		// bloom off that image is the zero-initialised one nothing ever writes.
+		AttachmentInfo quarter;
+		quarter.format = VK_FORMAT_R16G16B16A16_SFLOAT;
+		quarter.size_class = SizeClass::InputRelative;
+		quarter.size_relative_name = chain_input;
+		quarter.size_x = 0.25f;
+		quarter.size_y = 0.25f;
+		auto &off = graph.add_pass("bloom-disabled", RENDER_GRAPH_QUEUE_COMPUTE_BIT);
+		off.add_storage_texture_output("upsample-0", quarter);
+		off.add_texture_input(chain_input);
+		off.set_build_render_pass([](Vulkan::CommandBuffer &) {});
+		AttachmentInfo tonemap_info;
+		tonemap_info.size_class = SizeClass::InputRelative;
+		tonemap_info.size_relative_name = chain_input;
+		auto &tonemap = graph.add_pass("tonemap", RenderGraph::get_default_post_graphics_queue());
+		auto &out = tonemap.add_color_output("tonemapped", tonemap_info);
+		auto &hdr_res = tonemap.add_texture_input(chain_input);
+		auto &bloom_res = tonemap.add_texture_input("upsample-0");
+		tonemap.set_build_render_pass([this, &out, &hdr_res, &bloom_res](Vulkan::CommandBuffer &cmd) {
+			GrbImage hdr = graph.get_physical_texture_resource(hdr_res).as_grb();
+			GrbImage bloom = graph.get_physical_texture_resource(bloom_res).as_grb();
+			auto &ov = graph.get_physical_texture_resource(out);
+			GrbImage o = ov.as_grb();
+			cmd.check(grb_tonemap(&hdr, &bloom, nullptr, exposure.get_exposure(), &o, graph.is_sharded() ? graph.get_shard_plan().tonemap : GrbRows{ 0, 0 },
+			                      cmd.get_stream_handle()),
+			          "grb_tonemap");
+		});
+	}
+	std::string ui_source = "tonemapped";
+
+	// ---- AA after the post chain (FXAA) ----
+	if (uses_fxaa())
+	{
+		setup_fxaa_postprocess(graph, ui_source, "post-aa-output");
+		ui_source = "post-aa-output";
+	}
+	output_name = ui_source;
+	graph.set_backbuffer_source(ui_source);
+	graph.bake();
+	// keep feed-back buffers (average luminance) across re-bakes
+	graph.install_physical_buffers(std::move(physical_buffers));
+	baked = true;
+}
+
+void GrbhViewer::render_frame(const GrbhHostGBuffer *host, double frame_time)
+{
+	FrameParameters frame = context.get_frame_parameters();
+	frame.frame_time = frame_time;
+	frame.elapsed_time += frame_time;
+	context.set_frame_parameters(frame);
+
+	graph.setup_attachments(*device, nullptr);
+	cluster.setup_render_pass_resources(graph);
+
+	// update_scene: jitter.step, context.set_camera, LightClusterer::refresh
+	jitter.step(projection, view);
+	context.set_camera(projection, view);
+	cluster.refresh(context);
+
+	pending_upload = host;
+	graph.enqueue_render_passes(*device, composer);
+	pending_upload = nullptr;
+
+	if (config.timestamps)
+		for (auto &iv : device->collect_time_intervals())
+		{
+			auto &slot = timings[iv.first];
+			slot.first += iv.second;
+			slot.second++;
+		}
+}
+
+// ----------------------------------------------------------------------------- C API
+#define GRBH_TRY try {
+#define GRBH_CATCH                                  \
+	}                                               \
+	catch (const std::exception &e)                 \
+	{                                               \
+		return fail(e.what());                      \
+	}                                               \
+	catch (...)                                     \
+	{                                               \
+		return fail("unknown C++ exception");       \
+	}
+
+extern "C" const char *grbh_last_error(void)
+{
+	return t_error.c_str();
+}
+
+extern "C" uint16_t grbh_float_to_half(float v)
+{
+	return muglm::floatToHalf(v);
+}
+
+extern "C" int32_t grbh_viewer_create(const GrbhViewerConfig *config, GrbhViewer **out)
+{
+	if (!config || !out || config->width <= 0 || config->height <= 0)
+		return fail("grbh_viewer_create: bad config");
+	GRBH_TRY
+	auto v = std::make_unique<GrbhViewer>();
+	v->config = *config;
+	if (v->config.cluster_res[0] == 0)
+	{
+		v->config.cluster_res[0] = 128; // scene_viewer_application.cpp:407
+		v->config.cluster_res[1] = 64;
+		v->config.cluster_res[2] = 4096;
+	}
+	// cuda_device < 0: host-only viewer (camera / light preparation without touching a GPU)
+	if (config->cuda_device >= 0)
+		v->device = std::make_unique<Vulkan::Device>(config->cuda_device, static_cast<Vulkan::Stream>(config->cuda_stream));
+	v->lighting.directional.color = vec3(6.0f, 5.5f, 4.5f); // scene_viewer_application.cpp:380
+	v->lighting.directional.direction = normalize(vec3(0.3f, 0.8f, 0.5f));
+	*out = v.release();
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" void grbh_viewer_destroy(GrbhViewer *viewer)
+{
+	if (!viewer)
+		return;
+	if (viewer->device)
+		viewer->device->wait_idle();
+	viewer->graph.reset();
+	delete viewer;
+}
+
+extern "C" int32_t grbh_viewer_set_camera(GrbhViewer *v, const float *projection16, const float *view16)
+{
+	if (!v || !projection16 || !view16)
+		return fail("grbh_viewer_set_camera: null");
+	std::memcpy(v->projection.data(), projection16, 64);
+	std::memcpy(v->view.data(), view16, 64);
+	v->context.set_camera(v->projection, v->view);
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_set_directional(GrbhViewer *v, const float *color3, const float *direction3)
+{
+	if (!v || !color3 || !direction3)
+		return fail("grbh_viewer_set_directional: null");
+	v->lighting.directional.color = vec3(color3[0], color3[1], color3[2]);
+	v->lighting.directional.direction = vec3(direction3[0], direction3[1], direction3[2]);
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_set_exposure(GrbhViewer *v, float exposure)
+{
+	if (!v)
+		return fail("null viewer");
+	v->exposure.exposure = exposure;
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_set_lights(GrbhViewer *v, const GrbhLights *l)
+{
+	if (!v || !l || l->count < 0)
+		return fail("grbh_viewer_set_lights: bad arguments");
+	GRBH_TRY
+	v->light_storage.clear();
+	v->scene_lights.clear();
+	for (int i = 0; i < l->count; i++)
+	{
+		vec3 color(l->color[3 * i], l->color[3 * i + 1], l->color[3 * i + 2]);
+		vec3 pos(l->position[3 * i], l->position[3 * i + 1], l->position[3 * i + 2]);
+		PositionalLightInfo info;
+		if (l->is_point[i])
+		{
+			auto p = std::make_unique<PointLight>();
+			p->set_maximum_range(l->cutoff_range);
+			p->set_color(color);
+			info.transform = mat_affine(vec4(1, 0, 0, pos.x), vec4(0, 1, 0, pos.y), vec4(0, 0, 1, pos.z));
+			info.light = p.get();
+			v->light_storage.push_back(std::move(p));
+		}
+		else
+		{
+			auto s = std::make_unique<SpotLight>();
+			s->set_maximum_range(l->cutoff_range);
+			s->set_color(color);
+			s->set_spot_parameters(l->inner_cone[i], l->outer_cone[i]);
+			const float *r = l->rotation + 9 * i; // column-major 3x3
+			info.transform = mat_affine(vec4(r[0], r[3], r[6], pos.x), vec4(r[1], r[4], r[7], pos.y), vec4(r[2], r[5], r[8], pos.z));
+			info.light = s.get();
+			v->light_storage.push_back(std::move(s));
+		}
+		v->scene_lights.push_back(info);
+	}
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_nccl_unique_id(uint8_t out128[128])
+{
+	std::string err;
+	if (!NcclCollectives::get_unique_id(out128, err))
+		return fail(err);
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_init_collectives(GrbhViewer *v, const uint8_t id128[128], int32_t rank, int32_t world_size)
+{
+	if (!v || !id128 || rank < 0 || world_size <= 0 || rank >= world_size)
+		return fail("grbh_viewer_init_collectives: bad arguments");
+	cudaSetDevice(v->device->get_device_index());
+	auto c = std::make_unique<NcclCollectives>();
+	std::string err;
+	if (!c->init(id128, (unsigned)rank, (unsigned)world_size, err))
+		return fail(err);
+	v->collectives = std::move(c);
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_set_row_shards(GrbhViewer *v, const GrbRows *bands, int32_t count, int32_t rank)
+{
+	if (!v || count < 0 || (count && !bands) || (count && (rank < 0 || rank >= count)))
+		return fail("grbh_viewer_set_row_shards: bad arguments");
+	v->bands.assign(bands, bands + count);
+	v->rank = (unsigned)rank;
+	v->baked = false;
+	return 0;
+}
+
+extern "C" int32_t grbh_shard_plan(int32_t width, int32_t height, const GrbRows *bands, int32_t count, int32_t rank, int32_t fxaa, GrbRows *out9)
+{
+	if (width <= 0 || height <= 0 || count < 0 || (count && !bands) || !out9 || (count && (rank < 0 || rank >= count)))
+		return fail("grbh_shard_plan: bad arguments");
+	std::vector<GrbRows> b(bands, bands + count);
+	ShardPlan p = compute_shard_plan((unsigned)width, (unsigned)height, b, (unsigned)rank, fxaa != 0);
+	const GrbRows all[8] = { p.own, p.fxaa, p.tonemap, p.upsample0, p.downsample0, p.threshold, p.lighting, p.lum_grid };
+	for (int i = 0; i < 8; i++)
+		out9[i] = all[i];
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_bake(GrbhViewer *v)
+{
+	if (!v)
+		return fail("null viewer");
+	if (!v->device)
+		return fail("grbh_viewer_bake: host-only viewer (cuda_device < 0) cannot bake");
+	GRBH_TRY
+	cudaSetDevice(v->device->get_device_index());
+	// attachments are set up by the first render_frame (calling setup_attachments here as well
+	// would swap the history images once too often and fake a previous frame)
+	v->bake_render_graph();
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_render_frame(GrbhViewer *v, const GrbhHostGBuffer *host, double frame_time)
+{
+	if (!v || !v->baked)
+		return fail("grbh_viewer_render_frame: viewer not baked");
+	GRBH_TRY
+	cudaSetDevice(v->device->get_device_index());
+	v->render_frame(host, frame_time);
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_read_output(GrbhViewer *v, uint32_t *dst, GrbRows *rows_out)
+{
+	if (!v || !v->baked || !dst)
+		return fail("grbh_viewer_read_output: bad arguments");
+	GRBH_TRY
+	auto &view_ = v->graph.get_physical_texture_resource(v->graph.get_texture_resource(v->output_name));
+	GrbRows r = v->bands.size() > 1 ? v->bands[v->rank] : GrbRows{ 0, v->config.height };
+	size_t pitch = (size_t)v->config.width * 4;
+	auto stream = reinterpret_cast<cudaStream_t>(v->device->get_stream());
+	auto *src = static_cast<const uint8_t *>(view_.get_image().get_device_pointer()) + (size_t)r.y0 * pitch;
+	if (!Vulkan::cuda_ok(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(dst) + (size_t)r.y0 * pitch, src, pitch * (size_t)(r.y1 - r.y0),
+	                                     cudaMemcpyDeviceToHost, stream),
+	                     "output readback"))
+		return fail("cudaMemcpyAsync failed");
+	if (!Vulkan::cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize"))
+		return fail("cudaStreamSynchronize failed");
+	if (rows_out)
+		*rows_out = r;
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_sync(GrbhViewer *v)
+{
+	if (!v)
+		return fail("null viewer");
+	v->device->wait_idle();
+	cudaError_t err = cudaGetLastError();
+	if (err != cudaSuccess)
+		return fail(cudaGetErrorString(err));
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_get_image(GrbhViewer *v, const char *name, GrbImage *out)
+{
+	if (!v || !name || !out || !v->baked)
+		return fail("grbh_viewer_get_image: bad arguments");
+	GRBH_TRY
+	if (!v->graph.has_texture_resource(name))
+		return fail(std::string("no such resource: ") + name);
+	auto &res = v->graph.get_texture_resource(name);
+	*out = v->graph.get_physical_texture_resource(res).as_grb();
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_get_buffer(GrbhViewer *v, const char *name, void **ptr, uint64_t *size)
+{
+	if (!v || !name || !ptr || !v->baked)
+		return fail("grbh_viewer_get_buffer: bad arguments");
+	GRBH_TRY
+	if (!v->graph.has_texture_resource(name))
+		return fail(std::string("no such resource: ") + name);
+	auto &buf = v->graph.get_physical_buffer_resource(v->graph.get_buffer_resource(name));
+	*ptr = buf.get_device_pointer();
+	if (size)
+		*size = buf.get_create_info().size;
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_get_cluster(GrbhViewer *v, GrbClusterParameters *params, GrbClusterBuffers *buffers)
+{
+	if (!v || !v->baked)
+		return fail("grbh_viewer_get_cluster: viewer not baked");
+	if (params)
+		*params = v->cluster.get_cluster_parameters_bindless();
+	if (buffers)
+		*buffers = v->cluster.get_cluster_buffers();
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_get_light_prep(GrbhViewer *v, GrbPositionalLight *records, float *model_rows, uint32_t *type_mask, uint32_t *z_ranges,
+                                              int32_t capacity)
+{
+	if (!v)
+		return fail("null viewer");
+	// host prep only (no GPU work): usable on a machine without a device
+	v->cluster.set_scene_lights(&v->scene_lights);
+	if (v->config.cluster_res[0])
+		v->cluster.set_resolution((unsigned)v->config.cluster_res[0], (unsigned)v->config.cluster_res[1], (unsigned)v->config.cluster_res[2]);
+	v->cluster.refresh(v->context);
+	int n = (int)v->cluster.get_active_light_count();
+	if (n > capacity)
+		return fail("grbh_viewer_get_light_prep: capacity too small");
+	if (records)
+		std::memcpy(records, v->cluster.get_light_records().data(), sizeof(GrbPositionalLight) * n);
+	if (model_rows)
+		std::memcpy(model_rows, v->cluster.get_model_transforms().data(), 48 * (size_t)n);
+	if (type_mask)
+		std::memcpy(type_mask, v->cluster.get_type_mask().data(), sizeof(uint32_t) * ((n + 31) / 32));
+	if (z_ranges)
+		std::memcpy(z_ranges, v->cluster.get_z_ranges().data(), sizeof(uint32_t) * 2 * v->cluster.get_z_ranges().size());
+	return n;
+}
+
+extern "C" int32_t grbh_viewer_get_camera(GrbhViewer *v, GrbCamera *out, float *projection16, float *inv_projection16)
+{
+	if (!v || !out)
+		return fail("grbh_viewer_get_camera: null");
+	const auto &rp = v->context.get_render_parameters();
+	std::memcpy(out->view, rp.view.data(), 64);
+	std::memcpy(out->view_projection, rp.view_projection.data(), 64);
+	std::memcpy(out->inv_view_projection, rp.inv_view_projection.data(), 64);
+	for (int i = 0; i < 3; i++)
+	{
+		out->camera_position[i] = rp.camera_position[i];
+		out->camera_front[i] = rp.camera_front[i];
+	}
+	out->z_near = rp.z_near;
+	out->z_far = rp.z_far;
+	if (projection16)
+		std::memcpy(projection16, rp.projection.data(), 64);
+	if (inv_projection16)
+		std::memcpy(inv_projection16, rp.inv_projection.data(), 64);
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_get_pass_names(GrbhViewer *v, char *buffer, int32_t capacity)
+{
+	if (!v || !v->baked)
+		return fail("viewer not baked");
+	std::string all;
+	for (auto &n : v->graph.get_baked_pass_names())
+		all += n + "\n";
+	if (buffer && capacity > 0)
+		std::snprintf(buffer, (size_t)capacity, "%s", all.c_str());
+	return (int32_t)all.size() + 1;
+}
+
+extern "C" int32_t grbh_viewer_collect_timings(GrbhViewer *v, char *names, int32_t names_capacity, float *total_ms, int32_t *counts, int32_t capacity)
+{
+	if (!v)
+		return fail("null viewer");
+	std::string all;
+	int i = 0;
+	for (auto &kv : v->timings)
+	{
+		if (i < capacity)
+		{
+			if (total_ms)
+				total_ms[i] = (float)kv.second.first;
+			if (counts)
+				counts[i] = kv.second.second;
+		}
+		all += kv.first + "\n";
+		i++;
+	}
+	if (names && names_capacity > 0)
+		std::snprintf(names, (size_t)names_capacity, "%s", all.c_str());
+	v->timings.clear();
+	return i;
+}

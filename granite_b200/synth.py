@@ -122,20 +122,37 @@ def make_scene(width: int, height: int, seed: int = GBUFFER_SEED) -> Scene:
     sph_r = rng.uniform(1.0, 6.0, n_sph)
     sph_z = -rng.uniform(4.0, 150.0, n_sph)
     sph_x = rng.uniform(-0.6, 0.6, n_sph) * (eye[2] - sph_z) * tan_half * aspect
+    a_all = np.einsum("...k,...k", dirs, dirs)
     for cx, cz, r in zip(sph_x, sph_z, sph_r):
         c = np.array([cx, -2.0 + r, cz])
         oc = eye - c
-        b = dirs @ oc
-        a = np.einsum("...k,...k", dirs, dirs)
+        # conservative screen-space box of the sphere so only its pixels are intersected
+        dz = eye[2] - cz
+        if dz > r + 0.5:
+            k = 1.2 * r / (dz - r)
+            px0 = ((-oc[0] / dz - k) / (tan_half * aspect) * 0.5 + 0.5) * width
+            px1 = ((-oc[0] / dz + k) / (tan_half * aspect) * 0.5 + 0.5) * width
+            py0 = ((oc[1] / dz - k) / tan_half * 0.5 + 0.5) * height
+            py1 = ((oc[1] / dz + k) / tan_half * 0.5 + 0.5) * height
+            x0, x1 = int(max(px0 - 2, 0)), int(min(px1 + 3, width))
+            y0, y1 = int(max(py0 - 2, 0)), int(min(py1 + 3, height))
+        else:
+            x0, x1, y0, y1 = 0, width, 0, height
+        if x1 <= x0 or y1 <= y0:
+            continue
+        sub = (slice(y0, y1), slice(x0, x1))
+        d_sub = dirs[sub]
+        b = d_sub @ oc
+        a = a_all[sub]
         cc = oc @ oc - r * r
         disc = b * b - a * cc
         with np.errstate(invalid="ignore"):
             t_s = (-b - np.sqrt(disc)) / a
-        ok = (disc > 0) & (t_s > 0.2) & (t_s < t_hit)
-        t_hit = np.where(ok, t_s, t_hit)
-        p = eye + t_s[..., None] * dirs
+        ok = (disc > 0) & (t_s > 0.2) & (t_s < t_hit[sub])
+        t_hit[sub] = np.where(ok, t_s, t_hit[sub])
+        p = eye + t_s[..., None] * d_sub
         n = (p - c) / r
-        nrm = np.where(ok[..., None], n, nrm)
+        nrm[sub] = np.where(ok[..., None], n, nrm[sub])
 
     sky = ~np.isfinite(t_hit)
     t_safe = np.where(sky, 1.0, t_hit)

@@ -1,0 +1,255 @@
+"""ctypes binding of libgranite_b200_host.so (include/granite_b200_host.h): the application-side
+harness over the C++ host layer (RenderGraph, LightClusterer, pass builders).  This is the
+repo's public end-to-end API: host G-buffer in -> frame on the GPU(s) -> tonemapped image out.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libgranite_b200_host.so")
+
+AA_NONE, AA_FXAA, AA_TAA_LOW, AA_TAA_MEDIUM, AA_TAA_HIGH, AA_TAA_HIGH_PLUS_FXAA = 0, 1, 8, 9, 10, 100
+
+
+class GrbhViewerConfig(C.Structure):
+    _fields_ = [("cuda_device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("post_aa", C.c_int32),
+                ("hdr_bloom", C.c_int32), ("dynamic_exposure", C.c_int32), ("cluster_res", C.c_int32 * 3),
+                ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p)]
+
+
+class GrbhLights(C.Structure):
+    _fields_ = [("count", C.c_int32), ("color", C.c_void_p), ("position", C.c_void_p), ("is_point", C.c_void_p),
+                ("rotation", C.c_void_p), ("inner_cone", C.c_void_p), ("outer_cone", C.c_void_p), ("cutoff_range", C.c_float)]
+
+
+class GrbhHostGBuffer(C.Structure):
+    _fields_ = [("albedo", C.c_void_p), ("normal", C.c_void_p), ("pbr", C.c_void_p), ("depth", C.c_void_p),
+                ("emissive", C.c_void_p), ("mv", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        capi.lib()  # libgranite_b200.so first (the host library links against it)
+        if not os.path.exists(HOST_LIB_PATH):
+            raise capi.GrbError(f"{HOST_LIB_PATH} is missing: run `python -m granite_b200.build`")
+        _lib = C.CDLL(HOST_LIB_PATH)
+        _lib.grbh_last_error.restype = C.c_char_p
+        _lib.grbh_float_to_half.restype = C.c_uint16
+        _lib.grbh_float_to_half.argtypes = [C.c_float]
+        _lib.grbh_viewer_destroy.restype = None
+        _lib.grbh_viewer_destroy.argtypes = [C.c_void_p]
+        _lib.grbh_viewer_render_frame.argtypes = [C.c_void_p, C.POINTER(GrbhHostGBuffer), C.c_double]
+        _lib.grbh_viewer_set_exposure.argtypes = [C.c_void_p, C.c_float]
+    return _lib
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise capi.GrbError(f"{what}: {lib().grbh_last_error().decode()}")
+    return rc
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def band_partition(height: int, world: int, align: int = 64):
+    """Contiguous row bands aligned to `align` full-res rows (= 2 rows of the 1/32 bloom level,
+    SURVEY.md §8e), remainder on the last rank."""
+    n_units = (height + align - 1) // align
+    per = n_units // world
+    if per == 0:
+        raise ValueError("frame too small for this many ranks")
+    bands = []
+    y = 0
+    for r in range(world):
+        y1 = height if r == world - 1 else (y + per * align)
+        bands.append((y, y1))
+        y = y1
+    return bands
+
+
+PLAN_FIELDS = ("own", "fxaa", "tonemap", "upsample0", "downsample0", "threshold", "lighting", "lum_grid")
+
+
+def shard_plan(width, height, bands, rank, fxaa=False) -> dict:
+    """Rows of every stage one rank computes (host math of granite_b200/host/shard_plan.cpp)."""
+    arr = (capi.GrbRows * max(len(bands), 1))(*[capi.GrbRows(a, b) for a, b in bands])
+    out = (capi.GrbRows * 8)()
+    _check(lib().grbh_shard_plan(width, height, arr, len(bands), rank, int(fxaa), out), "grbh_shard_plan")
+    return {k: (out[i].y0, out[i].y1) for i, k in enumerate(PLAN_FIELDS)}
+
+
+class Viewer:
+    def __init__(self, width, height, post_aa=AA_NONE, hdr_bloom=True, dynamic_exposure=True, cuda_device=0,
+                 cluster_res=(128, 64, 4096), timestamps=False, stream=None):
+        cfg = GrbhViewerConfig()
+        cfg.cuda_device = cuda_device
+        cfg.width, cfg.height = width, height
+        cfg.post_aa = post_aa
+        cfg.hdr_bloom = int(hdr_bloom)
+        cfg.dynamic_exposure = int(dynamic_exposure)
+        cfg.cluster_res = (C.c_int32 * 3)(*cluster_res)
+        cfg.timestamps = int(timestamps)
+        cfg.cuda_stream = stream
+        self.width, self.height = width, height
+        self._h = C.c_void_p()
+        _check(lib().grbh_viewer_create(C.byref(cfg), C.byref(self._h)), "grbh_viewer_create")
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            lib().grbh_viewer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_camera(self, projection, view):
+        p = np.ascontiguousarray(projection, np.float32)
+        v = np.ascontiguousarray(view, np.float32)
+        _check(lib().grbh_viewer_set_camera(self._h, _vp(p), _vp(v)), "grbh_viewer_set_camera")
+
+    def set_directional(self, color, direction):
+        c = np.ascontiguousarray(color, np.float32)
+        d = np.ascontiguousarray(direction, np.float32)
+        _check(lib().grbh_viewer_set_directional(self._h, _vp(c), _vp(d)), "grbh_viewer_set_directional")
+
+    def set_exposure(self, e):
+        _check(lib().grbh_viewer_set_exposure(self._h, C.c_float(e)), "grbh_viewer_set_exposure")
+
+    def set_lights(self, lights, cutoff=1e10):
+        n = len(lights.color)
+        arrs = dict(color=np.ascontiguousarray(lights.color, np.float32), position=np.ascontiguousarray(lights.position, np.float32),
+                    is_point=np.ascontiguousarray(lights.is_point, np.uint8), rotation=np.ascontiguousarray(lights.rot, np.float32),
+                    inner=np.ascontiguousarray(lights.inner_cone, np.float32), outer=np.ascontiguousarray(lights.outer_cone, np.float32))
+        l = GrbhLights(n, _vp(arrs["color"]), _vp(arrs["position"]), _vp(arrs["is_point"]), _vp(arrs["rotation"]),
+                       _vp(arrs["inner"]), _vp(arrs["outer"]), cutoff)
+        _check(lib().grbh_viewer_set_lights(self._h, C.byref(l)), "grbh_viewer_set_lights")
+
+    def init_collectives(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().grbh_viewer_init_collectives(self._h, buf, rank, world), "grbh_viewer_init_collectives")
+
+    def set_row_shards(self, bands, rank):
+        arr = (capi.GrbRows * len(bands))(*[capi.GrbRows(a, b) for a, b in bands])
+        _check(lib().grbh_viewer_set_row_shards(self._h, arr, len(bands), rank), "grbh_viewer_set_row_shards")
+
+    def bake(self):
+        _check(lib().grbh_viewer_bake(self._h), "grbh_viewer_bake")
+
+    @staticmethod
+    def host_gbuffer(albedo, normal, pbr, depth, emissive, mv=None) -> GrbhHostGBuffer:
+        """Arguments: objects with a data pointer (numpy arrays or pinned torch tensors)."""
+        def ptr(x):
+            if x is None:
+                return None
+            return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+        return GrbhHostGBuffer(ptr(albedo), ptr(normal), ptr(pbr), ptr(depth), ptr(emissive), ptr(mv))
+
+    def render_frame(self, host_gbuffer: GrbhHostGBuffer | None, frame_time=1.0 / 60.0):
+        arg = C.byref(host_gbuffer) if host_gbuffer is not None else None
+        _check(lib().grbh_viewer_render_frame(self._h, arg, C.c_double(frame_time)), "grbh_viewer_render_frame")
+
+    def read_output(self, dst):
+        """dst: full-frame uint32 buffer (numpy array or pinned torch tensor). Returns the (y0, y1) band written."""
+        r = capi.GrbRows()
+        p = dst.data_ptr() if hasattr(dst, "data_ptr") else dst.ctypes.data
+        _check(lib().grbh_viewer_read_output(self._h, C.c_void_p(p), C.byref(r)), "grbh_viewer_read_output")
+        return r.y0, r.y1
+
+    def sync(self):
+        _check(lib().grbh_viewer_sync(self._h), "grbh_viewer_sync")
+
+    def image(self, name) -> capi.GrbImage:
+        img = capi.GrbImage()
+        _check(lib().grbh_viewer_get_image(self._h, name.encode(), C.byref(img)), f"grbh_viewer_get_image({name})")
+        return img
+
+    def download_image(self, name) -> np.ndarray:
+        """Device image -> numpy (H, W[, C]) of the format's natural integer type."""
+        import torch
+
+        img = self.image(name)
+        bpp = capi.TEXEL_BYTES[img.format]
+        self.sync()
+        out = np.empty((img.height, img.width * bpp), np.uint8)
+        t = torch.empty((img.height, img.row_pitch), dtype=torch.uint8, device="cuda")
+        rt = C.CDLL("libcudart.so.12")
+        rt.cudaMemcpy(C.c_void_p(t.data_ptr()), C.c_void_p(img.data), C.c_size_t(img.height * img.row_pitch), 3)
+        out[:] = t.cpu().numpy()[:, : img.width * bpp]
+        if bpp == 8:
+            return out.view(np.uint16).reshape(img.height, img.width, 4)
+        if bpp == 2:
+            return out.view(np.uint16).reshape(img.height, img.width)
+        if img.format == capi.FORMAT_D32_SFLOAT:
+            return out.view(np.float32).reshape(img.height, img.width)
+        return out.view(np.uint32).reshape(img.height, img.width)
+
+    def buffer(self, name):
+        ptr = C.c_void_p()
+        size = C.c_uint64()
+        _check(lib().grbh_viewer_get_buffer(self._h, name.encode(), C.byref(ptr), C.byref(size)), f"grbh_viewer_get_buffer({name})")
+        return ptr.value, size.value
+
+    def download_buffer(self, name, dtype=np.float32, count=None) -> np.ndarray:
+        ptr, size = self.buffer(name)
+        self.sync()
+        n = size if count is None else count * np.dtype(dtype).itemsize
+        out = np.empty(n, np.uint8)
+        rt = C.CDLL("libcudart.so.12")
+        rt.cudaMemcpy(_vp(out), C.c_void_p(ptr), C.c_size_t(n), 2)
+        return out.view(dtype)
+
+    def cluster(self):
+        p = capi.GrbClusterParameters()
+        b = capi.GrbClusterBuffers()
+        _check(lib().grbh_viewer_get_cluster(self._h, C.byref(p), C.byref(b)), "grbh_viewer_get_cluster")
+        return p, b
+
+    def light_prep(self, capacity=4096):
+        recs = np.zeros(capacity, capi.LIGHT_DTYPE)
+        model = np.zeros((capacity, 12), np.float32)
+        tmask = np.zeros(capacity // 32 + 1, np.uint32)
+        zr = np.zeros((capacity + 1, 2), np.uint32)
+        n = _check(lib().grbh_viewer_get_light_prep(self._h, _vp(recs), _vp(model), _vp(tmask), _vp(zr), capacity), "grbh_viewer_get_light_prep")
+        return n, recs[:n], model[:n], tmask[: (n + 31) // 32], zr[: max(n, 1)]
+
+    def camera(self):
+        cam = capi.GrbCamera()
+        proj = np.zeros(16, np.float32)
+        inv_proj = np.zeros(16, np.float32)
+        _check(lib().grbh_viewer_get_camera(self._h, C.byref(cam), _vp(proj), _vp(inv_proj)), "grbh_viewer_get_camera")
+        return cam, proj.reshape(4, 4), inv_proj.reshape(4, 4)
+
+    def pass_names(self):
+        buf = C.create_string_buffer(4096)
+        _check(lib().grbh_viewer_get_pass_names(self._h, buf, 4096), "grbh_viewer_get_pass_names")
+        return [n for n in buf.value.decode().split("\n") if n]
+
+    def collect_timings(self):
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        cnt = (C.c_int32 * 64)()
+        n = _check(lib().grbh_viewer_collect_timings(self._h, names, 4096, ms, cnt, 64), "grbh_viewer_collect_timings")
+        nm = [x for x in names.value.decode().split("\n") if x]
+        return {nm[i]: (ms[i], cnt[i]) for i in range(min(n, len(nm)))}
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _check(lib().grbh_nccl_unique_id(buf), "grbh_nccl_unique_id")
+    return bytes(buf)

@@ -165,10 +165,13 @@ typedef struct GrbGBuffer
 	GrbImage depth;    /* D32_SFLOAT, reverse-Z, 0 = far */
 	float directional_color[3];     /* DirectionalLightPush, renderer.cpp:1073-1103 */
 	float directional_direction[3];
+	/* Initial contents of the blend destination ("emissive", B10G11R11_UFLOAT).  data == NULL:
+	 * `hdr` itself holds them (HDR-main aliases emissive in the reference) and is updated in place. */
+	GrbImage emissive;
 } GrbGBuffer;
 
-/* hdr: B10G11R11_UFLOAT, read-modify-write ("HDR-main" aliases "emissive",
- * scene_viewer_application.cpp:956-963). */
+/* hdr: B10G11R11_UFLOAT; read-modify-write when gbuffer->emissive.data is NULL ("HDR-main"
+ * aliases "emissive", scene_viewer_application.cpp:956-963), write-only otherwise. */
 int32_t grb_deferred_lighting(const GrbGBuffer *gbuffer, const GrbCamera *cam,
                               const GrbClusterParameters *params, const GrbClusterBuffers *buf,
                               const GrbImage *hdr, GrbRows rows, void *stream);

@@ -1,0 +1,123 @@
+/*
+ * granite_b200_host.h -- C entry points of libgranite_b200_host.so: the application-side
+ * harness that drives the C++ host layer (granite_b200/host/: RenderGraph, LightClusterer,
+ * DeferredLightRenderer, setup_hdr_postprocess_compute, setup_taa_resolve,
+ * setup_fxaa_postprocess) the way SceneViewerApplication does in the reference
+ * (application/scene_viewer_application.cpp:876-991 add_main_pass_deferred, :1167-1318
+ * bake_render_graph, :1540-1611 render_frame).  The G-buffer, which the reference rasterises,
+ * is an INPUT here: it is uploaded from host memory by a "gbuffer" pass at the head of the graph.
+ *
+ * This is what bench.py's end-to-end measurement and the graph-level tests call.  All
+ * functions return 0 on success, negative on failure (grbh_last_error()).
+ */
+#ifndef GRANITE_B200_HOST_H_
+#define GRANITE_B200_HOST_H_
+
+#include <stdint.h>
+
+#include "granite_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct GrbhViewer GrbhViewer;
+
+typedef enum GrbhPostAA
+{
+	GRBH_AA_NONE = 0,
+	GRBH_AA_FXAA = 1,
+	GRBH_AA_TAA_LOW = 8,
+	GRBH_AA_TAA_MEDIUM = 9,
+	GRBH_AA_TAA_HIGH = 10,
+	/* BASELINE config 5: TAA (pre-tonemap) and FXAA (post-tonemap) chained explicitly */
+	GRBH_AA_TAA_HIGH_PLUS_FXAA = 100
+} GrbhPostAA;
+
+typedef struct GrbhViewerConfig
+{
+	int32_t cuda_device;
+	int32_t width, height;
+	int32_t post_aa;            /* GrbhPostAA */
+	int32_t hdr_bloom;          /* 1: full bloom chain; 0: tonemap only (BASELINE config 1) */
+	int32_t dynamic_exposure;   /* HDROptions::dynamic_exposure */
+	int32_t cluster_res[3];     /* LightClusterer::set_resolution; viewer default 128,64,4096 */
+	int32_t timestamps;         /* RenderGraph::enable_timestamps */
+	void *cuda_stream;          /* NULL: the device creates its own stream */
+} GrbhViewerConfig;
+
+/* Raw light list as the application owns it (before the clusterer sorts/packs it). */
+typedef struct GrbhLights
+{
+	int32_t count;
+	const float *color;       /* count x 3 */
+	const float *position;    /* count x 3 */
+	const uint8_t *is_point;  /* count */
+	const float *rotation;    /* count x 9, column-major node rotation (spots) */
+	const float *inner_cone;  /* count */
+	const float *outer_cone;  /* count */
+	float cutoff_range;       /* PositionalLight::set_maximum_range */
+} GrbhLights;
+
+/* Host-memory G-buffer of the full frame (pinned memory makes the uploads asynchronous).
+ * Only the rows this rank needs (its band + halo) are copied.  mv may be NULL without TAA. */
+typedef struct GrbhHostGBuffer
+{
+	const uint32_t *albedo;
+	const uint32_t *normal;
+	const uint16_t *pbr;
+	const float *depth;
+	const uint32_t *emissive;
+	const uint32_t *mv; /* R16G16_SFLOAT */
+} GrbhHostGBuffer;
+
+const char *grbh_last_error(void);
+
+int32_t grbh_viewer_create(const GrbhViewerConfig *config, GrbhViewer **out);
+void grbh_viewer_destroy(GrbhViewer *viewer);
+
+/* RenderContext::set_camera(projection, view) (renderer/render_context.cpp:54-87). */
+int32_t grbh_viewer_set_camera(GrbhViewer *viewer, const float *projection16, const float *view16);
+int32_t grbh_viewer_set_directional(GrbhViewer *viewer, const float *color3, const float *direction3);
+int32_t grbh_viewer_set_lights(GrbhViewer *viewer, const GrbhLights *lights);
+int32_t grbh_viewer_set_exposure(GrbhViewer *viewer, float exposure);
+
+/* Row sharding (multi-GPU): bands[r] = backbuffer rows of rank r.  Must precede bake. */
+int32_t grbh_nccl_unique_id(uint8_t out128[128]);
+int32_t grbh_viewer_init_collectives(GrbhViewer *viewer, const uint8_t id128[128], int32_t rank, int32_t world_size);
+int32_t grbh_viewer_set_row_shards(GrbhViewer *viewer, const GrbRows *bands, int32_t count, int32_t rank);
+
+/* The row plan of one rank of a row-sharded frame (granite_b200/host/shard_plan.hpp): out8 =
+ * {own, fxaa, tonemap, upsample0, downsample0, threshold, lighting, lum_grid}.  Pure host math. */
+int32_t grbh_shard_plan(int32_t width, int32_t height, const GrbRows *bands, int32_t count, int32_t rank, int32_t fxaa, GrbRows *out8);
+
+/* bake_render_graph: declares the passes, bakes, allocates attachments. */
+int32_t grbh_viewer_bake(GrbhViewer *viewer);
+
+/* One frame: (optionally) upload the host G-buffer rows, refresh the clusterer, record every
+ * pass on the stream.  Asynchronous; ordering with later calls is stream order. */
+int32_t grbh_viewer_render_frame(GrbhViewer *viewer, const GrbhHostGBuffer *host_gbuffer, double frame_time);
+/* Copies this rank's rows of the final image (R8G8B8A8) to host memory laid out as the full
+ * frame (row pitch = width*4) and waits for it. rows_out receives the band. */
+int32_t grbh_viewer_read_output(GrbhViewer *viewer, uint32_t *dst_full_frame, GrbRows *rows_out);
+int32_t grbh_viewer_sync(GrbhViewer *viewer);
+
+/* Introspection for tests: device views of graph resources by name (valid until next bake). */
+int32_t grbh_viewer_get_image(GrbhViewer *viewer, const char *resource_name, GrbImage *out);
+int32_t grbh_viewer_get_buffer(GrbhViewer *viewer, const char *resource_name, void **device_ptr, uint64_t *size);
+int32_t grbh_viewer_get_cluster(GrbhViewer *viewer, GrbClusterParameters *params, GrbClusterBuffers *buffers);
+/* Copies the sorted/packed host-side light data of the last refresh (for host-prep parity tests). */
+int32_t grbh_viewer_get_light_prep(GrbhViewer *viewer, GrbPositionalLight *records, float *model_rows, uint32_t *type_mask, uint32_t *z_ranges,
+                                   int32_t capacity);
+int32_t grbh_viewer_get_camera(GrbhViewer *viewer, GrbCamera *out, float *projection16, float *inv_projection16);
+/* Names of the baked passes, '\n' separated. Returns the length needed. */
+int32_t grbh_viewer_get_pass_names(GrbhViewer *viewer, char *buffer, int32_t capacity);
+/* Per-pass GPU time of the frames since the last call (needs config.timestamps):
+ * writes up to `capacity` (name, total ms, count) triples. Returns the number of passes. */
+int32_t grbh_viewer_collect_timings(GrbhViewer *viewer, char *names, int32_t names_capacity, float *total_ms, int32_t *counts, int32_t capacity);
+uint16_t grbh_float_to_half(float v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

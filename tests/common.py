@@ -15,6 +15,29 @@ def build_case(oracle, width, height, n_lights, spot_fraction=0.0):
     return scene, cam, lights, prep
 
 
+def oracle_camera_from_viewer(oracle, viewer_obj):
+    """The camera block the HOST LAYER derived (RenderContext::set_camera), repackaged for the
+    oracle: matrices are inputs of the hot path, so both sides must see the same bits (the host
+    layer's mat4 inverse is not the reference's cofactor expansion and differs by an ulp)."""
+    gcam, proj, inv_proj = viewer_obj.camera()
+    cam = oracle.Camera()
+    cam.projection[:] = proj.reshape(-1).tolist()
+    cam.inv_projection[:] = inv_proj.reshape(-1).tolist()
+    cam.view[:] = list(gcam.view)
+    cam.view_projection[:] = list(gcam.view_projection)
+    cam.inv_view_projection[:] = list(gcam.inv_view_projection)
+    cam.camera_position[:] = list(gcam.camera_position)
+    cam.camera_front[:] = list(gcam.camera_front)
+    cam.z_near, cam.z_far = gcam.z_near, gcam.z_far
+    return cam
+
+
+def build_case_for_viewer(oracle, viewer_obj, scene, lights):
+    cam = oracle_camera_from_viewer(oracle, viewer_obj)
+    prep = oracle.prepare_lights(cam, lights, res=synth.CLUSTER_RES)
+    return cam, prep
+
+
 def build_lights_case(oracle, aspect, n_lights, spot_fraction=0.0):
     """Camera + lights + oracle host prep only (no G-buffer)."""
     import math

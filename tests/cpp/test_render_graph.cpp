@@ -1,0 +1,216 @@
+// CPU-only checks of the RenderGraph declaration surface / bake logic (no device is touched:
+// bake() only needs one when a pass interface wants setup(device)).
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+#include "../../granite_b200/host/post/aa.hpp"
+#include "../../granite_b200/host/post/fxaa.hpp"
+#include "../../granite_b200/host/post/hdr.hpp"
+#include "../../granite_b200/host/render_graph.hpp"
+
+using namespace Granite;
+
+#define CHECK(cond)                                                         \
+	do                                                                      \
+	{                                                                       \
+		if (!(cond))                                                        \
+		{                                                                   \
+			std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+			std::exit(1);                                                   \
+		}                                                                   \
+	} while (0)
+
+template <typename F>
+static bool throws_logic_error(F &&f)
+{
+	try
+	{
+		f();
+	}
+	catch (const std::logic_error &)
+	{
+		return true;
+	}
+	return false;
+}
+
+static std::string join(const std::vector<std::string> &v)
+{
+	std::string s;
+	for (auto &x : v)
+		s += x + ",";
+	return s;
+}
+
+int main()
+{
+	ResourceDimensions dim;
+	dim.width = 3840;
+	dim.height = 2160;
+	dim.format = VK_FORMAT_R8G8B8A8_SRGB;
+
+	// --- add_pass is idempotent by name; declarators build the dependency DAG ---
+	{
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		auto &a = graph.add_pass("a", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+		CHECK(&a == &graph.add_pass("a", RENDER_GRAPH_QUEUE_COMPUTE_BIT));
+		CHECK(graph.find_pass("a") == &a && graph.find_pass("zzz") == nullptr);
+		AttachmentInfo hdr;
+		hdr.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+		a.add_color_output("HDR-main", hdr);
+		// a pass that does not contribute to the backbuffer is culled
+		auto &unused = graph.add_pass("unused", RENDER_GRAPH_QUEUE_COMPUTE_BIT);
+		BufferInfo bi;
+		bi.size = 64;
+		unused.add_storage_output("junk", bi);
+		FrameParameters frame;
+		HDROptions opts;
+		setup_hdr_postprocess_compute(graph, frame, "HDR-main", "tonemapped", opts);
+		setup_fxaa_postprocess(graph, "tonemapped", "post-aa-output");
+		graph.set_backbuffer_source("post-aa-output");
+		graph.bake();
+		CHECK(join(graph.get_baked_pass_names()) == "a,bloom-compute,tonemap,fxaa,");
+
+		// ceil(parent * scale) sizing (render_graph.cpp:3160-3171), incl. the non-2:1 step 135 -> 68
+		auto size_of = [&](const char *name) {
+			auto d = graph.get_resource_dimensions(graph.get_texture_resource(name));
+			return std::make_pair(d.width, d.height);
+		};
+		CHECK(size_of("threshold") == std::make_pair(1920u, 1080u));
+		CHECK(size_of("downsample-0") == std::make_pair(960u, 540u));
+		CHECK(size_of("downsample-2") == std::make_pair(240u, 135u));
+		CHECK(size_of("downsample-3") == std::make_pair(120u, 68u));
+		CHECK(size_of("tonemapped") == std::make_pair(3840u, 2160u));
+		// undefined formats inherit the backbuffer's
+		CHECK(graph.get_resource_dimensions(graph.get_texture_resource("tonemapped")).format == VK_FORMAT_R8G8B8A8_SRGB);
+		// FXAA flags its input for a UNORM alias view
+		CHECK(graph.get_texture_resource("tonemapped").get_attachment_info().flags & ATTACHMENT_INFO_UNORM_SRGB_ALIAS_BIT);
+		// physical indices: outputs distinct, culled resources unassigned
+		CHECK(graph.get_texture_resource("threshold").get_physical_index() != graph.get_texture_resource("downsample-0").get_physical_index());
+		CHECK(graph.get_buffer_resource("junk").get_physical_index() == RenderResource::Unused);
+	}
+
+	// --- 1080p pyramid: 1920x1080 -> 960x540, 480x270, 240x135, 120x68, 60x34 ---
+	{
+		RenderGraph graph;
+		ResourceDimensions d2 = dim;
+		d2.width = 1920;
+		d2.height = 1080;
+		graph.set_backbuffer_dimensions(d2);
+		AttachmentInfo hdr;
+		hdr.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+		graph.add_pass("a", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("HDR-main", hdr);
+		FrameParameters frame;
+		setup_hdr_postprocess(graph, frame, "HDR-main", "tonemapped", HDROptions{});
+		graph.set_backbuffer_source("tonemapped");
+		graph.bake();
+		auto d3 = graph.get_resource_dimensions(graph.get_texture_resource("downsample-3"));
+		CHECK(d3.width == 60 && d3.height == 34);
+	}
+
+	// --- read-modify-write aliasing shares the physical image ---
+	{
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo info;
+		info.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+		graph.add_pass("gbuffer", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("emissive", info);
+		graph.add_pass("lighting", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("HDR-main", info, "emissive");
+		graph.set_backbuffer_source("HDR-main");
+		graph.bake();
+		CHECK(graph.get_texture_resource("emissive").get_physical_index() == graph.get_texture_resource("HDR-main").get_physical_index());
+		CHECK(join(graph.get_baked_pass_names()) == "gbuffer,lighting,");
+	}
+
+	// --- misuse throws std::logic_error like the reference ---
+	{
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo info;
+		graph.add_pass("a", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("out", info);
+		graph.set_backbuffer_source("nope");
+		CHECK(throws_logic_error([&] { graph.bake(); }));
+		graph.set_backbuffer_source("out");
+		graph.find_pass("a")->add_texture_input("never-written");
+		CHECK(throws_logic_error([&] { graph.bake(); }));
+	}
+	{
+		RenderGraph graph; // cycle a -> b -> a
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo info;
+		auto &a = graph.add_pass("a", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+		auto &b = graph.add_pass("b", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+		a.add_color_output("x", info);
+		a.add_texture_input("y");
+		b.add_color_output("y", info);
+		b.add_texture_input("x");
+		graph.set_backbuffer_source("x");
+		CHECK(throws_logic_error([&] { graph.bake(); }));
+	}
+	{
+		RenderGraph graph; // executing before bake
+		Vulkan::Device *none = nullptr;
+		TaskComposer composer;
+		CHECK(throws_logic_error([&] { graph.enqueue_render_passes(*none, composer); }));
+		CHECK(throws_logic_error([&] { graph.set_row_shards({ GrbRows{ 0, 100 }, GrbRows{ 120, 200 } }, 0, nullptr); }));
+	}
+
+	// --- row shards scale per resource and tile every level exactly ---
+	{
+		struct NoCollectives : RenderGraphCollectives
+		{
+			unsigned get_rank() const override { return 0; }
+			unsigned get_world_size() const override { return 8; }
+			bool all_gather_rows(Vulkan::CommandBuffer &, Vulkan::ImageView &, const std::vector<GrbRows> &) override { return true; }
+			bool all_reduce_sum(Vulkan::CommandBuffer &, float *, size_t) override { return true; }
+		} coll;
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		std::vector<GrbRows> bands;
+		for (int r = 0; r < 8; r++)
+			bands.push_back(GrbRows{ r * 256, r == 7 ? 2160 : (r + 1) * 256 });
+		graph.set_row_shards(bands, 3, &coll);
+		CHECK(graph.is_sharded() && graph.get_shard_count() == 8 && graph.get_shard_rank() == 3);
+		for (unsigned hgt : { 2160u, 1080u, 540u })
+		{
+			int expect = 0;
+			for (unsigned r = 0; r < 8; r++)
+			{
+				GrbRows rows = graph.shard_rows_for_rank(r, hgt);
+				CHECK(rows.y0 == expect);
+				expect = rows.y1;
+			}
+			CHECK(expect == (int)hgt);
+		}
+		GrbRows halo = graph.shard_rows_for(2160, 8);
+		CHECK(halo.y0 == 3 * 256 - 8 && halo.y1 == 4 * 256 + 8);
+		GrbRows edge = graph.shard_rows_for_rank(0, 2160, 8);
+		CHECK(edge.y0 == 0 && edge.y1 == 264);
+	}
+
+	// --- PostAAType dispatch ---
+	{
+		CHECK(post_aa_type_is_supported(PostAAType::TAA_High) && !post_aa_type_is_supported(PostAAType::SMAA_Ultra));
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		TemporalJitter jitter;
+		CHECK(throws_logic_error([&] { setup_after_post_chain_antialiasing(PostAAType::SMAA_High, graph, jitter, 1.0f, "a", "d", "o"); }));
+		CHECK(!setup_before_post_chain_antialiasing(PostAAType::FXAA, graph, jitter, 1.0f, "a", "d", "mv", "o"));
+		CHECK(setup_before_post_chain_antialiasing(PostAAType::TAA_High, graph, jitter, 1.0f, "HDR-main", "depth", "mv", "HDR-resolved"));
+		CHECK(graph.find_pass("taa-resolve") != nullptr);
+		// 16-phase table: phases cycle, matrices are pure sub-pixel translations
+		mat4 p = perspective(0.785398f, 16.0f / 9.0f, 0.0625f, InfiniteFarPlane), v(1.0f);
+		for (int i = 0; i < 40; i++)
+		{
+			jitter.step(p, v);
+			CHECK(jitter.get_jitter_phase() < 16);
+			const mat4 &j = jitter.get_jitter_matrix();
+			CHECK(j[0][0] == 1.0f && j[1][1] == 1.0f && std::fabs(j[3][0]) <= 1.0f / 3840.0f + 1e-9f && std::fabs(j[3][1]) <= 1.0f / 2160.0f + 1e-9f);
+		}
+	}
+	std::printf("render graph checks passed\n");
+	return 0;
+}
