@@ -397,11 +397,17 @@ __global__ void __launch_bounds__(1024) z_range_scatter_kernel(const uint2 *__re
 		hi[z] = 0u;
 	}
 	__syncthreads();
-	for (int i = threadIdx.x; i < num_ranges; i += blockDim.x)
+	// one warp per light, lanes spread over that light's consecutive slices: the atomics of a
+	// warp then hit 32 different shared-memory words instead of serialising on a few (lights are
+	// depth-sorted, so neighbouring lights cover nearly the same slices)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, num_warps = blockDim.x >> 5;
+	for (int i = warp; i < num_ranges; i += num_warps)
 	{
 		uint2 r = __ldg(&z_ranges[i]);
+		if (r.x > r.y)
+			continue;
 		uint32_t zend = min(r.y, (uint32_t)(res_z - 1));
-		for (uint32_t z = r.x; z <= zend && r.x <= r.y; z++)
+		for (uint32_t z = r.x + lane; z <= zend; z += 32u)
 		{
 			atomicMin(&lo[z], (uint32_t)i);
 			atomicMax(&hi[z], (uint32_t)i);

@@ -112,14 +112,26 @@ GRB_DEV float ufloat_to_f32(uint32_t v)
 	return __uint_as_float(((e + 112u) << 23) | (m << (23 - MBITS)));
 }
 
+// The 11/10-bit unsigned floats are binary16 with the sign and the low 4/5 mantissa bits cut off
+// (same 5-bit exponent, bias 15, same denormal rule), so the hardware fp16 converters do all of
+// the work: decode = shift the code into a half and widen (exact, denormals/inf/NaN included);
+// encode = clamp negatives, convert round-toward-zero (never rounds up to inf) and drop the low
+// bits (truncation composes).  Bit-identical to f32_to_ufloat / ufloat_to_f32 above, which stay
+// as the readable definition.
 GRB_DEV uint32_t pack_r11g11b10(float r, float g, float b)
 {
-	return f32_to_ufloat<6>(r) | (f32_to_ufloat<6>(g) << 11) | (f32_to_ufloat<5>(b) << 22);
+	// fmaxf(NaN, 0) is 0 in CUDA; keep NaN a NaN like the reference conversion
+	uint32_t hr = __half_as_ushort(__float2half_rz(r != r ? r : fmaxf(r, 0.0f)));
+	uint32_t hg = __half_as_ushort(__float2half_rz(g != g ? g : fmaxf(g, 0.0f)));
+	uint32_t hb = __half_as_ushort(__float2half_rz(b != b ? b : fmaxf(b, 0.0f)));
+	return ((hr & 0x7fffu) >> 4) | (((hg & 0x7fffu) >> 4) << 11) | (((hb & 0x7fffu) >> 5) << 22);
 }
 
 GRB_DEV float3 unpack_r11g11b10(uint32_t p)
 {
-	return make_float3(ufloat_to_f32<6>(p & 0x7ffu), ufloat_to_f32<6>((p >> 11) & 0x7ffu), ufloat_to_f32<5>(p >> 22));
+	return make_float3(__half2float(__ushort_as_half((unsigned short)((p & 0x7ffu) << 4))),
+	                   __half2float(__ushort_as_half((unsigned short)(((p >> 11) & 0x7ffu) << 4))),
+	                   __half2float(__ushort_as_half((unsigned short)((p >> 22) << 5))));
 }
 
 GRB_DEV float h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }

@@ -23,6 +23,8 @@
 // differences.
 #include "grb_common.cuh"
 
+#include <cstdlib>
+
 namespace grb
 {
 __device__ float g_srgb8_to_linear[256];
@@ -60,8 +62,9 @@ struct Surface
 {
 	float3 pos, N, V;
 	float3 F0, one_minus_F0;
-	float3 diffuse_k;   // base_color * (1 - metallic) / PI
-	float m2;           // roughness'^4
+	float3 diffuse_k;       // base_color * (1 - metallic) / PI
+	float m2_minus_1;       // roughness'^4 - 1
+	float c_gd;             // 0.25 * roughness'^4 / PI  (numerator of G*D)
 	float one_minus_k, k, Vk; // Schlick-GGX visibility pieces
 };
 
@@ -78,25 +81,27 @@ __device__ __forceinline__ uint32_t cluster_mask_range(uint32_t mask, uint32_t r
 }
 
 // Cook-Torrance terms shared by the directional and the positional lights (lighting.h:26-46,
-// point.h:121-141, spot.h:124-144).  Returns (specular + diffuse) * NoL, to be scaled by the
-// light's colour/attenuation.
-__device__ __forceinline__ float3 brdf(const Surface &s, float3 L)
+// point.h:121-141, spot.h:124-144), arranged for the fewest issue slots -- the pass is bound by
+// instruction issue, not by HBM:
+//   specular + diffuse = F*G*D + (1-F)*dk = dk + F*(G*D - dk)
+//   D*G = (m2 / (PI d^2)) * (0.25 / max(Vk*Lk, 1e-3)),  d = NoH^2 (m2 - 1) + 1
+// Returns that sum per channel and NoL; the caller scales by NoL * colour * attenuation.
+__device__ __forceinline__ float3 brdf(const Surface &s, float3 L, float &NoL)
 {
 	float3 h = make_float3(s.V.x + L.x, s.V.y + L.y, s.V.z + L.z);
 	float inv_h = rsqrtf(dot3(h, h));
-	float NoL = fminf(fmaxf(dot3(s.N, L), 0.001f), 1.0f);
+	NoL = fminf(fmaxf(dot3(s.N, L), 0.001f), 1.0f);
 	float NoH = fminf(fmaxf(dot3(s.N, h) * inv_h, 0.0001f), 1.0f);
 	float HoV = fminf(fmaxf(dot3(h, s.V) * inv_h, 0.001f), 1.0f);
 	float f = 1.0f - HoV;
 	float f2 = f * f;
 	float f5 = f2 * f2 * f;
-	float3 F = make_float3(s.F0.x + s.one_minus_F0.x * f5, s.F0.y + s.one_minus_F0.y * f5, s.F0.z + s.one_minus_F0.z * f5);
-	float d = (NoH * s.m2 - NoH) * NoH + 1.0f;
-	float D = __fdividef(s.m2, kPi * d * d);
-	float G = __fdividef(0.25f, fmaxf(s.Vk * (NoL * s.one_minus_k + s.k), 0.001f));
-	float GD = G * D;
-	return make_float3(NoL * (F.x * GD + (1.0f - F.x) * s.diffuse_k.x), NoL * (F.y * GD + (1.0f - F.y) * s.diffuse_k.y),
-	                   NoL * (F.z * GD + (1.0f - F.z) * s.diffuse_k.z));
+	float d = fmaf(NoH * NoH, s.m2_minus_1, 1.0f);
+	float vl = fmaxf(s.Vk * fmaf(NoL, s.one_minus_k, s.k), 0.001f);
+	float GD = __fdividef(s.c_gd, d * d * vl);
+	float Fx = fmaf(s.one_minus_F0.x, f5, s.F0.x), Fy = fmaf(s.one_minus_F0.y, f5, s.F0.y), Fz = fmaf(s.one_minus_F0.z, f5, s.F0.z);
+	return make_float3(fmaf(Fx, GD - s.diffuse_k.x, s.diffuse_k.x), fmaf(Fy, GD - s.diffuse_k.y, s.diffuse_k.y),
+	                   fmaf(Fz, GD - s.diffuse_k.z, s.diffuse_k.z));
 }
 
 // World position of a pixel and its cluster coordinates.  The tile index and Z slice are part
@@ -171,10 +176,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		dst = __ldg(&p.emissive.at(x, y));
 
 		base_color = make_float3(s_srgb[a8 & 0xffu], s_srgb[(a8 >> 8) & 0xffu], s_srgb[(a8 >> 16) & 0xffu]);
-		s.N = make_float3(fsub(fmul(fdiv((float)(n10 & 0x3ffu), 1023.0f), 2.0f), 1.0f), fsub(fmul(fdiv((float)((n10 >> 10) & 0x3ffu), 1023.0f), 2.0f), 1.0f),
-		                  fsub(fmul(fdiv((float)((n10 >> 20) & 0x3ffu), 1023.0f), 2.0f), 1.0f));
-		const float metallic = fdiv((float)(mr & 0xffu), 255.0f);
-		const float roughness_in = fdiv((float)(mr >> 8), 255.0f);
+		// UNORM decode: these feed only the BRDF (not the bit-exact indices), a multiply by the
+		// reciprocal is within half an ulp of the division
+		s.N = make_float3(fmaf((float)(n10 & 0x3ffu), 2.0f / 1023.0f, -1.0f), fmaf((float)((n10 >> 10) & 0x3ffu), 2.0f / 1023.0f, -1.0f),
+		                  fmaf((float)((n10 >> 20) & 0x3ffu), 2.0f / 1023.0f, -1.0f));
+		const float metallic = (float)(mr & 0xffu) * (1.0f / 255.0f);
+		const float roughness_in = (float)(mr >> 8) * (1.0f / 255.0f);
 
 		int tile_index, z_index;
 		s.pos = reconstruct_position_and_cluster(p, x, y, depth, tile_index, z_index);
@@ -189,7 +196,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		s.V = make_float3(v.x * inv_v, v.y * inv_v, v.z * inv_v);
 		float rough = roughness_in * 0.75f + 0.25f;
 		float mm = rough * rough;
-		s.m2 = mm * mm;
+		float m2 = mm * mm;
+		s.m2_minus_1 = m2 - 1.0f;
+		s.c_gd = m2 * (0.25f * kInvPi);
 		float r1 = rough + 1.0f;
 		s.k = r1 * r1 * 0.125f;
 		s.one_minus_k = 1.0f - s.k;
@@ -202,10 +211,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		s.diffuse_k = make_float3(base_color.x * dk, base_color.y * dk, base_color.z * dk);
 
 		// ---- draw 1: directional.frag (LIGHTING_NO_AMBIENT, no shadows, VOLUMETRIC_DIFFUSE_FALLBACK) ----
-		float3 b = brdf(s, p.dir_dir);
+		float NoL;
+		float3 b = brdf(s, p.dir_dir, NoL);
 		float3 e = unpack_r11g11b10(dst);
-		dst = pack_r11g11b10(e.x + p.dir_color.x * b.x + base_color.x * 0.05f, e.y + p.dir_color.y * b.y + base_color.y * 0.05f,
-		                     e.z + p.dir_color.z * b.z + base_color.z * 0.05f);
+		dst = pack_r11g11b10(e.x + p.dir_color.x * NoL * b.x + base_color.x * 0.05f, e.y + p.dir_color.y * NoL * b.y + base_color.y * 0.05f,
+		                     e.z + p.dir_color.z * NoL * b.z + base_color.z * 0.05f);
 	}
 
 	// ---- draw 2: clustering.frag, warp-uniform walk over the union of the lanes' masks ----
@@ -225,35 +235,38 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		{
 			const int bit = __ffs(wmask) - 1;
 			wmask &= wmask - 1u;
-			const bool mine = (own >> bit) & 1u;
 			const float4 *lp = reinterpret_cast<const float4 *>(p.lights + (i * 32 + bit));
-			const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2); // color|scale_bias, position|offset_radius, direction|inv_radius
+			const float4 l1 = __ldg(lp + 1), l2 = __ldg(lp + 2); // position|offset_radius, direction|inv_radius
 			float3 l = make_float3(l1.x - s.pos.x, l1.y - s.pos.y, l1.z - s.pos.z);
 			float d2 = dot3(l, l);
+			// quick reject: beyond the light's radius the falloff is exactly 0 (point.h:41-43); most lights
+			// of a 30x34-pixel cluster tile do not reach this 8x4 block, so the warp usually leaves here
+			const bool near = ((own >> bit) & 1u) && (d2 * l2.w * l2.w < 1.0f);
+			if (!__any_sync(0xffffffffu, near))
+				continue;
+			const float4 l0 = __ldg(lp); // color|spot scale_bias
 			float inv_d = rsqrtf(d2);
-			float light_dist = fmaxf(0.1f, d2 * inv_d);
-			float t = __saturatef((light_dist * l2.w - 0.9f) * (1.0f / (1.0f - 0.9f)));
-			float falloff = 1.0f - t * t * (3.0f - 2.0f * t);
+			float inv_ld = fminf(inv_d, 10.0f); // 1 / max(0.1, dist)
+			float xr = fmaxf(0.1f, d2 * inv_d) * l2.w;
+			float t = __saturatef(fmaf(xr, 1.0f / (1.0f - 0.9f), -0.9f / (1.0f - 0.9f)));
+			float falloff = fmaf(-t * t, fmaf(-2.0f, t, 3.0f), 1.0f);
 			float3 L = make_float3(l.x * inv_d, l.y * inv_d, l.z * inv_d);
 			if (!((tm >> bit) & 1u))
 			{
 				// spot.h:34-84: cone term from the packed fp16 scale/bias
 				float2 sb = __half22float2(*reinterpret_cast<const __half2 *>(&l0.w));
 				float cone_angle = -(L.x * l2.x + L.y * l2.y + L.z * l2.z);
-				float cone = __saturatef(cone_angle * sb.x + sb.y);
+				float cone = __saturatef(fmaf(cone_angle, sb.x, sb.y));
 				falloff *= cone * cone;
 			}
-			const bool contributes = mine && falloff > 0.0f;
-			if (__any_sync(0xffffffffu, contributes))
+			float NoL;
+			float3 b = brdf(s, L, NoL);
+			float w = NoL * falloff * inv_ld * inv_ld;
+			if (near && falloff > 0.0f)
 			{
-				float atten = __fdividef(falloff, light_dist * light_dist);
-				float3 b = brdf(s, L);
-				if (contributes)
-				{
-					acc.x += l0.x * atten * b.x;
-					acc.y += l0.y * atten * b.y;
-					acc.z += l0.z * atten * b.z;
-				}
+				acc.x = fmaf(l0.x * w, b.x, acc.x);
+				acc.y = fmaf(l0.y * w, b.y, acc.y);
+				acc.z = fmaf(l0.z * w, b.z, acc.z);
 			}
 		}
 	}
@@ -265,6 +278,251 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 	}
 	else if (inside && p.emissive.p != p.hdr.p)
 		p.hdr.at(x, y) = __ldg(&p.emissive.at(x, y)); // sky keeps the attachment value
+}
+// ---------------------------------------------------------------------------------------------
+// Two pixels per thread, packed fp32 (FFMA2 / FMUL2 / FADD2 of sm_100).
+//
+// The pass is bound by instruction issue (ncu: ~80 % issue utilisation, 3 % DRAM), and ~60 % of
+// the issued instructions are fp32 multiply/add.  Blackwell issues TWO fp32 operations per
+// FFMA2-class instruction, so the kernel below carries two horizontally adjacent pixels per
+// thread in float2 lanes: the per-light vector math (light vector, distances, half vector, the
+// three dot products, Fresnel, the GGX terms) is issued once for both, and the per-light
+// control overhead (mask walk, record loads, votes) is amortised over twice the pixels.  A warp
+// covers a 16x4 pixel block, a CTA 64x4.  Results are the same function as the 1-pixel kernel;
+// lanes differ only in fp32 rounding of reassociated terms, far below the B10G11R11 step.
+using f2 = float2;
+__device__ __forceinline__ f2 mk2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 rsqrt2(f2 a) { return make_float2(rsqrtf(a.x), rsqrtf(a.y)); }
+__device__ __forceinline__ f2 clamp2(f2 a, float lo, float hi) { return make_float2(fminf(fmaxf(a.x, lo), hi), fminf(fmaxf(a.y, lo), hi)); }
+__device__ __forceinline__ f2 dot3_2(f2 ax, f2 ay, f2 az, f2 bx, f2 by, f2 bz) { return fma2(az, bz, fma2(ay, by, mul2(ax, bx))); }
+
+struct Surface2
+{
+	f2 npx, npy, npz; // -position
+	f2 Nx, Ny, Nz, Vx, Vy, Vz;
+	f2 F0x, F0y, F0z, oFx, oFy, oFz; // F0, 1 - F0
+	f2 dkx, dky, dkz, ndkx, ndky, ndkz; // diffuse_k and its negation
+	f2 m2m1, cgd, omk, k, Vk;
+};
+
+// dk + F * (G*D - dk) per channel for both pixels; NoL returned for the caller's weight.
+__device__ __forceinline__ void brdf2(const Surface2 &s, f2 Lx, f2 Ly, f2 Lz, f2 &NoL, f2 &tx, f2 &ty, f2 &tz)
+{
+	f2 hx = add2(s.Vx, Lx), hy = add2(s.Vy, Ly), hz = add2(s.Vz, Lz);
+	f2 inv_h = rsqrt2(dot3_2(hx, hy, hz, hx, hy, hz));
+	NoL = clamp2(dot3_2(s.Nx, s.Ny, s.Nz, Lx, Ly, Lz), 0.001f, 1.0f);
+	f2 NoH = clamp2(mul2(dot3_2(s.Nx, s.Ny, s.Nz, hx, hy, hz), inv_h), 0.0001f, 1.0f);
+	f2 HoV = clamp2(mul2(dot3_2(hx, hy, hz, s.Vx, s.Vy, s.Vz), inv_h), 0.001f, 1.0f);
+	f2 f = fma2(HoV, mk2(-1.0f), mk2(1.0f));
+	f2 fsq = mul2(f, f);
+	f2 f5 = mul2(mul2(fsq, fsq), f);
+	f2 d = fma2(mul2(NoH, NoH), s.m2m1, mk2(1.0f));
+	f2 vl = mul2(s.Vk, fma2(NoL, s.omk, s.k));
+	vl = make_float2(fmaxf(vl.x, 0.001f), fmaxf(vl.y, 0.001f));
+	f2 den = mul2(mul2(d, d), vl);
+	f2 GD = mul2(s.cgd, make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y)));
+	f2 Fx = fma2(s.oFx, f5, s.F0x), Fy = fma2(s.oFy, f5, s.F0y), Fz = fma2(s.oFz, f5, s.F0z);
+	tx = fma2(Fx, add2(GD, s.ndkx), s.dkx);
+	ty = fma2(Fy, add2(GD, s.ndky), s.dky);
+	tz = fma2(Fz, add2(GD, s.ndkz), s.dkz);
+}
+
+struct PixelSetup
+{
+	bool lit;
+	uint32_t dst, rx, ry;
+	int cluster_base;
+	float3 pos, N, V, F0, dk, base_color;
+	float m2m1, cgd, omk, k, Vk;
+};
+
+// Everything the 1-pixel kernel does before its light loop, for one pixel.
+__device__ __forceinline__ PixelSetup setup_pixel(const LightingParams &p, const float *s_srgb, int x, int y, bool inside, float depth, uint32_t a8,
+                                                 uint32_t n10, uint32_t mr, uint32_t emissive)
+{
+	PixelSetup q;
+	q.lit = inside && depth != 0.0f;
+	q.dst = emissive;
+	q.rx = 0xffffffffu;
+	q.ry = 0u;
+	q.cluster_base = 0;
+	q.pos = q.N = q.V = q.F0 = q.dk = q.base_color = make_float3(0.f, 0.f, 0.f);
+	q.m2m1 = q.cgd = q.omk = q.k = q.Vk = 0.0f;
+	if (!q.lit)
+		return q;
+	q.base_color = make_float3(s_srgb[a8 & 0xffu], s_srgb[(a8 >> 8) & 0xffu], s_srgb[(a8 >> 16) & 0xffu]);
+	q.N = make_float3(fmaf((float)(n10 & 0x3ffu), 2.0f / 1023.0f, -1.0f), fmaf((float)((n10 >> 10) & 0x3ffu), 2.0f / 1023.0f, -1.0f),
+	                  fmaf((float)((n10 >> 20) & 0x3ffu), 2.0f / 1023.0f, -1.0f));
+	const float metallic = (float)(mr & 0xffu) * (1.0f / 255.0f);
+	const float roughness_in = (float)(mr >> 8) * (1.0f / 255.0f);
+	int tile_index, z_index;
+	q.pos = reconstruct_position_and_cluster(p, x, y, depth, tile_index, z_index);
+	q.cluster_base = tile_index * p.n32;
+	uint2 zr = __ldg(&p.cluster_range[z_index]);
+	q.rx = zr.x;
+	q.ry = zr.y;
+	float3 v = make_float3(p.camera_pos.x - q.pos.x, p.camera_pos.y - q.pos.y, p.camera_pos.z - q.pos.z);
+	float inv_v = rsqrtf(dot3(v, v));
+	q.V = make_float3(v.x * inv_v, v.y * inv_v, v.z * inv_v);
+	float rough = roughness_in * 0.75f + 0.25f;
+	float mm = rough * rough;
+	float m2 = mm * mm;
+	q.m2m1 = m2 - 1.0f;
+	q.cgd = m2 * (0.25f * kInvPi);
+	float r1 = rough + 1.0f;
+	q.k = r1 * r1 * 0.125f;
+	q.omk = 1.0f - q.k;
+	float NoV = fminf(fmaxf(dot3(q.N, q.V), 0.001f), 1.0f);
+	q.Vk = NoV * q.omk + q.k;
+	q.F0 = make_float3(0.04f * (1.0f - metallic) + q.base_color.x * metallic, 0.04f * (1.0f - metallic) + q.base_color.y * metallic,
+	                   0.04f * (1.0f - metallic) + q.base_color.z * metallic);
+	float dk = (1.0f - metallic) * kInvPi;
+	q.dk = make_float3(q.base_color.x * dk, q.base_color.y * dk, q.base_color.z * dk);
+	return q;
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(const LightingParams p)
+{
+	__shared__ float s_srgb[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x)
+		s_srgb[i] = g_srgb8_to_linear[i];
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int x = ((blockIdx.x * kWarpsPerCta + warp) * 8 + (lane & 7)) * 2; // pixels x and x + 1 (width is even on this path)
+	const int y = p.y0 + blockIdx.y * 4 + (lane >> 3);
+	const bool inside = x < p.hdr.w && y < p.y1;
+
+	float2 depth = make_float2(0.f, 0.f);
+	uint2 a8 = make_uint2(0u, 0u), n10 = make_uint2(0u, 0u), em = make_uint2(0u, 0u);
+	uint32_t mr2 = 0u;
+	if (inside)
+	{
+		depth = __ldg(reinterpret_cast<const float2 *>(&p.depth.at(x, y)));
+		if (depth.x != 0.0f || depth.y != 0.0f)
+		{
+			a8 = __ldg(reinterpret_cast<const uint2 *>(&p.albedo.at(x, y)));
+			n10 = __ldg(reinterpret_cast<const uint2 *>(&p.normal.at(x, y)));
+			mr2 = __ldg(reinterpret_cast<const uint32_t *>(&p.pbr.at(x, y)));
+		}
+		em = __ldg(reinterpret_cast<const uint2 *>(&p.emissive.at(x, y)));
+	}
+	PixelSetup A = setup_pixel(p, s_srgb, x, y, inside, depth.x, a8.x, n10.x, mr2 & 0xffffu, em.x);
+	PixelSetup B = setup_pixel(p, s_srgb, x + 1, y, inside, depth.y, a8.y, n10.y, mr2 >> 16, em.y);
+
+	Surface2 s;
+	s.npx = make_float2(-A.pos.x, -B.pos.x); s.npy = make_float2(-A.pos.y, -B.pos.y); s.npz = make_float2(-A.pos.z, -B.pos.z);
+	s.Nx = make_float2(A.N.x, B.N.x); s.Ny = make_float2(A.N.y, B.N.y); s.Nz = make_float2(A.N.z, B.N.z);
+	s.Vx = make_float2(A.V.x, B.V.x); s.Vy = make_float2(A.V.y, B.V.y); s.Vz = make_float2(A.V.z, B.V.z);
+	s.F0x = make_float2(A.F0.x, B.F0.x); s.F0y = make_float2(A.F0.y, B.F0.y); s.F0z = make_float2(A.F0.z, B.F0.z);
+	s.oFx = make_float2(1.0f - A.F0.x, 1.0f - B.F0.x); s.oFy = make_float2(1.0f - A.F0.y, 1.0f - B.F0.y); s.oFz = make_float2(1.0f - A.F0.z, 1.0f - B.F0.z);
+	s.dkx = make_float2(A.dk.x, B.dk.x); s.dky = make_float2(A.dk.y, B.dk.y); s.dkz = make_float2(A.dk.z, B.dk.z);
+	s.ndkx = make_float2(-A.dk.x, -B.dk.x); s.ndky = make_float2(-A.dk.y, -B.dk.y); s.ndkz = make_float2(-A.dk.z, -B.dk.z);
+	s.m2m1 = make_float2(A.m2m1, B.m2m1); s.cgd = make_float2(A.cgd, B.cgd);
+	s.omk = make_float2(A.omk, B.omk); s.k = make_float2(A.k, B.k); s.Vk = make_float2(A.Vk, B.Vk);
+
+	// ---- draw 1: directional light for both pixels ----
+	uint32_t dstA = A.dst, dstB = B.dst;
+	{
+		f2 NoL, tx, ty, tz;
+		brdf2(s, mk2(p.dir_dir.x), mk2(p.dir_dir.y), mk2(p.dir_dir.z), NoL, tx, ty, tz);
+		if (A.lit)
+		{
+			float3 e = unpack_r11g11b10(dstA);
+			dstA = pack_r11g11b10(e.x + p.dir_color.x * NoL.x * tx.x + A.base_color.x * 0.05f, e.y + p.dir_color.y * NoL.x * ty.x + A.base_color.y * 0.05f,
+			                      e.z + p.dir_color.z * NoL.x * tz.x + A.base_color.z * 0.05f);
+		}
+		if (B.lit)
+		{
+			float3 e = unpack_r11g11b10(dstB);
+			dstB = pack_r11g11b10(e.x + p.dir_color.x * NoL.y * tx.y + B.base_color.x * 0.05f, e.y + p.dir_color.y * NoL.y * ty.y + B.base_color.y * 0.05f,
+			                      e.z + p.dir_color.z * NoL.y * tz.y + B.base_color.z * 0.05f);
+		}
+	}
+
+	// ---- draw 2: warp-uniform walk over the union of all 64 pixels' masks ----
+	const uint32_t loA = A.rx >> 5, hiA = A.ry >> 5, loB = B.rx >> 5, hiB = B.ry >> 5;
+	int z_start = (int)__reduce_min_sync(0xffffffffu, min(loA, loB));
+	int z_end = (int)__reduce_max_sync(0xffffffffu, max(A.lit ? hiA : 0u, B.lit ? hiB : 0u));
+	z_end = min(z_end, p.n32 - 1);
+	float3 accA = make_float3(0.f, 0.f, 0.f), accB = make_float3(0.f, 0.f, 0.f);
+	for (int i = z_start; i <= z_end; i++)
+	{
+		uint32_t ownA = 0u, ownB = 0u;
+		if (A.lit && (uint32_t)i >= loA && (uint32_t)i <= hiA)
+			ownA = cluster_mask_range(__ldg(&p.bitmask[A.cluster_base + i]), A.rx, A.ry, 32u * (uint32_t)i);
+		if (B.lit && (uint32_t)i >= loB && (uint32_t)i <= hiB)
+			ownB = cluster_mask_range(__ldg(&p.bitmask[B.cluster_base + i]), B.rx, B.ry, 32u * (uint32_t)i);
+		uint32_t wmask = __reduce_or_sync(0xffffffffu, ownA | ownB);
+		const uint32_t tm = __ldg(&p.type_mask[i]);
+		while (wmask)
+		{
+			const int bit = __ffs(wmask) - 1;
+			wmask &= wmask - 1u;
+			const float4 *lp = reinterpret_cast<const float4 *>(p.lights + (i * 32 + bit));
+			const float4 l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+			f2 lx = add2(mk2(l1.x), s.npx), ly = add2(mk2(l1.y), s.npy), lz = add2(mk2(l1.z), s.npz);
+			f2 d2 = dot3_2(lx, ly, lz, lx, ly, lz);
+			const float inv_r2 = l2.w * l2.w;
+			const bool nearA = ((ownA >> bit) & 1u) && (d2.x * inv_r2 < 1.0f);
+			const bool nearB = ((ownB >> bit) & 1u) && (d2.y * inv_r2 < 1.0f);
+			if (!__any_sync(0xffffffffu, nearA || nearB))
+				continue;
+			const float4 l0 = __ldg(lp);
+			f2 inv_d = rsqrt2(d2);
+			f2 inv_ld = make_float2(fminf(inv_d.x, 10.0f), fminf(inv_d.y, 10.0f));
+			f2 dist = mul2(d2, inv_d);
+			f2 xr = mul2(make_float2(fmaxf(dist.x, 0.1f), fmaxf(dist.y, 0.1f)), mk2(l2.w));
+			f2 t = fma2(xr, mk2(1.0f / (1.0f - 0.9f)), mk2(-0.9f / (1.0f - 0.9f)));
+			t = make_float2(__saturatef(t.x), __saturatef(t.y));
+			f2 falloff = fma2(mul2(mul2(t, t), fma2(mk2(-2.0f), t, mk2(3.0f))), mk2(-1.0f), mk2(1.0f));
+			f2 Lx = mul2(lx, inv_d), Ly = mul2(ly, inv_d), Lz = mul2(lz, inv_d);
+			if (!((tm >> bit) & 1u))
+			{
+				float2 sb = __half22float2(*reinterpret_cast<const __half2 *>(&l0.w));
+				f2 cone_angle = mul2(dot3_2(Lx, Ly, Lz, mk2(l2.x), mk2(l2.y), mk2(l2.z)), mk2(-1.0f));
+				f2 cone = fma2(cone_angle, mk2(sb.x), mk2(sb.y));
+				cone = make_float2(__saturatef(cone.x), __saturatef(cone.y));
+				falloff = mul2(falloff, mul2(cone, cone));
+			}
+			f2 NoL, tx, ty, tz;
+			brdf2(s, Lx, Ly, Lz, NoL, tx, ty, tz);
+			f2 w = mul2(mul2(NoL, falloff), mul2(inv_ld, inv_ld));
+			if (nearA && falloff.x > 0.0f)
+			{
+				accA.x = fmaf(l0.x * w.x, tx.x, accA.x);
+				accA.y = fmaf(l0.y * w.x, ty.x, accA.y);
+				accA.z = fmaf(l0.z * w.x, tz.x, accA.z);
+			}
+			if (nearB && falloff.y > 0.0f)
+			{
+				accB.x = fmaf(l0.x * w.y, tx.y, accB.x);
+				accB.y = fmaf(l0.y * w.y, ty.y, accB.y);
+				accB.z = fmaf(l0.z * w.y, tz.y, accB.z);
+			}
+		}
+	}
+
+	if (inside)
+	{
+		uint2 out = make_uint2(dstA, dstB);
+		if (A.lit)
+		{
+			float3 e = unpack_r11g11b10(dstA);
+			out.x = pack_r11g11b10(e.x + accA.x, e.y + accA.y, e.z + accA.z);
+		}
+		if (B.lit)
+		{
+			float3 e = unpack_r11g11b10(dstB);
+			out.y = pack_r11g11b10(e.x + accB.x, e.y + accB.y, e.z + accB.z);
+		}
+		// sky pixels carry the emissive value through (identical bits when blending in place)
+		if (A.lit || B.lit || p.emissive.p != p.hdr.p)
+			*reinterpret_cast<uint2 *>(&p.hdr.at(x, y)) = out;
+	}
 }
 } // namespace
 
@@ -357,6 +615,18 @@ extern "C" int32_t grb_deferred_lighting(const GrbGBuffer *g, const GrbCamera *c
 	p.y0 = rows.y0;
 	p.y1 = rows.y1;
 
+	// two pixels per thread (packed fp32) whenever rows can be addressed as aligned pixel pairs
+	static const bool force_1px = getenv("GRB_LIGHTING_1PX") != nullptr;
+	auto aligned8 = [](const void *ptr, int pitch_bytes) { return (reinterpret_cast<uintptr_t>(ptr) % 8) == 0 && (pitch_bytes % 8) == 0; };
+	const bool pairs = !force_1px && (w % 2) == 0 && aligned8(g->albedo.data, g->albedo.row_pitch) && aligned8(g->normal.data, g->normal.row_pitch) &&
+	                   aligned8(g->depth.data, g->depth.row_pitch) && (reinterpret_cast<uintptr_t>(g->pbr.data) % 4) == 0 && (g->pbr.row_pitch % 4) == 0 &&
+	                   aligned8(hdr->data, hdr->row_pitch) && (!g->emissive.data || aligned8(g->emissive.data, g->emissive.row_pitch));
+	if (pairs)
+	{
+		dim3 grid2((w / 2 + 8 * kWarpsPerCta - 1) / (8 * kWarpsPerCta), (rows.y1 - rows.y0 + 3) / 4, 1);
+		deferred_lighting2_kernel<<<grid2, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);
+		return check_launch("grb_deferred_lighting");
+	}
 	dim3 grid((w + 8 * kWarpsPerCta - 1) / (8 * kWarpsPerCta), (rows.y1 - rows.y0 + 3) / 4, 1);
 	deferred_lighting_kernel<<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);
 	return check_launch("grb_deferred_lighting");

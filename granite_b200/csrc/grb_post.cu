@@ -167,6 +167,43 @@ __global__ void __launch_bounds__(64) luminance_kernel(View<const uint2> d3, flo
 	luminance_tail(s, threadIdx.x, size_x, size_y, inv_sx, inv_sy, lum, lerp, lo, hi);
 }
 
+// Same function, restructured for latency: the reference's single 64-thread group is a serial
+// chain of ~32 dependent texture fetches per thread.  Here 256 threads first sample the whole
+// (w/2 x h/2) grid into shared memory (independent loads, one barrier), then 64 of them add their
+// strided samples in the reference's (y-iter, x-iter) order and run the same tree -- identical
+// association, so identical bits.
+constexpr int kLumFastThreads = 256;
+constexpr int kLumFastMaxSamples = 8192; // 32 KiB of shared memory
+
+__global__ void __launch_bounds__(kLumFastThreads) luminance_fast_kernel(View<const uint2> d3, float *lum, float lerp, float lo, float hi)
+{
+	__shared__ float grid[kLumFastMaxSamples];
+	__shared__ float s[64];
+	const int size_x = d3.w / 2, size_y = d3.h / 2;
+	const float inv_sx = 1.0f / (float)size_x, inv_sy = 1.0f / (float)size_y;
+	for (int i = threadIdx.x; i < size_x * size_y; i += kLumFastThreads)
+	{
+		int sy = i / size_x, sx = i - sy * size_x;
+		grid[i] = luminance_sample(d3, sx, sy, inv_sx, inv_sy);
+	}
+	__syncthreads();
+	if (threadIdx.x < 64)
+	{
+		const int iter_y = (size_y + 7) >> 3, iter_x = (size_x + 7) >> 3;
+		const int lx = threadIdx.x & 7, ly = threadIdx.x >> 3;
+		float total = 0.0f;
+		for (int y = 0; y < iter_y; y++)
+			for (int x = 0; x < iter_x; x++)
+			{
+				int sx = x * 8 + lx, sy = y * 8 + ly;
+				if (sx < size_x && sy < size_y)
+					total += grid[sy * size_x + sx];
+			}
+		s[threadIdx.x] = total;
+	}
+	luminance_tail(s, threadIdx.x, size_x, size_y, inv_sx, inv_sy, lum, lerp, lo, hi);
+}
+
 // Sharded form, step 1: every thread samples one grid texel of the rows this rank owns.
 __global__ void __launch_bounds__(kBlockX *kBlockY) luminance_grid_kernel(View<const uint2> d3, float *grid, int y0, int y1)
 {
@@ -227,6 +264,89 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) tonemap_kernel(View<const ui
 	else
 		px = float_to_unorm8(r) | (float_to_unorm8(g) << 8) | (float_to_unorm8(bl) << 16) | 0xff000000u;
 	out.at(x, y) = px;
+}
+
+// Vectorised tonemap: one thread produces 4 horizontally adjacent pixels (16-byte HDR load,
+// 16-byte store) and shares the bloom taps between them -- at an exact 1/4-resolution bloom image
+// the four pixels' bilinear footprints cover only 3 columns x 2 rows.  Weights are computed per
+// pixel with the same exact fp32 expressions as the generic kernel; the tone curve and the sRGB
+// OETF use the fast reciprocal / lg2 / ex2 units (error ~1e-4 LSB, the bar is 1 LSB), because
+// with the accurate powf this streaming pass was issue-bound at 8 % of the HBM roofline.
+__device__ __forceinline__ float uncharted2_fast(float x)
+{
+	const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+	return __fdividef(fmaf(x, fmaf(A, x, C * B), D * E), fmaf(x, fmaf(A, x, B), D * F)) - E / F;
+}
+
+__device__ __forceinline__ uint32_t srgb8_fast(float c)
+{
+	c = __saturatef(c); // also NaN -> 0
+	float s = c <= 0.0031308f ? c * (12.92f * 255.0f) : fmaf(__powf(c, 1.0f / 2.4f), 1.055f * 255.0f, -0.055f * 255.0f);
+	return (uint32_t)min(__float2int_rd(s + 0.5f), 255);
+}
+
+__device__ __forceinline__ uint32_t unorm8_fast(float c)
+{
+	return (uint32_t)__float2int_rd(fmaf(__saturatef(c), 255.0f, 0.5f));
+}
+
+template <bool DynamicExposure, bool SrgbTarget>
+__global__ void __launch_bounds__(kBlockX *kBlockY) tonemap4_kernel(View<const uint32_t> hdr, View<const uint2> bloom, const float *__restrict__ lum,
+                                                                   float exposure, View<uint32_t> out, int y0, int y1, float inv_w, float inv_h)
+{
+	const int x4 = (blockIdx.x * kBlockX + threadIdx.x) * 4;
+	const int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x4 >= out.w || y >= y1)
+		return;
+	const uint4 h4 = __ldg(reinterpret_cast<const uint4 *>(&hdr.at(x4, y)));
+	const uint32_t hp[4] = { h4.x, h4.y, h4.z, h4.w };
+
+	// bloom rows (shared by the 4 pixels)
+	const float v = ((float)y + 0.5f) * inv_h;
+	const float fy = fsub(fmul(v, (float)bloom.h), 0.5f);
+	const float fly = floorf(fy);
+	const float wb = fsub(fy, fly);
+	const int by = (int)fly;
+	const int r0 = iclamp(by, 0, bloom.h - 1), r1 = iclamp(by + 1, 0, bloom.h - 1);
+	// bloom columns k-1, k, k+1 with k = x4 / 4
+	const int k = x4 >> 2;
+	const int c0 = iclamp(k - 1, 0, bloom.w - 1), c1 = iclamp(k, 0, bloom.w - 1), c2 = iclamp(k + 1, 0, bloom.w - 1);
+	float3 top[3], bot[3];
+	{
+		const int cols[3] = { c0, c1, c2 };
+#pragma unroll
+		for (int i = 0; i < 3; i++)
+		{
+			float4 a = unpack_rgba16f(__ldg(&bloom.at(cols[i], r0)));
+			float4 b = unpack_rgba16f(__ldg(&bloom.at(cols[i], r1)));
+			top[i] = make_float3(a.x, a.y, a.z);
+			bot[i] = make_float3(b.x, b.y, b.z);
+		}
+	}
+	const float white_scale = 1.0f / uncharted2(11.2f);
+	const float kexp = DynamicExposure ? (__ldg(&lum[2]) * exposure) : exposure;
+	uint32_t px[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+	{
+		// horizontal weight with the generic sampler's exact arithmetic; its floor is k-1 for
+		// j < 2 and k for j >= 2 (ideal fractions .625 .875 .125 .375, never near an integer)
+		const float u = ((float)(x4 + j) + 0.5f) * inv_w;
+		const float fx = fsub(fmul(u, (float)bloom.w), 0.5f);
+		const float wa = fsub(fx, floorf(fx));
+		const int i0 = j < 2 ? 0 : 1;
+		const float3 t00 = top[i0], t10 = top[i0 + 1], t01 = bot[i0], t11 = bot[i0 + 1];
+		const float bx = bilin_mix(t00.x, t10.x, t01.x, t11.x, wa, wb);
+		const float bgr = bilin_mix(t00.y, t10.y, t01.y, t11.y, wa, wb);
+		const float bb = bilin_mix(t00.z, t10.z, t01.z, t11.z, wa, wb);
+		const float3 c = unpack_r11g11b10(hp[j]);
+		const float r = uncharted2_fast(fmul(fadd(c.x, bx), kexp)) * white_scale;
+		const float g = uncharted2_fast(fmul(fadd(c.y, bgr), kexp)) * white_scale;
+		const float b = uncharted2_fast(fmul(fadd(c.z, bb), kexp)) * white_scale;
+		px[j] = SrgbTarget ? (srgb8_fast(r) | (srgb8_fast(g) << 8) | (srgb8_fast(b) << 16) | 0xff000000u)
+		                   : (unorm8_fast(r) | (unorm8_fast(g) << 8) | (unorm8_fast(b) << 16) | 0xff000000u);
+	}
+	*reinterpret_cast<uint4 *>(&out.at(x4, y)) = make_uint4(px[0], px[1], px[2], px[3]);
 }
 
 // ------------------------------------------------------------------------------- K12
@@ -583,7 +703,10 @@ extern "C" int32_t grb_luminance(const GrbImage *d3, float *luminance, float ler
 		set_last_error("grb_luminance: d3 must be R16G16B16A16_SFLOAT (>= 2x2) and luminance non-null");
 		return GRB_ERR_INVALID_ARGUMENT;
 	}
-	luminance_kernel<<<1, 64, 0, as_stream(stream)>>>(view_of<const uint2>(d3), luminance, lerp, min_loglum, max_loglum);
+	if ((d3->width / 2) * (d3->height / 2) <= kLumFastMaxSamples)
+		luminance_fast_kernel<<<1, kLumFastThreads, 0, as_stream(stream)>>>(view_of<const uint2>(d3), luminance, lerp, min_loglum, max_loglum);
+	else
+		luminance_kernel<<<1, 64, 0, as_stream(stream)>>>(view_of<const uint2>(d3), luminance, lerp, min_loglum, max_loglum);
 	return check_launch("grb_luminance");
 }
 
@@ -634,6 +757,22 @@ extern "C" int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const
 	auto b = view_of<const uint2>(bloom);
 	auto o = view_of<uint32_t>(out);
 	cudaStream_t s = as_stream(stream);
+	// 4-pixel path: rows 16-byte aligned and the bloom image at exactly 1/4 width
+	const bool vec4 = (out->width % 4) == 0 && bloom->width * 4 == out->width && (hdr->row_pitch % 16) == 0 && (out->row_pitch % 16) == 0 &&
+	                  (reinterpret_cast<uintptr_t>(hdr->data) % 16) == 0 && (reinterpret_cast<uintptr_t>(out->data) % 16) == 0;
+	if (vec4)
+	{
+		dim3 grid4((out->width / 4 + kBlockX - 1) / kBlockX, (rows.y1 - rows.y0 + kBlockY - 1) / kBlockY, 1);
+		if (luminance && srgb)
+			tonemap4_kernel<true, true><<<grid4, block, 0, s>>>(h, b, luminance, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+		else if (luminance)
+			tonemap4_kernel<true, false><<<grid4, block, 0, s>>>(h, b, luminance, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+		else if (srgb)
+			tonemap4_kernel<false, true><<<grid4, block, 0, s>>>(h, b, nullptr, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+		else
+			tonemap4_kernel<false, false><<<grid4, block, 0, s>>>(h, b, nullptr, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+		return check_launch("grb_tonemap");
+	}
 	if (luminance && srgb)
 		tonemap_kernel<true, true><<<grid, block, 0, s>>>(h, b, luminance, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
 	else if (luminance)

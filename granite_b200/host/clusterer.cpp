@@ -27,9 +27,19 @@ void LightClusterer::set_resolution(unsigned x, unsigned y, unsigned z)
 	resolution_z = z;
 }
 
-size_t LightClusterer::transforms_offset_model() const { return sizeof(PositionalFragmentInfo) * ClustererMaxLightsBindless; }
-size_t LightClusterer::transforms_offset_type_mask() const { return transforms_offset_model() + sizeof(mat_affine) * ClustererMaxLightsBindless; }
-size_t LightClusterer::transforms_size() const { return transforms_offset_type_mask() + sizeof(uint32_t) * (ClustererMaxLightsBindless / 32); }
+// "cluster-transforms" holds, packed for the CURRENT light count n so one copy uploads it all:
+//   [n x PositionalFragmentInfo][n x mat_affine][128 x u32 type mask][max(n,1) x uvec2 Z ranges]
+// (the reference uploads lights / model / type_mask with three update_buffer calls into the
+// fixed-offset ClustererBindlessTransforms and the Z ranges through a fresh host-visible buffer,
+// clusterer.cpp:1178-1207, 1280-1284).
+static size_t packed_offset_model(size_t n) { return n * sizeof(PositionalFragmentInfo); }
+static size_t packed_offset_type_mask(size_t n) { return packed_offset_model(n) + n * sizeof(mat_affine); }
+static size_t packed_offset_z_ranges(size_t n) { return packed_offset_type_mask(n) + sizeof(uint32_t) * (ClustererMaxLightsBindless / 32); }
+static size_t packed_size(size_t n) { return packed_offset_z_ranges(n) + sizeof(uvec2) * (n ? n : 1); }
+
+size_t LightClusterer::transforms_offset_model() const { return packed_offset_model((size_t)parameters.num_lights); }
+size_t LightClusterer::transforms_offset_type_mask() const { return packed_offset_type_mask((size_t)parameters.num_lights); }
+size_t LightClusterer::transforms_size() const { return packed_size(ClustererMaxLightsBindless); }
 
 void LightClusterer::add_render_passes(RenderGraph &graph)
 {
@@ -53,10 +63,6 @@ void LightClusterer::add_render_passes_bindless(RenderGraph &graph)
 	res_cull = &pass.add_storage_output("cluster-cull-setup", att);
 	att.size = sizeof(vec4) * 6 * ClustererMaxLightsBindless;
 	res_spots = &pass.add_storage_output("cluster-transformed-spot", att);
-	// per-light Z slice ranges: a transient host-visible buffer in the reference
-	// (clusterer.cpp:1280-1284), a persistent graph buffer here
-	att.size = sizeof(uvec2) * ClustererMaxLightsBindless;
-	res_zranges = &pass.add_transfer_output("cluster-light-z-ranges", att);
 
 	pass.set_build_render_pass([this](Vulkan::CommandBuffer &cmd) { build_cluster_bindless_gpu(cmd); });
 }
@@ -77,19 +83,18 @@ void LightClusterer::setup_render_pass_resources(RenderGraph &graph)
 	transforms_buffer = graph.maybe_get_physical_buffer_resource(res_transforms);
 	cull_buffer = graph.maybe_get_physical_buffer_resource(res_cull);
 	spot_buffer = graph.maybe_get_physical_buffer_resource(res_spots);
-	zrange_buffer = graph.maybe_get_physical_buffer_resource(res_zranges);
 }
 
 GrbClusterBuffers LightClusterer::get_cluster_buffers() const
 {
 	GrbClusterBuffers b = {};
-	if (!transforms_buffer || !bitmask_buffer || !range_buffer || !cull_buffer || !spot_buffer || !zrange_buffer)
+	if (!transforms_buffer || !bitmask_buffer || !range_buffer || !cull_buffer || !spot_buffer)
 		return b;
 	auto *base = transforms_buffer->get<uint8_t>();
 	b.lights = reinterpret_cast<const GrbPositionalLight *>(base);
 	b.model = reinterpret_cast<const float *>(base + transforms_offset_model());
 	b.type_mask = reinterpret_cast<const uint32_t *>(base + transforms_offset_type_mask());
-	b.z_ranges = zrange_buffer->get<uint32_t>();
+	b.z_ranges = reinterpret_cast<const uint32_t *>(base + packed_offset_z_ranges((size_t)parameters.num_lights));
 	b.transformed_spots = spot_buffer->get<float>();
 	b.cull_setup = cull_buffer->get<float>();
 	b.bitmask = bitmask_buffer->get<uint32_t>();
@@ -259,14 +264,8 @@ void LightClusterer::build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd)
 	std::memcpy(s + lights_bytes + model_bytes, type_mask.data(), mask_bytes);
 	std::memcpy(s + lights_bytes + model_bytes + mask_bytes, volume_index_range.data(), range_bytes);
 
-	auto *base = transforms_buffer->get<uint8_t>();
-	if (lights_bytes)
-	{
-		cudaMemcpyAsync(base, s, lights_bytes, cudaMemcpyHostToDevice, stream);
-		cudaMemcpyAsync(base + transforms_offset_model(), s + lights_bytes, model_bytes, cudaMemcpyHostToDevice, stream);
-	}
-	cudaMemcpyAsync(base + transforms_offset_type_mask(), s + lights_bytes + model_bytes, mask_bytes, cudaMemcpyHostToDevice, stream);
-	cudaMemcpyAsync(zrange_buffer->get_device_pointer(), s + lights_bytes + model_bytes + mask_bytes, range_bytes, cudaMemcpyHostToDevice, stream);
+	// the staging slot already has the packed device layout: one H2D copy
+	cudaMemcpyAsync(transforms_buffer->get_device_pointer(), s, need, cudaMemcpyHostToDevice, stream);
 	cudaEventRecord(reinterpret_cast<cudaEvent_t>(staging_events[slot]), stream);
 	staging_event_pending[slot] = true;
 

@@ -82,9 +82,9 @@ private:
 	unsigned staging_slot = 0;
 
 	RenderBufferResource *res_bitmask = nullptr, *res_range = nullptr, *res_transforms = nullptr;
-	RenderBufferResource *res_cull = nullptr, *res_spots = nullptr, *res_zranges = nullptr;
+	RenderBufferResource *res_cull = nullptr, *res_spots = nullptr;
 	const Vulkan::Buffer *bitmask_buffer = nullptr, *range_buffer = nullptr, *transforms_buffer = nullptr;
-	const Vulkan::Buffer *cull_buffer = nullptr, *spot_buffer = nullptr, *zrange_buffer = nullptr;
+	const Vulkan::Buffer *cull_buffer = nullptr, *spot_buffer = nullptr;
 
 	float get_z_slice_extent(const RenderContext &ctx) const;
 	uvec2 compute_uint_range(vec2 range) const;
