@@ -386,16 +386,22 @@ __global__ void __launch_bounds__(32 * kBinWarps) binning_kernel(BinParams p, co
 // The reference scans all lights per slice (O(res_z * N)); integer min/max are order-free, so
 // the same function is built here by scattering each light over its own slices into a
 // shared-memory table with atomicMin/atomicMax (O(sum of slice extents)), one CTA.
+constexpr int kZRangeStaged = 4096;
+
 __global__ void __launch_bounds__(1024) z_range_scatter_kernel(const uint2 *__restrict__ z_ranges, int num_ranges, int res_z,
                                                               uint2 *__restrict__ cluster_range)
 {
 	extern __shared__ uint32_t smem[];
 	uint32_t *lo = smem, *hi = smem + res_z;
+	uint2 *ranges = reinterpret_cast<uint2 *>(smem + 2 * res_z); // staged copy of the per-light ranges
 	for (int z = threadIdx.x; z < res_z; z += blockDim.x)
 	{
 		lo[z] = 0xffffffffu;
 		hi[z] = 0u;
 	}
+	const int staged = min(num_ranges, kZRangeStaged);
+	for (int i = threadIdx.x; i < staged; i += blockDim.x)
+		ranges[i] = __ldg(&z_ranges[i]); // coalesced; the scatter below then never waits on L2
 	__syncthreads();
 	// one warp per light, lanes spread over that light's consecutive slices: the atomics of a
 	// warp then hit 32 different shared-memory words instead of serialising on a few (lights are
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(1024) z_range_scatter_kernel(const uint2 *__re
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, num_warps = blockDim.x >> 5;
 	for (int i = warp; i < num_ranges; i += num_warps)
 	{
-		uint2 r = __ldg(&z_ranges[i]);
+		uint2 r = i < staged ? ranges[i] : __ldg(&z_ranges[i]);
 		if (r.x > r.y)
 			continue;
 		uint32_t zend = min(r.y, (uint32_t)(res_z - 1));
@@ -543,8 +549,14 @@ extern "C" int32_t grb_cluster_z_range(const GrbClusterBuffers *buf, int32_t num
 		return GRB_ERR_INVALID_ARGUMENT;
 	}
 	int res_z = buf->resolution_z;
-	size_t smem = (size_t)res_z * 8;
-	if (smem <= 48 * 1024)
+	size_t smem = (size_t)res_z * 8 + (size_t)kZRangeStaged * 8;
+	static bool smem_opt_in = false; // 64 KiB of dynamic shared memory needs the opt-in once per process
+	if (!smem_opt_in && smem <= 96 * 1024)
+	{
+		cudaFuncSetAttribute(z_range_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+		smem_opt_in = true;
+	}
+	if (smem <= 96 * 1024)
 		z_range_scatter_kernel<<<1, 1024, smem, as_stream(stream)>>>(reinterpret_cast<const uint2 *>(buf->z_ranges), num_ranges, res_z,
 		                                                              reinterpret_cast<uint2 *>(buf->cluster_range));
 	else

@@ -350,21 +350,21 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) tonemap4_kernel(View<const u
 }
 
 // ------------------------------------------------------------------------------- K12
-__device__ __forceinline__ float3 unorm8_rgb(uint32_t p)
+__device__ __forceinline__ float3 fxaa_unpack(const float *lut, uint32_t p)
 {
-	return make_float3((float)(p & 0xffu) / 255.0f, (float)((p >> 8) & 0xffu) / 255.0f, (float)((p >> 16) & 0xffu) / 255.0f);
+	return make_float3(lut[p & 0xffu], lut[(p >> 8) & 0xffu], lut[(p >> 16) & 0xffu]);
 }
 
-__device__ __forceinline__ float3 fetch_unorm8(const View<const uint32_t> &im, int x, int y)
+__device__ __forceinline__ float3 fxaa_fetch(const float *lut, const View<const uint32_t> &im, int x, int y)
 {
-	return unorm8_rgb(__ldg(&im.at(iclamp(x, 0, im.w - 1), iclamp(y, 0, im.h - 1))));
+	return fxaa_unpack(lut, __ldg(&im.at(iclamp(x, 0, im.w - 1), iclamp(y, 0, im.h - 1))));
 }
 
-__device__ __forceinline__ float3 sample_unorm8(const View<const uint32_t> &im, float u, float v)
+__device__ __forceinline__ float3 fxaa_sample(const float *lut, const View<const uint32_t> &im, float u, float v)
 {
 	Bilin s = bilin_setup(u, v, im.w, im.h);
-	float3 t00 = unorm8_rgb(__ldg(&im.at(s.x0, s.y0))), t10 = unorm8_rgb(__ldg(&im.at(s.x1, s.y0)));
-	float3 t01 = unorm8_rgb(__ldg(&im.at(s.x0, s.y1))), t11 = unorm8_rgb(__ldg(&im.at(s.x1, s.y1)));
+	float3 t00 = fxaa_unpack(lut, __ldg(&im.at(s.x0, s.y0))), t10 = fxaa_unpack(lut, __ldg(&im.at(s.x1, s.y0)));
+	float3 t01 = fxaa_unpack(lut, __ldg(&im.at(s.x0, s.y1))), t11 = fxaa_unpack(lut, __ldg(&im.at(s.x1, s.y1)));
 	return make_float3(bilin_mix(t00.x, t10.x, t01.x, t11.x, s.a, s.b), bilin_mix(t00.y, t10.y, t01.y, t11.y, s.a, s.b),
 	                   bilin_mix(t00.z, t10.z, t01.z, t11.z, s.a, s.b));
 }
@@ -378,13 +378,24 @@ __device__ __forceinline__ float decode_srgb1(float c)
 	return fclamp(c <= 0.0404482362771082f ? small_side : pow_side, 0.0f, 1.0f);
 }
 
+// UNORM8 -> float is an IEEE division by 255 per channel in the contract; 63 of them per pixel
+// made this pass ALU-bound.  The 256 possible quotients are computed once per CTA (same IEEE
+// division) into shared memory, so the values are bit-identical and the pass is a table lookup.
 template <bool SrgbTarget>
 __global__ void __launch_bounds__(kBlockX *kBlockY) fxaa_kernel(View<const uint32_t> in, View<uint32_t> out, int y0, int y1, float inv_w, float inv_h)
 {
+	__shared__ float s_unorm[256];
+	{
+		int t = threadIdx.y * kBlockX + threadIdx.x;
+		s_unorm[t] = (float)t / 255.0f;
+	}
+	__syncthreads();
 	int x = blockIdx.x * kBlockX + threadIdx.x;
 	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
 	if (x >= out.w || y >= y1)
 		return;
+#define fetch_unorm8(IM, X, Y) fxaa_fetch(s_unorm, IM, X, Y)
+#define sample_unorm8(IM, U, V) fxaa_sample(s_unorm, IM, U, V)
 	const float FXAA_REDUCE_MIN = 1.0f / 128.0f, FXAA_REDUCE_MUL = 1.0f / 8.0f, FXAA_SPAN_MAX = 8.0f;
 	float u = ((float)x + 0.5f) * inv_w, v = ((float)y + 0.5f) * inv_h;
 	float lumaNW = luma_of(fetch_unorm8(in, x - 1, y - 1));
@@ -415,6 +426,8 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) fxaa_kernel(View<const uint3
 	else
 		px = float_to_unorm8(c.x) | (float_to_unorm8(c.y) << 8) | (float_to_unorm8(c.z) << 16);
 	out.at(x, y) = px | 0xff000000u;
+#undef fetch_unorm8
+#undef sample_unorm8
 }
 
 // ------------------------------------------------------------------------------- K13

@@ -52,7 +52,9 @@ void LightClusterer::add_render_passes_bindless(RenderGraph &graph)
 	BufferInfo att;
 	att.usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;
 
-	auto &pass = graph.add_pass("clustering-bindless", RENDER_GRAPH_QUEUE_COMPUTE_BIT);
+	// On the async-compute queue the build of frame N+1 overlaps the (HBM-bound) post chain of
+	// frame N: it only waits for frame N's lighting pass to release the cluster buffers.
+	auto &pass = graph.add_pass("clustering-bindless", async_compute ? RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT : RENDER_GRAPH_QUEUE_COMPUTE_BIT);
 	att.size = resolution_x * resolution_y * (ClustererMaxLightsBindless / 8);
 	res_bitmask = &pass.add_storage_output("cluster-bitmask", att);
 	att.size = resolution_z * sizeof(ivec2);

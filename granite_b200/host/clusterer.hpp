@@ -34,6 +34,8 @@ public:
 
 	void set_resolution(unsigned x, unsigned y, unsigned z);
 	void set_enable_clustering(bool enable) { enable_clustering = enable; }
+	// Declare the clustering pass on RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT (second CUDA stream).
+	void set_async_compute(bool enable) { async_compute = enable; }
 	void set_max_spot_lights(unsigned) {}
 	void set_max_point_lights(unsigned) {}
 
@@ -68,6 +70,7 @@ private:
 	const PositionalLightList *scene_lights = nullptr;
 	unsigned resolution_x = 64, resolution_y = 32, resolution_z = 16;
 	bool enable_clustering = true;
+	bool async_compute = false;
 
 	GrbClusterParameters parameters = {};
 	std::vector<PositionalFragmentInfo> lights;

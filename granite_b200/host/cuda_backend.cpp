@@ -63,8 +63,67 @@ Device::~Device()
 	}
 	for (auto e : event_pool)
 		cudaEventDestroy(e);
+	for (auto &side : side_streams)
+		if (side && side != stream)
+		{
+			cudaStreamSynchronize(side);
+			cudaStreamDestroy(side);
+		}
+	for (auto e : join_events)
+		if (e)
+			cudaEventDestroy(e);
 	if (owns_stream)
 		cudaStreamDestroy(stream);
+}
+
+Stream Device::get_queue_stream(unsigned idx)
+{
+	if (idx == 0 || idx > 2)
+		return stream;
+	std::lock_guard<std::mutex> hold(lock);
+	auto &side = side_streams[idx - 1];
+	if (!side)
+	{
+		// Side streams get the highest priority: their kernels are short (cluster build) or HBM-bound
+		// (post chain), and with priority the block scheduler hands them SM slots as the long,
+		// ALU-bound lighting grid on the main stream retires CTAs -- without it a later kernel only
+		// starts once the earlier grid has no CTAs left to issue, and nothing overlaps.
+		int least = 0, greatest = 0;
+		cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		cudaStream_t s;
+		if (cuda_ok(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest), "cudaStreamCreate(side)"))
+			side = s;
+		else
+			side = stream;
+	}
+	return side;
+}
+
+void Device::join_side_streams()
+{
+	for (int i = 0; i < 2; i++)
+	{
+		if (!side_streams[i] || side_streams[i] == stream)
+			continue;
+		if (!join_events[i])
+		{
+			cudaEvent_t e;
+			cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+			join_events[i] = e;
+		}
+		cudaEventRecord(join_events[i], side_streams[i]);
+		cudaStreamWaitEvent(stream, join_events[i], 0);
+	}
+}
+
+void Device::record_event_on(Event e, Stream s)
+{
+	cuda_ok(cudaEventRecord(e, s), "cudaEventRecord");
+}
+
+void Device::stream_wait_event(Stream s, Event e)
+{
+	cuda_ok(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent");
 }
 
 void *Device::allocate(size_t size)
@@ -90,6 +149,9 @@ void Device::free(void *ptr)
 
 void Device::wait_idle()
 {
+	for (auto side : side_streams)
+		if (side && side != stream)
+			cuda_ok(cudaStreamSynchronize(side), "cudaStreamSynchronize(side)");
 	cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
 }
 

@@ -113,6 +113,15 @@ public:
 	~Device();
 	int get_device_index() const { return index; }
 	Stream get_stream() const { return stream; }
+	// Side streams for passes declared on the asynchronous queues (the reference's async-compute
+	// queue): index 1 = RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT, 2 = RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT.
+	// Index 0 is the main stream.  Created on first use.
+	Stream get_queue_stream(unsigned index);
+	Stream get_async_stream() { return get_queue_stream(1); }
+	void record_event_on(Event e, Stream s);
+	void stream_wait_event(Stream s, Event e);
+	// Makes the main stream wait for everything recorded so far on the side streams.
+	void join_side_streams();
 	ImageHandle create_image(const ImageCreateInfo &info);
 	BufferHandle create_buffer(const BufferCreateInfo &info);
 	void *allocate(size_t size);
@@ -134,6 +143,8 @@ private:
 	int index;
 	Stream stream;
 	bool owns_stream = false;
+	Stream side_streams[2] = { nullptr, nullptr };
+	Event join_events[2] = { nullptr, nullptr };
 	std::mutex lock;
 	std::vector<TimeInterval> intervals;
 	std::vector<Event> event_pool;

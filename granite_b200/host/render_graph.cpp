@@ -6,6 +6,8 @@
 
 namespace Granite
 {
+bool RenderGraph::async_post = false;
+
 // ---------------------------------------------------------------- RenderPassInterface defaults
 bool RenderPassInterface::get_clear_depth_stencil(VkClearDepthStencilValue *value) const
 {
@@ -257,6 +259,9 @@ void RenderGraph::reset()
 	physical_history_attachments.clear();
 	physical_history_spare.clear();
 	physical_buffers.clear();
+	last_access.clear();
+	pass_done_events.clear();
+	physical_pingpong_spare.clear();
 	backbuffer_physical = RenderResource::Unused;
 	baked = false;
 }
@@ -450,6 +455,12 @@ void RenderGraph::setup_attachments(Vulkan::Device &dev, Vulkan::ImageView *swap
 		// history <-> current swap, renderer/render_graph.cpp:2706-2710
 		if (physical_has_history[i])
 			std::swap(physical_history_attachments[i], physical_attachments[i]);
+		else if (dim.flags & ATTACHMENT_INFO_PINGPONG_BIT)
+		{
+			if (physical_pingpong_spare.size() != physical_dimensions.size())
+				physical_pingpong_spare.resize(physical_dimensions.size());
+			std::swap(physical_pingpong_spare[i], physical_attachments[i]);
+		}
 		auto &att = physical_attachments[i];
 		if (!att || att->get_view_width() != dim.width || att->get_view_height() != dim.height || att->get_format() != dim.format)
 		{
@@ -462,35 +473,94 @@ void RenderGraph::setup_attachments(Vulkan::Device &dev, Vulkan::ImageView *swap
 	}
 }
 
+const void *RenderGraph::physical_key(const RenderResource &res, bool history)
+{
+	unsigned phys = res.get_physical_index();
+	if (phys == RenderResource::Unused)
+		return nullptr;
+	if (res.get_type() == RenderResource::Type::Buffer)
+		return physical_buffers[phys] ? physical_buffers[phys].get() : nullptr;
+	auto &view = history ? physical_history_attachments[phys] : physical_attachments[phys];
+	return view ? static_cast<const void *>(&view->get_image()) : nullptr;
+}
+
+Vulkan::Stream RenderGraph::get_writer_stream(const RenderResource &resource)
+{
+	unsigned idx = 0;
+	for (unsigned p : pass_stack)
+		if (resource.get_write_passes().count(p))
+			idx = queue_stream_index(passes[p]->get_queue());
+	return get_device().get_queue_stream(idx);
+}
+
 void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &composer)
 {
 	if (!baked)
 		throw std::logic_error("enqueue_render_passes() before bake().");
-	Vulkan::CommandBuffer cmd(dev, dev.get_stream());
+	// Each pass records on the stream of its queue (main, async compute, async graphics).
+	// Ordering ACROSS streams is derived from the declared resources: before a pass is recorded,
+	// its stream waits for the last pass that touched any of its physical images / buffers on
+	// another stream (covers RAW, WAR and WAW, also across frames because physical resources
+	// persist; ping-pong images alternate so consecutive frames do not meet on them).  Within a
+	// stream, stream order is the dependency.
+	if (pass_done_events.size() != passes.size())
+		pass_done_events.assign(passes.size(), nullptr);
+	unsigned errors = 0;
 	for (unsigned p : pass_stack)
 	{
 		auto &pass = *passes[p];
 		pass.prepare_render_pass(composer);
 		if (!pass.need_render_pass())
 			continue;
+		Vulkan::Stream stream = dev.get_queue_stream(queue_stream_index(pass.get_queue()));
+		Vulkan::CommandBuffer cmd(dev, stream);
+
+		auto wait_for = [&](const void *key) {
+			if (!key)
+				return;
+			auto itr = last_access.find(key);
+			if (itr != last_access.end() && itr->second.event && itr->second.stream != stream)
+				dev.stream_wait_event(stream, itr->second.event);
+		};
+		auto mark = [&](const void *key) {
+			if (key)
+				last_access[key] = LastAccess{ pass_done_events[p], stream };
+		};
+		for (auto *r : pass.get_all_reads())
+			wait_for(physical_key(*r, false));
+		for (auto *w : pass.get_all_writes())
+			wait_for(physical_key(*w, false));
+		for (auto *h : pass.get_history_inputs())
+			wait_for(physical_key(*h, true));
+
 		Vulkan::Event begin = nullptr, end = nullptr;
 		if (timestamps)
 		{
 			begin = dev.request_event();
 			end = dev.request_event();
-			dev.record_event(begin);
+			dev.record_event_on(begin, stream);
 		}
 		cmd.begin_region(pass.get_name().c_str());
 		pass.build_render_pass(cmd, 0);
 		cmd.end_region();
 		if (timestamps)
 		{
-			dev.record_event(end);
+			dev.record_event_on(end, stream);
 			dev.register_time_interval(pass.get_name(), begin, end);
 		}
+		if (!pass_done_events[p])
+			pass_done_events[p] = dev.request_event();
+		dev.record_event_on(pass_done_events[p], stream);
+		for (auto *r : pass.get_all_reads())
+			mark(physical_key(*r, false));
+		for (auto *w : pass.get_all_writes())
+			mark(physical_key(*w, false));
+		for (auto *h : pass.get_history_inputs())
+			mark(physical_key(*h, true));
+		errors += cmd.get_error_count();
 	}
-	if (cmd.get_error_count())
-		Vulkan::log_error("%u pass callback(s) reported errors this frame.\n", cmd.get_error_count());
+	if (errors)
+		Vulkan::log_error("%u pass callback(s) reported errors this frame.\n", errors);
 }
 
 Vulkan::ImageView &RenderGraph::get_physical_texture_resource(unsigned index)

@@ -82,7 +82,10 @@ enum RenderGraphQueueFlagBits
 {
 	RENDER_GRAPH_QUEUE_GRAPHICS_BIT = 1 << 0,
 	RENDER_GRAPH_QUEUE_COMPUTE_BIT = 1 << 1,
-	RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT = 1 << 2
+	RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT = 1 << 2,
+	// A second asynchronous queue for the post chain, so the (HBM-bound) post passes of frame N
+	// run beside the (ALU-bound) lighting of frame N+1.
+	RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT = 1 << 3
 };
 using RenderGraphQueueFlags = uint32_t;
 
@@ -91,7 +94,10 @@ enum AttachmentInfoFlagBits
 	ATTACHMENT_INFO_PERSISTENT_BIT = 1 << 0,
 	ATTACHMENT_INFO_UNORM_SRGB_ALIAS_BIT = 1 << 1,
 	ATTACHMENT_INFO_SUPPORTS_PREROTATE_BIT = 1 << 2,
-	ATTACHMENT_INFO_MIPGEN_BIT = 1 << 3
+	ATTACHMENT_INFO_MIPGEN_BIT = 1 << 3,
+	// Two physical images used on alternate frames: removes the write-after-read dependency
+	// between frame N's consumers and frame N+1's producer when they run on different streams.
+	ATTACHMENT_INFO_PINGPONG_BIT = 1 << 8
 };
 using AttachmentInfoFlags = uint32_t;
 
@@ -340,8 +346,18 @@ public:
 	std::vector<Vulkan::BufferHandle> consume_physical_buffers() const;
 	void install_physical_buffers(std::vector<Vulkan::BufferHandle> buffers);
 
-	static RenderGraphQueueFlagBits get_default_post_graphics_queue() { return RENDER_GRAPH_QUEUE_GRAPHICS_BIT; }
-	static RenderGraphQueueFlagBits get_default_compute_queue() { return RENDER_GRAPH_QUEUE_COMPUTE_BIT; }
+	// Like the reference these default to the main queue ("Don't use async compute by default",
+	// render_graph.hpp:889-893); set_async_post(true) moves the post chain to its own stream.
+	static RenderGraphQueueFlagBits get_default_post_graphics_queue() { return async_post ? RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT : RENDER_GRAPH_QUEUE_GRAPHICS_BIT; }
+	static RenderGraphQueueFlagBits get_default_compute_queue() { return async_post ? RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT : RENDER_GRAPH_QUEUE_COMPUTE_BIT; }
+	static void set_async_post(bool enable) { async_post = enable; }
+	// Stream index a queue flag records on: 0 main, 1 async compute, 2 async graphics (post).
+	static unsigned queue_stream_index(RenderGraphQueueFlagBits queue)
+	{
+		return queue == RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT ? 1u : (queue == RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT ? 2u : 0u);
+	}
+	// Stream of the pass that writes `resource` (for host readbacks of a graph output).
+	Vulkan::Stream get_writer_stream(const RenderResource &resource);
 
 	// Execution order decided by bake(): names of the passes that will run.
 	std::vector<std::string> get_baked_pass_names() const;
@@ -381,6 +397,17 @@ private:
 	std::vector<Vulkan::BufferHandle> physical_buffers;
 	unsigned backbuffer_physical = RenderResource::Unused;
 	bool baked = false;
+	// cross-stream ordering: last pass that touched each physical resource (event + stream)
+	struct LastAccess
+	{
+		Vulkan::Event event = nullptr;
+		Vulkan::Stream stream = nullptr;
+	};
+	std::unordered_map<const void *, LastAccess> last_access; // keyed by the physical image / buffer
+	std::vector<Vulkan::Event> pass_done_events;
+	std::vector<std::unique_ptr<Vulkan::ImageView>> physical_pingpong_spare;
+	static bool async_post;
+	const void *physical_key(const RenderResource &res, bool history);
 	std::vector<GrbRows> shard_bands;
 	unsigned shard_rank = 0;
 	bool shard_fxaa = false;

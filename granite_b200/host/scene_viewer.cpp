@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -117,9 +118,15 @@ void GrbhViewer::bake_render_graph()
 	cluster.set_resolution((unsigned)config.cluster_res[0], (unsigned)config.cluster_res[1], (unsigned)config.cluster_res[2]);
 	cluster.set_scene_lights(&scene_lights);
 	cluster.set_base_render_context(&context);
+	cluster.set_async_compute(getenv("GRB_NO_ASYNC_CLUSTER") == nullptr);
 	cluster.add_render_passes(graph);
 	lighting.cluster = &cluster;
 	context.set_lighting_parameters(&lighting);
+
+	// Post chain on its own stream (the reference's async-compute post, scene_viewer_application.cpp:
+	// 1238-1247) unless disabled; its input image then alternates between two copies per frame.
+	const bool async_post = getenv("GRB_NO_ASYNC_POST") == nullptr;
+	RenderGraph::set_async_post(async_post);
 
 	// ---- add_main_pass_deferred ----
 	AttachmentInfo emissive, albedo, normal, pbr, depth;
@@ -149,7 +156,10 @@ void GrbhViewer::bake_render_graph()
 	// The reference lets HDR-main alias emissive (add_color_output(..., "emissive")) and blends in
 	// place.  Here HDR-main is its own image and emissive a read-only input: same bytes moved,
 	// and the uploaded G-buffer stays intact, so a resident G-buffer can be lit again next frame.
-	auto &hdr_main = lighting_pass.add_color_output("HDR-main", emissive);
+	AttachmentInfo hdr_info = emissive;
+	if (async_post)
+		hdr_info.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
+	auto &hdr_main = lighting_pass.add_color_output("HDR-main", hdr_info);
 	auto &in_emissive = lighting_pass.add_attachment_input("emissive");
 	auto &in_albedo = lighting_pass.add_attachment_input("albedo");
 	auto &in_normal = lighting_pass.add_attachment_input("normal");
@@ -187,6 +197,8 @@ void GrbhViewer::bake_render_graph()
 		});
 	}
 	bool resolved = setup_before_post_chain_antialiasing(before, graph, jitter, 1.0f, light_output, "depth-transient", "mv-main", "HDR-resolved");
+	if (resolved && async_post)
+		graph.get_texture_resource("HDR-resolved").get_attachment_info().flags |= ATTACHMENT_INFO_PINGPONG_BIT;
 
 	// ---- HDR chain ----
 	std::string chain_input = resolved ? "HDR-resolved" : light_output;
@@ -467,7 +479,8 @@ extern "C" int32_t grbh_viewer_read_output(GrbhViewer *v, uint32_t *dst, GrbRows
 	auto &view_ = v->graph.get_physical_texture_resource(v->graph.get_texture_resource(v->output_name));
 	GrbRows r = v->bands.size() > 1 ? v->bands[v->rank] : GrbRows{ 0, v->config.height };
 	size_t pitch = (size_t)v->config.width * 4;
-	auto stream = reinterpret_cast<cudaStream_t>(v->device->get_stream());
+	// read back on the stream of the pass that produced the image
+	auto stream = reinterpret_cast<cudaStream_t>(v->graph.get_writer_stream(v->graph.get_texture_resource(v->output_name)));
 	auto *src = static_cast<const uint8_t *>(view_.get_image().get_device_pointer()) + (size_t)r.y0 * pitch;
 	if (!Vulkan::cuda_ok(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(dst) + (size_t)r.y0 * pitch, src, pitch * (size_t)(r.y1 - r.y0),
 	                                     cudaMemcpyDeviceToHost, stream),
@@ -479,6 +492,14 @@ extern "C" int32_t grbh_viewer_read_output(GrbhViewer *v, uint32_t *dst, GrbRows
 		*rows_out = r;
 	return 0;
 	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_join_streams(GrbhViewer *v)
+{
+	if (!v || !v->device)
+		return fail("null viewer");
+	v->device->join_side_streams();
+	return 0;
 }
 
 extern "C" int32_t grbh_viewer_sync(GrbhViewer *v)

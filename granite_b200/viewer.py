@@ -79,6 +79,90 @@ def band_partition(height: int, world: int, align: int = 64):
     return bands
 
 
+def band_partition_weighted(height: int, world: int, band_cost, align: int = 64):
+    """Contiguous `align`-row bands with roughly equal COST per rank (band_cost[i] = estimated work of
+    rows [i*align, (i+1)*align)).  Lighting cost follows the lights, not the pixel count, so equal-height
+    bands leave ranks idle; this balances the per-rank sum greedily along the prefix sums."""
+    cost = np.asarray(band_cost, np.float64)
+    n_units = (height + align - 1) // align
+    assert len(cost) == n_units
+    if world == 1:
+        return [(0, height)]
+    if n_units < world:
+        raise ValueError("frame too small for this many ranks")
+    prefix = np.concatenate([[0.0], np.cumsum(cost)])
+    total = prefix[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(prefix, target))
+        if k > 0 and abs(prefix[k - 1] - target) < abs(prefix[min(k, n_units)] - target):
+            k -= 1
+        k = max(k, cuts[-1] + 1)               # at least one unit per rank
+        k = min(k, n_units - (world - r))       # leave one unit for each remaining rank
+        cuts.append(k)
+    cuts.append(n_units)
+    return [(cuts[i] * align, min(cuts[i + 1] * align, height)) for i in range(world)]
+
+
+def estimate_band_cost(projection, view, light_positions, light_colors, width, height, depth=None, near=1.0 / 16.0,
+                       align: int = 64, tiles_x: int = 128, base_lights: float = 4.0):
+    """Host-side cost model for band_partition_weighted.  Per (64-row band, screen tile): pixels x
+    (base + number of lights whose projected bounding square AND view-depth range overlap the tile).
+    Light radius = sqrt(max colour / 0.1) (lights.cpp:63-70); tile depth range from the reverse-Z
+    depth image when given (view depth = near / depth), else unbounded.  Only relative weights matter."""
+    P = np.asarray(projection, np.float64).reshape(4, 4).T  # column-major storage -> math matrix
+    V = np.asarray(view, np.float64).reshape(4, 4).T
+    pos = np.asarray(light_positions, np.float64)
+    n_units = (height + align - 1) // align
+    if len(pos) == 0:
+        return np.full(n_units, float(width * align))
+    radius = np.sqrt(np.asarray(light_colors, np.float64).max(axis=1) / 0.1)
+    pv = (V @ np.concatenate([pos, np.ones((len(pos), 1))], axis=1).T).T
+    z = np.maximum(-pv[:, 2], 1e-3)
+    cy = (P[1, 1] * pv[:, 1] / z * 0.5 + 0.5) * height
+    cx = (P[0, 0] * pv[:, 0] / z * 0.5 + 0.5) * width
+    inside = z <= radius * 1.05
+    ry = np.where(inside, height, radius / z * abs(P[1, 1]) * height * 0.5)
+    rx = np.where(inside, width, radius / z * abs(P[0, 0]) * width * 0.5)
+    ly0, ly1, lx0, lx1 = cy - ry, cy + ry, cx - rx, cx + rx
+    lz0, lz1 = z - radius, z + radius
+
+    tile_w = width / tiles_x
+    tx0 = np.arange(tiles_x) * tile_w
+    by0 = np.arange(n_units) * align
+    by1 = np.minimum(by0 + align, height)
+    if depth is not None:
+        d = np.asarray(depth, np.float32)
+        zmin = np.full((n_units, tiles_x), np.inf)
+        zmax = np.full((n_units, tiles_x), -np.inf)
+        lit = np.zeros((n_units, tiles_x))
+        step = max(int(tile_w), 1)
+        for u in range(n_units):
+            rows = d[by0[u]:by1[u]]
+            cols = (rows.shape[1] // step) * step
+            blk = rows[:, :cols].reshape(rows.shape[0], -1, step)[:, :tiles_x]
+            with np.errstate(divide="ignore"):
+                vz = np.where(blk > 0, near / np.maximum(blk, 1e-30), np.nan)
+            has = np.isfinite(vz).any(axis=(0, 2))
+            k = vz.shape[1]
+            zmin[u, :k] = np.where(has, np.nanmin(np.where(np.isfinite(vz), vz, np.inf), axis=(0, 2)), np.inf)
+            zmax[u, :k] = np.where(has, np.nanmax(np.where(np.isfinite(vz), vz, -np.inf), axis=(0, 2)), -np.inf)
+            lit[u, :k] = np.isfinite(vz).mean(axis=(0, 2))
+    else:
+        zmin = np.zeros((n_units, tiles_x))
+        zmax = np.full((n_units, tiles_x), np.inf)
+        lit = np.ones((n_units, tiles_x))
+    cost = np.zeros(n_units)
+    for u in range(n_units):
+        row_ok = (ly1 > by0[u]) & (ly0 < by1[u])                                   # (L,)
+        xo = (lx1[None, :] > tx0[:, None]) & (lx0[None, :] < tx0[:, None] + tile_w)   # (T, L)
+        zo = (lz1[None, :] > zmin[u][:, None]) & (lz0[None, :] < zmax[u][:, None])    # (T, L)
+        n_l = (xo & zo & row_ok[None, :]).sum(axis=1)                              # lights per tile
+        cost[u] = float(((base_lights + n_l) * lit[u]).sum() * tile_w * (by1[u] - by0[u])) + 0.5 * width * (by1[u] - by0[u])
+    return cost
+
+
 PLAN_FIELDS = ("own", "fxaa", "tonemap", "upsample0", "downsample0", "threshold", "lighting", "lum_grid")
 
 
@@ -170,6 +254,9 @@ class Viewer:
         p = dst.data_ptr() if hasattr(dst, "data_ptr") else dst.ctypes.data
         _check(lib().grbh_viewer_read_output(self._h, C.c_void_p(p), C.byref(r)), "grbh_viewer_read_output")
         return r.y0, r.y1
+
+    def join_streams(self):
+        _check(lib().grbh_viewer_join_streams(self._h), "grbh_viewer_join_streams")
 
     def sync(self):
         _check(lib().grbh_viewer_sync(self._h), "grbh_viewer_sync")

@@ -101,6 +101,10 @@ int32_t grbh_viewer_render_frame(GrbhViewer *viewer, const GrbhHostGBuffer *host
  * frame (row pitch = width*4) and waits for it. rows_out receives the band. */
 int32_t grbh_viewer_read_output(GrbhViewer *viewer, uint32_t *dst_full_frame, GrbRows *rows_out);
 int32_t grbh_viewer_sync(GrbhViewer *viewer);
+/* Makes the viewer's main stream (config.cuda_stream) wait for everything recorded so far on its
+ * side streams (async cluster build, async post chain), so an event recorded on the main stream
+ * afterwards covers the whole frame. */
+int32_t grbh_viewer_join_streams(GrbhViewer *viewer);
 
 /* Introspection for tests: device views of graph resources by name (valid until next bake). */
 int32_t grbh_viewer_get_image(GrbhViewer *viewer, const char *resource_name, GrbImage *out);

@@ -126,15 +126,28 @@ def test_two_rank_gloo_frame_equals_single_rank(oracle, fxaa):
     assert covered == H
 
 
-@pytest.mark.parametrize("world", [3, 6])
-def test_emulated_many_ranks(oracle, world):
+def _bands_for(world, weighted):
+    from granite_b200 import synth, viewer
+
+    if not weighted:
+        return viewer.band_partition(H, world)
+    # cost-balanced bands in 8-row units, as bench.py builds them for N > 1
+    scene = synth.make_scene(W, H)
+    lights = synth.make_lights(N_LIGHTS, spot_fraction=0.25, aspect=W / H)
+    cost = viewer.estimate_band_cost(scene.projection, scene.view, lights.position, lights.color, W, H, depth=scene.depth, align=8)
+    return viewer.band_partition_weighted(H, world, cost, align=8)
+
+
+@pytest.mark.parametrize("world,weighted", [(3, False), (6, False), (4, True), (8, True)])
+def test_emulated_many_ranks(oracle, world, weighted):
     """Same protocol with the collectives emulated in-process (every band count the frame allows)."""
     from granite_b200 import viewer
     from tests import common
 
     scene, cam, lights, prep = common.build_case(oracle, W, H, N_LIGHTS, 0.25)
     _, _, _, f, _ = _reference_frame(oracle, scene, cam, prep)
-    bands = viewer.band_partition(H, world)
+    bands = _bands_for(world, weighted)
+    assert bands[0][0] == 0 and bands[-1][1] == H and all(a[1] == b[0] and a[1] % 8 == 0 for a, b in zip(bands, bands[1:]))
     # three passes emulate the two exchange steps: (0) collect every rank's d0 band, (1) with the
     # gathered d0, collect every rank's luminance-grid rows, (2) the real frame
     contributions = {}
