@@ -51,6 +51,10 @@ void LightClusterer::add_render_passes_bindless(RenderGraph &graph)
 {
 	BufferInfo att;
 	att.usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT | VK_BUFFER_USAGE_TRANSFER_DST_BIT;
+	// every buffer here is rewritten each frame; alternating two copies lets the build of frame
+	// N+1 run while frame N's lighting still reads the previous structure
+	if (async_compute)
+		att.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
 
 	// On the async-compute queue the build of frame N+1 overlaps the (HBM-bound) post chain of
 	// frame N: it only waits for frame N's lighting pass to release the cluster buffers.
@@ -145,16 +149,29 @@ void LightClusterer::refresh_bindless_prepare(const RenderContext &ctx)
 	// end of the node transform -- SURVEY.md §7 -- the intended key is this one.)  stable_sort
 	// keeps input order on ties so the light order, hence bit positions and fp accumulation
 	// order, is deterministic.
-	std::vector<unsigned> order;
+	auto &order = sort_order;
+	auto &keys = sort_keys;
 	if (scene_lights)
 	{
-		order.resize(scene_lights->size());
-		std::iota(order.begin(), order.end(), 0u);
-		std::vector<float> keys(order.size());
-		for (size_t i = 0; i < keys.size(); i++)
+		const size_t n = scene_lights->size();
+		// start from last frame's order: with coherent motion it is already sorted and the
+		// stable sort below is skipped (a stable sort of an already ordered sequence would not
+		// change it, so the result is the same as sorting from scratch... provided ties keep
+		// input order, which is why the identity order is the reset state)
+		if (order.size() != n)
+		{
+			order.resize(n);
+			std::iota(order.begin(), order.end(), 0u);
+		}
+		keys.resize(n);
+		for (size_t i = 0; i < n; i++)
 			keys[i] = dot((*scene_lights)[i].transform.get_translation(), rp.camera_front);
-		std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return keys[a] < keys[b]; });
+		auto by_key_then_input = [&](unsigned a, unsigned b) { return keys[a] < keys[b] || (keys[a] == keys[b] && a < b); };
+		if (!std::is_sorted(order.begin(), order.end(), by_key_then_input))
+			std::sort(order.begin(), order.end(), by_key_then_input);
 	}
+	else
+		order.clear();
 
 	unsigned index = 0;
 	for (unsigned src : order)

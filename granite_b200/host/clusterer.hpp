@@ -77,6 +77,8 @@ private:
 	std::vector<mat_affine> model;
 	std::vector<uint32_t> type_mask;
 	std::vector<uvec2> volume_index_range;
+	std::vector<unsigned> sort_order;
+	std::vector<float> sort_keys;
 	// pinned staging copy of {lights, model, type_mask, z ranges} for the async upload
 	void *staging = nullptr;
 	size_t staging_size = 0;

@@ -211,6 +211,36 @@ std::vector<std::pair<std::string, float>> Device::collect_time_intervals()
 	return out;
 }
 
+std::vector<Device::TimelineEntry> Device::collect_timeline()
+{
+	std::vector<TimeInterval> local;
+	{
+		std::lock_guard<std::mutex> hold(lock);
+		local.swap(intervals);
+	}
+	std::vector<TimelineEntry> out;
+	if (local.empty())
+		return out;
+	for (auto &iv : local)
+		cudaEventSynchronize(iv.end);
+	Event ref = local.front().begin;
+	for (auto &iv : local)
+	{
+		TimelineEntry e;
+		e.tag = iv.tag;
+		cudaEventElapsedTime(&e.begin_ms, ref, iv.begin);
+		cudaEventElapsedTime(&e.end_ms, ref, iv.end);
+		out.push_back(e);
+	}
+	std::lock_guard<std::mutex> hold(lock);
+	for (auto &iv : local)
+	{
+		event_pool.push_back(iv.begin);
+		event_pool.push_back(iv.end);
+	}
+	return out;
+}
+
 Image::Image(Device &device_, const ImageCreateInfo &info_) : device(device_), info(info_)
 {
 	unsigned texel = format_texel_size(info.format);

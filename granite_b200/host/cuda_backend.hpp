@@ -136,6 +136,14 @@ public:
 	void register_time_interval(const std::string &tag, Event begin, Event end);
 	// Resolves and clears the registered intervals: (tag, milliseconds).
 	std::vector<std::pair<std::string, float>> collect_time_intervals();
+	// Same intervals as (tag, begin ms, end ms) relative to the first interval ever registered:
+	// a GPU timeline (the counterpart of the reference's GRANITE_TIMELINE_TRACE for the GPU side).
+	struct TimelineEntry
+	{
+		std::string tag;
+		float begin_ms, end_ms;
+	};
+	std::vector<TimelineEntry> collect_timeline();
 	Event request_event();
 	void record_event(Event e);
 
@@ -148,6 +156,7 @@ private:
 	std::mutex lock;
 	std::vector<TimeInterval> intervals;
 	std::vector<Event> event_pool;
+	Event epoch = nullptr;
 };
 
 // Thrown (host side only, never across the C ABI) when a kernel launch or CUDA call fails and

@@ -262,6 +262,7 @@ void RenderGraph::reset()
 	last_access.clear();
 	pass_done_events.clear();
 	physical_pingpong_spare.clear();
+	physical_buffer_spare.clear();
 	backbuffer_physical = RenderResource::Unused;
 	baked = false;
 }
@@ -434,6 +435,13 @@ void RenderGraph::setup_attachments(Vulkan::Device &dev, Vulkan::ImageView *swap
 		auto &dim = physical_dimensions[i];
 		if (dim.buffer_info.size != 0)
 		{
+			// ping-pong buffers alternate between two allocations (fully rewritten every frame)
+			if (dim.flags & ATTACHMENT_INFO_PINGPONG_BIT)
+			{
+				if (physical_buffer_spare.size() != physical_dimensions.size())
+					physical_buffer_spare.resize(physical_dimensions.size());
+				std::swap(physical_buffer_spare[i], physical_buffers[i]);
+			}
 			// persistent across frames (and re-bakes via install_physical_buffers)
 			if (!physical_buffers[i] || physical_buffers[i]->get_create_info().size != dim.buffer_info.size)
 			{
@@ -504,7 +512,8 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 	// persist; ping-pong images alternate so consecutive frames do not meet on them).  Within a
 	// stream, stream order is the dependency.
 	if (pass_done_events.size() != passes.size())
-		pass_done_events.assign(passes.size(), nullptr);
+		pass_done_events.assign(passes.size(), std::array<Vulkan::Event, EventRing>{});
+	const unsigned slot = unsigned(frame_counter++ % EventRing);
 	unsigned errors = 0;
 	for (unsigned p : pass_stack)
 	{
@@ -524,7 +533,7 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 		};
 		auto mark = [&](const void *key) {
 			if (key)
-				last_access[key] = LastAccess{ pass_done_events[p], stream };
+				last_access[key] = LastAccess{ pass_done_events[p][slot], stream };
 		};
 		for (auto *r : pass.get_all_reads())
 			wait_for(physical_key(*r, false));
@@ -548,9 +557,9 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 			dev.record_event_on(end, stream);
 			dev.register_time_interval(pass.get_name(), begin, end);
 		}
-		if (!pass_done_events[p])
-			pass_done_events[p] = dev.request_event();
-		dev.record_event_on(pass_done_events[p], stream);
+		if (!pass_done_events[p][slot])
+			pass_done_events[p][slot] = dev.request_event();
+		dev.record_event_on(pass_done_events[p][slot], stream);
 		for (auto *r : pass.get_all_reads())
 			mark(physical_key(*r, false));
 		for (auto *w : pass.get_all_writes())

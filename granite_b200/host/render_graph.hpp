@@ -15,6 +15,7 @@
 // and per-pass GPU timestamps are CUDA events.
 #pragma once
 
+#include <array>
 #include <functional>
 #include <memory>
 #include <string>
@@ -404,8 +405,13 @@ private:
 		Vulkan::Stream stream = nullptr;
 	};
 	std::unordered_map<const void *, LastAccess> last_access; // keyed by the physical image / buffer
-	std::vector<Vulkan::Event> pass_done_events;
+	// one "pass done" event per pass per frame slot: a later frame re-recording the same event
+	// would turn "wait for frame N-2's reader" into "wait for frame N's", serialising the streams
+	enum { EventRing = 4 };
+	std::vector<std::array<Vulkan::Event, EventRing>> pass_done_events;
+	uint64_t frame_counter = 0;
 	std::vector<std::unique_ptr<Vulkan::ImageView>> physical_pingpong_spare;
+	std::vector<Vulkan::BufferHandle> physical_buffer_spare;
 	static bool async_post;
 	const void *physical_key(const RenderResource &res, bool history);
 	std::vector<GrbRows> shard_bands;

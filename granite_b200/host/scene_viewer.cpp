@@ -64,6 +64,8 @@ struct GrbhViewer
 	std::string output_name;
 	const GrbhHostGBuffer *pending_upload = nullptr;
 	std::map<std::string, std::pair<double, int>> timings;
+	std::vector<cudaEvent_t> pending_outputs; // one per async readback still in flight (oldest first)
+	std::vector<cudaEvent_t> free_output_events;
 
 	RenderTextureResource *res_emissive = nullptr, *res_albedo = nullptr, *res_normal = nullptr, *res_pbr = nullptr, *res_depth = nullptr,
 	                      *res_mv = nullptr;
@@ -136,7 +138,13 @@ void GrbhViewer::bake_render_graph()
 	pbr.format = VK_FORMAT_R8G8_UNORM;
 	depth.format = VK_FORMAT_D32_SFLOAT;
 
-	auto &gbuffer = graph.add_pass("gbuffer", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+	// pipelined I/O: uploads on the async-compute stream into ping-pong images, so the copy of the
+	// next frame's inputs overlaps this frame's lighting
+	const bool pipelined = config.pipelined_io != 0;
+	if (pipelined)
+		for (auto *info : { &emissive, &albedo, &normal, &pbr, &depth })
+			info->flags |= ATTACHMENT_INFO_PINGPONG_BIT;
+	auto &gbuffer = graph.add_pass("gbuffer", pipelined ? RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT : RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
 	res_emissive = &gbuffer.add_color_output("emissive", emissive);
 	res_albedo = &gbuffer.add_color_output("albedo", albedo);
 	res_normal = &gbuffer.add_color_output("normal", normal);
@@ -189,7 +197,9 @@ void GrbhViewer::bake_render_graph()
 		// add_mv_pass: the motion-vector image is an input of this path
 		AttachmentInfo mv;
 		mv.format = VK_FORMAT_R16G16_SFLOAT;
-		auto &mv_pass = graph.add_pass("mv", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+		if (pipelined)
+			mv.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
+		auto &mv_pass = graph.add_pass("mv", pipelined ? RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT : RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
 		res_mv = &mv_pass.add_color_output("mv-main", mv);
 		mv_pass.set_build_render_pass([this](Vulkan::CommandBuffer &cmd) {
 			if (pending_upload)
@@ -272,7 +282,7 @@ void GrbhViewer::render_frame(const GrbhHostGBuffer *host, double frame_time)
 	graph.enqueue_render_passes(*device, composer);
 	pending_upload = nullptr;
 
-	if (config.timestamps)
+	if (config.timestamps == 1)
 		for (auto &iv : device->collect_time_intervals())
 		{
 			auto &slot = timings[iv.first];
@@ -333,6 +343,10 @@ extern "C" void grbh_viewer_destroy(GrbhViewer *viewer)
 		return;
 	if (viewer->device)
 		viewer->device->wait_idle();
+	for (auto e : viewer->pending_outputs)
+		cudaEventDestroy(e);
+	for (auto e : viewer->free_output_events)
+		cudaEventDestroy(e);
 	viewer->graph.reset();
 	delete viewer;
 }
@@ -464,6 +478,8 @@ extern "C" int32_t grbh_viewer_render_frame(GrbhViewer *v, const GrbhHostGBuffer
 {
 	if (!v || !v->baked)
 		return fail("grbh_viewer_render_frame: viewer not baked");
+	if (v->config.pipelined_io && !host)
+		return fail("grbh_viewer_render_frame: pipelined_io viewers need the host G-buffer every frame");
 	GRBH_TRY
 	cudaSetDevice(v->device->get_device_index());
 	v->render_frame(host, frame_time);
@@ -492,6 +508,75 @@ extern "C" int32_t grbh_viewer_read_output(GrbhViewer *v, uint32_t *dst, GrbRows
 		*rows_out = r;
 	return 0;
 	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_read_output_async(GrbhViewer *v, uint32_t *dst, GrbRows *rows_out)
+{
+	if (!v || !v->baked || !dst)
+		return fail("grbh_viewer_read_output_async: bad arguments");
+	GRBH_TRY
+	auto &view_ = v->graph.get_physical_texture_resource(v->graph.get_texture_resource(v->output_name));
+	GrbRows r = v->bands.size() > 1 ? v->bands[v->rank] : GrbRows{ 0, v->config.height };
+	size_t pitch = (size_t)v->config.width * 4;
+	auto stream = reinterpret_cast<cudaStream_t>(v->graph.get_writer_stream(v->graph.get_texture_resource(v->output_name)));
+	auto *src = static_cast<const uint8_t *>(view_.get_image().get_device_pointer()) + (size_t)r.y0 * pitch;
+	if (!Vulkan::cuda_ok(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(dst) + (size_t)r.y0 * pitch, src, pitch * (size_t)(r.y1 - r.y0),
+	                                     cudaMemcpyDeviceToHost, stream),
+	                     "output readback"))
+		return fail("cudaMemcpyAsync failed");
+	cudaEvent_t e;
+	if (!v->free_output_events.empty())
+	{
+		e = v->free_output_events.back();
+		v->free_output_events.pop_back();
+	}
+	else
+		cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+	cudaEventRecord(e, stream);
+	v->pending_outputs.push_back(e);
+	if (rows_out)
+		*rows_out = r;
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_wait_outputs(GrbhViewer *v, int32_t max_pending)
+{
+	if (!v || max_pending < 0)
+		return fail("grbh_viewer_wait_outputs: bad arguments");
+	while ((int32_t)v->pending_outputs.size() > max_pending)
+	{
+		cudaEvent_t e = v->pending_outputs.front();
+		if (!Vulkan::cuda_ok(cudaEventSynchronize(e), "cudaEventSynchronize"))
+			return fail("cudaEventSynchronize failed");
+		v->pending_outputs.erase(v->pending_outputs.begin());
+		v->free_output_events.push_back(e);
+	}
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_collect_timeline(GrbhViewer *v, char *names, int32_t names_capacity, float *begin_ms, float *end_ms, int32_t capacity)
+{
+	if (!v || !v->device)
+		return fail("null viewer");
+	auto tl = v->device->collect_timeline();
+	std::string all;
+	int i = 0;
+	for (auto &e : tl)
+	{
+		if (i < capacity)
+		{
+			if (begin_ms)
+				begin_ms[i] = e.begin_ms;
+			if (end_ms)
+				end_ms[i] = e.end_ms;
+		}
+		all += e.tag + "\n";
+		i++;
+	}
+	if (names && names_capacity > 0)
+		std::snprintf(names, (size_t)names_capacity, "%s", all.c_str());
+	return i;
 }
 
 extern "C" int32_t grbh_viewer_join_streams(GrbhViewer *v)

@@ -20,7 +20,7 @@ AA_NONE, AA_FXAA, AA_TAA_LOW, AA_TAA_MEDIUM, AA_TAA_HIGH, AA_TAA_HIGH_PLUS_FXAA 
 class GrbhViewerConfig(C.Structure):
     _fields_ = [("cuda_device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("post_aa", C.c_int32),
                 ("hdr_bloom", C.c_int32), ("dynamic_exposure", C.c_int32), ("cluster_res", C.c_int32 * 3),
-                ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p)]
+                ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p), ("pipelined_io", C.c_int32)]
 
 
 class GrbhLights(C.Structure):
@@ -176,7 +176,7 @@ def shard_plan(width, height, bands, rank, fxaa=False) -> dict:
 
 class Viewer:
     def __init__(self, width, height, post_aa=AA_NONE, hdr_bloom=True, dynamic_exposure=True, cuda_device=0,
-                 cluster_res=(128, 64, 4096), timestamps=False, stream=None):
+                 cluster_res=(128, 64, 4096), timestamps=False, stream=None, pipelined_io=False):
         cfg = GrbhViewerConfig()
         cfg.cuda_device = cuda_device
         cfg.width, cfg.height = width, height
@@ -184,8 +184,9 @@ class Viewer:
         cfg.hdr_bloom = int(hdr_bloom)
         cfg.dynamic_exposure = int(dynamic_exposure)
         cfg.cluster_res = (C.c_int32 * 3)(*cluster_res)
-        cfg.timestamps = int(timestamps)
+        cfg.timestamps = int(timestamps)  # 1: aggregate per-pass times, 2: keep the raw timeline
         cfg.cuda_stream = stream
+        cfg.pipelined_io = int(pipelined_io)
         self.width, self.height = width, height
         self._h = C.c_void_p()
         _check(lib().grbh_viewer_create(C.byref(cfg), C.byref(self._h)), "grbh_viewer_create")
@@ -254,6 +255,16 @@ class Viewer:
         p = dst.data_ptr() if hasattr(dst, "data_ptr") else dst.ctypes.data
         _check(lib().grbh_viewer_read_output(self._h, C.c_void_p(p), C.byref(r)), "grbh_viewer_read_output")
         return r.y0, r.y1
+
+    def read_output_async(self, dst):
+        """Enqueue the device->host copy of this frame's rows; pair with wait_outputs()."""
+        r = capi.GrbRows()
+        ptr = dst.data_ptr() if hasattr(dst, "data_ptr") else dst.ctypes.data
+        _check(lib().grbh_viewer_read_output_async(self._h, C.c_void_p(ptr), C.byref(r)), "grbh_viewer_read_output_async")
+        return r.y0, r.y1
+
+    def wait_outputs(self, max_pending=0):
+        _check(lib().grbh_viewer_wait_outputs(self._h, int(max_pending)), "grbh_viewer_wait_outputs")
 
     def join_streams(self):
         _check(lib().grbh_viewer_join_streams(self._h), "grbh_viewer_join_streams")
@@ -334,6 +345,18 @@ class Viewer:
         n = _check(lib().grbh_viewer_collect_timings(self._h, names, 4096, ms, cnt, 64), "grbh_viewer_collect_timings")
         nm = [x for x in names.value.decode().split("\n") if x]
         return {nm[i]: (ms[i], cnt[i]) for i in range(min(n, len(nm)))}
+
+
+def _timeline(self, capacity=4096):
+    names = C.create_string_buffer(64 * capacity)
+    b = (C.c_float * capacity)()
+    e = (C.c_float * capacity)()
+    n = _check(lib().grbh_viewer_collect_timeline(self._h, names, 64 * capacity, b, e, capacity), "grbh_viewer_collect_timeline")
+    nm = [x for x in names.value.decode().split("\n") if x]
+    return [(nm[i], b[i], e[i]) for i in range(min(n, len(nm), capacity))]
+
+
+Viewer.collect_timeline = _timeline
 
 
 def nccl_unique_id() -> bytes:

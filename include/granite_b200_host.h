@@ -44,6 +44,9 @@ typedef struct GrbhViewerConfig
 	int32_t cluster_res[3];     /* LightClusterer::set_resolution; viewer default 128,64,4096 */
 	int32_t timestamps;         /* RenderGraph::enable_timestamps */
 	void *cuda_stream;          /* NULL: the device creates its own stream */
+	int32_t pipelined_io;       /* 1: the G-buffer upload runs on a side stream into images that alternate
+	                             * per frame, so frame N+1's host->device copy overlaps frame N's compute
+	                             * (every frame must then bring its G-buffer: render_frame(NULL) is an error) */
 } GrbhViewerConfig;
 
 /* Raw light list as the application owns it (before the clusterer sorts/packs it). */
@@ -100,6 +103,12 @@ int32_t grbh_viewer_render_frame(GrbhViewer *viewer, const GrbhHostGBuffer *host
 /* Copies this rank's rows of the final image (R8G8B8A8) to host memory laid out as the full
  * frame (row pitch = width*4) and waits for it. rows_out receives the band. */
 int32_t grbh_viewer_read_output(GrbhViewer *viewer, uint32_t *dst_full_frame, GrbRows *rows_out);
+/* Asynchronous form: enqueues the device->host copy of this frame's rows behind the frame and
+ * returns; grbh_viewer_wait_outputs(viewer, k) blocks until at most k such copies are pending
+ * (k = 0: all done).  With pipelined_io this keeps PCIe busy in both directions while the GPU
+ * computes the next frame. */
+int32_t grbh_viewer_read_output_async(GrbhViewer *viewer, uint32_t *dst_full_frame, GrbRows *rows_out);
+int32_t grbh_viewer_wait_outputs(GrbhViewer *viewer, int32_t max_pending);
 int32_t grbh_viewer_sync(GrbhViewer *viewer);
 /* Makes the viewer's main stream (config.cuda_stream) wait for everything recorded so far on its
  * side streams (async cluster build, async post chain), so an event recorded on the main stream
@@ -119,6 +128,9 @@ int32_t grbh_viewer_get_pass_names(GrbhViewer *viewer, char *buffer, int32_t cap
 /* Per-pass GPU time of the frames since the last call (needs config.timestamps):
  * writes up to `capacity` (name, total ms, count) triples. Returns the number of passes. */
 int32_t grbh_viewer_collect_timings(GrbhViewer *viewer, char *names, int32_t names_capacity, float *total_ms, int32_t *counts, int32_t capacity);
+/* GPU timeline of the passes recorded since the last call (config.timestamps == 2: intervals are
+ * kept, not aggregated): (name, begin ms, end ms) relative to the first interval. Returns the count. */
+int32_t grbh_viewer_collect_timeline(GrbhViewer *viewer, char *names, int32_t names_capacity, float *begin_ms, float *end_ms, int32_t capacity);
 uint16_t grbh_float_to_half(float v);
 
 #ifdef __cplusplus

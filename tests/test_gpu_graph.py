@@ -180,3 +180,33 @@ def test_taa_fxaa_chain(cuda, oracle):
         d = common.rgba8_channel_diff(out, ldr)
         assert (d <= 1).mean() > 0.999, f"frame {i}"
     v.close()
+
+
+def test_pipelined_io_frames_equal_serial_frames(cuda):
+    """Uploads on the side stream into ping-pong images + asynchronous readbacks must give the
+    same frames as the plain upload -> compute -> readback sequence."""
+    import torch
+
+    w, h = 640, 360
+    scene, lights = synth.make_scene(w, h), synth.make_lights(200, spot_fraction=0.25, aspect=w / h)
+    gb, keep = _host_gb(scene)
+    ref = []
+    v = _make_viewer(scene, lights)
+    for _ in range(4):
+        v.render_frame(gb)
+        out = np.zeros((h, w), np.uint32)
+        v.read_output(out)
+        ref.append(out)
+    v.close()
+    vp = _make_viewer(scene, lights, pipelined_io=True)
+    outs = [torch.zeros((h, w), dtype=torch.int32).pin_memory() for _ in range(4)]
+    for i in range(4):
+        vp.render_frame(gb)
+        vp.read_output_async(outs[i])
+        vp.wait_outputs(1)
+    vp.wait_outputs(0)
+    for i in range(4):
+        assert np.array_equal(outs[i].numpy().view(np.uint32), ref[i]), f"frame {i}"
+    with pytest.raises(Exception):
+        vp.render_frame(None)
+    vp.close()
