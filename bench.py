@@ -205,7 +205,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     lighting_b, chain_b, total_b = algorithmic_bytes(w, h, aa)
     config = {"workload": f"{args.workload}: {desc}", "width": w, "height": h, "lights": n_lights, "cluster_grid": "128x64x4096",
-              "sharding": f"{world} cost-balanced row bands (8-row units)" if world > 1 else "none",
+              "sharding": f"{world} row bands of equal measured lighting work (8-row units)" if world > 1 else "none",
               "l2": "per-frame inputs (182 MB G-buffer at 4K) exceed the 126 MB L2; no explicit flush",
               "algorithmic_mb_per_frame": round(total_b / 1e6, 2)}
 
@@ -255,11 +255,23 @@ def main():
         v.bake()
         return v
 
-    # Row bands: lighting cost follows the lights (87 % of this scene's lights project into ~64 rows
-    # below the horizon), so bands are balanced by an estimated cost, in units of 8 rows.
+    # Row bands: lighting cost follows the lights (in this scene 3 % of the rows hold over half of the
+    # light evaluations), so bands are cut for equal estimated work, in units of 8 rows.  The estimate
+    # is the lighting kernel's own cluster walk without shading (grb_lighting_row_cost), run once on
+    # an unsharded frame before the ranks split it.
     if world > 1:
-        cost = viewer.estimate_band_cost(scene.projection, scene.view, lights.position, lights.color, w, h, depth=scene.depth, align=8)
-        bands = viewer.band_partition_weighted(h, world, cost, align=8)
+        cal = viewer.Viewer(w, h, post_aa=viewer.AA_NONE, cuda_device=local_rank, stream=stream.cuda_stream)
+        cal.set_camera(scene.projection, scene.view)
+        cal.set_directional(scene.dir_color, scene.dir_direction)
+        cal.set_lights(lights)
+        cal.bake()
+        full = [np.ascontiguousarray(a) for a in (scene.albedo, scene.normal, scene.pbr, scene.depth, scene.emissive)]
+        cal.render_frame(viewer.Viewer.host_gbuffer(*full))
+        cost4 = torch.from_numpy(cal.measure_row_cost().astype(np.int64)).cuda()
+        cal.close()
+        del full
+        dist.broadcast(cost4, 0)
+        bands = viewer.band_partition_measured(h, w, world, cost4.cpu().numpy(), align=8)
     else:
         bands = [(0, h)]
     v = make_viewer(False)

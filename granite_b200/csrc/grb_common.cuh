@@ -168,6 +168,35 @@ GRB_DEV uint32_t float_to_unorm8(float c)
 	return (uint32_t)floorf(fadd(fmul(c, 255.0f), 0.5f));
 }
 
+// Raw MUFU ops.  rsqrtf() / __fdividef() / __log2f() / __exp2f() without -ftz wrap the MUFU in a
+// denormal rescue (compare, select and rescale on the way in and out) that costs more issue slots
+// than the operation itself.  Used only where the contract is "within 1 ULP of the stored
+// format" and a denormal argument can only mean a value the surrounding clamps absorb.
+__device__ __forceinline__ float rsqrt_fast(float x)
+{
+	float y;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+__device__ __forceinline__ float rcp_fast(float x)
+{
+	float y;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+__device__ __forceinline__ float lg2_fast(float x)
+{
+	float y;
+	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+__device__ __forceinline__ float ex2_fast(float x)
+{
+	float y;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+
 // ---------------------------------------------------------------------------------------
 // StockSampler::LinearClamp (vulkan/device.cpp:1077-1170): bilinear, clamp-to-edge, texel
 // centres at +0.5, exact fp32 weights.  (u, v) are the normalised coordinates the shader

@@ -66,6 +66,7 @@ struct Surface
 	float m2_minus_1;       // roughness'^4 - 1
 	float c_gd;             // 0.25 * roughness'^4 / PI  (numerator of G*D)
 	float one_minus_k, k, Vk; // Schlick-GGX visibility pieces
+	float NoV_raw;          // dot(N, V) before the clamp (half-vector algebra)
 };
 
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -88,17 +89,22 @@ __device__ __forceinline__ uint32_t cluster_mask_range(uint32_t mask, uint32_t r
 // Returns that sum per channel and NoL; the caller scales by NoL * colour * attenuation.
 __device__ __forceinline__ float3 brdf(const Surface &s, float3 L, float &NoL)
 {
-	float3 h = make_float3(s.V.x + L.x, s.V.y + L.y, s.V.z + L.z);
-	float inv_h = rsqrtf(dot3(h, h));
-	NoL = fminf(fmaxf(dot3(s.N, L), 0.001f), 1.0f);
-	float NoH = fminf(fmaxf(dot3(s.N, h) * inv_h, 0.0001f), 1.0f);
-	float HoV = fminf(fmaxf(dot3(h, s.V) * inv_h, 0.001f), 1.0f);
+	// With unit V and L:  |V+L|^2 = 2 + 2 VoL,  N.(V+L) = NoV + NoL,  V.(V+L) = 1 + VoL -- the half vector
+	// itself is never formed.
+	float VoL = dot3(s.V, L);
+	float NoLr = dot3(s.N, L);
+	float inv_h = rsqrt_fast(fmaf(VoL, 2.0f, 2.0f));
+	NoL = fminf(fmaxf(NoLr, 0.001f), 1.0f);
+	float NoH = fminf(fmaxf((NoLr + s.NoV_raw) * inv_h, 0.0001f), 1.0f);
+	// HoV = sqrt((1 + VoL) / 2) cannot exceed 1 by more than rounding, and 1 - HoV only enters as f^5
+	float HoV = fmaxf(fmaf(VoL, inv_h, inv_h), 0.001f);
 	float f = 1.0f - HoV;
 	float f2 = f * f;
 	float f5 = f2 * f2 * f;
 	float d = fmaf(NoH * NoH, s.m2_minus_1, 1.0f);
-	float vl = fmaxf(s.Vk * fmaf(NoL, s.one_minus_k, s.k), 0.001f);
-	float GD = __fdividef(s.c_gd, d * d * vl);
+	// max(Vk * Lk, 1e-3) of the shader is the identity: k = (r' + 1)^2 / 8 >= 0.195 bounds both factors
+	float vl = s.Vk * fmaf(NoL, s.one_minus_k, s.k);
+	float GD = s.c_gd * rcp_fast(d * d * vl);
 	float Fx = fmaf(s.one_minus_F0.x, f5, s.F0.x), Fy = fmaf(s.one_minus_F0.y, f5, s.F0.y), Fz = fmaf(s.one_minus_F0.z, f5, s.F0.z);
 	return make_float3(fmaf(Fx, GD - s.diffuse_k.x, s.diffuse_k.x), fmaf(Fy, GD - s.diffuse_k.y, s.diffuse_k.y),
 	                   fmaf(Fz, GD - s.diffuse_k.z, s.diffuse_k.z));
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 
 		// per-pixel BRDF invariants
 		float3 v = make_float3(p.camera_pos.x - s.pos.x, p.camera_pos.y - s.pos.y, p.camera_pos.z - s.pos.z);
-		float inv_v = rsqrtf(dot3(v, v));
+		float inv_v = rsqrt_fast(dot3(v, v));
 		s.V = make_float3(v.x * inv_v, v.y * inv_v, v.z * inv_v);
 		float rough = roughness_in * 0.75f + 0.25f;
 		float mm = rough * rough;
@@ -202,7 +208,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		float r1 = rough + 1.0f;
 		s.k = r1 * r1 * 0.125f;
 		s.one_minus_k = 1.0f - s.k;
-		float NoV = fminf(fmaxf(dot3(s.N, s.V), 0.001f), 1.0f);
+		s.NoV_raw = dot3(s.N, s.V);
+		float NoV = fminf(fmaxf(s.NoV_raw, 0.001f), 1.0f);
 		s.Vk = NoV * s.one_minus_k + s.k;
 		s.F0 = make_float3(0.04f * (1.0f - metallic) + base_color.x * metallic, 0.04f * (1.0f - metallic) + base_color.y * metallic,
 		                   0.04f * (1.0f - metallic) + base_color.z * metallic);
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 			if (!__any_sync(0xffffffffu, near))
 				continue;
 			const float4 l0 = __ldg(lp); // color|spot scale_bias
-			float inv_d = rsqrtf(d2);
+			float inv_d = rsqrt_fast(d2);
 			float inv_ld = fminf(inv_d, 10.0f); // 1 / max(0.1, dist)
 			float xr = fmaxf(0.1f, d2 * inv_d) * l2.w;
 			float t = __saturatef(fmaf(xr, 1.0f / (1.0f - 0.9f), -0.9f / (1.0f - 0.9f)));
@@ -295,7 +302,7 @@ __device__ __forceinline__ f2 mk2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ f2 rsqrt2(f2 a) { return make_float2(rsqrtf(a.x), rsqrtf(a.y)); }
+__device__ __forceinline__ f2 rsqrt2(f2 a) { return make_float2(rsqrt_fast(a.x), rsqrt_fast(a.y)); }
 __device__ __forceinline__ f2 clamp2(f2 a, float lo, float hi) { return make_float2(fminf(fmaxf(a.x, lo), hi), fminf(fmaxf(a.y, lo), hi)); }
 __device__ __forceinline__ f2 dot3_2(f2 ax, f2 ay, f2 az, f2 bx, f2 by, f2 bz) { return fma2(az, bz, fma2(ay, by, mul2(ax, bx))); }
 
@@ -305,25 +312,26 @@ struct Surface2
 	f2 Nx, Ny, Nz, Vx, Vy, Vz;
 	f2 F0x, F0y, F0z, oFx, oFy, oFz; // F0, 1 - F0
 	f2 dkx, dky, dkz, ndkx, ndky, ndkz; // diffuse_k and its negation
-	f2 m2m1, cgd, omk, k, Vk;
+	f2 m2m1, cgd, omk, k, Vk, NoVr;
 };
 
 // dk + F * (G*D - dk) per channel for both pixels; NoL returned for the caller's weight.
-__device__ __forceinline__ void brdf2(const Surface2 &s, f2 Lx, f2 Ly, f2 Lz, f2 &NoL, f2 &tx, f2 &ty, f2 &tz)
+__device__ __forceinline__ void brdf2(const Surface2 &s, f2 NoLr, f2 VoL, f2 &NoL, f2 &tx, f2 &ty, f2 &tz)
 {
-	f2 hx = add2(s.Vx, Lx), hy = add2(s.Vy, Ly), hz = add2(s.Vz, Lz);
-	f2 inv_h = rsqrt2(dot3_2(hx, hy, hz, hx, hy, hz));
-	NoL = clamp2(dot3_2(s.Nx, s.Ny, s.Nz, Lx, Ly, Lz), 0.001f, 1.0f);
-	f2 NoH = clamp2(mul2(dot3_2(s.Nx, s.Ny, s.Nz, hx, hy, hz), inv_h), 0.0001f, 1.0f);
-	f2 HoV = clamp2(mul2(dot3_2(hx, hy, hz, s.Vx, s.Vy, s.Vz), inv_h), 0.001f, 1.0f);
+	// NoLr = N.L and VoL = V.L for unit L; the half vector is never formed:
+	// |V+L|^2 = 2 + 2 VoL,  N.(V+L) = NoV + NoL,  V.(V+L) = 1 + VoL
+	f2 inv_h = rsqrt2(fma2(VoL, mk2(2.0f), mk2(2.0f)));
+	NoL = clamp2(NoLr, 0.001f, 1.0f);
+	f2 NoH = clamp2(mul2(add2(NoLr, s.NoVr), inv_h), 0.0001f, 1.0f);
+	f2 HoV = fma2(VoL, inv_h, inv_h); // <= 1 up to rounding, see brdf()
+	HoV = make_float2(fmaxf(HoV.x, 0.001f), fmaxf(HoV.y, 0.001f));
 	f2 f = fma2(HoV, mk2(-1.0f), mk2(1.0f));
 	f2 fsq = mul2(f, f);
 	f2 f5 = mul2(mul2(fsq, fsq), f);
 	f2 d = fma2(mul2(NoH, NoH), s.m2m1, mk2(1.0f));
-	f2 vl = mul2(s.Vk, fma2(NoL, s.omk, s.k));
-	vl = make_float2(fmaxf(vl.x, 0.001f), fmaxf(vl.y, 0.001f));
+	f2 vl = mul2(s.Vk, fma2(NoL, s.omk, s.k)); // >= 0.038, the shader's max(.., 1e-3) is the identity
 	f2 den = mul2(mul2(d, d), vl);
-	f2 GD = mul2(s.cgd, make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y)));
+	f2 GD = mul2(s.cgd, make_float2(rcp_fast(den.x), rcp_fast(den.y)));
 	f2 Fx = fma2(s.oFx, f5, s.F0x), Fy = fma2(s.oFy, f5, s.F0y), Fz = fma2(s.oFz, f5, s.F0z);
 	tx = fma2(Fx, add2(GD, s.ndkx), s.dkx);
 	ty = fma2(Fy, add2(GD, s.ndky), s.dky);
@@ -336,7 +344,7 @@ struct PixelSetup
 	uint32_t dst, rx, ry;
 	int cluster_base;
 	float3 pos, N, V, F0, dk, base_color;
-	float m2m1, cgd, omk, k, Vk;
+	float m2m1, cgd, omk, k, Vk, NoVr;
 };
 
 // Everything the 1-pixel kernel does before its light loop, for one pixel.
@@ -350,7 +358,7 @@ __device__ __forceinline__ PixelSetup setup_pixel(const LightingParams &p, const
 	q.ry = 0u;
 	q.cluster_base = 0;
 	q.pos = q.N = q.V = q.F0 = q.dk = q.base_color = make_float3(0.f, 0.f, 0.f);
-	q.m2m1 = q.cgd = q.omk = q.k = q.Vk = 0.0f;
+	q.m2m1 = q.cgd = q.omk = q.k = q.Vk = q.NoVr = 0.0f;
 	if (!q.lit)
 		return q;
 	q.base_color = make_float3(s_srgb[a8 & 0xffu], s_srgb[(a8 >> 8) & 0xffu], s_srgb[(a8 >> 16) & 0xffu]);
@@ -365,7 +373,7 @@ __device__ __forceinline__ PixelSetup setup_pixel(const LightingParams &p, const
 	q.rx = zr.x;
 	q.ry = zr.y;
 	float3 v = make_float3(p.camera_pos.x - q.pos.x, p.camera_pos.y - q.pos.y, p.camera_pos.z - q.pos.z);
-	float inv_v = rsqrtf(dot3(v, v));
+	float inv_v = rsqrt_fast(dot3(v, v));
 	q.V = make_float3(v.x * inv_v, v.y * inv_v, v.z * inv_v);
 	float rough = roughness_in * 0.75f + 0.25f;
 	float mm = rough * rough;
@@ -375,7 +383,8 @@ __device__ __forceinline__ PixelSetup setup_pixel(const LightingParams &p, const
 	float r1 = rough + 1.0f;
 	q.k = r1 * r1 * 0.125f;
 	q.omk = 1.0f - q.k;
-	float NoV = fminf(fmaxf(dot3(q.N, q.V), 0.001f), 1.0f);
+	q.NoVr = dot3(q.N, q.V);
+	float NoV = fminf(fmaxf(q.NoVr, 0.001f), 1.0f);
 	q.Vk = NoV * q.omk + q.k;
 	q.F0 = make_float3(0.04f * (1.0f - metallic) + q.base_color.x * metallic, 0.04f * (1.0f - metallic) + q.base_color.y * metallic,
 	                   0.04f * (1.0f - metallic) + q.base_color.z * metallic);
@@ -402,12 +411,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 	if (inside)
 	{
 		depth = __ldg(reinterpret_cast<const float2 *>(&p.depth.at(x, y)));
-		if (depth.x != 0.0f || depth.y != 0.0f)
-		{
-			a8 = __ldg(reinterpret_cast<const uint2 *>(&p.albedo.at(x, y)));
-			n10 = __ldg(reinterpret_cast<const uint2 *>(&p.normal.at(x, y)));
-			mr2 = __ldg(reinterpret_cast<const uint32_t *>(&p.pbr.at(x, y)));
-		}
+		// not gated on depth != 0: a dependent second round trip to HBM costs more than the sky's bytes
+		a8 = __ldg(reinterpret_cast<const uint2 *>(&p.albedo.at(x, y)));
+		n10 = __ldg(reinterpret_cast<const uint2 *>(&p.normal.at(x, y)));
+		mr2 = __ldg(reinterpret_cast<const uint32_t *>(&p.pbr.at(x, y)));
 		em = __ldg(reinterpret_cast<const uint2 *>(&p.emissive.at(x, y)));
 	}
 	PixelSetup A = setup_pixel(p, s_srgb, x, y, inside, depth.x, a8.x, n10.x, mr2 & 0xffffu, em.x);
@@ -423,12 +430,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 	s.ndkx = make_float2(-A.dk.x, -B.dk.x); s.ndky = make_float2(-A.dk.y, -B.dk.y); s.ndkz = make_float2(-A.dk.z, -B.dk.z);
 	s.m2m1 = make_float2(A.m2m1, B.m2m1); s.cgd = make_float2(A.cgd, B.cgd);
 	s.omk = make_float2(A.omk, B.omk); s.k = make_float2(A.k, B.k); s.Vk = make_float2(A.Vk, B.Vk);
+	s.NoVr = make_float2(A.NoVr, B.NoVr);
 
 	// ---- draw 1: directional light for both pixels ----
 	uint32_t dstA = A.dst, dstB = B.dst;
 	{
 		f2 NoL, tx, ty, tz;
-		brdf2(s, mk2(p.dir_dir.x), mk2(p.dir_dir.y), mk2(p.dir_dir.z), NoL, tx, ty, tz);
+		const f2 dx = mk2(p.dir_dir.x), dy = mk2(p.dir_dir.y), dz = mk2(p.dir_dir.z);
+		brdf2(s, dot3_2(s.Nx, s.Ny, s.Nz, dx, dy, dz), dot3_2(s.Vx, s.Vy, s.Vz, dx, dy, dz), NoL, tx, ty, tz);
 		if (A.lit)
 		{
 			float3 e = unpack_r11g11b10(dstA);
@@ -448,7 +457,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 	int z_start = (int)__reduce_min_sync(0xffffffffu, min(loA, loB));
 	int z_end = (int)__reduce_max_sync(0xffffffffu, max(A.lit ? hiA : 0u, B.lit ? hiB : 0u));
 	z_end = min(z_end, p.n32 - 1);
-	float3 accA = make_float3(0.f, 0.f, 0.f), accB = make_float3(0.f, 0.f, 0.f);
+	f2 accx = mk2(0.0f), accy = mk2(0.0f), accz = mk2(0.0f);
 	for (int i = z_start; i <= z_end; i++)
 	{
 		uint32_t ownA = 0u, ownB = 0u;
@@ -469,8 +478,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 			const float inv_r2 = l2.w * l2.w;
 			const bool nearA = ((ownA >> bit) & 1u) && (d2.x * inv_r2 < 1.0f);
 			const bool nearB = ((ownB >> bit) & 1u) && (d2.y * inv_r2 < 1.0f);
+			// quick reject: beyond the light's radius the falloff is exactly 0 (point.h:41-43)
 			if (!__any_sync(0xffffffffu, nearA || nearB))
 				continue;
+			// (requesting the next light's record ahead of this evaluation was tried: it needs 8 more
+			// registers, and at 4 CTAs per SM, or squeezed back into 96, the frame got slower)
 			const float4 l0 = __ldg(lp);
 			f2 inv_d = rsqrt2(d2);
 			f2 inv_ld = make_float2(fminf(inv_d.x, 10.0f), fminf(inv_d.y, 10.0f));
@@ -479,32 +491,28 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 			f2 t = fma2(xr, mk2(1.0f / (1.0f - 0.9f)), mk2(-0.9f / (1.0f - 0.9f)));
 			t = make_float2(__saturatef(t.x), __saturatef(t.y));
 			f2 falloff = fma2(mul2(mul2(t, t), fma2(mk2(-2.0f), t, mk2(3.0f))), mk2(-1.0f), mk2(1.0f));
-			f2 Lx = mul2(lx, inv_d), Ly = mul2(ly, inv_d), Lz = mul2(lz, inv_d);
+			// L = l * inv_d is never formed either: every use of it is a dot product
 			if (!((tm >> bit) & 1u))
 			{
 				float2 sb = __half22float2(*reinterpret_cast<const __half2 *>(&l0.w));
-				f2 cone_angle = mul2(dot3_2(Lx, Ly, Lz, mk2(l2.x), mk2(l2.y), mk2(l2.z)), mk2(-1.0f));
-				f2 cone = fma2(cone_angle, mk2(sb.x), mk2(sb.y));
+				f2 cone_angle = mul2(dot3_2(lx, ly, lz, mk2(l2.x), mk2(l2.y), mk2(l2.z)), inv_d);
+				f2 cone = fma2(cone_angle, mk2(-sb.x), mk2(sb.y));
 				cone = make_float2(__saturatef(cone.x), __saturatef(cone.y));
 				falloff = mul2(falloff, mul2(cone, cone));
 			}
+			f2 NoLr = mul2(dot3_2(s.Nx, s.Ny, s.Nz, lx, ly, lz), inv_d);
+			f2 VoL = mul2(dot3_2(s.Vx, s.Vy, s.Vz, lx, ly, lz), inv_d);
 			f2 NoL, tx, ty, tz;
-			brdf2(s, Lx, Ly, Lz, NoL, tx, ty, tz);
+			brdf2(s, NoLr, VoL, NoL, tx, ty, tz);
 			f2 w = mul2(mul2(NoL, falloff), mul2(inv_ld, inv_ld));
-			if (nearA && falloff.x > 0.0f)
-			{
-				accA.x = fmaf(l0.x * w.x, tx.x, accA.x);
-				accA.y = fmaf(l0.y * w.x, ty.x, accA.y);
-				accA.z = fmaf(l0.z * w.x, tz.x, accA.z);
-			}
-			if (nearB && falloff.y > 0.0f)
-			{
-				accB.x = fmaf(l0.x * w.y, tx.y, accB.x);
-				accB.y = fmaf(l0.y * w.y, ty.y, accB.y);
-				accB.z = fmaf(l0.z * w.y, tz.y, accB.z);
-			}
+			// a lane outside the light's mask or radius adds exactly 0 (falloff is 0 beyond the radius)
+			w = make_float2(nearA ? w.x : 0.0f, nearB ? w.y : 0.0f);
+			accx = fma2(mul2(mk2(l0.x), w), tx, accx);
+			accy = fma2(mul2(mk2(l0.y), w), ty, accy);
+			accz = fma2(mul2(mk2(l0.z), w), tz, accz);
 		}
 	}
+	const float3 accA = make_float3(accx.x, accy.x, accz.x), accB = make_float3(accx.y, accy.y, accz.y);
 
 	if (inside)
 	{
@@ -523,6 +531,79 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 		if (A.lit || B.lit || p.emissive.p != p.hdr.p)
 			*reinterpret_cast<uint2 *>(&p.hdr.at(x, y)) = out;
 	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Work estimate of the lighting pass per group of 4 pixel rows (one row of CTAs), in issued warp
+// instructions.  The light density of a frame is far from uniform (in the bench scene 3 % of the
+// rows hold over half of the light evaluations), so equal-height row bands do not split the pass
+// equally between GPUs.  This kernel repeats the lighting kernel's cluster walk for the same
+// 16x4 pixel blocks -- position, (tile, Z slice), word range, union of the lanes' masks, radius
+// test -- without shading, and charges each step what the shading kernel's SASS spends on it.
+constexpr uint32_t kCostSetup = 700u;   // per warp: G-buffer decode, position, BRDF invariants, directional light, stores
+constexpr uint32_t kCostWord = 45u;     // per 32-light word of the Z range: two mask loads, range masks, warp OR
+constexpr uint32_t kCostUnion = 29u;    // per light in the warp's union: record load, distance, radius vote
+constexpr uint32_t kCostEvaluate = 89u; // per light that reaches a pixel of the block: falloff, cone, BRDF, accumulate
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) lighting_cost_kernel(const LightingParams p, uint32_t *__restrict__ cost)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int x = ((blockIdx.x * kWarpsPerCta + warp) * 8 + (lane & 7)) * 2;
+	const int y = p.y0 + blockIdx.y * 4 + (lane >> 3);
+	if (__all_sync(0xffffffffu, x >= p.depth.w || y >= p.y1))
+		return;
+	float3 pos[2];
+	uint32_t rx[2] = { 0xffffffffu, 0xffffffffu }, ry[2] = { 0u, 0u };
+	int base[2] = { 0, 0 };
+	bool lit[2] = { false, false };
+#pragma unroll
+	for (int k = 0; k < 2; k++)
+	{
+		pos[k] = make_float3(0.f, 0.f, 0.f);
+		if (x + k < p.depth.w && y < p.y1)
+		{
+			const float depth = __ldg(&p.depth.at(x + k, y));
+			if (depth != 0.0f)
+			{
+				int tile_index, z_index;
+				pos[k] = reconstruct_position_and_cluster(p, x + k, y, depth, tile_index, z_index);
+				base[k] = tile_index * p.n32;
+				const uint2 zr = __ldg(&p.cluster_range[z_index]);
+				rx[k] = zr.x;
+				ry[k] = zr.y;
+				lit[k] = true;
+			}
+		}
+	}
+	const uint32_t lo0 = rx[0] >> 5, hi0 = ry[0] >> 5, lo1 = rx[1] >> 5, hi1 = ry[1] >> 5;
+	int z_start = (int)__reduce_min_sync(0xffffffffu, min(lo0, lo1));
+	int z_end = (int)__reduce_max_sync(0xffffffffu, max(lit[0] ? hi0 : 0u, lit[1] ? hi1 : 0u));
+	z_end = min(z_end, p.n32 - 1);
+	uint32_t total = kCostSetup;
+	for (int i = z_start; i <= z_end; i++)
+	{
+		uint32_t own0 = 0u, own1 = 0u;
+		if (lit[0] && (uint32_t)i >= lo0 && (uint32_t)i <= hi0)
+			own0 = cluster_mask_range(__ldg(&p.bitmask[base[0] + i]), rx[0], ry[0], 32u * (uint32_t)i);
+		if (lit[1] && (uint32_t)i >= lo1 && (uint32_t)i <= hi1)
+			own1 = cluster_mask_range(__ldg(&p.bitmask[base[1] + i]), rx[1], ry[1], 32u * (uint32_t)i);
+		uint32_t wmask = __reduce_or_sync(0xffffffffu, own0 | own1);
+		total += kCostWord;
+		while (wmask)
+		{
+			const int bit = __ffs(wmask) - 1;
+			wmask &= wmask - 1u;
+			const float4 *lp = reinterpret_cast<const float4 *>(p.lights + (i * 32 + bit));
+			const float4 l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+			const float inv_r2 = l2.w * l2.w;
+			const float3 a = make_float3(l1.x - pos[0].x, l1.y - pos[0].y, l1.z - pos[0].z);
+			const float3 b = make_float3(l1.x - pos[1].x, l1.y - pos[1].y, l1.z - pos[1].z);
+			const bool near = (((own0 >> bit) & 1u) && dot3(a, a) * inv_r2 < 1.0f) || (((own1 >> bit) & 1u) && dot3(b, b) * inv_r2 < 1.0f);
+			total += __any_sync(0xffffffffu, near) ? (kCostUnion + kCostEvaluate) : kCostUnion;
+		}
+	}
+	if (lane == 0)
+		atomicAdd(&cost[blockIdx.y], total);
 }
 } // namespace
 
@@ -662,4 +743,52 @@ extern "C" int32_t grb_debug_cluster_indices(const GrbImage *depth, const GrbCam
 	dim3 grid((depth->width + 31) / 32, (rows.y1 - rows.y0 + 3) / 4, 1);
 	cluster_indices_kernel<<<grid, 128, 0, as_stream(stream)>>>(p, out_tile, out_z);
 	return check_launch("grb_debug_cluster_indices");
+}
+
+extern "C" int32_t grb_lighting_row_cost(const GrbImage *depth, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
+                                         GrbRows rows, uint32_t *cost_per_4_rows, void *stream)
+{
+	if (!image_ok(depth, GRB_FORMAT_D32_SFLOAT, 4) || !cam || !params || !buf || !cost_per_4_rows)
+	{
+		set_last_error("grb_lighting_row_cost: bad arguments");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	if (!buf->cluster_range || (params->num_lights > 0 && (!buf->lights || !buf->bitmask)))
+	{
+		set_last_error("grb_lighting_row_cost: null cluster buffer");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	rows = full_rows(rows, depth->height);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	const int groups = (rows.y1 - rows.y0 + 3) / 4;
+	cudaError_t err = cudaMemsetAsync(cost_per_4_rows, 0, sizeof(uint32_t) * (size_t)groups, as_stream(stream));
+	if (err != cudaSuccess)
+	{
+		set_last_error(cudaGetErrorString(err));
+		return GRB_ERR_CUDA;
+	}
+	LightingParams p{};
+	p.depth = view_of<const float>(depth);
+	for (int i = 0; i < 16; i++)
+		p.ivp[i] = cam->inv_view_projection[i];
+	p.cbase = make_float3(params->camera_base[0], params->camera_base[1], params->camera_base[2]);
+	p.cfront = make_float3(params->camera_front[0], params->camera_front[1], params->camera_front[2]);
+	p.xy_scale = make_float2(params->xy_scale[0], params->xy_scale[1]);
+	p.res_x = params->resolution_xy[0];
+	p.res_y = params->resolution_xy[1];
+	p.n32 = params->num_lights_32;
+	p.z_max_index = params->z_max_index;
+	p.z_scale = params->z_scale;
+	p.inv_res_x = 1.0f / (float)depth->width;
+	p.inv_res_y = 1.0f / (float)depth->height;
+	p.lights = buf->lights;
+	p.bitmask = buf->bitmask;
+	p.cluster_range = reinterpret_cast<const uint2 *>(buf->cluster_range);
+	p.y0 = rows.y0;
+	p.y1 = rows.y1;
+	const int pairs = (depth->width + 1) / 2;
+	dim3 grid((pairs + 8 * kWarpsPerCta - 1) / (8 * kWarpsPerCta), groups, 1);
+	lighting_cost_kernel<<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p, cost_per_4_rows);
+	return check_launch("grb_lighting_row_cost");
 }

@@ -9,6 +9,8 @@
 // coalesced accesses; the small pyramid levels live entirely in the 126 MB L2.
 #include "grb_common.cuh"
 
+#include <cstdio>
+
 namespace grb
 {
 namespace
@@ -107,6 +109,80 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) bloom_upsample_kernel(View<c
 	float u = ((float)x + 0.5f) * inv_w;
 	float v = ((float)y + 0.5f) * inv_h;
 	out.at(x, y) = pack_rgba16f(tent9(src, u, v, 0.875f, inv_in_w, inv_in_h));
+}
+
+
+// ------------------------------------------------------------------------------- K8 + all-gather
+// Row-sharded frames: the first downsample (1/2 -> 1/4 resolution) of a rank's band is needed in
+// full by every rank for the pyramid tail.  Instead of producing the band locally and handing it
+// to a collective afterwards, the kernel stores each texel straight into the 1/4-resolution image
+// of every rank (its own and the peers' over NVLink / NVSwitch, plain 8-byte stores to mapped
+// peer memory) and then publishes "band of frame <epoch> landed" in every rank's flag array.
+// The consumer side is peer_wait_kernel below.  Texel values are those of
+// bloom_downsample_kernel<false>.
+struct PeerTargets
+{
+	uint2 *data[GRB_MAX_PEERS];
+	uint32_t *flags[GRB_MAX_PEERS];
+	int count;
+};
+
+__device__ __forceinline__ void store_release_system(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t load_acquire_system(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__global__ void __launch_bounds__(kBlockX *kBlockY) bloom_downsample_peers_kernel(View<const uint2> src, PeerTargets targets, int out_w, int out_pitch_texels,
+                                                                                 int y0, int y1, float inv_w, float inv_h, float inv_in_w, float inv_in_h,
+                                                                                 int flag_index, uint32_t epoch, unsigned *ctas_done)
+{
+	const int x = blockIdx.x * kBlockX + threadIdx.x;
+	const int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
+	if (x < out_w && y < y1)
+	{
+		const float u = ((float)x + 0.5f) * inv_w;
+		const float v = ((float)y + 0.5f) * inv_h;
+		const uint2 texel = pack_rgba16f(tent9(src, u, v, 1.75f, inv_in_w, inv_in_h));
+		const size_t at = (size_t)y * out_pitch_texels + x;
+		for (int r = 0; r < targets.count; r++)
+			targets.data[r][at] = texel;
+	}
+	// publish: every thread's stores are ordered before its CTA's arrival; the last CTA to arrive
+	// raises this rank's flag on every peer (threadFenceReduction pattern at system scope)
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0 && threadIdx.y == 0)
+	{
+		const unsigned total = gridDim.x * gridDim.y;
+		if (atomicAdd(ctas_done, 1u) == total - 1u)
+		{
+			*ctas_done = 0u;
+			__threadfence_system();
+			for (int r = 0; r < targets.count; r++)
+				store_release_system(targets.flags[r] + flag_index, epoch);
+		}
+	}
+}
+
+// One thread per producing rank spins until that rank's band of frame `epoch` has landed here.
+__global__ void peer_wait_kernel(const uint32_t *flags, int count, uint32_t epoch)
+{
+	if ((int)threadIdx.x < count)
+	{
+		// bounded (~4 s): a rank that died must not hang the GPUs of the others
+		for (unsigned spins = 0; (int32_t)(load_acquire_system(flags + threadIdx.x) - epoch) < 0; spins++)
+		{
+			if (spins > (1u << 25))
+			{
+				printf("granite_b200: timed out waiting for rank %d's band of frame %u\n", (int)threadIdx.x, epoch);
+				break;
+			}
+			__nanosleep(128);
+		}
+	}
 }
 
 // ------------------------------------------------------------------------------- K10
@@ -272,16 +348,18 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) tonemap_kernel(View<const ui
 // pixel with the same exact fp32 expressions as the generic kernel; the tone curve and the sRGB
 // OETF use the fast reciprocal / lg2 / ex2 units (error ~1e-4 LSB, the bar is 1 LSB), because
 // with the accurate powf this streaming pass was issue-bound at 8 % of the HBM roofline.
-__device__ __forceinline__ float uncharted2_fast(float x)
+// (uncharted2(x)) * white_scale with the constant term folded into one FMA
+__device__ __forceinline__ float uncharted2_fast_scaled(float x, float white_scale)
 {
 	const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
-	return __fdividef(fmaf(x, fmaf(A, x, C * B), D * E), fmaf(x, fmaf(A, x, B), D * F)) - E / F;
+	const float q = fmaf(x, fmaf(A, x, C * B), D * E) * rcp_fast(fmaf(x, fmaf(A, x, B), D * F));
+	return fmaf(q, white_scale, -(E / F) * white_scale);
 }
 
 __device__ __forceinline__ uint32_t srgb8_fast(float c)
 {
 	c = __saturatef(c); // also NaN -> 0
-	float s = c <= 0.0031308f ? c * (12.92f * 255.0f) : fmaf(__powf(c, 1.0f / 2.4f), 1.055f * 255.0f, -0.055f * 255.0f);
+	float s = c <= 0.0031308f ? c * (12.92f * 255.0f) : fmaf(ex2_fast(lg2_fast(c) * (1.0f / 2.4f)), 1.055f * 255.0f, -0.055f * 255.0f);
 	return (uint32_t)min(__float2int_rd(s + 0.5f), 255);
 }
 
@@ -340,9 +418,9 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) tonemap4_kernel(View<const u
 		const float bgr = bilin_mix(t00.y, t10.y, t01.y, t11.y, wa, wb);
 		const float bb = bilin_mix(t00.z, t10.z, t01.z, t11.z, wa, wb);
 		const float3 c = unpack_r11g11b10(hp[j]);
-		const float r = uncharted2_fast(fmul(fadd(c.x, bx), kexp)) * white_scale;
-		const float g = uncharted2_fast(fmul(fadd(c.y, bgr), kexp)) * white_scale;
-		const float b = uncharted2_fast(fmul(fadd(c.z, bb), kexp)) * white_scale;
+		const float r = uncharted2_fast_scaled(fmul(fadd(c.x, bx), kexp), white_scale);
+		const float g = uncharted2_fast_scaled(fmul(fadd(c.y, bgr), kexp), white_scale);
+		const float b = uncharted2_fast_scaled(fmul(fadd(c.z, bb), kexp), white_scale);
 		px[j] = SrgbTarget ? (srgb8_fast(r) | (srgb8_fast(g) << 8) | (srgb8_fast(b) << 16) | 0xff000000u)
 		                   : (unorm8_fast(r) | (unorm8_fast(g) << 8) | (unorm8_fast(b) << 16) | 0xff000000u);
 	}
@@ -690,6 +768,52 @@ extern "C" int32_t grb_bloom_downsample(const GrbImage *in, const GrbImage *hist
 		bloom_downsample_kernel<false><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint2>(in), View<const uint2>{}, lerp, view_of<uint2>(out),
 		                                                                       rows.y0, rows.y1, inv_w, inv_h, inv_in_w, inv_in_h);
 	return check_launch("grb_bloom_downsample");
+}
+
+extern "C" int32_t grb_bloom_downsample_to_peers(const GrbImage *in, const GrbImage *out_layout, void *const *peer_images, uint32_t *const *peer_flags,
+                                                 int32_t peer_count, int32_t flag_index, uint32_t epoch, uint32_t *scratch_counter, GrbRows rows,
+                                                 void *stream)
+{
+	if (!image_ok(in, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || !out_layout || out_layout->format != GRB_FORMAT_R16G16B16A16_SFLOAT || !peer_images ||
+	    !peer_flags || !scratch_counter || peer_count < 1 || peer_count > GRB_MAX_PEERS || flag_index < 0 || (out_layout->row_pitch % 8) != 0)
+	{
+		set_last_error("grb_bloom_downsample_to_peers: bad arguments");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	rows = full_rows(rows, out_layout->height);
+	PeerTargets targets{};
+	targets.count = peer_count;
+	for (int r = 0; r < peer_count; r++)
+	{
+		if (!peer_images[r] || !peer_flags[r])
+		{
+			set_last_error("grb_bloom_downsample_to_peers: null peer pointer");
+			return GRB_ERR_INVALID_ARGUMENT;
+		}
+		targets.data[r] = static_cast<uint2 *>(peer_images[r]);
+		targets.flags[r] = peer_flags[r];
+	}
+	// an empty band still has to raise the flags: one CTA with nothing to store
+	const int row_count = rows.y1 > rows.y0 ? rows.y1 - rows.y0 : 0;
+	dim3 grid = grid_for(out_layout->width, row_count > 0 ? row_count : 1), block(kBlockX, kBlockY);
+	if (row_count == 0)
+		grid = dim3(1, 1, 1);
+	bloom_downsample_peers_kernel<<<grid, block, 0, as_stream(stream)>>>(
+	    view_of<const uint2>(in), targets, row_count > 0 ? out_layout->width : 0, out_layout->row_pitch / 8, rows.y0, rows.y0 + row_count,
+	    1.0f / (float)out_layout->width, 1.0f / (float)out_layout->height, 1.0f / (float)in->width, 1.0f / (float)in->height, flag_index, epoch,
+	    scratch_counter);
+	return check_launch("grb_bloom_downsample_to_peers");
+}
+
+extern "C" int32_t grb_peer_wait(const uint32_t *local_flags, int32_t count, uint32_t epoch, void *stream)
+{
+	if (!local_flags || count < 1 || count > GRB_MAX_PEERS)
+	{
+		set_last_error("grb_peer_wait: bad arguments");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(local_flags, count, epoch);
+	return check_launch("grb_peer_wait");
 }
 
 extern "C" int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream)

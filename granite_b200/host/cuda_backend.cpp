@@ -2,8 +2,11 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <map>
 #include <stdexcept>
 
 namespace Granite
@@ -34,6 +37,54 @@ bool cuda_ok(int err, const char *what)
 		return true;
 	log_error("%s: %s\n", what, cudaGetErrorString((cudaError_t)err));
 	return false;
+}
+
+namespace
+{
+std::map<std::string, std::pair<double, unsigned>> &profile_sections()
+{
+	static std::map<std::string, std::pair<double, unsigned>> sections;
+	return sections;
+}
+double now_us()
+{
+	return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+} // namespace
+
+bool HostProfile::enabled()
+{
+	static const bool on = std::getenv("GRB_HOST_PROFILE") != nullptr;
+	return on;
+}
+
+void HostProfile::add(const char *name, double microseconds)
+{
+	auto &slot = profile_sections()[name];
+	slot.first += microseconds;
+	slot.second++;
+}
+
+void HostProfile::report(unsigned frames)
+{
+	if (!enabled() || !frames)
+		return;
+	std::fprintf(stderr, "[granite_b200] host profile over %u frames (us per frame, calls per frame):\n", frames);
+	for (auto &kv : profile_sections())
+		std::fprintf(stderr, "  %-36s %9.1f  %6.1f\n", kv.first.c_str(), kv.second.first / frames, double(kv.second.second) / frames);
+	profile_sections().clear();
+}
+
+ScopedHostTimer::ScopedHostTimer(const char *name_) : name(name_)
+{
+	if (HostProfile::enabled())
+		t0 = now_us();
+}
+
+ScopedHostTimer::~ScopedHostTimer()
+{
+	if (HostProfile::enabled())
+		HostProfile::add(name, now_us() - t0);
 }
 
 Device::Device(int cuda_device_index, Stream stream_) : index(cuda_device_index), stream(stream_)

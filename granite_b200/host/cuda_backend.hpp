@@ -186,6 +186,26 @@ private:
 void log_error(const char *fmt, ...);
 void log_info(const char *fmt, ...);
 bool cuda_ok(int cuda_error, const char *what);
+
+// Host-side section timer (GRB_HOST_PROFILE=1): accumulates wall time per named section of the
+// frame recording and prints the averages when the report is requested.
+struct HostProfile
+{
+	static bool enabled();
+	static void add(const char *name, double microseconds);
+	static void report(unsigned frames);
+};
+
+class ScopedHostTimer
+{
+public:
+	explicit ScopedHostTimer(const char *name_);
+	~ScopedHostTimer();
+
+private:
+	const char *name;
+	double t0 = 0.0;
+};
 } // namespace CUDA
 } // namespace Granite
 

@@ -1,6 +1,9 @@
 #include "nccl_collectives.hpp"
 
+#include <cuda_runtime.h>
 #include <dlfcn.h>
+
+#include <cstdlib>
 
 #include <cstring>
 #include <mutex>
@@ -28,6 +31,7 @@ struct NcclApi
 	int (*CommDestroy)(ncclComm_t) = nullptr;
 	int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, void *) = nullptr;
 	int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, void *) = nullptr;
+	int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, void *) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(int) = nullptr;
@@ -60,6 +64,7 @@ NcclApi &api()
 		GRB_SYM(CommDestroy, "ncclCommDestroy")
 		GRB_SYM(AllReduce, "ncclAllReduce")
 		GRB_SYM(Broadcast, "ncclBroadcast")
+		GRB_SYM(AllGather, "ncclAllGather")
 		GRB_SYM(GroupStart, "ncclGroupStart")
 		GRB_SYM(GroupEnd, "ncclGroupEnd")
 		GRB_SYM(GetErrorString, "ncclGetErrorString")
@@ -79,6 +84,7 @@ bool nccl_ok(int rc, const char *what)
 
 NcclCollectives::~NcclCollectives()
 {
+	release_peer_exchange();
 	if (comm && api().CommDestroy)
 		api().CommDestroy(comm);
 }
@@ -148,5 +154,125 @@ bool NcclCollectives::all_reduce_sum(Vulkan::CommandBuffer &cmd, float *data, si
 	if (!comm)
 		return false;
 	return nccl_ok(api().AllReduce(data, data, count, ncclFloat32, ncclSum, comm, cmd.get_stream_handle()), "ncclAllReduce");
+}
+
+// ----------------------------------------------------------------------------- peer exchange
+void NcclCollectives::release_peer_exchange()
+{
+	for (void *p : peer.opened)
+		cudaIpcCloseMemHandle(p);
+	peer.opened.clear();
+	for (auto &img : peer.local_images)
+	{
+		if (img)
+			cudaFree(img);
+		img = nullptr;
+	}
+	if (peer.local_flags)
+		cudaFree(peer.local_flags);
+	peer.local_flags = nullptr;
+	peer.ok = false;
+}
+
+bool NcclCollectives::setup_peer_exchange(size_t image_bytes)
+{
+	// Collective: every rank calls this with the same size at the same point of its first sharded frame.
+	struct Handles
+	{
+		cudaIpcMemHandle_t image[2];
+		cudaIpcMemHandle_t flags;
+		int ok;
+	};
+	auto &a = api();
+	Handles mine = {};
+	mine.ok = 1;
+	const char *mode = std::getenv("GRB_SHARD_EXCHANGE");
+	if (!comm || world > 8 || (mode && std::string(mode) == "nccl"))
+		mine.ok = 0;
+	if (mine.ok)
+	{
+		for (auto &img : peer.local_images)
+			mine.ok = mine.ok && cudaMalloc(&img, image_bytes) == cudaSuccess && cudaMemset(img, 0, image_bytes) == cudaSuccess;
+		void *f = nullptr;
+		mine.ok = mine.ok && cudaMalloc(&f, sizeof(uint32_t) * 16) == cudaSuccess && cudaMemset(f, 0, sizeof(uint32_t) * 16) == cudaSuccess;
+		peer.local_flags = static_cast<uint32_t *>(f);
+		for (int k = 0; k < 2 && mine.ok; k++)
+			mine.ok = cudaIpcGetMemHandle(&mine.image[k], peer.local_images[k]) == cudaSuccess;
+		mine.ok = mine.ok && cudaIpcGetMemHandle(&mine.flags, peer.local_flags) == cudaSuccess;
+		if (!mine.ok)
+			cudaGetLastError();
+	}
+
+	// exchange the handles (and whether every rank could create them) through the communicator
+	Handles *dev = nullptr;
+	std::vector<Handles> all(world);
+	bool ok = cudaMalloc(&dev, sizeof(Handles) * (world + 1)) == cudaSuccess;
+	cudaStream_t s = nullptr;
+	ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaMemcpyAsync(dev + world, &mine, sizeof(Handles), cudaMemcpyHostToDevice, s) == cudaSuccess;
+	ok = ok && nccl_ok(a.AllGather(dev + world, dev, sizeof(Handles), ncclInt8, comm, s), "ncclAllGather(ipc handles)");
+	ok = ok && cudaMemcpyAsync(all.data(), dev, sizeof(Handles) * world, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+	ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+	if (s)
+		cudaStreamDestroy(s);
+	if (dev)
+		cudaFree(dev);
+	for (unsigned r = 0; r < world && ok; r++)
+		ok = all[r].ok != 0;
+	for (unsigned r = 0; r < world && ok; r++)
+	{
+		if (r == rank)
+		{
+			peer.images[0][r] = peer.local_images[0];
+			peer.images[1][r] = peer.local_images[1];
+			peer.flags[r] = peer.local_flags;
+			continue;
+		}
+		void *p[3] = {};
+		ok = cudaIpcOpenMemHandle(&p[0], all[r].image[0], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+		     cudaIpcOpenMemHandle(&p[1], all[r].image[1], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+		     cudaIpcOpenMemHandle(&p[2], all[r].flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+		for (void *q : p)
+			if (q)
+				peer.opened.push_back(q);
+		peer.images[0][r] = p[0];
+		peer.images[1][r] = p[1];
+		peer.flags[r] = static_cast<uint32_t *>(p[2]);
+	}
+	if (!ok)
+	{
+		cudaGetLastError();
+		if (!(mode && std::string(mode) == "nccl"))
+			Vulkan::log_info("peer-memory exchange unavailable on rank %u (no IPC / peer access); using NCCL broadcasts.\n", rank);
+		release_peer_exchange();
+		return false;
+	}
+	peer.image_bytes = image_bytes;
+	return true;
+}
+
+bool NcclCollectives::peer_exchange_begin_frame(size_t image_bytes, PeerSlot &slot)
+{
+	if (!peer.tried || (peer.ok && peer.image_bytes != image_bytes))
+	{
+		// (a re-bake at another size re-creates the buffers; all ranks re-bake together)
+		if (peer.tried)
+			release_peer_exchange();
+		peer.tried = true;
+		peer.ok = setup_peer_exchange(image_bytes);
+	}
+	if (!peer.ok)
+		return false;
+	peer.epoch++;
+	const unsigned k = peer.epoch & 1u;
+	slot.count = world;
+	slot.epoch = peer.epoch;
+	slot.counter = peer.local_flags + 8;
+	for (unsigned r = 0; r < world; r++)
+	{
+		slot.images[r] = peer.images[k][r];
+		slot.flags[r] = peer.flags[r];
+	}
+	return true;
 }
 } // namespace Granite

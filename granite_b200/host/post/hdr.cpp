@@ -5,7 +5,8 @@
 // dependent ones.
 //
 // Row-sharded frames: levels t (1/2) and d0 (1/4) -- 95 % of the bloom bytes -- are produced for
-// the rank's own band only; d0 bands are all-gathered, the pyramid tail (d1..d3, u2, u1: < 1.5 MB
+// the rank's own band only; d0 bands are exchanged (peer stores from the downsample kernel, or
+// NCCL broadcasts), the pyramid tail (d1..d3, u2, u1: < 1.5 MB
 // in total at 4K) is computed redundantly on every rank, the average-luminance grid is summed
 // across ranks, u0 and the tonemap are again band-only.  Every texel any rank computes is
 // computed from the same inputs by the same kernel, so the frame is bit-identical for any
@@ -47,9 +48,24 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 
 	// bloom_threshold_build_compute: uses LAST frame's average luminance (hdr.cpp:355)
 	cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
-	cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, stream), "grb_bloom_downsample(d0)");
+	// The d0 bands are needed in full by every rank.  Preferred: the downsample kernel itself stores
+	// its band into every rank's copy over NVLink peer memory and raises a flag (no collective
+	// launch, no second pass over the band); otherwise NCCL broadcasts after a local downsample.
+	RenderGraphCollectives::PeerSlot slot;
+	const bool peer_stores = sharded && graph.get_collectives()->peer_exchange_begin_frame((size_t)d0.row_pitch * (size_t)d0.height, slot);
+	if (peer_stores)
+	{
+		const unsigned self = graph.get_collectives()->get_rank();
+		cmd.check(grb_bloom_downsample_to_peers(&t, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch, slot.counter, d0_rows,
+		                                        stream),
+		          "grb_bloom_downsample_to_peers");
+		cmd.check(grb_peer_wait(slot.flags[self], (int32_t)slot.count, slot.epoch, stream), "grb_peer_wait");
+		d0.data = slot.images[self]; // the pyramid tail reads the exchanged copy
+	}
+	else
+		cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, stream), "grb_bloom_downsample(d0)");
 
-	if (sharded)
+	if (sharded && !peer_stores)
 	{
 		std::vector<GrbRows> bands;
 		for (unsigned rank = 0; rank < graph.get_shard_count(); rank++)
@@ -72,7 +88,9 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	{
 		// luminance_build_compute (hdr.cpp:68-98): size = d3 / 2, lerp = 1 - 0.5^frame_time, clamp [-3, 2]
 		float lerp_lum = float(1.0 - std::pow(0.5, frame.frame_time));
-		if (sharded && r.lum_grid)
+		// with the exchanged d0 every rank holds the whole d3 and reduces it locally; the NCCL path
+		// keeps the reference split (band partial sums + all-reduce)
+		if (sharded && r.lum_grid && !peer_stores)
 		{
 			// each rank samples the grid rows of its own band; the sum over ranks of (value or 0)
 			// reassembles the grid exactly, then every rank reduces it in the shader's order

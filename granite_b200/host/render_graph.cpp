@@ -535,12 +535,15 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 			if (key)
 				last_access[key] = LastAccess{ pass_done_events[p][slot], stream };
 		};
-		for (auto *r : pass.get_all_reads())
-			wait_for(physical_key(*r, false));
-		for (auto *w : pass.get_all_writes())
-			wait_for(physical_key(*w, false));
-		for (auto *h : pass.get_history_inputs())
-			wait_for(physical_key(*h, true));
+		{
+			Vulkan::ScopedHostTimer timer("graph.cross-stream waits");
+			for (auto *r : pass.get_all_reads())
+				wait_for(physical_key(*r, false));
+			for (auto *w : pass.get_all_writes())
+				wait_for(physical_key(*w, false));
+			for (auto *h : pass.get_history_inputs())
+				wait_for(physical_key(*h, true));
+		}
 
 		Vulkan::Event begin = nullptr, end = nullptr;
 		if (timestamps)
@@ -550,13 +553,17 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 			dev.record_event_on(begin, stream);
 		}
 		cmd.begin_region(pass.get_name().c_str());
-		pass.build_render_pass(cmd, 0);
+		{
+			Vulkan::ScopedHostTimer timer(pass.get_name().c_str());
+			pass.build_render_pass(cmd, 0);
+		}
 		cmd.end_region();
 		if (timestamps)
 		{
 			dev.record_event_on(end, stream);
 			dev.register_time_interval(pass.get_name(), begin, end);
 		}
+		Vulkan::ScopedHostTimer timer("graph.pass-done event + marks");
 		if (!pass_done_events[p][slot])
 			pass_done_events[p][slot] = dev.request_event();
 		dev.record_event_on(pass_done_events[p][slot], stream);

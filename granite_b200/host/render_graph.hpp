@@ -48,6 +48,27 @@ public:
 	// Every rank contributes rows [rows[r].y0, rows[r].y1) of an image all ranks hold at full size.
 	virtual bool all_gather_rows(Vulkan::CommandBuffer &cmd, Vulkan::ImageView &image, const std::vector<GrbRows> &rows) = 0;
 	virtual bool all_reduce_sum(Vulkan::CommandBuffer &cmd, float *data, size_t count) = 0;
+
+	// Peer-memory exchange: a double-buffered image every rank holds in full, of which each rank
+	// PRODUCES some rows per frame by storing them into all ranks' copies from its own kernel
+	// (NVLink / NVSwitch peer stores) and then raising a per-rank flag.  begin_frame() returns
+	// this frame's slot: the copy's address on every rank as seen from this device, every rank's
+	// flag array, and the epoch to publish / wait for.  false = not available (single process
+	// without peer access, IPC refused...): callers then use all_gather_rows().
+	struct PeerSlot
+	{
+		void *images[8] = {};     // [rank] base address of this frame's slot on that rank
+		uint32_t *flags[8] = {};  // [rank] that rank's flag array (one uint32 per producing rank)
+		uint32_t *counter = nullptr; // local scratch for the producing kernel
+		uint32_t epoch = 0;
+		unsigned count = 0;
+	};
+	virtual bool peer_exchange_begin_frame(size_t image_bytes, PeerSlot &slot)
+	{
+		(void)image_bytes;
+		(void)slot;
+		return false;
+	}
 };
 
 class RenderPassInterface

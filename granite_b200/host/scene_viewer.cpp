@@ -63,6 +63,7 @@ struct GrbhViewer
 	bool baked = false;
 	std::string output_name;
 	const GrbhHostGBuffer *pending_upload = nullptr;
+	unsigned profiled_frames = 0;
 	std::map<std::string, std::pair<double, int>> timings;
 	std::vector<cudaEvent_t> pending_outputs; // one per async readback still in flight (oldest first)
 	std::vector<cudaEvent_t> free_output_events;
@@ -270,17 +271,27 @@ void GrbhViewer::render_frame(const GrbhHostGBuffer *host, double frame_time)
 	frame.elapsed_time += frame_time;
 	context.set_frame_parameters(frame);
 
-	graph.setup_attachments(*device, nullptr);
-	cluster.setup_render_pass_resources(graph);
+	{
+		Vulkan::ScopedHostTimer timer("frame.setup_attachments");
+		graph.setup_attachments(*device, nullptr);
+		cluster.setup_render_pass_resources(graph);
+	}
 
 	// update_scene: jitter.step, context.set_camera, LightClusterer::refresh
-	jitter.step(projection, view);
-	context.set_camera(projection, view);
-	cluster.refresh(context);
+	{
+		Vulkan::ScopedHostTimer timer("frame.camera + cluster refresh");
+		jitter.step(projection, view);
+		context.set_camera(projection, view);
+		cluster.refresh(context);
+	}
 
 	pending_upload = host;
-	graph.enqueue_render_passes(*device, composer);
+	{
+		Vulkan::ScopedHostTimer timer("frame.enqueue_render_passes");
+		graph.enqueue_render_passes(*device, composer);
+	}
 	pending_upload = nullptr;
+	profiled_frames++;
 
 	if (config.timestamps == 1)
 		for (auto &iv : device->collect_time_intervals())
@@ -343,6 +354,7 @@ extern "C" void grbh_viewer_destroy(GrbhViewer *viewer)
 		return;
 	if (viewer->device)
 		viewer->device->wait_idle();
+	Vulkan::HostProfile::report(viewer->profiled_frames);
 	for (auto e : viewer->pending_outputs)
 		cudaEventDestroy(e);
 	for (auto e : viewer->free_output_events)
@@ -681,6 +693,36 @@ extern "C" int32_t grbh_viewer_get_camera(GrbhViewer *v, GrbCamera *out, float *
 	if (inv_projection16)
 		std::memcpy(inv_projection16, rp.inv_projection.data(), 64);
 	return 0;
+}
+
+extern "C" int32_t grbh_viewer_measure_row_cost(GrbhViewer *v, uint32_t *out, int32_t capacity)
+{
+	if (!v || !v->baked || !v->device || !out)
+		return fail("grbh_viewer_measure_row_cost: needs a baked device viewer");
+	if (v->graph.is_sharded())
+		return fail("grbh_viewer_measure_row_cost: the viewer must hold the whole frame (not row-sharded)");
+	GRBH_TRY
+	const int groups = ((int)v->config.height + 3) / 4;
+	if (capacity < groups)
+		return fail("grbh_viewer_measure_row_cost: capacity too small");
+	v->device->wait_idle();
+	GrbImage depth = v->graph.get_physical_texture_resource(*v->res_depth).as_grb();
+	GrbCamera cam;
+	if (grbh_viewer_get_camera(v, &cam, nullptr, nullptr) != 0)
+		return -1;
+	GrbClusterParameters params = v->cluster.get_cluster_parameters_bindless();
+	GrbClusterBuffers buffers = v->cluster.get_cluster_buffers();
+	uint32_t *dev = nullptr;
+	if (!Vulkan::cuda_ok(cudaMalloc(&dev, sizeof(uint32_t) * groups), "cudaMalloc"))
+		return fail("cudaMalloc failed");
+	int32_t rc = grb_lighting_row_cost(&depth, &cam, &params, &buffers, GrbRows{ 0, 0 }, dev, v->device->get_stream());
+	bool ok = rc == GRB_OK && Vulkan::cuda_ok(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(v->device->get_stream())), "cudaStreamSynchronize") &&
+	          Vulkan::cuda_ok(cudaMemcpy(out, dev, sizeof(uint32_t) * groups, cudaMemcpyDeviceToHost), "cudaMemcpy");
+	cudaFree(dev);
+	if (!ok)
+		return fail(rc != GRB_OK ? grb_last_error_string() : "grbh_viewer_measure_row_cost: copy failed");
+	return groups;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_viewer_get_pass_names(GrbhViewer *v, char *buffer, int32_t capacity)

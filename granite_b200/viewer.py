@@ -163,6 +163,22 @@ def estimate_band_cost(projection, view, light_positions, light_colors, width, h
     return cost
 
 
+def band_partition_measured(height: int, width: int, world: int, cost_per_4_rows, align: int = 8, post_warp_inst_per_pixel: float = 9.4):
+    """Row bands of equal estimated GPU work from Viewer.measure_row_cost() (warp instructions of the
+    lighting pass per 4-row group).  The band-proportional part of the post chain (threshold,
+    first down/upsample, tonemap: ~300 thread instructions = 9.4 warp instructions per pixel, from
+    profiles/round1c_frame_launches.md) is added per row so that light-free bands are not free."""
+    assert align % 4 == 0
+    c = np.asarray(cost_per_4_rows, np.float64)
+    groups = (height + 3) // 4
+    assert len(c) == groups
+    c = c + post_warp_inst_per_pixel * width * 4.0
+    per = align // 4
+    n_units = (height + align - 1) // align
+    c = np.concatenate([c, np.zeros(n_units * per - groups)]).reshape(n_units, per).sum(axis=1)
+    return band_partition_weighted(height, world, c, align=align)
+
+
 PLAN_FIELDS = ("own", "fxaa", "tonemap", "upsample0", "downsample0", "threshold", "lighting", "lum_grid")
 
 
@@ -332,6 +348,14 @@ class Viewer:
         inv_proj = np.zeros(16, np.float32)
         _check(lib().grbh_viewer_get_camera(self._h, C.byref(cam), _vp(proj), _vp(inv_proj)), "grbh_viewer_get_camera")
         return cam, proj.reshape(4, 4), inv_proj.reshape(4, 4)
+
+    def measure_row_cost(self) -> np.ndarray:
+        """Estimated lighting work (warp instructions) per group of 4 rows of the frame rendered last;
+        unsharded viewers only (grbh_viewer_measure_row_cost)."""
+        groups = (self.height + 3) // 4
+        out = np.zeros(groups, np.uint32)
+        _check(lib().grbh_viewer_measure_row_cost(self._h, _vp(out), groups), "grbh_viewer_measure_row_cost")
+        return out
 
     def pass_names(self):
         buf = C.create_string_buffer(4096)

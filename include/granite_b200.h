@@ -182,6 +182,14 @@ int32_t grb_deferred_lighting(const GrbGBuffer *gbuffer, const GrbCamera *cam,
 int32_t grb_debug_cluster_indices(const GrbImage *depth, const GrbCamera *cam, const GrbClusterParameters *params,
                                   int32_t *out_tile, int32_t *out_z, GrbRows rows, void *stream);
 
+/* Work estimate of grb_deferred_lighting per group of 4 pixel rows (rows.y0 + 4 i ...), in warp
+ * instructions: the same cluster walk (clusterer_bindless.h:39-81) without shading.  The
+ * reference has no equivalent -- it never splits a frame; here the figure weighs the screen-row
+ * bands of a multi-GPU run.  cost_per_4_rows: device array of
+ * ceil(rows / 4) uint32, overwritten. */
+int32_t grb_lighting_row_cost(const GrbImage *depth, const GrbCamera *cam, const GrbClusterParameters *params,
+                              const GrbClusterBuffers *buf, GrbRows rows, uint32_t *cost_per_4_rows, void *stream);
+
 /* ---- HDR post chain: replaces the "bloom-compute" and "tonemap" passes
  * (renderer/post/hdr.cpp:308-400) ---- */
 /* K7 bloom_threshold.comp; hdr.cpp:115-144. luminance: device float[3] {avg_log, avg_lin,
@@ -192,6 +200,19 @@ int32_t grb_bloom_threshold(const GrbImage *hdr, const float *luminance, const G
  * image of the same size; lerp = 1 - 0.001^frame_time. */
 int32_t grb_bloom_downsample(const GrbImage *in, const GrbImage *history, float lerp,
                              const GrbImage *out, GrbRows rows, void *stream);
+/* K8 fused with the exchange a row-sharded frame needs after it: the band
+ * rows [rows.y0, rows.y1) of the 1/4-resolution level are stored into that image on EVERY rank --
+ * peer_images[r] is the base address, valid on this device, of rank r's image (cudaIpc-mapped
+ * peer memory over NVLink / NVSwitch; one entry is this rank's own image), all with out_layout's
+ * size and pitch -- and then flags[flag_index] = epoch is release-stored into every rank's flag
+ * array.  scratch_counter: one zero-initialised uint32 in local device memory.  No reference
+ * equivalent (the reference never splits a frame). */
+#define GRB_MAX_PEERS 8
+int32_t grb_bloom_downsample_to_peers(const GrbImage *in, const GrbImage *out_layout, void *const *peer_images,
+                                      uint32_t *const *peer_flags, int32_t peer_count, int32_t flag_index, uint32_t epoch,
+                                      uint32_t *scratch_counter, GrbRows rows, void *stream);
+/* Stream-ordered wait until local_flags[0..count) have all reached `epoch` (acquire, system scope). */
+int32_t grb_peer_wait(const uint32_t *local_flags, int32_t count, uint32_t epoch, void *stream);
 /* K9 bloom_upsample.comp; hdr.cpp:189-216. */
 int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream);
 /* K10 luminance.comp; hdr.cpp:68-98 (size = d3 / 2, lerp = 1 - 0.5^frame_time, clamp [-3,2]).

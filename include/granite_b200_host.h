@@ -90,6 +90,12 @@ int32_t grbh_nccl_unique_id(uint8_t out128[128]);
 int32_t grbh_viewer_init_collectives(GrbhViewer *viewer, const uint8_t id128[128], int32_t rank, int32_t world_size);
 int32_t grbh_viewer_set_row_shards(GrbhViewer *viewer, const GrbRows *bands, int32_t count, int32_t rank);
 
+/* Work estimate of the lighting pass per group of 4 backbuffer rows for the frame last rendered by
+ * an UNSHARDED viewer (its depth image and light cluster are resident): grb_lighting_row_cost() on
+ * the viewer's resources, copied to the host.  out: ceil(height / 4) values.  Feed the sums per
+ * band unit to a weighted partition to get bands of equal lighting work (granite_b200/viewer.py). */
+int32_t grbh_viewer_measure_row_cost(GrbhViewer *viewer, uint32_t *out, int32_t capacity);
+
 /* The row plan of one rank of a row-sharded frame (granite_b200/host/shard_plan.hpp): out8 =
  * {own, fxaa, tonemap, upsample0, downsample0, threshold, lighting, lum_grid}.  Pure host math. */
 int32_t grbh_shard_plan(int32_t width, int32_t height, const GrbRows *bands, int32_t count, int32_t rank, int32_t fxaa, GrbRows *out8);

@@ -84,6 +84,68 @@ def test_cluster_indices_bit_exact(cuda, oracle, w, h, n, spots):
     assert np.array_equal(out_z.cpu().numpy(), zi)
 
 
+@pytest.mark.parametrize("w,h,n,spots", [pytest.param(640, 360, 300, 0.25, id="small-300-25pct-spots"), pytest.param(322, 190, 100, 0.0, id="ragged-322x190")])
+def test_lighting_row_cost_is_the_cluster_walk(cuda, oracle, w, h, n, spots):
+    """grb_lighting_row_cost charges 700 + 45 words + 29 union lights + 89 lights in reach per 16x4
+    block; recomputed here from the oracle's cluster (indices, bitmask, ranges) in numpy."""
+    from granite_b200 import capi, harness
+
+    scene, cam, lights, prep = common.build_case(oracle, w, h, n, spots)
+    clus = oracle.cluster_build(cam, prep)
+    _, tile, zi, _ = oracle.deferred_lighting(scene, cam, prep, clus, want_indices=True)
+    dev, gcam = _cluster(cuda, oracle, cam, prep)
+    depth = harness.to_dev(scene.depth)
+    groups = (h + 3) // 4
+    out = torch.full((groups,), 12345, dtype=torch.int32, device="cuda")
+    img = capi.image(depth, capi.FORMAT_D32_SFLOAT)
+    capi.check(capi.lib().grb_lighting_row_cost(C.byref(img), C.byref(gcam), C.byref(dev.params), C.byref(dev.buffers), capi.rows(),
+                                                C.c_void_p(out.data_ptr()), capi.stream_ptr()), "grb_lighting_row_cost")
+    got = out.cpu().numpy().astype(np.int64)
+
+    # world positions in float64 (the radius test is the only non-integer step)
+    ivp = np.asarray(list(cam.inv_view_projection), np.float64).reshape(4, 4).T
+    ys, xs = np.mgrid[0:h, 0:w]
+    clip = np.stack([2 * (xs + 0.5) / w - 1, 2 * (ys + 0.5) / h - 1, scene.depth.astype(np.float64), np.ones((h, w))], -1) @ ivp.T
+    pos = clip[..., :3] / clip[..., 3:4]
+    lpos = prep.records["position"].astype(np.float64)
+    inv_r = prep.records["inv_radius"].astype(np.float64)
+    n32 = prep.n32
+    bitmask = clus.bitmask.reshape(-1, n32)
+    want = np.zeros(groups, np.int64)
+    borderline = 0
+    for g in range(groups):
+        for bx in range(0, w, 16):
+            sl = (slice(4 * g, min(4 * g + 4, h)), slice(bx, min(bx + 16, w)))
+            lit = scene.depth[sl] != 0
+            total = 700
+            if lit.any():
+                t, z, P = tile[sl][lit], zi[sl][lit], pos[sl][lit]
+                rx, ry = clus.range[z, 0].astype(np.int64), clus.range[z, 1].astype(np.int64)
+                lo, hi = int((rx >> 5).min()), min(int((ry >> 5).max()), n32 - 1)
+                for i in range(lo, hi + 1):
+                    total += 45
+                    first = np.clip(rx, 32 * i, 32 * i + 32) - 32 * i
+                    last = np.clip(np.maximum(ry + 1, rx), 32 * i, 32 * i + 32) - 32 * i  # exclusive
+                    own = bitmask[t, i].astype(np.int64)
+                    inrange = ((rx >> 5) <= i) & ((ry >> 5) >= i)
+                    rm = np.where(last - first >= 32, 0xFFFFFFFF, ((1 << np.maximum(last - first, 0)) - 1) << first)
+                    own = np.where(inrange, own & rm, 0)
+                    union = int(np.bitwise_or.reduce(own))
+                    for b in range(32):
+                        if not (union >> b) & 1:
+                            continue
+                        li = 32 * i + b
+                        d2 = ((P - lpos[li]) ** 2).sum(-1) * inv_r[li] ** 2
+                        has = ((own >> b) & 1) == 1
+                        near = has & (d2 < 1.0)
+                        borderline += int((has & (np.abs(d2 - 1.0) < 1e-5)).any())
+                        total += 29 + (89 if near.any() else 0)
+            want[g] += total
+    # a light whose radius passes within rounding of a pixel may be counted either way
+    assert np.abs(got - want).sum() <= 89 * borderline, (np.abs(got - want).sum(), borderline)
+    assert got.sum() > 700 * groups * ((w + 15) // 16)
+
+
 @pytest.mark.parametrize("w,h,n,spots", CONFIGS)
 def test_deferred_lighting_parity(cuda, oracle, w, h, n, spots):
     from granite_b200 import harness
