@@ -205,7 +205,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     lighting_b, chain_b, total_b = algorithmic_bytes(w, h, aa)
     config = {"workload": f"{args.workload}: {desc}", "width": w, "height": h, "lights": n_lights, "cluster_grid": "128x64x4096",
-              "sharding": f"{world} row bands of equal measured lighting work (8-row units)" if world > 1 else "none",
+              "sharding": f"{world} row bands (8-row units): balanced by measured lighting time for the resident region, equal rows for the end-to-end region" if world > 1 else "none",
               "l2": "per-frame inputs (182 MB G-buffer at 4K) exceed the 126 MB L2; no explicit flush",
               "algorithmic_mb_per_frame": round(total_b / 1e6, 2)}
 
@@ -238,7 +238,7 @@ def main():
     post = {"none": viewer.AA_NONE, "taa+fxaa": viewer.AA_TAA_HIGH_PLUS_FXAA}[aa]
     stream = torch.cuda.current_stream()
 
-    def make_viewer(timestamps, pipelined_io=False):
+    def make_viewer(timestamps, pipelined_io=False, use_bands=None):
         v = viewer.Viewer(w, h, post_aa=post, cuda_device=local_rank, timestamps=timestamps, stream=stream.cuda_stream, pipelined_io=pipelined_io)
         v.set_camera(scene.projection, scene.view)
         v.set_directional(scene.dir_color, scene.dir_direction)
@@ -251,7 +251,7 @@ def main():
                 uid.copy_(torch.frombuffer(bytearray(viewer.nccl_unique_id()), dtype=torch.uint8))
             dist.broadcast(uid, 0)
             v.init_collectives(bytes(uid.cpu().numpy().tobytes()), rank, world)
-            v.set_row_shards(bands, rank)
+            v.set_row_shards(use_bands if use_bands is not None else bands, rank)
         v.bake()
         return v
 
@@ -271,9 +271,40 @@ def main():
         cal.close()
         del full
         dist.broadcast(cost4, 0)
-        bands = viewer.band_partition_measured(h, w, world, cost4.cpu().numpy(), align=8)
+        cost4 = cost4.cpu().numpy()
+        bands = viewer.band_partition_measured(h, w, world, cost4, align=8)
+        # ... then a few steps of feedback: each rank times the band-dependent passes of its own
+        # band (lighting + the per-row post work), the cuts move towards equal time.  Per-band times
+        # of this pass are not additive (a narrow band of light-dense rows leaves SMs idle), which a
+        # work estimate alone cannot see.
+        cal_gb = viewer.Viewer.host_gbuffer(*[np.ascontiguousarray(a) for a in (scene.albedo, scene.normal, scene.pbr, scene.depth, scene.emissive)])
+        prior = np.repeat(cost4.astype(np.float64) / 4.0, 4)[:h] + 9.4 * w
+        history = []
+        for _ in range(6):
+            vt = make_viewer(True, use_bands=bands)
+            vt.render_frame(cal_gb)
+            for _ in range(4):
+                vt.render_frame(None)
+            vt.sync()
+            vt.collect_timings()
+            for _ in range(30):
+                vt.render_frame(None)
+            vt.sync()
+            tm = {k: ms / max(c, 1) for k, (ms, c) in vt.collect_timings().items()}
+            vt.close()
+            mine = torch.tensor([tm.get("lighting", 0.0) + 2.5 * tm.get("tonemap", 0.0)], dtype=torch.float64, device="cuda")
+            allt = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allt, mine)
+            times = [float(x.item()) for x in allt]
+            history.append((max(times), list(bands)))
+            bands = viewer.rebalance_bands(bands, times, h, align=8, damping=0.7, prior_per_row=prior)
+        bands = min(history, key=lambda e: e[0])[1]
+        e2e_bands = viewer.band_partition(h, world, align=8)  # uploads dominate end to end: equal rows
     else:
         bands = [(0, h)]
+        e2e_bands = bands
+    if world > 1:
+        config["resident_bands"] = [list(b) for b in bands]
     v = make_viewer(False)
     own = bands[rank]
     plan = viewer.shard_plan(w, h, bands if world > 1 else [], rank, aa == "taa+fxaa")
@@ -290,8 +321,10 @@ def main():
     host = [pin(scene.albedo), pin(scene.normal), pin(scene.pbr), pin(scene.depth), pin(scene.emissive)]
     gb = viewer.Viewer.host_gbuffer(*host, mv)
     out = torch.zeros((h, w), dtype=torch.int32).pin_memory()
-    h2d = (in_rows[1] - in_rows[0]) * w * (LIGHTING_BYTES_PER_PIXEL - 4 + (4 if mv is not None else 0))
-    d2h = (own[1] - own[0]) * w * 4
+    # bytes the whole job copies per step in the end-to-end region (all ranks)
+    e2e_plans = [viewer.shard_plan(w, h, e2e_bands if world > 1 else [], r, aa == "taa+fxaa") for r in range(world)]
+    h2d = sum((pl["lighting"][1] - pl["lighting"][0]) for pl in e2e_plans) * w * (LIGHTING_BYTES_PER_PIXEL - 4 + (4 if mv is not None else 0))
+    d2h = sum((pl["own"][1] - pl["own"][0]) for pl in e2e_plans) * w * 4
 
     def barrier():
         torch.cuda.synchronize()
@@ -335,7 +368,7 @@ def main():
     # upload of step i+1 and the readback of step i-1 overlap the compute of step i), so the wall
     # clock below is the sustained frame rate of the public API, PCIe included. ----
     v.close()
-    v = make_viewer(False, pipelined_io=True)
+    v = make_viewer(False, pipelined_io=True, use_bands=e2e_bands)
     outs = [out, torch.zeros((h, w), dtype=torch.int32).pin_memory()]
     for i in range(max(args.warmup // 2, 3)):
         v.render_frame(gb)
@@ -372,7 +405,7 @@ def main():
         vt.render_frame(None)
     vt.sync()
     timings = {k: ms / max(c, 1) for k, (ms, c) in vt.collect_timings().items()}
-    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 10 + (2 if world > 1 else 0), "tonemap": 1, "taa-resolve": 1, "fxaa": 1,
+    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 10 + (1 if world > 1 else 0), "tonemap": 1, "taa-resolve": 1, "fxaa": 1,
                 "gbuffer": 0, "mv": 0}
     launches_per_frame = sum(n_launch.get(p, 0) for p in vt.pass_names())
     vt.close()
@@ -390,7 +423,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_frame * args.steps,
         "hbm_gbs_whole_frame": total_b / (ms_resident / args.steps * 1e-3) / 1e9 / 1.0,
-        "roofline": {"kernel": "deferred_lighting_kernel (pass 'lighting')", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "deferred_lighting2_kernel (pass 'lighting')", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(), "peak_source": f"of {peak_kind}",
                      "bytes_per_pixel": LIGHTING_BYTES_PER_PIXEL, "note": "ALU-bound at this light density: see DESIGN.md"},
         "pass_ms": {k: round(val, 4) for k, val in timings.items()},

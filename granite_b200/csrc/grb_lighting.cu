@@ -393,18 +393,16 @@ __device__ __forceinline__ PixelSetup setup_pixel(const LightingParams &p, const
 	return q;
 }
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(const LightingParams p)
+// G-buffer fetch + per-pixel invariants for the pixel pair (x, x + 1) of row y.
+struct PairSetup
 {
-	__shared__ float s_srgb[256];
-	for (int i = threadIdx.x; i < 256; i += blockDim.x)
-		s_srgb[i] = g_srgb8_to_linear[i];
-	__syncthreads();
+	PixelSetup A, B;
+	Surface2 s;
+	int z_start, z_end; // the warp's range of 32-light words (empty when z_end < z_start)
+};
 
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int x = ((blockIdx.x * kWarpsPerCta + warp) * 8 + (lane & 7)) * 2; // pixels x and x + 1 (width is even on this path)
-	const int y = p.y0 + blockIdx.y * 4 + (lane >> 3);
-	const bool inside = x < p.hdr.w && y < p.y1;
-
+__device__ __forceinline__ void setup_pair(const LightingParams &p, const float *s_srgb, int x, int y, bool inside, PairSetup &q)
+{
 	float2 depth = make_float2(0.f, 0.f);
 	uint2 a8 = make_uint2(0u, 0u), n10 = make_uint2(0u, 0u), em = make_uint2(0u, 0u);
 	uint32_t mr2 = 0u;
@@ -417,10 +415,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 		mr2 = __ldg(reinterpret_cast<const uint32_t *>(&p.pbr.at(x, y)));
 		em = __ldg(reinterpret_cast<const uint2 *>(&p.emissive.at(x, y)));
 	}
-	PixelSetup A = setup_pixel(p, s_srgb, x, y, inside, depth.x, a8.x, n10.x, mr2 & 0xffffu, em.x);
-	PixelSetup B = setup_pixel(p, s_srgb, x + 1, y, inside, depth.y, a8.y, n10.y, mr2 >> 16, em.y);
-
-	Surface2 s;
+	q.A = setup_pixel(p, s_srgb, x, y, inside, depth.x, a8.x, n10.x, mr2 & 0xffffu, em.x);
+	q.B = setup_pixel(p, s_srgb, x + 1, y, inside, depth.y, a8.y, n10.y, mr2 >> 16, em.y);
+	const PixelSetup &A = q.A, &B = q.B;
+	Surface2 &s = q.s;
 	s.npx = make_float2(-A.pos.x, -B.pos.x); s.npy = make_float2(-A.pos.y, -B.pos.y); s.npz = make_float2(-A.pos.z, -B.pos.z);
 	s.Nx = make_float2(A.N.x, B.N.x); s.Ny = make_float2(A.N.y, B.N.y); s.Nz = make_float2(A.N.z, B.N.z);
 	s.Vx = make_float2(A.V.x, B.V.x); s.Vy = make_float2(A.V.y, B.V.y); s.Vz = make_float2(A.V.z, B.V.z);
@@ -431,34 +429,21 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 	s.m2m1 = make_float2(A.m2m1, B.m2m1); s.cgd = make_float2(A.cgd, B.cgd);
 	s.omk = make_float2(A.omk, B.omk); s.k = make_float2(A.k, B.k); s.Vk = make_float2(A.Vk, B.Vk);
 	s.NoVr = make_float2(A.NoVr, B.NoVr);
+	const uint32_t loA = A.rx >> 5, hiA = A.ry >> 5, loB = B.rx >> 5, hiB = B.ry >> 5; // unlit: (0x7ffffff, 0) => empty
+	q.z_start = (int)__reduce_min_sync(0xffffffffu, min(loA, loB));
+	q.z_end = min((int)__reduce_max_sync(0xffffffffu, max(A.lit ? hiA : 0u, B.lit ? hiB : 0u)), p.n32 - 1);
+}
 
-	// ---- draw 1: directional light for both pixels ----
-	uint32_t dstA = A.dst, dstB = B.dst;
-	{
-		f2 NoL, tx, ty, tz;
-		const f2 dx = mk2(p.dir_dir.x), dy = mk2(p.dir_dir.y), dz = mk2(p.dir_dir.z);
-		brdf2(s, dot3_2(s.Nx, s.Ny, s.Nz, dx, dy, dz), dot3_2(s.Vx, s.Vy, s.Vz, dx, dy, dz), NoL, tx, ty, tz);
-		if (A.lit)
-		{
-			float3 e = unpack_r11g11b10(dstA);
-			dstA = pack_r11g11b10(e.x + p.dir_color.x * NoL.x * tx.x + A.base_color.x * 0.05f, e.y + p.dir_color.y * NoL.x * ty.x + A.base_color.y * 0.05f,
-			                      e.z + p.dir_color.z * NoL.x * tz.x + A.base_color.z * 0.05f);
-		}
-		if (B.lit)
-		{
-			float3 e = unpack_r11g11b10(dstB);
-			dstB = pack_r11g11b10(e.x + p.dir_color.x * NoL.y * tx.y + B.base_color.x * 0.05f, e.y + p.dir_color.y * NoL.y * ty.y + B.base_color.y * 0.05f,
-			                      e.z + p.dir_color.z * NoL.y * tz.y + B.base_color.z * 0.05f);
-		}
-	}
-
-	// ---- draw 2: warp-uniform walk over the union of all 64 pixels' masks ----
+// draw 2 (clustering.frag): warp-uniform walk over the union of all 64 pixels' masks, words
+// first, first + step, ... <= q.z_end; adds the lights' contribution to (accx, accy, accz).
+__device__ __forceinline__ void walk_lights(const LightingParams &p, const PairSetup &q, int first, int step, float4 (*staged)[32], f2 &accx, f2 &accy,
+                                            f2 &accz)
+{
+	const int lane = threadIdx.x & 31;
+	const PixelSetup &A = q.A, &B = q.B;
+	const Surface2 &s = q.s;
 	const uint32_t loA = A.rx >> 5, hiA = A.ry >> 5, loB = B.rx >> 5, hiB = B.ry >> 5;
-	int z_start = (int)__reduce_min_sync(0xffffffffu, min(loA, loB));
-	int z_end = (int)__reduce_max_sync(0xffffffffu, max(A.lit ? hiA : 0u, B.lit ? hiB : 0u));
-	z_end = min(z_end, p.n32 - 1);
-	f2 accx = mk2(0.0f), accy = mk2(0.0f), accz = mk2(0.0f);
-	for (int i = z_start; i <= z_end; i++)
+	for (int i = first; i <= q.z_end; i += step)
 	{
 		uint32_t ownA = 0u, ownB = 0u;
 		if (A.lit && (uint32_t)i >= loA && (uint32_t)i <= hiA)
@@ -466,13 +451,26 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 		if (B.lit && (uint32_t)i >= loB && (uint32_t)i <= hiB)
 			ownB = cluster_mask_range(__ldg(&p.bitmask[B.cluster_base + i]), B.rx, B.ry, 32u * (uint32_t)i);
 		uint32_t wmask = __reduce_or_sync(0xffffffffu, ownA | ownB);
+		if (!wmask)
+			continue;
 		const uint32_t tm = __ldg(&p.type_mask[i]);
+		// Stage the word's records in shared memory, lane b fetching light 32 i + b: one parallel trip
+		// to L1/L2 per word.  Reading each record with a broadcast load right before its first use
+		// (one dependent trip per light) was the largest stall in light-dense regions.
+		__syncwarp();
+		if ((wmask >> lane) & 1u)
+		{
+			const float4 *mine = reinterpret_cast<const float4 *>(p.lights + (i * 32 + lane));
+			staged[0][lane] = __ldg(mine);
+			staged[1][lane] = __ldg(mine + 1);
+			staged[2][lane] = __ldg(mine + 2);
+		}
+		__syncwarp();
 		while (wmask)
 		{
 			const int bit = __ffs(wmask) - 1;
 			wmask &= wmask - 1u;
-			const float4 *lp = reinterpret_cast<const float4 *>(p.lights + (i * 32 + bit));
-			const float4 l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+			const float4 l1 = staged[1][bit], l2 = staged[2][bit]; // position|offset_radius, direction|inv_radius
 			f2 lx = add2(mk2(l1.x), s.npx), ly = add2(mk2(l1.y), s.npy), lz = add2(mk2(l1.z), s.npz);
 			f2 d2 = dot3_2(lx, ly, lz, lx, ly, lz);
 			const float inv_r2 = l2.w * l2.w;
@@ -481,9 +479,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 			// quick reject: beyond the light's radius the falloff is exactly 0 (point.h:41-43)
 			if (!__any_sync(0xffffffffu, nearA || nearB))
 				continue;
-			// (requesting the next light's record ahead of this evaluation was tried: it needs 8 more
-			// registers, and at 4 CTAs per SM, or squeezed back into 96, the frame got slower)
-			const float4 l0 = __ldg(lp);
+			const float4 l0 = staged[0][bit]; // color|spot scale_bias
 			f2 inv_d = rsqrt2(d2);
 			f2 inv_ld = make_float2(fminf(inv_d.x, 10.0f), fminf(inv_d.y, 10.0f));
 			f2 dist = mul2(d2, inv_d);
@@ -512,6 +508,52 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting2_kernel(c
 			accz = fma2(mul2(mk2(l0.z), w), tz, accz);
 		}
 	}
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 5) deferred_lighting2_kernel(const LightingParams p)
+{
+	__shared__ float s_srgb[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x)
+		s_srgb[i] = g_srgb8_to_linear[i];
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int x = ((blockIdx.x * kWarpsPerCta + warp) * 8 + (lane & 7)) * 2; // pixels x and x + 1 (width is even on this path)
+	const int y = p.y0 + blockIdx.y * 4 + (lane >> 3);
+	const bool inside = x < p.hdr.w && y < p.y1;
+
+	__shared__ float4 s_lights[kWarpsPerCta][3][32];
+	PairSetup q;
+	setup_pair(p, s_srgb, x, y, inside, q);
+	const PixelSetup &A = q.A, &B = q.B;
+
+	// ---- draw 1: directional light for both pixels ----
+	uint32_t dstA = A.dst, dstB = B.dst;
+	{
+		const Surface2 &s = q.s;
+		f2 NoL, tx, ty, tz;
+		const f2 dx = mk2(p.dir_dir.x), dy = mk2(p.dir_dir.y), dz = mk2(p.dir_dir.z);
+		brdf2(s, dot3_2(s.Nx, s.Ny, s.Nz, dx, dy, dz), dot3_2(s.Vx, s.Vy, s.Vz, dx, dy, dz), NoL, tx, ty, tz);
+		if (A.lit)
+		{
+			float3 e = unpack_r11g11b10(dstA);
+			dstA = pack_r11g11b10(e.x + p.dir_color.x * NoL.x * tx.x + A.base_color.x * 0.05f, e.y + p.dir_color.y * NoL.x * ty.x + A.base_color.y * 0.05f,
+			                      e.z + p.dir_color.z * NoL.x * tz.x + A.base_color.z * 0.05f);
+		}
+		if (B.lit)
+		{
+			float3 e = unpack_r11g11b10(dstB);
+			dstB = pack_r11g11b10(e.x + p.dir_color.x * NoL.y * tx.y + B.base_color.x * 0.05f, e.y + p.dir_color.y * NoL.y * ty.y + B.base_color.y * 0.05f,
+			                      e.z + p.dir_color.z * NoL.y * tz.y + B.base_color.z * 0.05f);
+		}
+	}
+
+	// ---- draw 2 ----
+	// (Handing the light-dense blocks -- hundreds of lights per pixel, one warp busy for ~100 us --
+	// to a second kernel that spreads a block's lights over four warps was tried: bit-compatible,
+	// but the frame got 9 % slower, because the dense blocks then no longer overlap the cheap ones.)
+	f2 accx = mk2(0.0f), accy = mk2(0.0f), accz = mk2(0.0f);
+	walk_lights(p, q, q.z_start, 1, s_lights[warp], accx, accy, accz);
 	const float3 accA = make_float3(accx.x, accy.x, accz.x), accB = make_float3(accx.y, accy.y, accz.y);
 
 	if (inside)

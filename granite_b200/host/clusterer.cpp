@@ -276,7 +276,10 @@ void LightClusterer::build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd)
 	const unsigned slot = staging_slot;
 	staging_slot ^= 1u;
 	if (staging_event_pending[slot])
+	{
+		Vulkan::ScopedHostTimer timer("(flow control: wait for staging slot)");
 		cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(staging_events[slot]));
+	}
 	auto *s = static_cast<uint8_t *>(staging) + slot * slot_size;
 	std::memcpy(s, lights.data(), lights_bytes);
 	std::memcpy(s + lights_bytes, model.data(), model_bytes);

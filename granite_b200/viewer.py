@@ -179,6 +179,41 @@ def band_partition_measured(height: int, width: int, world: int, cost_per_4_rows
     return band_partition_weighted(height, world, c, align=align)
 
 
+def rebalance_bands(bands, band_times, height: int, align: int = 8, damping: float = 0.7, prior_per_row=None):
+    """One step of feedback load balancing for row bands: `band_times[r]` is what rank r needed for
+    the band-dependent part of its last frames (e.g. the lighting pass, GPU-timed).  The time is
+    taken as uniformly spread over the band's rows -- or along `prior_per_row` (e.g. the measured
+    work estimate) within the band -- and the cuts are moved towards equal time, damped, in units
+    of `align` rows, keeping at least one unit per rank.  Iterate a few times: the per-band times of
+    this pass are not additive over rows (a band that leaves SMs idle is slower than its share)."""
+    world = len(bands)
+    t = np.asarray(band_times, np.float64)
+    assert len(t) == world and world >= 1
+    n_units = (height + align - 1) // align
+    density = np.zeros(n_units)
+    for (y0, y1), tr in zip(bands, t):
+        u0, u1 = y0 // align, (y1 + align - 1) // align
+        if prior_per_row is not None:
+            w = np.add.reduceat(np.asarray(prior_per_row, np.float64)[y0:y1], np.arange(0, y1 - y0, align)) + 1e-9
+        else:
+            w = np.ones(u1 - u0)
+        density[u0:u1] = tr * w / w.sum()
+    target = band_partition_weighted(height, world, density, align=align)
+    out = []
+    prev = 0
+    for r in range(world):
+        if r == world - 1:
+            y1 = height
+        else:
+            want = bands[r][1] + damping * (target[r][1] - bands[r][1])
+            y1 = int(round(want / align)) * align
+            y1 = max(y1, prev + align)
+            y1 = min(y1, height - (world - 1 - r) * align)
+        out.append((prev, y1))
+        prev = y1
+    return out
+
+
 PLAN_FIELDS = ("own", "fxaa", "tonemap", "upsample0", "downsample0", "threshold", "lighting", "lum_grid")
 
 

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--equal-bands", action="store_true")
+    ap.add_argument("--bands", default="", help="explicit cuts, e.g. 792,944,1040 for 4 ranks")
+    ap.add_argument("--show", default="", help="ranks to print (default all), e.g. 0,4")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -43,7 +45,11 @@ def main():
     v.set_lights(lights)
     bands = [(0, h)]
     if world > 1:
-        if args.equal_bands:
+        if args.bands:
+            cuts = [0] + [int(x) for x in args.bands.split(",")] + [h]
+            bands = list(zip(cuts[:-1], cuts[1:]))
+            assert len(bands) == world
+        elif args.equal_bands:
             bands = viewer.band_partition(h, world)
         else:
             cost = viewer.estimate_band_cost(scene.projection, scene.view, lights.position, lights.color, w, h, depth=scene.depth, align=8)
@@ -70,7 +76,7 @@ def main():
     for r in range(world):
         if world > 1:
             dist.barrier()
-        if r != rank:
+        if r != rank or (args.show and str(rank) not in args.show.split(",")):
             continue
         print(f"--- rank {rank} of {world}, rows {bands[rank] if world > 1 else (0, h)}")
         for name, b, e in tl:
