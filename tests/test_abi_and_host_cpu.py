@@ -169,3 +169,42 @@ def test_band_partition():
     assert b8[0] == (0, 256) and b8[-1] == (1792, 2160) and all(a[1] == b[0] for a, b in zip(b8, b8[1:]))
     with pytest.raises(ValueError):
         viewer.band_partition(256, 8)
+
+
+def test_measured_and_feedback_band_partitions():
+    """band_partition_measured / rebalance_bands: valid tilings in 8-row units, one unit per rank at
+    least, and the feedback step converges on a synthetic cost peaked like the bench scene's
+    (a few dozen very expensive rows)."""
+    from granite_b200 import viewer
+
+    h, w = 2160, 3840
+    rows = np.arange(h)
+    per_row = 1.0 + 60.0 * np.exp(-(((rows - 1130) / 25.0) ** 2))
+
+    def check(bands, world):
+        assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == h
+        assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        assert all((b[1] - b[0]) >= 8 and b[0] % 8 == 0 for b in bands)
+
+    cost4 = (per_row.reshape(-1, 4).sum(axis=1) * 1e4).astype(np.uint32)
+    for world in (2, 4, 8):
+        bands = viewer.band_partition_measured(h, w, world, cost4, align=8, post_warp_inst_per_pixel=0.0)
+        check(bands, world)
+        work = [per_row[a:b].sum() for a, b in bands]
+        assert max(work) < 1.6 * per_row.sum() / world  # equal work up to the 8-row granularity at the peak
+        # the thin bands sit on the expensive rows
+        assert min(b[1] - b[0] for b in bands) < h // world
+
+        # feedback from "measured times" that are NOT the work: a band never beats a latency floor
+        def times(bs):
+            return [max(per_row[a:b].sum(), 0.12 * per_row.sum()) if per_row[a:b].max() > 30 else per_row[a:b].sum() for a, b in bs]
+
+        cur = viewer.band_partition(h, world, align=8)
+        first = max(times(cur))
+        best = first
+        for _ in range(8):
+            cur = viewer.rebalance_bands(cur, times(cur), h, align=8, prior_per_row=per_row)
+            check(cur, world)
+            best = min(best, max(times(cur)))
+        assert best <= first
+    assert viewer.rebalance_bands([(0, h)], [1.0], h) == [(0, h)]
