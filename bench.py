@@ -27,16 +27,20 @@ import numpy as np
 
 WORKLOADS = {
     # name: (width, height, lights, post_aa, description)
+    "c1": (256, 256, 16, "none", "256x256 G-buffer, 16 point lights + directional, tonemap only (no bloom, fixed exposure): the reference's smallest case"),
     "c3": (3840, 2160, 4096, "none", "3840x2160 G-buffer, 4096 clustered point lights + directional, bloom + luminance + tonemap"),
     "c2": (1920, 1080, 1024, "none", "1920x1080 G-buffer, 1024 clustered lights, full bloom/tonemap chain"),
     "c5": (3840, 2160, 4096, "taa+fxaa", "3840x2160 TAA(q2) + FXAA post-AA with history buffer"),
 }
+NO_BLOOM = {"c1"}  # BASELINE config 1: DYNAMIC_EXPOSURE=0, bloom disabled
 LIGHTING_BYTES_PER_PIXEL = 22  # 4 albedo + 4 normal + 2 pbr + 4 depth + 4 emissive read, 4 HDR write
 
 
-def algorithmic_bytes(w, h, aa):
+def algorithmic_bytes(w, h, aa, bloom=True):
     """Compulsory HBM traffic per frame, unfused pass-by-pass accounting of SURVEY.md §8d."""
     px = w * h
+    if not bloom:
+        return px * LIGHTING_BYTES_PER_PIXEL, px * 8, px * (LIGHTING_BYTES_PER_PIXEL + 8)
     sz = [(math.ceil(w * s), math.ceil(h * s)) for s in (0.5, 0.25, 0.125, 0.0625, 0.03125)]
     t, d0, d1, d2, d3 = [a * b for a, b in sz]
     lighting = px * LIGHTING_BYTES_PER_PIXEL
@@ -121,7 +125,7 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------------
-def oracle_frame_time(w, h, n_lights, aa, steps, warmup, budget_s=150.0):
+def oracle_frame_time(w, h, n_lights, aa, steps, warmup, budget_s=150.0, bloom=True):
     """Times the CPU oracle (the reference's algorithm restated in C, OpenMP over rows) on a bounded
     sample of the frame: the cluster build and the pyramid tail in full, the per-pixel passes on a
     band of rows, scaled to the whole frame."""
@@ -144,6 +148,11 @@ def oracle_frame_time(w, h, n_lights, aa, steps, warmup, budget_s=150.0):
         hdr = oracle.deferred_lighting(scene, cam, prep, clus, rows=(0, rows))
         t2 = time.perf_counter()
         hs = hdr[:rows]
+        if not bloom:
+            zero = np.zeros((-(-rows // 4), -(-w // 4), 4), np.uint16)
+            oracle.tonemap(hs, zero, None, 1.0)
+            t3 = time.perf_counter()
+            return (t3 - t1), (t1 - t0), 0.0
         psz = oracle.pyramid_sizes(w, rows)
         t = oracle.bloom_threshold(hs, np.zeros(3, np.float32), psz[0])
         d0 = oracle.bloom_downsample(t, psz[1])
@@ -173,8 +182,8 @@ def oracle_frame_time(w, h, n_lights, aa, steps, warmup, budget_s=150.0):
         return band, fixed, extra
 
     # calibrate on one 64-row band, then pick the largest band that fits the budget
-    band, fixed, _ = frame(64)
-    est_full = band * (h / 64.0) + fixed
+    band, fixed, _ = frame(min(64, h))
+    est_full = band * (h / float(min(64, h))) + fixed
     frac = min(1.0, budget_s / max(est_full * (steps + warmup), 1e-9))
     rows = int(max(64, min(h, (int(h * frac) // 64) * 64)))
     for _ in range(warmup):
@@ -203,17 +212,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    lighting_b, chain_b, total_b = algorithmic_bytes(w, h, aa)
+    bloom = args.workload not in NO_BLOOM
+    lighting_b, chain_b, total_b = algorithmic_bytes(w, h, aa, bloom)
     config = {"workload": f"{args.workload}: {desc}", "width": w, "height": h, "lights": n_lights, "cluster_grid": "128x64x4096",
               "sharding": f"{world} row bands (8-row units): balanced by measured lighting time for the resident region, equal rows for the end-to-end region" if world > 1 else "none",
-              "l2": "per-frame inputs (182 MB G-buffer at 4K) exceed the 126 MB L2; no explicit flush",
+              "l2": (f"per-frame inputs ({w * h * LIGHTING_BYTES_PER_PIXEL / 1e6:.0f} MB of G-buffer + HDR) exceed the 126 MB L2; no explicit flush"
+                     if w * h * LIGHTING_BYTES_PER_PIXEL > 126e6 else
+                     f"per-frame inputs ({w * h * LIGHTING_BYTES_PER_PIXEL / 1e6:.1f} MB) fit in the 126 MB L2 and are not flushed: not a headline configuration"),
               "algorithmic_mb_per_frame": round(total_b / 1e6, 2)}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         steps = min(args.steps, 5)  # each CPU step is seconds long; bounded so the run stays within minutes
-        sec, cores, sample = oracle_frame_time(w, h, n_lights, aa, steps, min(args.warmup, 1))
+        sec, cores, sample = oracle_frame_time(w, h, n_lights, aa, steps, min(args.warmup, 1), bloom=bloom)
         fps = 1.0 / sec
         line = {"impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
                 "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
@@ -239,7 +251,8 @@ def main():
     stream = torch.cuda.current_stream()
 
     def make_viewer(timestamps, pipelined_io=False, use_bands=None):
-        v = viewer.Viewer(w, h, post_aa=post, cuda_device=local_rank, timestamps=timestamps, stream=stream.cuda_stream, pipelined_io=pipelined_io)
+        v = viewer.Viewer(w, h, post_aa=post, hdr_bloom=bloom, dynamic_exposure=bloom, cuda_device=local_rank, timestamps=timestamps,
+                          stream=stream.cuda_stream, pipelined_io=pipelined_io)
         v.set_camera(scene.projection, scene.view)
         v.set_directional(scene.dir_color, scene.dir_direction)
         v.set_lights(lights)
@@ -405,7 +418,7 @@ def main():
         vt.render_frame(None)
     vt.sync()
     timings = {k: ms / max(c, 1) for k, (ms, c) in vt.collect_timings().items()}
-    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 10 + (1 if world > 1 else 0), "tonemap": 1, "taa-resolve": 1, "fxaa": 1,
+    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 10 + (1 if world > 1 else 0), "tonemap": 1, "bloom-disabled": 0, "taa-resolve": 1, "fxaa": 1,
                 "gbuffer": 0, "mv": 0}
     launches_per_frame = sum(n_launch.get(p, 0) for p in vt.pass_names())
     vt.close()
@@ -430,7 +443,7 @@ def main():
         "host_record_ms_per_step": round(host_ms / args.steps, 4),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores, sample = oracle_frame_time(w, h, n_lights, aa, steps=1, warmup=0, budget_s=25.0)
+        sec, cores, sample = oracle_frame_time(w, h, n_lights, aa, steps=1, warmup=0, budget_s=25.0, bloom=bloom)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
         print(json.dumps(line))
