@@ -405,17 +405,14 @@ class Viewer:
         nm = [x for x in names.value.decode().split("\n") if x]
         return {nm[i]: (ms[i], cnt[i]) for i in range(min(n, len(nm)))}
 
-
-def _timeline(self, capacity=4096):
-    names = C.create_string_buffer(64 * capacity)
-    b = (C.c_float * capacity)()
-    e = (C.c_float * capacity)()
-    n = _check(lib().grbh_viewer_collect_timeline(self._h, names, 64 * capacity, b, e, capacity), "grbh_viewer_collect_timeline")
-    nm = [x for x in names.value.decode().split("\n") if x]
-    return [(nm[i], b[i], e[i]) for i in range(min(n, len(nm), capacity))]
-
-
-Viewer.collect_timeline = _timeline
+    def collect_timeline(self, capacity=4096):
+        """[(pass name, begin ms, end ms)] relative to the first recorded pass (viewer created with timestamps=2)."""
+        names = C.create_string_buffer(64 * capacity)
+        b = (C.c_float * capacity)()
+        e = (C.c_float * capacity)()
+        n = _check(lib().grbh_viewer_collect_timeline(self._h, names, 64 * capacity, b, e, capacity), "grbh_viewer_collect_timeline")
+        nm = [x for x in names.value.decode().split("\n") if x]
+        return [(nm[i], b[i], e[i]) for i in range(min(n, len(nm), capacity))]
 
 
 def nccl_unique_id() -> bytes:
