@@ -129,6 +129,11 @@ def test_two_rank_gloo_frame_equals_single_rank(oracle, fxaa):
 def _bands_for(world, weighted):
     from granite_b200 import synth, viewer
 
+    if weighted == "thin":
+        # what the feedback balancer produces around light-dense rows: bands of one or two 8-row units
+        cuts = [0, H // 2 - 24, H // 2 - 16, H // 2 - 8, H // 2 + 8, H // 2 + 16, H][: world] + [H]
+        cuts = sorted(set(c - c % 8 for c in cuts[:-1])) + [H]
+        return list(zip(cuts[:-1], cuts[1:]))
     if not weighted:
         return viewer.band_partition(H, world)
     # cost-balanced bands in 8-row units, as bench.py builds them for N > 1
@@ -138,7 +143,7 @@ def _bands_for(world, weighted):
     return viewer.band_partition_weighted(H, world, cost, align=8)
 
 
-@pytest.mark.parametrize("world,weighted", [(3, False), (6, False), (4, True), (8, True)])
+@pytest.mark.parametrize("world,weighted", [(3, False), (6, False), (4, True), (8, True), (6, "thin")])
 def test_emulated_many_ranks(oracle, world, weighted):
     """Same protocol with the collectives emulated in-process (every band count the frame allows)."""
     from granite_b200 import viewer
@@ -147,6 +152,7 @@ def test_emulated_many_ranks(oracle, world, weighted):
     scene, cam, lights, prep = common.build_case(oracle, W, H, N_LIGHTS, 0.25)
     _, _, _, f, _ = _reference_frame(oracle, scene, cam, prep)
     bands = _bands_for(world, weighted)
+    assert len(bands) == world
     assert bands[0][0] == 0 and bands[-1][1] == H and all(a[1] == b[0] and a[1] % 8 == 0 for a, b in zip(bands, bands[1:]))
     # three passes emulate the two exchange steps: (0) collect every rank's d0 band, (1) with the
     # gathered d0, collect every rank's luminance-grid rows, (2) the real frame
