@@ -376,6 +376,23 @@ def main():
     barrier()
     ms_resident = max_over_ranks(e0.elapsed_time(e1))
 
+    # frame-period distribution (outside the timed region above): one marker per frame on the main
+    # stream, i.e. after that frame's lighting; reported for rank 0 only, informational
+    n_mark = min(args.steps, 100)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_mark + 1)]
+    marks[0].record(stream)
+    for i in range(n_mark):
+        v.render_frame(None)
+        marks[i + 1].record(stream)
+    v.join_streams()
+    barrier()
+    try:
+        periods = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(n_mark))
+        frame_stats = {"p10": round(periods[n_mark // 10], 4), "p50": round(periods[n_mark // 2], 4), "p90": round(periods[(n_mark * 9) // 10], 4),
+                       "frames": n_mark}
+    except Exception as exc:  # never let the extra statistic cost the run
+        frame_stats = {"error": str(exc)[:80]}
+
     # ---- timed region 2: end to end through the host API.  Every step copies its G-buffer rows from
     # pinned host memory to the device and its result rows back; frames are pipelined two deep (the
     # upload of step i+1 and the readback of step i-1 overlap the compute of step i), so the wall
@@ -441,6 +458,7 @@ def main():
                      "bytes_per_pixel": LIGHTING_BYTES_PER_PIXEL, "note": "ALU-bound at this light density: see DESIGN.md"},
         "pass_ms": {k: round(val, 4) for k, val in timings.items()},
         "host_record_ms_per_step": round(host_ms / args.steps, 4),
+        "frame_period_ms": frame_stats,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cores, sample = oracle_frame_time(w, h, n_lights, aa, steps=1, warmup=0, budget_s=25.0, bloom=bloom)
