@@ -267,7 +267,7 @@ void LightClusterer::build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd)
 		for (auto &e : staging_events)
 		{
 			cudaEvent_t ev;
-			cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+			Vulkan::cuda_ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate(staging)");
 			e = ev;
 		}
 	}
@@ -287,8 +287,9 @@ void LightClusterer::build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd)
 	std::memcpy(s + lights_bytes + model_bytes + mask_bytes, volume_index_range.data(), range_bytes);
 
 	// the staging slot already has the packed device layout: one H2D copy
-	cudaMemcpyAsync(transforms_buffer->get_device_pointer(), s, need, cudaMemcpyHostToDevice, stream);
-	cudaEventRecord(reinterpret_cast<cudaEvent_t>(staging_events[slot]), stream);
+	if (!Vulkan::cuda_ok(cudaMemcpyAsync(transforms_buffer->get_device_pointer(), s, need, cudaMemcpyHostToDevice, stream), "light upload"))
+		return;
+	Vulkan::cuda_ok(cudaEventRecord(reinterpret_cast<cudaEvent_t>(staging_events[slot]), stream), "cudaEventRecord(staging)");
 	staging_event_pending[slot] = true;
 
 	const auto &rp = context->get_render_parameters();

@@ -159,11 +159,11 @@ void Device::join_side_streams()
 		if (!join_events[i])
 		{
 			cudaEvent_t e;
-			cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+			cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate(join)");
 			join_events[i] = e;
 		}
-		cudaEventRecord(join_events[i], side_streams[i]);
-		cudaStreamWaitEvent(stream, join_events[i], 0);
+		cuda_ok(cudaEventRecord(join_events[i], side_streams[i]), "cudaEventRecord(join)");
+		cuda_ok(cudaStreamWaitEvent(stream, join_events[i], 0), "cudaStreamWaitEvent(join)");
 	}
 }
 

@@ -96,7 +96,8 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 			// reassembles the grid exactly, then every rank reduces it in the shader's order
 			float *grid = graph.get_physical_buffer_resource(*r.lum_grid).get<float>();
 			const int size_x = d3.width / 2, size_y = d3.height / 2;
-			cudaMemsetAsync(grid, 0, sizeof(float) * size_x * size_y, reinterpret_cast<cudaStream_t>(cmd.get_stream()));
+			Vulkan::cuda_ok(cudaMemsetAsync(grid, 0, sizeof(float) * size_x * size_y, reinterpret_cast<cudaStream_t>(cmd.get_stream())),
+			                "cudaMemsetAsync(luminance grid)");
 			GrbRows grid_rows = plan.lum_grid;
 			if (grid_rows.y1 > grid_rows.y0)
 				cmd.check(grb_luminance_grid(&d3, grid, grid_rows, stream), "grb_luminance_grid");
