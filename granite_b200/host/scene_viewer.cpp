@@ -440,6 +440,9 @@ extern "C" int32_t grbh_viewer_init_collectives(GrbhViewer *v, const uint8_t id1
 {
 	if (!v || !id128 || rank < 0 || world_size <= 0 || rank >= world_size)
 		return fail("grbh_viewer_init_collectives: bad arguments");
+	if (!v->device)
+		return fail("grbh_viewer_init_collectives: host-only viewer (cuda_device < 0) has no device to communicate from");
+	GRBH_TRY
 	cudaSetDevice(v->device->get_device_index());
 	auto c = std::make_unique<NcclCollectives>();
 	std::string err;
@@ -447,28 +450,33 @@ extern "C" int32_t grbh_viewer_init_collectives(GrbhViewer *v, const uint8_t id1
 		return fail(err);
 	v->collectives = std::move(c);
 	return 0;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_viewer_set_row_shards(GrbhViewer *v, const GrbRows *bands, int32_t count, int32_t rank)
 {
 	if (!v || count < 0 || (count && !bands) || (count && (rank < 0 || rank >= count)))
 		return fail("grbh_viewer_set_row_shards: bad arguments");
+	GRBH_TRY
 	v->bands.assign(bands, bands + count);
 	v->rank = (unsigned)rank;
 	v->baked = false;
 	return 0;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_shard_plan(int32_t width, int32_t height, const GrbRows *bands, int32_t count, int32_t rank, int32_t fxaa, GrbRows *out9)
 {
 	if (width <= 0 || height <= 0 || count < 0 || (count && !bands) || !out9 || (count && (rank < 0 || rank >= count)))
 		return fail("grbh_shard_plan: bad arguments");
+	GRBH_TRY
 	std::vector<GrbRows> b(bands, bands + count);
 	ShardPlan p = compute_shard_plan((unsigned)width, (unsigned)height, b, (unsigned)rank, fxaa != 0);
 	const GrbRows all[8] = { p.own, p.fxaa, p.tonemap, p.upsample0, p.downsample0, p.threshold, p.lighting, p.lum_grid };
 	for (int i = 0; i < 8; i++)
 		out9[i] = all[i];
 	return 0;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_viewer_bake(GrbhViewer *v)
@@ -556,6 +564,7 @@ extern "C" int32_t grbh_viewer_wait_outputs(GrbhViewer *v, int32_t max_pending)
 {
 	if (!v || max_pending < 0)
 		return fail("grbh_viewer_wait_outputs: bad arguments");
+	GRBH_TRY
 	while ((int32_t)v->pending_outputs.size() > max_pending)
 	{
 		cudaEvent_t e = v->pending_outputs.front();
@@ -565,12 +574,14 @@ extern "C" int32_t grbh_viewer_wait_outputs(GrbhViewer *v, int32_t max_pending)
 		v->free_output_events.push_back(e);
 	}
 	return 0;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_viewer_collect_timeline(GrbhViewer *v, char *names, int32_t names_capacity, float *begin_ms, float *end_ms, int32_t capacity)
 {
 	if (!v || !v->device)
 		return fail("null viewer");
+	GRBH_TRY
 	auto tl = v->device->collect_timeline();
 	std::string all;
 	int i = 0;
@@ -589,6 +600,7 @@ extern "C" int32_t grbh_viewer_collect_timeline(GrbhViewer *v, char *names, int3
 	if (names && names_capacity > 0)
 		std::snprintf(names, (size_t)names_capacity, "%s", all.c_str());
 	return i;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_viewer_join_streams(GrbhViewer *v)
@@ -729,12 +741,14 @@ extern "C" int32_t grbh_viewer_get_pass_names(GrbhViewer *v, char *buffer, int32
 {
 	if (!v || !v->baked)
 		return fail("viewer not baked");
+	GRBH_TRY
 	std::string all;
 	for (auto &n : v->graph.get_baked_pass_names())
 		all += n + "\n";
 	if (buffer && capacity > 0)
 		std::snprintf(buffer, (size_t)capacity, "%s", all.c_str());
 	return (int32_t)all.size() + 1;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_viewer_collect_timings(GrbhViewer *v, char *names, int32_t names_capacity, float *total_ms, int32_t *counts, int32_t capacity)
