@@ -23,7 +23,10 @@
 // differences.
 #include "grb_common.cuh"
 
+#include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 namespace grb
 {
@@ -89,16 +92,17 @@ __device__ __forceinline__ uint32_t cluster_mask_range(uint32_t mask, uint32_t r
 // Returns that sum per channel and NoL; the caller scales by NoL * colour * attenuation.
 __device__ __forceinline__ float3 brdf(const Surface &s, float3 L, float &NoL)
 {
-	// With unit V and L:  |V+L|^2 = 2 + 2 VoL,  N.(V+L) = NoV + NoL,  V.(V+L) = 1 + VoL -- the half vector
-	// itself is never formed.
-	float VoL = dot3(s.V, L);
-	float NoLr = dot3(s.N, L);
-	float inv_h = rsqrt_fast(fmaf(VoL, 2.0f, 2.0f));
-	NoL = fminf(fmaxf(NoLr, 0.001f), 1.0f);
-	float NoH = fminf(fmaxf((NoLr + s.NoV_raw) * inv_h, 0.0001f), 1.0f);
-	// HoV = sqrt((1 + VoL) / 2) cannot exceed 1 by more than rounding, and 1 - HoV only enters as f^5
-	float HoV = fmaxf(fmaf(VoL, inv_h, inv_h), 0.001f);
-	float f = 1.0f - HoV;
+	// The half vector is formed explicitly: h = V + L.  (|V+L|^2 = 2 + 2 VoL is cheaper by two
+	// instructions but loses all precision when L approaches -V: the relative error of the sum is
+	// eps/|h|^2, and a bright light at a grazing angle then moves the pixel by several B10G11R11
+	// codes.)  With unit V and L: HoV = (1 + VoL)/|h| = |h|/2 and NoL = N.h - N.V.
+	float3 h = make_float3(s.V.x + L.x, s.V.y + L.y, s.V.z + L.z);
+	float hh = dot3(h, h);
+	float inv_h = rsqrt_fast(hh);
+	float Nh = dot3(s.N, h);
+	NoL = fminf(fmaxf(Nh - s.NoV_raw, 0.001f), 1.0f);
+	float NoH = fminf(fmaxf(Nh * inv_h, 0.0001f), 1.0f);
+	float f = fminf(fmaf(hh * inv_h, -0.5f, 1.0f), 0.999f); // 1 - max(HoV, 0.001)
 	float f2 = f * f;
 	float f5 = f2 * f2 * f;
 	float d = fmaf(NoH * NoH, s.m2_minus_1, 1.0f);
@@ -576,6 +580,483 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 5) deferred_lighting2_kerne
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent form: one 512-thread CTA per SM, the frame's light table resident in shared memory.
+//
+// What bounded the kernel above in the light-dense rows (100-230 lights per pixel) was not issue
+// slots but a chain of dependent round trips per 32-light word: bitmask word (L2) -> warp OR ->
+// records (L2) -> per light: distance, vote, branch.  Here
+//   * the whole light table (48 B x 4096 = 192 KiB) is copied ONCE per CTA into shared memory by
+//     the bulk-copy engine (cp.async.bulk, one mbarrier) while the first pixel blocks are being
+//     set up; every record read after that is a shared-memory broadcast;
+//   * a warp first builds the list of lights that can reach its 16x4 pixel block: the bitmask rows
+//     of the (<= 4) cluster tiles under the block are read lane-parallel (lane j owns words j,
+//     j + 32, ...), cut to the hull of the pixels' Z-slice ranges, and each candidate is tested
+//     by its own lane against the block's world-space bounding box (sphere-box distance);
+//     ballots compact the survivors, in ascending light order, into a per-warp list;
+//   * the list is then shaded two lights per iteration -- two independent dependency chains --
+//     with no votes, branches or mask tests inside: a light that does not reach a pixel adds
+//     exactly 0 there because the smoothstep range falloff (point.h:41-43) is exactly 0 beyond
+//     the radius, which is the invariant the clusterer is built on;
+//   * the sums over lights are kept as  S1 = sum c w (1-f5),  S2 = sum c G w (1-f5),
+//     S3 = sum c G w f5  (c colour, w = NoL falloff / d^2, f5 the Schlick weight, G = D*Vis), so
+//     that F0 and the diffuse colour leave the loop:  result = dk (1-F0) S1 + F0 S2 + S3;
+//   * pixel blocks are handed out through an atomic queue in chunks, so a warp that drew cheap
+//     blocks simply draws more.
+constexpr int kPWarps = 16;
+constexpr int kListCap = 160; // light list entries per warp; shaded in batches when it fills up
+
+struct QueueSlot
+{
+	unsigned next_block;
+	unsigned ctas_done;
+};
+__device__ QueueSlot g_light_queue[64];
+
+struct PersistentArgs
+{
+	QueueSlot *queue;
+	int blocks_x, blocks_y, strip_rows, total_items; // strip_rows = ceil(blocks_y / 8), total_items = 8 * strip_rows * blocks_x
+	int n_lights;
+	unsigned rec_bytes; // n_lights * 48, multiple of 16
+	int use_bulk_copy;
+};
+
+struct SurfaceP
+{
+	f2 npx, npy, npz; // -position
+	f2 Nx, Ny, Nz, Vx, Vy, Vz;
+	f2 m2m1, cgd, omk, k, Vk, nNoVr; // nNoVr = -dot(N, V)
+};
+
+__device__ __forceinline__ f2 rcp2(f2 a) { return make_float2(rcp_fast(a.x), rcp_fast(a.y)); }
+__device__ __forceinline__ f2 min2(f2 a, float hi) { return make_float2(fminf(a.x, hi), fminf(a.y, hi)); }
+__device__ __forceinline__ f2 max2(f2 a, float lo) { return make_float2(fmaxf(a.x, lo), fmaxf(a.y, lo)); }
+__device__ __forceinline__ f2 sat2(f2 a) { return make_float2(__saturatef(a.x), __saturatef(a.y)); }
+
+// Per light and pixel pair: a = w (1 - f5), G a, G f5 w  for the (unnormalised) half vector h = V + L
+// and the attenuation w_pre (everything of the weight except NoL).
+__device__ __forceinline__ void shade_terms(const SurfaceP &s, f2 hx, f2 hy, f2 hz, f2 w_pre, f2 &a, f2 &ga, f2 &gb)
+{
+	f2 hh = dot3_2(hx, hy, hz, hx, hy, hz);
+	f2 inv_h = rsqrt2(hh);
+	f2 Nh = dot3_2(s.Nx, s.Ny, s.Nz, hx, hy, hz);
+	f2 NoH = clamp2(mul2(Nh, inv_h), 0.0001f, 1.0f);
+	f2 NoL = clamp2(add2(Nh, s.nNoVr), 0.001f, 1.0f);          // N.L = N.h - N.V
+	f2 f = min2(fma2(mul2(hh, inv_h), mk2(-0.5f), mk2(1.0f)), 0.999f); // 1 - max(HoV, 0.001), HoV = |h| / 2
+	f2 fsq = mul2(f, f);
+	f2 f5 = mul2(mul2(fsq, fsq), f);
+	f2 d = fma2(mul2(NoH, NoH), s.m2m1, mk2(1.0f));
+	f2 vl = mul2(s.Vk, fma2(NoL, s.omk, s.k)); // >= 0.038: the shader's max(.., 1e-3) is the identity
+	f2 g = mul2(s.cgd, rcp2(mul2(mul2(d, d), vl)));
+	f2 w = mul2(NoL, w_pre);
+	f2 b = mul2(w, f5);
+	a = fma2(b, mk2(-1.0f), w);
+	ga = mul2(g, a);
+	gb = mul2(g, b);
+}
+
+// point.h:33-81 / spot.h:34-84 for one light record and the pixel pair, then shade_terms.
+// SPOTS = false: both lights of the iteration are point lights (straight-line code, the two
+// calls interleave freely); SPOTS = true: the cone term is computed and selected per light.
+template <bool SPOTS>
+__device__ __forceinline__ void light_terms(const SurfaceP &s, const float4 l0, const float4 l1, const float4 l2, bool is_spot, f2 &a, f2 &ga, f2 &gb)
+{
+	f2 lx = add2(mk2(l1.x), s.npx), ly = add2(mk2(l1.y), s.npy), lz = add2(mk2(l1.z), s.npz);
+	f2 d2 = dot3_2(lx, ly, lz, lx, ly, lz);
+	f2 inv_d = rsqrt2(d2);
+	f2 inv_ld = min2(inv_d, 10.0f); // 1 / max(0.1, dist)
+	f2 xr = mul2(max2(mul2(d2, inv_d), 0.1f), mk2(l2.w));
+	f2 t = sat2(fma2(xr, mk2(1.0f / (1.0f - 0.9f)), mk2(-0.9f / (1.0f - 0.9f))));
+	f2 falloff = fma2(mul2(mul2(t, t), fma2(mk2(-2.0f), t, mk2(3.0f))), mk2(-1.0f), mk2(1.0f));
+	if (SPOTS)
+	{
+		float2 sb = __half22float2(*reinterpret_cast<const __half2 *>(&l0.w));
+		f2 cone_angle = mul2(dot3_2(lx, ly, lz, mk2(l2.x), mk2(l2.y), mk2(l2.z)), inv_d);
+		f2 cone = sat2(fma2(cone_angle, mk2(-sb.x), mk2(sb.y)));
+		cone = mul2(cone, cone);
+		falloff = mul2(falloff, is_spot ? cone : mk2(1.0f));
+	}
+	f2 w_pre = mul2(falloff, mul2(inv_ld, inv_ld));
+	shade_terms(s, fma2(lx, inv_d, s.Vx), fma2(ly, inv_d, s.Vy), fma2(lz, inv_d, s.Vz), w_pre, a, ga, gb);
+}
+
+// order-preserving float <-> unsigned key (for the integer warp reductions)
+__device__ __forceinline__ unsigned fkey(float f)
+{
+	unsigned u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_kernel(const LightingParams p, const PersistentArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	// layout: [records (n_lights + 1) x 48 B][srgb LUT 1 KiB][lists kPWarps x (kListCap + 2) u16][G-buffer prefetch slots][mbarrier]
+	float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);
+	const unsigned rec_total = a.rec_bytes + 48u;
+	float *s_srgb = reinterpret_cast<float *>(smem_raw + rec_total);
+	uint16_t *s_lists = reinterpret_cast<uint16_t *>(smem_raw + rec_total + 1024u);
+	const unsigned lists_bytes = (kPWarps * (kListCap + 2) * 2u + 15u) & ~15u;
+	unsigned char *s_prefetch = smem_raw + rec_total + 1024u + lists_bytes; // 48 B per thread
+	uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_prefetch + 32u * kPWarps * 48u);
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t bar = smem_u32(s_bar);
+	if (threadIdx.x == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		// the dummy record that pads an odd batch: black, infinitely far away, falloff exactly 0
+		s_rec[3 * a.n_lights + 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+		s_rec[3 * a.n_lights + 1] = make_float4(1.0e18f, 0.f, 0.f, 0.f);
+		s_rec[3 * a.n_lights + 2] = make_float4(0.f, 0.f, 1.f, 1.f);
+	}
+	for (int i = threadIdx.x; i < 256; i += blockDim.x)
+		s_srgb[i] = g_srgb8_to_linear[i];
+	__syncthreads();
+	if (a.use_bulk_copy)
+	{
+		if (threadIdx.x == 0 && a.rec_bytes)
+		{
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(a.rec_bytes) : "memory");
+			const unsigned char *src = reinterpret_cast<const unsigned char *>(p.lights);
+			for (unsigned off = 0; off < a.rec_bytes; off += 32768u)
+			{
+				const unsigned n = min(32768u, a.rec_bytes - off);
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_raw + off)),
+				             "l"(src + off), "r"(n), "r"(bar)
+				             : "memory");
+			}
+		}
+	}
+	else
+	{
+		const float4 *src = reinterpret_cast<const float4 *>(p.lights);
+		for (unsigned i = threadIdx.x; i < a.rec_bytes / 16u; i += blockDim.x)
+			s_rec[i] = __ldg(src + i);
+		__syncthreads();
+	}
+	bool table_ready = !a.use_bulk_copy || a.rec_bytes == 0;
+
+	uint16_t *list = s_lists + warp * (kListCap + 2);
+	const unsigned dummy_entry = (unsigned)a.n_lights;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const unsigned total = (unsigned)a.total_items;
+	const unsigned n_warps = gridDim.x * kPWarps;
+
+	// Work items: the image is cut into 8 horizontal strips and item i is block (i / 8) of strip
+	// (i % 8): the 8 items of a chunk lie in 8 different strips, so the light-dense rows (a few
+	// percent of the rows hold half of the light evaluations) are dealt out one block per chunk
+	// instead of eight in a row to the same warp.  Chunks of 8 items while plenty are left, single
+	// items at the end.  Returns false when the queue is drained.
+	unsigned next = 0, end = 0;
+	auto fetch_item = [&](int &bx, int &by) -> bool {
+		for (;;)
+		{
+			if (next >= end)
+			{
+				unsigned got = 0, want = 1;
+				if (lane == 0)
+				{
+					const unsigned seen = *reinterpret_cast<volatile unsigned *>(&a.queue->next_block);
+					want = (seen < total && total - seen > 16u * n_warps) ? 8u : 1u;
+					got = atomicAdd(&a.queue->next_block, want);
+				}
+				got = __shfl_sync(0xffffffffu, got, 0);
+				want = __shfl_sync(0xffffffffu, want, 0);
+				if (got >= total)
+					return false;
+				next = got;
+				end = min(got + want, total);
+			}
+			const unsigned item = next++;
+			const unsigned g = item >> 3, strip = item & 7u;
+			bx = (int)(g % (unsigned)a.blocks_x);
+			by = (int)(strip * (unsigned)a.strip_rows + g / (unsigned)a.blocks_x);
+			if (by < a.blocks_y)
+				return true;
+		}
+	};
+	// The G-buffer words of the NEXT block are copied asynchronously (cp.async, no registers held)
+	// into this lane's 48-byte slot while the current block is shaded: the HBM round trip at the head
+	// of every block otherwise leaves the warp idle for a seventh of its time.
+	const uint32_t pf_slot = smem_u32(s_prefetch + (size_t)threadIdx.x * 48u);
+	auto prefetch_gbuffer = [&](int bx, int by) {
+		const int x = (bx * 8 + (lane & 7)) * 2;
+		const int y = p.y0 + by * 4 + (lane >> 3);
+		if (x < p.hdr.w && y < p.y1)
+		{
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_slot), "l"(&p.depth.at(x, y)) : "memory");
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_slot + 8u), "l"(&p.albedo.at(x, y)) : "memory");
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_slot + 16u), "l"(&p.normal.at(x, y)) : "memory");
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_slot + 24u), "l"(&p.emissive.at(x, y)) : "memory");
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pf_slot + 32u), "l"(&p.pbr.at(x, y)) : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+
+	int bx = 0, by = 0;
+	bool have = fetch_item(bx, by);
+	if (have)
+		prefetch_gbuffer(bx, by);
+	while (have)
+	{
+		const int x = (bx * 8 + (lane & 7)) * 2;
+		const int y = p.y0 + by * 4 + (lane >> 3);
+		const bool inside = x < p.hdr.w && y < p.y1;
+
+		// ---- G-buffer words (prefetched) and per-pixel invariants ----
+		float2 depth = make_float2(0.f, 0.f);
+		uint2 a8 = make_uint2(0u, 0u), n10 = make_uint2(0u, 0u), em = make_uint2(0u, 0u);
+		uint32_t mr2 = 0u;
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		if (inside)
+		{
+			const unsigned char *slot = s_prefetch + (size_t)threadIdx.x * 48u;
+			depth = *reinterpret_cast<const float2 *>(slot);
+			a8 = *reinterpret_cast<const uint2 *>(slot + 8);
+			n10 = *reinterpret_cast<const uint2 *>(slot + 16);
+			em = *reinterpret_cast<const uint2 *>(slot + 24);
+			mr2 = *reinterpret_cast<const uint32_t *>(slot + 32);
+		}
+		// the slot is free again: start on the next block's words
+		have = fetch_item(bx, by);
+		if (have)
+			prefetch_gbuffer(bx, by);
+
+		const PixelSetup A = setup_pixel(p, s_srgb, x, y, inside, depth.x, a8.x, n10.x, mr2 & 0xffffu, em.x);
+		const PixelSetup B = setup_pixel(p, s_srgb, x + 1, y, inside, depth.y, a8.y, n10.y, mr2 >> 16, em.y);
+		if (!__any_sync(0xffffffffu, A.lit || B.lit))
+		{
+			// sky block: the attachment value is carried through
+			if (inside && p.emissive.p != p.hdr.p)
+				*reinterpret_cast<uint2 *>(&p.hdr.at(x, y)) = em;
+			continue;
+		}
+		SurfaceP s;
+		s.npx = make_float2(-A.pos.x, -B.pos.x); s.npy = make_float2(-A.pos.y, -B.pos.y); s.npz = make_float2(-A.pos.z, -B.pos.z);
+		s.Nx = make_float2(A.N.x, B.N.x); s.Ny = make_float2(A.N.y, B.N.y); s.Nz = make_float2(A.N.z, B.N.z);
+		s.Vx = make_float2(A.V.x, B.V.x); s.Vy = make_float2(A.V.y, B.V.y); s.Vz = make_float2(A.V.z, B.V.z);
+		s.m2m1 = make_float2(A.m2m1, B.m2m1); s.cgd = make_float2(A.cgd, B.cgd);
+		s.omk = make_float2(A.omk, B.omk); s.k = make_float2(A.k, B.k); s.Vk = make_float2(A.Vk, B.Vk);
+		s.nNoVr = make_float2(-A.NoVr, -B.NoVr);
+		// per channel: result = Ad * S1 + F0 * S2 + S3 with Ad = dk (1 - F0)
+		const f2 F0x = make_float2(A.F0.x, B.F0.x), F0y = make_float2(A.F0.y, B.F0.y), F0z = make_float2(A.F0.z, B.F0.z);
+		const f2 Adx = make_float2(A.dk.x * (1.0f - A.F0.x), B.dk.x * (1.0f - B.F0.x));
+		const f2 Ady = make_float2(A.dk.y * (1.0f - A.F0.y), B.dk.y * (1.0f - B.F0.y));
+		const f2 Adz = make_float2(A.dk.z * (1.0f - A.F0.z), B.dk.z * (1.0f - B.F0.z));
+
+		// ---- draw 1: directional.frag (LIGHTING_NO_AMBIENT, no shadows, VOLUMETRIC_DIFFUSE_FALLBACK) ----
+		uint32_t dstA = A.dst, dstB = B.dst;
+		{
+			f2 ta, tga, tgb;
+			shade_terms(s, add2(s.Vx, mk2(p.dir_dir.x)), add2(s.Vy, mk2(p.dir_dir.y)), add2(s.Vz, mk2(p.dir_dir.z)), mk2(1.0f), ta, tga, tgb);
+			const f2 rx = fma2(Adx, ta, fma2(F0x, tga, tgb)), ry = fma2(Ady, ta, fma2(F0y, tga, tgb)), rz = fma2(Adz, ta, fma2(F0z, tga, tgb));
+			if (A.lit)
+			{
+				float3 e = unpack_r11g11b10(dstA);
+				dstA = pack_r11g11b10(e.x + p.dir_color.x * rx.x + A.base_color.x * 0.05f, e.y + p.dir_color.y * ry.x + A.base_color.y * 0.05f,
+				                      e.z + p.dir_color.z * rz.x + A.base_color.z * 0.05f);
+			}
+			if (B.lit)
+			{
+				float3 e = unpack_r11g11b10(dstB);
+				dstB = pack_r11g11b10(e.x + p.dir_color.x * rx.y + B.base_color.x * 0.05f, e.y + p.dir_color.y * ry.y + B.base_color.y * 0.05f,
+				                      e.z + p.dir_color.z * rz.y + B.base_color.z * 0.05f);
+			}
+		}
+
+		// ---- draw 2, step 1: candidate words.  Lane j owns words j, j + 32, j + 64, j + 96. ----
+		uint32_t cand0 = 0u, cand1 = 0u, cand2 = 0u, cand3 = 0u;
+		{
+			const int tileA = A.lit ? A.cluster_base : -1, tileB = B.lit ? B.cluster_base : -1; // tile_index * n32
+			bool coveredA = !A.lit, coveredB = !B.lit;
+			for (;;)
+			{
+				// next uncovered pixel's tile; A pixels first
+				const unsigned remA = __ballot_sync(0xffffffffu, !coveredA), remB = __ballot_sync(0xffffffffu, !coveredB);
+				if (!(remA | remB))
+					break;
+				const int base = remA ? __shfl_sync(0xffffffffu, tileA, __ffs(remA) - 1) : __shfl_sync(0xffffffffu, tileB, __ffs(remB) - 1);
+				const bool inA = A.lit && tileA == base, inB = B.lit && tileB == base;
+				coveredA |= inA;
+				coveredB |= inB;
+				// hull of the Z-slice light ranges of the block's pixels in this tile (a superset of their
+				// union; the box test below removes what lies between two depth layers)
+				const unsigned lo = __reduce_min_sync(0xffffffffu, min(inA ? A.rx : 0xffffffffu, inB ? B.rx : 0xffffffffu));
+				const unsigned hi = __reduce_max_sync(0xffffffffu, max(inA ? A.ry : 0u, inB ? B.ry : 0u));
+				if (lo > hi)
+					continue; // empty slices: (0xffffffff, 0)
+				// cluster_mask_range (clusterer_bindless_buffers.h:17-27) for a warp-uniform range: only the
+				// first and the last word of [lo, hi] are cut
+				const unsigned wlo = lo >> 5, whi_raw = hi >> 5, whi = min(whi_raw, (unsigned)p.n32 - 1u);
+				const uint32_t cut_lo = 0xffffffffu << (lo & 31u), cut_hi = 0xffffffffu >> (31u - (hi & 31u));
+				const uint32_t *row = p.bitmask + base;
+				auto take = [&](unsigned j) -> uint32_t {
+					if (j < wlo || j > whi)
+						return 0u;
+					return __ldg(row + j) & (j == wlo ? cut_lo : 0xffffffffu) & (j == whi_raw ? cut_hi : 0xffffffffu);
+				};
+				cand0 |= take((unsigned)lane);
+				if (p.n32 > 32)
+				{
+					cand1 |= take((unsigned)lane + 32u);
+					cand2 |= take((unsigned)lane + 64u);
+					cand3 |= take((unsigned)lane + 96u);
+				}
+			}
+		}
+
+		// world-space bounding box of the block's lit pixels
+		float bmin_x, bmin_y, bmin_z, bmax_x, bmax_y, bmax_z;
+		{
+			const unsigned kInf = 0xffffffffu;
+			unsigned lx = kInf, ly = kInf, lz = kInf, hx = 0u, hy = 0u, hz = 0u;
+			if (A.lit)
+			{
+				lx = hx = fkey(A.pos.x); ly = hy = fkey(A.pos.y); lz = hz = fkey(A.pos.z);
+			}
+			if (B.lit)
+			{
+				const unsigned kx = fkey(B.pos.x), ky = fkey(B.pos.y), kz = fkey(B.pos.z);
+				lx = min(lx, kx); ly = min(ly, ky); lz = min(lz, kz);
+				hx = max(hx, kx); hy = max(hy, ky); hz = max(hz, kz);
+			}
+			bmin_x = fkey_inv(__reduce_min_sync(0xffffffffu, lx)); bmin_y = fkey_inv(__reduce_min_sync(0xffffffffu, ly));
+			bmin_z = fkey_inv(__reduce_min_sync(0xffffffffu, lz));
+			bmax_x = fkey_inv(__reduce_max_sync(0xffffffffu, hx)); bmax_y = fkey_inv(__reduce_max_sync(0xffffffffu, hy));
+			bmax_z = fkey_inv(__reduce_max_sync(0xffffffffu, hz));
+		}
+
+		if (!table_ready)
+		{
+			// the light table (bulk copy issued at kernel start) must have landed before its first use
+			uint32_t done = 0;
+			while (!done)
+				asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar) : "memory");
+			table_ready = true;
+		}
+
+		// ---- draw 2, steps 2 + 3: compact the candidates that touch the box into the list, shade the list ----
+		f2 S1x = mk2(0.f), S1y = mk2(0.f), S1z = mk2(0.f), S2x = mk2(0.f), S2y = mk2(0.f), S2z = mk2(0.f), S3x = mk2(0.f), S3y = mk2(0.f), S3z = mk2(0.f);
+		int k = 0;
+		unsigned nz = __ballot_sync(0xffffffffu, cand0 != 0u);
+		bool more = true;
+		while (more)
+		{
+			int count = 0;
+			while (count <= kListCap - 32)
+			{
+				while (nz == 0u && k < 3)
+				{
+					k++;
+					nz = __ballot_sync(0xffffffffu, (k == 1 ? cand1 : (k == 2 ? cand2 : cand3)) != 0u);
+				}
+				if (nz == 0u)
+				{
+					more = false;
+					break;
+				}
+				const int j = __ffs(nz) - 1;
+				nz &= nz - 1u;
+				const uint32_t mine = k == 0 ? cand0 : (k == 1 ? cand1 : (k == 2 ? cand2 : cand3));
+				const uint32_t word = __shfl_sync(0xffffffffu, mine, j);
+				const unsigned widx = (unsigned)(j + 32 * k);
+				const unsigned li = widx * 32u + (unsigned)lane;
+				bool pass = false;
+				if ((word >> lane) & 1u)
+				{
+					const float4 l1 = s_rec[3u * li + 1u];
+					const float inv_r = s_rec[3u * li + 2u].w;
+					const float dx = fmaxf(fmaxf(bmin_x - l1.x, l1.x - bmax_x), 0.0f);
+					const float dy = fmaxf(fmaxf(bmin_y - l1.y, l1.y - bmax_y), 0.0f);
+					const float dz = fmaxf(fmaxf(bmin_z - l1.z, l1.z - bmax_z), 0.0f);
+					pass = (dx * dx + dy * dy + dz * dz) * (inv_r * inv_r) < 1.0005f;
+				}
+				const unsigned m = __ballot_sync(0xffffffffu, pass);
+				if (pass)
+				{
+					const unsigned is_spot = ((__ldg(&p.type_mask[widx]) >> lane) & 1u) ^ 1u;
+					list[count + __popc(m & lt_mask)] = (uint16_t)(li | (is_spot << 15));
+				}
+				count += __popc(m);
+			}
+			if (count == 0)
+				break;
+			if (lane == 0)
+				list[count] = (uint16_t)dummy_entry; // pads an odd batch
+			__syncwarp();
+			for (int e = 0; e < count; e += 2)
+			{
+				const uint32_t two = *reinterpret_cast<const uint32_t *>(list + e);
+				const unsigned i0 = two & 0x7fffu, i1 = (two >> 16) & 0x7fffu;
+				const bool spot0 = (two & 0x8000u) != 0u, spot1 = (two & 0x80000000u) != 0u;
+				const float4 a0 = s_rec[3u * i0], a1 = s_rec[3u * i0 + 1u], a2 = s_rec[3u * i0 + 2u];
+				const float4 b0 = s_rec[3u * i1], b1 = s_rec[3u * i1 + 1u], b2 = s_rec[3u * i1 + 2u];
+				f2 ta, tga, tgb, ua, uga, ugb;
+				if (two & 0x80008000u)
+				{
+					light_terms<true>(s, a0, a1, a2, spot0, ta, tga, tgb);
+					light_terms<true>(s, b0, b1, b2, spot1, ua, uga, ugb);
+				}
+				else
+				{
+					light_terms<false>(s, a0, a1, a2, false, ta, tga, tgb);
+					light_terms<false>(s, b0, b1, b2, false, ua, uga, ugb);
+				}
+				S1x = fma2(mk2(a0.x), ta, S1x); S1y = fma2(mk2(a0.y), ta, S1y); S1z = fma2(mk2(a0.z), ta, S1z);
+				S2x = fma2(mk2(a0.x), tga, S2x); S2y = fma2(mk2(a0.y), tga, S2y); S2z = fma2(mk2(a0.z), tga, S2z);
+				S3x = fma2(mk2(a0.x), tgb, S3x); S3y = fma2(mk2(a0.y), tgb, S3y); S3z = fma2(mk2(a0.z), tgb, S3z);
+				S1x = fma2(mk2(b0.x), ua, S1x); S1y = fma2(mk2(b0.y), ua, S1y); S1z = fma2(mk2(b0.z), ua, S1z);
+				S2x = fma2(mk2(b0.x), uga, S2x); S2y = fma2(mk2(b0.y), uga, S2y); S2z = fma2(mk2(b0.z), uga, S2z);
+				S3x = fma2(mk2(b0.x), ugb, S3x); S3y = fma2(mk2(b0.y), ugb, S3y); S3z = fma2(mk2(b0.z), ugb, S3z);
+			}
+			__syncwarp();
+		}
+
+		if (inside)
+		{
+			const f2 rx = fma2(Adx, S1x, fma2(F0x, S2x, S3x)), ry = fma2(Ady, S1y, fma2(F0y, S2y, S3y)), rz = fma2(Adz, S1z, fma2(F0z, S2z, S3z));
+			uint2 out = make_uint2(dstA, dstB);
+			if (A.lit)
+			{
+				float3 e = unpack_r11g11b10(dstA);
+				out.x = pack_r11g11b10(e.x + rx.x, e.y + ry.x, e.z + rz.x);
+			}
+			if (B.lit)
+			{
+				float3 e = unpack_r11g11b10(dstB);
+				out.y = pack_r11g11b10(e.x + rx.y, e.y + ry.y, e.z + rz.y);
+			}
+			if (A.lit || B.lit || p.emissive.p != p.hdr.p)
+				*reinterpret_cast<uint2 *>(&p.hdr.at(x, y)) = out;
+		}
+	}
+
+	if (!table_ready)
+	{
+		// never leave with the bulk copy still in flight towards this CTA's shared memory
+		uint32_t done = 0;
+		while (!done)
+			asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar) : "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		// the last CTA to finish re-arms the queue slot for its next launch
+		__threadfence();
+		if (atomicAdd(&a.queue->ctas_done, 1u) == gridDim.x - 1u)
+		{
+			a.queue->next_block = 0u;
+			a.queue->ctas_done = 0u;
+			__threadfence();
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // Work estimate of the lighting pass per group of 4 pixel rows (one row of CTAs), in issued warp
 // instructions.  The light density of a frame is far from uniform (in the bench scene 3 % of the
 // rows hold over half of the light evaluations), so equal-height row bands do not split the pass
@@ -648,6 +1129,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lighting_cost_kernel(const 
 		atomicAdd(&cost[blockIdx.y], total);
 }
 } // namespace
+
+// per-device launch state of the persistent kernel (one process may drive several GPUs)
+constexpr int kMaxDevices = 64;
+struct DeviceInfo
+{
+	std::atomic<bool> ready{ false };
+	int sm_count = 0, smem_max = 0;
+	QueueSlot *queue = nullptr;
+	std::atomic<unsigned> next_slot{ 0 };
+};
+static DeviceInfo g_device_info[kMaxDevices];
+static std::mutex g_device_lock;
 
 int32_t upload_srgb_lut(const float *lut256)
 {
@@ -744,6 +1237,60 @@ extern "C" int32_t grb_deferred_lighting(const GrbGBuffer *g, const GrbCamera *c
 	const bool pairs = !force_1px && (w % 2) == 0 && aligned8(g->albedo.data, g->albedo.row_pitch) && aligned8(g->normal.data, g->normal.row_pitch) &&
 	                   aligned8(g->depth.data, g->depth.row_pitch) && (reinterpret_cast<uintptr_t>(g->pbr.data) % 4) == 0 && (g->pbr.row_pitch % 4) == 0 &&
 	                   aligned8(hdr->data, hdr->row_pitch) && (!g->emissive.data || aligned8(g->emissive.data, g->emissive.row_pitch));
+	static const bool force_v2 = getenv("GRB_LIGHTING_V2") != nullptr;
+	if (pairs && !force_v2 && params->num_lights <= 4096 && params->num_lights_32 <= 128)
+	{
+		// persistent kernel: one CTA per SM, light table in shared memory
+		int device = 0;
+		cudaError_t err = cudaGetDevice(&device);
+		if (err != cudaSuccess || device < 0 || device >= kMaxDevices)
+		{
+			set_last_error("grb_deferred_lighting: cudaGetDevice failed");
+			return GRB_ERR_CUDA;
+		}
+		DeviceInfo &di = g_device_info[device];
+		if (!di.ready.load(std::memory_order_acquire))
+		{
+			std::lock_guard<std::mutex> hold(g_device_lock);
+			if (!di.ready.load(std::memory_order_relaxed))
+			{
+				int sms = 0, smem_max = 0;
+				err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+				if (err == cudaSuccess)
+					err = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+				if (err == cudaSuccess)
+					err = cudaFuncSetAttribute(deferred_lighting_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+				void *q = nullptr;
+				if (err == cudaSuccess)
+					err = cudaGetSymbolAddress(&q, g_light_queue);
+				if (err != cudaSuccess)
+				{
+					set_last_error(cudaGetErrorString(err));
+					return GRB_ERR_CUDA;
+				}
+				di.sm_count = sms;
+				di.smem_max = smem_max;
+				di.queue = static_cast<QueueSlot *>(q);
+				di.ready.store(true, std::memory_order_release);
+			}
+		}
+		PersistentArgs a;
+		a.blocks_x = (w / 2 + 7) / 8;
+		a.blocks_y = (rows.y1 - rows.y0 + 3) / 4;
+		a.strip_rows = (a.blocks_y + 7) / 8;
+		a.total_items = 8 * a.strip_rows * a.blocks_x;
+		a.n_lights = params->num_lights;
+		a.rec_bytes = (unsigned)params->num_lights * 48u;
+		a.use_bulk_copy = (reinterpret_cast<uintptr_t>(buf->lights) % 16) == 0 ? 1 : 0;
+		a.queue = di.queue + (di.next_slot.fetch_add(1u, std::memory_order_relaxed) % 64u);
+		const size_t smem = (size_t)a.rec_bytes + 48u + 1024u + ((kPWarps * (kListCap + 2) * 2u + 15u) & ~15u) + 32u * kPWarps * 48u + 16u;
+		if (smem <= (size_t)di.smem_max)
+		{
+			const int ctas = std::min(di.sm_count, std::max(1, (a.blocks_x * a.blocks_y + kPWarps - 1) / kPWarps));
+			deferred_lighting_persistent_kernel<<<ctas, 32 * kPWarps, smem, as_stream(stream)>>>(p, a);
+			return check_launch("grb_deferred_lighting");
+		}
+	}
 	if (pairs)
 	{
 		dim3 grid2((w / 2 + 8 * kWarpsPerCta - 1) / (8 * kWarpsPerCta), (rows.y1 - rows.y0 + 3) / 4, 1);

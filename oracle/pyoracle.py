@@ -17,11 +17,23 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libgranite_refmath.so")
 
 
+_REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for k in (1, 2, 3, 4)]
+
+
 def build(ref: bool = True) -> None:
-    """Compile liboracle.so (always) and oracle/_ref (only where /root/reference exists)."""
+    """Compile liboracle.so (always) and oracle/_ref (only where /root/reference exists):
+    the reference's math/ (`make ref`) and its clusterer compute shaders run on the CPU through its
+    vendored glslang + spirv-cross (`make ref-shaders`, ~1 min the first time)."""
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
     if ref and os.path.isdir("/root/reference/math"):
         subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+    if ref and os.path.isdir("/root/reference/third_party/spirv-cross") and os.path.isdir("/root/reference/third_party/glslang"):
+        shim = os.path.join(_HERE, "ref_shader_shim.cpp")
+        stale = any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(shim) for p in _REF_KERNEL_PATHS)
+        if stale:
+            r = subprocess.run(["make", "-s", "-j8", "-C", _HERE, "ref-shaders"], capture_output=True, text=True)
+            if r.returncode != 0:  # checker infrastructure: report, never break the product build
+                print("oracle: `make ref-shaders` failed (the reference-shader pin is unavailable):\n" + r.stdout[-2000:] + r.stderr[-2000:])
 
 
 class Light(C.Structure):
@@ -91,6 +103,18 @@ def ref():
         _ref.ref_float_to_half.argtypes = [C.c_float]
         _ref.ref_infinite_far_plane.restype = C.c_float
     return _ref
+
+
+_ref_kernels = None
+
+
+def ref_kernels():
+    """{1..4: CDLL} of the reference's clusterer compute shaders compiled for the CPU
+    (oracle/_ref/libgranite_ref_k*.so, see ref_shader_shim.cpp), or None when they were not built."""
+    global _ref_kernels
+    if _ref_kernels is None and all(os.path.exists(p) for p in _REF_KERNEL_PATHS):
+        _ref_kernels = {k: C.CDLL(p) for k, p in zip((1, 2, 3, 4), _REF_KERNEL_PATHS)}
+    return _ref_kernels
 
 
 def _p(a):
@@ -182,6 +206,64 @@ def cluster_build(cam: Camera, prep):
     crange = np.zeros((rz, 2), np.uint32)
     L.orc_z_range(_p(prep.z_ranges), max(n, 1), rz, _p(crange))
     return SimpleNamespace(spots=spots, cull=cull, bitmask=bitmask, range=crange)
+
+
+def _farr(x, dtype=np.float32):
+    return np.ascontiguousarray(np.array(list(x), dtype))
+
+
+def ref_spot_transform(cam: Camera, prep):
+    """K1 through the reference's own shader (clusterer_bindless_spot_transform.comp)."""
+    n = prep.n
+    out = np.zeros((max(n, 1), 24), np.float32)
+    vp, cp, cf = _farr(cam.view_projection), _farr(cam.camera_position), _farr(cam.camera_front)
+    ref_kernels()[1].refk1_spot_transform(_p(vp), _p(cp), _p(cf), _f(cam.z_near), _f(cam.z_far), _p(prep.model), n, _p(out))
+    return out
+
+
+def ref_cull_setup(cam: Camera, prep, spots):
+    """K2 through the reference's own shader (clusterer_bindless_setup.comp)."""
+    n, pr = prep.n, prep.params
+    out = np.zeros((max(n, 1), 128), np.float32)
+    keep = [_farr(cam.view), _farr(pr.transform), _farr(pr.clip_scale), _farr(pr.camera_base), _farr(pr.camera_front), _farr(pr.xy_scale),
+            _farr(pr.resolution_xy, np.int32), _farr(pr.inv_resolution_xy)]
+    spots = _c(spots, np.float32)
+    ref_kernels()[2].refk2_cull_setup(*[_p(k) for k in keep], pr.num_lights_32, pr.z_max_index, _f(pr.z_scale), _p(prep.records),
+                                      _p(prep.type_mask), _p(spots), n, _p(out))
+    return out
+
+
+def ref_binning(prep, cull, window=None):
+    """K3 through the reference's own shader.  The reference runs the SUBGROUPS=1 variant on NVIDIA
+    (clusterer.cpp:1519-1561): a coarse test of each 8x4-tile block AND the per-tile test, both with
+    the shader's test_point_light / test_spot_light.  Only the SUBGROUPS=0 variant (per-tile test
+    alone) can execute without subgroup hardware, so the coarse pass is that same executable run on
+    the 16x16 grid of 8x4-tile blocks (resolution 128x64 makes `2 * tile * inv_resolution` exact in
+    both forms), and the two masks are ANDed.  window = (tx0, tx1, ty0, ty1) in tiles, multiples of
+    (8, 4); tiles outside it are returned as zeros.  Returns (composite, fine_only)."""
+    pr = prep.params
+    n, n32 = prep.n, pr.num_lights_32
+    rx, ry = int(pr.resolution_xy[0]), int(pr.resolution_xy[1])
+    tx0, tx1, ty0, ty1 = window if window else (0, rx, 0, ry)
+    assert tx0 % 8 == 0 and tx1 % 8 == 0 and ty0 % 4 == 0 and ty1 % 4 == 0
+    cull = _c(cull, np.float32)
+    k3 = ref_kernels()[3].refk3_binning
+    clip, res, inv = _farr(pr.clip_scale), _farr(pr.resolution_xy, np.int32), _farr(pr.inv_resolution_xy)
+    fine = np.zeros((ry, rx, max(n32, 1)), np.uint32)
+    k3(_p(clip), _p(res), _p(inv), n32, _p(prep.type_mask), _p(cull), n, tx0, tx1, ty0, ty1, _p(fine))
+    res_c = np.array([rx // 8, ry // 4], np.int32)
+    inv_c = np.array([np.float32(8.0) * np.float32(pr.inv_resolution_xy[0]), np.float32(4.0) * np.float32(pr.inv_resolution_xy[1])], np.float32)
+    coarse = np.zeros((ry // 4, rx // 8, max(n32, 1)), np.uint32)
+    k3(_p(clip), _p(res_c), _p(inv_c), n32, _p(prep.type_mask), _p(cull), n, tx0 // 8, tx1 // 8, ty0 // 4, ty1 // 4, _p(coarse))
+    return fine & np.repeat(np.repeat(coarse, 4, 0), 8, 1), fine
+
+
+def ref_z_range(prep):
+    """K4 through the reference's own shader (clusterer_bindless_z_range.comp, the naive form)."""
+    rz = prep.res[2]
+    out = np.zeros((rz, 2), np.uint32)
+    ref_kernels()[4].refk4_z_range(_p(prep.z_ranges), max(prep.n, 1), rz, _p(out))
+    return out
 
 
 def deferred_lighting(scene, cam: Camera, prep, clus, rows=None, want_indices=False):

@@ -69,7 +69,7 @@ def test_config1_single_tonemap_pass(cuda, oracle):
     v.close()
 
 
-@pytest.mark.parametrize("w,h,n,spots", [(640, 360, 300, 0.25), (1920, 1080, 1024, 0.0)])
+@pytest.mark.parametrize("w,h,n,spots", [(640, 360, 300, 0.25), (1920, 1080, 1024, 0.0), (3840, 2160, 4096, 0.0)])
 def test_full_chain_frames(cuda, oracle, w, h, n, spots):
     scene, lights = synth.make_scene(w, h), synth.make_lights(n, spot_fraction=spots, aspect=w / h)
     v = _make_viewer(scene, lights)
@@ -133,12 +133,13 @@ def test_chain_is_bit_exact_given_identical_hdr(cuda, oracle):
     v.close()
 
 
-def test_taa_fxaa_chain(cuda, oracle):
-    """BASELINE config 5 wiring: TAA (quality 2) before the HDR chain, FXAA after it, with history."""
+@pytest.mark.parametrize("w,h,n", [(640, 360, 100), (3840, 2160, 4096)])
+def test_taa_fxaa_chain(cuda, oracle, w, h, n):
+    """BASELINE config 5 wiring: TAA (quality 2) before the HDR chain, FXAA after it, with history
+    (3 frames; the second case is config 5 itself: 3840x2160, 4096 lights)."""
     from granite_b200 import viewer
 
-    w, h = 640, 360
-    scene, lights = synth.make_scene(w, h), synth.make_lights(100, aspect=w / h)
+    scene, lights = synth.make_scene(w, h), synth.make_lights(n, aspect=w / h)
     rng = np.random.default_rng(5)
     mv = np.zeros((h, w, 2), np.float16)
     m = rng.random((h, w)) < 0.1

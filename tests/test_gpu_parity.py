@@ -19,6 +19,8 @@ CONFIGS = [
     pytest.param(640, 360, 300, 0.25, id="small-300-25pct-spots"),
     pytest.param(1920, 1080, 1024, 0.0, id="C2-1080p-1024pt"),
 ]
+# the benchmarked configuration (BASELINE config 3): 100-230 candidate lights per pixel in the dense rows
+C3 = pytest.param(3840, 2160, 4096, 0.0, id="C3-4K-4096pt")
 
 
 def _canon(a):
@@ -65,7 +67,7 @@ def test_cluster_build_bit_exact(cuda, oracle, w, h, n, spots):
         assert not (got.bitmask[..., -1] >> np.uint32(n % 32)).any()
 
 
-@pytest.mark.parametrize("w,h,n,spots", CONFIGS)
+@pytest.mark.parametrize("w,h,n,spots", CONFIGS + [C3])
 def test_cluster_indices_bit_exact(cuda, oracle, w, h, n, spots):
     from granite_b200 import capi, harness
 
@@ -146,7 +148,7 @@ def test_lighting_row_cost_is_the_cluster_walk(cuda, oracle, w, h, n, spots):
     assert got.sum() > 700 * groups * ((w + 15) // 16)
 
 
-@pytest.mark.parametrize("w,h,n,spots", CONFIGS)
+@pytest.mark.parametrize("w,h,n,spots", CONFIGS + [C3, pytest.param(3840, 2160, 4096, 0.25, id="C3-4K-4096-25pct-spots")])
 def test_deferred_lighting_parity(cuda, oracle, w, h, n, spots):
     from granite_b200 import harness
 
@@ -265,7 +267,7 @@ def test_tonemap(cuda, oracle, w, h, dynamic):
     assert (got == ref).mean() > 0.999
 
 
-@pytest.mark.parametrize("w,h", [(256, 256), (1280, 720), (333, 177)])
+@pytest.mark.parametrize("w,h", [(256, 256), (1280, 720), (333, 177), (3840, 2160)])
 @pytest.mark.parametrize("srgb", [True, False])
 def test_fxaa(cuda, oracle, w, h, srgb):
     from granite_b200 import harness
@@ -299,8 +301,7 @@ def _taa_inputs(rng, w, h):
     return hdr, depth, mv.view(np.uint16), hist.view(np.uint16), reproj
 
 
-@pytest.mark.parametrize("w,h", [(256, 256), (1280, 720), (333, 177)])
-@pytest.mark.parametrize("quality", [0, 1, 2])
+@pytest.mark.parametrize("w,h,quality", [(w, h, q) for (w, h) in [(256, 256), (1280, 720), (333, 177)] for q in (0, 1, 2)] + [(3840, 2160, 2)])
 def test_taa_resolve_bit_exact(cuda, oracle, w, h, quality):
     from granite_b200 import harness
 
