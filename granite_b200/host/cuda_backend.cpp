@@ -1,5 +1,7 @@
 #include "cuda_backend.hpp"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <cuda_runtime.h>
 
 #include <chrono>
@@ -184,8 +186,27 @@ void *Device::allocate(size_t size)
 		size = 16;
 	if (!cuda_ok(cudaMalloc(&p, size), "cudaMalloc"))
 		throw std::runtime_error("granite_b200: out of device memory");
-	// zero-initialised like the graph's buffers (render_graph.cpp:2587); ordered on the graph stream
+	// zero-initialised like the graph's buffers (render_graph.cpp:2587).  The fill runs on the graph
+	// stream, but the first writer of a fresh resource may record on a side stream (cluster build,
+	// pipelined G-buffer upload, bloom), and the graph's hazard tracking has no entry for a resource
+	// that nobody has touched yet: make every side stream wait for the fill.
 	cuda_ok(cudaMemsetAsync(p, 0, size, stream), "cudaMemsetAsync");
+	bool has_side = false;
+	for (auto side : side_streams)
+		has_side = has_side || (side && side != stream);
+	if (has_side)
+	{
+		if (!alloc_event)
+		{
+			cudaEvent_t e;
+			cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate(alloc)");
+			alloc_event = e;
+		}
+		cuda_ok(cudaEventRecord(alloc_event, stream), "cudaEventRecord(alloc)");
+		for (auto side : side_streams)
+			if (side && side != stream)
+				cuda_ok(cudaStreamWaitEvent(side, alloc_event, 0), "cudaStreamWaitEvent(alloc)");
+	}
 	return p;
 }
 
@@ -345,7 +366,10 @@ bool CommandBuffer::check(int32_t result, const char *what)
 	return false;
 }
 
-void CommandBuffer::begin_region(const char *) {}
-void CommandBuffer::end_region() {}
+// NVTX ranges around every pass callback (Vulkan::CommandBuffer::begin_region / end_region label
+// the pass in RenderDoc; here it is what Nsight Systems / ncu --nvtx show).  Header-only NVTX3:
+// without a profiler attached the calls are a pointer test.
+void CommandBuffer::begin_region(const char *name) { nvtxRangePushA(name ? name : "pass"); }
+void CommandBuffer::end_region() { nvtxRangePop(); }
 } // namespace CUDA
 } // namespace Granite

@@ -153,6 +153,7 @@ private:
 	bool owns_stream = false;
 	Stream side_streams[2] = { nullptr, nullptr };
 	Event join_events[2] = { nullptr, nullptr };
+	Event alloc_event = nullptr; // orders the zero fill of a fresh allocation before the side streams
 	std::mutex lock;
 	std::vector<TimeInterval> intervals;
 	std::vector<Event> event_pool;

@@ -167,9 +167,14 @@ void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &fr
 	if (options.dynamic_exposure)
 	{
 		res->lum = &bloom_pass.add_storage_output("average-luminance", buffer_info);
-		// scratch for the row-sharded luminance sum: the (d3/2) sample grid; 64 KiB covers 16K frames
+		// scratch for the row-sharded luminance sum: the (d3/2) sample grid (hdr.cpp:78-79), sized from
+		// the backbuffer: d3 = ceil(dim / 32)
 		BufferInfo grid_info;
-		grid_info.size = 64 * 1024;
+		{
+			const auto dim = graph.get_backbuffer_dimensions();
+			const size_t gx = (size_t(dim.width) + 31) / 32 / 2 + 1, gy = (size_t(dim.height) + 31) / 32 / 2 + 1;
+			grid_info.size = std::max<size_t>(gx * gy * sizeof(float), 64 * 1024);
+		}
 		grid_info.usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT;
 		res->lum_grid = &bloom_pass.add_storage_output("average-luminance-grid", grid_info);
 	}

@@ -508,9 +508,10 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 	// Each pass records on the stream of its queue (main, async compute, async graphics).
 	// Ordering ACROSS streams is derived from the declared resources: before a pass is recorded,
 	// its stream waits for the last pass that touched any of its physical images / buffers on
-	// another stream (covers RAW, WAR and WAW, also across frames because physical resources
-	// persist; ping-pong images alternate so consecutive frames do not meet on them).  Within a
-	// stream, stream order is the dependency.
+	// another stream: readers wait for the last writer, writers for the last access on every other
+	// stream (RAW, WAR and WAW, also across frames because physical resources persist; ping-pong
+	// images alternate so consecutive frames do not meet on them).  Within a stream, stream order is
+	// the dependency.
 	if (pass_done_events.size() != passes.size())
 		pass_done_events.assign(passes.size(), std::array<Vulkan::Event, EventRing>{});
 	const unsigned slot = unsigned(frame_counter++ % EventRing);
@@ -524,25 +525,41 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 		Vulkan::Stream stream = dev.get_queue_stream(queue_stream_index(pass.get_queue()));
 		Vulkan::CommandBuffer cmd(dev, stream);
 
-		auto wait_for = [&](const void *key) {
+		const unsigned stream_index = queue_stream_index(pass.get_queue());
+		auto wait_for = [&](const void *key, bool writes) {
 			if (!key)
 				return;
 			auto itr = last_access.find(key);
-			if (itr != last_access.end() && itr->second.event && itr->second.stream != stream)
-				dev.stream_wait_event(stream, itr->second.event);
+			if (itr == last_access.end())
+				return;
+			auto &la = itr->second;
+			if (la.write_event && la.write_stream != stream)
+				dev.stream_wait_event(stream, la.write_event);
+			if (writes)
+				for (unsigned i = 0; i < 3; i++)
+					if (la.stream_event[i] && la.stream_of[i] != stream && la.stream_event[i] != la.write_event)
+						dev.stream_wait_event(stream, la.stream_event[i]);
 		};
-		auto mark = [&](const void *key) {
-			if (key)
-				last_access[key] = LastAccess{ pass_done_events[p][slot], stream };
+		auto mark = [&](const void *key, bool writes) {
+			if (!key)
+				return;
+			auto &la = last_access[key];
+			la.stream_event[stream_index % 3] = pass_done_events[p][slot];
+			la.stream_of[stream_index % 3] = stream;
+			if (writes)
+			{
+				la.write_event = pass_done_events[p][slot];
+				la.write_stream = stream;
+			}
 		};
 		{
 			Vulkan::ScopedHostTimer timer("graph.cross-stream waits");
 			for (auto *r : pass.get_all_reads())
-				wait_for(physical_key(*r, false));
+				wait_for(physical_key(*r, false), false);
 			for (auto *w : pass.get_all_writes())
-				wait_for(physical_key(*w, false));
+				wait_for(physical_key(*w, false), true);
 			for (auto *h : pass.get_history_inputs())
-				wait_for(physical_key(*h, true));
+				wait_for(physical_key(*h, true), false);
 		}
 
 		Vulkan::Event begin = nullptr, end = nullptr;
@@ -568,11 +585,11 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 			pass_done_events[p][slot] = dev.request_event();
 		dev.record_event_on(pass_done_events[p][slot], stream);
 		for (auto *r : pass.get_all_reads())
-			mark(physical_key(*r, false));
+			mark(physical_key(*r, false), false);
 		for (auto *w : pass.get_all_writes())
-			mark(physical_key(*w, false));
+			mark(physical_key(*w, false), true);
 		for (auto *h : pass.get_history_inputs())
-			mark(physical_key(*h, true));
+			mark(physical_key(*h, true), false);
 		errors += cmd.get_error_count();
 	}
 	if (errors)

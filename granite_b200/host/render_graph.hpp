@@ -419,11 +419,16 @@ private:
 	std::vector<Vulkan::BufferHandle> physical_buffers;
 	unsigned backbuffer_physical = RenderResource::Unused;
 	bool baked = false;
-	// cross-stream ordering: last pass that touched each physical resource (event + stream)
+	// cross-stream ordering per physical resource: the last writer, and the last access (read or
+	// write) recorded on each of the three queue streams.  A reader waits for the writer; a writer
+	// waits for the last access on every other stream (RAW, WAW and WAR, also when two passes on
+	// different streams read the resource before the next write).
 	struct LastAccess
 	{
-		Vulkan::Event event = nullptr;
-		Vulkan::Stream stream = nullptr;
+		Vulkan::Event write_event = nullptr;
+		Vulkan::Stream write_stream = nullptr;
+		Vulkan::Event stream_event[3] = { nullptr, nullptr, nullptr };
+		Vulkan::Stream stream_of[3] = { nullptr, nullptr, nullptr };
 	};
 	std::unordered_map<const void *, LastAccess> last_access; // keyed by the physical image / buffer
 	// one "pass done" event per pass per frame slot: a later frame re-recording the same event

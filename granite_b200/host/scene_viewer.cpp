@@ -280,8 +280,10 @@ void GrbhViewer::render_frame(const GrbhHostGBuffer *host, double frame_time)
 	// update_scene: jitter.step, context.set_camera, LightClusterer::refresh
 	{
 		Vulkan::ScopedHostTimer timer("frame.camera + cluster refresh");
+		// scene_viewer_application.cpp:1431-1432: the frame is rendered (and clustered, and lit) with the
+		// jittered projection; the reprojection keeps the unjittered history (temporal.cpp:239-243)
 		jitter.step(projection, view);
-		context.set_camera(projection, view);
+		context.set_camera(jitter.get_jittered_projection(), view);
 		cluster.refresh(context);
 	}
 
@@ -615,11 +617,28 @@ extern "C" int32_t grbh_viewer_sync(GrbhViewer *v)
 {
 	if (!v)
 		return fail("null viewer");
+	if (!v->device)
+		return fail("grbh_viewer_sync: host-only viewer (no CUDA device)");
+	GRBH_TRY
 	v->device->wait_idle();
 	cudaError_t err = cudaGetLastError();
 	if (err != cudaSuccess)
 		return fail(cudaGetErrorString(err));
 	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_get_taa_reprojection(GrbhViewer *v, float *out16)
+{
+	if (!v || !out16)
+		return fail("grbh_viewer_get_taa_reprojection: bad arguments");
+	GRBH_TRY
+	// the matrix the taa-resolve pass pushed for the LAST rendered frame (temporal.cpp:239-243)
+	mat4 reproj = translate(vec3(0.5f, 0.5f, 0.0f)) * scale(vec3(0.5f, 0.5f, 1.0f)) * v->jitter.get_history_view_proj(1) *
+	              v->jitter.get_history_inv_view_proj(0);
+	std::memcpy(out16, reproj.data(), 16 * sizeof(float));
+	return 0;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_viewer_get_image(GrbhViewer *v, const char *name, GrbImage *out)

@@ -384,6 +384,12 @@ class Viewer:
         _check(lib().grbh_viewer_get_camera(self._h, C.byref(cam), _vp(proj), _vp(inv_proj)), "grbh_viewer_get_camera")
         return cam, proj.reshape(4, 4), inv_proj.reshape(4, 4)
 
+    def taa_reprojection(self) -> np.ndarray:
+        """clip(now) -> UV(previous frame) of the last rendered frame (4x4, column-major rows as stored)."""
+        out = np.zeros(16, np.float32)
+        _check(lib().grbh_viewer_get_taa_reprojection(self._h, _vp(out)), "grbh_viewer_get_taa_reprojection")
+        return out.reshape(4, 4)
+
     def measure_row_cost(self) -> np.ndarray:
         """Estimated lighting work (warp instructions) per group of 4 rows of the frame rendered last;
         unsharded viewers only (grbh_viewer_measure_row_cost)."""

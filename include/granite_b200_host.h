@@ -129,6 +129,9 @@ int32_t grbh_viewer_get_cluster(GrbhViewer *viewer, GrbClusterParameters *params
 int32_t grbh_viewer_get_light_prep(GrbhViewer *viewer, GrbPositionalLight *records, float *model_rows, uint32_t *type_mask, uint32_t *z_ranges,
                                    int32_t capacity);
 int32_t grbh_viewer_get_camera(GrbhViewer *viewer, GrbCamera *out, float *projection16, float *inv_projection16);
+/* clip(now) -> UV(previous frame) as the taa-resolve pass of the last rendered frame used it
+ * (renderer/post/temporal.cpp:239-243: unjittered history matrices). */
+int32_t grbh_viewer_get_taa_reprojection(GrbhViewer *viewer, float *out16);
 /* Names of the baked passes, '\n' separated. Returns the length needed. */
 int32_t grbh_viewer_get_pass_names(GrbhViewer *viewer, char *buffer, int32_t capacity);
 /* Per-pass GPU time of the frames since the last call (needs config.timestamps):

@@ -148,28 +148,25 @@ def test_taa_fxaa_chain(cuda, oracle, w, h, n):
     v = _make_viewer(scene, lights, post_aa=viewer.AA_TAA_HIGH_PLUS_FXAA)
     assert v.pass_names() == ["gbuffer", "clustering-bindless", "lighting", "mv", "taa-resolve", "bloom-compute", "tonemap", "fxaa"]
     gb, keep = _host_gb(scene, mv32)
-    cam, prep = common.build_case_for_viewer(oracle, v, scene, lights)
-
-    clus = oracle.cluster_build(cam, prep)
-    hdr = oracle.deferred_lighting(scene, cam, prep, clus)
-    got_hdr = None
     hist = None
     lum = np.zeros(3, np.float32)
     d3_hist = None
     out = np.zeros((h, w), np.uint32)
-    # camera is static: reproj = T*S*VP*inv(VP); take the matrix the host layer itself uses by
-    # building it from the same camera block (inverse() differs from the oracle's by an ulp)
-    vcam, _, _ = v.camera()
-    vp = np.array(list(vcam.view_projection), np.float32).reshape(4, 4)
-    ivp = np.array(list(vcam.inv_view_projection), np.float32).reshape(4, 4)
-    ts = np.array([[0.5, 0, 0, 0], [0, 0.5, 0, 0], [0, 0, 1, 0], [0.5, 0.5, 0, 1]], np.float32)
-    reproj = oracle.mat4_mul(oracle.mat4_mul(ts, vp), ivp)
+    cameras = []
     for i in range(3):
         v.render_frame(gb)
         v.read_output(out)
-        if got_hdr is None:
-            got_hdr = v.download_image("HDR-main")
-            assert common.max_code_diff_r11g11b10(got_hdr, hdr) <= 1
+        # The frame is clustered and lit with the JITTERED projection of this frame
+        # (scene_viewer_application.cpp:1431-1432); the history is reprojected with the unjittered
+        # matrices (temporal.cpp:239-243).  Both are taken from the host layer (its mat4 inverse differs
+        # from the oracle's by an ulp, and matrices are inputs of the path).
+        cam, prep = common.build_case_for_viewer(oracle, v, scene, lights)
+        cameras.append(np.array(list(cam.view_projection), np.float32))
+        clus = oracle.cluster_build(cam, prep)
+        hdr = oracle.deferred_lighting(scene, cam, prep, clus)
+        got_hdr = v.download_image("HDR-main")
+        assert common.max_code_diff_r11g11b10(got_hdr, hdr) <= 1, f"frame {i}"
+        reproj = v.taa_reprojection()
         # oracle continues from the GPU's own lit image so TAA/FXAA parity is isolated from lighting ulps
         res_c, res_h = oracle.taa_resolve(got_hdr, scene.depth, mv.view(np.uint16), hist, reproj, 2)
         hist = res_h
@@ -180,6 +177,8 @@ def test_taa_fxaa_chain(cuda, oracle, w, h, n):
         assert common.max_code_diff_r11g11b10(got_res, res_c) <= 1, f"frame {i}"
         d = common.rgba8_channel_diff(out, ldr)
         assert (d <= 1).mean() > 0.999, f"frame {i}"
+    # the 16-phase jitter moves the projection every frame
+    assert not np.array_equal(cameras[0], cameras[1]) and not np.array_equal(cameras[1], cameras[2])
     v.close()
 
 
