@@ -18,13 +18,53 @@ void set_last_error(const char *msg)
 	std::snprintf(t_last_error, sizeof(t_last_error), "%s", msg ? msg : "");
 }
 
+// Device-side failures that no CUDA error code reports (a bounded spin that ran out) are written by
+// the kernel into a word of mapped pinned host memory, one per device, allocated by grb_init.  Every
+// entry point ends in check_launch, which reads the word without synchronising: the call after the
+// failing kernel has run returns GRB_ERR_CUDA with the decoded reason.
+struct DeviceErrorWord
+{
+	volatile uint32_t *host = nullptr;
+	uint32_t *device = nullptr;
+};
+static DeviceErrorWord g_error_words[64];
+static std::mutex g_error_lock;
+
+uint32_t *device_error_word()
+{
+	int device = -1;
+	if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64)
+		return nullptr;
+	return g_error_words[device].device;
+}
+
+static int32_t poll_device_error(const char *what)
+{
+	int device = -1;
+	if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64)
+		return GRB_OK;
+	volatile uint32_t *w = g_error_words[device].host;
+	if (!w || *w == 0u)
+		return GRB_OK;
+	const uint32_t code = *w;
+	*w = 0u; // reported once
+	if ((code >> 24) == GRB_DEVICE_ERROR_PEER_TIMEOUT)
+		std::snprintf(t_last_error, sizeof(t_last_error), "%s: an earlier grb_peer_wait timed out waiting for rank %u's band (frame epoch %u, low 16 bits); the "
+		              "frame that followed used stale data", what, (code >> 16) & 0xffu, code & 0xffffu);
+	else
+		std::snprintf(t_last_error, sizeof(t_last_error), "%s: device-side error word 0x%08x", what, code);
+	return GRB_ERR_CUDA;
+}
+
 int32_t check_launch(const char *what)
 {
 	cudaError_t err = cudaGetLastError();
-	if (err == cudaSuccess)
-		return GRB_OK;
-	std::snprintf(t_last_error, sizeof(t_last_error), "%s: %s", what, cudaGetErrorString(err));
-	return GRB_ERR_CUDA;
+	if (err != cudaSuccess)
+	{
+		std::snprintf(t_last_error, sizeof(t_last_error), "%s: %s", what, cudaGetErrorString(err));
+		return GRB_ERR_CUDA;
+	}
+	return poll_device_error(what);
 }
 
 int32_t upload_srgb_lut(const float *lut256); // grb_lighting.cu
@@ -73,5 +113,17 @@ extern "C" int32_t grb_init(void)
 	}
 	static std::mutex lock;
 	std::lock_guard<std::mutex> hold(lock);
+	if (device < 64 && !grb::g_error_words[device].host)
+	{
+		void *host = nullptr, *dev = nullptr;
+		if (cudaHostAlloc(&host, sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dev, host, 0) == cudaSuccess)
+		{
+			*static_cast<uint32_t *>(host) = 0u;
+			grb::g_error_words[device].host = static_cast<volatile uint32_t *>(host);
+			grb::g_error_words[device].device = static_cast<uint32_t *>(dev);
+		}
+		else
+			cudaGetLastError(); // the error word is optional: without it a timeout is only printed
+	}
 	return grb::upload_srgb_lut(lut);
 }

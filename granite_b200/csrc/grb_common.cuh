@@ -19,6 +19,9 @@ namespace grb
 // ---------------------------------------------------------------------------------------
 void set_last_error(const char *msg);
 int32_t check_launch(const char *what);
+// mapped host word of the current device for device-side failures (null before grb_init)
+uint32_t *device_error_word();
+constexpr uint32_t GRB_DEVICE_ERROR_PEER_TIMEOUT = 1u; // word = code << 24 | rank << 16 | (epoch & 0xffff)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -604,6 +605,22 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 5) deferred_lighting2_kerne
 //     blocks simply draws more.
 constexpr int kPWarps = 16;
 constexpr int kListCap = 160; // light list entries per warp; shaded in batches when it fills up
+constexpr int kMaxOrderRows = 2048; // block rows whose schedule fits in shared memory (images up to 8192 rows)
+
+#ifdef GRB_LIGHTING_DEBUG
+constexpr int kDbgBlocks = 240 * 540;
+__device__ uint2 g_dbg_block[kDbgBlocks];   // (cycles, start ns since this warp's start)
+__device__ uint2 g_dbg_warp_end[256 * 16];  // (warp start ns low bits, ns from warp start to warp end)
+__device__ unsigned long long g_dbg_t0;
+__device__ unsigned g_dbg_warp_items[256 * 16];
+__device__ uint2 g_dbg_warp_last[256 * 16][8]; // ring of the last 8 (item, fetch time ns) per warp
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#endif
 
 struct QueueSlot
 {
@@ -615,8 +632,9 @@ __device__ QueueSlot g_light_queue[64];
 struct PersistentArgs
 {
 	QueueSlot *queue;
-	int blocks_x, blocks_y, strip_rows, total_items; // strip_rows = ceil(blocks_y / 8), total_items = 8 * strip_rows * blocks_x
+	int blocks_x, blocks_y, total_items; // total_items = blocks_x * blocks_y
 	int n_lights;
+	uint32_t *schedule; // optional: [blocks_x, blocks_y, valid, 0][cost per block row][block rows by falling cost]
 	unsigned rec_bytes; // n_lights * 48, multiple of 16
 	int use_bulk_copy;
 };
@@ -701,6 +719,7 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 	const unsigned lists_bytes = (kPWarps * (kListCap + 2) * 2u + 15u) & ~15u;
 	unsigned char *s_prefetch = smem_raw + rec_total + 1024u + lists_bytes; // 48 B per thread
 	uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_prefetch + 32u * kPWarps * 48u);
+	uint16_t *s_order = reinterpret_cast<uint16_t *>(s_bar + 2); // kMaxOrderRows entries
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t bar = smem_u32(s_bar);
@@ -715,6 +734,14 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 	}
 	for (int i = threadIdx.x; i < 256; i += blockDim.x)
 		s_srgb[i] = g_srgb8_to_linear[i];
+	// Block rows in the order of falling cost, as measured by the previous launch on the same
+	// schedule buffer (longest-processing-time-first: the queue then ends on the cheapest rows and
+	// no warp is left holding an expensive block while the others have run dry).
+	const bool scheduled = a.schedule && a.blocks_y <= kMaxOrderRows && a.schedule[0] == (uint32_t)a.blocks_x &&
+	                       a.schedule[1] == (uint32_t)a.blocks_y && a.schedule[2] == 1u;
+	if (scheduled)
+		for (int i = threadIdx.x; i < a.blocks_y; i += blockDim.x)
+			s_order[i] = (uint16_t)a.schedule[4 + a.blocks_y + i];
 	__syncthreads();
 	if (a.use_bulk_copy)
 	{
@@ -746,38 +773,50 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 	const unsigned total = (unsigned)a.total_items;
 	const unsigned n_warps = gridDim.x * kPWarps;
 
-	// Work items: the image is cut into 8 horizontal strips and item i is block (i / 8) of strip
-	// (i % 8): the 8 items of a chunk lie in 8 different strips, so the light-dense rows (a few
-	// percent of the rows hold half of the light evaluations) are dealt out one block per chunk
-	// instead of eight in a row to the same warp.  Chunks of 8 items while plenty are left, single
-	// items at the end.  Returns false when the queue is drained.
-	unsigned next = 0, end = 0;
-	auto fetch_item = [&](int &bx, int &by) -> bool {
-		for (;;)
+	// Work items are pixel blocks, row by row in schedule order, handed out in chunks of up to 4
+	// (guided: single blocks near the end).  The atomic for the NEXT chunk is issued when the last
+	// block of the current chunk is taken, so its round trip to L2 overlaps that block's shading.
+	unsigned next = 0, end = 0, pend_got = 0, pend_want = 0, last_seen = 0;
+	bool pending = false;
+	auto issue_grab = [&]() {
+		if (lane == 0)
 		{
-			if (next >= end)
-			{
-				unsigned got = 0, want = 1;
-				if (lane == 0)
-				{
-					const unsigned seen = *reinterpret_cast<volatile unsigned *>(&a.queue->next_block);
-					want = (seen < total && total - seen > 16u * n_warps) ? 8u : 1u;
-					got = atomicAdd(&a.queue->next_block, want);
-				}
-				got = __shfl_sync(0xffffffffu, got, 0);
-				want = __shfl_sync(0xffffffffu, want, 0);
-				if (got >= total)
-					return false;
-				next = got;
-				end = min(got + want, total);
-			}
-			const unsigned item = next++;
-			const unsigned g = item >> 3, strip = item & 7u;
-			bx = (int)(g % (unsigned)a.blocks_x);
-			by = (int)(strip * (unsigned)a.strip_rows + g / (unsigned)a.blocks_x);
-			if (by < a.blocks_y)
-				return true;
+			const unsigned left = last_seen < total ? total - last_seen : 0u;
+			pend_want = min(max(left / (16u * n_warps), 1u), 4u);
+			pend_got = atomicAdd(&a.queue->next_block, pend_want);
 		}
+		pending = true;
+	};
+	auto fetch_item = [&](int &bx, int &by) -> bool {
+		if (next >= end)
+		{
+			if (!pending)
+				issue_grab();
+			const unsigned got = __shfl_sync(0xffffffffu, pend_got, 0), want = __shfl_sync(0xffffffffu, pend_want, 0);
+			pending = false;
+			last_seen = got + want;
+			if (got >= total)
+				return false;
+			next = got;
+			end = min(got + want, total);
+		}
+		const unsigned item = next++;
+		// no reservation ahead of time near the end of the queue: an item reserved by a warp that is
+		// still busy is an item no idle warp can take
+		if (next >= end && last_seen + 6u * n_warps < total)
+			issue_grab();
+#ifdef GRB_LIGHTING_DEBUG
+		if (lane == 0)
+		{
+			const unsigned wid = blockIdx.x * kPWarps + warp;
+			g_dbg_warp_items[wid]++;
+			g_dbg_warp_last[wid][g_dbg_warp_items[wid] & 7u] = make_uint2(item, (uint32_t)(globaltimer_ns() - g_dbg_t0));
+		}
+#endif
+		const unsigned row = item / (unsigned)a.blocks_x;
+		bx = (int)(item - row * (unsigned)a.blocks_x);
+		by = scheduled ? (int)s_order[row] : (int)row;
+		return true;
 	};
 	// The G-buffer words of the NEXT block are copied asynchronously (cp.async, no registers held)
 	// into this lane's 48-byte slot while the current block is shaded: the HBM round trip at the head
@@ -797,12 +836,19 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 		asm volatile("cp.async.commit_group;" ::: "memory");
 	};
 
+#ifdef GRB_LIGHTING_DEBUG
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+		g_dbg_t0 = globaltimer_ns();
+	const unsigned long long s_t0 = globaltimer_ns();
+#endif
 	int bx = 0, by = 0;
 	bool have = fetch_item(bx, by);
 	if (have)
 		prefetch_gbuffer(bx, by);
 	while (have)
 	{
+		const long long t_begin = clock64();
+		const int cur_by = by;
 		const int x = (bx * 8 + (lane & 7)) * 2;
 		const int y = p.y0 + by * 4 + (lane >> 3);
 		const bool inside = x < p.hdr.w && y < p.y1;
@@ -929,7 +975,6 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			bmax_x = fkey_inv(__reduce_max_sync(0xffffffffu, hx)); bmax_y = fkey_inv(__reduce_max_sync(0xffffffffu, hy));
 			bmax_z = fkey_inv(__reduce_max_sync(0xffffffffu, hz));
 		}
-
 		if (!table_ready)
 		{
 			// the light table (bulk copy issued at kernel start) must have landed before its first use
@@ -988,9 +1033,11 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			if (lane == 0)
 				list[count] = (uint16_t)dummy_entry; // pads an odd batch
 			__syncwarp();
+			uint32_t two_next = *reinterpret_cast<const uint32_t *>(list);
 			for (int e = 0; e < count; e += 2)
 			{
-				const uint32_t two = *reinterpret_cast<const uint32_t *>(list + e);
+				const uint32_t two = two_next;
+				two_next = *reinterpret_cast<const uint32_t *>(list + e + 2); // in bounds: the list has room for kListCap + 2 entries
 				const unsigned i0 = two & 0x7fffu, i1 = (two >> 16) & 0x7fffu;
 				const bool spot0 = (two & 0x8000u) != 0u, spot1 = (two & 0x80000000u) != 0u;
 				const float4 a0 = s_rec[3u * i0], a1 = s_rec[3u * i0 + 1u], a2 = s_rec[3u * i0 + 2u];
@@ -1033,8 +1080,22 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			if (A.lit || B.lit || p.emissive.p != p.hdr.p)
 				*reinterpret_cast<uint2 *>(&p.hdr.at(x, y)) = out;
 		}
+		if (a.schedule && lane == 0)
+			atomicAdd(&a.schedule[4 + cur_by], (uint32_t)((clock64() - t_begin) >> 5));
+#ifdef GRB_LIGHTING_DEBUG
+		if (lane == 0)
+		{
+			const int bi = cur_by * a.blocks_x + (x >> 4);
+			if (bi < kDbgBlocks)
+				g_dbg_block[bi] = make_uint2((uint32_t)(clock64() - t_begin), (uint32_t)(globaltimer_ns() - s_t0));
+		}
+#endif
 	}
 
+#ifdef GRB_LIGHTING_DEBUG
+	if (lane == 0)
+		g_dbg_warp_end[blockIdx.x * kPWarps + warp] = make_uint2((uint32_t)(s_t0 & 0xffffffffu), (uint32_t)(globaltimer_ns() - s_t0));
+#endif
 	if (!table_ready)
 	{
 		// never leave with the bulk copy still in flight towards this CTA's shared memory
@@ -1043,16 +1104,57 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(bar) : "memory");
 	}
 	__syncthreads();
+	// The last CTA to finish re-arms the queue slot for its next launch and turns this launch's row
+	// costs into the next launch's schedule (rank sort; the light table's shared memory is free now).
+	uint32_t *s_flag = reinterpret_cast<uint32_t *>(s_bar + 1);
 	if (threadIdx.x == 0)
 	{
-		// the last CTA to finish re-arms the queue slot for its next launch
 		__threadfence();
-		if (atomicAdd(&a.queue->ctas_done, 1u) == gridDim.x - 1u)
+		const bool last = atomicAdd(&a.queue->ctas_done, 1u) == gridDim.x - 1u;
+		if (last)
 		{
 			a.queue->next_block = 0u;
 			a.queue->ctas_done = 0u;
 			__threadfence();
 		}
+		*s_flag = last ? 1u : 0u;
+	}
+	__syncthreads();
+	if (*s_flag && a.schedule && a.blocks_y <= kMaxOrderRows && (size_t)a.blocks_y * 4u <= (size_t)rec_total)
+	{
+		uint32_t *s_cost = reinterpret_cast<uint32_t *>(smem_raw);
+		volatile uint32_t *cost = a.schedule + 4;
+		for (int i = threadIdx.x; i < a.blocks_y; i += blockDim.x)
+			s_cost[i] = cost[i];
+		__syncthreads();
+		for (int i = threadIdx.x; i < a.blocks_y; i += blockDim.x)
+		{
+			const uint32_t mine = s_cost[i];
+			int rank = 0;
+			for (int j = 0; j < a.blocks_y; j++)
+			{
+				const uint32_t c = s_cost[j];
+				rank += (c > mine || (c == mine && j < i)) ? 1 : 0;
+			}
+			a.schedule[4 + a.blocks_y + rank] = (uint32_t)i;
+			a.schedule[4 + i] = 0u;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			a.schedule[0] = (uint32_t)a.blocks_x;
+			a.schedule[1] = (uint32_t)a.blocks_y;
+			a.schedule[2] = 1u;
+			__threadfence();
+		}
+	}
+	else if (*s_flag && a.schedule)
+	{
+		// too many rows for the in-kernel sort: raster order next time, costs cleared
+		for (int i = threadIdx.x; i < a.blocks_y; i += blockDim.x)
+			a.schedule[4 + i] = 0u;
+		if (threadIdx.x == 0)
+			a.schedule[2] = 0u;
 	}
 }
 
@@ -1156,8 +1258,38 @@ int32_t upload_srgb_lut(const float *lut256)
 
 using namespace grb;
 
+#ifdef GRB_LIGHTING_DEBUG
+extern "C" int32_t grb_debug_lighting_dump(void *blocks, void *warps)
+{
+	cudaDeviceSynchronize();
+	cudaMemcpyFromSymbol(blocks, g_dbg_block, sizeof(uint2) * kDbgBlocks);
+	cudaMemcpyFromSymbol(warps, g_dbg_warp_end, sizeof(uint2) * 256 * 16);
+	return 0;
+}
+extern "C" int32_t grb_debug_lighting_dump2(void *items, void *last)
+{
+	cudaMemcpyFromSymbol(items, g_dbg_warp_items, sizeof(unsigned) * 256 * 16);
+	cudaMemcpyFromSymbol(last, g_dbg_warp_last, sizeof(uint2) * 256 * 16 * 8);
+	static unsigned zero[256 * 16];
+	cudaMemcpyToSymbol(g_dbg_warp_items, zero, sizeof(zero));
+	return 0;
+}
+#endif
+
+extern "C" uint64_t grb_lighting_schedule_bytes(int32_t height)
+{
+	const uint64_t rows = (uint64_t)((height > 0 ? height : 0) + 3) / 4;
+	return (4u + 2u * rows) * sizeof(uint32_t);
+}
+
 extern "C" int32_t grb_deferred_lighting(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
                                          const GrbImage *hdr, GrbRows rows, void *stream)
+{
+	return grb_deferred_lighting_scheduled(g, cam, params, buf, hdr, rows, nullptr, stream);
+}
+
+extern "C" int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params,
+                                                   const GrbClusterBuffers *buf, const GrbImage *hdr, GrbRows rows, void *schedule, void *stream)
 {
 	if (!g || !cam || !params || !buf || !hdr)
 	{
@@ -1277,13 +1409,13 @@ extern "C" int32_t grb_deferred_lighting(const GrbGBuffer *g, const GrbCamera *c
 		PersistentArgs a;
 		a.blocks_x = (w / 2 + 7) / 8;
 		a.blocks_y = (rows.y1 - rows.y0 + 3) / 4;
-		a.strip_rows = (a.blocks_y + 7) / 8;
-		a.total_items = 8 * a.strip_rows * a.blocks_x;
+		a.total_items = a.blocks_x * a.blocks_y;
+		a.schedule = static_cast<uint32_t *>(schedule);
 		a.n_lights = params->num_lights;
 		a.rec_bytes = (unsigned)params->num_lights * 48u;
 		a.use_bulk_copy = (reinterpret_cast<uintptr_t>(buf->lights) % 16) == 0 ? 1 : 0;
 		a.queue = di.queue + (di.next_slot.fetch_add(1u, std::memory_order_relaxed) % 64u);
-		const size_t smem = (size_t)a.rec_bytes + 48u + 1024u + ((kPWarps * (kListCap + 2) * 2u + 15u) & ~15u) + 32u * kPWarps * 48u + 16u;
+		const size_t smem = (size_t)a.rec_bytes + 48u + 1024u + ((kPWarps * (kListCap + 2) * 2u + 15u) & ~15u) + 32u * kPWarps * 48u + 16u + kMaxOrderRows * 2u;
 		if (smem <= (size_t)di.smem_max)
 		{
 			const int ctas = std::min(di.sm_count, std::max(1, (a.blocks_x * a.blocks_y + kPWarps - 1) / kPWarps));

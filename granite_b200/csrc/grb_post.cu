@@ -10,6 +10,7 @@
 #include "grb_common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace grb
 {
@@ -168,16 +169,21 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) bloom_downsample_peers_kerne
 }
 
 // One thread per producing rank spins until that rank's band of frame `epoch` has landed here.
-__global__ void peer_wait_kernel(const uint32_t *flags, int count, uint32_t epoch)
+__global__ void peer_wait_kernel(const uint32_t *flags, int count, uint32_t epoch, uint32_t *error_word, unsigned max_spins)
 {
 	if ((int)threadIdx.x < count)
 	{
 		// bounded (~4 s): a rank that died must not hang the GPUs of the others
 		for (unsigned spins = 0; (int32_t)(load_acquire_system(flags + threadIdx.x) - epoch) < 0; spins++)
 		{
-			if (spins > (1u << 25))
+			if (spins > max_spins)
 			{
 				printf("granite_b200: timed out waiting for rank %d's band of frame %u\n", (int)threadIdx.x, epoch);
+				if (error_word) // picked up by the next grb_* call on this device (check_launch)
+				{
+					*reinterpret_cast<volatile uint32_t *>(error_word) = (GRB_DEVICE_ERROR_PEER_TIMEOUT << 24) | ((uint32_t)threadIdx.x << 16) | (epoch & 0xffffu);
+					__threadfence_system();
+				}
 				break;
 			}
 			__nanosleep(128);
@@ -812,7 +818,11 @@ extern "C" int32_t grb_peer_wait(const uint32_t *local_flags, int32_t count, uin
 		set_last_error("grb_peer_wait: bad arguments");
 		return GRB_ERR_INVALID_ARGUMENT;
 	}
-	peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(local_flags, count, epoch);
+	// ~4 s by default; GRB_PEER_WAIT_SPINS shortens the bound (tests of the timeout path)
+	unsigned max_spins = 1u << 25;
+	if (const char *e = getenv("GRB_PEER_WAIT_SPINS"))
+		max_spins = (unsigned)strtoul(e, nullptr, 10);
+	peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(local_flags, count, epoch, device_error_word(), max_spins);
 	return check_launch("grb_peer_wait");
 }
 

@@ -113,9 +113,19 @@ class GBufferDevice:
         self.struct = g
 
 
-def deferred_lighting(gb: GBufferDevice, cam: capi.GrbCamera, cluster: ClusterDevice, hdr: torch.Tensor, rows=None):
+def lighting_schedule(height: int) -> torch.Tensor:
+    """Zero-initialised schedule buffer for grb_deferred_lighting_scheduled (kept across frames)."""
+    return torch.zeros(int(capi.lib().grb_lighting_schedule_bytes(height)) // 4, dtype=torch.int32, device="cuda")
+
+
+def deferred_lighting(gb: GBufferDevice, cam: capi.GrbCamera, cluster: ClusterDevice, hdr: torch.Tensor, rows=None, schedule=None):
     """hdr: int32 (H, W) tensor holding the emissive / HDR-main attachment; updated in place."""
     img = capi.image(hdr, capi.FORMAT_B10G11R11_UFLOAT)
+    if schedule is not None:
+        capi.check(capi.lib().grb_deferred_lighting_scheduled(C.byref(gb.struct), C.byref(cam), C.byref(cluster.params), C.byref(cluster.buffers),
+                                                              C.byref(img), capi.rows(rows), _ptr(schedule), capi.stream_ptr()),
+                   "grb_deferred_lighting_scheduled")
+        return
     capi.check(capi.lib().grb_deferred_lighting(C.byref(gb.struct), C.byref(cam), C.byref(cluster.params), C.byref(cluster.buffers),
                                                 C.byref(img), capi.rows(rows), capi.stream_ptr()), "grb_deferred_lighting")
 

@@ -154,14 +154,28 @@ void LightClusterer::refresh_bindless_prepare(const RenderContext &ctx)
 	if (scene_lights)
 	{
 		const size_t n = scene_lights->size();
-		// start from last frame's order: with coherent motion it is already sorted and the
-		// stable sort below is skipped (a stable sort of an already ordered sequence would not
-		// change it, so the result is the same as sorting from scratch... provided ties keep
-		// input order, which is why the identity order is the reset state)
-		if (order.size() != n)
+		// gather_positional_lights (renderer/scene.cpp:333-358): only lights whose world-space AABB
+		// passes the visibility frustum reach the sort.  Last frame's order is the starting point:
+		// with coherent motion it is already sorted and the sort below is skipped (ties keep input
+		// order, so sorting from the previous order and sorting from scratch agree).
+		const Frustum &frustum = ctx.get_visibility_frustum();
+		visible.resize(n);
+		size_t n_visible = 0;
+		for (size_t i = 0; i < n; i++)
 		{
-			order.resize(n);
-			std::iota(order.begin(), order.end(), 0u);
+			const auto &l = (*scene_lights)[i];
+			visible[i] = !frustum_culling || frustum.intersects_fast(l.light->get_static_aabb().transform(l.transform));
+			n_visible += visible[i] ? 1 : 0;
+		}
+		bool same_set = order.size() == n_visible;
+		for (size_t i = 0; same_set && i < order.size(); i++)
+			same_set = order[i] < n && visible[order[i]];
+		if (!same_set)
+		{
+			order.clear();
+			for (size_t i = 0; i < n; i++)
+				if (visible[i])
+					order.push_back((unsigned)i);
 		}
 		keys.resize(n);
 		for (size_t i = 0; i < n; i++)

@@ -41,6 +41,8 @@ public:
 
 	// The scene's positional lights (replaces the ECS gather in renderer/threaded_scene.cpp:112-153).
 	void set_scene_lights(const PositionalLightList *lights) { scene_lights = lights; }
+	// the reference always culls the light list against the camera frustum (scene.cpp:333-358)
+	void set_enable_frustum_culling(bool enable) { frustum_culling = enable; }
 
 	// RenderPassCreator surface
 	void add_render_passes(RenderGraph &graph);
@@ -68,6 +70,8 @@ public:
 private:
 	const RenderContext *context = nullptr;
 	const PositionalLightList *scene_lights = nullptr;
+	bool frustum_culling = true;
+	std::vector<uint8_t> visible;
 	unsigned resolution_x = 64, resolution_y = 32, resolution_z = 16;
 	bool enable_clustering = true;
 	bool async_compute = false;

@@ -54,6 +54,16 @@ void SpotLight::set_range(float range)
 	falloff_range = range;
 	// tan(outer half-angle): lateral extent of the cone per unit of depth
 	xy_range = std::sqrt(1.0f - outer_cone * outer_cone) / outer_cone;
+	const float reach = min(falloff_range, cutoff_range);
+	const float side = xy_range * reach;
+	aabb = AABB(vec3(-side, -side, -reach), vec3(side, side, 0.0f)); // the cone looks down -Z
+}
+
+void PointLight::set_range(float range)
+{
+	falloff_range = range;
+	const float reach = min(falloff_range, cutoff_range);
+	aabb = AABB(vec3(-reach), vec3(reach));
 }
 
 mat_affine SpotLight::build_model_matrix(const mat_affine &transform) const

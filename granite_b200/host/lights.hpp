@@ -2,6 +2,7 @@
 // renderer/lights/lights.hpp + light_info.hpp for the members the clusterer path uses.
 #pragma once
 
+#include "frustum.hpp"
 #include "math.hpp"
 #include "render_context.hpp"
 
@@ -34,11 +35,15 @@ public:
 	const vec3 &get_color() const { return color; }
 	void set_maximum_range(float range);
 	float get_maximum_range() const { return min(falloff_range, cutoff_range); }
+	// local-space bounds the scene's visibility test transforms by the node transform
+	// (renderer/lights/lights.cpp:77-89 spot, :196-201 point; renderer/scene.cpp:1130)
+	const AABB &get_static_aabb() const { return aabb; }
 
 protected:
 	vec3 color = vec3(1.0f);
 	float falloff_range = 1.0f;
 	float cutoff_range = 1e10f;
+	AABB aabb;
 	void recompute_range();
 	virtual void set_range(float range) = 0;
 
@@ -53,7 +58,7 @@ public:
 	PositionalFragmentInfo get_shader_info(const mat_affine &transform) const;
 
 private:
-	void set_range(float range) override { falloff_range = range; }
+	void set_range(float range) override;
 };
 
 class SpotLight : public PositionalLight

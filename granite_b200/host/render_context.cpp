@@ -12,6 +12,7 @@ void RenderContext::set_camera(const mat4 &projection, const mat4 &view)
 	camera.inv_projection = inverse(projection);
 	camera.inv_view = inverse(view);
 	camera.inv_view_projection = inverse(camera.view_projection);
+	frustum.build_planes(camera.inv_view_projection);
 
 	camera.camera_position = camera.inv_view[3].xyz();
 	camera.camera_up = camera.inv_view[1].xyz();

@@ -3,6 +3,7 @@
 // (directional light), and RenderContext::set_camera (renderer/render_context.cpp:54-87).
 #pragma once
 
+#include "frustum.hpp"
 #include "math.hpp"
 
 namespace Granite
@@ -49,7 +50,13 @@ public:
 	void set_camera(const mat4 &projection, const mat4 &view);
 	// Takes a parameter block computed elsewhere (e.g. by the application's own camera code)
 	// verbatim: the matrices are inputs to this path, not something it derives.
-	void set_render_parameters(const RenderParameters &params) { camera = params; }
+	void set_render_parameters(const RenderParameters &params)
+	{
+		camera = params;
+		frustum.build_planes(camera.inv_view_projection);
+	}
+	// renderer/render_context.cpp:69, render_context.hpp:108
+	const Frustum &get_visibility_frustum() const { return frustum; }
 	const RenderParameters &get_render_parameters() const { return camera; }
 	void set_frame_parameters(const FrameParameters &frame_) { frame = frame_; }
 	const FrameParameters &get_frame_parameters() const { return frame; }
@@ -58,6 +65,7 @@ public:
 
 private:
 	RenderParameters camera;
+	Frustum frustum;
 	FrameParameters frame;
 	const LightingParameters *lighting = nullptr;
 };

@@ -5,7 +5,7 @@
 namespace Granite
 {
 void DeferredLightRenderer::render_light(Vulkan::CommandBuffer &cmd, const RenderContext &context, const GBufferViews &gb, Vulkan::ImageView &hdr,
-                                         GrbRows rows)
+                                         GrbRows rows, void *schedule)
 {
 	auto *light = context.get_lighting_parameters();
 	if (!light || !gb.albedo || !gb.normal || !gb.pbr || !gb.depth)
@@ -43,8 +43,6 @@ void DeferredLightRenderer::render_light(Vulkan::CommandBuffer &cmd, const Rende
 
 	GrbClusterParameters params = {};
 	GrbClusterBuffers buffers = {};
-	uint32_t empty_range[2] = { 0xffffffffu, 0u };
-	(void)empty_range;
 	if (light->cluster && light->cluster->get_cluster_bitmask_buffer())
 	{
 		params = light->cluster->get_cluster_parameters_bindless();
@@ -56,7 +54,7 @@ void DeferredLightRenderer::render_light(Vulkan::CommandBuffer &cmd, const Rende
 		return;
 	}
 	GrbImage hdr_img = hdr.as_grb();
-	cmd.check(grb_deferred_lighting(&g, &cam, &params, &buffers, &hdr_img, rows, cmd.get_stream_handle()), "grb_deferred_lighting");
+	cmd.check(grb_deferred_lighting_scheduled(&g, &cam, &params, &buffers, &hdr_img, rows, schedule, cmd.get_stream_handle()), "grb_deferred_lighting");
 }
 
 void DeferredLightingPass::setup_dependencies(RenderPass &self, RenderGraph &graph_)
@@ -88,6 +86,7 @@ void DeferredLightingPass::build_render_pass(Vulkan::CommandBuffer &cmd)
 	if (res_emissive)
 		gb.emissive = &graph->get_physical_texture_resource(*res_emissive);
 	auto &hdr = graph->get_physical_texture_resource(*res_hdr);
-	DeferredLightRenderer::render_light(cmd, context, gb, hdr, graph->is_sharded() ? graph->get_shard_plan().lighting : GrbRows{ 0, 0 });
+	void *schedule = res_schedule ? graph->get_physical_buffer_resource(*res_schedule).get_device_pointer() : nullptr;
+	DeferredLightRenderer::render_light(cmd, context, gb, hdr, graph->is_sharded() ? graph->get_shard_plan().lighting : GrbRows{ 0, 0 }, schedule);
 }
 } // namespace Granite

@@ -25,8 +25,9 @@ class DeferredLightRenderer
 {
 public:
 	// Adds directional + clustered lighting into `hdr` (in place; HDR-main aliases emissive).
+	// schedule: optional device buffer of grb_lighting_schedule_bytes(height) bytes kept across frames
 	static void render_light(Vulkan::CommandBuffer &cmd, const RenderContext &context, const GBufferViews &gbuffer,
-	                         Vulkan::ImageView &hdr, GrbRows rows);
+	                         Vulkan::ImageView &hdr, GrbRows rows, void *schedule = nullptr);
 };
 
 // The "lighting" pass: reads albedo/normal/pbr/depth attachments + the cluster buffers, writes
@@ -46,10 +47,12 @@ private:
 	RenderGraph *graph = nullptr;
 	RenderTextureResource *res_albedo = nullptr, *res_normal = nullptr, *res_pbr = nullptr, *res_depth = nullptr, *res_hdr = nullptr;
 	RenderTextureResource *res_emissive = nullptr;
+	RenderBufferResource *res_schedule = nullptr;
 	unsigned halo_rows = 0;
 
 public:
 	// extra rows around a row shard that downstream passes (bloom threshold, FXAA) read
 	void set_shard_halo(unsigned rows) { halo_rows = rows; }
+	void set_schedule(RenderBufferResource &schedule) { res_schedule = &schedule; }
 };
 } // namespace Granite

@@ -175,8 +175,14 @@ void GrbhViewer::bake_render_graph()
 	auto &in_pbr = lighting_pass.add_attachment_input("pbr");
 	auto &in_depth = lighting_pass.add_attachment_input("depth-transient");
 	lighting_pass.set_depth_stencil_input("depth-transient");
+	// work schedule of the lighting kernel: row costs of this frame order the next frame's rows
+	BufferInfo schedule_info;
+	schedule_info.size = (size_t)grb_lighting_schedule_bytes(config.height);
+	schedule_info.usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT;
+	auto &schedule = lighting_pass.add_storage_output("lighting-schedule", schedule_info);
 	auto light_iface = std::make_shared<DeferredLightingPass>(context, &cluster);
 	light_iface->set_resources(graph, in_albedo, in_normal, in_pbr, in_depth, hdr_main, &in_emissive);
+	light_iface->set_schedule(schedule);
 	light_iface->set_shard_halo(uses_fxaa() ? 12u : 8u);
 	lighting_pass.set_render_pass_interface(light_iface);
 

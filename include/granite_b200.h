@@ -175,6 +175,16 @@ typedef struct GrbGBuffer
 int32_t grb_deferred_lighting(const GrbGBuffer *gbuffer, const GrbCamera *cam,
                               const GrbClusterParameters *params, const GrbClusterBuffers *buf,
                               const GrbImage *hdr, GrbRows rows, void *stream);
+/* Same pass with a caller-owned SCHEDULE buffer: grb_lighting_schedule_bytes(image height) bytes of
+ * device memory, zero-initialised once and then left alone, used by one stream at a time.  Each
+ * launch measures what every row of pixel blocks cost and leaves them sorted by falling cost; the
+ * next launch hands the rows out in that order (longest first), so the pass no longer ends with a
+ * few warps holding the expensive blocks.  Results are identical with or without it.  A null
+ * schedule is allowed (raster order). */
+uint64_t grb_lighting_schedule_bytes(int32_t height);
+int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *gbuffer, const GrbCamera *cam, const GrbClusterParameters *params,
+                                        const GrbClusterBuffers *buffers, const GrbImage *hdr_inout, GrbRows rows, void *schedule,
+                                        void *stream);
 
 /* Diagnostic: the (tile index, Z slice) the lighting kernel addresses for every pixel, -1 for sky
  * (clusterer_bindless.h:39-47).  Same device function as grb_deferred_lighting uses; exists so

@@ -79,6 +79,13 @@ void orc_cluster_params(const orc_camera_t *cam, int num_lights, int res_x, int 
 void orc_light_z_ranges(const orc_camera_t *cam, const orc_light_t *lights, const float *model_rows,
                         const uint32_t *type_mask, int num_lights, int res_z, uint32_t *z_ranges);
 
+/* ---- light visibility: renderer/scene.cpp:333-358 gather_positional_lights ---- */
+void orc_frustum_planes(const float *inv_view_projection16, float *planes24);                 /* math/frustum.cpp:109-156 */
+void orc_transform_aabb(const float *rows12, const float *lo3, const float *hi3, float *out_lo3, float *out_hi3); /* math/simd.hpp:386-419 */
+int orc_frustum_cull(const float *lo3, const float *hi3, const float *planes24);              /* math/simd.hpp:34-60, 1 = visible */
+int orc_light_visible(const float *planes24, int is_point, const float *color3, float cutoff_range, float outer_cone,
+                      const float *rows12);                                                    /* lights.cpp:77-89,196-201 */
+
 /* ---- clusterer kernels ---- */
 /* K1 clusterer_bindless_spot_transform.comp:33-73. out: 6 vec4 per light. */
 void orc_spot_transform(const orc_camera_t *cam, const float *model_rows, int num_lights, float *transformed_spots);

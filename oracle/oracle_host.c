@@ -370,3 +370,153 @@ uint16_t orc_f32_to_f16(float f) { return f32_to_f16_rne(f); }
 float orc_f16_to_f32(uint16_t h) { return f16_to_f32(h); }
 uint32_t orc_linear_to_srgb8(float c) { return linear_to_srgb8(c); }
 float orc_srgb8_to_linear(uint32_t v) { return srgb8_to_linear(v); }
+
+/* ---- visibility of positional lights (renderer/scene.cpp:333-358) -------------------------------
+ * A light is gathered when the world-space AABB of its static AABB passes the visibility frustum.
+ * math/frustum.cpp:109-156 Frustum::build_planes(inv_view_projection): six planes (left, right, near,
+ * far, top, bottom) through the unprojected corners, far plane dropped for an infinite projection,
+ * each flipped to face the frustum centre.  planes24 = 6 x vec4. */
+static void unproject3(const float *m, float x, float y, float z, float *out3)
+{
+	/* inv_view_projection * vec4(x, y, z, 1): muglm mat4 * vec4 = ((c0*x + c1*y) + c2*z) + c3*w  (math/muglm/muglm_impl.hpp) */
+	float r[4];
+	for (int i = 0; i < 4; i++)
+		r[i] = m[i] * x + m[4 + i] * y + m[8 + i] * z + m[12 + i] * 1.0f;
+	out3[0] = r[0] / r[3];
+	out3[1] = r[1] / r[3];
+	out3[2] = r[2] / r[3];
+}
+
+static void cross3(const float *a, const float *b, float *o)
+{
+	o[0] = a[1] * b[2] - a[2] * b[1];
+	o[1] = a[2] * b[0] - a[0] * b[2];
+	o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+static void plane_normal(const float *p0, const float *p1, const float *q0, const float *q1, float *n)
+{
+	/* normalize(cross(p0 - p1, q0 - q1)), normalize(v) = v * (1 / sqrt(dot(v, v))) */
+	float a[3] = { p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2] };
+	float b[3] = { q0[0] - q1[0], q0[1] - q1[1], q0[2] - q1[2] };
+	float c[3];
+	cross3(a, b, c);
+	float inv = 1.0f / sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+	n[0] = c[0] * inv;
+	n[1] = c[1] * inv;
+	n[2] = c[2] * inv;
+}
+
+void orc_frustum_planes(const float *inv_vp, float *planes24)
+{
+	const int infinite_z = inv_vp[15] == 0.0f;
+	const float far_z = infinite_z ? 1e-10f : 0.0f; /* FarClipInfiniteClamp, frustum.cpp:62 */
+	float TLN[3], BLN[3], BLF[3], TRN[3], TRF[3], BRN[3], BRF[3];
+	unproject3(inv_vp, -1.0f, -1.0f, 1.0f, TLN);
+	unproject3(inv_vp, -1.0f, +1.0f, 1.0f, BLN);
+	unproject3(inv_vp, -1.0f, +1.0f, far_z, BLF);
+	unproject3(inv_vp, +1.0f, -1.0f, 1.0f, TRN);
+	unproject3(inv_vp, +1.0f, -1.0f, far_z, TRF);
+	unproject3(inv_vp, +1.0f, +1.0f, 1.0f, BRN);
+	unproject3(inv_vp, +1.0f, +1.0f, far_z, BRF);
+	float center[4];
+	for (int i = 0; i < 4; i++)
+		center[i] = inv_vp[i] * 0.0f + inv_vp[4 + i] * 0.0f + inv_vp[8 + i] * 0.5f + inv_vp[12 + i] * 1.0f;
+	float l[3], r[3], n[3], f[3], t[3], b[3];
+	plane_normal(BLF, BLN, TLN, BLN, l);
+	plane_normal(TRF, TRN, BRN, TRN, r);
+	plane_normal(BLN, BRN, TRN, BRN, n);
+	plane_normal(TRF, BRF, BLF, BRF, f);
+	plane_normal(TLN, TRN, TRF, TRN, t);
+	plane_normal(BRF, BRN, BLN, BRN, b);
+	const float *normals[6] = { l, r, n, f, t, b };
+	const float *points[6] = { BLN, TRN, BRN, BRF, TRN, BRN };
+	for (int i = 0; i < 6; i++)
+	{
+		float *p = planes24 + 4 * i;
+		const float *nn = normals[i], *pt = points[i];
+		p[0] = nn[0];
+		p[1] = nn[1];
+		p[2] = nn[2];
+		p[3] = -(nn[0] * pt[0] + nn[1] * pt[1] + nn[2] * pt[2]);
+		if (i == 3 && infinite_z)
+			p[0] = p[1] = p[2] = p[3] = 0.0f;
+		/* winding: dot(center, p) < 0 => p = -p  (vec4 dot: (x + y) ... muglm dot(vec4) = a.x*b.x + a.y*b.y + a.z*b.z + a.w*b.w) */
+		float d = center[0] * p[0] + center[1] * p[1] + center[2] * p[2] + center[3] * p[3];
+		if (d < 0.0f)
+		{
+			p[0] = -p[0];
+			p[1] = -p[1];
+			p[2] = -p[2];
+			p[3] = -p[3];
+		}
+	}
+}
+
+/* math/simd.hpp:386-419 SIMD::transform_aabb(AABB&, const AABB&, const mat_affine&): per output
+ * component c: t[c] + M[c][0] * pick(x) + M[c][1] * pick(y) + M[c][2] * pick(z), added in that order;
+ * pick = hi where the matrix element is > 0 (for the maximum), lo otherwise (and vice versa). */
+void orc_transform_aabb(const float *rows12, const float *lo3, const float *hi3, float *out_lo3, float *out_hi3)
+{
+	for (int c = 0; c < 3; c++)
+	{
+		const float *row = rows12 + 4 * c;
+		float hi = row[3], lo = row[3];
+		for (int k = 0; k < 3; k++)
+		{
+			const int pos = row[k] > 0.0f;
+			hi = hi + row[k] * (pos ? hi3[k] : lo3[k]);
+			lo = lo + row[k] * (pos ? lo3[k] : hi3[k]);
+		}
+		out_hi3[c] = hi;
+		out_lo3[c] = lo;
+	}
+}
+
+/* math/simd.hpp:34-60 SIMD::frustum_cull: per plane, the corner furthest along the plane normal
+ * (hi where the plane component is > 0, w = 1); the products are summed pairwise ((x + y) + (z + w),
+ * two horizontal adds) and the box is visible when no sum has its sign bit set. */
+int orc_frustum_cull(const float *lo3, const float *hi3, const float *planes24)
+{
+	for (int i = 0; i < 6; i++)
+	{
+		const float *p = planes24 + 4 * i;
+		float d[4];
+		for (int k = 0; k < 3; k++)
+			d[k] = p[k] * (p[k] > 0.0f ? hi3[k] : lo3[k]);
+		d[3] = p[3] * 1.0f;
+		float s = (d[0] + d[1]) + (d[2] + d[3]);
+		if (signbit(s))
+			return 0;
+	}
+	return 1;
+}
+
+/* Static AABB of a light (renderer/lights/lights.cpp:77-89 SpotLight::set_range, :196-201
+ * PointLight::set_range), moved to world space by the node transform and tested: 1 = gathered. */
+int orc_light_visible(const float *planes24, int is_point, const float *color3, float cutoff_range, float outer_cone, const float *rows12)
+{
+	const float target_atten = 0.1f;
+	float max_color = f_max(f_max(color3[0], color3[1]), color3[2]);
+	float falloff_range = sqrtf(max_color / target_atten);
+	float max_range = f_min(falloff_range, cutoff_range);
+	float lo[3], hi[3];
+	if (is_point)
+	{
+		lo[0] = lo[1] = lo[2] = -max_range;
+		hi[0] = hi[1] = hi[2] = max_range;
+	}
+	else
+	{
+		float oc = f_clamp(outer_cone, 0.001f, 1.0f);
+		float xy = sqrtf(1.0f - oc * oc) / oc;
+		xy *= max_range;
+		lo[0] = lo[1] = -xy;
+		lo[2] = -max_range;
+		hi[0] = hi[1] = xy;
+		hi[2] = 0.0f;
+	}
+	float wlo[3], whi[3];
+	orc_transform_aabb(rows12, lo, hi, wlo, whi);
+	return orc_frustum_cull(wlo, whi, planes24);
+}

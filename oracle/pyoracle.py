@@ -160,8 +160,35 @@ def camera_setup(projection, view) -> Camera:
 
 
 # ---------------- light prep ----------------
-def prepare_lights(cam: Camera, lights, res=(128, 64, 4096), cutoff=1e10):
-    """Host prep: records (sorted order as given), model rows, type mask, cluster params, z ranges."""
+def visible_lights(cam: Camera, lights, cutoff=1e10):
+    """renderer/scene.cpp:333-358: boolean mask of the lights whose world AABB passes the camera's
+    visibility frustum (the list the clusterer then sorts and truncates)."""
+    L = lib()
+    L.orc_light_visible.restype = C.c_int
+    planes = np.zeros(24, np.float32)
+    ivp = np.array(list(cam.inv_view_projection), np.float32)
+    L.orc_frustum_planes(_p(ivp), _p(planes))
+    keep = np.zeros(len(lights.color), bool)
+    for i in range(len(lights.color)):
+        col = _c(lights.color[i], np.float32); pos = lights.position[i]
+        if lights.is_point[i]:
+            rows = np.array([[1, 0, 0, pos[0]], [0, 1, 0, pos[1]], [0, 0, 1, pos[2]]], np.float32)
+        else:
+            r = np.asarray(lights.rot[i], np.float32).reshape(-1)  # column-major 3x3, as the host API takes it
+            rows = np.array([[r[0], r[3], r[6], pos[0]], [r[1], r[4], r[7], pos[1]], [r[2], r[5], r[8], pos[2]]], np.float32)
+        rows = np.ascontiguousarray(rows)
+        keep[i] = bool(L.orc_light_visible(_p(planes), int(bool(lights.is_point[i])), _p(col), _f(cutoff), _f(lights.outer_cone[i]), _p(rows)))
+    return keep
+
+
+def prepare_lights(cam: Camera, lights, res=(128, 64, 4096), cutoff=1e10, cull=True):
+    """Host prep: frustum cull (scene.cpp:333-358), then records (sorted order as given), model rows,
+    type mask, cluster params, z ranges."""
+    if cull and len(lights.color):
+        keep = visible_lights(cam, lights, cutoff)
+        if not keep.all():
+            lights = type(lights)(lights.color[keep], lights.position[keep], lights.is_point[keep], lights.rot[keep],
+                                  lights.inner_cone[keep], lights.outer_cone[keep])
     n = len(lights.color)
     n32 = (n + 31) // 32
     recs = np.zeros(max(n, 1), LIGHT_DTYPE)

@@ -2,11 +2,15 @@
 // Thin extern "C" exports over the REFERENCE's own host math (math/muglm, math/transforms),
 // compiled from the sources where they lie under /root/reference into oracle/_ref/
 // (see oracle/Makefile target `ref`).  Used only to pin oracle_host.c's restatements
-// (perspective, inverse, mat4 multiply, floatToHalf, camera look_at) bit-for-bit.
+// (perspective, inverse, mat4 multiply, floatToHalf, camera look_at, frustum planes, AABB
+// transform and the frustum/AABB test of the light gather) bit-for-bit.
 // No reference source is copied into this repository.
 #include "muglm/muglm_impl.hpp"
 #include "muglm/matrix_helper.hpp"
 #include "transforms.hpp"
+#include "aabb.hpp"
+#include "frustum.hpp"
+#include "simd.hpp"
 #include <cstring>
 
 using namespace muglm;
@@ -52,5 +56,35 @@ void ref_camera_view(const float *eye, const float *at, const float *up, float *
 float ref_infinite_far_plane(void)
 {
 	return InfiniteFarPlane;
+}
+
+// math/frustum.cpp:109-156
+void ref_frustum_planes(const float *inv_vp16, float *planes24)
+{
+	mat4 m;
+	memcpy(&m, inv_vp16, 64);
+	Granite::Frustum f;
+	f.build_planes(m);
+	memcpy(planes24, f.get_planes(), 6 * 16);
+}
+
+// math/simd.hpp:386-419 (mat_affine overload): what Scene::update_cached_transforms_range applies
+void ref_transform_aabb(const float *rows12, const float *lo3, const float *hi3, float *out_lo3, float *out_hi3)
+{
+	mat_affine m;
+	memcpy(&m, rows12, 48);
+	Granite::AABB in(vec3(lo3[0], lo3[1], lo3[2]), vec3(hi3[0], hi3[1], hi3[2])), out;
+	Granite::SIMD::transform_aabb(out, in, m);
+	memcpy(out_lo3, &out.get_minimum(), 12);
+	memcpy(out_hi3, &out.get_maximum(), 12);
+}
+
+// math/simd.hpp:34-60: 1 = visible
+int ref_frustum_cull(const float *lo3, const float *hi3, const float *planes24)
+{
+	Granite::AABB box(vec3(lo3[0], lo3[1], lo3[2]), vec3(hi3[0], hi3[1], hi3[2]));
+	vec4 planes[6];
+	memcpy(planes, planes24, sizeof(planes));
+	return Granite::SIMD::frustum_cull(box, planes) ? 1 : 0;
 }
 }

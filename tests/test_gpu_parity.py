@@ -166,6 +166,17 @@ def test_deferred_lighting_parity(cuda, oracle, w, h, n, spots):
     exact = float((got == ref).mean())
     print(f"lighting exact-match fraction: {exact:.5f}")
     assert exact > 0.97
+    # the work schedule (rows by falling cost, fed back from the previous launch) only reorders the
+    # pixel blocks: every launch on the same schedule buffer reproduces the unscheduled frame
+    sched = harness.lighting_schedule(h)
+    for _ in range(3):
+        hdr_s = gb.emissive.clone()
+        harness.deferred_lighting(gb, gcam, dev, hdr_s, schedule=sched)
+        assert torch.equal(hdr, hdr_s)
+    head = sched[:4].cpu().numpy()
+    assert head[2] == 1 and head[1] == (h + 3) // 4, "the kernel publishes the next schedule"
+    order = sched[4 + (h + 3) // 4: 4 + 2 * ((h + 3) // 4)].cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange((h + 3) // 4)), "a permutation of the block rows"
     # row sharding is bit-invariant
     hdr2 = gb.emissive.clone()
     cut = (h // 3) & ~3
@@ -330,3 +341,26 @@ def test_error_reporting(cuda):
     rc = capi.lib().grb_bloom_upsample(C.byref(bad), C.byref(bad), capi.rows(), capi.stream_ptr())
     assert rc == -2
     assert b"R16G16B16A16_SFLOAT" in capi.lib().grb_last_error_string()
+
+
+def test_peer_wait_timeout_reaches_the_error_string(cuda, monkeypatch):
+    """A rank that never publishes its band must not go unnoticed: the bounded spin writes a device
+    error word and the NEXT entry point on the device returns GRB_ERR_CUDA naming the rank."""
+    from granite_b200 import capi
+
+    monkeypatch.setenv("GRB_PEER_WAIT_SPINS", "200")
+    flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+    flags[0] = 7  # rank 0 has published epoch 7, rank 1 never does
+    L = capi.lib()
+    L.grb_peer_wait.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p]
+    assert L.grb_peer_wait(C.c_void_p(flags.data_ptr()), 2, 7, capi.stream_ptr()) == 0
+    torch.cuda.synchronize()
+    bad = capi.GrbImage(None, 0, 0, 0, 0)
+    img = torch.zeros((8, 8, 4), dtype=torch.int16, device="cuda")
+    ok = capi.image(img, capi.FORMAT_R16G16B16A16_SFLOAT)
+    rc = L.grb_bloom_upsample(C.byref(ok), C.byref(ok), capi.rows(), capi.stream_ptr())
+    assert rc == -3, rc  # GRB_ERR_CUDA
+    msg = L.grb_last_error_string()
+    assert b"timed out waiting for rank 1" in msg, msg
+    # reported once: the device is usable again
+    assert L.grb_bloom_upsample(C.byref(ok), C.byref(ok), capi.rows(), capi.stream_ptr()) == 0

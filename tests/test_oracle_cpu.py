@@ -256,3 +256,39 @@ def test_row_ranges_compose(oracle):
     a = oracle.tonemap(hdr, bloom, None, 1.0, rows=(0, 17))
     b = oracle.tonemap(hdr, bloom, None, 1.0, rows=(17, 50))
     assert np.array_equal(full[:17], a[:17]) and np.array_equal(full[17:], b[17:])
+
+
+# --------------------------------------------------------------------------------------
+# light visibility (renderer/scene.cpp:333-358) pinned against the reference's math/frustum.cpp,
+# aabb.hpp and simd.hpp (oracle/_ref)
+# --------------------------------------------------------------------------------------
+def test_frustum_planes_and_box_test_match_reference(oracle):
+    r = _ref_or_skip(oracle)
+    L = oracle.lib()
+    rng = np.random.default_rng(21)
+    L.orc_frustum_cull.restype = C.c_int
+    r.ref_frustum_cull.restype = C.c_int
+    for fovy, aspect, far in [(math.pi / 4, 16 / 9, synth.FLT_MAX), (1.0, 1.0, 200.0), (0.6, 2.39, 1000.0)]:
+        proj = oracle.perspective(fovy, aspect, 1 / 16, far)
+        for eye in [(0.0, 0.0, 8.0), (3.0, 2.0, -5.0)]:
+            cam = oracle.camera_setup(proj, synth.look_at_view(eye, (0.0, 0.0, 0.0)))
+            ivp = np.array(list(cam.inv_view_projection), np.float32)
+            mine, ref = np.zeros(24, np.float32), np.zeros(24, np.float32)
+            L.orc_frustum_planes(_vp(ivp), _vp(mine))
+            r.ref_frustum_planes(_vp(ivp), _vp(ref))
+            assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+            seen = [0, 0]
+            for _ in range(400):
+                # boxes around the frustum boundary: a random affine transform of a random static box
+                rot = np.linalg.qr(rng.normal(size=(3, 3)))[0].astype(np.float32) * np.float32(rng.uniform(0.5, 2.0))
+                rows = np.concatenate([rot, rng.uniform(-60, 60, size=(3, 1)).astype(np.float32)], 1).astype(np.float32).copy()
+                lo = -rng.uniform(0.1, 12.0, 3).astype(np.float32)
+                hi = rng.uniform(0.0, 12.0, 3).astype(np.float32)
+                a_lo, a_hi, b_lo, b_hi = (np.zeros(3, np.float32) for _ in range(4))
+                L.orc_transform_aabb(_vp(rows), _vp(lo), _vp(hi), _vp(a_lo), _vp(a_hi))
+                r.ref_transform_aabb(_vp(rows), _vp(lo), _vp(hi), _vp(b_lo), _vp(b_hi))
+                assert np.array_equal(a_lo.view(np.uint32), b_lo.view(np.uint32)) and np.array_equal(a_hi.view(np.uint32), b_hi.view(np.uint32))
+                m, f = L.orc_frustum_cull(_vp(a_lo), _vp(a_hi), _vp(mine)), r.ref_frustum_cull(_vp(b_lo), _vp(b_hi), _vp(ref))
+                assert m == f
+                seen[m] += 1
+            assert seen[0] > 20 and seen[1] > 20, seen
