@@ -319,8 +319,10 @@ __global__ void __launch_bounds__(64) luminance_finalize_kernel(const float *__r
 // ------------------------------------------------------------------------------- K11
 __device__ __forceinline__ float uncharted2(float x)
 {
-	const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
-	return ((x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F)) - E / F;
+	// glslang folds C*B, D*E, D*F and E/F in double precision from the literals and rounds once:
+	// D*F = (float)0.06 = 0x3d75c28f (0.2f * 0.3f would be 0x3d75c290), E/F = (float)(0.02 / 0.30).
+	const float A = 0.15f, B = 0.50f, CB = (float)(0.10 * 0.50), DE = (float)(0.20 * 0.02), DF = (float)(0.20 * 0.30), EF = (float)(0.02 / 0.30);
+	return ((x * (A * x + CB) + DE) / (x * (A * x + B) + DF)) - EF;
 }
 
 template <bool DynamicExposure, bool SrgbTarget>
@@ -357,9 +359,9 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) tonemap_kernel(View<const ui
 // (uncharted2(x)) * white_scale with the constant term folded into one FMA
 __device__ __forceinline__ float uncharted2_fast_scaled(float x, float white_scale)
 {
-	const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
-	const float q = fmaf(x, fmaf(A, x, C * B), D * E) * rcp_fast(fmaf(x, fmaf(A, x, B), D * F));
-	return fmaf(q, white_scale, -(E / F) * white_scale);
+	const float A = 0.15f, B = 0.50f, CB = (float)(0.10 * 0.50), DE = (float)(0.20 * 0.02), DF = (float)(0.20 * 0.30), EF = (float)(0.02 / 0.30);
+	const float q = fmaf(x, fmaf(A, x, CB), DE) * rcp_fast(fmaf(x, fmaf(A, x, B), DF));
+	return fmaf(q, white_scale, -EF * white_scale);
 }
 
 __device__ __forceinline__ uint32_t srgb8_fast(float c)
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) fxaa_kernel(View<const uint3
 	float rcpDirMin = 1.0f / (fmin_(fabsf(dx), fabsf(dy)) + dirReduce);
 	dx = fclamp(dx * rcpDirMin, -FXAA_SPAN_MAX, FXAA_SPAN_MAX) * inv_w;
 	dy = fclamp(dy * rcpDirMin, -FXAA_SPAN_MAX, FXAA_SPAN_MAX) * inv_h;
-	const float k0 = 1.0f / 3.0f - 0.5f, k1 = 2.0f / 3.0f - 0.5f;
+	const float k0 = (float)(1.0 / 3.0 - 0.5), k1 = (float)(2.0 / 3.0 - 0.5); // folded by glslang in double, then rounded
 	float3 a0 = sample_unorm8(in, u + dx * k0, v + dy * k0);
 	float3 a1 = sample_unorm8(in, u + dx * k1, v + dy * k1);
 	float3 rgbA = make_float3(0.5f * (a0.x + a1.x), 0.5f * (a0.y + a1.y), 0.5f * (a0.z + a1.z));

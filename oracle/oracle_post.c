@@ -172,7 +172,12 @@ void orc_luminance(const uint16_t *d3, int w, int h, float lerp, float min_loglu
 static float uncharted2(float x)
 {
 	const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
-	return ((x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F)) - E / F;
+	/* The shader compiler (glslang) folds the constant sub-expressions C*B, D*E, D*F, E/F in DOUBLE
+	 * precision from the decimal literals and then rounds once to fp32 -- e.g. D*F = 0.06 ->
+	 * 0x3d75c28f, not 0.2f*0.3f = 0x3d75c290 (pinned by tests/test_oracle_ref_post_shaders.py). */
+	const float CB = (float)(0.10 * 0.50), DE = (float)(0.20 * 0.02), DF = (float)(0.20 * 0.30), EF = (float)(0.02 / 0.30);
+	(void)C; (void)D; (void)E; (void)F;
+	return ((x * (A * x + CB) + DE) / (x * (A * x + B) + DF)) - EF;
 }
 
 void orc_tonemap(const uint32_t *hdr, int w, int h, const uint16_t *bloom, int bw, int bh,
@@ -254,7 +259,8 @@ void orc_fxaa(const uint32_t *in, int w, int h, int target_srgb, uint32_t *out, 
 			float rcpDirMin = 1.0f / (f_min(fabsf(dx), fabsf(dy)) + dirReduce);
 			dx = f_clamp(dx * rcpDirMin, -FXAA_SPAN_MAX, FXAA_SPAN_MAX) * inv_x;
 			dy = f_clamp(dy * rcpDirMin, -FXAA_SPAN_MAX, FXAA_SPAN_MAX) * inv_y;
-			const float k0 = 1.0f / 3.0f - 0.5f, k1 = 2.0f / 3.0f - 0.5f;
+			/* folded by glslang in double precision, then rounded: +-0.16666667163372039794921875 */
+			const float k0 = (float)(1.0 / 3.0 - 0.5), k1 = (float)(2.0 / 3.0 - 0.5);
 			vec3 a0 = sample_unorm8_linear(in, w, h, u + dx * k0, v + dy * k0);
 			vec3 a1 = sample_unorm8_linear(in, w, h, u + dx * k1, v + dy * k1);
 			vec3 rgbA = v3(0.5f * (a0.x + a1.x), 0.5f * (a0.y + a1.y), 0.5f * (a0.z + a1.z));

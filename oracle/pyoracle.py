@@ -18,6 +18,9 @@ _REF_PATH = os.path.join(_HERE, "_ref", "libgranite_refmath.so")
 
 
 _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for k in (1, 2, 3, 4)]
+# post-processing shaders K7-K13 (ref_post_shim.cpp); ids as in oracle/Makefile POST_IDS
+_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43)
+_REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
 
 
 def build(ref: bool = True) -> None:
@@ -30,6 +33,8 @@ def build(ref: bool = True) -> None:
     if ref and os.path.isdir("/root/reference/third_party/spirv-cross") and os.path.isdir("/root/reference/third_party/glslang"):
         shim = os.path.join(_HERE, "ref_shader_shim.cpp")
         stale = any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(shim) for p in _REF_KERNEL_PATHS)
+        pshim = os.path.join(_HERE, "ref_post_shim.cpp")
+        stale = stale or any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(pshim) for p in _REF_POST_PATHS.values())
         if stale:
             r = subprocess.run(["make", "-s", "-j8", "-C", _HERE, "ref-shaders"], capture_output=True, text=True)
             if r.returncode != 0:  # checker infrastructure: report, never break the product build
@@ -115,6 +120,19 @@ def ref_kernels():
     if _ref_kernels is None and all(os.path.exists(p) for p in _REF_KERNEL_PATHS):
         _ref_kernels = {k: C.CDLL(p) for k, p in zip((1, 2, 3, 4), _REF_KERNEL_PATHS)}
     return _ref_kernels
+
+
+_ref_post = None
+
+
+def ref_post_kernels():
+    """{id: CDLL} of the reference's post-processing shaders (K7-K13) compiled for the CPU
+    (oracle/_ref/libgranite_ref_p*.so, see ref_post_shim.cpp), or None when they were not built."""
+    global _ref_post
+    if _ref_post is None and all(os.path.exists(p) for p in _REF_POST_PATHS.values()):
+        lib()  # liboracle.so supplies the storage-format helpers the shim links against
+        _ref_post = {k: C.CDLL(p) for k, p in _REF_POST_PATHS.items()}
+    return _ref_post
 
 
 def _p(a):
@@ -376,6 +394,76 @@ def taa_resolve(hdr, depth, mv, history, reproj, quality=2, rows=None):
     y0, y1 = rows if rows else (0, h)
     lib().orc_taa_resolve(_p(_c(hdr, np.uint32)), _p(_c(depth, np.float32)), _p(_c(mv, np.uint16)), _p(hist), w, h,
                           _p(_c(reproj, np.float32)), int(quality), _p(out_c), _p(out_h), y0, y1)
+    return out_c, out_h
+
+
+# ---------------- the reference's own post shaders on the CPU (oracle/_ref) ----------------
+def ref_bloom_threshold(hdr, lum3, out_wh):
+    h_in, w_in = hdr.shape
+    w, h = out_wh
+    out = np.zeros((h, w, 4), np.uint16)
+    ref_post_kernels()[7].refk7_bloom_threshold(_p(_c(hdr, np.uint32)), w_in, h_in, _p(_c(lum3, np.float32)), _p(out), w, h)
+    return out
+
+
+def ref_bloom_downsample(src, out_wh, history=None, lerp=0.0):
+    h_in, w_in = src.shape[:2]
+    w, h = out_wh
+    out = np.zeros((h, w, 4), np.uint16)
+    k = ref_post_kernels()
+    if history is None:
+        k[8].refk8_bloom_downsample(_p(_c(src, np.uint16)), w_in, h_in, None, _f(0.0), _p(out), w, h)
+    else:
+        k[18].refk8_bloom_downsample_feedback(_p(_c(src, np.uint16)), w_in, h_in, _p(_c(history, np.uint16)), _f(lerp), _p(out), w, h)
+    return out
+
+
+def ref_bloom_upsample(src, out_wh):
+    h_in, w_in = src.shape[:2]
+    w, h = out_wh
+    out = np.zeros((h, w, 4), np.uint16)
+    ref_post_kernels()[9].refk9_bloom_upsample(_p(_c(src, np.uint16)), w_in, h_in, _p(out), w, h)
+    return out
+
+
+def ref_luminance(d3, lum3, lerp, lo=-3.0, hi=2.0):
+    h, w = d3.shape[:2]
+    l3 = _c(lum3, np.float32).copy()
+    ref_post_kernels()[10].refk10_luminance(_p(_c(d3, np.uint16)), w, h, _f(lerp), _f(lo), _f(hi), _p(l3))
+    return l3
+
+
+def ref_tonemap(hdr, bloom, lum3, exposure=1.0, rows=None):
+    h, w = hdr.shape
+    bh, bw = bloom.shape[:2]
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    ref_post_kernels()[11].refk11_tonemap(_p(_c(hdr, np.uint32)), w, h, _p(_c(bloom, np.uint16)), bw, bh, _p(_c(lum3, np.float32)), _f(exposure),
+                                          _p(out), y0, y1)
+    return out
+
+
+def ref_fxaa(img, target_srgb=True, rows=None):
+    h, w = img.shape
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    k = ref_post_kernels()
+    (k[22].refk12_fxaa_srgb if target_srgb else k[12].refk12_fxaa_unorm)(_p(_c(img, np.uint32)), w, h, _p(out), y0, y1)
+    return out
+
+
+def ref_taa_resolve(hdr, depth, mv, history, reproj, quality=2, rows=None):
+    h, w = hdr.shape
+    out_c = np.zeros((h, w), np.uint32)
+    out_h = np.zeros((h, w, 4), np.uint16)
+    y0, y1 = rows if rows else (0, h)
+    k = ref_post_kernels()
+    if history is None:
+        fn = k[43].refk13_taa_nohistory
+    else:
+        fn = {0: k[23].refk13_taa_q0, 1: k[33].refk13_taa_q1, 2: k[13].refk13_taa_q2}[int(quality)]
+    fn(_p(_c(hdr, np.uint32)), _p(_c(depth, np.float32)), _p(_c(mv, np.uint16)), None if history is None else _p(_c(history, np.uint16)), w, h,
+       _p(_c(reproj, np.float32)), _p(out_c), _p(out_h), y0, y1)
     return out_c, out_h
 
 
