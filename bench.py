@@ -464,7 +464,8 @@ def main():
         vt.render_frame(None)
     vt.sync()
     timings = {k: ms / max(c, 1) for k, (ms, c) in vt.collect_timings().items()}
-    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 10 + (1 if world > 1 else 0), "tonemap": 1, "bloom-disabled": 0, "taa-resolve": 1, "fxaa": 1,
+    # bloom-compute: fused threshold + d0, d1, d2, d3, luminance, u2, u1, u0 (sharded: threshold and d0 apart + the peer wait)
+    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 8 if world == 1 else 11, "tonemap": 1, "bloom-disabled": 0, "taa-resolve": 1, "fxaa": 1,
                 "gbuffer": 0, "mv": 0}
     launches_per_frame = sum(n_launch.get(p, 0) for p in vt.pass_names())
     vt.close()
@@ -507,7 +508,12 @@ def main():
                 ov.bake()
                 arrays = [np.ascontiguousarray(a) for a in (osc.albedo, osc.normal, osc.pbr, osc.depth, osc.emissive)]
                 if oaa == "taa+fxaa":
-                    arrays.append(np.ascontiguousarray(mv.numpy().view(np.uint32)))
+                    # zero motion vectors on 90 % of the pixels, <= 2 px on the rest
+                    orng = np.random.default_rng(5)
+                    omv = np.zeros((oh, ow, 2), np.float16)
+                    om = orng.random((oh, ow)) < 0.1
+                    omv[om] = (orng.uniform(-2, 2, size=(int(om.sum()), 2)) / np.array([ow, oh])).astype(np.float16)
+                    arrays.append(np.ascontiguousarray(omv).view(np.uint32)[..., 0])
                 ogb = viewer.Viewer.host_gbuffer(*arrays)
                 ov.render_frame(ogb)
                 for _ in range(5):

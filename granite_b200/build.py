@@ -18,6 +18,8 @@ UNITS = [
     ("grb_api.cu", []),
     ("grb_cluster.cu", ["-fmad=false"]),
     ("grb_post.cu", ["-fmad=false"]),
+    ("grb_post_tiles.cu", ["-fmad=false"]),
+    ("grb_post_fast.cu", []),
     ("grb_lighting.cu", []),
 ]
 

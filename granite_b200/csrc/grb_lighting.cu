@@ -115,6 +115,29 @@ __device__ __forceinline__ float3 brdf(const Surface &s, float3 L, float &NoL)
 	                   fmaf(Fz, GD - s.diffuse_k.z, s.diffuse_k.z));
 }
 
+// Cluster tile column / row of a pixel column / row: the same non-contracted expression the per-pixel
+// path below uses (clustering.frag:38, clusterer_bindless.h:39-41), monotone in x and in y.
+__device__ __forceinline__ int cluster_tile_x(const LightingParams &p, int x)
+{
+	return iclamp(__float2int_rz(fmul(fmul(fadd((float)x, 0.5f), p.inv_res_x), p.xy_scale.x)), 0, p.res_x - 1);
+}
+__device__ __forceinline__ int cluster_tile_y(const LightingParams &p, int y)
+{
+	return iclamp(__float2int_rz(fmul(fmul(fadd((float)y, 0.5f), p.inv_res_y), p.xy_scale.y)), 0, p.res_y - 1);
+}
+__device__ __forceinline__ float warp_min_f32(float v)
+{
+	float r;
+	asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+	return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v)
+{
+	float r;
+	asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+	return r;
+}
+
 // World position of a pixel and its cluster coordinates.  The tile index and Z slice are part
 // of the bit-exact contract with the reference (clustering.vert:10-14, clustering.frag:38-39,
 // clusterer_bindless.h:39-47), so every op here is a non-contracted IEEE op in a fixed order.
@@ -915,65 +938,50 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 		}
 
 		// ---- draw 2, step 1: candidate words.  Lane j owns words j, j + 32, j + 64, j + 96. ----
+		// The block's cluster tiles follow from its pixel rectangle alone (the per-pixel tile index is a
+		// monotone function of x and of y), so the tile loop is warp-uniform: no votes, no shuffles.
+		// Every tile's bitmask row is cut to the hull of the Z-slice light ranges of the block's lit
+		// pixels -- a superset of each pixel's own (tile, slice) mask; the box test below removes what
+		// lies between two depth layers or in a neighbouring tile only.
 		uint32_t cand0 = 0u, cand1 = 0u, cand2 = 0u, cand3 = 0u;
 		{
-			const int tileA = A.lit ? A.cluster_base : -1, tileB = B.lit ? B.cluster_base : -1; // tile_index * n32
-			bool coveredA = !A.lit, coveredB = !B.lit;
-			for (;;)
+			const unsigned lo = __reduce_min_sync(0xffffffffu, min(A.lit ? A.rx : 0xffffffffu, B.lit ? B.rx : 0xffffffffu));
+			const unsigned hi = __reduce_max_sync(0xffffffffu, max(A.lit ? A.ry : 0u, B.lit ? B.ry : 0u));
+			if (lo <= hi) // otherwise empty slices only: (0xffffffff, 0)
 			{
-				// next uncovered pixel's tile; A pixels first
-				const unsigned remA = __ballot_sync(0xffffffffu, !coveredA), remB = __ballot_sync(0xffffffffu, !coveredB);
-				if (!(remA | remB))
-					break;
-				const int base = remA ? __shfl_sync(0xffffffffu, tileA, __ffs(remA) - 1) : __shfl_sync(0xffffffffu, tileB, __ffs(remB) - 1);
-				const bool inA = A.lit && tileA == base, inB = B.lit && tileB == base;
-				coveredA |= inA;
-				coveredB |= inB;
-				// hull of the Z-slice light ranges of the block's pixels in this tile (a superset of their
-				// union; the box test below removes what lies between two depth layers)
-				const unsigned lo = __reduce_min_sync(0xffffffffu, min(inA ? A.rx : 0xffffffffu, inB ? B.rx : 0xffffffffu));
-				const unsigned hi = __reduce_max_sync(0xffffffffu, max(inA ? A.ry : 0u, inB ? B.ry : 0u));
-				if (lo > hi)
-					continue; // empty slices: (0xffffffff, 0)
+				const int px0 = (x - 2 * (lane & 7)), py0 = y - (lane >> 3); // the block's first pixel
+				const int px1 = min(px0 + 15, p.hdr.w - 1), py1 = min(py0 + 3, p.y1 - 1);
+				const int tx0 = cluster_tile_x(p, px0), tx1 = cluster_tile_x(p, px1), ty0 = cluster_tile_y(p, py0), ty1 = cluster_tile_y(p, py1);
 				// cluster_mask_range (clusterer_bindless_buffers.h:17-27) for a warp-uniform range: only the
 				// first and the last word of [lo, hi] are cut
 				const unsigned wlo = lo >> 5, whi_raw = hi >> 5, whi = min(whi_raw, (unsigned)p.n32 - 1u);
 				const uint32_t cut_lo = 0xffffffffu << (lo & 31u), cut_hi = 0xffffffffu >> (31u - (hi & 31u));
-				const uint32_t *row = p.bitmask + base;
-				auto take = [&](unsigned j) -> uint32_t {
-					if (j < wlo || j > whi)
-						return 0u;
-					return __ldg(row + j) & (j == wlo ? cut_lo : 0xffffffffu) & (j == whi_raw ? cut_hi : 0xffffffffu);
+				auto cut = [&](unsigned j) -> uint32_t {
+					return (j < wlo || j > whi) ? 0u : ((j == wlo ? cut_lo : 0xffffffffu) & (j == whi_raw ? cut_hi : 0xffffffffu));
 				};
-				cand0 |= take((unsigned)lane);
-				if (p.n32 > 32)
-				{
-					cand1 |= take((unsigned)lane + 32u);
-					cand2 |= take((unsigned)lane + 64u);
-					cand3 |= take((unsigned)lane + 96u);
-				}
+				const uint32_t m0 = cut((unsigned)lane), m1 = cut((unsigned)lane + 32u), m2 = cut((unsigned)lane + 64u), m3 = cut((unsigned)lane + 96u);
+				for (int ty = ty0; ty <= ty1; ty++)
+					for (int tx = tx0; tx <= tx1; tx++)
+					{
+						const uint32_t *row = p.bitmask + (size_t)(ty * p.res_x + tx) * (size_t)p.n32;
+						if (m0) cand0 |= __ldg(row + lane) & m0;
+						if (m1) cand1 |= __ldg(row + lane + 32) & m1;
+						if (m2) cand2 |= __ldg(row + lane + 64) & m2;
+						if (m3) cand3 |= __ldg(row + lane + 96) & m3;
+					}
 			}
 		}
 
-		// world-space bounding box of the block's lit pixels
+		// world-space bounding box of the block's lit pixels (float warp reductions: redux.sync.f32, sm_100a)
 		float bmin_x, bmin_y, bmin_z, bmax_x, bmax_y, bmax_z;
 		{
-			const unsigned kInf = 0xffffffffu;
-			unsigned lx = kInf, ly = kInf, lz = kInf, hx = 0u, hy = 0u, hz = 0u;
-			if (A.lit)
-			{
-				lx = hx = fkey(A.pos.x); ly = hy = fkey(A.pos.y); lz = hz = fkey(A.pos.z);
-			}
-			if (B.lit)
-			{
-				const unsigned kx = fkey(B.pos.x), ky = fkey(B.pos.y), kz = fkey(B.pos.z);
-				lx = min(lx, kx); ly = min(ly, ky); lz = min(lz, kz);
-				hx = max(hx, kx); hy = max(hy, ky); hz = max(hz, kz);
-			}
-			bmin_x = fkey_inv(__reduce_min_sync(0xffffffffu, lx)); bmin_y = fkey_inv(__reduce_min_sync(0xffffffffu, ly));
-			bmin_z = fkey_inv(__reduce_min_sync(0xffffffffu, lz));
-			bmax_x = fkey_inv(__reduce_max_sync(0xffffffffu, hx)); bmax_y = fkey_inv(__reduce_max_sync(0xffffffffu, hy));
-			bmax_z = fkey_inv(__reduce_max_sync(0xffffffffu, hz));
+			const float kBig = 3.0e38f;
+			const float ax = A.lit ? A.pos.x : kBig, ay = A.lit ? A.pos.y : kBig, az = A.lit ? A.pos.z : kBig;
+			const float bxx = B.lit ? B.pos.x : kBig, byy = B.lit ? B.pos.y : kBig, bzz = B.lit ? B.pos.z : kBig;
+			bmin_x = warp_min_f32(fminf(ax, bxx)); bmin_y = warp_min_f32(fminf(ay, byy)); bmin_z = warp_min_f32(fminf(az, bzz));
+			bmax_x = warp_max_f32(fmaxf(A.lit ? A.pos.x : -kBig, B.lit ? B.pos.x : -kBig));
+			bmax_y = warp_max_f32(fmaxf(A.lit ? A.pos.y : -kBig, B.lit ? B.pos.y : -kBig));
+			bmax_z = warp_max_f32(fmaxf(A.lit ? A.pos.z : -kBig, B.lit ? B.pos.z : -kBig));
 		}
 		if (!table_ready)
 		{
@@ -1081,7 +1089,7 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 				*reinterpret_cast<uint2 *>(&p.hdr.at(x, y)) = out;
 		}
 		if (a.schedule && lane == 0)
-			atomicAdd(&a.schedule[4 + cur_by], (uint32_t)((clock64() - t_begin) >> 5));
+			atomicMax(&a.schedule[4 + cur_by], (uint32_t)((clock64() - t_begin) >> 5)); // key = the row's most expensive block
 #ifdef GRB_LIGHTING_DEBUG
 		if (lane == 0)
 		{

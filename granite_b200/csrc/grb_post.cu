@@ -728,6 +728,18 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) taa_kernel(TaaInputs in, Mat
 } // namespace
 } // namespace grb
 
+namespace grb
+{
+// grb_post_tiles.cu: TMA + shared-memory tile form of the 2:1 pyramid steps; false = not eligible
+bool launch_tent_tiled(bool up, const GrbImage *in, const GrbImage *history, float lerp, const GrbImage *out, GrbRows rows, cudaStream_t stream, int32_t *rc);
+// grb_post_fast.cu: issue-optimised forms of the full-resolution passes (1 unit of the stored format)
+bool launch_tonemap_fast(const GrbImage *hdr, const GrbImage *bloom, const float *luminance, float exposure, const GrbImage *out, GrbRows rows, cudaStream_t stream,
+                         int32_t *rc);
+bool launch_fxaa_fast(const GrbImage *in, const GrbImage *out, GrbRows rows, cudaStream_t stream, int32_t *rc);
+bool launch_taa_fast(const GrbImage *hdr, const GrbImage *depth, const GrbImage *mv, const GrbImage *history, const float *reproj16, const GrbImage *out_color,
+                     const GrbImage *out_history, GrbRows rows, cudaStream_t stream, int32_t *rc);
+} // namespace grb
+
 using namespace grb;
 
 extern "C" int32_t grb_bloom_threshold(const GrbImage *hdr, const float *luminance, const GrbImage *out, GrbRows rows, void *stream)
@@ -766,6 +778,11 @@ extern "C" int32_t grb_bloom_downsample(const GrbImage *in, const GrbImage *hist
 	rows = full_rows(rows, out->height);
 	if (rows.y1 <= rows.y0)
 		return GRB_OK;
+	{
+		int32_t rc = GRB_OK;
+		if (launch_tent_tiled(false, in, history, lerp, out, rows, as_stream(stream), &rc))
+			return rc;
+	}
 	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
 	float inv_w = 1.0f / (float)out->width, inv_h = 1.0f / (float)out->height;   // hdr.cpp:178-179
 	float inv_in_w = 1.0f / (float)in->width, inv_in_h = 1.0f / (float)in->height; // hdr.cpp:180-181
@@ -838,6 +855,11 @@ extern "C" int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, G
 	rows = full_rows(rows, out->height);
 	if (rows.y1 <= rows.y0)
 		return GRB_OK;
+	{
+		int32_t rc = GRB_OK;
+		if (launch_tent_tiled(true, in, nullptr, 0.0f, out, rows, as_stream(stream), &rc))
+			return rc;
+	}
 	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
 	bloom_upsample_kernel<<<grid, block, 0, as_stream(stream)>>>(view_of<const uint2>(in), view_of<uint2>(out), rows.y0, rows.y1,
 	                                                              1.0f / (float)out->width, 1.0f / (float)out->height, 1.0f / (float)in->width,
@@ -906,6 +928,11 @@ extern "C" int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const
 	auto b = view_of<const uint2>(bloom);
 	auto o = view_of<uint32_t>(out);
 	cudaStream_t s = as_stream(stream);
+	{
+		int32_t rc = GRB_OK;
+		if (launch_tonemap_fast(hdr, bloom, luminance, dynamic_exposure, out, rows, s, &rc))
+			return rc;
+	}
 	// 4-pixel path: rows 16-byte aligned and the bloom image at exactly 1/4 width
 	const bool vec4 = (out->width % 4) == 0 && bloom->width * 4 == out->width && (hdr->row_pitch % 16) == 0 && (out->row_pitch % 16) == 0 &&
 	                  (reinterpret_cast<uintptr_t>(hdr->data) % 16) == 0 && (reinterpret_cast<uintptr_t>(out->data) % 16) == 0;
@@ -944,6 +971,11 @@ extern "C" int32_t grb_fxaa(const GrbImage *in, const GrbImage *out, GrbRows row
 	rows = full_rows(rows, out->height);
 	if (rows.y1 <= rows.y0)
 		return GRB_OK;
+	{
+		int32_t rc = GRB_OK;
+		if (launch_fxaa_fast(in, out, rows, as_stream(stream), &rc))
+			return rc;
+	}
 	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
 	float inv_w = 1.0f / (float)in->width, inv_h = 1.0f / (float)in->height; // fxaa.cpp:45-46
 	if (out->format == GRB_FORMAT_R8G8B8A8_SRGB)
@@ -979,6 +1011,12 @@ extern "C" int32_t grb_taa_resolve(const GrbImage *hdr, const GrbImage *depth, c
 	rows = full_rows(rows, hdr->height);
 	if (rows.y1 <= rows.y0)
 		return GRB_OK;
+	if (history && quality == 2)
+	{
+		int32_t rc = GRB_OK;
+		if (launch_taa_fast(hdr, depth, mv, history, reproj16, out_color, out_history, rows, as_stream(stream), &rc))
+			return rc;
+	}
 	TaaInputs in{};
 	in.hdr = view_of<const uint32_t>(hdr);
 	Mat4 m{};

@@ -144,6 +144,15 @@ def bloom_threshold(hdr_t, lum_t, out_t, rows=None):
     capi.check(capi.lib().grb_bloom_threshold(C.byref(hi), _ptr(lum_t), C.byref(oi), capi.rows(rows), capi.stream_ptr()), "grb_bloom_threshold")
 
 
+def bloom_threshold_downsample(hdr_t, lum_t, d0_t, threshold_t=None, rows=None):
+    """Fused K7 + first K8 (TMA tiles); raises GrbError when the shape is not eligible."""
+    hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
+    oi = _img16(d0_t)
+    ti = C.byref(_img16(threshold_t)) if threshold_t is not None else None
+    capi.check(capi.lib().grb_bloom_threshold_downsample(C.byref(hi), _ptr(lum_t), ti, C.byref(oi), capi.rows(rows), capi.stream_ptr()),
+               "grb_bloom_threshold_downsample")
+
+
 def bloom_downsample(in_t, out_t, history_t=None, lerp=0.0, rows=None):
     ii, oi = _img16(in_t), _img16(out_t)
     hi = C.byref(_img16(history_t)) if history_t is not None else None

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace Granite
 {
@@ -46,13 +47,20 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	GrbRows d0_rows = sharded ? plan.downsample0 : all_rows();
 	GrbRows t_rows = sharded ? plan.threshold : all_rows();
 
-	// bloom_threshold_build_compute: uses LAST frame's average luminance (hdr.cpp:355)
-	cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
+	// bloom_threshold_build_compute: uses LAST frame's average luminance (hdr.cpp:355).
+	// Unsharded frames run threshold + first downsample as ONE kernel with the threshold image kept in shared memory; it is only written out when
+	// GRB_BLOOM_KEEP_THRESHOLD is set (nothing downstream reads it).
+	static const bool keep_threshold = getenv("GRB_BLOOM_KEEP_THRESHOLD") != nullptr;
+	bool head_fused = false;
+	if (!sharded)
+		head_fused = grb_bloom_threshold_downsample(&hdr, lum, keep_threshold ? &t : nullptr, &d0, d0_rows, stream) == GRB_OK;
+	if (!head_fused)
+		cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
 	// The d0 bands are needed in full by every rank.  Preferred: the downsample kernel itself stores
 	// its band into every rank's copy over NVLink peer memory and raises a flag (no collective
 	// launch, no second pass over the band); otherwise NCCL broadcasts after a local downsample.
 	RenderGraphCollectives::PeerSlot slot;
-	const bool peer_stores = sharded && graph.get_collectives()->peer_exchange_begin_frame((size_t)d0.row_pitch * (size_t)d0.height, slot);
+	const bool peer_stores = sharded && !head_fused && graph.get_collectives()->peer_exchange_begin_frame((size_t)d0.row_pitch * (size_t)d0.height, slot);
 	if (peer_stores)
 	{
 		const unsigned self = graph.get_collectives()->get_rank();
@@ -62,7 +70,7 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 		cmd.check(grb_peer_wait(slot.flags[self], (int32_t)slot.count, slot.epoch, stream), "grb_peer_wait");
 		d0.data = slot.images[self]; // the pyramid tail reads the exchanged copy
 	}
-	else
+	else if (!head_fused)
 		cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, stream), "grb_bloom_downsample(d0)");
 
 	if (sharded && !peer_stores)

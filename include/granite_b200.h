@@ -210,6 +210,14 @@ int32_t grb_bloom_threshold(const GrbImage *hdr, const float *luminance, const G
  * image of the same size; lerp = 1 - 0.001^frame_time. */
 int32_t grb_bloom_downsample(const GrbImage *in, const GrbImage *history, float lerp,
                              const GrbImage *out, GrbRows rows, void *stream);
+/* K7 + the first K8 dispatch in one pass: d0 = downsample(threshold(hdr)) with the 1/2-resolution
+ * threshold image kept in shared memory (TMA-loaded HDR tiles; granite_b200/csrc/grb_post_tiles.cu).
+ * threshold_out may be NULL; when given, its rows 2*rows.y0 .. 2*rows.y1 are written too, bit-identical
+ * to grb_bloom_threshold.  Needs exact 2:1 size steps hdr -> threshold -> d0 and 16-byte aligned rows;
+ * otherwise returns GRB_ERR_UNSUPPORTED_FORMAT and the caller issues the two calls above.
+ * Replaces hdr.cpp:355-356 (bloom_threshold_build_compute + bloom_downsample_build_compute). */
+int32_t grb_bloom_threshold_downsample(const GrbImage *hdr, const float *luminance, const GrbImage *threshold_out,
+                                       const GrbImage *d0, GrbRows rows, void *stream);
 /* K8 fused with the exchange a row-sharded frame needs after it: the band
  * rows [rows.y0, rows.y1) of the 1/4-resolution level are stored into that image on EVERY rank --
  * peer_images[r] is the base address, valid on this device, of rank r's image (cudaIpc-mapped

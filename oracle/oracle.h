@@ -121,6 +121,10 @@ void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, cons
                            uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
                            int32_t *out_light_count, int y0, int y1);
 
+/* One additive blend into a B10G11R11 attachment (renderer.cpp:1009-1011): dst = q(unpack(dst) + src) where
+ * mask != 0.  Used by the tests that run the reference's own fragment shaders (oracle/_ref). */
+void orc_blend_add_r11g11b10(uint32_t *dst, const float *src_rgb, const uint8_t *mask, int64_t count);
+
 /* ---- HDR chain ---- */
 /* K7 bloom_threshold.comp:23-45.  lum3: {avg_log, avg_lin, avg_inv_lin} or NULL (DYNAMIC_EXPOSURE=0). */
 void orc_bloom_threshold(const uint32_t *hdr, int w_in, int h_in, const float *lum3,

@@ -262,3 +262,15 @@ void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, cons
 		}
 	}
 }
+
+/* renderer.cpp:1009-1011: additive blend, the attachment store quantises (oracle_math.h pack_r11g11b10) */
+void orc_blend_add_r11g11b10(uint32_t *dst, const float *src_rgb, const uint8_t *mask, int64_t count)
+{
+	for (int64_t i = 0; i < count; i++)
+	{
+		if (!mask[i])
+			continue;
+		vec3 d = unpack_r11g11b10(dst[i]);
+		dst[i] = pack_r11g11b10(v3(d.x + src_rgb[3 * i + 0], d.y + src_rgb[3 * i + 1], d.z + src_rgb[3 * i + 2]));
+	}
+}

@@ -21,6 +21,8 @@ _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for 
 # post-processing shaders K7-K13 (ref_post_shim.cpp); ids as in oracle/Makefile POST_IDS
 _REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
+# deferred-lighting fragment shaders K5 (clustering.frag) and K6 (directional.frag), ref_light_shim.cpp
+_REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6)}
 
 
 def build(ref: bool = True) -> None:
@@ -35,6 +37,8 @@ def build(ref: bool = True) -> None:
         stale = any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(shim) for p in _REF_KERNEL_PATHS)
         pshim = os.path.join(_HERE, "ref_post_shim.cpp")
         stale = stale or any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(pshim) for p in _REF_POST_PATHS.values())
+        lshim = os.path.join(_HERE, "ref_light_shim.cpp")
+        stale = stale or any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(lshim) for p in _REF_LIGHT_PATHS.values())
         if stale:
             r = subprocess.run(["make", "-s", "-j8", "-C", _HERE, "ref-shaders"], capture_output=True, text=True)
             if r.returncode != 0:  # checker infrastructure: report, never break the product build
@@ -331,6 +335,48 @@ def deferred_lighting(scene, cam: Camera, prep, clus, rows=None, want_indices=Fa
     if want_indices:
         return hdr, tile, zidx, cnt
     return hdr
+
+
+_ref_light = None
+
+
+def ref_light_kernels():
+    """{5, 6: CDLL} of the reference's clustering.frag / directional.frag compiled for the CPU, or None."""
+    global _ref_light
+    if _ref_light is None and all(os.path.exists(p) for p in _REF_LIGHT_PATHS.values()):
+        lib()
+        _ref_light = {k: C.CDLL(p) for k, p in _REF_LIGHT_PATHS.items()}
+    return _ref_light
+
+
+def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None):
+    """renderer.cpp:1004-1156 with the reference's own fragment shaders: the two draws' colours
+    (fp32), then the two additive blends into B10G11R11 with DESIGN.md section 2's store rule:
+    q(q(emissive + directional) + clustered).  Returns (hdr, directional_rgb, clustered_rgb)."""
+    H, W = scene.depth.shape
+    k = ref_light_kernels()
+    y0, y1 = rows if rows else (0, H)
+    alb, nrm, pbr, dep = _c(scene.albedo, np.uint32), _c(scene.normal, np.uint32), _c(scene.pbr, np.uint16), _c(scene.depth, np.float32)
+    ivp = _farr(list(cam.inv_view_projection))
+    cpos, cfront = _farr(list(cam.camera_position)), _farr(list(cam.camera_front))
+    d_rgb = np.zeros((H, W, 3), np.float32)
+    c_rgb = np.zeros((H, W, 3), np.float32)
+    k[6].refk6_directional(W, H, _p(alb), _p(nrm), _p(pbr), _p(dep), _p(ivp), _p(cpos), _p(cfront), _p(_farr(list(scene.dir_color))),
+                           _p(_farr(list(scene.dir_direction))), y0, y1, _p(d_rgb))
+    P = prep.params
+    k[5].refk5_clustering(W, H, _p(alb), _p(nrm), _p(pbr), _p(dep), _p(ivp), _p(cpos), _p(_farr(list(P.camera_base))), _p(_farr(list(P.camera_front))),
+                          _p(_farr(list(P.xy_scale))), _p(np.array(list(P.resolution_xy), np.int32)), int(P.num_lights), int(P.num_lights_32),
+                          int(P.z_max_index), _f(P.z_scale), _p(prep.records), _p(_c(prep.type_mask, np.uint32)), _p(_c(clus.bitmask, np.uint32)),
+                          _p(_c(clus.range, np.uint32)), y0, y1, _p(c_rgb))
+    L = lib()
+    L.orc_blend_add_r11g11b10.restype = None
+    hdr = _c(scene.emissive, np.uint32).copy()
+    lit = dep != 0.0
+    lit[:y0] = False
+    lit[y1:] = False
+    for rgb in (d_rgb, c_rgb):
+        L.orc_blend_add_r11g11b10(_p(hdr), _p(np.ascontiguousarray(rgb)), _p(np.ascontiguousarray(lit, dtype=np.uint8)), hdr.size)
+    return hdr, d_rgb, c_rgb
 
 
 # ---------------- HDR chain ----------------

@@ -1,0 +1,231 @@
+// oracle/ref_light_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Host driver for the reference's own deferred-lighting fragment shaders, executed on the CPU:
+//   KERNEL=5  assets/shaders/lights/clustering.frag  (K5: clustered point / spot lights)
+//   KERNEL=6  assets/shaders/lights/directional.frag (K6: directional light, VOLUMETRIC_DIFFUSE_FALLBACK,
+//             no shadows -- the variant renderer.cpp:1018-1105 selects for the viewer without shadow maps)
+// GLSL where it lies under /root/reference -> SPIR-V (vendored glslang) -> C++ (vendored spirv-cross
+// `--cpp --vulkan-semantics`) -> #included here (GEN_CPP); see oracle/Makefile `ref-shaders`.  The
+// statements that run are the reference's: compute_cluster_light (clusterer_bindless.h:29-84),
+// cluster_mask_range, compute_point_light / compute_spot_light (point.h, spot.h), the BRDF (pbr.h),
+// compute_lighting (lighting.h:6-82).
+//
+// What the shim supplies (nothing of it is shader arithmetic):
+//   * subpassLoad: the G-buffer texel of the fragment, decoded by the attachment formats
+//     (R8G8B8A8_SRGB through the oracle's EOTF table, A2B10G10R10 / R8G8 as n / (2^k - 1), D32);
+//   * vClip: clustering.vert:10-14 outputs invVP * (ndc.xy, 0, 1) at the three vertices of the
+//     full-screen triangle and the rasteriser interpolates it; per pixel that is
+//     (col0 * ndc.x + col1 * ndc.y) + col3 with ndc = 2 (frag + 0.5) / size - 1;
+//   * a subgroup of ONE invocation: subgroupMin / Max / Or are the identity, i.e. every pixel walks
+//     exactly its own (tile, Z-slice) mask.  (On a GPU the OR over a subgroup only ADDS lights whose
+//     range falloff is exactly 0 at the pixels that did not have them: tests/test_oracle_cpu.py's
+//     brute-force test shows the sum does not change by a bit.)
+//   * the SSBOs: spirv-cross's deprecated C++ backend does not declare StorageBuffer-class blocks, so the
+//     three block names the generated code uses are rewritten by the Makefile's sed to the *_BLOCK macros
+//     below, which are plain pointers.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define GLM_FORCE_PURE
+#ifndef GLM_SWIZZLE
+#define GLM_SWIZZLE
+#endif
+#ifndef GLM_FORCE_RADIANS
+#define GLM_FORCE_RADIANS
+#endif
+#include <glm/glm.hpp>
+
+extern "C" float orc_srgb8_to_linear(uint32_t v);
+
+#define SPIRV_CROSS_SAMPLER_HPP
+#define SPIRV_CROSS_IMAGE_HPP
+namespace spirv_cross
+{
+struct subpassInput
+{
+	glm::vec4 value;
+};
+inline glm::vec4 subpassLoad(const subpassInput &s) { return s.value; }
+struct sampler2D
+{
+	int unused;
+};
+template <typename T> inline T subgroupMin(T v) { return v; }
+template <typename T> inline T subgroupMax(T v) { return v; }
+template <typename T> inline T subgroupOr(T v) { return v; }
+} // namespace spirv_cross
+
+#include "spirv_cross/internal_interface.hpp"
+
+// GLSL mix(): the Vulkan specification's form x * (1 - a) + y * a (see ref_shader_shim.cpp)
+inline float mix(const float &x, const float &y, const float &a) { return x * (1.0f - a) + y * a; }
+inline glm::vec3 mix(const glm::vec3 &x, const glm::vec3 &y, const glm::vec3 &a) { return x * (glm::vec3(1.0f) - a) + y * a; }
+
+namespace shim
+{
+static const void *g_transforms = nullptr;
+static const void *g_bitmask = nullptr;
+static const void *g_range = nullptr;
+struct BitmaskBlock
+{
+	uint32_t cluster_bitmask[1];
+};
+struct RangeBlock
+{
+	glm::uvec2 cluster_range[1];
+};
+template <typename S>
+struct TransformsBlock
+{
+	typename S::ClustererBindlessTransforms cluster_transforms;
+};
+} // namespace shim
+#define BITMASK_BLOCK (*static_cast<const shim::BitmaskBlock *>(shim::g_bitmask))
+#define RANGE_BLOCK (*static_cast<const shim::RangeBlock *>(shim::g_range))
+#define TRANSFORMS_BLOCK (*static_cast<const shim::TransformsBlock<Shader> *>(shim::g_transforms))
+
+#include GEN_CPP
+
+namespace
+{
+using Sh = Impl::Shader;
+using spirv_cross::subpassInput;
+
+struct GBufferIn
+{
+	int w, h;
+	const uint32_t *albedo, *normal;
+	const uint16_t *pbr;
+	const float *depth;
+};
+
+struct Frag
+{
+	subpassInput base, normal, pbr, depth;
+	glm::vec4 vclip, frag_coord;
+	glm::vec3 color;
+};
+
+// returns false for sky pixels (depth == 0: never shaded, renderer.cpp:1056-1057)
+bool load_fragment(const GBufferIn &g, const float *ivp, int x, int y, Frag &f)
+{
+	const size_t i = (size_t)y * g.w + x;
+	const float depth = g.depth[i];
+	if (depth == 0.0f)
+		return false;
+	const uint32_t a = g.albedo[i], n = g.normal[i];
+	const uint32_t mr = g.pbr[i];
+	f.base.value = glm::vec4(orc_srgb8_to_linear(a & 255u), orc_srgb8_to_linear((a >> 8) & 255u), orc_srgb8_to_linear((a >> 16) & 255u), (float)(a >> 24) / 255.0f);
+	f.normal.value = glm::vec4((float)(n & 1023u) / 1023.0f, (float)((n >> 10) & 1023u) / 1023.0f, (float)((n >> 20) & 1023u) / 1023.0f, (float)(n >> 30) / 3.0f);
+	f.pbr.value = glm::vec4((float)(mr & 255u) / 255.0f, (float)(mr >> 8) / 255.0f, 0.0f, 1.0f);
+	f.depth.value = glm::vec4(depth, 0.0f, 0.0f, 1.0f);
+	const float inv_x = 1.0f / (float)g.w, inv_y = 1.0f / (float)g.h;
+	const float ndc_x = 2.0f * ((float)x + 0.5f) * inv_x - 1.0f, ndc_y = 2.0f * ((float)y + 0.5f) * inv_y - 1.0f;
+	f.vclip = glm::vec4(ivp[0] * ndc_x + ivp[4] * ndc_y + ivp[12], ivp[1] * ndc_x + ivp[5] * ndc_y + ivp[13], ivp[2] * ndc_x + ivp[6] * ndc_y + ivp[14],
+	                    ivp[3] * ndc_x + ivp[7] * ndc_y + ivp[15]);
+	f.frag_coord = glm::vec4((float)x + 0.5f, (float)y + 0.5f, depth, 1.0f);
+	return true;
+}
+
+struct Runner
+{
+	spirv_cross_shader_t *sh;
+	const spirv_cross_interface *itf;
+	Frag f;
+	Runner() : sh(nullptr), itf(spirv_cross_get_interface())
+	{
+		sh = itf->construct();
+		resource(3, 0, &f.base);
+		resource(3, 1, &f.normal);
+		resource(3, 2, &f.pbr);
+		resource(3, 3, &f.depth);
+		spirv_cross_set_stage_input(sh, 0, &f.vclip, sizeof(f.vclip));
+		spirv_cross_set_stage_output(sh, 0, &f.color, sizeof(f.color));
+		spirv_cross_set_builtin(sh, SPIRV_CROSS_BUILTIN_FRAG_COORD, &f.frag_coord, sizeof(f.frag_coord));
+	}
+	~Runner() { itf->destruct(sh); }
+	void resource(unsigned set, unsigned binding, void *ptr)
+	{
+		void *p = ptr;
+		spirv_cross_set_resource(sh, set, binding, &p, sizeof(p));
+	}
+	// out_rgb: h x w x 3 floats, the fragment colour of this draw (0 where nothing was drawn)
+	void draw(const GBufferIn &g, const float *ivp, int y0, int y1, float *out_rgb)
+	{
+		for (int y = y0; y < y1; y++)
+			for (int x = 0; x < g.w; x++)
+			{
+				float *o = out_rgb + ((size_t)y * g.w + x) * 3;
+				o[0] = o[1] = o[2] = 0.0f;
+				if (!load_fragment(g, ivp, x, y, f))
+					continue;
+				itf->invoke(sh);
+				o[0] = f.color.x;
+				o[1] = f.color.y;
+				o[2] = f.color.z;
+			}
+	}
+};
+} // namespace
+
+extern "C" {
+#if KERNEL == 5
+// renderer.cpp:1107-1156.  The cluster parameters are the oracle's orc_cluster_params_t fields.
+void refk5_clustering(int w, int h, const uint32_t *albedo, const uint32_t *normal, const uint16_t *pbr, const float *depth, const float *inv_view_projection16,
+                      const float *camera_pos3, const float *camera_base3, const float *camera_front3, const float *xy_scale2, const int32_t *resolution_xy2,
+                      int num_lights, int num_lights_32, int z_max_index, float z_scale, const void *lights48, const uint32_t *type_mask, const uint32_t *bitmask,
+                      const uint32_t *cluster_range, int y0, int y1, float *out_rgb)
+{
+	static_assert(sizeof(Sh::PositionalLightInfo) == 48, "light record layout");
+	auto *blob = new shim::TransformsBlock<Sh>();
+	std::memset(static_cast<void *>(blob), 0, sizeof(*blob));
+	std::memcpy(blob->cluster_transforms.lights.data(), lights48, (size_t)num_lights * 48);
+	std::memcpy(blob->cluster_transforms.type_mask.data(), type_mask, (size_t)num_lights_32 * 4);
+	shim::g_transforms = blob;
+	shim::g_bitmask = bitmask;
+	shim::g_range = cluster_range;
+	Sh::Resources::ClusterParameters ubo;
+	std::memset(static_cast<void *>(&ubo), 0, sizeof(ubo));
+	ubo.cluster.camera_base = glm::vec3(camera_base3[0], camera_base3[1], camera_base3[2]);
+	ubo.cluster.camera_front = glm::vec3(camera_front3[0], camera_front3[1], camera_front3[2]);
+	ubo.cluster.xy_scale = glm::vec2(xy_scale2[0], xy_scale2[1]);
+	ubo.cluster.resolution_xy = glm::ivec2(resolution_xy2[0], resolution_xy2[1]);
+	ubo.cluster.num_lights = num_lights;
+	ubo.cluster.num_lights_32 = num_lights_32;
+	ubo.cluster.z_max_index = z_max_index;
+	ubo.cluster.z_scale = z_scale;
+	Sh::Resources::Registers reg;
+	std::memset(static_cast<void *>(&reg), 0, sizeof(reg));
+	reg.inverse_view_projection_col2 = glm::vec4(inv_view_projection16[8], inv_view_projection16[9], inv_view_projection16[10], inv_view_projection16[11]);
+	reg.camera_pos = glm::vec3(camera_pos3[0], camera_pos3[1], camera_pos3[2]);
+	reg.inv_resolution = glm::vec2(1.0f / (float)w, 1.0f / (float)h); // renderer.cpp:1101-1102,1120
+	GBufferIn g = { w, h, albedo, normal, pbr, depth };
+	{
+		Runner r;
+		r.resource(0, 8, &ubo);
+		spirv_cross_set_push_constant(r.sh, &reg, sizeof(reg));
+		r.draw(g, inv_view_projection16, y0, y1, out_rgb);
+	}
+	delete blob;
+}
+#elif KERNEL == 6
+// renderer.cpp:1018-1105
+void refk6_directional(int w, int h, const uint32_t *albedo, const uint32_t *normal, const uint16_t *pbr, const float *depth, const float *inv_view_projection16,
+                       const float *camera_pos3, const float *camera_front3, const float *dir_color3, const float *dir_direction3, int y0, int y1, float *out_rgb)
+{
+	Sh::Resources::Registers reg;
+	std::memset(static_cast<void *>(&reg), 0, sizeof(reg));
+	reg.inverse_view_projection_col2 = glm::vec4(inv_view_projection16[8], inv_view_projection16[9], inv_view_projection16[10], inv_view_projection16[11]);
+	reg.color = glm::vec3(dir_color3[0], dir_color3[1], dir_color3[2]);
+	reg.camera_pos = glm::vec3(camera_pos3[0], camera_pos3[1], camera_pos3[2]);
+	reg.direction = glm::vec3(dir_direction3[0], dir_direction3[1], dir_direction3[2]);
+	reg.camera_front = glm::vec3(camera_front3[0], camera_front3[1], camera_front3[2]);
+	reg.inv_resolution = glm::vec2(1.0f / (float)w, 1.0f / (float)h);
+	GBufferIn g = { w, h, albedo, normal, pbr, depth };
+	Runner r;
+	spirv_cross_set_push_constant(r.sh, &reg, sizeof(reg));
+	r.draw(g, inv_view_projection16, y0, y1, out_rgb);
+}
+#endif
+}
