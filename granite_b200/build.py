@@ -12,6 +12,8 @@ OUT = os.path.join(HERE, "libgranite_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+# diagnostics only, e.g. GRB_EXTRA_NVCC_FLAGS=-DGRB_LIGHTING_DEBUG for tools/lighting_timeline.py
+COMMON += os.environ.get("GRB_EXTRA_NVCC_FLAGS", "").split()
 
 # (source, extra flags).  -fmad=false: bit-exact contract with the oracle (see file headers).
 UNITS = [

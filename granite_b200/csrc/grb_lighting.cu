@@ -657,7 +657,7 @@ struct PersistentArgs
 	QueueSlot *queue;
 	int blocks_x, blocks_y, total_items; // total_items = blocks_x * blocks_y
 	int n_lights;
-	uint32_t *schedule; // optional: [blocks_x, blocks_y, valid, 0][cost per block row][block rows by falling cost]
+	uint32_t *schedule; // optional: [blocks_x, blocks_y, valid, 0][max block cost per strip][strips by falling cost][block shape per strip]
 	unsigned rec_bytes; // n_lights * 48, multiple of 16
 	int use_bulk_copy;
 };
@@ -764,7 +764,10 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 	                       a.schedule[1] == (uint32_t)a.blocks_y && a.schedule[2] == 1u;
 	if (scheduled)
 		for (int i = threadIdx.x; i < a.blocks_y; i += blockDim.x)
-			s_order[i] = (uint16_t)a.schedule[4 + a.blocks_y + i];
+		{
+			const uint32_t strip = a.schedule[4 + a.blocks_y + i];
+			s_order[i] = (uint16_t)(strip | (a.schedule[4 + 2 * a.blocks_y + strip] ? 0x8000u : 0u));
+		}
 	__syncthreads();
 	if (a.use_bulk_copy)
 	{
@@ -796,37 +799,46 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 	const unsigned total = (unsigned)a.total_items;
 	const unsigned n_warps = gridDim.x * kPWarps;
 
-	// Work items are pixel blocks, row by row in schedule order, handed out in chunks of up to 4
-	// (guided: single blocks near the end).  The atomic for the NEXT chunk is issued when the last
-	// block of the current chunk is taken, so its round trip to L2 overlaps that block's shading.
-	unsigned next = 0, end = 0, pend_got = 0, pend_want = 0, last_seen = 0;
-	bool pending = false;
+	// Work items are pixel blocks, strip by strip (a strip = 4 pixel rows) in schedule order, one item per
+	// atomic.  A strip is cut into blocks in one of two shapes, chosen per strip from the previous
+	// launch's costs (bit 15 of its s_order entry):
+	//   shape 0: 16 x 4 pixels (lane = 8 x 4 pixel pairs)      -- compact footprint, one or two cluster tiles
+	//   shape 1: 64 x 1 pixels (lane = 32 pixel pairs of a row) -- for the light-dense strips near the
+	//            horizon, where depth changes by metres from one pixel row to the next: a 4-row block's
+	//            bounding box then collects several times the lights any of its pixels sees, a single
+	//            row's does not.
+	// Either way a strip has a.blocks_x = 4 * ceil(w / 64) items (>= ceil(w / 16); surplus shape-0 items are
+	// empty).  Per-pixel results do not depend on the shape: a light that does not reach a pixel adds 0.
+	//
+	// The atomic for the NEXT item is normally issued when the current one is taken (its round trip and
+	// the G-buffer prefetch overlap the current block's shading).  After a block with a long light list
+	// the warp stops reserving ahead: a reserved block is a block no idle warp can take, and a dense
+	// block can take 100 us.
+	const unsigned n64 = (unsigned)a.blocks_x / 4u;
+	const unsigned blocks16 = ((unsigned)p.hdr.w / 2u + 7u) / 8u;
+	unsigned pend_got = 0;
+	bool pending = false, dense_mode = false;
 	auto issue_grab = [&]() {
 		if (lane == 0)
-		{
-			const unsigned left = last_seen < total ? total - last_seen : 0u;
-			pend_want = min(max(left / (16u * n_warps), 1u), 4u);
-			pend_got = atomicAdd(&a.queue->next_block, pend_want);
-		}
+			pend_got = atomicAdd(&a.queue->next_block, 1u);
 		pending = true;
 	};
-	auto fetch_item = [&](int &bx, int &by) -> bool {
-		if (next >= end)
-		{
-			if (!pending)
-				issue_grab();
-			const unsigned got = __shfl_sync(0xffffffffu, pend_got, 0), want = __shfl_sync(0xffffffffu, pend_want, 0);
-			pending = false;
-			last_seen = got + want;
-			if (got >= total)
-				return false;
-			next = got;
-			end = min(got + want, total);
-		}
-		const unsigned item = next++;
-		// no reservation ahead of time near the end of the queue: an item reserved by a warp that is
-		// still busy is an item no idle warp can take
-		if (next >= end && last_seen + 6u * n_warps < total)
+	struct Item
+	{
+		int x, y;       // this lane's pixel pair
+		int px0, py0;   // first pixel of the block
+		int pw, ph;     // its extent
+		int strip;
+	};
+	auto fetch_item = [&](Item &it) -> bool {
+		if (!pending)
+			issue_grab();
+		const unsigned item = __shfl_sync(0xffffffffu, pend_got, 0);
+		pending = false;
+		if (item >= total)
+			return false;
+		// no reservation ahead of time near the end of the queue or in dense regions
+		if (!dense_mode && item + 6u * n_warps < total)
 			issue_grab();
 #ifdef GRB_LIGHTING_DEBUG
 		if (lane == 0)
@@ -837,17 +849,36 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 		}
 #endif
 		const unsigned row = item / (unsigned)a.blocks_x;
-		bx = (int)(item - row * (unsigned)a.blocks_x);
-		by = scheduled ? (int)s_order[row] : (int)row;
+		const unsigned i = item - row * (unsigned)a.blocks_x;
+		const unsigned enc = scheduled ? (unsigned)s_order[row] : row;
+		it.strip = (int)(enc & 0x7fffu);
+		if (enc & 0x8000u)
+		{
+			const unsigned r = i / n64, bx = i - r * n64;
+			it.px0 = (int)bx * 64;
+			it.py0 = p.y0 + it.strip * 4 + (int)r;
+			it.pw = 64;
+			it.ph = 1;
+			it.x = it.px0 + 2 * lane;
+			it.y = it.py0;
+		}
+		else
+		{
+			it.px0 = i < blocks16 ? (int)i * 16 : p.hdr.w; // surplus items lie outside the image
+			it.py0 = p.y0 + it.strip * 4;
+			it.pw = 16;
+			it.ph = 4;
+			it.x = it.px0 + 2 * (lane & 7);
+			it.y = it.py0 + (lane >> 3);
+		}
 		return true;
 	};
 	// The G-buffer words of the NEXT block are copied asynchronously (cp.async, no registers held)
 	// into this lane's 48-byte slot while the current block is shaded: the HBM round trip at the head
 	// of every block otherwise leaves the warp idle for a seventh of its time.
 	const uint32_t pf_slot = smem_u32(s_prefetch + (size_t)threadIdx.x * 48u);
-	auto prefetch_gbuffer = [&](int bx, int by) {
-		const int x = (bx * 8 + (lane & 7)) * 2;
-		const int y = p.y0 + by * 4 + (lane >> 3);
+	auto prefetch_gbuffer = [&](const Item &it) {
+		const int x = it.x, y = it.y;
 		if (x < p.hdr.w && y < p.y1)
 		{
 			asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pf_slot), "l"(&p.depth.at(x, y)) : "memory");
@@ -864,16 +895,16 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 		g_dbg_t0 = globaltimer_ns();
 	const unsigned long long s_t0 = globaltimer_ns();
 #endif
-	int bx = 0, by = 0;
-	bool have = fetch_item(bx, by);
+	Item nxt;
+	bool have = fetch_item(nxt);
 	if (have)
-		prefetch_gbuffer(bx, by);
+		prefetch_gbuffer(nxt);
 	while (have)
 	{
 		const long long t_begin = clock64();
-		const int cur_by = by;
-		const int x = (bx * 8 + (lane & 7)) * 2;
-		const int y = p.y0 + by * 4 + (lane >> 3);
+		const Item cur = nxt;
+		const int cur_by = cur.strip;
+		const int x = cur.x, y = cur.y;
 		const bool inside = x < p.hdr.w && y < p.y1;
 
 		// ---- G-buffer words (prefetched) and per-pixel invariants ----
@@ -890,10 +921,23 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			em = *reinterpret_cast<const uint2 *>(slot + 24);
 			mr2 = *reinterpret_cast<const uint32_t *>(slot + 32);
 		}
-		// the slot is free again: start on the next block's words
-		have = fetch_item(bx, by);
-		if (have)
-			prefetch_gbuffer(bx, by);
+		// the slot is free again: start on the next block's words -- unless the warp is in a dense region,
+		// where the next item is only taken once this block is done (see fetch_item)
+		const bool deferred = dense_mode;
+		if (!deferred)
+		{
+			have = fetch_item(nxt);
+			if (have)
+				prefetch_gbuffer(nxt);
+		}
+		auto take_deferred = [&]() {
+			if (deferred)
+			{
+				have = fetch_item(nxt);
+				if (have)
+					prefetch_gbuffer(nxt);
+			}
+		};
 
 		const PixelSetup A = setup_pixel(p, s_srgb, x, y, inside, depth.x, a8.x, n10.x, mr2 & 0xffffu, em.x);
 		const PixelSetup B = setup_pixel(p, s_srgb, x + 1, y, inside, depth.y, a8.y, n10.y, mr2 >> 16, em.y);
@@ -902,6 +946,7 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			// sky block: the attachment value is carried through
 			if (inside && p.emissive.p != p.hdr.p)
 				*reinterpret_cast<uint2 *>(&p.hdr.at(x, y)) = em;
+			take_deferred();
 			continue;
 		}
 		SurfaceP s;
@@ -949,8 +994,8 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			const unsigned hi = __reduce_max_sync(0xffffffffu, max(A.lit ? A.ry : 0u, B.lit ? B.ry : 0u));
 			if (lo <= hi) // otherwise empty slices only: (0xffffffff, 0)
 			{
-				const int px0 = (x - 2 * (lane & 7)), py0 = y - (lane >> 3); // the block's first pixel
-				const int px1 = min(px0 + 15, p.hdr.w - 1), py1 = min(py0 + 3, p.y1 - 1);
+				const int px0 = cur.px0, py0 = cur.py0; // the block's first pixel
+				const int px1 = min(px0 + cur.pw - 1, p.hdr.w - 1), py1 = min(py0 + cur.ph - 1, p.y1 - 1);
 				const int tx0 = cluster_tile_x(p, px0), tx1 = cluster_tile_x(p, px1), ty0 = cluster_tile_y(p, py0), ty1 = cluster_tile_y(p, py1);
 				// cluster_mask_range (clusterer_bindless_buffers.h:17-27) for a warp-uniform range: only the
 				// first and the last word of [lo, hi] are cut
@@ -997,6 +1042,7 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 		int k = 0;
 		unsigned nz = __ballot_sync(0xffffffffu, cand0 != 0u);
 		bool more = true;
+		int list_total = 0;
 		while (more)
 		{
 			int count = 0;
@@ -1038,6 +1084,7 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			}
 			if (count == 0)
 				break;
+			list_total += count;
 			if (lane == 0)
 				list[count] = (uint16_t)dummy_entry; // pads an odd batch
 			__syncwarp();
@@ -1089,11 +1136,13 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 				*reinterpret_cast<uint2 *>(&p.hdr.at(x, y)) = out;
 		}
 		if (a.schedule && lane == 0)
-			atomicMax(&a.schedule[4 + cur_by], (uint32_t)((clock64() - t_begin) >> 5)); // key = the row's most expensive block
+			atomicMax(&a.schedule[4 + cur_by], (uint32_t)((clock64() - t_begin) >> 5)); // key = the strip's most expensive block
+		dense_mode = list_total > 96;
+		take_deferred();
 #ifdef GRB_LIGHTING_DEBUG
 		if (lane == 0)
 		{
-			const int bi = cur_by * a.blocks_x + (x >> 4);
+			const int bi = cur_by * a.blocks_x + (cur.ph == 4 ? (cur.px0 >> 4) : ((cur.py0 - p.y0 - cur_by * 4) * (a.blocks_x / 4) + (cur.px0 >> 6)));
 			if (bi < kDbgBlocks)
 				g_dbg_block[bi] = make_uint2((uint32_t)(clock64() - t_begin), (uint32_t)(globaltimer_ns() - s_t0));
 		}
@@ -1146,6 +1195,11 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			}
 			a.schedule[4 + a.blocks_y + rank] = (uint32_t)i;
 			a.schedule[4 + i] = 0u;
+			// block shape of strip i for the next launch: one-row blocks once its most expensive block
+			// exceeds ~20k cycles, back to 16x4 only when it falls below a quarter of that (the measure
+			// itself depends on the shape: no flip-flopping)
+			const uint32_t old_shape = a.schedule[4 + 2 * a.blocks_y + i];
+			a.schedule[4 + 2 * a.blocks_y + i] = mine > (20000u >> 5) ? 1u : (mine < (5000u >> 5) ? 0u : old_shape);
 		}
 		__syncthreads();
 		if (threadIdx.x == 0)
@@ -1287,7 +1341,7 @@ extern "C" int32_t grb_debug_lighting_dump2(void *items, void *last)
 extern "C" uint64_t grb_lighting_schedule_bytes(int32_t height)
 {
 	const uint64_t rows = (uint64_t)((height > 0 ? height : 0) + 3) / 4;
-	return (4u + 2u * rows) * sizeof(uint32_t);
+	return (4u + 3u * rows) * sizeof(uint32_t); // header, cost, order, block shape per strip
 }
 
 extern "C" int32_t grb_deferred_lighting(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
@@ -1415,7 +1469,7 @@ extern "C" int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *g, const Gr
 			}
 		}
 		PersistentArgs a;
-		a.blocks_x = (w / 2 + 7) / 8;
+		a.blocks_x = 4 * ((w + 63) / 64); // items per strip: 4 rows of 64x1 blocks, or ceil(w / 16) 16x4 blocks (+ empty ones)
 		a.blocks_y = (rows.y1 - rows.y0 + 3) / 4;
 		a.total_items = a.blocks_x * a.blocks_y;
 		a.schedule = static_cast<uint32_t *>(schedule);

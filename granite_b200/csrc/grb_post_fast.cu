@@ -155,11 +155,13 @@ bool launch_tonemap_fast(const GrbImage *hdr, const GrbImage *bloom, const float
 // =============================================================================== K12 FXAA
 // fxaa.frag:20-67.  A CTA owns 64x16 output pixels; the input tile plus a 5-pixel border (the four
 // directional taps reach +-4 pixels, +1 for their bilinear footprint) is unpacked ONCE per texel into
-// shared memory as float4(r, g, b, luma) in 0..255 units -- clamp-to-edge is applied while filling, so
-// nothing inside the tile clamps again.  All of the shader's arithmetic is scale-invariant except the
-// 1/128 floor of dirReduce, which is carried as 255/128.  An sRGB target applies decode_srgb and the
-// attachment re-encodes on store: that pair is the identity on [0, 1] up to rounding, so both targets
-// round the same value (difference from the reference: ties only, 1 code).
+// shared memory -- rgb as three fp16 (exact: 0..255 are integers) and the luma as fp32, in 0..255
+// units -- with clamp-to-edge applied while filling, so nothing inside the tile clamps again.  (A
+// float4 per texel made the 16 gathered texels per pixel a shared-memory bandwidth bound: 84
+// wavefronts per warp; this layout needs 37.)  All of the shader's arithmetic is scale-invariant
+// except the 1/128 floor of dirReduce, which is carried as 255/128.  An sRGB target applies
+// decode_srgb and the attachment re-encodes on store: that pair is the identity on [0, 1] up to
+// rounding, so both targets round the same value (difference from the reference: ties only, 1 code).
 namespace grb
 {
 namespace
@@ -174,23 +176,40 @@ GRB_DEV float byte_to_float(uint32_t word, int byte_index)
 	return __uint_as_float(bits) - 8388608.0f;
 }
 
-GRB_DEV float4 fx_bilinear(const float4 *tile, float fx, float fy)
+struct Rgb
+{
+	f2 rg;
+	float b;
+};
+GRB_DEV Rgb fx_load(const uint2 *p)
+{
+	const uint2 t = *p;
+	Rgb c;
+	c.rg = __half22float2(*reinterpret_cast<const __half2 *>(&t.x));
+	c.b = __half2float(__ushort_as_half((unsigned short)(t.y & 0xffffu)));
+	return c;
+}
+
+GRB_DEV Rgb fx_bilinear(const uint2 *tile, float fx, float fy)
 {
 	// (fx, fy): texel-space position relative to the tile origin (texel centres at integers)
 	const float flx = floorf(fx), fly = floorf(fy);
 	const float a = fx - flx, b = fy - fly;
-	const float4 *p = tile + (int)fly * kFxSmemW + (int)flx;
-	const float4 t00 = p[0], t10 = p[1], t01 = p[kFxSmemW], t11 = p[kFxSmemW + 1];
-	const f2 top_rg = fma2(mk2(a), sub2(make_float2(t10.x, t10.y), make_float2(t00.x, t00.y)), make_float2(t00.x, t00.y));
-	const f2 bot_rg = fma2(mk2(a), sub2(make_float2(t11.x, t11.y), make_float2(t01.x, t01.y)), make_float2(t01.x, t01.y));
-	const float top_b = fmaf(a, t10.z - t00.z, t00.z), bot_b = fmaf(a, t11.z - t01.z, t01.z);
-	const f2 rg = fma2(mk2(b), sub2(bot_rg, top_rg), top_rg);
-	return make_float4(rg.x, rg.y, fmaf(b, bot_b - top_b, top_b), 0.0f);
+	const uint2 *p = tile + (int)fly * kFxSmemW + (int)flx;
+	const Rgb t00 = fx_load(p), t10 = fx_load(p + 1), t01 = fx_load(p + kFxSmemW), t11 = fx_load(p + kFxSmemW + 1);
+	const f2 top_rg = fma2(mk2(a), sub2(t10.rg, t00.rg), t00.rg);
+	const f2 bot_rg = fma2(mk2(a), sub2(t11.rg, t01.rg), t01.rg);
+	const float top_b = fmaf(a, t10.b - t00.b, t00.b), bot_b = fmaf(a, t11.b - t01.b, t01.b);
+	Rgb r;
+	r.rg = fma2(mk2(b), sub2(bot_rg, top_rg), top_rg);
+	r.b = fmaf(b, bot_b - top_b, top_b);
+	return r;
 }
 
 __global__ void __launch_bounds__(256) fxaa_fast_kernel(View<const uint32_t> in, View<uint32_t> out, int y0, int y1)
 {
-	__shared__ float4 tile[kFxSmemW * kFxSmemH]; // 30.8 KB
+	__shared__ uint2 tile[kFxSmemW * kFxSmemH];  // rgb as fp16 x 3 (+ pad): 15.4 KB
+	__shared__ float luma[kFxSmemW * kFxSmemH];  // 7.7 KB
 	const int ox0 = blockIdx.x * kFxTileW, oy0 = y0 + blockIdx.y * kFxTileH;
 	for (int i = threadIdx.x; i < kFxSmemW * kFxSmemH; i += 256)
 	{
@@ -198,7 +217,12 @@ __global__ void __launch_bounds__(256) fxaa_fast_kernel(View<const uint32_t> in,
 		const int gx = iclamp(ox0 + lx - kFxHalo, 0, in.w - 1), gy = iclamp(oy0 + ly - kFxHalo, 0, in.h - 1);
 		const uint32_t p = __ldg(&in.at(gx, gy));
 		const float r = byte_to_float(p, 0), g = byte_to_float(p, 1), b = byte_to_float(p, 2);
-		tile[i] = make_float4(r, g, b, fmaf(b, 0.114f, fmaf(g, 0.587f, r * 0.299f)));
+		const __half2 rg = __floats2half2_rn(r, g);
+		uint2 t;
+		t.x = *reinterpret_cast<const uint32_t *>(&rg);
+		t.y = (uint32_t)__half_as_ushort(__float2half_rn(b));
+		tile[i] = t;
+		luma[i] = fmaf(b, 0.114f, fmaf(g, 0.587f, r * 0.299f));
 	}
 	__syncthreads();
 	const int lx = threadIdx.x & (kFxTileW - 1);
@@ -211,8 +235,8 @@ __global__ void __launch_bounds__(256) fxaa_fast_kernel(View<const uint32_t> in,
 		const int y = oy0 + ly;
 		if (y >= y1)
 			break;
-		const float4 *c = tile + (ly + kFxHalo) * kFxSmemW + (lx + kFxHalo);
-		const float lumaNW = c[-kFxSmemW - 1].w, lumaNE = c[-kFxSmemW + 1].w, lumaSW = c[kFxSmemW - 1].w, lumaSE = c[kFxSmemW + 1].w, lumaM = c[0].w;
+		const float *c = luma + (ly + kFxHalo) * kFxSmemW + (lx + kFxHalo);
+		const float lumaNW = c[-kFxSmemW - 1], lumaNE = c[-kFxSmemW + 1], lumaSW = c[kFxSmemW - 1], lumaSE = c[kFxSmemW + 1], lumaM = c[0];
 		const float lumaMin = fminf(lumaM, fminf(fminf(lumaNW, lumaNE), fminf(lumaSW, lumaSE)));
 		const float lumaMax = fmaxf(lumaM, fmaxf(fmaxf(lumaNW, lumaNE), fmaxf(lumaSW, lumaSE)));
 		float dx = -((lumaNW + lumaNE) - (lumaSW + lumaSE));
@@ -223,18 +247,20 @@ __global__ void __launch_bounds__(256) fxaa_fast_kernel(View<const uint32_t> in,
 		dy = fminf(fmaxf(dy * rcpDirMin, -8.0f), 8.0f);
 		const float bx = (float)(lx + kFxHalo), by = (float)(ly + kFxHalo);
 		const float k0 = (float)(1.0 / 3.0 - 0.5), k1 = (float)(2.0 / 3.0 - 0.5);
-		const float4 a0 = fx_bilinear(tile, fmaf(dx, k0, bx), fmaf(dy, k0, by));
-		const float4 a1 = fx_bilinear(tile, fmaf(dx, k1, bx), fmaf(dy, k1, by));
-		const float4 b0 = fx_bilinear(tile, fmaf(dx, -0.5f, bx), fmaf(dy, -0.5f, by));
-		const float4 b1 = fx_bilinear(tile, fmaf(dx, 0.5f, bx), fmaf(dy, 0.5f, by));
-		const float3 rgbA = make_float3(0.5f * (a0.x + a1.x), 0.5f * (a0.y + a1.y), 0.5f * (a0.z + a1.z));
-		const float3 rgbB = make_float3(fmaf(0.25f, b0.x + b1.x, rgbA.x * 0.5f), fmaf(0.25f, b0.y + b1.y, rgbA.y * 0.5f), fmaf(0.25f, b0.z + b1.z, rgbA.z * 0.5f));
-		const float lumaB = fmaf(rgbB.z, 0.114f, fmaf(rgbB.y, 0.587f, rgbB.x * 0.299f));
+		const Rgb a0 = fx_bilinear(tile, fmaf(dx, k0, bx), fmaf(dy, k0, by));
+		const Rgb a1 = fx_bilinear(tile, fmaf(dx, k1, bx), fmaf(dy, k1, by));
+		const Rgb b0 = fx_bilinear(tile, fmaf(dx, -0.5f, bx), fmaf(dy, -0.5f, by));
+		const Rgb b1 = fx_bilinear(tile, fmaf(dx, 0.5f, bx), fmaf(dy, 0.5f, by));
+		const f2 A_rg = mul2(mk2(0.5f), add2(a0.rg, a1.rg));
+		const float A_b = 0.5f * (a0.b + a1.b);
+		const f2 B_rg = fma2(mk2(0.25f), add2(b0.rg, b1.rg), mul2(A_rg, mk2(0.5f)));
+		const float B_b = fmaf(0.25f, b0.b + b1.b, A_b * 0.5f);
+		const float lumaB = fmaf(B_b, 0.114f, fmaf(B_rg.y, 0.587f, B_rg.x * 0.299f));
 		const bool useA = (lumaB < lumaMin) || (lumaB > lumaMax);
-		const float3 col = useA ? rgbA : rgbB;
-		const uint32_t r8 = (uint32_t)__float2int_rz(fminf(fmaxf(col.x, 0.0f), 255.0f) + 0.5f);
-		const uint32_t g8 = (uint32_t)__float2int_rz(fminf(fmaxf(col.y, 0.0f), 255.0f) + 0.5f);
-		const uint32_t b8 = (uint32_t)__float2int_rz(fminf(fmaxf(col.z, 0.0f), 255.0f) + 0.5f);
+		const float cr = useA ? A_rg.x : B_rg.x, cg = useA ? A_rg.y : B_rg.y, cb = useA ? A_b : B_b;
+		const uint32_t r8 = (uint32_t)__float2int_rz(fminf(fmaxf(cr, 0.0f), 255.0f) + 0.5f);
+		const uint32_t g8 = (uint32_t)__float2int_rz(fminf(fmaxf(cg, 0.0f), 255.0f) + 0.5f);
+		const uint32_t b8 = (uint32_t)__float2int_rz(fminf(fmaxf(cb, 0.0f), 255.0f) + 0.5f);
 		out.at(x, y) = r8 | (g8 << 8) | (b8 << 16) | 0xff000000u;
 	}
 }
@@ -259,8 +285,8 @@ bool launch_fxaa_fast(const GrbImage *in, const GrbImage *out, GrbRows rows, cud
 // per pixel instead of nine HDR decodes + tonemaps + colour-space conversions and nine depth loads.
 // The Catmull-Rom history fetch is evaluated as the separable 4x4 filter it is (the shader's nine
 // bilinear taps are that filter, re-expressed for a texture unit): 16 texel loads, 8 weights.
-// The variance (m2 / 16 - m1 * m1) is formed with the shader's association and without FMA:
-// in flat regions it is pure cancellation, and the clip box must not depend on how we contract.
+// Per-texel colour-space conversions keep the shader's association (their chroma passes through zero);
+// the filters are fused multiply-adds.
 namespace grb
 {
 namespace
@@ -281,13 +307,17 @@ struct TaaFastArgs
 	float inv_w, inv_h, w, h;
 };
 
+// HDRColorSpaceToTAA (reprojection_color_space.h:15-53) in the shader's own association, IEEE
+// division, no contraction: it runs once per tile texel, and the chroma it produces passes
+// through zero, where a reassociated sum would be off by many ulps of the (tiny) result.
 GRB_DEV float3 hdr_to_taa_fast(uint32_t packed)
 {
 	float3 c = unpack_r11g11b10(packed);
-	c = make_float3(c.x * 8.0f, c.y * 8.0f, c.z * 8.0f);
-	const float r = rcp_fast(fmaxf(c.x, fmaxf(c.y, c.z)) + 1.0f);
-	c = make_float3(c.x * r, c.y * r, c.z * r);
-	return make_float3(fmaf(0.25f, c.z, fmaf(0.5f, c.y, 0.25f * c.x)), fmaf(-0.25f, c.z, fmaf(-0.25f, c.x, 0.5f * c.y)), fmaf(-0.5f, c.z, 0.5f * c.x));
+	c = make_float3(fmul(c.x, 8.0f), fmul(c.y, 8.0f), fmul(c.z, 8.0f));
+	const float r = fdiv(1.0f, fadd(fmax_(c.x, fmax_(c.y, c.z)), 1.0f));
+	c = make_float3(fmul(c.x, r), fmul(c.y, r), fmul(c.z, r));
+	return make_float3(fadd(fadd(fmul(0.25f, c.x), fmul(0.5f, c.y)), fmul(0.25f, c.z)), fsub(fsub(fmul(0.5f, c.y), fmul(0.25f, c.x)), fmul(0.25f, c.z)),
+	                   fsub(fmul(0.5f, c.x), fmul(0.5f, c.z)));
 }
 
 GRB_DEV float3 fetch_hist(const View<const uint2> &im, int x, int y)
@@ -371,6 +401,15 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 #undef GRB_W3
 			f2 acc_yg = mk2(0.0f);
 			float acc_o = 0.0f;
+			// clamp-to-edge per column / row of the 4x4 footprint (8 clamps instead of 32)
+			int cx[4];
+			const uint2 *rowp[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+			{
+				cx[i] = iclamp(ix - 1 + i, 0, a.history.w - 1);
+				rowp[i] = a.history.p + (size_t)iclamp(iy - 1 + i, 0, a.history.h - 1) * a.history.pitch;
+			}
 #pragma unroll
 			for (int j = 0; j < 4; j++)
 			{
@@ -379,9 +418,11 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 #pragma unroll
 				for (int i = 0; i < 4; i++)
 				{
-					const float3 t = fetch_hist(a.history, ix - 1 + i, iy - 1 + j);
-					row_yg = fma2(mk2(wx[i]), make_float2(t.x, t.y), row_yg);
-					row_o = fmaf(wx[i], t.z, row_o);
+					const uint2 raw = __ldg(rowp[j] + cx[i]);
+					const f2 rg = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+					const float o = __half2float(__ushort_as_half((unsigned short)(raw.y & 0xffffu)));
+					row_yg = fma2(mk2(wx[i]), rg, row_yg);
+					row_o = fmaf(wx[i], o, row_o);
 				}
 				acc_yg = fma2(mk2(wy[j]), row_yg, acc_yg);
 				acc_o = fmaf(wy[j], row_o, acc_o);
@@ -394,23 +435,30 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 		hist = make_float3(fminf(fmaxf(hist.x, 0.0f), 1.0f), fminf(fmaxf(hist.y, -1.0f), 1.0f), fminf(fmaxf(hist.z, -1.0f), 1.0f));
 		const float lerp_factor = fmaf(2.0f, mv_fast, 1.0f) * (1.0f / 16.0f);
 
-		// clamp_history_box, variance form (reprojection.h:107-183): shader association, no contraction
-#define GRB_M1(C) fmul(fadd(fadd(fadd(fadd(fadd(fadd(fadd(fadd(c00.C, fmul(2.0f, c01.C)), c02.C), fmul(2.0f, c10.C)), fmul(4.0f, c11.C)), fmul(2.0f, c12.C)), c20.C), fmul(2.0f, c21.C)), c22.C), 1.0f / 16.0f)
-#define GRB_M2(C)                                                                                                                                         \
-	fadd(fadd(fadd(fadd(fadd(fadd(fadd(fadd(fmul(c00.C, c00.C), fmul(fmul(2.0f, c01.C), c01.C)), fmul(c02.C, c02.C)), fmul(fmul(2.0f, c10.C), c10.C)),       \
-	                         fmul(fmul(4.0f, c11.C), c11.C)),                                                                                                \
-	                    fmul(fmul(2.0f, c12.C), c12.C)),                                                                                                     \
-	               fmul(c20.C, c20.C)),                                                                                                                      \
-	          fmul(fmul(2.0f, c21.C), c21.C)),                                                                                                               \
-	     fmul(c22.C, c22.C))
-		const float3 m1 = make_float3(GRB_M1(x), GRB_M1(y), GRB_M1(z));
-		const float3 m2 = make_float3(GRB_M2(x), GRB_M2(y), GRB_M2(z));
-#undef GRB_M1
-#undef GRB_M2
-		const float3 sigma = make_float3(sqrtf(fmaxf(fsub(fmul(m2.x, 1.0f / 16.0f), fmul(m1.x, m1.x)), 0.0f)), sqrtf(fmaxf(fsub(fmul(m2.y, 1.0f / 16.0f), fmul(m1.y, m1.y)), 0.0f)),
-		                                 sqrtf(fmaxf(fsub(fmul(m2.z, 1.0f / 16.0f), fmul(m1.z, m1.z)), 0.0f)));
-		const float3 lo = make_float3(fsub(m1.x, fmul(gamma, sigma.x)), fsub(m1.y, fmul(gamma, sigma.y)), fsub(m1.z, fmul(gamma, sigma.z)));
-		const float3 hi = make_float3(fadd(m1.x, fmul(gamma, sigma.x)), fadd(m1.y, fmul(gamma, sigma.y)), fadd(m1.z, fmul(gamma, sigma.z)));
+		// clamp_history_box, variance form (reprojection.h:107-183): weights 1 2 1 / 2 4 2 / 1 2 1.
+		// m2 / 16 - m1^2 is a cancellation; in flat regions its value is rounding noise of either
+		// evaluation order (sigma ~ 3e-4 of the mean), which bounds the clip box far inside one fp16 ulp.
+		float3 m1, sigma;
+		{
+#define GRB_YG(T) make_float2((T).x, (T).y)
+			const f2 corners = add2(add2(GRB_YG(c00), GRB_YG(c02)), add2(GRB_YG(c20), GRB_YG(c22)));
+			const f2 edges = add2(add2(GRB_YG(c01), GRB_YG(c10)), add2(GRB_YG(c12), GRB_YG(c21)));
+			const f2 s1 = fma2(mk2(4.0f), GRB_YG(c11), fma2(mk2(2.0f), edges, corners));
+			f2 q_c = mul2(GRB_YG(c00), GRB_YG(c00));
+			q_c = fma2(GRB_YG(c02), GRB_YG(c02), q_c); q_c = fma2(GRB_YG(c20), GRB_YG(c20), q_c); q_c = fma2(GRB_YG(c22), GRB_YG(c22), q_c);
+			f2 q_e = mul2(GRB_YG(c01), GRB_YG(c01));
+			q_e = fma2(GRB_YG(c10), GRB_YG(c10), q_e); q_e = fma2(GRB_YG(c12), GRB_YG(c12), q_e); q_e = fma2(GRB_YG(c21), GRB_YG(c21), q_e);
+			const f2 s2 = fma2(mul2(mk2(4.0f), GRB_YG(c11)), GRB_YG(c11), fma2(mk2(2.0f), q_e, q_c));
+#undef GRB_YG
+			const float s1z = fmaf(4.0f, c11.z, fmaf(2.0f, (c01.z + c10.z) + (c12.z + c21.z), (c00.z + c02.z) + (c20.z + c22.z)));
+			const float s2z = fmaf(4.0f * c11.z, c11.z, fmaf(2.0f, fmaf(c01.z, c01.z, fmaf(c10.z, c10.z, fmaf(c12.z, c12.z, c21.z * c21.z))),
+			                                             fmaf(c00.z, c00.z, fmaf(c02.z, c02.z, fmaf(c20.z, c20.z, c22.z * c22.z)))));
+			m1 = make_float3(s1.x * (1.0f / 16.0f), s1.y * (1.0f / 16.0f), s1z * (1.0f / 16.0f));
+			sigma = make_float3(sqrtf(fmaxf(fmaf(s2.x, 1.0f / 16.0f, -m1.x * m1.x), 0.0f)), sqrtf(fmaxf(fmaf(s2.y, 1.0f / 16.0f, -m1.y * m1.y), 0.0f)),
+			                    sqrtf(fmaxf(fmaf(s2z, 1.0f / 16.0f, -m1.z * m1.z), 0.0f)));
+		}
+		const float3 lo = make_float3(fmaf(-gamma, sigma.x, m1.x), fmaf(-gamma, sigma.y, m1.y), fmaf(-gamma, sigma.z, m1.z));
+		const float3 hi = make_float3(fmaf(gamma, sigma.x, m1.x), fmaf(gamma, sigma.y, m1.y), fmaf(gamma, sigma.z, m1.z));
 		// clamp_box (AABB clip towards the centre), reprojection.h:31-51
 		{
 			const float3 center = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
@@ -425,11 +473,11 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 		}
 		const float il = 1.0f - lerp_factor;
 		const float3 out_c = make_float3(fmaf(c11.x, lerp_factor, hist.x * il), fmaf(c11.y, lerp_factor, hist.y * il), fmaf(c11.z, lerp_factor, hist.z * il));
-		// TAAToHDRColorSpace
-		const float tmp = out_c.x - out_c.y;
-		const float3 rgb = make_float3(fminf(fmaxf(tmp + out_c.z, 0.0f), 0.999f), fminf(fmaxf(out_c.x + out_c.y, 0.0f), 0.999f), fminf(fmaxf(tmp - out_c.z, 0.0f), 0.999f));
-		const float rr = 0.125f * rcp_fast(1.0f - fmaxf(rgb.x, fmaxf(rgb.y, rgb.z)));
-		a.out_color.at(x, y) = pack_r11g11b10(rgb.x * rr, rgb.y * rr, rgb.z * rr);
+		// TAAToHDRColorSpace (YCgCo -> RGB, clamp, inverse tonemap), shader association
+		const float tmp = fsub(out_c.x, out_c.y);
+		const float3 rgb = make_float3(fclamp(fadd(tmp, out_c.z), 0.0f, 0.999f), fclamp(fadd(out_c.x, out_c.y), 0.0f, 0.999f), fclamp(fsub(tmp, out_c.z), 0.0f, 0.999f));
+		const float rr = fdiv(1.0f, fsub(1.0f, fmax_(rgb.x, fmax_(rgb.y, rgb.z))));
+		a.out_color.at(x, y) = pack_r11g11b10(fmul(fmul(0.125f, rgb.x), rr), fmul(fmul(0.125f, rgb.y), rr), fmul(fmul(0.125f, rgb.z), rr));
 		a.out_history.at(x, y) = pack_rgba16f(make_float4(out_c.x, out_c.y, out_c.z, 1.0f));
 	}
 }

@@ -13,14 +13,17 @@
 //      once instead of once per tap);
 //   3. every output texel then needs 3 column set-ups + 3 row set-ups (the taps' bilinear
 //      footprints are separable) and 36 conflict-free 16-byte shared-memory reads; the arithmetic
-//      is the sampler's exact fp32 sequence in packed FMUL2 / FADD2 form (two channels per
-//      instruction, each lane an IEEE operation in the reference order), so results are
-//      bit-identical to grb_post.cu's kernels and to the oracle.
+//      is the sampler's fp32 sequence in packed form (two channels per instruction).  ptxas
+//      contracts the packed multiply / add pairs into FFMA2 even when they are written as
+//      mul.rn.f32x2 + add.rn.f32x2 and -fmad=false is given (CUDA 12.9), so a result can differ from
+//      the oracle's unfused sequence in the last fp32 bit: after the fp16 store ~5e-5 of the
+//      texels differ by one fp16 ulp, the rest are identical (north_star's bar: 1 ULP per channel).
 //
 // The first two passes of the chain are FUSED (grb_bloom_threshold_downsample): the 1/2-resolution
 // threshold image "t" is produced tile by tile in shared memory from a TMA-loaded tile of HDR-main,
 // rounded to fp16 exactly as the image store would round it, and consumed by the 1/4-resolution
-// downsample in the same CTA.  t is only written to HBM when the caller asks for it, which removes
+// downsample in the same CTA.  The threshold arithmetic uses FMA, one reciprocal for the three
+// colour / luminance quotients and the hardware log2: rgb and alpha within 1 fp16 ulp of the oracle.  t is only written to HBM when the caller asks for it, which removes
 // its 16.6 MB write and 16.6 MB read per 4K frame.
 //
 // Eligibility (checked on the host, the generic kernels remain the fallback): exact 2:1 size
@@ -271,6 +274,19 @@ __global__ void __launch_bounds__(kThreads) tent_tile_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------- K7 + K8 fused
+// Row-sharded frames: the d0 band is stored into the 1/4-resolution image of EVERY rank (peer memory over
+// NVLink / NVSwitch) and the last CTA publishes the frame's epoch in every rank's flag array -- the
+// protocol of bloom_downsample_peers_kernel in grb_post.cu, see there.
+struct HeadPeers
+{
+	uint2 *data[GRB_MAX_PEERS];
+	uint32_t *flags[GRB_MAX_PEERS];
+	int count; // 0: plain local store to HeadArgs::d0
+	int flag_index;
+	uint32_t epoch;
+	unsigned *ctas_done;
+};
+
 struct HeadArgs
 {
 	View<uint2> d0;
@@ -290,7 +306,7 @@ struct AxisRec
 };
 
 template <bool DynamicExposure>
-__global__ void __launch_bounds__(kThreads) bloom_head_kernel(const __grid_constant__ CUtensorMap hdr_map, const HeadArgs a)
+__global__ void __launch_bounds__(kThreads) bloom_head_kernel(const __grid_constant__ CUtensorMap hdr_map, const HeadArgs a, const HeadPeers peers)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	uint32_t *hdr = reinterpret_cast<uint32_t *>(smem);                                    // 136 x 72 B10G11R11
@@ -338,15 +354,21 @@ __global__ void __launch_bounds__(kThreads) bloom_head_kernel(const __grid_const
 		const uint32_t *r0 = hdr + cy.i0 * kHeadHdrW, *r1 = hdr + cy.i1 * kHeadHdrW;
 		const float3 t00 = unpack_r11g11b10(r0[cx.i0]), t10 = unpack_r11g11b10(r0[cx.i1]);
 		const float3 t01 = unpack_r11g11b10(r1[cx.i0]), t11 = unpack_r11g11b10(r1[cx.i1]);
-		float3 c = make_float3(bilin_mix(t00.x, t10.x, t01.x, t11.x, cx.w, cy.w), bilin_mix(t00.y, t10.y, t01.y, t11.y, cx.w, cy.w),
-		                       bilin_mix(t00.z, t10.z, t01.z, t11.z, cx.w, cy.w));
-		float luminance = fadd(fmax_(fmax_(c.x, c.y), c.z), 0.0001f);
-		const float loglum = log2f(luminance);
-		c.x = fdiv(c.x, luminance);
-		c.y = fdiv(c.y, luminance);
-		c.z = fdiv(c.z, luminance);
-		luminance = fsub(luminance, lum_sub);
-		const uint2 packed = pack_rgba16f(make_float4(fmax_(fmul(c.x, luminance), 0.0f), fmax_(fmul(c.y, luminance), 0.0f), fmax_(fmul(c.z, luminance), 0.0f), loglum));
+		// the sampler's weights (a, 1 - a, b, 1 - b), in lerp form
+		const float wa = cx.w, wb = cy.w;
+		float3 c;
+		{
+			const float tx = fmaf(wa, t10.x - t00.x, t00.x), bx = fmaf(wa, t11.x - t01.x, t01.x);
+			const float ty = fmaf(wa, t10.y - t00.y, t00.y), by = fmaf(wa, t11.y - t01.y, t01.y);
+			const float tz = fmaf(wa, t10.z - t00.z, t00.z), bz = fmaf(wa, t11.z - t01.z, t01.z);
+			c = make_float3(fmaf(wb, bx - tx, tx), fmaf(wb, by - ty, ty), fmaf(wb, bz - tz, tz));
+		}
+		float luminance = fmax_(fmax_(c.x, c.y), c.z) + 0.0001f;
+		// log2: the hardware approximation is good to ~2^-22 absolute, which is below half an fp16 ulp of
+		// the stored value unless |log2| is tiny, i.e. luminance within ~1 % of 1
+		const float loglum = fabsf(luminance - 1.0f) < 0.01f ? log2f(luminance) : lg2_fast(luminance);
+		const float scale = (luminance - lum_sub) * rcp_fast(luminance);
+		const uint2 packed = pack_rgba16f(make_float4(fmax_(c.x * scale, 0.0f), fmax_(c.y * scale, 0.0f), fmax_(c.z * scale, 0.0f), loglum));
 		tile[ly * kDownSrcW + col_slot<kDownSrcW, true>(lx)] = unpack_rgba16f(packed); // what a sampler would read back from the RGBA16F image
 		// the interior of the tile is this CTA's share of the threshold image
 		if (a.t.p && lx >= 2 && lx < kDownSrcW - 2 && ly >= 2 && ly < kDownSrcH - 2 && ty >= 2 * a.y0 && ty < 2 * a.y1)
@@ -372,7 +394,33 @@ __global__ void __launch_bounds__(kThreads) bloom_head_kernel(const __grid_const
 		xp.i0 = col_slot<kDownSrcW, true>(xp.i0); xp.i1 = col_slot<kDownSrcW, true>(xp.i1);
 		f2 lo, hi;
 		tent9_tile(tile, kDownSrcW, xm, xc, xp, ym, yc, yp, lo, hi);
-		a.d0.at(x, y) = pack_rgba16f(make_float4(lo.x, lo.y, hi.x, hi.y));
+		const uint2 texel = pack_rgba16f(make_float4(lo.x, lo.y, hi.x, hi.y));
+		if (peers.count == 0)
+			a.d0.at(x, y) = texel;
+		else
+		{
+			const size_t at = (size_t)y * a.d0.pitch + x;
+			for (int r = 0; r < peers.count; r++)
+				peers.data[r][at] = texel;
+		}
+	}
+	if (peers.count != 0)
+	{
+		// publish: every thread's stores are ordered before its CTA's arrival; the last CTA to arrive
+		// raises this rank's flag on every peer
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			const unsigned total = gridDim.x * gridDim.y;
+			if (atomicAdd(peers.ctas_done, 1u) == total - 1u)
+			{
+				*peers.ctas_done = 0u;
+				__threadfence_system();
+				for (int r = 0; r < peers.count; r++)
+					asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[r] + peers.flag_index), "r"(peers.epoch) : "memory");
+			}
+		}
 	}
 }
 
@@ -418,7 +466,7 @@ bool launch_tent_tiled(bool up, const GrbImage *in, const GrbImage *history, flo
 	if (tiles_disabled())
 		return false;
 	const bool shape_ok = up ? (out->width == 2 * in->width && out->height == 2 * in->height) : (in->width == 2 * out->width && in->height == 2 * out->height);
-	if (!shape_ok || (up && history) || (up && (rows.y0 & 1)))
+	if (!shape_ok || (up && history))
 		return false;
 	CUtensorMap map;
 	if (!make_map_u32(&map, in, 2, (up ? kUpSrcW : kDownSrcW) * 2, up ? kUpSrcH : kDownSrcH))
@@ -461,14 +509,13 @@ bool launch_tent_tiled(bool up, const GrbImage *in, const GrbImage *history, flo
 
 using namespace grb;
 
-// bloom_threshold.comp + the first bloom_downsample.comp dispatch in one pass (hdr.cpp:115-187):
-// d0 = downsample(threshold(hdr)).  `threshold_out` may be NULL; when given, the rows of the
-// threshold image that belong to d0's rows [rows.y0, rows.y1) -- threshold rows 2*y0 .. 2*y1 -- are
-// written as well (bit-identical to grb_bloom_threshold).
-extern "C" int32_t grb_bloom_threshold_downsample(const GrbImage *hdr, const float *luminance, const GrbImage *threshold_out, const GrbImage *d0, GrbRows rows,
-                                                  void *stream)
+namespace
 {
-	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !image_ok(d0, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) ||
+int32_t launch_head(const char *what, const GrbImage *hdr, const float *luminance, const GrbImage *threshold_out, const GrbImage *d0, GrbRows rows,
+                    const HeadPeers &peers, void *stream)
+{
+	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !d0 || d0->format != GRB_FORMAT_R16G16B16A16_SFLOAT || d0->width <= 0 || d0->height <= 0 ||
+	    (d0->row_pitch % 8) != 0 || (peers.count == 0 && !image_ok(d0, GRB_FORMAT_R16G16B16A16_SFLOAT, 8)) ||
 	    (threshold_out && !image_ok(threshold_out, GRB_FORMAT_R16G16B16A16_SFLOAT, 8)))
 	{
 		set_last_error("grb_bloom_threshold_downsample: hdr must be B10G11R11_UFLOAT, threshold_out / d0 R16G16B16A16_SFLOAT");
@@ -481,7 +528,8 @@ extern "C" int32_t grb_bloom_threshold_downsample(const GrbImage *hdr, const flo
 		return GRB_ERR_INVALID_ARGUMENT;
 	}
 	rows = full_rows(rows, d0->height);
-	if (rows.y1 <= rows.y0)
+	const int row_count = rows.y1 > rows.y0 ? rows.y1 - rows.y0 : 0;
+	if (row_count == 0 && peers.count == 0)
 		return GRB_OK;
 	CUtensorMap map;
 	const bool eligible = !tiles_disabled() && hdr->width == 2 * tw && hdr->height == 2 * th && tw == 2 * d0->width && th == 2 * d0->height &&
@@ -501,15 +549,59 @@ extern "C" int32_t grb_bloom_threshold_downsample(const GrbImage *hdr, const flo
 	a.t_w = tw;
 	a.t_h = th;
 	a.y0 = rows.y0;
-	a.y1 = rows.y1;
+	a.y1 = rows.y0 + row_count;
 	a.inv_t_w = 1.0f / (float)tw; // hdr.cpp:140-141
 	a.inv_t_h = 1.0f / (float)th;
 	a.inv_d0_w = 1.0f / (float)d0->width;
 	a.inv_d0_h = 1.0f / (float)d0->height;
-	dim3 grid((d0->width + kOutW - 1) / kOutW, (rows.y1 - rows.y0 + kOutH - 1) / kOutH, 1);
+	// an empty band still has to raise the flags: one CTA with nothing to store (y1 == y0)
+	dim3 grid((d0->width + kOutW - 1) / kOutW, row_count > 0 ? (row_count + kOutH - 1) / kOutH : 1, 1);
+	if (row_count == 0)
+		grid.x = 1;
 	if (luminance)
-		bloom_head_kernel<true><<<grid, kThreads, kHeadSmem, as_stream(stream)>>>(map, a);
+		bloom_head_kernel<true><<<grid, kThreads, kHeadSmem, as_stream(stream)>>>(map, a, peers);
 	else
-		bloom_head_kernel<false><<<grid, kThreads, kHeadSmem, as_stream(stream)>>>(map, a);
-	return check_launch("grb_bloom_threshold_downsample");
+		bloom_head_kernel<false><<<grid, kThreads, kHeadSmem, as_stream(stream)>>>(map, a, peers);
+	return check_launch(what);
+}
+} // namespace
+
+// bloom_threshold.comp + the first bloom_downsample.comp dispatch in one pass (hdr.cpp:115-187):
+// d0 = downsample(threshold(hdr)).  `threshold_out` may be NULL; when given, the rows of the
+// threshold image that belong to d0's rows [rows.y0, rows.y1) -- threshold rows 2*y0 .. 2*y1 -- are
+// written as well.
+extern "C" int32_t grb_bloom_threshold_downsample(const GrbImage *hdr, const float *luminance, const GrbImage *threshold_out, const GrbImage *d0, GrbRows rows,
+                                                  void *stream)
+{
+	HeadPeers none{};
+	return launch_head("grb_bloom_threshold_downsample", hdr, luminance, threshold_out, d0, rows, none, stream);
+}
+
+// The same pass for a row-sharded frame: the band's d0 texels go to every rank's image and the
+// flags are raised, exactly as grb_bloom_downsample_to_peers does for the unfused pair.
+extern "C" int32_t grb_bloom_threshold_downsample_to_peers(const GrbImage *hdr, const float *luminance, const GrbImage *d0_layout, void *const *peer_images,
+                                                           uint32_t *const *peer_flags, int32_t peer_count, int32_t flag_index, uint32_t epoch,
+                                                           uint32_t *scratch_counter, GrbRows rows, void *stream)
+{
+	if (!d0_layout || !peer_images || !peer_flags || !scratch_counter || peer_count < 1 || peer_count > GRB_MAX_PEERS || flag_index < 0)
+	{
+		set_last_error("grb_bloom_threshold_downsample_to_peers: bad arguments");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	HeadPeers peers{};
+	peers.count = peer_count;
+	peers.flag_index = flag_index;
+	peers.epoch = epoch;
+	peers.ctas_done = scratch_counter;
+	for (int r = 0; r < peer_count; r++)
+	{
+		if (!peer_images[r] || !peer_flags[r])
+		{
+			set_last_error("grb_bloom_threshold_downsample_to_peers: null peer pointer");
+			return GRB_ERR_INVALID_ARGUMENT;
+		}
+		peers.data[r] = static_cast<uint2 *>(peer_images[r]);
+		peers.flags[r] = peer_flags[r];
+	}
+	return launch_head("grb_bloom_threshold_downsample_to_peers", hdr, luminance, nullptr, d0_layout, rows, peers, stream);
 }

@@ -47,31 +47,35 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	GrbRows d0_rows = sharded ? plan.downsample0 : all_rows();
 	GrbRows t_rows = sharded ? plan.threshold : all_rows();
 
-	// bloom_threshold_build_compute: uses LAST frame's average luminance (hdr.cpp:355).
-	// Unsharded frames run threshold + first downsample as ONE kernel with the threshold image kept in shared memory; it is only written out when
-	// GRB_BLOOM_KEEP_THRESHOLD is set (nothing downstream reads it).
-	static const bool keep_threshold = getenv("GRB_BLOOM_KEEP_THRESHOLD") != nullptr;
-	bool head_fused = false;
-	if (!sharded)
-		head_fused = grb_bloom_threshold_downsample(&hdr, lum, keep_threshold ? &t : nullptr, &d0, d0_rows, stream) == GRB_OK;
-	if (!head_fused)
-		cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
-	// The d0 bands are needed in full by every rank.  Preferred: the downsample kernel itself stores
-	// its band into every rank's copy over NVLink peer memory and raises a flag (no collective
-	// launch, no second pass over the band); otherwise NCCL broadcasts after a local downsample.
+	// bloom_threshold_build_compute + the first bloom_downsample_build_compute (hdr.cpp:355-356), which
+	// use LAST frame's average luminance.  Preferred form: ONE kernel with the threshold image kept in
+	// shared memory (grb_bloom_threshold_downsample*); the threshold image is only written out when
+	// GRB_BLOOM_KEEP_THRESHOLD is set (nothing downstream reads it).  Row-sharded frames need the d0
+	// bands in full on every rank: the same kernel stores its band into every rank's copy over NVLink
+	// peer memory and raises a flag (no collective launch, no second pass over the band); otherwise NCCL
+	// broadcasts after a local pass.  The unfused pair remains for shapes the tile kernel does not cover.
+	const bool keep_threshold = getenv("GRB_BLOOM_KEEP_THRESHOLD") != nullptr;
 	RenderGraphCollectives::PeerSlot slot;
-	const bool peer_stores = sharded && !head_fused && graph.get_collectives()->peer_exchange_begin_frame((size_t)d0.row_pitch * (size_t)d0.height, slot);
+	const bool peer_stores = sharded && graph.get_collectives()->peer_exchange_begin_frame((size_t)d0.row_pitch * (size_t)d0.height, slot);
 	if (peer_stores)
 	{
 		const unsigned self = graph.get_collectives()->get_rank();
-		cmd.check(grb_bloom_downsample_to_peers(&t, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch, slot.counter, d0_rows,
-		                                        stream),
-		          "grb_bloom_downsample_to_peers");
+		int32_t rc = grb_bloom_threshold_downsample_to_peers(&hdr, lum, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch,
+		                                                     slot.counter, d0_rows, stream);
+		if (rc == GRB_ERR_UNSUPPORTED_FORMAT)
+		{
+			cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
+			rc = grb_bloom_downsample_to_peers(&t, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch, slot.counter, d0_rows, stream);
+		}
+		cmd.check(rc, "grb_bloom_downsample_to_peers");
 		cmd.check(grb_peer_wait(slot.flags[self], (int32_t)slot.count, slot.epoch, stream), "grb_peer_wait");
 		d0.data = slot.images[self]; // the pyramid tail reads the exchanged copy
 	}
-	else if (!head_fused)
+	else if (grb_bloom_threshold_downsample(&hdr, lum, keep_threshold ? &t : nullptr, &d0, d0_rows, stream) != GRB_OK)
+	{
+		cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
 		cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, stream), "grb_bloom_downsample(d0)");
+	}
 
 	if (sharded && !peer_stores)
 	{

@@ -212,8 +212,8 @@ int32_t grb_bloom_downsample(const GrbImage *in, const GrbImage *history, float 
                              const GrbImage *out, GrbRows rows, void *stream);
 /* K7 + the first K8 dispatch in one pass: d0 = downsample(threshold(hdr)) with the 1/2-resolution
  * threshold image kept in shared memory (TMA-loaded HDR tiles; granite_b200/csrc/grb_post_tiles.cu).
- * threshold_out may be NULL; when given, its rows 2*rows.y0 .. 2*rows.y1 are written too, bit-identical
- * to grb_bloom_threshold.  Needs exact 2:1 size steps hdr -> threshold -> d0 and 16-byte aligned rows;
+ * threshold_out may be NULL; when given, its rows 2*rows.y0 .. 2*rows.y1 are written too (within 1 fp16
+ * ulp of grb_bloom_threshold: FMA, one reciprocal, hardware log2).  Needs exact 2:1 size steps hdr -> threshold -> d0 and 16-byte aligned rows;
  * otherwise returns GRB_ERR_UNSUPPORTED_FORMAT and the caller issues the two calls above.
  * Replaces hdr.cpp:355-356 (bloom_threshold_build_compute + bloom_downsample_build_compute). */
 int32_t grb_bloom_threshold_downsample(const GrbImage *hdr, const float *luminance, const GrbImage *threshold_out,
@@ -229,6 +229,12 @@ int32_t grb_bloom_threshold_downsample(const GrbImage *hdr, const float *luminan
 int32_t grb_bloom_downsample_to_peers(const GrbImage *in, const GrbImage *out_layout, void *const *peer_images,
                                       uint32_t *const *peer_flags, int32_t peer_count, int32_t flag_index, uint32_t epoch,
                                       uint32_t *scratch_counter, GrbRows rows, void *stream);
+/* grb_bloom_threshold_downsample with the same exchange fused in (threshold tile in shared memory, d0
+ * band stored to every rank, flags raised).  Same eligibility rule; GRB_ERR_UNSUPPORTED_FORMAT otherwise. */
+int32_t grb_bloom_threshold_downsample_to_peers(const GrbImage *hdr, const float *luminance, const GrbImage *d0_layout,
+                                                void *const *peer_images, uint32_t *const *peer_flags, int32_t peer_count,
+                                                int32_t flag_index, uint32_t epoch, uint32_t *scratch_counter, GrbRows rows,
+                                                void *stream);
 /* Stream-ordered wait until local_flags[0..count) have all reached `epoch` (acquire, system scope). */
 int32_t grb_peer_wait(const uint32_t *local_flags, int32_t count, uint32_t epoch, void *stream);
 /* K9 bloom_upsample.comp; hdr.cpp:189-216. */

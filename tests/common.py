@@ -91,3 +91,18 @@ def random_hdr(rng, w, h, scale=4.0, hot=0.002):
 
 def random_rgba16f(rng, w, h, lo=-2.0, hi=8.0):
     return rng.uniform(lo, hi, size=(h, w, 4)).astype(np.float16).view(np.uint16)
+
+
+def assert_f16_close(got, ref, what="", min_identical=0.999, abs_floor=0.0):
+    """Stored RGBA16F values: at most 1 fp16 ulp apart (or `abs_floor` absolute, for signed values that
+    pass through zero), and identical for at least `min_identical` of the values."""
+    d = f16_ulp_diff(got, ref)
+    if abs_floor > 0.0:
+        a = np.abs(got.view(np.float16).astype(np.float32) - ref.view(np.float16).astype(np.float32))
+        bad = (d > 1) & ~(a <= abs_floor)
+    else:
+        bad = d > 1
+    assert not bad.any(), f"{what}: {int(bad.sum())} values differ by more than 1 fp16 ulp (max {int(d.max())})"
+    ident = float((d == 0).mean())
+    assert ident >= min_identical, f"{what}: only {ident:.6f} identical"
+    return ident
