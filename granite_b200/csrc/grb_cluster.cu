@@ -6,6 +6,8 @@
 // Replaces LightClusterer::build_cluster_bindless_gpu (renderer/lights/clusterer.cpp:1463-1573).
 #include "grb_common.cuh"
 
+#include <cstdlib>
+
 namespace grb
 {
 namespace
@@ -383,48 +385,51 @@ __global__ void __launch_bounds__(32 * kBinWarps) binning_kernel(BinParams p, co
 
 // ------------------------------------------------------------------------------- K4
 // cluster_range[z] = (first, last) light index whose [zmin, zmax] slice range covers z.
-// The reference scans all lights per slice (O(res_z * N)); integer min/max are order-free, so
-// the same function is built here by scattering each light over its own slices into a
-// shared-memory table with atomicMin/atomicMax (O(sum of slice extents)), one CTA.
-constexpr int kZRangeStaged = 4096;
+// K4 (clusterer_bindless_z_range.comp:20-51): per Z slice, the first and the last light whose slice
+// range contains it.  Integer min / max are order-free, so any decomposition gives the reference's
+// bits.  One CTA owns 32 consecutive slices -- lane = slice -- and its 32 warps split the light list:
+// a warp reads one light's range with a uniform load, skips it when it misses the segment, and
+// otherwise every lane updates its own running (first, last) in registers; the warps' partial results
+// meet in 64 shared-memory words.  No atomics in the loop, no dynamic shared memory, res_z / 32 CTAs
+// instead of one (round 1's single-CTA scatter sat at 0.02 IPC for 25 us).
+constexpr int kZSegWarps = 32;
 
-__global__ void __launch_bounds__(1024) z_range_scatter_kernel(const uint2 *__restrict__ z_ranges, int num_ranges, int res_z,
-                                                              uint2 *__restrict__ cluster_range)
+__global__ void __launch_bounds__(32 * kZSegWarps) z_range_segment_kernel(const uint2 *__restrict__ z_ranges, int num_ranges, int res_z,
+                                                                         uint2 *__restrict__ cluster_range)
 {
-	extern __shared__ uint32_t smem[];
-	uint32_t *lo = smem, *hi = smem + res_z;
-	uint2 *ranges = reinterpret_cast<uint2 *>(smem + 2 * res_z); // staged copy of the per-light ranges
-	for (int z = threadIdx.x; z < res_z; z += blockDim.x)
+	__shared__ uint32_t s_lo[32], s_hi[32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (warp == 0)
 	{
-		lo[z] = 0xffffffffu;
-		hi[z] = 0u;
+		s_lo[lane] = 0xffffffffu;
+		s_hi[lane] = 0u;
 	}
-	const int staged = min(num_ranges, kZRangeStaged);
-	for (int i = threadIdx.x; i < staged; i += blockDim.x)
-		ranges[i] = __ldg(&z_ranges[i]); // coalesced; the scatter below then never waits on L2
 	__syncthreads();
-	// one warp per light, lanes spread over that light's consecutive slices: the atomics of a
-	// warp then hit 32 different shared-memory words instead of serialising on a few (lights are
-	// depth-sorted, so neighbouring lights cover nearly the same slices)
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, num_warps = blockDim.x >> 5;
-	for (int i = warp; i < num_ranges; i += num_warps)
+	const uint32_t seg_lo = blockIdx.x * 32u, seg_hi = seg_lo + 31u;
+	const uint32_t z = seg_lo + (uint32_t)lane;
+	uint32_t lo = 0xffffffffu, hi = 0u;
+	for (int i = warp; i < num_ranges; i += kZSegWarps)
 	{
-		uint2 r = i < staged ? ranges[i] : __ldg(&z_ranges[i]);
-		if (r.x > r.y)
+		const uint2 r = __ldg(&z_ranges[i]);
+		if (r.x > seg_hi || r.y < seg_lo || r.x > r.y)
 			continue;
-		uint32_t zend = min(r.y, (uint32_t)(res_z - 1));
-		for (uint32_t z = r.x + lane; z <= zend; z += 32u)
+		if (z >= r.x && z <= r.y)
 		{
-			atomicMin(&lo[z], (uint32_t)i);
-			atomicMax(&hi[z], (uint32_t)i);
+			lo = min(lo, (uint32_t)i);
+			hi = max(hi, (uint32_t)i);
 		}
 	}
+	if (lo != 0xffffffffu)
+	{
+		atomicMin(&s_lo[lane], lo);
+		atomicMax(&s_hi[lane], hi);
+	}
 	__syncthreads();
-	for (int z = threadIdx.x; z < res_z; z += blockDim.x)
-		cluster_range[z] = make_uint2(lo[z], hi[z]);
+	if (warp == 0 && z < (uint32_t)res_z)
+		cluster_range[z] = make_uint2(s_lo[lane], s_hi[lane]);
 }
 
-// Fallback for res_z too large for shared memory: the reference's per-slice scan.
+// The reference's per-slice scan (O(res_z * N)); kept as a cross-check (GRB_ZRANGE_SCAN).
 __global__ void __launch_bounds__(128) z_range_scan_kernel(const uint2 *__restrict__ z_ranges, int num_ranges, int res_z, uint2 *__restrict__ cluster_range)
 {
 	uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
@@ -548,17 +553,11 @@ extern "C" int32_t grb_cluster_z_range(const GrbClusterBuffers *buf, int32_t num
 		set_last_error("grb_cluster_z_range: null buffer or empty range list (pass one (~0u,0) entry for zero lights)");
 		return GRB_ERR_INVALID_ARGUMENT;
 	}
-	int res_z = buf->resolution_z;
-	size_t smem = (size_t)res_z * 8 + (size_t)kZRangeStaged * 8;
-	static bool smem_opt_in = false; // 64 KiB of dynamic shared memory needs the opt-in once per process
-	if (!smem_opt_in && smem <= 96 * 1024)
-	{
-		cudaFuncSetAttribute(z_range_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-		smem_opt_in = true;
-	}
-	if (smem <= 96 * 1024)
-		z_range_scatter_kernel<<<1, 1024, smem, as_stream(stream)>>>(reinterpret_cast<const uint2 *>(buf->z_ranges), num_ranges, res_z,
-		                                                              reinterpret_cast<uint2 *>(buf->cluster_range));
+	const int res_z = buf->resolution_z;
+	static const bool scan = getenv("GRB_ZRANGE_SCAN") != nullptr; // the reference's per-slice scan, for cross-checks
+	if (!scan)
+		z_range_segment_kernel<<<(res_z + 31) / 32, 32 * kZSegWarps, 0, as_stream(stream)>>>(reinterpret_cast<const uint2 *>(buf->z_ranges), num_ranges, res_z,
+		                                                                                    reinterpret_cast<uint2 *>(buf->cluster_range));
 	else
 		z_range_scan_kernel<<<(res_z + 127) / 128, 128, 0, as_stream(stream)>>>(reinterpret_cast<const uint2 *>(buf->z_ranges), num_ranges, res_z,
 		                                                                         reinterpret_cast<uint2 *>(buf->cluster_range));

@@ -659,6 +659,7 @@ struct PersistentArgs
 	int n_lights;
 	uint32_t *schedule; // optional: [blocks_x, blocks_y, valid, 0][max block cost per strip][strips by falling cost][block shape per strip]
 	unsigned rec_bytes; // n_lights * 48, multiple of 16
+	unsigned row_shape_threshold; // 0 = every strip uses 16x4 blocks (default); else cost (cycles >> 5) above which a strip switches to 64x1 blocks
 	int use_bulk_copy;
 };
 
@@ -1195,11 +1196,13 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			}
 			a.schedule[4 + a.blocks_y + rank] = (uint32_t)i;
 			a.schedule[4 + i] = 0u;
-			// block shape of strip i for the next launch: one-row blocks once its most expensive block
-			// exceeds ~20k cycles, back to 16x4 only when it falls below a quarter of that (the measure
-			// itself depends on the shape: no flip-flopping)
+			// block shape of strip i for the next launch (only when the experiment is switched on, see
+			// PersistentArgs::row_shape_threshold): one-row blocks once its most expensive block exceeds the
+			// threshold, back to 16x4 only when it falls below a quarter of that (the measure itself
+			// depends on the shape: no flip-flopping)
 			const uint32_t old_shape = a.schedule[4 + 2 * a.blocks_y + i];
-			a.schedule[4 + 2 * a.blocks_y + i] = mine > (20000u >> 5) ? 1u : (mine < (5000u >> 5) ? 0u : old_shape);
+			a.schedule[4 + 2 * a.blocks_y + i] =
+			    a.row_shape_threshold == 0u ? 0u : (mine > a.row_shape_threshold ? 1u : (mine < a.row_shape_threshold / 4u ? 0u : old_shape));
 		}
 		__syncthreads();
 		if (threadIdx.x == 0)
@@ -1476,6 +1479,12 @@ extern "C" int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *g, const Gr
 		a.n_lights = params->num_lights;
 		a.rec_bytes = (unsigned)params->num_lights * 48u;
 		a.use_bulk_copy = (reinterpret_cast<uintptr_t>(buf->lights) % 16) == 0 ? 1 : 0;
+		{
+			// experiment, off by default: measured on the bench scene the one-row blocks execute 7 % MORE instructions (their
+			// lists are not shorter: depth varies along x as much as across 4 rows there) -- DESIGN.md section 4
+			static const char *e = getenv("GRB_LIGHTING_ROW_BLOCKS");
+			a.row_shape_threshold = e ? (unsigned)strtoul(e, nullptr, 10) : 0u;
+		}
 		a.queue = di.queue + (di.next_slot.fetch_add(1u, std::memory_order_relaxed) % 64u);
 		const size_t smem = (size_t)a.rec_bytes + 48u + 1024u + ((kPWarps * (kListCap + 2) * 2u + 15u) & ~15u) + 32u * kPWarps * 48u + 16u + kMaxOrderRows * 2u;
 		if (smem <= (size_t)di.smem_max)

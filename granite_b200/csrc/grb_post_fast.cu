@@ -283,8 +283,9 @@ bool launch_fxaa_fast(const GrbImage *in, const GrbImage *out, GrbRows rows, cud
 // plus a 1-pixel border is converted ONCE to float4(Y, Cg, Co, depth) in shared memory -- the 3x3
 // neighbourhood statistics and the nearest-depth search then cost nine 16-byte shared-memory reads
 // per pixel instead of nine HDR decodes + tonemaps + colour-space conversions and nine depth loads.
-// The Catmull-Rom history fetch is evaluated as the separable 4x4 filter it is (the shader's nine
-// bilinear taps are that filter, re-expressed for a texture unit): 16 texel loads, 8 weights.
+// The Catmull-Rom history fetch (nine bilinear taps in the shader) is evaluated as a separable
+// weighted sum over the texels those taps touch, with the taps' positions formed by the shader's own
+// arithmetic (see the comment at the filter).
 // Per-texel colour-space conversions keep the shader's association (their chroma passes through zero);
 // the filters are fused multiply-adds.
 namespace grb
@@ -366,66 +367,84 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 		float old_u, old_v;
 		if (mvx == 0.0f && mvy == 0.0f)
 		{
-			const float cx = fmaf(2.0f, u, -1.0f), cy = fmaf(2.0f, v, -1.0f);
+			// The history position is formed with the shader's association and IEEE division: an ulp of u is
+			// 1e-4 texel at 4K, and the Catmull-Rom weights amplify it by the local contrast of the history.
+			const float cx = fsub(fmul(2.0f, u), 1.0f), cy = fsub(fmul(2.0f, v), 1.0f);
 			const float *m = a.m;
-			const float px = fmaf(m[8], d, fmaf(m[4], cy, m[0] * cx)) + m[12];
-			const float py = fmaf(m[9], d, fmaf(m[5], cy, m[1] * cx)) + m[13];
-			const float pw = fmaf(m[11], d, fmaf(m[7], cy, m[3] * cx)) + m[15];
-			const float rw = rcp_fast(pw);
-			old_u = px * rw;
-			old_v = py * rw;
-			mvx = u - old_u;
-			mvy = v - old_v;
+			const float px = fadd(fadd(fadd(fmul(m[0], cx), fmul(m[4], cy)), fmul(m[8], d)), m[12]);
+			const float py = fadd(fadd(fadd(fmul(m[1], cx), fmul(m[5], cy)), fmul(m[9], d)), m[13]);
+			const float pw = fadd(fadd(fadd(fmul(m[3], cx), fmul(m[7], cy)), fmul(m[11], d)), m[15]);
+			old_u = fdiv(px, pw);
+			old_v = fdiv(py, pw);
+			mvx = fsub(u, old_u);
+			mvy = fsub(v, old_v);
 		}
 		else
 		{
-			old_u = u - mvx;
-			old_v = v - mvy;
+			old_u = fsub(u, mvx);
+			old_v = fsub(v, mvy);
 		}
-		// Catmull-Rom, reprojection.h:286-334: weights of texels t1-1 .. t1+2 around the sample position
+		// Catmull-Rom, reprojection.h:286-334.  The shader takes 9 bilinear samples at (t0, t12, t3) x
+		// (t0, t12, t3): t0 and t3 aim at texel centres, t12 between two texels.  Those positions pass
+		// through normalised coordinates, so what the sampler sees is off by an ulp of u -- 1e-4 texel at
+		// 4K -- and its bilinear weights leak that much of a neighbouring texel (in or out of the 4x4
+		// footprint).  To stay within fp32 rounding of that arithmetic the three positions per axis are
+		// formed with the shader's own operations; each yields (texel, weight) for two texels, six "slots"
+		// per axis, and the 9 samples x 4 texels collapse to a 6 x 6 weighted sum over slot pairs (slots
+		// that name the same texel simply load it twice from L1).
 		float3 hist;
 		{
-			const float spx = old_u * a.w, spy = old_v * a.h;
-			const float t1x = floorf(spx - 0.5f) + 0.5f, t1y = floorf(spy - 0.5f) + 0.5f;
-			const float fx = spx - t1x, fy = spy - t1y;
-			const int ix = (int)(t1x - 0.5f), iy = (int)(t1y - 0.5f); // texel index of t1
-#define GRB_W0(f) ((f) * (-0.5f + (f) * (1.0f - 0.5f * (f))))
-#define GRB_W1(f) (1.0f + (f) * (f) * (-2.5f + 1.5f * (f)))
-#define GRB_W2(f) ((f) * (0.5f + (f) * (2.0f - 1.5f * (f))))
-#define GRB_W3(f) ((f) * (f) * (-0.5f + 0.5f * (f)))
-			const float wx[4] = { GRB_W0(fx), GRB_W1(fx), GRB_W2(fx), GRB_W3(fx) };
-			const float wy[4] = { GRB_W0(fy), GRB_W1(fy), GRB_W2(fy), GRB_W3(fy) };
-#undef GRB_W0
-#undef GRB_W1
-#undef GRB_W2
-#undef GRB_W3
+			const float spx = fmul(old_u, a.w), spy = fmul(old_v, a.h);
+			const float t1x = fadd(floorf(fsub(spx, 0.5f)), 0.5f), t1y = fadd(floorf(fsub(spy, 0.5f)), 0.5f);
+			const float fx = fsub(spx, t1x), fy = fsub(spy, t1y);
+			int sx[6], sy[6];
+			float wxs[6], wys[6];
+			auto axis_slots = [](float t1, float f, float inv_n, float n_f, int n, int *slot, float *wgt) {
+				// weights of the four Catmull-Rom taps (shader expressions, left to right, no contraction)
+				const float w0 = fmul(f, fadd(-0.5f, fmul(f, fsub(1.0f, fmul(0.5f, f)))));
+				const float w1 = fadd(1.0f, fmul(fmul(f, f), fadd(-2.5f, fmul(1.5f, f))));
+				const float w2 = fmul(f, fadd(0.5f, fmul(f, fsub(2.0f, fmul(1.5f, f)))));
+				const float w3 = fmul(fmul(f, f), fadd(-0.5f, fmul(0.5f, f)));
+				const float w12 = fadd(w1, w2);
+				const float o12 = fdiv(w2, fadd(w1, w2));
+				const float pos[3] = { fmul(fsub(t1, 1.0f), inv_n), fmul(fadd(t1, o12), inv_n), fmul(fadd(t1, 2.0f), inv_n) };
+				const float wt[3] = { w0, w12, w3 };
+#pragma unroll
+				for (int k = 0; k < 3; k++)
+				{
+					// LinearClamp along this axis (grb_common.cuh bilin_setup)
+					const float g = fsub(fmul(pos[k], n_f), 0.5f);
+					float fl = floorf(g);
+					const float frac = fsub(g, fl);
+					fl = fclamp(fl, -2.0f, n_f + 1.0f);
+					const int i = (int)fl;
+					slot[2 * k] = iclamp(i, 0, n - 1);
+					slot[2 * k + 1] = iclamp(i + 1, 0, n - 1);
+					wgt[2 * k] = wt[k] * (1.0f - frac);
+					wgt[2 * k + 1] = wt[k] * frac;
+				}
+			};
+			axis_slots(t1x, fx, a.inv_w, a.w, a.history.w, sx, wxs);
+			axis_slots(t1y, fy, a.inv_h, a.h, a.history.h, sy, wys);
 			f2 acc_yg = mk2(0.0f);
 			float acc_o = 0.0f;
-			// clamp-to-edge per column / row of the 4x4 footprint (8 clamps instead of 32)
-			int cx[4];
-			const uint2 *rowp[4];
 #pragma unroll
-			for (int i = 0; i < 4; i++)
+			for (int j = 0; j < 6; j++)
 			{
-				cx[i] = iclamp(ix - 1 + i, 0, a.history.w - 1);
-				rowp[i] = a.history.p + (size_t)iclamp(iy - 1 + i, 0, a.history.h - 1) * a.history.pitch;
-			}
-#pragma unroll
-			for (int j = 0; j < 4; j++)
-			{
+				const uint2 *rowp = a.history.p + (size_t)sy[j] * a.history.pitch;
 				f2 row_yg = mk2(0.0f);
 				float row_o = 0.0f;
 #pragma unroll
-				for (int i = 0; i < 4; i++)
+				for (int i = 0; i < 6; i++)
 				{
-					const uint2 raw = __ldg(rowp[j] + cx[i]);
+					const uint2 raw = __ldg(rowp + sx[i]);
 					const f2 rg = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
 					const float o = __half2float(__ushort_as_half((unsigned short)(raw.y & 0xffffu)));
-					row_yg = fma2(mk2(wx[i]), rg, row_yg);
-					row_o = fmaf(wx[i], o, row_o);
+					row_yg = fma2(mk2(wxs[i]), rg, row_yg);
+					row_o = fmaf(wxs[i], o, row_o);
 				}
-				acc_yg = fma2(mk2(wy[j]), row_yg, acc_yg);
-				acc_o = fmaf(wy[j], row_o, acc_o);
+				acc_yg = fma2(mk2(wys[j]), row_yg, acc_yg);
+				acc_o = fmaf(wys[j], row_o, acc_o);
 			}
 			hist = make_float3(acc_yg.x, acc_yg.y, acc_o);
 		}

@@ -4,7 +4,7 @@
  * Public entry points of the CPU oracle (liboracle.so, plain C ABI so the
  * Python tests can call it through ctypes on numpy buffers).  Every function
  * cites the reference file:line it restates (paths relative to the Granite
- * tree, commit 7c59ad8089).  "parity unpinned": see oracle_math.h.
+ * tree, commit 7c59ad8089).  Parity status (pinned to the reference's own shaders run on the CPU): see oracle_math.h.
  */
 #ifndef ORACLE_H_
 #define ORACLE_H_

@@ -7,12 +7,21 @@
  * cpu_baseline / --impl reference legs may build, load or call it.  The
  * product (granite_b200/) never includes or links anything from here.
  *
- * PARITY STATUS: "parity unpinned" for the per-pixel kernels -- the reference
- * holds no golden vectors or numeric asserts for K1..K13
- * and its Vulkan path cannot run in the build container.  What IS pinned:
- * the host-math helpers (perspective / inverse / look_at / floatToHalf) are
- * checked bit-for-bit against the reference's own math/muglm compiled into
- * oracle/_ref (see oracle/Makefile, tests/test_oracle_refmath.py).
+ * PARITY STATUS: pinned to the reference itself.  The reference holds no golden
+ * vectors or numeric asserts for K1..K13 and its
+ * Vulkan path cannot run in the build container, but its own shaders can be
+ * executed on the CPU: GLSL (untouched, under /root/reference) -> SPIR-V with
+ * the reference's vendored glslang -> C++ with its vendored spirv-cross
+ * (`make -C oracle ref-shaders`, ref_{shader,post,light}_shim.cpp).  Every
+ * kernel of this oracle is compared with those executables (K1-K4, K7-K13 bit
+ * for bit on stored values; K5+K6 <= 1 B10G11R11 code, > 99.9 % identical) in
+ * tests/test_oracle_ref_*shaders.py, and against fixtures they wrote
+ * (tests/golden/ref*.npz) where /root/reference does not exist.  The host-math
+ * helpers (perspective / inverse / look_at / floatToHalf / frustum) are checked
+ * bit for bit against the reference's own math/ compiled into oracle/_ref
+ * (`make ref`, tests/test_oracle_cpu.py).  DESIGN.md section 2 lists what the
+ * shims supply (sampler filtering, storage formats: the things the reference
+ * leaves to the Vulkan implementation).
  *
  * Arithmetic contract (SURVEY.md §8c "Oracle definition we adopt"):
  *   - fp32 everywhere ("mediump" is a no-op on desktop GPUs), evaluated
