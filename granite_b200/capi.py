@@ -79,7 +79,7 @@ ENTRY_POINTS = [
     "grb_cluster_spot_transform", "grb_cluster_cull_setup", "grb_cluster_binning", "grb_cluster_z_range",
     "grb_cluster_build", "grb_deferred_lighting", "grb_deferred_lighting_scheduled", "grb_lighting_schedule_bytes", "grb_debug_cluster_indices", "grb_lighting_row_cost",
     "grb_bloom_threshold", "grb_bloom_threshold_downsample", "grb_bloom_threshold_downsample_to_peers", "grb_bloom_downsample", "grb_bloom_downsample_to_peers", "grb_peer_wait", "grb_bloom_upsample",
-    "grb_luminance", "grb_luminance_grid", "grb_luminance_finalize", "grb_tonemap",
+    "grb_luminance", "grb_luminance_grid", "grb_luminance_finalize", "grb_bloom_tail", "grb_tonemap",
     "grb_fxaa", "grb_taa_resolve",
 ]
 
@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
             "grb_luminance": [IMG, P, F, F, F, P],
             "grb_luminance_grid": [IMG, P, GrbRows, P],
             "grb_luminance_finalize": [P, I, I, P, F, F, F, P],
+            "grb_bloom_tail": [IMG, IMG, IMG, IMG, IMG, F, P, F, F, F, IMG, IMG, P],
             "grb_tonemap": [IMG, IMG, P, F, IMG, GrbRows, P],
             "grb_fxaa": [IMG, IMG, GrbRows, P],
             "grb_taa_resolve": [IMG, IMG, IMG, IMG, P, I, IMG, IMG, GrbRows, P],

@@ -394,30 +394,52 @@ __global__ void __launch_bounds__(32 * kBinWarps) binning_kernel(BinParams p, co
 // instead of one (round 1's single-CTA scatter sat at 0.02 IPC for 25 us).
 constexpr int kZSegWarps = 32;
 
+constexpr int kZSegStage = 2048; // light ranges staged per round (16 KiB)
+
 __global__ void __launch_bounds__(32 * kZSegWarps) z_range_segment_kernel(const uint2 *__restrict__ z_ranges, int num_ranges, int res_z,
                                                                          uint2 *__restrict__ cluster_range)
 {
 	__shared__ uint32_t s_lo[32], s_hi[32];
+	__shared__ uint2 s_ranges[kZSegStage];
+	__shared__ int s_any;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	if (warp == 0)
 	{
 		s_lo[lane] = 0xffffffffu;
 		s_hi[lane] = 0u;
 	}
-	__syncthreads();
 	const uint32_t seg_lo = blockIdx.x * 32u, seg_hi = seg_lo + 31u;
 	const uint32_t z = seg_lo + (uint32_t)lane;
 	uint32_t lo = 0xffffffffu, hi = 0u;
-	for (int i = warp; i < num_ranges; i += kZSegWarps)
+	for (int base = 0; base < num_ranges; base += kZSegStage)
 	{
-		const uint2 r = __ldg(&z_ranges[i]);
-		if (r.x > seg_hi || r.y < seg_lo || r.x > r.y)
-			continue;
-		if (z >= r.x && z <= r.y)
+		// stage a round of ranges with coalesced loads (a uniform global load per light made the loop a
+		// chain of L2 round trips); note whether any of them touches this segment at all
+		const int count = min(kZSegStage, num_ranges - base);
+		if (threadIdx.x == 0)
+			s_any = 0;
+		__syncthreads();
+		bool touches = false;
+		for (int i = threadIdx.x; i < count; i += 32 * kZSegWarps)
 		{
-			lo = min(lo, (uint32_t)i);
-			hi = max(hi, (uint32_t)i);
+			const uint2 r = __ldg(&z_ranges[base + i]);
+			s_ranges[i] = r;
+			touches |= r.x <= seg_hi && r.y >= seg_lo && r.x <= r.y;
 		}
+		if (__any_sync(0xffffffffu, touches) && lane == 0)
+			s_any = 1;
+		__syncthreads();
+		if (s_any)
+			for (int i = warp; i < count; i += kZSegWarps)
+			{
+				const uint2 r = s_ranges[i]; // broadcast
+				if (z >= r.x && z <= r.y)
+				{
+					lo = min(lo, (uint32_t)(base + i));
+					hi = max(hi, (uint32_t)(base + i));
+				}
+			}
+		__syncthreads();
 	}
 	if (lo != 0xffffffffu)
 	{

@@ -255,6 +255,22 @@ GRB_DEV float4 sample_rgba16f(const View<const uint2> &im, float u, float v)
 	return bilin_mix4(t00, t10, t01, t11, s.a, s.b);
 }
 
+// Bilinear weight within 2^-9 of 0 or 1 -> exactly 0 or 1: the TAA history taps only (oracle_math.h
+// snap_weight; a sampler's fixed-point position has 8 fractional bits).
+GRB_DEV float snap_weight(float f) { return f <= 0.001953125f ? 0.0f : (f >= 1.0f - 0.001953125f ? 1.0f : f); }
+
+GRB_DEV float4 sample_rgba16f_snap(const View<const uint2> &im, float u, float v)
+{
+	Bilin s = bilin_setup(u, v, im.w, im.h);
+	s.a = snap_weight(s.a);
+	s.b = snap_weight(s.b);
+	float4 t00 = unpack_rgba16f(__ldg(&im.at(s.x0, s.y0)));
+	float4 t10 = unpack_rgba16f(__ldg(&im.at(s.x1, s.y0)));
+	float4 t01 = unpack_rgba16f(__ldg(&im.at(s.x0, s.y1)));
+	float4 t11 = unpack_rgba16f(__ldg(&im.at(s.x1, s.y1)));
+	return bilin_mix4(t00, t10, t01, t11, s.a, s.b);
+}
+
 GRB_DEV float3 fetch_hdr_clamped(const View<const uint32_t> &im, int x, int y)
 {
 	return unpack_r11g11b10(__ldg(&im.at(iclamp(x, 0, im.w - 1), iclamp(y, 0, im.h - 1))));

@@ -9,6 +9,9 @@
 // coalesced accesses; the small pyramid levels live entirely in the 126 MB L2.
 #include "grb_common.cuh"
 
+#include <cooperative_groups.h>
+
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -588,7 +591,7 @@ __device__ __forceinline__ float3 sample_catmull_rom(const View<const uint2> &te
 	float3 result = make_float3(0.0f, 0.0f, 0.0f);
 #define GRB_ACC(UU, VV, WA, WB)                      \
 	{                                                \
-		float3 s = sample_rgb16f(tex, (UU), (VV));   \
+		float4 s4 = sample_rgba16f_snap(tex, (UU), (VV)); float3 s = make_float3(s4.x, s4.y, s4.z); \
 		result.x += s.x * (WA) * (WB);               \
 		result.y += s.y * (WA) * (WB);               \
 		result.z += s.z * (WA) * (WB);               \
@@ -724,6 +727,128 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) taa_kernel(TaaInputs in, Mat
 	float3 color = taa_to_hdr(out_c);
 	out_color.at(x, y) = pack_r11g11b10(color.x, color.y, color.z);
 	out_history.at(x, y) = pack_rgba16f(make_float4(out_c.x, out_c.y, out_c.z, 1.0f));
+}
+
+// ------------------------------------------------------------------------------- pyramid tail
+// d1, d2, d3 (+FEEDBACK), luminance, u2, u1 -- everything of "bloom-compute" below 1/4 resolution
+// (hdr.cpp:357-376) -- as ONE cooperative launch with a grid barrier between levels.  At 4K these six
+// dispatches touch 1.4 MB and 0.3 M texels altogether; as separate kernels each costs a launch and an
+// almost empty GPU (7 - 9 us apiece, 46 us in a row), which is what a frame's latency and a row-sharded
+// frame's replicated part consist of.  The arithmetic is the bit-exact form of this file (tent9 /
+// luminance_tail), so every level equals the oracle bit for bit; sources are read with ld.global.cg
+// (L2): they were written by other SMs earlier in the same launch.
+__device__ __forceinline__ float4 sample_rgba16f_cg(const View<const uint2> &im, float u, float v)
+{
+	Bilin s = bilin_setup(u, v, im.w, im.h);
+	float4 t00 = unpack_rgba16f(__ldcg(&im.at(s.x0, s.y0)));
+	float4 t10 = unpack_rgba16f(__ldcg(&im.at(s.x1, s.y0)));
+	float4 t01 = unpack_rgba16f(__ldcg(&im.at(s.x0, s.y1)));
+	float4 t11 = unpack_rgba16f(__ldcg(&im.at(s.x1, s.y1)));
+	return bilin_mix4(t00, t10, t01, t11, s.a, s.b);
+}
+
+__device__ __forceinline__ float4 tent9_cg(const View<const uint2> &src, float u, float v, float off, float inv_in_w, float inv_in_h)
+{
+	const float du = off * inv_in_w, dv = off * inv_in_h;
+	const float um = u + (-du), up = u + du;
+	const float vm = v + (-dv), vp = v + dv;
+	float4 s = sample_rgba16f_cg(src, u, v);
+	float4 acc = make_float4(0.25f * s.x, 0.25f * s.y, 0.25f * s.z, 0.25f * s.w);
+#define GRB_TAP(W, U, V)                     \
+	s = sample_rgba16f_cg(src, (U), (V));    \
+	acc.x += (W)*s.x;                        \
+	acc.y += (W)*s.y;                        \
+	acc.z += (W)*s.z;                        \
+	acc.w += (W)*s.w;
+	GRB_TAP(0.0625f, um, vp)
+	GRB_TAP(0.125f, u, vp)
+	GRB_TAP(0.0625f, up, vp)
+	GRB_TAP(0.125f, um, v)
+	GRB_TAP(0.125f, up, v)
+	GRB_TAP(0.0625f, um, vm)
+	GRB_TAP(0.125f, u, vm)
+	GRB_TAP(0.0625f, up, vm)
+#undef GRB_TAP
+	return acc;
+}
+
+struct TailArgs
+{
+	View<const uint2> d0;
+	View<uint2> d1, d2, d3, u2, u1;
+	View<const uint2> history; // p == nullptr: FEEDBACK = 0
+	float lerp_d3;
+	float *lum; // nullptr: no dynamic exposure
+	float lerp_lum, lo, hi;
+};
+
+constexpr int kTailThreads = 256;
+
+__device__ __forceinline__ void tail_level(const View<const uint2> &src, const View<uint2> &dst, float off, const View<const uint2> *history, float lerp,
+                                          unsigned first_cta, unsigned num_ctas)
+{
+	const float inv_w = 1.0f / (float)dst.w, inv_h = 1.0f / (float)dst.h, inv_in_w = 1.0f / (float)src.w, inv_in_h = 1.0f / (float)src.h;
+	const int total = dst.w * dst.h;
+	for (int i = (int)((blockIdx.x - first_cta) * kTailThreads + threadIdx.x); i < total; i += (int)(num_ctas * kTailThreads))
+	{
+		const int y = i / dst.w, x = i - y * dst.w;
+		const float u = ((float)x + 0.5f) * inv_w, v = ((float)y + 0.5f) * inv_h;
+		float4 value = tent9_cg(src, u, v, off, inv_in_w, inv_in_h);
+		if (history)
+		{
+			const float4 hs = unpack_rgba16f(__ldg(&history->at(x, y))); // last frame's image: read-only here
+			value = make_float4(fmix(hs.x, value.x, lerp), fmix(hs.y, value.y, lerp), fmix(hs.z, value.z, lerp), fmix(hs.w, value.w, 1.0f));
+		}
+		dst.at(x, y) = pack_rgba16f(value);
+	}
+}
+
+__global__ void __launch_bounds__(kTailThreads) bloom_tail_kernel(const TailArgs a)
+{
+	namespace cg = cooperative_groups;
+	cg::grid_group grid = cg::this_grid();
+	__shared__ float s_grid[kLumFastMaxSamples];
+	__shared__ float s_part[64];
+	auto as_src = [](const View<uint2> &v) { return View<const uint2>{ v.p, v.w, v.h, v.pitch }; };
+	tail_level(a.d0, a.d1, 1.75f, nullptr, 0.0f, 0u, gridDim.x);
+	grid.sync();
+	tail_level(as_src(a.d1), a.d2, 1.75f, nullptr, 0.0f, 0u, gridDim.x);
+	grid.sync();
+	tail_level(as_src(a.d2), a.d3, 1.75f, a.history.p ? &a.history : nullptr, a.lerp_d3, 0u, gridDim.x);
+	grid.sync();
+	// the luminance reduction (one CTA, luminance.comp's association order) runs beside the first upsample
+	const bool lum_cta = a.lum != nullptr && blockIdx.x == 0 && gridDim.x > 1;
+	if (a.lum != nullptr && (lum_cta || gridDim.x == 1))
+	{
+		const View<const uint2> d3 = as_src(a.d3);
+		const int size_x = d3.w / 2, size_y = d3.h / 2;
+		const float inv_sx = 1.0f / (float)size_x, inv_sy = 1.0f / (float)size_y;
+		for (int i = threadIdx.x; i < size_x * size_y; i += kTailThreads)
+		{
+			const int sy = i / size_x, sx = i - sy * size_x;
+			s_grid[i] = sample_rgba16f_cg(d3, ((float)sx + 0.5f) * inv_sx, ((float)sy + 0.5f) * inv_sy).w;
+		}
+		__syncthreads();
+		if (threadIdx.x < 64)
+		{
+			const int iter_y = (size_y + 7) >> 3, iter_x = (size_x + 7) >> 3;
+			const int lx = threadIdx.x & 7, ly = threadIdx.x >> 3;
+			float total = 0.0f;
+			for (int y = 0; y < iter_y; y++)
+				for (int x = 0; x < iter_x; x++)
+				{
+					const int sx = x * 8 + lx, sy = y * 8 + ly;
+					if (sx < size_x && sy < size_y)
+						total += s_grid[sy * size_x + sx];
+				}
+			s_part[threadIdx.x] = total;
+		}
+		luminance_tail(s_part, threadIdx.x, size_x, size_y, inv_sx, inv_sy, a.lum, a.lerp_lum, a.lo, a.hi);
+	}
+	if (!lum_cta)
+		tail_level(as_src(a.d3), a.u2, 0.875f, nullptr, 0.0f, a.lum != nullptr && gridDim.x > 1 ? 1u : 0u, a.lum != nullptr && gridDim.x > 1 ? gridDim.x - 1u : gridDim.x);
+	grid.sync();
+	tail_level(as_src(a.u2), a.u1, 0.875f, nullptr, 0.0f, 0u, gridDim.x);
 }
 } // namespace
 } // namespace grb
@@ -1044,4 +1169,65 @@ extern "C" int32_t grb_taa_resolve(const GrbImage *hdr, const GrbImage *depth, c
 		GRB_LAUNCH(2, true);
 #undef GRB_LAUNCH
 	return check_launch("grb_taa_resolve");
+}
+
+// d1 .. d3 (+ temporal feedback), the average-luminance update, u2 and u1 in one cooperative launch
+// (hdr.cpp:357-376: three bloom_downsample dispatches, luminance, two bloom_upsample dispatches).
+// `history` (last frame's d3) and `luminance` may be NULL.  Returns GRB_ERR_UNSUPPORTED_FORMAT when the
+// device cannot launch cooperatively or the luminance grid exceeds the kernel's shared memory; the
+// caller then issues the six calls.
+extern "C" int32_t grb_bloom_tail(const GrbImage *d0, const GrbImage *d1, const GrbImage *d2, const GrbImage *d3, const GrbImage *history, float lerp_d3,
+                                  float *luminance, float lerp_luminance, float min_loglum, float max_loglum, const GrbImage *u2, const GrbImage *u1,
+                                  void *stream)
+{
+	const GrbImage *all[6] = { d0, d1, d2, d3, u2, u1 };
+	for (const GrbImage *im : all)
+		if (!image_ok(im, GRB_FORMAT_R16G16B16A16_SFLOAT, 8))
+		{
+			set_last_error("grb_bloom_tail: every level must be R16G16B16A16_SFLOAT");
+			return GRB_ERR_UNSUPPORTED_FORMAT;
+		}
+	if (history && (!image_ok(history, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || history->width != d3->width || history->height != d3->height || history->data == d3->data))
+	{
+		set_last_error("grb_bloom_tail: history must match d3 and not alias it");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	if (u2->width != d2->width || u2->height != d2->height || u1->width != d1->width || u1->height != d1->height)
+	{
+		set_last_error("grb_bloom_tail: u2 / u1 must have the sizes of d2 / d1");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	static const bool disabled = getenv("GRB_BLOOM_NO_FUSED_TAIL") != nullptr;
+	int device = 0, coop = 0, sms = 0;
+	if (disabled || cudaGetDevice(&device) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop ||
+	    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+	    (luminance && (d3->width < 2 || d3->height < 2 || (d3->width / 2) * (d3->height / 2) > kLumFastMaxSamples)))
+	{
+		set_last_error("grb_bloom_tail: cooperative launch unavailable (or luminance grid too large); issue the separate calls");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
+	TailArgs a;
+	a.d0 = view_of<const uint2>(d0);
+	a.d1 = view_of<uint2>(d1);
+	a.d2 = view_of<uint2>(d2);
+	a.d3 = view_of<uint2>(d3);
+	a.u2 = view_of<uint2>(u2);
+	a.u1 = view_of<uint2>(u1);
+	a.history = history ? view_of<const uint2>(history) : View<const uint2>{};
+	a.lerp_d3 = lerp_d3;
+	a.lum = luminance;
+	a.lerp_lum = lerp_luminance;
+	a.lo = min_loglum;
+	a.hi = max_loglum;
+	// one CTA per SM is co-resident by construction; the largest level (d1 / u1) decides how many are useful
+	const int texels = d1->width * d1->height;
+	int ctas = std::min(sms, std::max(1, (texels + kTailThreads - 1) / kTailThreads));
+	void *params[] = { &a };
+	cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(bloom_tail_kernel), dim3(ctas), dim3(kTailThreads), params, 0, as_stream(stream));
+	if (err != cudaSuccess)
+	{
+		set_last_error(cudaGetErrorString(err));
+		return GRB_ERR_CUDA;
+	}
+	return check_launch("grb_bloom_tail");
 }

@@ -385,20 +385,18 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 			old_v = fsub(v, mvy);
 		}
 		// Catmull-Rom, reprojection.h:286-334.  The shader takes 9 bilinear samples at (t0, t12, t3) x
-		// (t0, t12, t3): t0 and t3 aim at texel centres, t12 between two texels.  Those positions pass
-		// through normalised coordinates, so what the sampler sees is off by an ulp of u -- 1e-4 texel at
-		// 4K -- and its bilinear weights leak that much of a neighbouring texel (in or out of the 4x4
-		// footprint).  To stay within fp32 rounding of that arithmetic the three positions per axis are
-		// formed with the shader's own operations; each yields (texel, weight) for two texels, six "slots"
-		// per axis, and the 9 samples x 4 texels collapse to a 6 x 6 weighted sum over slot pairs (slots
-		// that name the same texel simply load it twice from L1).
+		// (t0, t12, t3): t0 and t3 aim at texel centres, t12 lies between two texels.  The positions are
+		// formed with the shader's own operations (they pass through normalised coordinates); a tap within
+		// 2^-9 texel of a centre IS that texel (snap_weight, grb_common.cuh -- a sampler's fixed-point position
+		// has 8 fractional bits), so per axis the taps name four texels: one for t0, two for t12, one for
+		// t3, and the 9 samples collapse to a separable 4 x 4 weighted sum.
 		float3 hist;
 		{
 			const float spx = fmul(old_u, a.w), spy = fmul(old_v, a.h);
 			const float t1x = fadd(floorf(fsub(spx, 0.5f)), 0.5f), t1y = fadd(floorf(fsub(spy, 0.5f)), 0.5f);
 			const float fx = fsub(spx, t1x), fy = fsub(spy, t1y);
-			int sx[6], sy[6];
-			float wxs[6], wys[6];
+			int sx[4], sy[4];
+			float wxs[4], wys[4];
 			auto axis_slots = [](float t1, float f, float inv_n, float n_f, int n, int *slot, float *wgt) {
 				// weights of the four Catmull-Rom taps (shader expressions, left to right, no contraction)
 				const float w0 = fmul(f, fadd(-0.5f, fmul(f, fsub(1.0f, fmul(0.5f, f)))));
@@ -406,36 +404,43 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 				const float w2 = fmul(f, fadd(0.5f, fmul(f, fsub(2.0f, fmul(1.5f, f)))));
 				const float w3 = fmul(fmul(f, f), fadd(-0.5f, fmul(0.5f, f)));
 				const float w12 = fadd(w1, w2);
-				const float o12 = fdiv(w2, fadd(w1, w2));
-				const float pos[3] = { fmul(fsub(t1, 1.0f), inv_n), fmul(fadd(t1, o12), inv_n), fmul(fadd(t1, 2.0f), inv_n) };
-				const float wt[3] = { w0, w12, w3 };
-#pragma unroll
-				for (int k = 0; k < 3; k++)
-				{
-					// LinearClamp along this axis (grb_common.cuh bilin_setup)
-					const float g = fsub(fmul(pos[k], n_f), 0.5f);
+				const float o12 = fdiv(w2, w12);
+				// LinearClamp along this axis (grb_common.cuh bilin_setup) for the three positions
+				auto locate = [&](float pos, int &i, float &frac) {
+					const float g = fsub(fmul(pos, n_f), 0.5f);
 					float fl = floorf(g);
-					const float frac = fsub(g, fl);
+					frac = snap_weight(fsub(g, fl));
 					fl = fclamp(fl, -2.0f, n_f + 1.0f);
-					const int i = (int)fl;
-					slot[2 * k] = iclamp(i, 0, n - 1);
-					slot[2 * k + 1] = iclamp(i + 1, 0, n - 1);
-					wgt[2 * k] = wt[k] * (1.0f - frac);
-					wgt[2 * k + 1] = wt[k] * frac;
-				}
+					i = (int)fl;
+				};
+				int i0, i12, i3;
+				float f0, f12, f3;
+				locate(fmul(fsub(t1, 1.0f), inv_n), i0, f0);
+				locate(fmul(fadd(t1, o12), inv_n), i12, f12);
+				locate(fmul(fadd(t1, 2.0f), inv_n), i3, f3);
+				// t0 / t3: snapped to one texel (for any image up to 8192 texels wide the position is within
+				// 2^-10 of a centre; a weight that did not snap keeps its larger share -- never taken there)
+				slot[0] = iclamp(f0 >= 0.5f ? i0 + 1 : i0, 0, n - 1);
+				wgt[0] = w0;
+				slot[1] = iclamp(i12, 0, n - 1);
+				wgt[1] = w12 * (1.0f - f12);
+				slot[2] = iclamp(i12 + 1, 0, n - 1);
+				wgt[2] = w12 * f12;
+				slot[3] = iclamp(f3 >= 0.5f ? i3 + 1 : i3, 0, n - 1);
+				wgt[3] = w3;
 			};
 			axis_slots(t1x, fx, a.inv_w, a.w, a.history.w, sx, wxs);
 			axis_slots(t1y, fy, a.inv_h, a.h, a.history.h, sy, wys);
 			f2 acc_yg = mk2(0.0f);
 			float acc_o = 0.0f;
 #pragma unroll
-			for (int j = 0; j < 6; j++)
+			for (int j = 0; j < 4; j++)
 			{
 				const uint2 *rowp = a.history.p + (size_t)sy[j] * a.history.pitch;
 				f2 row_yg = mk2(0.0f);
 				float row_o = 0.0f;
 #pragma unroll
-				for (int i = 0; i < 6; i++)
+				for (int i = 0; i < 4; i++)
 				{
 					const uint2 raw = __ldg(rowp + sx[i]);
 					const f2 rg = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 bool launch_taa_fast(const GrbImage *hdr, const GrbImage *depth, const GrbImage *mv, const GrbImage *history, const float *reproj16, const GrbImage *out_color,
                      const GrbImage *out_history, GrbRows rows, cudaStream_t stream, int32_t *rc)
 {
-	if (exact_requested())
+	if (exact_requested() || hdr->width > 8192 || hdr->height > 8192)
 		return false;
 	TaaFastArgs a;
 	a.hdr = view_of<const uint32_t>(hdr);

@@ -165,6 +165,15 @@ def bloom_upsample(in_t, out_t, rows=None):
     capi.check(capi.lib().grb_bloom_upsample(C.byref(ii), C.byref(oi), capi.rows(rows), capi.stream_ptr()), "grb_bloom_upsample")
 
 
+def bloom_tail(d0_t, d1_t, d2_t, d3_t, history_t, lerp_d3, lum_t, lerp_lum, u2_t, u1_t, lo=-3.0, hi=2.0):
+    """d1, d2, d3 (+feedback), luminance, u2, u1 in one cooperative launch."""
+    im = [_img16(t) for t in (d0_t, d1_t, d2_t, d3_t, u2_t, u1_t)]
+    hi_ = C.byref(_img16(history_t)) if history_t is not None else None
+    capi.check(capi.lib().grb_bloom_tail(C.byref(im[0]), C.byref(im[1]), C.byref(im[2]), C.byref(im[3]), hi_, C.c_float(lerp_d3), _ptr(lum_t),
+                                         C.c_float(lerp_lum), C.c_float(lo), C.c_float(hi), C.byref(im[4]), C.byref(im[5]), capi.stream_ptr()),
+               "grb_bloom_tail")
+
+
 def luminance(d3_t, lum_t, lerp, lo=-3.0, hi=2.0):
     di = _img16(d3_t)
     capi.check(capi.lib().grb_luminance(C.byref(di), _ptr(lum_t), C.c_float(lerp), C.c_float(lo), C.c_float(hi), capi.stream_ptr()), "grb_luminance")

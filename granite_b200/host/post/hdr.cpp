@@ -85,24 +85,29 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 		graph.get_collectives()->all_gather_rows(cmd, graph.get_physical_texture_resource(*r.d0), bands);
 	}
 
-	cmd.check(grb_bloom_downsample(&d0, nullptr, 0.0f, &d1, all_rows(), stream), "grb_bloom_downsample(d1)");
-	cmd.check(grb_bloom_downsample(&d1, nullptr, 0.0f, &d2, all_rows(), stream), "grb_bloom_downsample(d2)");
-
-	// d3 blends with its own previous frame (hdr.cpp:156-167, 182): lerp = 1 - 0.001^frame_time
+	// d3 blends with its own previous frame (hdr.cpp:156-167, 182): lerp = 1 - 0.001^frame_time;
+	// luminance_build_compute (hdr.cpp:68-98): size = d3 / 2, lerp = 1 - 0.5^frame_time, clamp [-3, 2]
 	auto *history = graph.get_physical_history_texture_resource(*r.d3);
 	GrbImage hist;
 	if (history)
 		hist = history->as_grb();
-	float lerp_d3 = float(1.0 - std::pow(0.001, frame.frame_time));
-	cmd.check(grb_bloom_downsample(&d2, history ? &hist : nullptr, lerp_d3, &d3, all_rows(), stream), "grb_bloom_downsample(d3)");
+	const float lerp_d3 = float(1.0 - std::pow(0.001, frame.frame_time));
+	const float lerp_lum = float(1.0 - std::pow(0.5, frame.frame_time));
+	// with the exchanged d0 every rank holds the whole d3 and reduces it locally; the NCCL path keeps
+	// the reference split (band partial sums + all-reduce) and the separate calls
+	const bool nccl_luminance = lum && sharded && r.lum_grid && !peer_stores;
 
-	if (lum)
+	// Everything below 1/4 resolution -- d1, d2, d3, luminance, u2, u1 -- is one cooperative launch
+	// (grid barriers between the levels); six separate dispatches when that is not available.
+	bool tail_fused = false;
+	if (!nccl_luminance)
+		tail_fused = grb_bloom_tail(&d0, &d1, &d2, &d3, history ? &hist : nullptr, lerp_d3, lum, lerp_lum, -3.0f, 2.0f, &u2, &u1, stream) == GRB_OK;
+	if (!tail_fused)
 	{
-		// luminance_build_compute (hdr.cpp:68-98): size = d3 / 2, lerp = 1 - 0.5^frame_time, clamp [-3, 2]
-		float lerp_lum = float(1.0 - std::pow(0.5, frame.frame_time));
-		// with the exchanged d0 every rank holds the whole d3 and reduces it locally; the NCCL path
-		// keeps the reference split (band partial sums + all-reduce)
-		if (sharded && r.lum_grid && !peer_stores)
+		cmd.check(grb_bloom_downsample(&d0, nullptr, 0.0f, &d1, all_rows(), stream), "grb_bloom_downsample(d1)");
+		cmd.check(grb_bloom_downsample(&d1, nullptr, 0.0f, &d2, all_rows(), stream), "grb_bloom_downsample(d2)");
+		cmd.check(grb_bloom_downsample(&d2, history ? &hist : nullptr, lerp_d3, &d3, all_rows(), stream), "grb_bloom_downsample(d3)");
+		if (nccl_luminance)
 		{
 			// each rank samples the grid rows of its own band; the sum over ranks of (value or 0)
 			// reassembles the grid exactly, then every rank reduces it in the shader's order
@@ -116,12 +121,11 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 			graph.get_collectives()->all_reduce_sum(cmd, grid, (size_t)size_x * size_y);
 			cmd.check(grb_luminance_finalize(grid, size_x, size_y, lum, lerp_lum, -3.0f, 2.0f, stream), "grb_luminance_finalize");
 		}
-		else
+		else if (lum)
 			cmd.check(grb_luminance(&d3, lum, lerp_lum, -3.0f, 2.0f, stream), "grb_luminance");
+		cmd.check(grb_bloom_upsample(&d3, &u2, all_rows(), stream), "grb_bloom_upsample(u2)");
+		cmd.check(grb_bloom_upsample(&u2, &u1, all_rows(), stream), "grb_bloom_upsample(u1)");
 	}
-
-	cmd.check(grb_bloom_upsample(&d3, &u2, all_rows(), stream), "grb_bloom_upsample(u2)");
-	cmd.check(grb_bloom_upsample(&u2, &u1, all_rows(), stream), "grb_bloom_upsample(u1)");
 	// u0 feeds the tonemap's bilinear bloom tap: own band (+ the tonemap halo FXAA needs) at 1/4 res
 	GrbRows u0_rows = sharded ? plan.upsample0 : all_rows();
 	cmd.check(grb_bloom_upsample(&u1, &u0, u0_rows, stream), "grb_bloom_upsample(u0)");

@@ -250,6 +250,13 @@ int32_t grb_luminance(const GrbImage *d3, float *luminance, float lerp, float mi
 int32_t grb_luminance_grid(const GrbImage *d3, float *grid, GrbRows rows, void *stream);
 int32_t grb_luminance_finalize(const float *grid, int32_t size_x, int32_t size_y, float *luminance,
                                float lerp, float min_loglum, float max_loglum, void *stream);
+/* Everything of "bloom-compute" below 1/4 resolution in ONE cooperative launch with grid barriers between
+ * the levels: d1, d2, d3 (history / lerp_d3 as in grb_bloom_downsample), the luminance update (luminance may
+ * be NULL), u2, u1 (hdr.cpp:357-376).  Bit-identical to the six separate calls on their generic kernels.
+ * GRB_ERR_UNSUPPORTED_FORMAT when the device cannot launch cooperatively: issue the six calls instead. */
+int32_t grb_bloom_tail(const GrbImage *d0, const GrbImage *d1, const GrbImage *d2, const GrbImage *d3,
+                       const GrbImage *history, float lerp_d3, float *luminance, float lerp_luminance,
+                       float min_loglum, float max_loglum, const GrbImage *u2, const GrbImage *u1, void *stream);
 /* K11 tonemap.frag; hdr.cpp:283-306. out: R8G8B8A8_SRGB (or _UNORM: stores linear). */
 int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const float *luminance,
                     float dynamic_exposure, const GrbImage *out, GrbRows rows, void *stream);

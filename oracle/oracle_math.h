@@ -272,6 +272,26 @@ static inline float bilin_mix(float t00, float t10, float t01, float t11, float 
 	return top * (1.0f - b) + bot * b;
 }
 
+/* A bilinear weight within 2^-9 of 0 or 1 becomes exactly 0 or 1.  Used ONLY by the history taps of
+ * sample_catmull_rom (reprojection.h:286-334): the shader aims taps t0 and t3 at texel centres through
+ * normalised coordinates, whose fp32 rounding is ~1e-4 texel at 4K; a GPU's sampler converts the
+ * position to fixed point with 8 fractional bits and therefore fetches the texel, whereas an exact-weight
+ * evaluation would blend in 1e-4 of a neighbour (decision table). */
+static inline float snap_weight(float f) { return f <= 0.001953125f ? 0.0f : (f >= 1.0f - 0.001953125f ? 1.0f : f); }
+
+static inline vec4 sample16f_linear_snap(img16f im, float u, float v)
+{
+	bilin_t s = bilin_setup(u, v, im.w, im.h);
+	s.a = snap_weight(s.a);
+	s.b = snap_weight(s.b);
+	vec4 t00 = fetch16f(im, s.x0, s.y0), t10 = fetch16f(im, s.x1, s.y0);
+	vec4 t01 = fetch16f(im, s.x0, s.y1), t11 = fetch16f(im, s.x1, s.y1);
+	return v4(bilin_mix(t00.x, t10.x, t01.x, t11.x, s.a, s.b),
+	          bilin_mix(t00.y, t10.y, t01.y, t11.y, s.a, s.b),
+	          bilin_mix(t00.z, t10.z, t01.z, t11.z, s.a, s.b),
+	          bilin_mix(t00.w, t10.w, t01.w, t11.w, s.a, s.b));
+}
+
 static inline vec4 sample16f_linear(img16f im, float u, float v)
 {
 	bilin_t s = bilin_setup(u, v, im.w, im.h);

@@ -412,7 +412,7 @@ static vec3 sample_catmull_rom(img16f tex, float u, float v, const float *rt)
 	float t3x = (t1x + 2.0f) * rt[0], t3y = (t1y + 2.0f) * rt[1];
 	float t12x = (t1x + o12x) * rt[0], t12y = (t1y + o12y) * rt[1];
 	vec3 result = v3(0, 0, 0);
-#define ACC(uu, vv, wa, wb) do { vec3 s = sample16f_rgb(tex, (uu), (vv)); \
+#define ACC(uu, vv, wa, wb) do { vec4 s4 = sample16f_linear_snap(tex, (uu), (vv)); vec3 s = v3(s4.x, s4.y, s4.z); \
 		result.x += s.x * (wa) * (wb); result.y += s.y * (wa) * (wb); result.z += s.z * (wa) * (wb); } while (0)
 	ACC(t0x, t0y, w0x, w0y);
 	ACC(t12x, t0y, w12x, w0y);

@@ -78,6 +78,9 @@ struct sampler2D
 	// sampling at a pixel centre = exact fetch".  Set by the rasteriser loop; null = never.
 	const glm::vec2 *frag_uv = nullptr;
 	const glm::ivec2 *frag_px = nullptr;
+	// The TAA history sampler only: a bilinear weight within 2^-9 of 0 or 1 is exactly 0 or 1 (oracle_math.h
+	// snap_weight: Catmull-Rom taps aimed at texel centres through normalised coordinates).
+	bool snap_centres = false;
 
 	glm::vec4 texel(int x, int y) const
 	{
@@ -148,7 +151,12 @@ struct sampler2D
 		}
 		if (frag_uv && uv.x == frag_uv->x && uv.y == frag_uv->y)
 			return texel(frag_px->x + off.x, frag_px->y + off.y);
-		const Foot f = footprint(uv);
+		Foot f = footprint(uv);
+		if (snap_centres)
+		{
+			f.a = f.a <= 0.001953125f ? 0.0f : (f.a >= 1.0f - 0.001953125f ? 1.0f : f.a);
+			f.b = f.b <= 0.001953125f ? 0.0f : (f.b >= 1.0f - 0.001953125f ? 1.0f : f.b);
+		}
 		const glm::vec4 t00 = texel(f.x0 + off.x, f.y0 + off.y), t10 = texel(f.x0 + 1 + off.x, f.y0 + off.y);
 		const glm::vec4 t01 = texel(f.x0 + off.x, f.y0 + 1 + off.y), t11 = texel(f.x0 + 1 + off.x, f.y0 + 1 + off.y);
 		const float ia = 1.0f - f.a, ib = 1.0f - f.b;
@@ -451,6 +459,9 @@ refk13_taa_nohistory
 	sampler2D s_depth = make_sampler(depth, w, h, spirv_cross::FMT_D32F, false);
 	sampler2D s_mv = make_sampler(mv, w, h, spirv_cross::FMT_RG16F, false);
 	sampler2D s_hist = make_sampler(history, w, h, spirv_cross::FMT_RGBA16F, true);
+#if KERNEL == 13
+	s_hist.snap_centres = true; // quality 2 = sample_catmull_rom
+#endif
 	r.resource(0, 1, &s_depth);
 	r.resource(0, 2, &s_mv);
 	r.resource(0, 3, &s_hist);

@@ -106,3 +106,29 @@ def assert_f16_close(got, ref, what="", min_identical=0.999, abs_floor=0.0):
     ident = float((d == 0).mean())
     assert ident >= min_identical, f"{what}: only {ident:.6f} identical"
     return ident
+
+
+def unpack_r11g11b10_np(p: np.ndarray) -> np.ndarray:
+    """Decode packed B10G11R11_UFLOAT to float32 (..., 3): 5-bit exponent (bias 15), 6 / 6 / 5 mantissa bits."""
+    p = p.astype(np.uint32)
+
+    def dec(v, mbits):
+        e = (v >> mbits).astype(np.int32)
+        m = (v & ((1 << mbits) - 1)).astype(np.float64)
+        normal = np.ldexp(1.0 + m / (1 << mbits), e - 15)
+        denorm = np.ldexp(m / (1 << mbits), -14)
+        return np.where(e == 0, denorm, np.where(e == 31, np.inf, normal)).astype(np.float32)
+
+    return np.stack([dec(p & 0x7FF, 6), dec((p >> 11) & 0x7FF, 6), dec(p >> 22, 5)], -1)
+
+
+def assert_r11g11b10_close(got, ref, what="", abs_floor=2.0 ** -16, min_identical=0.99):
+    """Stored B10G11R11 values: at most 1 code apart per channel, or -- for values so close to zero that a
+    code is a few 1e-6 -- within `abs_floor` absolute."""
+    d = np.stack([np.abs(a - b) for a, b in zip(r11g11b10_codes(got), r11g11b10_codes(ref))], -1)
+    a = np.abs(unpack_r11g11b10_np(got) - unpack_r11g11b10_np(ref))
+    bad = (d > 1) & ~(a <= abs_floor)
+    assert not bad.any(), f"{what}: {int(bad.sum())} channels differ by more than one code (max {int(d.max())}, max abs {float(a[d > 1].max()) if (d > 1).any() else 0.0:.3e})"
+    ident = float((d == 0).mean())
+    assert ident >= min_identical, f"{what}: only {ident:.6f} identical"
+    return ident

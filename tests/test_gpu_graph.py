@@ -180,7 +180,8 @@ def test_taa_fxaa_chain(cuda, oracle, w, h, n):
         lum, d3_hist = f.lum, f.d3
         ldr = oracle.fxaa(f.ldr, True)
         got_res = v.download_image("HDR-resolved")
-        assert common.max_code_diff_r11g11b10(got_res, res_c) <= 1, f"frame {i}"
+        # TAA tile kernel: 1 code, or 2^-16 absolute for the nearly black pixels of a real frame (a code is 1e-6 there)
+        common.assert_r11g11b10_close(got_res, res_c, f"frame {i}: HDR-resolved", min_identical=0.97)
         d = common.rgba8_channel_diff(out, ldr)
         assert (d <= 1).mean() > 0.999, f"frame {i}"
     # the 16-phase jitter moves the projection every frame

@@ -284,6 +284,42 @@ def test_bloom_upsample_bit_exact(cuda, oracle, w_in, h_in, w, h):
         assert not got[:band[0]].any() and not got[band[1]:].any()
 
 
+@pytest.mark.parametrize("w0,h0", [(960, 540), (480, 270), (64, 36), (33, 17)])
+@pytest.mark.parametrize("feedback,dynamic", [(True, True), (False, False), (False, True)])
+def test_bloom_tail_fused_bit_exact(cuda, oracle, w0, h0, feedback, dynamic):
+    """d1, d2, d3 (+history), luminance, u2, u1 in one cooperative launch: every level bit for bit the
+    oracle's (the kernel uses the unfused arithmetic), the log-average exact, its exp2 within 4 ulps."""
+    import math
+
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w0 + 7 * h0 + feedback)
+    d0 = common.random_rgba16f(rng, w0, h0)
+    sz = [(w0, h0)]
+    for _ in range(3):
+        sz.append((int(math.ceil(sz[-1][0] * 0.5)), int(math.ceil(sz[-1][1] * 0.5))))
+    if sz[3][0] < 2 or sz[3][1] < 2:
+        pytest.skip("d3 too small for the luminance grid")
+    hist = common.random_rgba16f(rng, *sz[3]) if feedback else None
+    lerp_d3, lerp_lum = float(np.float32(1.0 - 0.001 ** (1 / 60))), float(np.float32(1.0 - 0.5 ** (1 / 60)))
+    lum0 = np.array([0.3, 2.0 ** 0.3, 2.0 ** -0.3], np.float32)
+    d1 = oracle.bloom_downsample(d0, sz[1])
+    d2 = oracle.bloom_downsample(d1, sz[2])
+    d3 = oracle.bloom_downsample(d2, sz[3], hist, lerp_d3)
+    lum_ref = oracle.luminance(d3, lum0, lerp_lum)
+    u2 = oracle.bloom_upsample(d3, sz[2])
+    u1 = oracle.bloom_upsample(u2, sz[1])
+    t = {k: harness.new_rgba16f(*s_) for k, s_ in (("d1", sz[1]), ("d2", sz[2]), ("d3", sz[3]), ("u2", sz[2]), ("u1", sz[1]))}
+    lum_t = harness.to_dev(lum0.copy()) if dynamic else None
+    harness.bloom_tail(harness.to_dev(d0), t["d1"], t["d2"], t["d3"], harness.to_dev(hist) if feedback else None, lerp_d3, lum_t, lerp_lum, t["u2"], t["u1"])
+    for k, ref in (("d1", d1), ("d2", d2), ("d3", d3), ("u2", u2), ("u1", u1)):
+        assert np.array_equal(harness.to_host(t[k], np.uint16), ref), k
+    if dynamic:
+        lum = lum_t.cpu().numpy()
+        assert lum.view(np.uint32)[0] == lum_ref.view(np.uint32)[0]
+        assert common.f32_ulp_diff(lum[1:], lum_ref[1:]).max() <= 4
+
+
 @pytest.mark.parametrize("w,h", [(8, 8), (60, 34), (120, 68), (61, 35)])
 def test_luminance(cuda, oracle, w, h):
     from granite_b200 import harness
