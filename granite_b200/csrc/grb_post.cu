@@ -782,7 +782,7 @@ struct TailArgs
 	float lerp_lum, lo, hi;
 };
 
-constexpr int kTailThreads = 256;
+constexpr int kTailThreads = 512; // two CTAs per SM: one thread per texel of the largest level at 4K
 
 __device__ __forceinline__ void tail_level(const View<const uint2> &src, const View<uint2> &dst, float off, const View<const uint2> *history, float lerp,
                                           unsigned first_cta, unsigned num_ctas)
@@ -1219,9 +1219,17 @@ extern "C" int32_t grb_bloom_tail(const GrbImage *d0, const GrbImage *d1, const 
 	a.lerp_lum = lerp_luminance;
 	a.lo = min_loglum;
 	a.hi = max_loglum;
-	// one CTA per SM is co-resident by construction; the largest level (d1 / u1) decides how many are useful
+	// every CTA must be co-resident (grid barrier): ask the occupancy calculator; the largest level
+	// (d1 / u1) decides how many CTAs are useful
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bloom_tail_kernel, kTailThreads, 0) != cudaSuccess || per_sm < 1)
+	{
+		cudaGetLastError();
+		set_last_error("grb_bloom_tail: occupancy query failed");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
 	const int texels = d1->width * d1->height;
-	int ctas = std::min(sms, std::max(1, (texels + kTailThreads - 1) / kTailThreads));
+	int ctas = std::min(sms * std::min(per_sm, 2), std::max(1, (texels + kTailThreads - 1) / kTailThreads));
 	void *params[] = { &a };
 	cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(bloom_tail_kernel), dim3(ctas), dim3(kTailThreads), params, 0, as_stream(stream));
 	if (err != cudaSuccess)

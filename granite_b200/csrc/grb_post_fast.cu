@@ -510,7 +510,12 @@ __global__ void __launch_bounds__(256) taa_fast_kernel(const TaaFastArgs a)
 bool launch_taa_fast(const GrbImage *hdr, const GrbImage *depth, const GrbImage *mv, const GrbImage *history, const float *reproj16, const GrbImage *out_color,
                      const GrbImage *out_history, GrbRows rows, cudaStream_t stream, int32_t *rc)
 {
-	if (exact_requested() || hdr->width > 8192 || hdr->height > 8192)
+	// Opt-in (GRB_TAA_TILES=1): at 3840x2160 this kernel takes 556 us against 584 us for the exact kernel in
+	// grb_post.cu -- 216 M instructions at 35 % issue utilisation, 16 warps per SM waiting on the history
+	// loads behind the exact reprojection arithmetic -- which does not pay for giving up bit-exactness.
+	// DESIGN.md section 8 says what would (a history tile in shared memory).
+	const char *tiles = getenv("GRB_TAA_TILES");
+	if (!tiles || tiles[0] == '0' || exact_requested() || hdr->width > 8192 || hdr->height > 8192)
 		return false;
 	TaaFastArgs a;
 	a.hdr = view_of<const uint32_t>(hdr);
