@@ -626,9 +626,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 5) deferred_lighting2_kerne
 //     that F0 and the diffuse colour leave the loop:  result = dk (1-F0) S1 + F0 S2 + S3;
 //   * pixel blocks are handed out through an atomic queue in chunks, so a warp that drew cheap
 //     blocks simply draws more.
-constexpr int kPWarps = 16;
-constexpr int kListCap = 160; // light list entries per warp; shaded in batches when it fills up
-constexpr int kMaxOrderRows = 2048; // block rows whose schedule fits in shared memory (images up to 8192 rows)
+#ifndef GRB_LIGHTING_WARPS
+#define GRB_LIGHTING_WARPS 16
+#endif
+constexpr int kPWarps = GRB_LIGHTING_WARPS;      // 16: two lights per iteration, 128 registers; 20: one light, <= 102 registers
+constexpr bool kPairLights = kPWarps <= 16;
+constexpr unsigned kSlotBytes = kPWarps > 16 ? 40u : 48u; // G-buffer prefetch slot per thread (36 bytes used)
+constexpr int kListCap = kPWarps > 16 ? 128 : 160; // light list entries per warp; shaded in batches when it fills up
+constexpr int kMaxOrderRows = kPWarps > 16 ? 1024 : 2048; // block rows whose schedule fits in shared memory (images up to 4096 / 8192 rows)
 
 #ifdef GRB_LIGHTING_DEBUG
 constexpr int kDbgBlocks = 240 * 540;
@@ -742,7 +747,7 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 	uint16_t *s_lists = reinterpret_cast<uint16_t *>(smem_raw + rec_total + 1024u);
 	const unsigned lists_bytes = (kPWarps * (kListCap + 2) * 2u + 15u) & ~15u;
 	unsigned char *s_prefetch = smem_raw + rec_total + 1024u + lists_bytes; // 48 B per thread
-	uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_prefetch + 32u * kPWarps * 48u);
+	uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_prefetch + 32u * kPWarps * kSlotBytes);
 	uint16_t *s_order = reinterpret_cast<uint16_t *>(s_bar + 2); // kMaxOrderRows entries
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -877,7 +882,7 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 	// The G-buffer words of the NEXT block are copied asynchronously (cp.async, no registers held)
 	// into this lane's 48-byte slot while the current block is shaded: the HBM round trip at the head
 	// of every block otherwise leaves the warp idle for a seventh of its time.
-	const uint32_t pf_slot = smem_u32(s_prefetch + (size_t)threadIdx.x * 48u);
+	const uint32_t pf_slot = smem_u32(s_prefetch + (size_t)threadIdx.x * kSlotBytes);
 	auto prefetch_gbuffer = [&](const Item &it) {
 		const int x = it.x, y = it.y;
 		if (x < p.hdr.w && y < p.y1)
@@ -915,7 +920,7 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		if (inside)
 		{
-			const unsigned char *slot = s_prefetch + (size_t)threadIdx.x * 48u;
+			const unsigned char *slot = s_prefetch + (size_t)threadIdx.x * kSlotBytes;
 			depth = *reinterpret_cast<const float2 *>(slot);
 			a8 = *reinterpret_cast<const uint2 *>(slot + 8);
 			n10 = *reinterpret_cast<const uint2 *>(slot + 16);
@@ -1089,8 +1094,26 @@ __global__ void __launch_bounds__(32 * kPWarps, 1) deferred_lighting_persistent_
 			if (lane == 0)
 				list[count] = (uint16_t)dummy_entry; // pads an odd batch
 			__syncwarp();
+			if (!kPairLights)
+			{
+				// one light per iteration: a third fewer live registers, which buys four more warps per SM
+				for (int e = 0; e < count; e++)
+				{
+					const unsigned ent = list[e];
+					const unsigned i0 = ent & 0x7fffu;
+					const float4 a0 = s_rec[3u * i0], a1 = s_rec[3u * i0 + 1u], a2 = s_rec[3u * i0 + 2u];
+					f2 ta, tga, tgb;
+					if (ent & 0x8000u)
+						light_terms<true>(s, a0, a1, a2, true, ta, tga, tgb);
+					else
+						light_terms<false>(s, a0, a1, a2, false, ta, tga, tgb);
+					S1x = fma2(mk2(a0.x), ta, S1x); S1y = fma2(mk2(a0.y), ta, S1y); S1z = fma2(mk2(a0.z), ta, S1z);
+					S2x = fma2(mk2(a0.x), tga, S2x); S2y = fma2(mk2(a0.y), tga, S2y); S2z = fma2(mk2(a0.z), tga, S2z);
+					S3x = fma2(mk2(a0.x), tgb, S3x); S3y = fma2(mk2(a0.y), tgb, S3y); S3z = fma2(mk2(a0.z), tgb, S3z);
+				}
+			}
 			uint32_t two_next = *reinterpret_cast<const uint32_t *>(list);
-			for (int e = 0; e < count; e += 2)
+			for (int e = 0; kPairLights && e < count; e += 2)
 			{
 				const uint32_t two = two_next;
 				two_next = *reinterpret_cast<const uint32_t *>(list + e + 2); // in bounds: the list has room for kListCap + 2 entries
@@ -1486,7 +1509,7 @@ extern "C" int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *g, const Gr
 			a.row_shape_threshold = e ? (unsigned)strtoul(e, nullptr, 10) : 0u;
 		}
 		a.queue = di.queue + (di.next_slot.fetch_add(1u, std::memory_order_relaxed) % 64u);
-		const size_t smem = (size_t)a.rec_bytes + 48u + 1024u + ((kPWarps * (kListCap + 2) * 2u + 15u) & ~15u) + 32u * kPWarps * 48u + 16u + kMaxOrderRows * 2u;
+		const size_t smem = (size_t)a.rec_bytes + 48u + 1024u + ((kPWarps * (kListCap + 2) * 2u + 15u) & ~15u) + 32u * kPWarps * kSlotBytes + 16u + kMaxOrderRows * 2u;
 		if (smem <= (size_t)di.smem_max)
 		{
 			const int ctas = std::min(di.sm_count, std::max(1, (a.blocks_x * a.blocks_y + kPWarps - 1) / kPWarps));

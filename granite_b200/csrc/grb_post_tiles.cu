@@ -463,7 +463,10 @@ bool tiles_disabled()
 // (the caller then runs the generic kernel); true means "launched" and `*rc` holds the result.
 bool launch_tent_tiled(bool up, const GrbImage *in, const GrbImage *history, float lerp, const GrbImage *out, GrbRows rows, cudaStream_t stream, int32_t *rc)
 {
-	if (tiles_disabled())
+	// Only the large levels (1/4 resolution of a 4K frame) are worth a tile kernel; the levels below stay
+	// on the bit-exact generic kernels, which is also what the fused tail (grb_bloom_tail) computes -- a
+	// level's arithmetic must not depend on whether the caller fused the tail or a frame is row-sharded.
+	if (tiles_disabled() || (long long)out->width * out->height < 200000)
 		return false;
 	const bool shape_ok = up ? (out->width == 2 * in->width && out->height == 2 * in->height) : (in->width == 2 * out->width && in->height == 2 * out->height);
 	if (!shape_ok || (up && history))

@@ -250,7 +250,7 @@ def test_bloom_downsample_bit_exact(cuda, oracle, w_in, h_in, w, h, feedback):
     full = harness.to_host(out, np.uint16)
     # exact 2:1 steps run the TMA tile kernel, whose packed multiply-adds are contracted by ptxas
     # (grb_post_tiles.cu): 1 fp16 ulp on ~5e-5 of the texels; other shapes are bit-exact
-    tiled = (w_in == 2 * w and h_in == 2 * h)
+    tiled = (w_in == 2 * w and h_in == 2 * h and w * h >= 200000)  # smaller levels stay on the generic kernels
     if tiled:
         common.assert_f16_close(full, ref, "downsample")
     else:
@@ -273,7 +273,7 @@ def test_bloom_upsample_bit_exact(cuda, oracle, w_in, h_in, w, h):
     out = harness.new_rgba16f(w, h)
     harness.bloom_upsample(harness.to_dev(src), out)
     full = harness.to_host(out, np.uint16)
-    if w == 2 * w_in and h == 2 * h_in:
+    if w == 2 * w_in and h == 2 * h_in and w * h >= 200000:
         common.assert_f16_close(full, ref, "upsample")
     else:
         assert np.array_equal(full, ref)
