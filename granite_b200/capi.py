@@ -77,7 +77,7 @@ class GrbGBuffer(C.Structure):
 ENTRY_POINTS = [
     "grb_abi_version", "grb_init", "grb_last_error_string",
     "grb_cluster_spot_transform", "grb_cluster_cull_setup", "grb_cluster_binning", "grb_cluster_z_range",
-    "grb_cluster_build", "grb_deferred_lighting", "grb_deferred_lighting_scheduled", "grb_lighting_schedule_bytes", "grb_debug_cluster_indices", "grb_lighting_row_cost",
+    "grb_cluster_build", "grb_deferred_lighting", "grb_deferred_lighting_blocks", "grb_deferred_lighting_scheduled", "grb_lighting_schedule_bytes", "grb_debug_cluster_indices", "grb_lighting_row_cost",
     "grb_bloom_threshold", "grb_bloom_threshold_downsample", "grb_bloom_threshold_downsample_to_peers", "grb_bloom_downsample", "grb_bloom_downsample_to_peers", "grb_peer_wait", "grb_bloom_upsample",
     "grb_luminance", "grb_luminance_grid", "grb_luminance_finalize", "grb_bloom_tail", "grb_tonemap",
     "grb_fxaa", "grb_taa_resolve",
@@ -110,6 +110,8 @@ def lib() -> C.CDLL:
             "grb_cluster_build": [C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters), C.POINTER(GrbClusterBuffers), P],
             "grb_deferred_lighting": [C.POINTER(GrbGBuffer), C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters),
                                       C.POINTER(GrbClusterBuffers), IMG, GrbRows, P],
+            "grb_deferred_lighting_blocks": [C.POINTER(GrbGBuffer), C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters),
+                                             C.POINTER(GrbClusterBuffers), IMG, GrbRows, P],
             "grb_deferred_lighting_scheduled": [C.POINTER(GrbGBuffer), C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters),
                                                 C.POINTER(GrbClusterBuffers), IMG, GrbRows, P, P],
             "grb_debug_cluster_indices": [IMG, C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters), P, P, GrbRows, P],

@@ -1376,8 +1376,30 @@ extern "C" int32_t grb_deferred_lighting(const GrbGBuffer *g, const GrbCamera *c
 	return grb_deferred_lighting_scheduled(g, cam, params, buf, hdr, rows, nullptr, stream);
 }
 
+static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
+                                        const GrbImage *hdr, GrbRows rows, void *schedule, void *stream, bool blocks_only);
+
 extern "C" int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params,
                                                    const GrbClusterBuffers *buf, const GrbImage *hdr, GrbRows rows, void *schedule, void *stream)
+{
+	return launch_deferred_lighting(g, cam, params, buf, hdr, rows, schedule, stream, false);
+}
+
+// The same pass as a plain grid of short-lived CTAs (one per 64x4 pixel block) instead of persistent ones.
+// For callers whose other streams must get SMs WHILE lighting runs: a persistent CTA keeps its SM (all of
+// its registers and shared memory) until the work queue is empty, so kernels of other streams that become
+// runnable in the meantime wait for the whole pass -- measured on a frame split over 2 GPUs, where the
+// post chain waits for the peer's band: 2441 frames/s with the persistent kernel, 3321 with this one.
+// Results are within the same parity bar; the two forms associate the per-light sums differently, so
+// they are not bit-identical to each other (use one form for every rank of a sharded frame).
+extern "C" int32_t grb_deferred_lighting_blocks(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
+                                                const GrbImage *hdr, GrbRows rows, void *stream)
+{
+	return launch_deferred_lighting(g, cam, params, buf, hdr, rows, nullptr, stream, true);
+}
+
+static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
+                                        const GrbImage *hdr, GrbRows rows, void *schedule, void *stream, bool blocks_only)
 {
 	if (!g || !cam || !params || !buf || !hdr)
 	{
@@ -1458,7 +1480,7 @@ extern "C" int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *g, const Gr
 	                   aligned8(g->depth.data, g->depth.row_pitch) && (reinterpret_cast<uintptr_t>(g->pbr.data) % 4) == 0 && (g->pbr.row_pitch % 4) == 0 &&
 	                   aligned8(hdr->data, hdr->row_pitch) && (!g->emissive.data || aligned8(g->emissive.data, g->emissive.row_pitch));
 	static const bool force_v2 = getenv("GRB_LIGHTING_V2") != nullptr;
-	if (pairs && !force_v2 && params->num_lights <= 4096 && params->num_lights_32 <= 128)
+	if (pairs && !force_v2 && !blocks_only && params->num_lights <= 4096 && params->num_lights_32 <= 128)
 	{
 		// persistent kernel: one CTA per SM, light table in shared memory
 		int device = 0;

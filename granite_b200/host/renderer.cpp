@@ -5,7 +5,7 @@
 namespace Granite
 {
 void DeferredLightRenderer::render_light(Vulkan::CommandBuffer &cmd, const RenderContext &context, const GBufferViews &gb, Vulkan::ImageView &hdr,
-                                         GrbRows rows, void *schedule)
+                                         GrbRows rows, void *schedule, bool blocks_form)
 {
 	auto *light = context.get_lighting_parameters();
 	if (!light || !gb.albedo || !gb.normal || !gb.pbr || !gb.depth)
@@ -54,7 +54,12 @@ void DeferredLightRenderer::render_light(Vulkan::CommandBuffer &cmd, const Rende
 		return;
 	}
 	GrbImage hdr_img = hdr.as_grb();
-	cmd.check(grb_deferred_lighting_scheduled(&g, &cam, &params, &buffers, &hdr_img, rows, schedule, cmd.get_stream_handle()), "grb_deferred_lighting");
+	// Row-sharded frames (rows != whole image, no schedule): the block form, so that the exchange-dependent
+	// post chain of the previous frame can interleave with this pass (see grb_deferred_lighting_blocks).
+	if (blocks_form)
+		cmd.check(grb_deferred_lighting_blocks(&g, &cam, &params, &buffers, &hdr_img, rows, cmd.get_stream_handle()), "grb_deferred_lighting_blocks");
+	else
+		cmd.check(grb_deferred_lighting_scheduled(&g, &cam, &params, &buffers, &hdr_img, rows, schedule, cmd.get_stream_handle()), "grb_deferred_lighting");
 }
 
 void DeferredLightingPass::setup_dependencies(RenderPass &self, RenderGraph &graph_)
@@ -87,6 +92,7 @@ void DeferredLightingPass::build_render_pass(Vulkan::CommandBuffer &cmd)
 		gb.emissive = &graph->get_physical_texture_resource(*res_emissive);
 	auto &hdr = graph->get_physical_texture_resource(*res_hdr);
 	void *schedule = res_schedule ? graph->get_physical_buffer_resource(*res_schedule).get_device_pointer() : nullptr;
-	DeferredLightRenderer::render_light(cmd, context, gb, hdr, graph->is_sharded() ? graph->get_shard_plan().lighting : GrbRows{ 0, 0 }, schedule);
+	const bool sharded = graph->is_sharded() && graph->get_shard_count() > 1;
+	DeferredLightRenderer::render_light(cmd, context, gb, hdr, graph->is_sharded() ? graph->get_shard_plan().lighting : GrbRows{ 0, 0 }, schedule, sharded);
 }
 } // namespace Granite

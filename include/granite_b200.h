@@ -175,6 +175,11 @@ typedef struct GrbGBuffer
 int32_t grb_deferred_lighting(const GrbGBuffer *gbuffer, const GrbCamera *cam,
                               const GrbClusterParameters *params, const GrbClusterBuffers *buf,
                               const GrbImage *hdr, GrbRows rows, void *stream);
+/* Same pass as a plain grid of short-lived CTAs (no persistent CTAs, no schedule): the form for callers whose
+ * other streams must get SMs while lighting runs, e.g. every rank of a row-sharded frame (granite_b200/csrc/
+ * grb_lighting.cu).  Within the same parity bar; not bit-identical to the persistent form. */
+int32_t grb_deferred_lighting_blocks(const GrbGBuffer *gbuffer, const GrbCamera *cam, const GrbClusterParameters *params,
+                                     const GrbClusterBuffers *buf, const GrbImage *hdr, GrbRows rows, void *stream);
 /* Same pass with a caller-owned SCHEDULE buffer: grb_lighting_schedule_bytes(image height) bytes of
  * device memory, zero-initialised once and then left alone, used by one stream at a time.  Each
  * launch measures what every row of pixel blocks cost and leaves them sorted by falling cost; the
