@@ -80,7 +80,7 @@ ENTRY_POINTS = [
     "grb_cluster_build", "grb_deferred_lighting", "grb_deferred_lighting_blocks", "grb_deferred_lighting_scheduled", "grb_lighting_schedule_bytes", "grb_debug_cluster_indices", "grb_lighting_row_cost",
     "grb_bloom_threshold", "grb_bloom_threshold_downsample", "grb_bloom_threshold_downsample_to_peers", "grb_bloom_downsample", "grb_bloom_downsample_to_peers", "grb_peer_wait", "grb_bloom_upsample",
     "grb_luminance", "grb_luminance_grid", "grb_luminance_finalize", "grb_bloom_tail", "grb_tonemap",
-    "grb_fxaa", "grb_taa_resolve",
+    "grb_pq10_encode", "grb_fxaa", "grb_taa_resolve",
 ]
 
 _lib = None
@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
             "grb_luminance_finalize": [P, I, I, P, F, F, F, P],
             "grb_bloom_tail": [IMG, IMG, IMG, IMG, IMG, F, P, F, F, F, IMG, IMG, P],
             "grb_tonemap": [IMG, IMG, P, F, IMG, GrbRows, P],
+            "grb_pq10_encode": [IMG, IMG, P, F, F, F, IMG, GrbRows, P],
             "grb_fxaa": [IMG, IMG, GrbRows, P],
             "grb_taa_resolve": [IMG, IMG, IMG, IMG, P, I, IMG, IMG, GrbRows, P],
         }

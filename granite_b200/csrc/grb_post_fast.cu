@@ -538,3 +538,104 @@ bool launch_taa_fast(const GrbImage *hdr, const GrbImage *depth, const GrbImage 
 	return true;
 }
 } // namespace grb
+
+// =============================================================================== K14 HDR10 / PQ
+// pq10_encode.frag:20-52 (setup_hdr10_pq_encoding, renderer/post/hdr.cpp:595-658): scene colour +
+// UI layer -> display primaries -> soft knee above 0.75 -> ST.2084 (PQ) -> A2B10G10R10.  Four pixels
+// per thread, 16-byte loads and stores; the two pow() per channel are lg2 / ex2 (the output has 10 bits).
+namespace grb
+{
+namespace
+{
+struct PqParams
+{
+	float m[9]; // column-major mat3
+	float hdr_pre, ui_pre, max_light, inv_max;
+};
+
+GRB_DEV float pq_channel_fast(float col, float max_light)
+{
+	const float ck = col * 4.0f;
+	const float knee = ck * rcp_fast(1.0f + ck);
+	const float c = col > 0.75f ? knee : col;
+	const float y = c * max_light * (1.0f / 10000.0f);
+	// pow(y, m1): y <= 0 (black, or negative after the primaries conversion: NaN in the shader, stored as 0) -> 0
+	const float p = y > 0.0f ? ex2_fast(lg2_fast(y) * 0.1593017578125f) : 0.0f;
+	const float num = fmaf(18.8515625f, p, 0.8359375f), den = fmaf(18.6875f, p, 1.0f);
+	const float n = ex2_fast(lg2_fast(num * rcp_fast(den)) * 78.84375f);
+	return y >= 0.0f ? n : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) pq10_encode_kernel(View<const uint32_t> hdr, View<const uint32_t> ui, PqParams q, View<uint32_t> out, int y0, int y1)
+{
+	const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+	const int y = y0 + blockIdx.y * 8 + threadIdx.y;
+	if (x4 >= out.w || y >= y1)
+		return;
+	uint32_t hp[4], up[4], px[4];
+	if (x4 + 3 < out.w && (reinterpret_cast<uintptr_t>(&hdr.at(x4, y)) & 15u) == 0 && (reinterpret_cast<uintptr_t>(&ui.at(x4, y)) & 15u) == 0)
+	{
+		const uint4 h4 = __ldg(reinterpret_cast<const uint4 *>(&hdr.at(x4, y))), u4 = __ldg(reinterpret_cast<const uint4 *>(&ui.at(x4, y)));
+		hp[0] = h4.x; hp[1] = h4.y; hp[2] = h4.z; hp[3] = h4.w;
+		up[0] = u4.x; up[1] = u4.y; up[2] = u4.z; up[3] = u4.w;
+	}
+	else
+		for (int j = 0; j < 4; j++)
+		{
+			const int xx = min(x4 + j, out.w - 1);
+			hp[j] = __ldg(&hdr.at(xx, y));
+			up[j] = __ldg(&ui.at(xx, y));
+		}
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+	{
+		const float3 c = unpack_r11g11b10(hp[j]);
+		const float k255 = 1.0f / 255.0f;
+		const float ur = (float)(up[j] & 0xffu) * k255, ug = (float)((up[j] >> 8) & 0xffu) * k255, ub = (float)((up[j] >> 16) & 0xffu) * k255,
+		            ua = (float)(up[j] >> 24) * k255;
+		const float s = q.hdr_pre * ua;
+		const float r = fmaf(c.x, s, ur * q.ui_pre), g = fmaf(c.y, s, ug * q.ui_pre), b = fmaf(c.z, s, ub * q.ui_pre);
+		const float cr = fmaf(q.m[6], b, fmaf(q.m[3], g, q.m[0] * r)) * q.inv_max;
+		const float cg = fmaf(q.m[7], b, fmaf(q.m[4], g, q.m[1] * r)) * q.inv_max;
+		const float cb = fmaf(q.m[8], b, fmaf(q.m[5], g, q.m[2] * r)) * q.inv_max;
+		const uint32_t qr = (uint32_t)__float2int_rz(fmaf(__saturatef(pq_channel_fast(cr, q.max_light)), 1023.0f, 0.5f));
+		const uint32_t qg = (uint32_t)__float2int_rz(fmaf(__saturatef(pq_channel_fast(cg, q.max_light)), 1023.0f, 0.5f));
+		const uint32_t qb = (uint32_t)__float2int_rz(fmaf(__saturatef(pq_channel_fast(cb, q.max_light)), 1023.0f, 0.5f));
+		px[j] = qr | (qg << 10) | (qb << 20) | (3u << 30);
+	}
+	if (x4 + 3 < out.w && (reinterpret_cast<uintptr_t>(&out.at(x4, y)) & 15u) == 0)
+		*reinterpret_cast<uint4 *>(&out.at(x4, y)) = make_uint4(px[0], px[1], px[2], px[3]);
+	else
+		for (int j = 0; j < 4 && x4 + j < out.w; j++)
+			out.at(x4 + j, y) = px[j];
+}
+} // namespace
+} // namespace grb
+
+using namespace grb;
+
+extern "C" int32_t grb_pq10_encode(const GrbImage *hdr, const GrbImage *ui, const float *primary_conversion16, float hdr_pre_exposure, float ui_pre_exposure,
+                                   float max_light_level, const GrbImage *out, GrbRows rows, void *stream)
+{
+	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !image_ok(ui, GRB_FORMAT_R8G8B8A8_UNORM, 4) ||
+	    !image_ok(out, GRB_FORMAT_A2B10G10R10_UNORM_PACK32, 4) || !primary_conversion16 || !(max_light_level > 0.0f) || hdr->width != out->width ||
+	    hdr->height != out->height || ui->width != out->width || ui->height != out->height)
+	{
+		set_last_error("grb_pq10_encode: hdr B10G11R11_UFLOAT, ui R8G8B8A8_UNORM, out A2B10G10R10_UNORM of one size; max_light_level > 0");
+		return GRB_ERR_UNSUPPORTED_FORMAT;
+	}
+	rows = full_rows(rows, out->height);
+	if (rows.y1 <= rows.y0)
+		return GRB_OK;
+	PqParams q;
+	for (int c = 0; c < 3; c++)
+		for (int r = 0; r < 3; r++)
+			q.m[c * 3 + r] = primary_conversion16[c * 4 + r]; // mat3(mat4)
+	q.hdr_pre = hdr_pre_exposure;
+	q.ui_pre = ui_pre_exposure;
+	q.max_light = max_light_level;
+	q.inv_max = 1.0f / max_light_level; // hdr.cpp:637
+	dim3 block(32, 8), grid((out->width + 127) / 128, (rows.y1 - rows.y0 + 7) / 8, 1);
+	pq10_encode_kernel<<<grid, block, 0, as_stream(stream)>>>(view_of<const uint32_t>(hdr), view_of<const uint32_t>(ui), q, view_of<uint32_t>(out), rows.y0, rows.y1);
+	return check_launch("grb_pq10_encode");
+}

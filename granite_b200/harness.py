@@ -203,6 +203,15 @@ def fxaa(in_t, out_t, target_srgb=True, rows=None):
     capi.check(capi.lib().grb_fxaa(C.byref(ii), C.byref(oi), capi.rows(rows), capi.stream_ptr()), "grb_fxaa")
 
 
+def pq10_encode(hdr_t, ui_t, primary16, hdr_pre, ui_pre, max_light, out_t, rows=None):
+    hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
+    ui = capi.image(ui_t, capi.FORMAT_R8G8B8A8_UNORM)
+    oi = capi.image(out_t, capi.FORMAT_A2B10G10R10_UNORM)
+    m = (C.c_float * 16)(*np.asarray(primary16, np.float32).reshape(-1).tolist())
+    capi.check(capi.lib().grb_pq10_encode(C.byref(hi), C.byref(ui), m, float(hdr_pre), float(ui_pre), float(max_light), C.byref(oi), capi.rows(rows),
+                                          capi.stream_ptr()), "grb_pq10_encode")
+
+
 def taa_resolve(hdr_t, depth_t, mv_t, history_t, reproj, quality, out_color_t, out_history_t, rows=None):
     hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
     oc = capi.image(out_color_t, capi.FORMAT_B10G11R11_UFLOAT)

@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <memory>
+#include <utility>
 
 namespace Granite
 {
@@ -222,5 +224,132 @@ void setup_hdr_postprocess(RenderGraph &graph, const FrameParameters &frame, con
                            const HDROptions &options, const HDRDynamicExposureInterface *iface)
 {
 	setup_hdr_postprocess_compute(graph, frame, input, output, options, iface);
+}
+// ---------------------------------------------------------------------------------------------------- HDR10 / PQ
+namespace
+{
+// Chromaticities (x, y) -> XYZ, Y = 1; then the per-primary scale that makes R+G+B land on the white point
+// (renderer/post/hdr.cpp:563-578 through math/transforms' compute_xyz_matrix).  Done in double, as a 4x4 so that the
+// host's own Gauss-Jordan inverse serves; rounded to fp32 once at the end.
+struct Mat3d
+{
+	double m[3][3]; // m[col][row]
+};
+
+// x = inverse(a) * rhs by Gauss-Jordan elimination with partial pivoting.
+void solve3(const Mat3d &m, const double rhs[3], double x[3])
+{
+	double a[3][4];
+	for (int r = 0; r < 3; r++)
+	{
+		for (int c = 0; c < 3; c++)
+			a[r][c] = m.m[c][r];
+		a[r][3] = rhs[r];
+	}
+	for (int k = 0; k < 3; k++)
+	{
+		int piv = k;
+		for (int r = k + 1; r < 3; r++)
+			if (std::fabs(a[r][k]) > std::fabs(a[piv][k]))
+				piv = r;
+		if (piv != k)
+			for (int c = 0; c < 4; c++)
+				std::swap(a[k][c], a[piv][c]);
+		for (int r = 0; r < 3; r++)
+		{
+			if (r == k)
+				continue;
+			const double f = a[r][k] / a[k][k];
+			for (int c = k; c < 4; c++)
+				a[r][c] -= f * a[k][c];
+		}
+	}
+	for (int r = 0; r < 3; r++)
+		x[r] = a[r][3] / a[r][r];
+}
+
+Mat3d xyz_from_chromaticities(const VkHdrMetadataEXT &md)
+{
+	const VkXYColorEXT prim[3] = { md.displayPrimaryRed, md.displayPrimaryGreen, md.displayPrimaryBlue };
+	Mat3d p;
+	for (int c = 0; c < 3; c++)
+	{
+		const double x = prim[c].x, y = prim[c].y;
+		p.m[c][0] = x / y;
+		p.m[c][1] = 1.0;
+		p.m[c][2] = (1.0 - x - y) / y;
+	}
+	const double wx = md.whitePoint.x, wy = md.whitePoint.y;
+	const double white[3] = { wx / wy, 1.0, (1.0 - wx - wy) / wy };
+	double scale[3];
+	solve3(p, white, scale);
+	for (int c = 0; c < 3; c++)
+		for (int r = 0; r < 3; r++)
+			p.m[c][r] *= scale[c];
+	return p;
+}
+} // namespace
+
+muglm::mat4 compute_rec709_to_display_primaries(const VkHdrMetadataEXT &metadata)
+{
+	VkHdrMetadataEXT rec709 = {};
+	rec709.displayPrimaryRed = { 0.640f, 0.330f };
+	rec709.displayPrimaryGreen = { 0.3f, 0.6f };
+	rec709.displayPrimaryBlue = { 0.150f, 0.060f };
+	rec709.whitePoint = { 0.3127f, 0.3290f };
+	const Mat3d src = xyz_from_chromaticities(rec709), dst = xyz_from_chromaticities(metadata);
+	muglm::mat4 out(1.0f); // mat4(mat3): identity elsewhere (hdr.cpp:651)
+	for (int col = 0; col < 3; col++)
+	{
+		double x[3];
+		solve3(dst, src.m[col], x); // column of inverse(dst) * src
+		for (int r = 0; r < 3; r++)
+			out[col][r] = (float)x[r];
+	}
+	return out;
+}
+
+void setup_hdr10_pq_encoding(RenderGraph &graph, const std::string &output, const std::string &hdr_input, const std::string &ui_input,
+                             const HDR10PQEncodingConfig &config, const VkHdrMetadataEXT &static_metadata)
+{
+	struct PQEncoder : RenderPassInterface
+	{
+		HDR10PQEncodingConfig config = {};
+		RenderGraph *graph = nullptr;
+		RenderPass *self = nullptr;
+		RenderTextureResource *hdr = nullptr;
+		RenderTextureResource *ui = nullptr;
+		muglm::mat4 primary_conversion;
+		float max_light_level = 1000.0f;
+
+		bool get_clear_color(unsigned, VkClearColorValue *) const override { return false; }
+
+		void build_render_pass(Vulkan::CommandBuffer &cmd) override
+		{
+			GrbImage h = graph->get_physical_texture_resource(*hdr).as_grb();
+			GrbImage u = graph->get_physical_texture_resource(*ui).as_grb_unorm();
+			GrbImage o = graph->get_physical_texture_resource(*self->get_color_outputs()[0]).as_grb();
+			const GrbRows rows = graph->is_sharded() ? graph->get_shard_plan().own : GrbRows{ 0, 0 };
+			cmd.check(grb_pq10_encode(&h, &u, primary_conversion.data(), config.hdr_pre_exposure, config.ui_pre_exposure, max_light_level, &o, rows,
+			                          cmd.get_stream_handle()),
+			          "grb_pq10_encode");
+		}
+	};
+
+	auto &pq10 = graph.add_pass("pq10", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+	AttachmentInfo att;
+	att.size_class = SizeClass::InputRelative;
+	att.size_relative_name = hdr_input;
+	att.format = VK_FORMAT_A2B10G10R10_UNORM_PACK32; // the HDR10 swapchain format the reference's default attachment resolves to
+	auto pass = std::make_shared<PQEncoder>();
+	pass->config = config;
+	pass->graph = &graph;
+	pass->self = &pq10;
+	pass->primary_conversion = compute_rec709_to_display_primaries(static_metadata);
+	pass->max_light_level = static_metadata.maxContentLightLevel; // hdr.cpp:652
+	pq10.add_color_output(output, att);
+	pass->hdr = &pq10.add_texture_input(hdr_input);
+	pass->ui = &pq10.add_texture_input(ui_input);
+	pq10.set_render_pass_interface(std::move(pass));
 }
 } // namespace Granite

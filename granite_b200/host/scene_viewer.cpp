@@ -62,6 +62,7 @@ struct GrbhViewer
 	mat4 projection = mat4(1.0f), view = mat4(1.0f);
 	bool baked = false;
 	std::string output_name;
+	bool ui_layer_cleared = false;
 	const GrbhHostGBuffer *pending_upload = nullptr;
 	unsigned profiled_frames = 0;
 	std::map<std::string, std::pair<double, int>> timings;
@@ -217,50 +218,99 @@ void GrbhViewer::bake_render_graph()
 	if (resolved && async_post)
 		graph.get_texture_resource("HDR-resolved").get_attachment_info().flags |= ATTACHMENT_INFO_PINGPONG_BIT;
 
-	// ---- HDR chain ----
+	// ---- HDR10 swapchain: no bloom / tonemap, the scene goes to the PQ encoder (scene_viewer_application.cpp:1233-1288) ----
 	std::string chain_input = resolved ? "HDR-resolved" : light_output;
-	HDROptions opts;
-	opts.dynamic_exposure = config.dynamic_exposure != 0;
-	if (config.hdr_bloom)
-		setup_hdr_postprocess_compute(graph, context.get_frame_parameters(), chain_input, "tonemapped", opts, &exposure);
+	std::string ui_source;
+	if (config.hdr10_output)
+	{
+		// "ui": the application's widgets over a layer cleared to (0, 0, 0, 1) (scene_viewer_application.cpp:1296-1302).
+		// Widget rendering is the application's; this viewer draws none, so the layer is its clear colour.
+		AttachmentInfo ui_info;
+		ui_info.format = VK_FORMAT_R8G8B8A8_UNORM;
+		ui_info.size_class = SizeClass::InputRelative;
+		ui_info.size_relative_name = chain_input;
+		auto &ui = graph.add_pass("ui", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+		auto &ui_layer = ui.add_color_output("ui-temporary", ui_info);
+		ui.add_texture_input(chain_input);
+		ui.set_get_clear_color([](unsigned, VkClearColorValue *value) {
+			if (value)
+			{
+				value->float32[0] = value->float32[1] = value->float32[2] = 0.0f;
+				value->float32[3] = 1.0f;
+			}
+			return true;
+		});
+		ui_layer_cleared = false;
+		ui.set_build_render_pass([this, &ui_layer](Vulkan::CommandBuffer &cmd) {
+			if (ui_layer_cleared)
+				return; // nothing draws into the layer afterwards
+			auto &view_ = graph.get_physical_texture_resource(ui_layer);
+			const std::vector<uint32_t> clear((size_t)config.width * (size_t)config.height, 0xff000000u);
+			Vulkan::cuda_ok(cudaMemcpyAsync(view_.get_image().get_device_pointer(), clear.data(), clear.size() * 4, cudaMemcpyHostToDevice,
+			                                reinterpret_cast<cudaStream_t>(cmd.get_stream())),
+			                "ui layer clear");
+			Vulkan::cuda_ok(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(cmd.get_stream())), "ui layer clear");
+			ui_layer_cleared = true;
+		});
+
+		HDR10PQEncodingConfig hdr10_config = {};
+		hdr10_config.hdr_pre_exposure = 500.0f; // scene_viewer_application.cpp:1284-1285
+		hdr10_config.ui_pre_exposure = 400.0f;
+		VkHdrMetadataEXT md = {};
+		md.displayPrimaryRed = { 0.708f, 0.292f }; // BT.2020, D65
+		md.displayPrimaryGreen = { 0.170f, 0.797f };
+		md.displayPrimaryBlue = { 0.131f, 0.046f };
+		md.whitePoint = { 0.3127f, 0.3290f };
+		md.maxContentLightLevel = config.hdr10_max_content_light_level > 0.0f ? config.hdr10_max_content_light_level : 1000.0f;
+		setup_hdr10_pq_encoding(graph, "ui-output", chain_input, "ui-temporary", hdr10_config, md);
+		ui_source = "ui-output";
+	}
 	else
 	{
-		// BASELINE config 1: a single tonemap pass.  tonemap.frag always samples uBloom; with
-		// bloom off that image is the zero-initialised one nothing ever writes.
-		AttachmentInfo quarter;
-		quarter.format = VK_FORMAT_R16G16B16A16_SFLOAT;
-		quarter.size_class = SizeClass::InputRelative;
-		quarter.size_relative_name = chain_input;
-		quarter.size_x = 0.25f;
-		quarter.size_y = 0.25f;
-		auto &off = graph.add_pass("bloom-disabled", RENDER_GRAPH_QUEUE_COMPUTE_BIT);
-		off.add_storage_texture_output("upsample-0", quarter);
-		off.add_texture_input(chain_input);
-		off.set_build_render_pass([](Vulkan::CommandBuffer &) {});
-		AttachmentInfo tonemap_info;
-		tonemap_info.size_class = SizeClass::InputRelative;
-		tonemap_info.size_relative_name = chain_input;
-		auto &tonemap = graph.add_pass("tonemap", RenderGraph::get_default_post_graphics_queue());
-		auto &out = tonemap.add_color_output("tonemapped", tonemap_info);
-		auto &hdr_res = tonemap.add_texture_input(chain_input);
-		auto &bloom_res = tonemap.add_texture_input("upsample-0");
-		tonemap.set_build_render_pass([this, &out, &hdr_res, &bloom_res](Vulkan::CommandBuffer &cmd) {
-			GrbImage hdr = graph.get_physical_texture_resource(hdr_res).as_grb();
-			GrbImage bloom = graph.get_physical_texture_resource(bloom_res).as_grb();
-			auto &ov = graph.get_physical_texture_resource(out);
-			GrbImage o = ov.as_grb();
-			cmd.check(grb_tonemap(&hdr, &bloom, nullptr, exposure.get_exposure(), &o, graph.is_sharded() ? graph.get_shard_plan().tonemap : GrbRows{ 0, 0 },
-			                      cmd.get_stream_handle()),
-			          "grb_tonemap");
-		});
-	}
-	std::string ui_source = "tonemapped";
+		// ---- HDR chain ----
+		HDROptions opts;
+		opts.dynamic_exposure = config.dynamic_exposure != 0;
+		if (config.hdr_bloom)
+			setup_hdr_postprocess_compute(graph, context.get_frame_parameters(), chain_input, "tonemapped", opts, &exposure);
+		else
+		{
+			// BASELINE config 1: a single tonemap pass.  tonemap.frag always samples uBloom; with
+			// bloom off that image is the zero-initialised one nothing ever writes.
+			AttachmentInfo quarter;
+			quarter.format = VK_FORMAT_R16G16B16A16_SFLOAT;
+			quarter.size_class = SizeClass::InputRelative;
+			quarter.size_relative_name = chain_input;
+			quarter.size_x = 0.25f;
+			quarter.size_y = 0.25f;
+			auto &off = graph.add_pass("bloom-disabled", RENDER_GRAPH_QUEUE_COMPUTE_BIT);
+			off.add_storage_texture_output("upsample-0", quarter);
+			off.add_texture_input(chain_input);
+			off.set_build_render_pass([](Vulkan::CommandBuffer &) {});
+			AttachmentInfo tonemap_info;
+			tonemap_info.size_class = SizeClass::InputRelative;
+			tonemap_info.size_relative_name = chain_input;
+			auto &tonemap = graph.add_pass("tonemap", RenderGraph::get_default_post_graphics_queue());
+			auto &out = tonemap.add_color_output("tonemapped", tonemap_info);
+			auto &hdr_res = tonemap.add_texture_input(chain_input);
+			auto &bloom_res = tonemap.add_texture_input("upsample-0");
+			tonemap.set_build_render_pass([this, &out, &hdr_res, &bloom_res](Vulkan::CommandBuffer &cmd) {
+				GrbImage hdr = graph.get_physical_texture_resource(hdr_res).as_grb();
+				GrbImage bloom = graph.get_physical_texture_resource(bloom_res).as_grb();
+				auto &ov = graph.get_physical_texture_resource(out);
+				GrbImage o = ov.as_grb();
+				cmd.check(grb_tonemap(&hdr, &bloom, nullptr, exposure.get_exposure(), &o, graph.is_sharded() ? graph.get_shard_plan().tonemap : GrbRows{ 0, 0 },
+				                      cmd.get_stream_handle()),
+				          "grb_tonemap");
+			});
+		}
+		ui_source = "tonemapped";
 
-	// ---- AA after the post chain (FXAA) ----
-	if (uses_fxaa())
-	{
-		setup_fxaa_postprocess(graph, ui_source, "post-aa-output");
-		ui_source = "post-aa-output";
+		// ---- AA after the post chain (FXAA) ----
+		if (uses_fxaa())
+		{
+			setup_fxaa_postprocess(graph, ui_source, "post-aa-output");
+			ui_source = "post-aa-output";
+		}
 	}
 	output_name = ui_source;
 	graph.set_backbuffer_source(ui_source);
@@ -337,6 +387,8 @@ extern "C" int32_t grbh_viewer_create(const GrbhViewerConfig *config, GrbhViewer
 {
 	if (!config || !out || config->width <= 0 || config->height <= 0)
 		return fail("grbh_viewer_create: bad config");
+	if (config->hdr10_output && (config->post_aa == GRBH_AA_FXAA || config->post_aa == GRBH_AA_TAA_HIGH_PLUS_FXAA))
+		return fail("grbh_viewer_create: FXAA reads the tonemapped 8-bit image; an HDR10 output has none (use TAA)");
 	GRBH_TRY
 	auto v = std::make_unique<GrbhViewer>();
 	v->config = *config;
@@ -434,6 +486,20 @@ extern "C" int32_t grbh_viewer_set_lights(GrbhViewer *v, const GrbhLights *l)
 	}
 	return 0;
 	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_rec709_to_display_primaries(const float *primaries_xy8, float *out16)
+{
+	if (!primaries_xy8 || !out16)
+		return fail("grbh_rec709_to_display_primaries: bad arguments");
+	VkHdrMetadataEXT md = {};
+	md.displayPrimaryRed = { primaries_xy8[0], primaries_xy8[1] };
+	md.displayPrimaryGreen = { primaries_xy8[2], primaries_xy8[3] };
+	md.displayPrimaryBlue = { primaries_xy8[4], primaries_xy8[5] };
+	md.whitePoint = { primaries_xy8[6], primaries_xy8[7] };
+	const muglm::mat4 m = Granite::compute_rec709_to_display_primaries(md);
+	std::memcpy(out16, m.data(), 64);
+	return GRB_OK;
 }
 
 extern "C" int32_t grbh_nccl_unique_id(uint8_t out128[128])

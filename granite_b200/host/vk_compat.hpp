@@ -40,6 +40,18 @@ union VkClearColorValue
 	uint32_t uint32[4];
 };
 
+// VK_EXT_hdr_metadata, the fields setup_hdr10_pq_encoding reads (renderer/post/hdr.cpp:563-593, 652).
+struct VkXYColorEXT
+{
+	float x, y;
+};
+
+struct VkHdrMetadataEXT
+{
+	VkXYColorEXT displayPrimaryRed, displayPrimaryGreen, displayPrimaryBlue, whitePoint;
+	float maxLuminance, minLuminance, maxContentLightLevel, maxFrameAverageLightLevel;
+};
+
 namespace Granite
 {
 inline unsigned format_texel_size(VkFormat format)

@@ -20,7 +20,8 @@ AA_NONE, AA_FXAA, AA_TAA_LOW, AA_TAA_MEDIUM, AA_TAA_HIGH, AA_TAA_HIGH_PLUS_FXAA 
 class GrbhViewerConfig(C.Structure):
     _fields_ = [("cuda_device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("post_aa", C.c_int32),
                 ("hdr_bloom", C.c_int32), ("dynamic_exposure", C.c_int32), ("cluster_res", C.c_int32 * 3),
-                ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p), ("pipelined_io", C.c_int32)]
+                ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p), ("pipelined_io", C.c_int32),
+                ("hdr10_output", C.c_int32), ("hdr10_max_content_light_level", C.c_float)]
 
 
 class GrbhLights(C.Structure):
@@ -227,7 +228,7 @@ def shard_plan(width, height, bands, rank, fxaa=False) -> dict:
 
 class Viewer:
     def __init__(self, width, height, post_aa=AA_NONE, hdr_bloom=True, dynamic_exposure=True, cuda_device=0,
-                 cluster_res=(128, 64, 4096), timestamps=False, stream=None, pipelined_io=False):
+                 cluster_res=(128, 64, 4096), timestamps=False, stream=None, pipelined_io=False, hdr10_output=False, hdr10_max_cll=1000.0):
         cfg = GrbhViewerConfig()
         cfg.cuda_device = cuda_device
         cfg.width, cfg.height = width, height
@@ -238,6 +239,8 @@ class Viewer:
         cfg.timestamps = int(timestamps)  # 1: aggregate per-pass times, 2: keep the raw timeline
         cfg.cuda_stream = stream
         cfg.pipelined_io = int(pipelined_io)
+        cfg.hdr10_output = int(hdr10_output)
+        cfg.hdr10_max_content_light_level = float(hdr10_max_cll)
         self.width, self.height = width, height
         self._h = C.c_void_p()
         _check(lib().grbh_viewer_create(C.byref(cfg), C.byref(self._h)), "grbh_viewer_create")
@@ -419,6 +422,14 @@ class Viewer:
         n = _check(lib().grbh_viewer_collect_timeline(self._h, names, 64 * capacity, b, e, capacity), "grbh_viewer_collect_timeline")
         nm = [x for x in names.value.decode().split("\n") if x]
         return [(nm[i], b[i], e[i]) for i in range(min(n, len(nm), capacity))]
+
+
+def rec709_to_display_primaries(primaries_xy8) -> np.ndarray:
+    """The "pq10" pass's primary_conversion (host/post/hdr.cpp, renderer/post/hdr.cpp:580-593) as a column-major 4x4."""
+    p = (C.c_float * 8)(*np.asarray(primaries_xy8, np.float32).reshape(-1).tolist())
+    out = (C.c_float * 16)()
+    _check(lib().grbh_rec709_to_display_primaries(p, out), "grbh_rec709_to_display_primaries")
+    return np.array(out, np.float32)
 
 
 def nccl_unique_id() -> bytes:

@@ -267,6 +267,12 @@ int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const float *lum
                     float dynamic_exposure, const GrbImage *out, GrbRows rows, void *stream);
 
 /* ---- post AA ---- */
+/* HDR10 output encoding: pq10_encode.frag, the "pq10" pass of setup_hdr10_pq_encoding (renderer/post/hdr.cpp:595-658).
+ * hdr: linear scene colour (B10G11R11); ui: R8G8B8A8_UNORM layer, alpha = share of the scene that shows through;
+ * primary_conversion16: column-major mat4 (upper 3x3 used) Rec.709 -> display primaries (hdr.cpp:580-593);
+ * out: A2B10G10R10_UNORM_PACK32 holding ST.2084 (PQ) code values, alpha = 1. */
+int32_t grb_pq10_encode(const GrbImage *hdr, const GrbImage *ui, const float *primary_conversion16, float hdr_pre_exposure,
+                        float ui_pre_exposure, float max_light_level, const GrbImage *out, GrbRows rows, void *stream);
 /* K12 fxaa.frag; renderer/post/fxaa.cpp:41-55. in: 8-bit image viewed as UNORM; if out's
  * format is *_SRGB the shader's FXAA_TARGET_SRGB path applies. */
 int32_t grb_fxaa(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream);

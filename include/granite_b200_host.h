@@ -47,6 +47,10 @@ typedef struct GrbhViewerConfig
 	int32_t pipelined_io;       /* 1: the G-buffer upload runs on a side stream into images that alternate
 	                             * per frame, so frame N+1's host->device copy overlaps frame N's compute
 	                             * (every frame must then bring its G-buffer: render_frame(NULL) is an error) */
+	int32_t hdr10_output;       /* 1: HDR10 swapchain (scene_viewer_application.cpp:1233-1288): no bloom / tonemap; the lit
+	                             * (and TAA-resolved) scene goes through a "ui" pass (cleared to 0,0,0,1: no widgets) and the
+	                             * "pq10" pass into an A2B10G10R10 image of ST.2084 codes, BT.2020 primaries, D65 */
+	float hdr10_max_content_light_level; /* VkHdrMetadataEXT::maxContentLightLevel in nits; <= 0: 1000 */
 } GrbhViewerConfig;
 
 /* Raw light list as the application owns it (before the clusterer sorts/packs it). */
@@ -84,6 +88,10 @@ int32_t grbh_viewer_set_camera(GrbhViewer *viewer, const float *projection16, co
 int32_t grbh_viewer_set_directional(GrbhViewer *viewer, const float *color3, const float *direction3);
 int32_t grbh_viewer_set_lights(GrbhViewer *viewer, const GrbhLights *lights);
 int32_t grbh_viewer_set_exposure(GrbhViewer *viewer, float exposure);
+
+/* Rec.709 -> display primaries, the matrix setup_hdr10_pq_encoding pushes (renderer/post/hdr.cpp:580-593, 651).
+ * primaries_xy8: red, green, blue, white chromaticities (VkHdrMetadataEXT order); out16: column-major mat4. */
+int32_t grbh_rec709_to_display_primaries(const float *primaries_xy8, float *out16);
 
 /* Row sharding (multi-GPU): bands[r] = backbuffer rows of rank r.  Must precede bake. */
 int32_t grbh_nccl_unique_id(uint8_t out128[128]);

@@ -148,6 +148,16 @@ void orc_taa_resolve(const uint32_t *hdr, const float *depth, const uint16_t *mv
                      int w, int h, const float *reproj16, int quality,
                      uint32_t *out_color, uint16_t *out_history, int y0, int y1);
 
+/* K14 pq10_encode.frag:20-52 + hdr.cpp:595-658 (setup_hdr10_pq_encoding): HDR10 / ST.2084 output encoding.
+ * hdr: B10G11R11 linear scene colour; ui: R8G8B8A8_UNORM (alpha = how much of the scene shows through);
+ * primary16: column-major mat4 whose upper 3x3 converts Rec.709 to the display's primaries;
+ * out: A2B10G10R10_UNORM_PACK32 (alpha = 1). */
+void orc_pq10_encode(const uint32_t *hdr, const uint32_t *ui, int w, int h, const float *primary16, float hdr_pre_exposure,
+                     float ui_pre_exposure, float max_light_level, uint32_t *out, int y0, int y1);
+/* hdr.cpp:580-593 compute_rec709_to_st2020 (math/transforms.cpp:352-370 compute_xyz_matrix): primaries8 =
+ * display red.xy, green.xy, blue.xy, white.xy (VkHdrMetadataEXT); out9 = column-major mat3. */
+void orc_rec709_to_display_primaries(const float *primaries8, float *out9);
+
 /* ---- format helpers exported for tests ---- */
 uint32_t orc_pack_r11g11b10(float r, float g, float b);
 void orc_unpack_r11g11b10(uint32_t p, float *rgb);

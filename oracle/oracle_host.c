@@ -520,3 +520,52 @@ int orc_light_visible(const float *planes24, int is_point, const float *color3, 
 	orc_transform_aabb(rows12, lo, hi, wlo, whi);
 	return orc_frustum_cull(wlo, whi, planes24);
 }
+
+/* ---- HDR10 output: Rec.709 -> display primaries (hdr.cpp:580-593, math/transforms.cpp:352-370) ----
+ * Evaluated in double precision and rounded once: the matrix is a per-swapchain constant, and the
+ * reference's fp32 chain (two 3x3 inverses) agrees with it to a few ulps (tests/test_oracle_cpu.py). */
+static void xyz_matrix_d(const float *p8, double m[9])
+{
+	double prim[4][3];
+	for (int i = 0; i < 4; i++)
+	{
+		double x = p8[2 * i], y = p8[2 * i + 1];
+		prim[i][0] = x / y; /* convert_primary */
+		prim[i][1] = 1.0;
+		prim[i][2] = (1.0 - x - y) / y;
+	}
+	/* component_scale = inverse([r g b]) * white  (Cramer) */
+	const double *r = prim[0], *g = prim[1], *b = prim[2], *wt = prim[3];
+	double det = r[0] * (g[1] * b[2] - b[1] * g[2]) - g[0] * (r[1] * b[2] - b[1] * r[2]) + b[0] * (r[1] * g[2] - g[1] * r[2]);
+	double sx = (wt[0] * (g[1] * b[2] - b[1] * g[2]) - g[0] * (wt[1] * b[2] - b[1] * wt[2]) + b[0] * (wt[1] * g[2] - g[1] * wt[2])) / det;
+	double sy = (r[0] * (wt[1] * b[2] - b[1] * wt[2]) - wt[0] * (r[1] * b[2] - b[1] * r[2]) + b[0] * (r[1] * wt[2] - wt[1] * r[2])) / det;
+	double sz = (r[0] * (g[1] * wt[2] - wt[1] * g[2]) - g[0] * (r[1] * wt[2] - wt[1] * r[2]) + wt[0] * (r[1] * g[2] - g[1] * r[2])) / det;
+	for (int i = 0; i < 3; i++)
+	{
+		m[0 + i] = r[i] * sx; /* column 0 */
+		m[3 + i] = g[i] * sy;
+		m[6 + i] = b[i] * sz;
+	}
+}
+
+static void inverse3_d(const double a[9], double o[9])
+{
+	/* column-major a[c*3+r] */
+	double c00 = a[4] * a[8] - a[7] * a[5], c01 = a[7] * a[2] - a[1] * a[8], c02 = a[1] * a[5] - a[4] * a[2];
+	double det = a[0] * c00 + a[3] * c01 + a[6] * c02;
+	o[0] = c00 / det; o[1] = c01 / det; o[2] = c02 / det;
+	o[3] = (a[6] * a[5] - a[3] * a[8]) / det; o[4] = (a[0] * a[8] - a[6] * a[2]) / det; o[5] = (a[3] * a[2] - a[0] * a[5]) / det;
+	o[6] = (a[3] * a[7] - a[6] * a[4]) / det; o[7] = (a[6] * a[1] - a[0] * a[7]) / det; o[8] = (a[0] * a[4] - a[3] * a[1]) / det;
+}
+
+void orc_rec709_to_display_primaries(const float *primaries8, float *out9)
+{
+	static const float rec709[8] = { 0.640f, 0.330f, 0.3f, 0.6f, 0.150f, 0.060f, 0.3127f, 0.3290f }; /* hdr.cpp:585-589 */
+	double src[9], dst[9], inv[9];
+	xyz_matrix_d(rec709, src);
+	xyz_matrix_d(primaries8, dst);
+	inverse3_d(dst, inv);
+	for (int c = 0; c < 3; c++)
+		for (int r = 0; r < 3; r++)
+			out9[c * 3 + r] = (float)(inv[0 * 3 + r] * src[c * 3 + 0] + inv[1 * 3 + r] * src[c * 3 + 1] + inv[2 * 3 + r] * src[c * 3 + 2]);
+}

@@ -524,3 +524,52 @@ void orc_taa_resolve(const uint32_t *hdr, const float *depth, const uint16_t *mv
 		}
 	}
 }
+
+/* ---- K14: pq10_encode.frag ---- */
+static float pq_channel(float nits)
+{
+	/* encode_pq (pq10_encode.frag:20-32); the constants are exact binary fractions */
+	const float c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f, m1 = 0.1593017578125f, m2 = 78.84375f;
+	float y = nits / 10000.0f;
+	float p = powf(y, m1);
+	float num = c1 + c2 * p;
+	float den = 1.0f + c3 * p;
+	return powf(num / den, m2);
+}
+
+static uint32_t unorm10(float c)
+{
+	if (!(c > 0.0f)) c = 0.0f; /* also NaN (pow of a negative colour after the primaries conversion) */
+	if (c > 1.0f) c = 1.0f;
+	return (uint32_t)floorf(c * 1023.0f + 0.5f);
+}
+
+void orc_pq10_encode(const uint32_t *hdr, const uint32_t *ui, int w, int h, const float *m, float hdr_pre_exposure,
+                     float ui_pre_exposure, float max_light_level, uint32_t *out, int y0, int y1)
+{
+	const float inv_max = 1.0f / max_light_level; /* hdr.cpp:637 */
+	(void)h;
+#pragma omp parallel for
+	for (int y = y0; y < y1; y++)
+		for (int x = 0; x < w; x++)
+		{
+			size_t i = (size_t)y * w + x;
+			vec3 c = unpack_r11g11b10(hdr[i]);
+			uint32_t u = ui[i];
+			float ur = (float)(u & 0xffu) / 255.0f, ug = (float)((u >> 8) & 0xffu) / 255.0f, ub = (float)((u >> 16) & 0xffu) / 255.0f, ua = (float)(u >> 24) / 255.0f;
+			float s = hdr_pre_exposure * ua;
+			vec3 col = v3(c.x * s + ur * ui_pre_exposure, c.y * s + ug * ui_pre_exposure, c.z * s + ub * ui_pre_exposure);
+			/* mat3(primary_conversion) * col: columns summed left to right */
+			col = v3(m[0] * col.x + m[4] * col.y + m[8] * col.z, m[1] * col.x + m[5] * col.y + m[9] * col.z, m[2] * col.x + m[6] * col.y + m[10] * col.z);
+			col = v3(col.x * inv_max, col.y * inv_max, col.z * inv_max);
+			float k[3] = { col.x, col.y, col.z };
+			for (int j = 0; j < 3; j++)
+			{
+				float ck = k[j] * 4.0f;
+				float saturated = ck / (1.0f + ck);
+				k[j] = k[j] > 0.75f ? saturated : k[j]; /* mix(col, saturated, greaterThan(col, 0.75)) */
+				k[j] = pq_channel(k[j] * max_light_level);
+			}
+			out[i] = unorm10(k[0]) | (unorm10(k[1]) << 10) | (unorm10(k[2]) << 20) | (3u << 30);
+		}
+}

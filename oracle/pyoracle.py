@@ -19,7 +19,7 @@ _REF_PATH = os.path.join(_HERE, "_ref", "libgranite_refmath.so")
 
 _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for k in (1, 2, 3, 4)]
 # post-processing shaders K7-K13 (ref_post_shim.cpp); ids as in oracle/Makefile POST_IDS
-_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43)
+_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
 # deferred-lighting fragment shaders K5 (clustering.frag) and K6 (directional.frag), ref_light_shim.cpp
 _REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6)}
@@ -511,6 +511,48 @@ def ref_taa_resolve(hdr, depth, mv, history, reproj, quality=2, rows=None):
     fn(_p(_c(hdr, np.uint32)), _p(_c(depth, np.float32)), _p(_c(mv, np.uint16)), None if history is None else _p(_c(history, np.uint16)), w, h,
        _p(_c(reproj, np.float32)), _p(out_c), _p(out_h), y0, y1)
     return out_c, out_h
+
+
+# BT.2020 primaries + D65, the HDR10 swapchain metadata the tests use
+BT2020_PRIMARIES = (0.708, 0.292, 0.170, 0.797, 0.131, 0.046, 0.3127, 0.3290)
+
+
+def rec709_to_display_primaries(primaries8=BT2020_PRIMARIES):
+    """hdr.cpp:580-593 as a column-major mat4 (upper 3x3 filled), ready for pq10_encode."""
+    out = np.zeros(9, np.float32)
+    lib().orc_rec709_to_display_primaries(_p(_farr(primaries8)), _p(out))
+    m = np.zeros((4, 4), np.float32)
+    m[:3, :3] = out.reshape(3, 3)  # rows of `m` are COLUMNS (column-major storage)
+    m[3, 3] = 1.0
+    return m.reshape(-1)
+
+
+def ref_rec709_to_display_primaries(primaries8=BT2020_PRIMARIES):
+    """The same matrix from the reference's own fp32 chain (oracle/ref_shim.cpp), as a column-major mat4."""
+    out = np.zeros(9, np.float32)
+    ref().ref_rec709_to_display_primaries(_p(_farr(primaries8)), _p(out))
+    m = np.zeros((4, 4), np.float32)
+    m[:3, :3] = out.reshape(3, 3)
+    m[3, 3] = 1.0
+    return m.reshape(-1)
+
+
+def pq10_encode(hdr, ui, primary16, hdr_pre=500.0, ui_pre=400.0, max_light=1000.0, rows=None):
+    h, w = hdr.shape
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    lib().orc_pq10_encode(_p(_c(hdr, np.uint32)), _p(_c(ui, np.uint32)), w, h, _p(_c(primary16, np.float32)), _f(hdr_pre), _f(ui_pre), _f(max_light),
+                          _p(out), y0, y1)
+    return out
+
+
+def ref_pq10_encode(hdr, ui, primary16, hdr_pre=500.0, ui_pre=400.0, max_light=1000.0, rows=None):
+    h, w = hdr.shape
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    ref_post_kernels()[14].refk14_pq10_encode(_p(_c(hdr, np.uint32)), _p(_c(ui, np.uint32)), w, h, _p(_c(primary16, np.float32)), _f(hdr_pre), _f(ui_pre),
+                                              _f(max_light), _p(out), y0, y1)
+    return out
 
 
 def pyramid_sizes(w, h):

@@ -17,6 +17,7 @@
 //   KERNEL=12  post/fxaa.frag (FXAA_TARGET_SRGB=0/1 -> KERNEL 12 / 22) -> refk12_fxaa
 //   KERNEL=13  post/taa_resolve.frag (TAA_QUALITY=2, REPROJECTION_HISTORY=1; 23: quality 0, 33: quality 1,
 //              43: no history)                                   -> refk13_taa_resolve
+//   KERNEL=14  post/pq10_encode.frag (HDR10 / ST.2084 output encoding) -> refk14_pq10_encode
 //
 // What the shim supplies -- and the reference leaves to the Vulkan implementation -- is exactly
 // the list DESIGN.md section 2 fixes once for oracle and product alike:
@@ -178,6 +179,7 @@ inline glm::vec4 textureGatherOffset(const sampler2D &s, const glm::vec2 &uv, co
 }
 inline glm::vec4 textureGather(const sampler2D &s, const glm::vec2 &uv, int comp = 0) { return textureGatherOffset(s, uv, glm::ivec2(0), comp); }
 inline glm::ivec2 textureSize(const sampler2D &s, int) { return glm::ivec2(s.w, s.h); }
+typedef sampler2D texture2D; // separate images are only ever texelFetch'ed
 
 // rgba16f storage image
 struct image2D
@@ -217,6 +219,7 @@ inline float mix(const float &x, const float &y, const bool &a) { return a ? y :
 struct ShimMat4
 {
 	glm::vec4 c[4];
+	const glm::vec4 &operator[](int i) const { return c[i]; }
 };
 inline glm::vec4 operator*(const ShimMat4 &m, const glm::vec4 &v) { return ((m.c[0] * v.x + m.c[1] * v.y) + m.c[2] * v.z) + m.c[3] * v.w; }
 #define mat4 ShimMat4
@@ -485,6 +488,35 @@ refk13_taa_nohistory
 		out_history[4 * i + 1] = orc_f32_to_f16(hist.y);
 		out_history[4 * i + 2] = orc_f32_to_f16(hist.z);
 		out_history[4 * i + 3] = orc_f32_to_f16(1.0f); // a vec3 output to an RGBA16F attachment: alpha = 1
+	});
+}
+#elif KERNEL == 14
+// hdr.cpp:619-642: texelFetch of the scene colour and the UI layer, Config UBO at (1, 0); the attachment is
+// A2B10G10R10_UNORM (HDR10 swapchain): round to nearest, NaN -> 0
+void refk14_pq10_encode(const uint32_t *hdr, const uint32_t *ui, int w, int h, const float *primary16, float hdr_pre_exposure, float ui_pre_exposure,
+                        float max_light_level, uint32_t *out, int y0, int y1)
+{
+	sampler2D s_hdr = make_sampler(hdr, w, h, spirv_cross::FMT_R11G11B10, false);
+	sampler2D s_ui = make_sampler(ui, w, h, spirv_cross::FMT_RGBA8_UNORM, false);
+	Sh::Resources::Config cfg;
+	std::memcpy(&cfg.primary_conversion, primary16, 64);
+	cfg.hdr_pre_exposure = hdr_pre_exposure;
+	cfg.ui_pre_exposure = ui_pre_exposure;
+	cfg.max_light_level = max_light_level;
+	cfg.inv_max_light_level = 1.0f / max_light_level; // hdr.cpp:637
+	glm::vec4 color(0.0f);
+	Runner r;
+	r.resource(0, 0, &s_hdr);
+	r.resource(0, 1, &s_ui);
+	r.resource(1, 0, &cfg);
+	spirv_cross_set_stage_output(r.sh, 0, &color, sizeof(color));
+	r.raster(w, h, y0, y1, nullptr, [&](int x, int y) {
+		auto q = [](float c) -> uint32_t {
+			if (!(c > 0.0f)) c = 0.0f;
+			if (c > 1.0f) c = 1.0f;
+			return (uint32_t)std::floor(c * 1023.0f + 0.5f);
+		};
+		out[(size_t)y * w + x] = q(color.x) | (q(color.y) << 10) | (q(color.z) << 20) | (3u << 30);
 	});
 }
 #endif

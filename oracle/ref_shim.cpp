@@ -87,4 +87,17 @@ int ref_frustum_cull(const float *lo3, const float *hi3, const float *planes24)
 	memcpy(planes, planes24, sizeof(planes));
 	return Granite::SIMD::frustum_cull(box, planes) ? 1 : 0;
 }
+
+// renderer/post/hdr.cpp:580-593 compute_rec709_to_st2020, with the reference's compute_xyz_matrix
+// (math/transforms.cpp:352-370) and muglm's mat3 inverse / product: column-major mat3 out.
+void ref_rec709_to_display_primaries(const float *primaries8, float *out9)
+{
+	Granite::Primaries rec709 = { vec2(0.640f, 0.330f), vec2(0.3f, 0.6f), vec2(0.150f, 0.060f), vec2(0.3127f, 0.3290f) };
+	Granite::Primaries disp = { vec2(primaries8[0], primaries8[1]), vec2(primaries8[2], primaries8[3]), vec2(primaries8[4], primaries8[5]),
+	                            vec2(primaries8[6], primaries8[7]) };
+	const mat3 srgb_to_xyz = Granite::compute_xyz_matrix(rec709);
+	const mat3 xyz_to_display = inverse(Granite::compute_xyz_matrix(disp));
+	const mat3 m = xyz_to_display * srgb_to_xyz;
+	memcpy(out9, &m, 36);
+}
 }

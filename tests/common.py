@@ -81,6 +81,14 @@ def rgba8_channel_diff(a, b):
     return np.abs(a - b)
 
 
+def a2b10g10r10_channel_diff(a, b):
+    """|difference| of the three 10-bit channels and of the 2-bit alpha, as one (..., 4) array."""
+    a = np.ascontiguousarray(a).astype(np.uint32)
+    b = np.ascontiguousarray(b).astype(np.uint32)
+    ch = lambda v: np.stack([v & 1023, (v >> 10) & 1023, (v >> 20) & 1023, v >> 30], -1).astype(np.int32)
+    return np.abs(ch(a) - ch(b))
+
+
 def random_hdr(rng, w, h, scale=4.0, hot=0.002):
     """Random B10G11R11 image with a few very bright texels (drives bloom)."""
     rgb = (rng.random((h, w, 3)) ** 3 * scale).astype(np.float32)

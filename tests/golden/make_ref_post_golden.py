@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/refpost_*.npz: outputs of the REFERENCE's own post-processing shaders
-(K7 threshold, K8 downsample +FEEDBACK, K9 upsample, K10 luminance, K11 tonemap, K12 FXAA, K13 TAA),
+(K7 threshold, K8 downsample +FEEDBACK, K9 upsample, K10 luminance, K11 tonemap, K12 FXAA, K13 TAA, HDR10 PQ encode),
 executed on the CPU through the reference's vendored glslang + spirv-cross (`make -C oracle
 ref-shaders`, oracle/ref_post_shim.cpp).  Needs /root/reference; the fixtures let machines without it
 (the GPU box) check the oracle -- and through it the CUDA kernels -- against reference-derived vectors.
@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import pyoracle as oracle  # noqa: E402
 from tests import common  # noqa: E402
-from tests.test_oracle_ref_post_shaders import impls, run_chain, taa_inputs  # noqa: E402
+from tests.test_oracle_ref_post_shaders import impls, pq_inputs, run_chain, taa_inputs  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -51,6 +51,15 @@ def main():
         aa[f"taa_q{q}_color"], aa[f"taa_q{q}_history"] = oracle.ref_taa_resolve(hdr, depth, mv, hist, reproj, q)
     aa["taa_first_color"], aa["taa_first_history"] = oracle.ref_taa_resolve(hdr, depth, mv, None, reproj, 2)
     np.savez_compressed(os.path.join(HERE, "refpost_aa_128x80.npz"), **aa)
+
+    # HDR10 output encoding (pq10_encode.frag) with the matrix the reference's own math computes for BT.2020 primaries
+    w, h = 96, 64
+    rng = np.random.default_rng(2084)
+    hdr, ui = pq_inputs(rng, w, h)
+    m = oracle.ref_rec709_to_display_primaries(oracle.BT2020_PRIMARIES)
+    pq = {"hdr": hdr, "ui": ui, "primaries": np.asarray(oracle.BT2020_PRIMARIES, np.float32), "primary_conversion": m,
+          "pq10": oracle.ref_pq10_encode(hdr, ui, m, 500.0, 400.0, 1000.0)}
+    np.savez_compressed(os.path.join(HERE, "refpost_pq10_96x64.npz"), **pq)
     print("written")
 
 

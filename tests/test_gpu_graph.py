@@ -71,6 +71,36 @@ def test_config1_single_tonemap_pass(cuda, oracle):
     v.close()
 
 
+@pytest.mark.parametrize("aa", ["none", "taa"])
+def test_hdr10_output_frames(cuda, oracle, aa):
+    """HDR10 swapchain (scene_viewer_application.cpp:1233-1288): lighting (+ TAA) -> "ui" -> "pq10", no bloom / tonemap.
+    The encoder is checked on the HDR image the device itself produced (that image has its own tests)."""
+    from granite_b200 import viewer
+
+    w, h = 640, 360
+    scene, lights = synth.make_scene(w, h), synth.make_lights(200, aspect=w / h)
+    v = _make_viewer(scene, lights, post_aa=viewer.AA_TAA_HIGH if aa == "taa" else viewer.AA_NONE, hdr10_output=True, hdr10_max_cll=1000.0)
+    names = v.pass_names()
+    assert names[-2:] == ["ui", "pq10"] and "tonemap" not in names and "bloom-compute" not in names
+    m = oracle.rec709_to_display_primaries(oracle.BT2020_PRIMARIES)
+    assert common.f32_ulp_diff(viewer.rec709_to_display_primaries(oracle.BT2020_PRIMARIES).reshape(4, 4)[:3, :3].reshape(-1),
+                               np.asarray(m, np.float32).reshape(4, 4)[:3, :3].reshape(-1)).max() <= 2
+    mv = np.zeros((h, w), np.uint32) if aa == "taa" else None
+    gb, keep = _host_gb(scene, mv)
+    for frame in range(3):
+        v.render_frame(gb)
+        out = np.zeros((h, w), np.uint32)
+        assert v.read_output(out) == (0, h)
+        src = v.download_image("HDR-resolved" if aa == "taa" else "HDR-main")
+        ui = v.download_image("ui-temporary")
+        assert np.all(ui == 0xFF000000)
+        ref = oracle.pq10_encode(src, ui, viewer.rec709_to_display_primaries(oracle.BT2020_PRIMARIES), 500.0, 400.0, 1000.0)
+        d = common.a2b10g10r10_channel_diff(out, ref)
+        assert d.max() <= 1 and (d == 0).mean() > 0.99, f"frame {frame}"
+        assert (out >> 30).min() == 3
+    v.close()
+
+
 @pytest.mark.parametrize("w,h,n,spots", [(640, 360, 300, 0.25), (1920, 1080, 1024, 0.0), (3840, 2160, 4096, 0.0)])
 def test_full_chain_frames(cuda, oracle, w, h, n, spots):
     scene, lights = synth.make_scene(w, h), synth.make_lights(n, spot_fraction=spots, aspect=w / h)

@@ -396,6 +396,28 @@ def test_fxaa(cuda, oracle, w, h, srgb):
     assert (d == 0).mean() > 0.995  # rounding ties at x.5 of the folded sRGB round trip on this blocky image
 
 
+@pytest.mark.parametrize("w,h,rows", [(96, 64, None), (333, 177, (10, 150)), (1921, 1080, None), (3840, 2160, None)])
+def test_pq10_encode(cuda, oracle, w, h, rows):
+    """HDR10 output encoding (pq10_encode.frag, hdr.cpp:595-658) vs the oracle, whose codes equal the reference
+    shader's bit for bit (tests/test_oracle_ref_post_shaders.py).  Odd widths take the unaligned load / store path."""
+    from granite_b200 import harness
+    from tests.test_oracle_ref_post_shaders import pq_inputs
+
+    rng = np.random.default_rng(w + 7 * h)
+    hdr, ui = pq_inputs(rng, w, h)
+    m = oracle.rec709_to_display_primaries(oracle.BT2020_PRIMARIES)
+    for max_light in (1000.0, 4000.0):
+        ref = oracle.pq10_encode(hdr, ui, m, 500.0, 400.0, max_light, rows=rows)
+        out = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+        harness.pq10_encode(harness.to_dev(hdr), harness.to_dev(ui), m, 500.0, 400.0, max_light, out, rows=rows)
+        got = harness.to_host(out, np.uint32)
+        d = common.a2b10g10r10_channel_diff(got, ref)
+        print(f"pq10 {w}x{h} max_light {max_light}: identical {float((d == 0).mean()):.6f}, max code diff {int(d.max())}")
+        assert d.max() <= 1 and (d == 0).mean() > 0.99
+        if rows:  # nothing outside the band is written
+            assert not got[: rows[0]].any() and not got[rows[1]:].any()
+
+
 def _taa_inputs(rng, w, h):
     hdr = common.random_hdr(rng, w, h, scale=2.0)
     depth = rng.uniform(0.0005, 0.03, size=(h, w)).astype(np.float32)

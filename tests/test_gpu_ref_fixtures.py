@@ -79,6 +79,21 @@ def test_cuda_aa_vs_reference_shader_fixture(cuda):
     assert np.array_equal(harness.to_host(oc, np.uint32), g["taa_first_color"]) and np.array_equal(harness.to_host(oh, np.uint16), g["taa_first_history"])
 
 
+def test_cuda_pq10_vs_reference_shader_fixture(cuda):
+    """pq10_encode.frag: the kernel evaluates the two pow() per channel with lg2 / ex2, so a code may round the other
+    way at an exact .5 of the 10-bit scale: 1 code, rarely."""
+    import torch
+
+    from granite_b200 import harness
+
+    p = np.load(os.path.join(GOLDEN, "refpost_pq10_96x64.npz"))
+    h, w = p["hdr"].shape
+    out = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    harness.pq10_encode(harness.to_dev(p["hdr"]), harness.to_dev(p["ui"]), p["primary_conversion"], 500.0, 400.0, 1000.0, out)
+    d = common.a2b10g10r10_channel_diff(harness.to_host(out, np.uint32), p["pq10"])
+    assert d.max() <= 1 and (d == 0).mean() > 0.99
+
+
 def test_cuda_lighting_vs_reference_shader_fixture(cuda, oracle):
     """HDR-main lit by the CUDA kernel vs the image the reference's directional.frag + clustering.frag
     produce for the same seeded scene (the cluster structure is built on the GPU too)."""
