@@ -38,6 +38,11 @@ class GrbRows(C.Structure):
     _fields_ = [("y0", C.c_int32), ("y1", C.c_int32)]
 
 
+class GrbBloomTailOptions(C.Structure):
+    _fields_ = [("u0", C.c_void_p), ("u0_rows", GrbRows), ("peer_flags", C.c_void_p), ("peer_count", C.c_int32), ("peer_epoch", C.c_uint32),
+                ("max_ctas", C.c_int32)]
+
+
 class GrbPositionalLight(C.Structure):
     _fields_ = [("color", C.c_float * 3), ("spot_scale_bias", C.c_uint16 * 2),
                 ("position", C.c_float * 3), ("offset_radius", C.c_uint16 * 2),
@@ -76,10 +81,10 @@ class GrbGBuffer(C.Structure):
 
 ENTRY_POINTS = [
     "grb_abi_version", "grb_init", "grb_last_error_string",
-    "grb_cluster_spot_transform", "grb_cluster_cull_setup", "grb_cluster_binning", "grb_cluster_z_range",
+    "grb_cluster_spot_transform", "grb_cluster_cull_setup", "grb_cluster_binning", "grb_cluster_binning_rows", "grb_cluster_z_range",
     "grb_cluster_build", "grb_deferred_lighting", "grb_deferred_lighting_blocks", "grb_deferred_lighting_scheduled", "grb_lighting_schedule_bytes", "grb_debug_cluster_indices", "grb_lighting_row_cost",
-    "grb_bloom_threshold", "grb_bloom_threshold_downsample", "grb_bloom_threshold_downsample_to_peers", "grb_bloom_downsample", "grb_bloom_downsample_to_peers", "grb_peer_wait", "grb_bloom_upsample",
-    "grb_luminance", "grb_luminance_grid", "grb_luminance_finalize", "grb_bloom_tail", "grb_tonemap",
+    "grb_bloom_threshold", "grb_bloom_threshold_downsample", "grb_bloom_threshold_downsample_to_peers", "grb_bloom_downsample", "grb_bloom_downsample_to_peers", "grb_peer_wait", "grb_bloom_upsample", "grb_bloom_upsample_exact",
+    "grb_luminance", "grb_luminance_grid", "grb_luminance_finalize", "grb_bloom_tail", "grb_bloom_tail_ex", "grb_tonemap",
     "grb_pq10_encode", "grb_fxaa", "grb_taa_resolve",
 ]
 
@@ -106,6 +111,7 @@ def lib() -> C.CDLL:
             "grb_cluster_spot_transform": [C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters), C.POINTER(GrbClusterBuffers), P],
             "grb_cluster_cull_setup": [C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters), C.POINTER(GrbClusterBuffers), P],
             "grb_cluster_binning": [C.POINTER(GrbClusterParameters), C.POINTER(GrbClusterBuffers), P],
+            "grb_cluster_binning_rows": [C.POINTER(GrbClusterParameters), C.POINTER(GrbClusterBuffers), I, I, P],
             "grb_cluster_z_range": [C.POINTER(GrbClusterBuffers), I, P],
             "grb_cluster_build": [C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters), C.POINTER(GrbClusterBuffers), P],
             "grb_deferred_lighting": [C.POINTER(GrbGBuffer), C.POINTER(GrbCamera), C.POINTER(GrbClusterParameters),
@@ -120,10 +126,12 @@ def lib() -> C.CDLL:
             "grb_bloom_threshold_downsample": [IMG, P, IMG, IMG, GrbRows, P],
             "grb_bloom_downsample": [IMG, IMG, F, IMG, GrbRows, P],
             "grb_bloom_upsample": [IMG, IMG, GrbRows, P],
+            "grb_bloom_upsample_exact": [IMG, IMG, GrbRows, P],
             "grb_luminance": [IMG, P, F, F, F, P],
             "grb_luminance_grid": [IMG, P, GrbRows, P],
             "grb_luminance_finalize": [P, I, I, P, F, F, F, P],
             "grb_bloom_tail": [IMG, IMG, IMG, IMG, IMG, F, P, F, F, F, IMG, IMG, P],
+            "grb_bloom_tail_ex": [IMG, IMG, IMG, IMG, IMG, F, P, F, F, F, IMG, IMG, P, P],
             "grb_tonemap": [IMG, IMG, P, F, IMG, GrbRows, P],
             "grb_pq10_encode": [IMG, IMG, P, F, F, F, IMG, GrbRows, P],
             "grb_fxaa": [IMG, IMG, GrbRows, P],

@@ -287,6 +287,7 @@ struct BinParams
 	float2 clip_scale_zw;
 	int res_x, res_y;
 	int num_lights, num_lights_32;
+	int first_block_y; // first row of 8x4-tile blocks this launch covers
 };
 
 __device__ __forceinline__ bool test_point_light(const BinParams &p, float2 uv, float2 stride, const float4 *__restrict__ d)
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(32 * kBinWarps) binning_kernel(BinParams p, co
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const int chunk = blockIdx.x * kBinWarps + warp;
-	const int bx = blockIdx.y, by = blockIdx.z;
+	const int bx = blockIdx.y, by = p.first_block_y + blockIdx.z;
 	if (chunk >= p.num_lights_32)
 		return;
 
@@ -545,7 +546,7 @@ extern "C" int32_t grb_cluster_cull_setup(const GrbCamera *cam, const GrbCluster
 	return check_launch("grb_cluster_cull_setup");
 }
 
-extern "C" int32_t grb_cluster_binning(const GrbClusterParameters *params, const GrbClusterBuffers *buf, void *stream)
+extern "C" int32_t grb_cluster_binning_rows(const GrbClusterParameters *params, const GrbClusterBuffers *buf, int32_t tile_y0, int32_t tile_y1, void *stream)
 {
 	if (!args_ok(params, buf, "grb_cluster_binning: bad parameters (resolution must be a multiple of 8x4)"))
 		return GRB_ERR_INVALID_ARGUMENT;
@@ -563,9 +564,24 @@ extern "C" int32_t grb_cluster_binning(const GrbClusterParameters *params, const
 	p.res_y = params->resolution_xy[1];
 	p.num_lights = params->num_lights;
 	p.num_lights_32 = params->num_lights_32;
-	dim3 grid((p.num_lights_32 + kBinWarps - 1) / kBinWarps, p.res_x / 8, p.res_y / 4);
+	// whole blocks of 4 tile rows; an empty or inverted range means every row
+	if (tile_y1 <= tile_y0)
+	{
+		tile_y0 = 0;
+		tile_y1 = p.res_y;
+	}
+	const int by0 = max(tile_y0, 0) / 4, by1 = (min(tile_y1, p.res_y) + 3) / 4;
+	if (by1 <= by0)
+		return GRB_OK;
+	p.first_block_y = by0;
+	dim3 grid((p.num_lights_32 + kBinWarps - 1) / kBinWarps, p.res_x / 8, by1 - by0);
 	binning_kernel<<<grid, 32 * kBinWarps, 0, as_stream(stream)>>>(p, buf->type_mask, reinterpret_cast<const float4 *>(buf->cull_setup), buf->bitmask);
 	return check_launch("grb_cluster_binning");
+}
+
+extern "C" int32_t grb_cluster_binning(const GrbClusterParameters *params, const GrbClusterBuffers *buf, void *stream)
+{
+	return grb_cluster_binning_rows(params, buf, 0, 0, stream);
 }
 
 extern "C" int32_t grb_cluster_z_range(const GrbClusterBuffers *buf, int32_t num_ranges, void *stream)

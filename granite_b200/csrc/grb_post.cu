@@ -780,18 +780,28 @@ struct TailArgs
 	float lerp_d3;
 	float *lum; // nullptr: no dynamic exposure
 	float lerp_lum, lo, hi;
+	// optional extras (grb_bloom_tail_ex)
+	View<uint2> u0; // p == nullptr: u0 is a separate dispatch
+	int u0_y0, u0_y1;
+	const uint32_t *wait_flags; // row-sharded frames: every rank's "d0 band of frame wait_epoch landed" flag
+	int wait_count;
+	uint32_t wait_epoch;
+	uint32_t *error_word;
+	unsigned max_spins;
 };
 
-constexpr int kTailThreads = 512; // two CTAs per SM: one thread per texel of the largest level at 4K
+constexpr int kTailThreads = 1024; // few, fat CTAs: the launch shares the machine with the next frame's lighting pass, one CTA per SM it touches
 
 __device__ __forceinline__ void tail_level(const View<const uint2> &src, const View<uint2> &dst, float off, const View<const uint2> *history, float lerp,
-                                          unsigned first_cta, unsigned num_ctas)
+                                          unsigned first_cta, unsigned num_ctas, int y0 = 0, int y1 = -1)
 {
 	const float inv_w = 1.0f / (float)dst.w, inv_h = 1.0f / (float)dst.h, inv_in_w = 1.0f / (float)src.w, inv_in_h = 1.0f / (float)src.h;
-	const int total = dst.w * dst.h;
+	if (y1 < 0)
+		y1 = dst.h;
+	const int total = dst.w * (y1 - y0);
 	for (int i = (int)((blockIdx.x - first_cta) * kTailThreads + threadIdx.x); i < total; i += (int)(num_ctas * kTailThreads))
 	{
-		const int y = i / dst.w, x = i - y * dst.w;
+		const int yr = i / dst.w, x = i - yr * dst.w, y = y0 + yr;
 		const float u = ((float)x + 0.5f) * inv_w, v = ((float)y + 0.5f) * inv_h;
 		float4 value = tent9_cg(src, u, v, off, inv_in_w, inv_in_h);
 		if (history)
@@ -810,6 +820,31 @@ __global__ void __launch_bounds__(kTailThreads) bloom_tail_kernel(const TailArgs
 	__shared__ float s_grid[kLumFastMaxSamples];
 	__shared__ float s_part[64];
 	auto as_src = [](const View<uint2> &v) { return View<const uint2>{ v.p, v.w, v.h, v.pitch }; };
+	if (a.wait_flags)
+	{
+		// Row-sharded frames: d0 is assembled from every rank's band (stores over NVLink peer memory, then a
+		// release-store of the frame's epoch into this rank's flag array).  Waiting HERE instead of in a kernel
+		// of its own lets the CTAs of this launch take their SM slots before the next frame's lighting pass
+		// fills the machine; they are few (max_ctas) and spin with nanosleep.  Bounded (~4 s): a rank that
+		// died must not hang the GPUs of the others.
+		if ((int)threadIdx.x < a.wait_count)
+			for (unsigned spins = 0; (int32_t)(load_acquire_system(a.wait_flags + threadIdx.x) - a.wait_epoch) < 0; spins++)
+			{
+				if (spins > a.max_spins)
+				{
+					if (blockIdx.x == 0)
+						printf("granite_b200: timed out waiting for rank %d's band of frame %u\n", (int)threadIdx.x, a.wait_epoch);
+					if (a.error_word) // picked up by the next grb_* call on this device (check_launch)
+					{
+						*reinterpret_cast<volatile uint32_t *>(a.error_word) = (GRB_DEVICE_ERROR_PEER_TIMEOUT << 24) | ((uint32_t)threadIdx.x << 16) | (a.wait_epoch & 0xffffu);
+						__threadfence_system();
+					}
+					break;
+				}
+				__nanosleep(128);
+			}
+		__syncthreads();
+	}
 	tail_level(a.d0, a.d1, 1.75f, nullptr, 0.0f, 0u, gridDim.x);
 	grid.sync();
 	tail_level(as_src(a.d1), a.d2, 1.75f, nullptr, 0.0f, 0u, gridDim.x);
@@ -849,6 +884,11 @@ __global__ void __launch_bounds__(kTailThreads) bloom_tail_kernel(const TailArgs
 		tail_level(as_src(a.d3), a.u2, 0.875f, nullptr, 0.0f, a.lum != nullptr && gridDim.x > 1 ? 1u : 0u, a.lum != nullptr && gridDim.x > 1 ? gridDim.x - 1u : gridDim.x);
 	grid.sync();
 	tail_level(as_src(a.u2), a.u1, 0.875f, nullptr, 0.0f, 0u, gridDim.x);
+	if (a.u0.p)
+	{
+		grid.sync();
+		tail_level(as_src(a.u1), a.u0, 0.875f, nullptr, 0.0f, 0u, gridDim.x, a.u0_y0, a.u0_y1);
+	}
 }
 } // namespace
 } // namespace grb
@@ -970,7 +1010,7 @@ extern "C" int32_t grb_peer_wait(const uint32_t *local_flags, int32_t count, uin
 	return check_launch("grb_peer_wait");
 }
 
-extern "C" int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream)
+static int32_t bloom_upsample_impl(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream, bool allow_tiles)
 {
 	if (!image_ok(in, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || !image_ok(out, GRB_FORMAT_R16G16B16A16_SFLOAT, 8))
 	{
@@ -980,6 +1020,7 @@ extern "C" int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, G
 	rows = full_rows(rows, out->height);
 	if (rows.y1 <= rows.y0)
 		return GRB_OK;
+	if (allow_tiles)
 	{
 		int32_t rc = GRB_OK;
 		if (launch_tent_tiled(true, in, nullptr, 0.0f, out, rows, as_stream(stream), &rc))
@@ -990,6 +1031,18 @@ extern "C" int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, G
 	                                                              1.0f / (float)out->width, 1.0f / (float)out->height, 1.0f / (float)in->width,
 	                                                              1.0f / (float)in->height);
 	return check_launch("grb_bloom_upsample");
+}
+
+extern "C" int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream)
+{
+	return bloom_upsample_impl(in, out, rows, stream, true);
+}
+
+// The shader's arithmetic, statement for statement, at every size (the form the fused tail uses for u0): what a
+// frame falls back to when the cooperative launch is not available, so that its texels do not depend on that.
+extern "C" int32_t grb_bloom_upsample_exact(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream)
+{
+	return bloom_upsample_impl(in, out, rows, stream, false);
 }
 
 extern "C" int32_t grb_luminance(const GrbImage *d3, float *luminance, float lerp, float min_loglum, float max_loglum, void *stream)
@@ -1176,10 +1229,35 @@ extern "C" int32_t grb_taa_resolve(const GrbImage *hdr, const GrbImage *depth, c
 // `history` (last frame's d3) and `luminance` may be NULL.  Returns GRB_ERR_UNSUPPORTED_FORMAT when the
 // device cannot launch cooperatively or the luminance grid exceeds the kernel's shared memory; the
 // caller then issues the six calls.
+extern "C" int32_t grb_bloom_tail_ex(const GrbImage *d0, const GrbImage *d1, const GrbImage *d2, const GrbImage *d3, const GrbImage *history, float lerp_d3,
+                                     float *luminance, float lerp_luminance, float min_loglum, float max_loglum, const GrbImage *u2, const GrbImage *u1,
+                                     const GrbBloomTailOptions *opt, void *stream);
+
 extern "C" int32_t grb_bloom_tail(const GrbImage *d0, const GrbImage *d1, const GrbImage *d2, const GrbImage *d3, const GrbImage *history, float lerp_d3,
                                   float *luminance, float lerp_luminance, float min_loglum, float max_loglum, const GrbImage *u2, const GrbImage *u1,
                                   void *stream)
 {
+	return grb_bloom_tail_ex(d0, d1, d2, d3, history, lerp_d3, luminance, lerp_luminance, min_loglum, max_loglum, u2, u1, nullptr, stream);
+}
+
+// The same launch with extras (all optional): u0 rows computed after u1 (the seventh dispatch of the pyramid), a wait
+// for the peer-stored d0 bands of a row-sharded frame at the start of the kernel (instead of grb_peer_wait), and a
+// cap on the number of CTAs so that the launch can sit beside another kernel that wants the rest of the machine.
+extern "C" int32_t grb_bloom_tail_ex(const GrbImage *d0, const GrbImage *d1, const GrbImage *d2, const GrbImage *d3, const GrbImage *history, float lerp_d3,
+                                     float *luminance, float lerp_luminance, float min_loglum, float max_loglum, const GrbImage *u2, const GrbImage *u1,
+                                     const GrbBloomTailOptions *opt, void *stream)
+{
+	if (opt && opt->u0 &&
+	    (!image_ok(opt->u0, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || opt->u0->width != d0->width || opt->u0->height != d0->height || opt->u0->data == d0->data))
+	{
+		set_last_error("grb_bloom_tail_ex: u0 must be R16G16B16A16_SFLOAT of d0's size and not alias it");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	if (opt && opt->peer_flags && (opt->peer_count <= 0 || opt->peer_count > GRB_MAX_PEERS))
+	{
+		set_last_error("grb_bloom_tail_ex: peer_count out of range");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
 	const GrbImage *all[6] = { d0, d1, d2, d3, u2, u1 };
 	for (const GrbImage *im : all)
 		if (!image_ok(im, GRB_FORMAT_R16G16B16A16_SFLOAT, 8))
@@ -1219,6 +1297,37 @@ extern "C" int32_t grb_bloom_tail(const GrbImage *d0, const GrbImage *d1, const 
 	a.lerp_lum = lerp_luminance;
 	a.lo = min_loglum;
 	a.hi = max_loglum;
+	a.u0 = View<uint2>{};
+	a.u0_y0 = a.u0_y1 = 0;
+	a.wait_flags = nullptr;
+	a.wait_count = 0;
+	a.wait_epoch = 0u;
+	a.error_word = nullptr;
+	a.max_spins = 1u << 25;
+	int max_ctas = 0;
+	if (opt)
+	{
+		if (opt->u0)
+		{
+			const GrbRows r = full_rows(opt->u0_rows, opt->u0->height);
+			if (r.y1 > r.y0)
+			{
+				a.u0 = view_of<uint2>(opt->u0);
+				a.u0_y0 = r.y0;
+				a.u0_y1 = r.y1;
+			}
+		}
+		if (opt->peer_flags)
+		{
+			a.wait_flags = opt->peer_flags;
+			a.wait_count = opt->peer_count;
+			a.wait_epoch = opt->peer_epoch;
+			a.error_word = device_error_word();
+			if (const char *e = getenv("GRB_PEER_WAIT_SPINS"))
+				a.max_spins = (unsigned)strtoul(e, nullptr, 10);
+		}
+		max_ctas = opt->max_ctas;
+	}
 	// every CTA must be co-resident (grid barrier): ask the occupancy calculator; the largest level
 	// (d1 / u1) decides how many CTAs are useful
 	int per_sm = 0;
@@ -1230,6 +1339,8 @@ extern "C" int32_t grb_bloom_tail(const GrbImage *d0, const GrbImage *d1, const 
 	}
 	const int texels = d1->width * d1->height;
 	int ctas = std::min(sms * std::min(per_sm, 2), std::max(1, (texels + kTailThreads - 1) / kTailThreads));
+	if (max_ctas > 0)
+		ctas = std::min(ctas, max_ctas);
 	void *params[] = { &a };
 	cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(bloom_tail_kernel), dim3(ctas), dim3(kTailThreads), params, 0, as_stream(stream));
 	if (err != cudaSuccess)

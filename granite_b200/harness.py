@@ -165,10 +165,20 @@ def bloom_upsample(in_t, out_t, rows=None):
     capi.check(capi.lib().grb_bloom_upsample(C.byref(ii), C.byref(oi), capi.rows(rows), capi.stream_ptr()), "grb_bloom_upsample")
 
 
-def bloom_tail(d0_t, d1_t, d2_t, d3_t, history_t, lerp_d3, lum_t, lerp_lum, u2_t, u1_t, lo=-3.0, hi=2.0):
-    """d1, d2, d3 (+feedback), luminance, u2, u1 in one cooperative launch."""
+def bloom_tail(d0_t, d1_t, d2_t, d3_t, history_t, lerp_d3, lum_t, lerp_lum, u2_t, u1_t, lo=-3.0, hi=2.0, u0_t=None, u0_rows=None, max_ctas=0):
+    """d1, d2, d3 (+feedback), luminance, u2, u1 in one cooperative launch; with u0_t also (rows of) u0."""
     im = [_img16(t) for t in (d0_t, d1_t, d2_t, d3_t, u2_t, u1_t)]
     hi_ = C.byref(_img16(history_t)) if history_t is not None else None
+    if u0_t is not None or max_ctas:
+        opt = capi.GrbBloomTailOptions()
+        u0i = _img16(u0_t) if u0_t is not None else None
+        opt.u0 = C.cast(C.pointer(u0i), C.c_void_p) if u0i is not None else None
+        opt.u0_rows = capi.rows(u0_rows)
+        opt.max_ctas = int(max_ctas)
+        capi.check(capi.lib().grb_bloom_tail_ex(C.byref(im[0]), C.byref(im[1]), C.byref(im[2]), C.byref(im[3]), hi_, C.c_float(lerp_d3), _ptr(lum_t),
+                                                C.c_float(lerp_lum), C.c_float(lo), C.c_float(hi), C.byref(im[4]), C.byref(im[5]), C.byref(opt),
+                                                capi.stream_ptr()), "grb_bloom_tail_ex")
+        return
     capi.check(capi.lib().grb_bloom_tail(C.byref(im[0]), C.byref(im[1]), C.byref(im[2]), C.byref(im[3]), hi_, C.c_float(lerp_d3), _ptr(lum_t),
                                          C.c_float(lerp_lum), C.c_float(lo), C.c_float(hi), C.byref(im[4]), C.byref(im[5]), capi.stream_ptr()),
                "grb_bloom_tail")

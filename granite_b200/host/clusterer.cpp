@@ -323,7 +323,17 @@ void LightClusterer::build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd)
 	// update_bindless_mask_buffer_gpu: K1 -> K2 -> K3 (stream order replaces the barriers)
 	cmd.check(grb_cluster_spot_transform(&cam, &parameters, &buf, cmd.get_stream_handle()), "grb_cluster_spot_transform");
 	cmd.check(grb_cluster_cull_setup(&cam, &parameters, &buf, cmd.get_stream_handle()), "grb_cluster_cull_setup");
-	cmd.check(grb_cluster_binning(&parameters, &buf, cmd.get_stream_handle()), "grb_cluster_binning");
+	int tile_y0 = 0, tile_y1 = 0;
+	if (lit_y1 > lit_y0 && lit_height > 0)
+	{
+		// tile row of a pixel row: floor((y + 0.5) / height * resolution_y) (clustering.frag through
+		// clusterer_bindless.h:29-40); one tile row of margin covers the rounding of that product
+		tile_y0 = int((long long)lit_y0 * (long long)resolution_y / lit_height) - 1;
+		tile_y1 = int(((long long)lit_y1 * (long long)resolution_y + lit_height - 1) / lit_height) + 1;
+		tile_y0 = tile_y0 < 0 ? 0 : tile_y0;
+		tile_y1 = tile_y1 > int(resolution_y) ? int(resolution_y) : tile_y1;
+	}
+	cmd.check(grb_cluster_binning_rows(&parameters, &buf, tile_y0, tile_y1, cmd.get_stream_handle()), "grb_cluster_binning");
 	// update_bindless_range_buffer_gpu: K4
 	cmd.check(grb_cluster_z_range(&buf, (int32_t)volume_index_range.size(), cmd.get_stream_handle()), "grb_cluster_z_range");
 }

@@ -36,6 +36,15 @@ public:
 	void set_enable_clustering(bool enable) { enable_clustering = enable; }
 	// Declare the clustering pass on RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT (second CUDA stream).
 	void set_async_compute(bool enable) { async_compute = enable; }
+	// Row-sharded frames: only the cluster tiles under pixel rows [y0, y1) of a frame `height` rows tall are consumed
+	// by this rank's lighting pass, so only those tile rows are binned (one tile row of margin either side).
+	// y1 <= y0: every row (default).
+	void set_lit_pixel_rows(int y0, int y1, int height)
+	{
+		lit_y0 = y0;
+		lit_y1 = y1;
+		lit_height = height;
+	}
 	void set_max_spot_lights(unsigned) {}
 	void set_max_point_lights(unsigned) {}
 
@@ -75,6 +84,7 @@ private:
 	unsigned resolution_x = 64, resolution_y = 32, resolution_z = 16;
 	bool enable_clustering = true;
 	bool async_compute = false;
+	int lit_y0 = 0, lit_y1 = 0, lit_height = 0;
 
 	GrbClusterParameters parameters = {};
 	std::vector<PositionalFragmentInfo> lights;

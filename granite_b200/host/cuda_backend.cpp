@@ -131,7 +131,7 @@ Device::~Device()
 
 Stream Device::get_queue_stream(unsigned idx)
 {
-	if (idx == 0 || idx > 2)
+	if (idx == 0 || idx > 3)
 		return stream;
 	std::lock_guard<std::mutex> hold(lock);
 	auto &side = side_streams[idx - 1];
@@ -154,7 +154,7 @@ Stream Device::get_queue_stream(unsigned idx)
 
 void Device::join_side_streams()
 {
-	for (int i = 0; i < 2; i++)
+	for (int i = 0; i < 3; i++)
 	{
 		if (!side_streams[i] || side_streams[i] == stream)
 			continue;

@@ -114,7 +114,8 @@ public:
 	int get_device_index() const { return index; }
 	Stream get_stream() const { return stream; }
 	// Side streams for passes declared on the asynchronous queues (the reference's async-compute
-	// queue): index 1 = RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT, 2 = RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT.
+	// queue): index 1 = RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT, 2 = RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT,
+	// 3 = RENDER_GRAPH_QUEUE_ASYNC_POST_COMPUTE_BIT.
 	// Index 0 is the main stream.  Created on first use.
 	Stream get_queue_stream(unsigned index);
 	Stream get_async_stream() { return get_queue_stream(1); }
@@ -151,8 +152,8 @@ private:
 	int index;
 	Stream stream;
 	bool owns_stream = false;
-	Stream side_streams[2] = { nullptr, nullptr };
-	Event join_events[2] = { nullptr, nullptr };
+	Stream side_streams[3] = { nullptr, nullptr, nullptr };
+	Event join_events[3] = { nullptr, nullptr, nullptr };
 	Event alloc_event = nullptr; // orders the zero fill of a fresh allocation before the side streams
 	std::mutex lock;
 	std::vector<TimeInterval> intervals;

@@ -70,7 +70,6 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 			rc = grb_bloom_downsample_to_peers(&t, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch, slot.counter, d0_rows, stream);
 		}
 		cmd.check(rc, "grb_bloom_downsample_to_peers");
-		cmd.check(grb_peer_wait(slot.flags[self], (int32_t)slot.count, slot.epoch, stream), "grb_peer_wait");
 		d0.data = slot.images[self]; // the pyramid tail reads the exchanged copy
 	}
 	else if (grb_bloom_threshold_downsample(&hdr, lum, keep_threshold ? &t : nullptr, &d0, d0_rows, stream) != GRB_OK)
@@ -78,6 +77,11 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 		cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
 		cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, stream), "grb_bloom_downsample(d0)");
 	}
+	// Everything above wants the whole machine for a few tens of microseconds; everything below is latency-bound
+	// and small.  The next frame's lighting pass (a persistent kernel that takes every SM it is given) waits for this
+	// mark, so the two do not fight over SMs, and starts while the pyramid tail below -- already resident on a
+	// few SMs, see max_ctas -- runs beside it.
+	graph.signal_mark("bloom-head", cmd);
 
 	if (sharded && !peer_stores)
 	{
@@ -99,11 +103,32 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	// the reference split (band partial sums + all-reduce) and the separate calls
 	const bool nccl_luminance = lum && sharded && r.lum_grid && !peer_stores;
 
-	// Everything below 1/4 resolution -- d1, d2, d3, luminance, u2, u1 -- is one cooperative launch
-	// (grid barriers between the levels); six separate dispatches when that is not available.
-	bool tail_fused = false;
+	// Everything below 1/4 resolution -- d1, d2, d3, luminance, u2, u1 -- and the last upsample u0 (own band + the
+	// tonemap halo when row-sharded) is one cooperative launch (grid barriers between the levels); separate
+	// dispatches when that is not available.  Row-sharded frames: the kernel itself waits for the peers' d0 bands.
+	GrbRows u0_rows = sharded ? plan.upsample0 : all_rows();
+	bool tail_fused = false, peers_awaited = false;
 	if (!nccl_luminance)
-		tail_fused = grb_bloom_tail(&d0, &d1, &d2, &d3, history ? &hist : nullptr, lerp_d3, lum, lerp_lum, -3.0f, 2.0f, &u2, &u1, stream) == GRB_OK;
+	{
+		static const int tail_ctas = [] {
+			const char *e = getenv("GRB_BLOOM_TAIL_CTAS");
+			return e ? atoi(e) : 16;
+		}();
+		GrbBloomTailOptions opt = {};
+		opt.u0 = &u0;
+		opt.u0_rows = u0_rows;
+		if (peer_stores)
+		{
+			opt.peer_flags = slot.flags[graph.get_collectives()->get_rank()];
+			opt.peer_count = (int32_t)slot.count;
+			opt.peer_epoch = slot.epoch;
+		}
+		opt.max_ctas = tail_ctas;
+		tail_fused = grb_bloom_tail_ex(&d0, &d1, &d2, &d3, history ? &hist : nullptr, lerp_d3, lum, lerp_lum, -3.0f, 2.0f, &u2, &u1, &opt, stream) == GRB_OK;
+		peers_awaited = tail_fused;
+	}
+	if (peer_stores && !peers_awaited)
+		cmd.check(grb_peer_wait(slot.flags[graph.get_collectives()->get_rank()], (int32_t)slot.count, slot.epoch, stream), "grb_peer_wait");
 	if (!tail_fused)
 	{
 		cmd.check(grb_bloom_downsample(&d0, nullptr, 0.0f, &d1, all_rows(), stream), "grb_bloom_downsample(d1)");
@@ -129,8 +154,8 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 		cmd.check(grb_bloom_upsample(&u2, &u1, all_rows(), stream), "grb_bloom_upsample(u1)");
 	}
 	// u0 feeds the tonemap's bilinear bloom tap: own band (+ the tonemap halo FXAA needs) at 1/4 res
-	GrbRows u0_rows = sharded ? plan.upsample0 : all_rows();
-	cmd.check(grb_bloom_upsample(&u1, &u0, u0_rows, stream), "grb_bloom_upsample(u0)");
+	if (!tail_fused)
+		cmd.check(grb_bloom_upsample_exact(&u1, &u0, u0_rows, stream), "grb_bloom_upsample(u0)"); // the arithmetic the fused tail uses
 }
 
 void tonemap_build_render_pass(RenderPass &pass, Vulkan::CommandBuffer &cmd, const RenderTextureResource &hdr_res,

@@ -260,6 +260,7 @@ void RenderGraph::reset()
 	physical_history_spare.clear();
 	physical_buffers.clear();
 	last_access.clear();
+	marks.clear();
 	pass_done_events.clear();
 	physical_pingpong_spare.clear();
 	physical_buffer_spare.clear();
@@ -536,7 +537,7 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 			if (la.write_event && la.write_stream != stream)
 				dev.stream_wait_event(stream, la.write_event);
 			if (writes)
-				for (unsigned i = 0; i < 3; i++)
+				for (unsigned i = 0; i < 4; i++)
 					if (la.stream_event[i] && la.stream_of[i] != stream && la.stream_event[i] != la.write_event)
 						dev.stream_wait_event(stream, la.stream_event[i]);
 		};
@@ -544,8 +545,8 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 			if (!key)
 				return;
 			auto &la = last_access[key];
-			la.stream_event[stream_index % 3] = pass_done_events[p][slot];
-			la.stream_of[stream_index % 3] = stream;
+			la.stream_event[stream_index % 4] = pass_done_events[p][slot];
+			la.stream_of[stream_index % 4] = stream;
 			if (writes)
 			{
 				la.write_event = pass_done_events[p][slot];
@@ -560,6 +561,8 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 				wait_for(physical_key(*w, false), true);
 			for (auto *h : pass.get_history_inputs())
 				wait_for(physical_key(*h, true), false);
+			for (auto &name : pass.get_wait_marks())
+				wait_mark(name, cmd);
 		}
 
 		Vulkan::Event begin = nullptr, end = nullptr;
@@ -594,6 +597,26 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 	}
 	if (errors)
 		Vulkan::log_error("%u pass callback(s) reported errors this frame.\n", errors);
+}
+
+void RenderGraph::signal_mark(const std::string &name, Vulkan::CommandBuffer &cmd)
+{
+	auto &m = marks[name];
+	// a small ring: re-recording the event a waiter of an earlier frame still refers to would move its wait forward
+	auto &e = m.events[m.next];
+	m.next = (m.next + 1) % m.events.size();
+	if (!e)
+		e = cmd.get_device().request_event();
+	cmd.get_device().record_event_on(e, cmd.get_stream());
+	m.latest = e;
+	m.stream = cmd.get_stream();
+}
+
+void RenderGraph::wait_mark(const std::string &name, Vulkan::CommandBuffer &cmd)
+{
+	auto itr = marks.find(name);
+	if (itr != marks.end() && itr->second.latest && itr->second.stream != cmd.get_stream())
+		cmd.get_device().stream_wait_event(cmd.get_stream(), itr->second.latest);
 }
 
 Vulkan::ImageView &RenderGraph::get_physical_texture_resource(unsigned index)

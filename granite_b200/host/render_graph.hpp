@@ -107,7 +107,10 @@ enum RenderGraphQueueFlagBits
 	RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT = 1 << 2,
 	// A second asynchronous queue for the post chain, so the (HBM-bound) post passes of frame N
 	// run beside the (ALU-bound) lighting of frame N+1.
-	RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT = 1 << 3
+	RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT = 1 << 3,
+	// Not in the reference: a third asynchronous queue, so that the bloom pyramid of frame N (whose tail
+	// runs beside the lighting of frame N+1) does not hold back the tonemap of frame N-1 or vice versa.
+	RENDER_GRAPH_QUEUE_ASYNC_POST_COMPUTE_BIT = 1 << 4
 };
 using RenderGraphQueueFlags = uint32_t;
 
@@ -244,6 +247,9 @@ public:
 	const std::vector<RenderTextureResource *> &get_storage_texture_outputs() const { return storage_texture_outputs; }
 	const std::vector<RenderTextureResource *> &get_attachment_inputs() const { return attachments_inputs; }
 	const std::vector<RenderTextureResource *> &get_history_inputs() const { return history_inputs; }
+	// Not in the reference: this pass starts only after the latest RenderGraph::signal_mark(name) (any frame).
+	void add_wait_mark(const std::string &name) { wait_marks.push_back(name); }
+	const std::vector<std::string> &get_wait_marks() const { return wait_marks; }
 	const std::vector<RenderTextureResource *> &get_texture_inputs() const { return texture_inputs; }
 	const std::vector<RenderBufferResource *> &get_storage_outputs() const { return storage_outputs; }
 	const std::vector<RenderBufferResource *> &get_transfer_outputs() const { return transfer_outputs; }
@@ -304,6 +310,7 @@ private:
 	unsigned index;
 	RenderGraphQueueFlagBits queue;
 	RenderPassInterfaceHandle render_pass_handle;
+	std::vector<std::string> wait_marks;
 	std::function<void(Vulkan::CommandBuffer &)> build_render_pass_cb;
 	std::function<bool(VkClearDepthStencilValue *)> get_clear_depth_stencil_cb;
 	std::function<bool(unsigned, VkClearColorValue *)> get_clear_color_cb;
@@ -371,13 +378,20 @@ public:
 	// Like the reference these default to the main queue ("Don't use async compute by default",
 	// render_graph.hpp:889-893); set_async_post(true) moves the post chain to its own stream.
 	static RenderGraphQueueFlagBits get_default_post_graphics_queue() { return async_post ? RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT : RENDER_GRAPH_QUEUE_GRAPHICS_BIT; }
-	static RenderGraphQueueFlagBits get_default_compute_queue() { return async_post ? RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT : RENDER_GRAPH_QUEUE_COMPUTE_BIT; }
+	static RenderGraphQueueFlagBits get_default_compute_queue() { return async_post ? RENDER_GRAPH_QUEUE_ASYNC_POST_COMPUTE_BIT : RENDER_GRAPH_QUEUE_COMPUTE_BIT; }
 	static void set_async_post(bool enable) { async_post = enable; }
-	// Stream index a queue flag records on: 0 main, 1 async compute, 2 async graphics (post).
+	// Stream index a queue flag records on: 0 main, 1 async compute, 2 async graphics (tonemap, AA), 3 async post compute (bloom).
 	static unsigned queue_stream_index(RenderGraphQueueFlagBits queue)
 	{
-		return queue == RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT ? 1u : (queue == RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT ? 2u : 0u);
+		return queue == RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT ? 1u :
+		       (queue == RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT ? 2u : (queue == RENDER_GRAPH_QUEUE_ASYNC_POST_COMPUTE_BIT ? 3u : 0u));
 	}
+	// Ordering marks between passes that share no resource: signal_mark records an event at the current point of the
+	// pass being built (cmd's stream); wait_mark makes cmd's stream wait for the latest signal of that name (no-op
+	// before the first signal).  Used to phase the frame: the next lighting pass starts after this frame's
+	// full-machine bloom kernel, see host/post/hdr.cpp.
+	void signal_mark(const std::string &name, Vulkan::CommandBuffer &cmd);
+	void wait_mark(const std::string &name, Vulkan::CommandBuffer &cmd);
 	// Stream of the pass that writes `resource` (for host readbacks of a graph output).
 	Vulkan::Stream get_writer_stream(const RenderResource &resource);
 
@@ -427,10 +441,18 @@ private:
 	{
 		Vulkan::Event write_event = nullptr;
 		Vulkan::Stream write_stream = nullptr;
-		Vulkan::Event stream_event[3] = { nullptr, nullptr, nullptr };
-		Vulkan::Stream stream_of[3] = { nullptr, nullptr, nullptr };
+		Vulkan::Event stream_event[4] = { nullptr, nullptr, nullptr, nullptr };
+		Vulkan::Stream stream_of[4] = { nullptr, nullptr, nullptr, nullptr };
 	};
 	std::unordered_map<const void *, LastAccess> last_access; // keyed by the physical image / buffer
+	struct Mark
+	{
+		std::array<Vulkan::Event, 4> events = { nullptr, nullptr, nullptr, nullptr };
+		unsigned next = 0;
+		Vulkan::Event latest = nullptr;
+		Vulkan::Stream stream = nullptr;
+	};
+	std::unordered_map<std::string, Mark> marks;
 	// one "pass done" event per pass per frame slot: a later frame re-recording the same event
 	// would turn "wait for frame N-2's reader" into "wait for frame N's", serialising the streams
 	enum { EventRing = 4 };

@@ -1,5 +1,6 @@
 #include "renderer.hpp"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace Granite
@@ -67,6 +68,9 @@ void DeferredLightingPass::setup_dependencies(RenderPass &self, RenderGraph &gra
 	// scene.add_render_pass_dependencies(lighting, LIGHTING_BIT) -> clusterer adds its storage inputs
 	if (clusterer)
 		clusterer->setup_render_pass_dependencies(graph_, self);
+	// The persistent kernel takes every SM it is given: let the previous frame's full-machine bloom kernel finish
+	// first (host/post/hdr.cpp signals the mark); the latency-bound rest of that chain then runs beside this pass.
+	self.add_wait_mark("bloom-head");
 }
 
 void DeferredLightingPass::set_resources(RenderGraph &graph_, RenderTextureResource &albedo, RenderTextureResource &normal, RenderTextureResource &pbr,
@@ -92,7 +96,11 @@ void DeferredLightingPass::build_render_pass(Vulkan::CommandBuffer &cmd)
 		gb.emissive = &graph->get_physical_texture_resource(*res_emissive);
 	auto &hdr = graph->get_physical_texture_resource(*res_hdr);
 	void *schedule = res_schedule ? graph->get_physical_buffer_resource(*res_schedule).get_device_pointer() : nullptr;
+	// GRB_SHARDED_BLOCKS=1: the block form of the kernel for row-sharded frames (many short CTAs instead of one
+	// persistent CTA per SM), as before the frame was phased.
+	static const bool sharded_blocks = getenv("GRB_SHARDED_BLOCKS") != nullptr;
 	const bool sharded = graph->is_sharded() && graph->get_shard_count() > 1;
-	DeferredLightRenderer::render_light(cmd, context, gb, hdr, graph->is_sharded() ? graph->get_shard_plan().lighting : GrbRows{ 0, 0 }, schedule, sharded);
+	DeferredLightRenderer::render_light(cmd, context, gb, hdr, graph->is_sharded() ? graph->get_shard_plan().lighting : GrbRows{ 0, 0 }, schedule,
+	                                    sharded && sharded_blocks);
 }
 } // namespace Granite

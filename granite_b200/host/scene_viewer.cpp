@@ -123,6 +123,13 @@ void GrbhViewer::bake_render_graph()
 	cluster.set_scene_lights(&scene_lights);
 	cluster.set_base_render_context(&context);
 	cluster.set_async_compute(getenv("GRB_NO_ASYNC_CLUSTER") == nullptr);
+	if (bands.size() > 1)
+	{
+		const GrbRows lit = input_rows();
+		cluster.set_lit_pixel_rows(lit.y0, lit.y1, config.height);
+	}
+	else
+		cluster.set_lit_pixel_rows(0, 0, 0);
 	cluster.add_render_passes(graph);
 	lighting.cluster = &cluster;
 	context.set_lighting_parameters(&lighting);

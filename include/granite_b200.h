@@ -148,6 +148,11 @@ int32_t grb_cluster_cull_setup(const GrbCamera *cam, const GrbClusterParameters 
                                const GrbClusterBuffers *buf, void *stream);
 /* K3 clusterer_bindless_binning.comp (SUBGROUPS=1, 32-wide: clusterer.cpp:1519-1561). */
 int32_t grb_cluster_binning(const GrbClusterParameters *params, const GrbClusterBuffers *buf, void *stream);
+/* The same for tile rows [tile_y0, tile_y1) only (widened to whole blocks of 4 tile rows; an empty range = all rows):
+ * a rank of a row-sharded frame bins the tile rows its own pixel rows fall into, the other rows of the bitmask are
+ * left as they are. */
+int32_t grb_cluster_binning_rows(const GrbClusterParameters *params, const GrbClusterBuffers *buffers, int32_t tile_y0,
+                                 int32_t tile_y1, void *stream);
 /* K4 clusterer_bindless_z_range[_opt].comp; push block clusterer.cpp:1291-1300. */
 int32_t grb_cluster_z_range(const GrbClusterBuffers *buf, int32_t num_ranges, void *stream);
 /* All four in the order build_cluster_bindless_gpu records them. */
@@ -244,6 +249,9 @@ int32_t grb_bloom_threshold_downsample_to_peers(const GrbImage *hdr, const float
 int32_t grb_peer_wait(const uint32_t *local_flags, int32_t count, uint32_t epoch, void *stream);
 /* K9 bloom_upsample.comp; hdr.cpp:189-216. */
 int32_t grb_bloom_upsample(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream);
+/* Same, never through the tile kernel: the shader's arithmetic statement for statement at every size (bit-exact to the
+ * oracle; the tile kernel is within 1 fp16 ulp). */
+int32_t grb_bloom_upsample_exact(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream);
 /* K10 luminance.comp; hdr.cpp:68-98 (size = d3 / 2, lerp = 1 - 0.5^frame_time, clamp [-3,2]).
  * Single-device form: reads d3, updates luminance[3] in place. */
 int32_t grb_luminance(const GrbImage *d3, float *luminance, float lerp, float min_loglum,
@@ -262,6 +270,24 @@ int32_t grb_luminance_finalize(const float *grid, int32_t size_x, int32_t size_y
 int32_t grb_bloom_tail(const GrbImage *d0, const GrbImage *d1, const GrbImage *d2, const GrbImage *d3,
                        const GrbImage *history, float lerp_d3, float *luminance, float lerp_luminance,
                        float min_loglum, float max_loglum, const GrbImage *u2, const GrbImage *u1, void *stream);
+
+/* The same launch with optional extras.  u0 / u0_rows: also compute those rows of u0 from u1 (the last upsample of
+ * hdr.cpp:376) after u1.  peer_flags / peer_count / peer_epoch: row-sharded frames whose d0 was assembled by
+ * grb_bloom_*_to_peers -- the kernel itself waits (bounded) until every rank's flag reached peer_epoch, replacing
+ * grb_peer_wait.  max_ctas > 0 caps the launch so that it can run beside a kernel that fills the other SMs. */
+typedef struct GrbBloomTailOptions
+{
+	const GrbImage *u0;
+	GrbRows u0_rows;
+	const uint32_t *peer_flags;
+	int32_t peer_count;
+	uint32_t peer_epoch;
+	int32_t max_ctas;
+} GrbBloomTailOptions;
+int32_t grb_bloom_tail_ex(const GrbImage *d0, const GrbImage *d1, const GrbImage *d2, const GrbImage *d3,
+                          const GrbImage *history, float lerp_d3, float *luminance, float lerp_luminance,
+                          float min_loglum, float max_loglum, const GrbImage *u2, const GrbImage *u1,
+                          const GrbBloomTailOptions *options, void *stream);
 /* K11 tonemap.frag; hdr.cpp:283-306. out: R8G8B8A8_SRGB (or _UNORM: stores linear). */
 int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const float *luminance,
                     float dynamic_exposure, const GrbImage *out, GrbRows rows, void *stream);

@@ -321,6 +321,43 @@ def test_bloom_tail_fused_bit_exact(cuda, oracle, w0, h0, feedback, dynamic):
         assert common.f32_ulp_diff(lum[1:], lum_ref[1:]).max() <= 4
 
 
+@pytest.mark.parametrize("w0,h0,rows,ctas", [(960, 540, None, 0), (960, 540, (128, 280), 16), (66, 37, (3, 30), 2), (480, 270, None, 1)])
+def test_bloom_tail_with_u0_and_cta_cap(cuda, oracle, w0, h0, rows, ctas):
+    """grb_bloom_tail_ex: the last upsample u0 (rows of it) inside the same launch, and the launch capped to a few
+    CTAs (the form the frame uses beside the next lighting pass): every level bit for bit the oracle's."""
+    import math
+
+    from granite_b200 import harness
+
+    rng = np.random.default_rng(w0 * 3 + h0)
+    d0 = common.random_rgba16f(rng, w0, h0)
+    sz = [(w0, h0)]
+    for _ in range(3):
+        sz.append((int(math.ceil(sz[-1][0] * 0.5)), int(math.ceil(sz[-1][1] * 0.5))))
+    hist = common.random_rgba16f(rng, *sz[3])
+    lerp_d3, lerp_lum = float(np.float32(1.0 - 0.001 ** (1 / 60))), float(np.float32(1.0 - 0.5 ** (1 / 60)))
+    lum0 = np.array([0.3, 2.0 ** 0.3, 2.0 ** -0.3], np.float32)
+    d1 = oracle.bloom_downsample(d0, sz[1])
+    d2 = oracle.bloom_downsample(d1, sz[2])
+    d3 = oracle.bloom_downsample(d2, sz[3], hist, lerp_d3)
+    lum_ref = oracle.luminance(d3, lum0, lerp_lum)
+    u2 = oracle.bloom_upsample(d3, sz[2])
+    u1 = oracle.bloom_upsample(u2, sz[1])
+    u0 = oracle.bloom_upsample(u1, sz[0])
+    t = {k: harness.new_rgba16f(*s_) for k, s_ in (("d1", sz[1]), ("d2", sz[2]), ("d3", sz[3]), ("u2", sz[2]), ("u1", sz[1]), ("u0", sz[0]))}
+    lum_t = harness.to_dev(lum0.copy())
+    harness.bloom_tail(harness.to_dev(d0), t["d1"], t["d2"], t["d3"], harness.to_dev(hist), lerp_d3, lum_t, lerp_lum, t["u2"], t["u1"], u0_t=t["u0"],
+                       u0_rows=rows, max_ctas=ctas)
+    for k, ref in (("d1", d1), ("d2", d2), ("d3", d3), ("u2", u2), ("u1", u1)):
+        assert np.array_equal(harness.to_host(t[k], np.uint16), ref), k
+    got = harness.to_host(t["u0"], np.uint16)
+    y0, y1 = rows if rows else (0, h0)
+    assert np.array_equal(got[y0:y1], u0[y0:y1]), "u0"
+    assert not got[:y0].any() and not got[y1:].any()
+    lum = lum_t.cpu().numpy()
+    assert lum.view(np.uint32)[0] == lum_ref.view(np.uint32)[0] and common.f32_ulp_diff(lum[1:], lum_ref[1:]).max() <= 4
+
+
 @pytest.mark.parametrize("w,h", [(8, 8), (60, 34), (120, 68), (61, 35)])
 def test_luminance(cuda, oracle, w, h):
     from granite_b200 import harness

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--equal-bands", action="store_true")
     ap.add_argument("--bands", default="", help="explicit cuts, e.g. 792,944,1040 for 4 ranks")
     ap.add_argument("--show", default="", help="ranks to print (default all), e.g. 0,4")
+    ap.add_argument("--compact", action="store_true", help="one line per frame: lighting start / duration and period, cluster / bloom / tonemap intervals")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -79,6 +80,24 @@ def main():
         if r != rank or (args.show and str(rank) not in args.show.split(",")):
             continue
         print(f"--- rank {rank} of {world}, rows {bands[rank] if world > 1 else (0, h)}")
+        if args.compact:
+            frames, cur = [], {}
+            for name, b, e in tl:
+                if name in cur:
+                    frames.append(cur)
+                    cur = {}
+                cur[name] = (b * 1000, e * 1000)
+            frames.append(cur)
+            prev = None
+            for i, f in enumerate(frames):
+                L = f.get("lighting", (0, 0))
+                line = f"frame {i:3d}: lighting {L[0]:8.1f} +{L[1] - L[0]:6.1f}  period {L[0] - prev if prev is not None else 0:6.1f} |"
+                for k in ("clustering-bindless", "bloom-compute", "tonemap"):
+                    if k in f:
+                        line += f" {k.split('-')[0]} {f[k][0] - L[0]:+7.1f}..{f[k][1] - L[0]:+7.1f}"
+                print(line)
+                prev = L[0]
+            continue
         for name, b, e in tl:
             print(f"{name:22s} {b * 1000:9.1f} -> {e * 1000:9.1f} us  ({(e - b) * 1000:7.1f})")
         sys.stdout.flush()
