@@ -278,7 +278,10 @@ def main():
     scene = synth.make_scene(w, h)
     lights = synth.make_lights(n_lights, aspect=w / h)
     post = {"none": viewer.AA_NONE, "taa+fxaa": viewer.AA_TAA_HIGH_PLUS_FXAA}[aa]
-    stream = torch.cuda.current_stream()
+    # One priority level above the lowest: the library's tonemap / AA stream sits below the stream that carries the
+    # lighting pass (host/cuda_backend.cpp), so its kernels run in the gap between two lighting passes.
+    stream = torch.cuda.Stream(priority=-1)
+    torch.cuda.set_stream(stream)
 
     def make_viewer(timestamps, pipelined_io=False, use_bands=None):
         v = viewer.Viewer(w, h, post_aa=post, hdr_bloom=bloom, dynamic_exposure=bloom, cuda_device=local_rank, timestamps=timestamps,

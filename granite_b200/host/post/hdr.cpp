@@ -30,6 +30,7 @@ struct BloomResources
 	RenderTextureResource *t, *d0, *u0, *d1, *u1, *d2, *u2, *d3, *hdr;
 	const RenderBufferResource *lum;
 	const RenderBufferResource *lum_grid;
+	const RenderBufferResource *lum_updated; // this frame's copy for the tonemap pass (alternates between two buffers)
 };
 
 GrbRows all_rows() { return GrbRows{ 0, 0 }; }
@@ -107,16 +108,23 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	// tonemap halo when row-sharded) is one cooperative launch (grid barriers between the levels); separate
 	// dispatches when that is not available.  Row-sharded frames: the kernel itself waits for the peers' d0 bands.
 	GrbRows u0_rows = sharded ? plan.upsample0 : all_rows();
-	bool tail_fused = false, peers_awaited = false;
+	bool tail_fused = false, peers_awaited = false, tail_has_u0 = false;
 	if (!nccl_luminance)
 	{
 		static const int tail_ctas = [] {
 			const char *e = getenv("GRB_BLOOM_TAIL_CTAS");
 			return e ? atoi(e) : 16;
 		}();
+		// u0 inside the launch costs the few SMs the launch sits on four times as long (at 4K it is 80 % of the texels
+		// below 1/4 resolution); as its own tile kernel it is 14 us of the whole machine.
+		static const bool u0_in_tail = getenv("GRB_BLOOM_U0_IN_TAIL") != nullptr;
 		GrbBloomTailOptions opt = {};
-		opt.u0 = &u0;
-		opt.u0_rows = u0_rows;
+		if (u0_in_tail)
+		{
+			opt.u0 = &u0;
+			opt.u0_rows = u0_rows;
+		}
+		tail_has_u0 = u0_in_tail;
 		if (peer_stores)
 		{
 			opt.peer_flags = slot.flags[graph.get_collectives()->get_rank()];
@@ -154,8 +162,14 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 		cmd.check(grb_bloom_upsample(&u2, &u1, all_rows(), stream), "grb_bloom_upsample(u1)");
 	}
 	// u0 feeds the tonemap's bilinear bloom tap: own band (+ the tonemap halo FXAA needs) at 1/4 res
-	if (!tail_fused)
-		cmd.check(grb_bloom_upsample_exact(&u1, &u0, u0_rows, stream), "grb_bloom_upsample(u0)"); // the arithmetic the fused tail uses
+	if (!tail_fused || !tail_has_u0)
+		cmd.check(grb_bloom_upsample(&u1, &u0, u0_rows, stream), "grb_bloom_upsample(u0)");
+	// The tonemap pass of this frame runs while the NEXT frame's pyramid is already updating the average luminance
+	// in place: it reads its own copy.
+	if (lum && r.lum_updated)
+		Vulkan::cuda_ok(cudaMemcpyAsync(graph.get_physical_buffer_resource(*r.lum_updated).get<float>(), lum, 3 * sizeof(float), cudaMemcpyDeviceToDevice,
+		                                reinterpret_cast<cudaStream_t>(cmd.get_stream())),
+		                "cudaMemcpyAsync(average-luminance-updated)");
 }
 
 void tonemap_build_render_pass(RenderPass &pass, Vulkan::CommandBuffer &cmd, const RenderTextureResource &hdr_res,
@@ -199,7 +213,13 @@ void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &fr
 	auto res = std::make_shared<BloomResources>();
 	res->t = &bloom_pass.add_storage_texture_output("threshold", downsample_info);
 	res->d0 = &bloom_pass.add_storage_texture_output("downsample-0", level(0.25f));
-	res->u0 = &bloom_pass.add_storage_texture_output("upsample-0", level(0.25f));
+	{
+		// tonemap(N) reads upsample-0 while bloom(N+1) may already be writing it: two copies, like the HDR input
+		auto u0_info = level(0.25f);
+		if (RenderGraph::get_default_compute_queue() != RENDER_GRAPH_QUEUE_COMPUTE_BIT)
+			u0_info.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
+		res->u0 = &bloom_pass.add_storage_texture_output("upsample-0", u0_info);
+	}
 	res->d1 = &bloom_pass.add_storage_texture_output("downsample-1", level(0.125f));
 	res->u1 = &bloom_pass.add_storage_texture_output("upsample-1", level(0.125f));
 	res->d2 = &bloom_pass.add_storage_texture_output("downsample-2", level(0.0625f));
@@ -207,9 +227,16 @@ void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &fr
 	res->d3 = &bloom_pass.add_storage_texture_output("downsample-3", level(0.03125f));
 	res->lum = nullptr;
 	res->lum_grid = nullptr;
+	res->lum_updated = nullptr;
 	if (options.dynamic_exposure)
 	{
 		res->lum = &bloom_pass.add_storage_output("average-luminance", buffer_info);
+		// what the reference's fragment path calls "average-luminance-updated" (hdr.cpp:519-533): the value the tonemap
+		// pass of THIS frame reads
+		BufferInfo updated_info = buffer_info;
+		if (RenderGraph::get_default_compute_queue() != RENDER_GRAPH_QUEUE_COMPUTE_BIT)
+			updated_info.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
+		res->lum_updated = &bloom_pass.add_storage_output("average-luminance-updated", updated_info);
 		// scratch for the row-sharded luminance sum: the (d3/2) sample grid (hdr.cpp:78-79), sized from
 		// the backbuffer: d3 = ceil(dim / 32)
 		BufferInfo grid_info;
@@ -236,7 +263,7 @@ void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &fr
 		auto &bloom_res = tonemap.add_texture_input("upsample-0");
 		const RenderBufferResource *ubo_res = nullptr;
 		if (options.dynamic_exposure)
-			ubo_res = &tonemap.add_uniform_input("average-luminance");
+			ubo_res = &tonemap.add_uniform_input("average-luminance-updated");
 		tonemap.set_build_render_pass([&tonemap, &hdr_res, &bloom_res, ubo_res, iface, &graph](Vulkan::CommandBuffer &cmd) {
 			// FXAA downstream reads +-9 rows around a band: tonemap that halo too when a consumer declared it
 			unsigned halo = graph.find_pass("fxaa") ? 12u : 0u;
