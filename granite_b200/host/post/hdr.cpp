@@ -27,7 +27,7 @@ namespace
 {
 struct BloomResources
 {
-	RenderTextureResource *t, *d0, *u0, *d1, *u1, *d2, *u2, *d3, *hdr;
+	RenderTextureResource *t, *d0, *d1, *u1, *d2, *u2, *d3, *hdr;
 	const RenderBufferResource *lum;
 	const RenderBufferResource *lum_grid;
 	const RenderBufferResource *lum_updated; // this frame's copy for the tonemap pass (alternates between two buffers)
@@ -42,7 +42,7 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	float *lum = r.lum ? graph.get_physical_buffer_resource(*r.lum).get<float>() : nullptr;
 
 	GrbImage hdr = img(r.hdr), t = img(r.t), d0 = img(r.d0), d1 = img(r.d1), d2 = img(r.d2), d3 = img(r.d3);
-	GrbImage u2 = img(r.u2), u1 = img(r.u1), u0 = img(r.u0);
+	GrbImage u2 = img(r.u2), u1 = img(r.u1);
 	const bool sharded = graph.is_sharded() && graph.get_shard_count() > 1;
 
 	// Rows of each band-only level (shard_plan.hpp derives them from the rows this rank owns).
@@ -104,27 +104,19 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	// the reference split (band partial sums + all-reduce) and the separate calls
 	const bool nccl_luminance = lum && sharded && r.lum_grid && !peer_stores;
 
-	// Everything below 1/4 resolution -- d1, d2, d3, luminance, u2, u1 -- and the last upsample u0 (own band + the
-	// tonemap halo when row-sharded) is one cooperative launch (grid barriers between the levels); separate
-	// dispatches when that is not available.  Row-sharded frames: the kernel itself waits for the peers' d0 bands.
-	GrbRows u0_rows = sharded ? plan.upsample0 : all_rows();
-	bool tail_fused = false, peers_awaited = false, tail_has_u0 = false;
+	// Everything below 1/4 resolution -- d1, d2, d3, luminance, u2, u1 -- is one cooperative launch (grid barriers
+	// between the levels); separate dispatches when that is not available.  Row-sharded frames: the kernel itself
+	// waits for the peers' d0 bands.  The last upsample, u0, is issued by the tonemap pass (below): at 4K it is 80 % of
+	// the texels below 1/4 resolution, wants the whole machine for 14 us, and so belongs with the other
+	// full-machine kernels in the gap between two lighting passes, not beside one.
+	bool tail_fused = false, peers_awaited = false;
 	if (!nccl_luminance)
 	{
 		static const int tail_ctas = [] {
 			const char *e = getenv("GRB_BLOOM_TAIL_CTAS");
 			return e ? atoi(e) : 16;
 		}();
-		// u0 inside the launch costs the few SMs the launch sits on four times as long (at 4K it is 80 % of the texels
-		// below 1/4 resolution); as its own tile kernel it is 14 us of the whole machine.
-		static const bool u0_in_tail = getenv("GRB_BLOOM_U0_IN_TAIL") != nullptr;
 		GrbBloomTailOptions opt = {};
-		if (u0_in_tail)
-		{
-			opt.u0 = &u0;
-			opt.u0_rows = u0_rows;
-		}
-		tail_has_u0 = u0_in_tail;
 		if (peer_stores)
 		{
 			opt.peer_flags = slot.flags[graph.get_collectives()->get_rank()];
@@ -161,9 +153,6 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 		cmd.check(grb_bloom_upsample(&d3, &u2, all_rows(), stream), "grb_bloom_upsample(u2)");
 		cmd.check(grb_bloom_upsample(&u2, &u1, all_rows(), stream), "grb_bloom_upsample(u1)");
 	}
-	// u0 feeds the tonemap's bilinear bloom tap: own band (+ the tonemap halo FXAA needs) at 1/4 res
-	if (!tail_fused || !tail_has_u0)
-		cmd.check(grb_bloom_upsample(&u1, &u0, u0_rows, stream), "grb_bloom_upsample(u0)");
 	// The tonemap pass of this frame runs while the NEXT frame's pyramid is already updating the average luminance
 	// in place: it reads its own copy.
 	if (lum && r.lum_updated)
@@ -173,12 +162,21 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 }
 
 void tonemap_build_render_pass(RenderPass &pass, Vulkan::CommandBuffer &cmd, const RenderTextureResource &hdr_res,
-                               const RenderTextureResource &bloom_res, const RenderBufferResource *ubo_res, const HDRDynamicExposureInterface *iface,
-                               unsigned)
+                               const RenderTextureResource &bloom_res, const RenderTextureResource *u1_res, const RenderBufferResource *ubo_res,
+                               const HDRDynamicExposureInterface *iface, unsigned)
 {
 	auto &graph = pass.get_graph();
 	GrbImage hdr = graph.get_physical_texture_resource(hdr_res).as_grb();
 	GrbImage bloom = graph.get_physical_texture_resource(bloom_res).as_grb();
+	if (u1_res)
+	{
+		// bloom_upsample_build_compute for "upsample-0" (hdr.cpp:376): the bilinear bloom tap below reads it; own
+		// band (+ the tonemap halo FXAA needs) at 1/4 resolution when row-sharded
+		GrbImage u1 = graph.get_physical_texture_resource(*u1_res).as_grb();
+		const bool sharded = graph.is_sharded() && graph.get_shard_count() > 1;
+		cmd.check(grb_bloom_upsample(&u1, &bloom, sharded ? graph.get_shard_plan().upsample0 : GrbRows{ 0, 0 }, cmd.get_stream_handle()),
+		          "grb_bloom_upsample(u0)");
+	}
 	const float *lum = ubo_res ? graph.get_physical_buffer_resource(*ubo_res).get<float>() : nullptr;
 	auto &out_view = graph.get_physical_texture_resource(*pass.get_color_outputs()[0]);
 	GrbImage out = out_view.as_grb();
@@ -213,15 +211,15 @@ void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &fr
 	auto res = std::make_shared<BloomResources>();
 	res->t = &bloom_pass.add_storage_texture_output("threshold", downsample_info);
 	res->d0 = &bloom_pass.add_storage_texture_output("downsample-0", level(0.25f));
-	{
-		// tonemap(N) reads upsample-0 while bloom(N+1) may already be writing it: two copies, like the HDR input
-		auto u0_info = level(0.25f);
-		if (RenderGraph::get_default_compute_queue() != RENDER_GRAPH_QUEUE_COMPUTE_BIT)
-			u0_info.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
-		res->u0 = &bloom_pass.add_storage_texture_output("upsample-0", u0_info);
-	}
 	res->d1 = &bloom_pass.add_storage_texture_output("downsample-1", level(0.125f));
-	res->u1 = &bloom_pass.add_storage_texture_output("upsample-1", level(0.125f));
+	{
+		// the tonemap pass of frame N reads upsample-1 (for its u0) while the pyramid of frame N+1 may already be
+		// writing it: two copies, like the HDR input
+		auto u1_info = level(0.125f);
+		if (RenderGraph::get_default_compute_queue() != RENDER_GRAPH_QUEUE_COMPUTE_BIT)
+			u1_info.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
+		res->u1 = &bloom_pass.add_storage_texture_output("upsample-1", u1_info);
+	}
 	res->d2 = &bloom_pass.add_storage_texture_output("downsample-2", level(0.0625f));
 	res->u2 = &bloom_pass.add_storage_texture_output("upsample-2", level(0.0625f));
 	res->d3 = &bloom_pass.add_storage_texture_output("downsample-3", level(0.03125f));
@@ -260,14 +258,15 @@ void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &fr
 		auto &tonemap = graph.add_pass("tonemap", RenderGraph::get_default_post_graphics_queue());
 		tonemap.add_color_output(output, tonemap_info);
 		auto &hdr_res = tonemap.add_texture_input(input);
-		auto &bloom_res = tonemap.add_texture_input("upsample-0");
+		auto &bloom_res = tonemap.add_storage_texture_output("upsample-0", level(0.25f));
+		auto *u1_res = &tonemap.add_texture_input("upsample-1");
 		const RenderBufferResource *ubo_res = nullptr;
 		if (options.dynamic_exposure)
 			ubo_res = &tonemap.add_uniform_input("average-luminance-updated");
-		tonemap.set_build_render_pass([&tonemap, &hdr_res, &bloom_res, ubo_res, iface, &graph](Vulkan::CommandBuffer &cmd) {
+		tonemap.set_build_render_pass([&tonemap, &hdr_res, &bloom_res, u1_res, ubo_res, iface, &graph](Vulkan::CommandBuffer &cmd) {
 			// FXAA downstream reads +-9 rows around a band: tonemap that halo too when a consumer declared it
 			unsigned halo = graph.find_pass("fxaa") ? 12u : 0u;
-			tonemap_build_render_pass(tonemap, cmd, hdr_res, bloom_res, ubo_res, iface, halo);
+			tonemap_build_render_pass(tonemap, cmd, hdr_res, bloom_res, u1_res, ubo_res, iface, halo);
 		});
 	}
 }
