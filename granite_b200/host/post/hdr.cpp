@@ -41,6 +41,19 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	auto img = [&](RenderTextureResource *res) { return graph.get_physical_texture_resource(*res).as_grb(); };
 	float *lum = r.lum ? graph.get_physical_buffer_resource(*r.lum).get<float>() : nullptr;
 
+	// When the post chain has its own stream and the HDR input was written on the main stream (the lighting pass),
+	// the full-machine first kernel of this pass is recorded on the MAIN stream, directly behind its producer and
+	// directly in front of the next lighting pass: a dependency that hops between streams costs 10 - 20 us of
+	// latency each way on an otherwise idle device, and this chain (lighting -> threshold + downsample -> next
+	// lighting) is the frame's critical path.  The rest of the pass stays on the post stream and waits for it.
+	Vulkan::Stream main_stream = cmd.get_device().get_stream();
+	static const bool head_on_post_stream = getenv("GRB_BLOOM_HEAD_ON_POST_STREAM") != nullptr;
+	const bool head_on_main = !head_on_post_stream && cmd.get_stream() != main_stream && graph.get_writer_stream(*r.hdr) == main_stream;
+	Vulkan::CommandBuffer head_cmd(cmd.get_device(), head_on_main ? main_stream : cmd.get_stream());
+	void *head_stream = head_cmd.get_stream_handle();
+	if (head_on_main)
+		graph.wait_mark("bloom-done", head_cmd); // last frame's tail (reads d0, writes the luminance) ended long ago: no latency
+
 	GrbImage hdr = img(r.hdr), t = img(r.t), d0 = img(r.d0), d1 = img(r.d1), d2 = img(r.d2), d3 = img(r.d3);
 	GrbImage u2 = img(r.u2), u1 = img(r.u1);
 	const bool sharded = graph.is_sharded() && graph.get_shard_count() > 1;
@@ -64,25 +77,28 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	{
 		const unsigned self = graph.get_collectives()->get_rank();
 		int32_t rc = grb_bloom_threshold_downsample_to_peers(&hdr, lum, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch,
-		                                                     slot.counter, d0_rows, stream);
+		                                                     slot.counter, d0_rows, head_stream);
 		if (rc == GRB_ERR_UNSUPPORTED_FORMAT)
 		{
-			cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
-			rc = grb_bloom_downsample_to_peers(&t, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch, slot.counter, d0_rows, stream);
+			cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, head_stream), "grb_bloom_threshold");
+			rc = grb_bloom_downsample_to_peers(&t, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch, slot.counter, d0_rows,
+			                                   head_stream);
 		}
 		cmd.check(rc, "grb_bloom_downsample_to_peers");
 		d0.data = slot.images[self]; // the pyramid tail reads the exchanged copy
 	}
-	else if (grb_bloom_threshold_downsample(&hdr, lum, keep_threshold ? &t : nullptr, &d0, d0_rows, stream) != GRB_OK)
+	else if (grb_bloom_threshold_downsample(&hdr, lum, keep_threshold ? &t : nullptr, &d0, d0_rows, head_stream) != GRB_OK)
 	{
-		cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
-		cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, stream), "grb_bloom_downsample(d0)");
+		cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, head_stream), "grb_bloom_threshold");
+		cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, head_stream), "grb_bloom_downsample(d0)");
 	}
 	// Everything above wants the whole machine for a few tens of microseconds; everything below is latency-bound
 	// and small.  The next frame's lighting pass (a persistent kernel that takes every SM it is given) waits for this
 	// mark, so the two do not fight over SMs, and starts while the pyramid tail below -- already resident on a
 	// few SMs, see max_ctas -- runs beside it.
-	graph.signal_mark("bloom-head", cmd);
+	graph.signal_mark("bloom-head", head_cmd);
+	if (head_on_main)
+		graph.wait_mark("bloom-head", cmd);
 
 	if (sharded && !peer_stores)
 	{
@@ -159,6 +175,7 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 		Vulkan::cuda_ok(cudaMemcpyAsync(graph.get_physical_buffer_resource(*r.lum_updated).get<float>(), lum, 3 * sizeof(float), cudaMemcpyDeviceToDevice,
 		                                reinterpret_cast<cudaStream_t>(cmd.get_stream())),
 		                "cudaMemcpyAsync(average-luminance-updated)");
+	graph.signal_mark("bloom-done", cmd);
 }
 
 void tonemap_build_render_pass(RenderPass &pass, Vulkan::CommandBuffer &cmd, const RenderTextureResource &hdr_res,
