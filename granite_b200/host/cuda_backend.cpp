@@ -144,15 +144,18 @@ Stream Device::get_queue_stream(unsigned idx)
 		// (post chain), and with priority the block scheduler hands them SM slots as the long,
 		// ALU-bound lighting grid on the main stream retires CTAs -- without it a later kernel only
 		// starts once the earlier grid has no CTAs left to issue, and nothing overlaps.
-		// The tonemap / AA stream (index 2) is the exception: lowest priority, BELOW the main stream when that was
-		// created one level up (a caller-supplied main stream keeps whatever priority it has).  Its full-resolution
-		// kernels become ready while the next frame's lighting pass is running; at high priority they would take
-		// every SM slot that frees up and crawl there, at low priority they wait for the gap between two
-		// lighting passes and run beside the bloom head.
+		// The tonemap / AA stream (index 2) is the exception: it gets the priority of an own main stream (one level
+		// above the lowest; GRB_POST_GRAPHICS_PRIORITY overrides).  Its full-resolution kernels become ready while the
+		// next frame's lighting pass is running; at high priority they would take every SM slot that frees up and crawl
+		// there.  At the lighting stream's priority the CTAs of that pass which are still waiting for an SM go first,
+		// and the tonemap runs in the gap between two lighting passes, sharing the machine with the bloom head.
 		int least = 0, greatest = 0;
 		cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		int post_graphics = least > greatest ? least - 1 : least;
+		if (const char *e = getenv("GRB_POST_GRAPHICS_PRIORITY"))
+			post_graphics = atoi(e);
 		cudaStream_t s;
-		if (cuda_ok(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, idx == 2 ? least : greatest), "cudaStreamCreate(side)"))
+		if (cuda_ok(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, idx == 2 ? post_graphics : greatest), "cudaStreamCreate(side)"))
 			side = s;
 		else
 			side = stream;
