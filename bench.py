@@ -278,10 +278,7 @@ def main():
     scene = synth.make_scene(w, h)
     lights = synth.make_lights(n_lights, aspect=w / h)
     post = {"none": viewer.AA_NONE, "taa+fxaa": viewer.AA_TAA_HIGH_PLUS_FXAA}[aa]
-    # One priority level above the lowest: the library's tonemap / AA stream sits below the stream that carries the
-    # lighting pass (host/cuda_backend.cpp), so its kernels run in the gap between two lighting passes.
-    stream = torch.cuda.Stream(priority=-1)
-    torch.cuda.set_stream(stream)
+    stream = torch.cuda.current_stream()
 
     def make_viewer(timestamps, pipelined_io=False, use_bands=None):
         v = viewer.Viewer(w, h, post_aa=post, hdr_bloom=bloom, dynamic_exposure=bloom, cuda_device=local_rank, timestamps=timestamps,
@@ -476,8 +473,8 @@ def main():
     vt.sync()
     timings = {k: ms / max(c, 1) for k, (ms, c) in vt.collect_timings().items()}
     # bloom-compute: the fused threshold + d0 kernel (which also stores the band to the peers when row-sharded) and one
-    # cooperative launch for d1, d2, d3, luminance, u2, u1 (which also waits for the peers' bands); tonemap: u0 + tonemap
-    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 2, "tonemap": 2 if bloom else 1, "bloom-disabled": 0, "taa-resolve": 1, "fxaa": 1,
+    # cooperative launch for d1, d2, d3, luminance, u2, u1, u0 (which also waits for the peers' bands)
+    n_launch = {"clustering-bindless": 4, "lighting": 1, "bloom-compute": 2, "tonemap": 1, "bloom-disabled": 0, "taa-resolve": 1, "fxaa": 1,
                 "gbuffer": 0, "mv": 0}
     launches_per_frame = sum(n_launch.get(p, 0) for p in vt.pass_names())
     vt.close()

@@ -95,11 +95,8 @@ Device::Device(int cuda_device_index, Stream stream_) : index(cuda_device_index)
 		throw std::runtime_error("granite_b200: cannot select the CUDA device");
 	if (!stream)
 	{
-		// one level above the lowest priority: the tonemap / AA stream (index 2) sits below the main stream, see get_queue_stream
-		int least = 0, greatest = 0;
-		cudaDeviceGetStreamPriorityRange(&least, &greatest);
 		cudaStream_t s;
-		if (!cuda_ok(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, least > greatest ? least - 1 : least), "cudaStreamCreate"))
+		if (!cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate"))
 			throw std::runtime_error("granite_b200: cannot create a stream");
 		stream = s;
 		owns_stream = true;
@@ -144,18 +141,10 @@ Stream Device::get_queue_stream(unsigned idx)
 		// (post chain), and with priority the block scheduler hands them SM slots as the long,
 		// ALU-bound lighting grid on the main stream retires CTAs -- without it a later kernel only
 		// starts once the earlier grid has no CTAs left to issue, and nothing overlaps.
-		// The tonemap / AA stream (index 2) is the exception: it gets the priority of an own main stream (one level
-		// above the lowest; GRB_POST_GRAPHICS_PRIORITY overrides).  Its full-resolution kernels become ready while the
-		// next frame's lighting pass is running; at high priority they would take every SM slot that frees up and crawl
-		// there.  At the lighting stream's priority the CTAs of that pass which are still waiting for an SM go first,
-		// and the tonemap runs in the gap between two lighting passes, sharing the machine with the bloom head.
 		int least = 0, greatest = 0;
 		cudaDeviceGetStreamPriorityRange(&least, &greatest);
-		int post_graphics = least > greatest ? least - 1 : least;
-		if (const char *e = getenv("GRB_POST_GRAPHICS_PRIORITY"))
-			post_graphics = atoi(e);
 		cudaStream_t s;
-		if (cuda_ok(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, idx == 2 ? post_graphics : greatest), "cudaStreamCreate(side)"))
+		if (cuda_ok(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest), "cudaStreamCreate(side)"))
 			side = s;
 		else
 			side = stream;

@@ -27,10 +27,9 @@ namespace
 {
 struct BloomResources
 {
-	RenderTextureResource *t, *d0, *d1, *u1, *d2, *u2, *d3, *hdr;
+	RenderTextureResource *t, *d0, *u0, *d1, *u1, *d2, *u2, *d3, *hdr;
 	const RenderBufferResource *lum;
 	const RenderBufferResource *lum_grid;
-	const RenderBufferResource *lum_updated; // this frame's copy for the tonemap pass (alternates between two buffers)
 };
 
 GrbRows all_rows() { return GrbRows{ 0, 0 }; }
@@ -41,21 +40,8 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	auto img = [&](RenderTextureResource *res) { return graph.get_physical_texture_resource(*res).as_grb(); };
 	float *lum = r.lum ? graph.get_physical_buffer_resource(*r.lum).get<float>() : nullptr;
 
-	// GRB_BLOOM_HEAD_ON_MAIN=1 records the full-machine first kernel of this pass on the MAIN stream, directly behind
-	// the lighting pass that produced its input and in front of the next one (no stream hop on that chain).  Measured
-	// at 4K: slower (0.464 vs 0.448 ms per frame) -- behind the head the tonemap of the previous frame, which the next
-	// lighting pass also has to wait for (it overwrites that frame's HDR image), then runs alone instead of sharing
-	// the 15 us the hop costs.  Kept as a switch.
-	Vulkan::Stream main_stream = cmd.get_device().get_stream();
-	static const bool head_on_main_stream = getenv("GRB_BLOOM_HEAD_ON_MAIN") != nullptr;
-	const bool head_on_main = head_on_main_stream && cmd.get_stream() != main_stream && graph.get_writer_stream(*r.hdr) == main_stream;
-	Vulkan::CommandBuffer head_cmd(cmd.get_device(), head_on_main ? main_stream : cmd.get_stream());
-	void *head_stream = head_cmd.get_stream_handle();
-	if (head_on_main)
-		graph.wait_mark("bloom-done", head_cmd); // last frame's tail (reads d0, writes the luminance) ended long ago: no latency
-
 	GrbImage hdr = img(r.hdr), t = img(r.t), d0 = img(r.d0), d1 = img(r.d1), d2 = img(r.d2), d3 = img(r.d3);
-	GrbImage u2 = img(r.u2), u1 = img(r.u1);
+	GrbImage u2 = img(r.u2), u1 = img(r.u1), u0 = img(r.u0);
 	const bool sharded = graph.is_sharded() && graph.get_shard_count() > 1;
 
 	// Rows of each band-only level (shard_plan.hpp derives them from the rows this rank owns).
@@ -77,28 +63,25 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	{
 		const unsigned self = graph.get_collectives()->get_rank();
 		int32_t rc = grb_bloom_threshold_downsample_to_peers(&hdr, lum, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch,
-		                                                     slot.counter, d0_rows, head_stream);
+		                                                     slot.counter, d0_rows, stream);
 		if (rc == GRB_ERR_UNSUPPORTED_FORMAT)
 		{
-			cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, head_stream), "grb_bloom_threshold");
-			rc = grb_bloom_downsample_to_peers(&t, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch, slot.counter, d0_rows,
-			                                   head_stream);
+			cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
+			rc = grb_bloom_downsample_to_peers(&t, &d0, slot.images, slot.flags, (int32_t)slot.count, (int32_t)self, slot.epoch, slot.counter, d0_rows, stream);
 		}
 		cmd.check(rc, "grb_bloom_downsample_to_peers");
 		d0.data = slot.images[self]; // the pyramid tail reads the exchanged copy
 	}
-	else if (grb_bloom_threshold_downsample(&hdr, lum, keep_threshold ? &t : nullptr, &d0, d0_rows, head_stream) != GRB_OK)
+	else if (grb_bloom_threshold_downsample(&hdr, lum, keep_threshold ? &t : nullptr, &d0, d0_rows, stream) != GRB_OK)
 	{
-		cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, head_stream), "grb_bloom_threshold");
-		cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, head_stream), "grb_bloom_downsample(d0)");
+		cmd.check(grb_bloom_threshold(&hdr, lum, &t, t_rows, stream), "grb_bloom_threshold");
+		cmd.check(grb_bloom_downsample(&t, nullptr, 0.0f, &d0, d0_rows, stream), "grb_bloom_downsample(d0)");
 	}
 	// Everything above wants the whole machine for a few tens of microseconds; everything below is latency-bound
 	// and small.  The next frame's lighting pass (a persistent kernel that takes every SM it is given) waits for this
 	// mark, so the two do not fight over SMs, and starts while the pyramid tail below -- already resident on a
 	// few SMs, see max_ctas -- runs beside it.
-	graph.signal_mark("bloom-head", head_cmd);
-	if (head_on_main)
-		graph.wait_mark("bloom-head", cmd);
+	graph.signal_mark("bloom-head", cmd);
 
 	if (sharded && !peer_stores)
 	{
@@ -120,11 +103,10 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 	// the reference split (band partial sums + all-reduce) and the separate calls
 	const bool nccl_luminance = lum && sharded && r.lum_grid && !peer_stores;
 
-	// Everything below 1/4 resolution -- d1, d2, d3, luminance, u2, u1 -- is one cooperative launch (grid barriers
-	// between the levels); separate dispatches when that is not available.  Row-sharded frames: the kernel itself
-	// waits for the peers' d0 bands.  The last upsample, u0, is issued by the tonemap pass (below): at 4K it is 80 % of
-	// the texels below 1/4 resolution, wants the whole machine for 14 us, and so belongs with the other
-	// full-machine kernels in the gap between two lighting passes, not beside one.
+	// Everything below 1/4 resolution -- d1, d2, d3, luminance, u2, u1 -- and the last upsample u0 (own band + the
+	// tonemap halo when row-sharded) is one cooperative launch (grid barriers between the levels); separate
+	// dispatches when that is not available.  Row-sharded frames: the kernel itself waits for the peers' d0 bands.
+	GrbRows u0_rows = sharded ? plan.upsample0 : all_rows();
 	bool tail_fused = false, peers_awaited = false;
 	if (!nccl_luminance)
 	{
@@ -133,6 +115,8 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 			return e ? atoi(e) : 16;
 		}();
 		GrbBloomTailOptions opt = {};
+		opt.u0 = &u0;
+		opt.u0_rows = u0_rows;
 		if (peer_stores)
 		{
 			opt.peer_flags = slot.flags[graph.get_collectives()->get_rank()];
@@ -169,31 +153,18 @@ void bloom_build_compute(Vulkan::CommandBuffer &cmd, RenderGraph &graph, const F
 		cmd.check(grb_bloom_upsample(&d3, &u2, all_rows(), stream), "grb_bloom_upsample(u2)");
 		cmd.check(grb_bloom_upsample(&u2, &u1, all_rows(), stream), "grb_bloom_upsample(u1)");
 	}
-	// The tonemap pass of this frame runs while the NEXT frame's pyramid is already updating the average luminance
-	// in place: it reads its own copy.
-	if (lum && r.lum_updated)
-		Vulkan::cuda_ok(cudaMemcpyAsync(graph.get_physical_buffer_resource(*r.lum_updated).get<float>(), lum, 3 * sizeof(float), cudaMemcpyDeviceToDevice,
-		                                reinterpret_cast<cudaStream_t>(cmd.get_stream())),
-		                "cudaMemcpyAsync(average-luminance-updated)");
-	graph.signal_mark("bloom-done", cmd);
+	// u0 feeds the tonemap's bilinear bloom tap: own band (+ the tonemap halo FXAA needs) at 1/4 res
+	if (!tail_fused)
+		cmd.check(grb_bloom_upsample_exact(&u1, &u0, u0_rows, stream), "grb_bloom_upsample(u0)"); // the arithmetic the fused tail uses
 }
 
 void tonemap_build_render_pass(RenderPass &pass, Vulkan::CommandBuffer &cmd, const RenderTextureResource &hdr_res,
-                               const RenderTextureResource &bloom_res, const RenderTextureResource *u1_res, const RenderBufferResource *ubo_res,
-                               const HDRDynamicExposureInterface *iface, unsigned)
+                               const RenderTextureResource &bloom_res, const RenderBufferResource *ubo_res, const HDRDynamicExposureInterface *iface,
+                               unsigned)
 {
 	auto &graph = pass.get_graph();
 	GrbImage hdr = graph.get_physical_texture_resource(hdr_res).as_grb();
 	GrbImage bloom = graph.get_physical_texture_resource(bloom_res).as_grb();
-	if (u1_res)
-	{
-		// bloom_upsample_build_compute for "upsample-0" (hdr.cpp:376): the bilinear bloom tap below reads it; own
-		// band (+ the tonemap halo FXAA needs) at 1/4 resolution when row-sharded
-		GrbImage u1 = graph.get_physical_texture_resource(*u1_res).as_grb();
-		const bool sharded = graph.is_sharded() && graph.get_shard_count() > 1;
-		cmd.check(grb_bloom_upsample(&u1, &bloom, sharded ? graph.get_shard_plan().upsample0 : GrbRows{ 0, 0 }, cmd.get_stream_handle()),
-		          "grb_bloom_upsample(u0)");
-	}
 	const float *lum = ubo_res ? graph.get_physical_buffer_resource(*ubo_res).get<float>() : nullptr;
 	auto &out_view = graph.get_physical_texture_resource(*pass.get_color_outputs()[0]);
 	GrbImage out = out_view.as_grb();
@@ -228,30 +199,17 @@ void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &fr
 	auto res = std::make_shared<BloomResources>();
 	res->t = &bloom_pass.add_storage_texture_output("threshold", downsample_info);
 	res->d0 = &bloom_pass.add_storage_texture_output("downsample-0", level(0.25f));
+	res->u0 = &bloom_pass.add_storage_texture_output("upsample-0", level(0.25f));
 	res->d1 = &bloom_pass.add_storage_texture_output("downsample-1", level(0.125f));
-	{
-		// the tonemap pass of frame N reads upsample-1 (for its u0) while the pyramid of frame N+1 may already be
-		// writing it: two copies, like the HDR input
-		auto u1_info = level(0.125f);
-		if (RenderGraph::get_default_compute_queue() != RENDER_GRAPH_QUEUE_COMPUTE_BIT)
-			u1_info.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
-		res->u1 = &bloom_pass.add_storage_texture_output("upsample-1", u1_info);
-	}
+	res->u1 = &bloom_pass.add_storage_texture_output("upsample-1", level(0.125f));
 	res->d2 = &bloom_pass.add_storage_texture_output("downsample-2", level(0.0625f));
 	res->u2 = &bloom_pass.add_storage_texture_output("upsample-2", level(0.0625f));
 	res->d3 = &bloom_pass.add_storage_texture_output("downsample-3", level(0.03125f));
 	res->lum = nullptr;
 	res->lum_grid = nullptr;
-	res->lum_updated = nullptr;
 	if (options.dynamic_exposure)
 	{
 		res->lum = &bloom_pass.add_storage_output("average-luminance", buffer_info);
-		// what the reference's fragment path calls "average-luminance-updated" (hdr.cpp:519-533): the value the tonemap
-		// pass of THIS frame reads
-		BufferInfo updated_info = buffer_info;
-		if (RenderGraph::get_default_compute_queue() != RENDER_GRAPH_QUEUE_COMPUTE_BIT)
-			updated_info.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
-		res->lum_updated = &bloom_pass.add_storage_output("average-luminance-updated", updated_info);
 		// scratch for the row-sharded luminance sum: the (d3/2) sample grid (hdr.cpp:78-79), sized from
 		// the backbuffer: d3 = ceil(dim / 32)
 		BufferInfo grid_info;
@@ -275,15 +233,14 @@ void setup_hdr_postprocess_compute(RenderGraph &graph, const FrameParameters &fr
 		auto &tonemap = graph.add_pass("tonemap", RenderGraph::get_default_post_graphics_queue());
 		tonemap.add_color_output(output, tonemap_info);
 		auto &hdr_res = tonemap.add_texture_input(input);
-		auto &bloom_res = tonemap.add_storage_texture_output("upsample-0", level(0.25f));
-		auto *u1_res = &tonemap.add_texture_input("upsample-1");
+		auto &bloom_res = tonemap.add_texture_input("upsample-0");
 		const RenderBufferResource *ubo_res = nullptr;
 		if (options.dynamic_exposure)
-			ubo_res = &tonemap.add_uniform_input("average-luminance-updated");
-		tonemap.set_build_render_pass([&tonemap, &hdr_res, &bloom_res, u1_res, ubo_res, iface, &graph](Vulkan::CommandBuffer &cmd) {
+			ubo_res = &tonemap.add_uniform_input("average-luminance");
+		tonemap.set_build_render_pass([&tonemap, &hdr_res, &bloom_res, ubo_res, iface, &graph](Vulkan::CommandBuffer &cmd) {
 			// FXAA downstream reads +-9 rows around a band: tonemap that halo too when a consumer declared it
 			unsigned halo = graph.find_pass("fxaa") ? 12u : 0u;
-			tonemap_build_render_pass(tonemap, cmd, hdr_res, bloom_res, u1_res, ubo_res, iface, halo);
+			tonemap_build_render_pass(tonemap, cmd, hdr_res, bloom_res, ubo_res, iface, halo);
 		});
 	}
 }

@@ -39,7 +39,7 @@ def main():
     w, h, n_lights, aa, _ = bench.WORKLOADS[args.workload]
     scene = synth.make_scene(w, h)
     lights = synth.make_lights(n_lights, aspect=w / h)
-    stream = torch.cuda.Stream(priority=-1)
+    stream = torch.cuda.Stream()
     v = viewer.Viewer(w, h, cuda_device=local_rank, timestamps=2, stream=stream.cuda_stream)
     v.set_camera(scene.projection, scene.view)
     v.set_directional(scene.dir_color, scene.dir_direction)
