@@ -29,6 +29,7 @@ struct NcclApi
 	int (*GetUniqueId)(NcclUniqueId *) = nullptr;
 	int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int) = nullptr;
 	int (*CommDestroy)(ncclComm_t) = nullptr;
+	int (*CommAbort)(ncclComm_t) = nullptr; // optional
 	int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, void *) = nullptr;
 	int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, void *) = nullptr;
 	int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, void *) = nullptr;
@@ -69,6 +70,7 @@ NcclApi &api()
 		GRB_SYM(GroupEnd, "ncclGroupEnd")
 		GRB_SYM(GetErrorString, "ncclGetErrorString")
 #undef GRB_SYM
+		a.CommAbort = reinterpret_cast<decltype(a.CommAbort)>(dlsym(a.handle, "ncclCommAbort"));
 	});
 	return a;
 }
@@ -87,6 +89,22 @@ NcclCollectives::~NcclCollectives()
 	release_peer_exchange();
 	if (comm && api().CommDestroy)
 		api().CommDestroy(comm);
+}
+
+// A collective that failed leaves the communicator in an undefined state and its peers possibly blocked inside
+// the same collective: abort it (ncclCommAbort frees the resources without waiting for outstanding operations) so
+// that every later call on this rank fails fast -- the sharded passes then report errors frame by frame, the
+// reference's LOGE-and-continue convention -- instead of queueing more work behind a dead collective.
+bool NcclCollectives::collective_failed(const char *what)
+{
+	Vulkan::log_error("%s failed: aborting the communicator of rank %u; row-sharded passes will report errors from here on.\n", what, rank);
+	if (comm)
+	{
+		if (api().CommAbort)
+			api().CommAbort(comm);
+		comm = nullptr;
+	}
+	return false;
 }
 
 bool NcclCollectives::get_unique_id(unsigned char out[NcclUniqueIdBytes], std::string &error)
@@ -146,14 +164,16 @@ bool NcclCollectives::all_gather_rows(Vulkan::CommandBuffer &cmd, Vulkan::ImageV
 		ok = nccl_ok(a.Broadcast(p, p, bytes, ncclInt8, (int)r, comm, cmd.get_stream_handle()), "ncclBroadcast");
 	}
 	ok = nccl_ok(a.GroupEnd(), "ncclGroupEnd") && ok;
-	return ok;
+	return ok ? true : collective_failed("all_gather_rows");
 }
 
 bool NcclCollectives::all_reduce_sum(Vulkan::CommandBuffer &cmd, float *data, size_t count)
 {
 	if (!comm)
 		return false;
-	return nccl_ok(api().AllReduce(data, data, count, ncclFloat32, ncclSum, comm, cmd.get_stream_handle()), "ncclAllReduce");
+	if (nccl_ok(api().AllReduce(data, data, count, ncclFloat32, ncclSum, comm, cmd.get_stream_handle()), "ncclAllReduce"))
+		return true;
+	return collective_failed("all_reduce_sum");
 }
 
 // ----------------------------------------------------------------------------- peer exchange

@@ -30,6 +30,7 @@ public:
 	bool peer_exchange_begin_frame(size_t image_bytes, PeerSlot &slot) override;
 
 private:
+	bool collective_failed(const char *what);
 	void *comm = nullptr;
 	unsigned rank = 0, world = 1;
 
