@@ -79,6 +79,8 @@ void LightClusterer::setup_render_pass_dependencies(RenderGraph &, RenderPass &t
 	target.add_storage_read_only_input("cluster-bitmask");
 	target.add_storage_read_only_input("cluster-range");
 	target.add_storage_read_only_input("cluster-transforms");
+	// the shadow atlas is managed outside the graph (clusterer.cpp:92); a no-op while nothing registers it
+	target.add_external_lock("bindless-shadowmaps", VK_PIPELINE_STAGE_FRAGMENT_SHADER_BIT, VK_ACCESS_2_SHADER_SAMPLED_READ_BIT);
 }
 
 // renderer/lights/clusterer.cpp:107-116

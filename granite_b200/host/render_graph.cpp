@@ -127,6 +127,78 @@ RenderBufferResource &RenderPass::add_storage_read_only_input(const std::string 
 	return add_uniform_input(name, stages);
 }
 
+void RenderPass::add_proxy_output(const std::string &name, VkPipelineStageFlags2 stages, VkAccessFlags2, const std::string &input)
+{
+	if (stages == 0)
+		throw std::logic_error("add_proxy_output: stages must not be 0.");
+	auto &res = graph.get_proxy_resource(name);
+	res.written_in_pass(index);
+	writes.push_back(&res);
+	if (!input.empty())
+	{
+		auto &input_res = graph.get_proxy_resource(input);
+		input_res.read_in_pass(index);
+		reads.push_back(&input_res);
+	}
+}
+
+void RenderPass::add_proxy_input(const std::string &name, VkPipelineStageFlags2 stages, VkAccessFlags2)
+{
+	if (stages == 0)
+		throw std::logic_error("add_proxy_input: stages must not be 0.");
+	auto &res = graph.get_proxy_resource(name);
+	res.read_in_pass(index);
+	reads.push_back(&res);
+}
+
+void RenderPass::add_external_lock(const std::string &name, VkPipelineStageFlags2 stages, VkAccessFlags2 access)
+{
+	auto *iface = graph.find_external_lock_interface(name);
+	if (!iface)
+		return;
+	iface->mark_access_in_queue(queue, stages, access);
+	for (auto &l : lock_interfaces)
+		if (l.iface == iface)
+		{
+			l.stages |= stages;
+			return;
+		}
+	lock_interfaces.push_back({ iface, stages });
+}
+
+Vulkan::Event RenderPassExternalLockInterface::external_acquire_event()
+{
+	std::lock_guard<std::mutex> hold(lock);
+	return produced;
+}
+
+void RenderPassExternalLockInterface::external_release_event(Vulkan::Event event)
+{
+	if (!event)
+		return;
+	std::lock_guard<std::mutex> hold(lock);
+	for (auto e : consumed)
+		if (e == event)
+			return;
+	consumed.push_back(event);
+}
+
+void RenderPassExternalLockInterface::acquire_internal(Vulkan::Device &device, Vulkan::Stream stream)
+{
+	std::lock_guard<std::mutex> hold(lock);
+	for (auto e : consumed)
+		device.stream_wait_event(stream, e);
+	consumed.clear();
+}
+
+void RenderPassExternalLockInterface::release_internal(Vulkan::Device &device, Vulkan::Stream stream)
+{
+	std::lock_guard<std::mutex> hold(lock);
+	if (!produced)
+		produced = device.request_event();
+	device.record_event_on(produced, stream);
+}
+
 RenderBufferResource &RenderPass::add_storage_output(const std::string &name, const BufferInfo &info, const std::string &input)
 {
 	auto &res = graph.get_or_create_buffer(name);
@@ -226,6 +298,13 @@ RenderBufferResource &RenderGraph::get_or_create_buffer(const std::string &name)
 RenderTextureResource &RenderGraph::get_texture_resource(const std::string &name) { return get_or_create_texture(name); }
 RenderBufferResource &RenderGraph::get_buffer_resource(const std::string &name) { return get_or_create_buffer(name); }
 
+RenderBufferResource &RenderGraph::get_proxy_resource(const std::string &name)
+{
+	auto &res = get_or_create_buffer(name);
+	res.set_proxy(true);
+	return res;
+}
+
 RenderPass &RenderGraph::add_pass(const std::string &name, RenderGraphQueueFlagBits queue)
 {
 	auto itr = pass_to_index.find(name);
@@ -261,6 +340,7 @@ void RenderGraph::reset()
 	physical_buffers.clear();
 	last_access.clear();
 	marks.clear();
+	external_lock_interfaces.clear();
 	pass_done_events.clear();
 	physical_pingpong_spare.clear();
 	physical_buffer_spare.clear();
@@ -488,7 +568,11 @@ const void *RenderGraph::physical_key(const RenderResource &res, bool history)
 	if (phys == RenderResource::Unused)
 		return nullptr;
 	if (res.get_type() == RenderResource::Type::Buffer)
+	{
+		if (static_cast<const RenderBufferResource &>(res).is_proxy())
+			return &res; // no memory behind it: the resource object itself is the key the ordering hangs on
 		return physical_buffers[phys] ? physical_buffers[phys].get() : nullptr;
+	}
 	auto &view = history ? physical_history_attachments[phys] : physical_attachments[phys];
 	return view ? static_cast<const void *>(&view->get_image()) : nullptr;
 }
@@ -563,6 +647,9 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 				wait_for(physical_key(*h, true), false);
 			for (auto &name : pass.get_wait_marks())
 				wait_mark(name, cmd);
+			for (auto &l : pass.get_lock_interfaces())
+				if (Vulkan::Event e = l.iface->external_acquire_event())
+					dev.stream_wait_event(stream, e);
 		}
 
 		Vulkan::Event begin = nullptr, end = nullptr;
@@ -587,6 +674,8 @@ void RenderGraph::enqueue_render_passes(Vulkan::Device &dev, TaskComposer &compo
 		if (!pass_done_events[p][slot])
 			pass_done_events[p][slot] = dev.request_event();
 		dev.record_event_on(pass_done_events[p][slot], stream);
+		for (auto &l : pass.get_lock_interfaces())
+			l.iface->external_release_event(pass_done_events[p][slot]);
 		for (auto *r : pass.get_all_reads())
 			mark(physical_key(*r, false), false);
 		for (auto *w : pass.get_all_writes())

@@ -18,6 +18,7 @@
 #include <array>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -114,6 +115,38 @@ enum RenderGraphQueueFlagBits
 };
 using RenderGraphQueueFlags = uint32_t;
 
+// A resource managed OUTSIDE the graph (the reference's clustered shadow atlas, its scene transform buffer:
+// render_graph.hpp:76-126), which passes of the graph read.  The reference hands Vulkan semaphores back and forth;
+// here they are CUDA events: the owner records one behind its writes (release_internal), consumer passes declared
+// with RenderPass::add_external_lock(name, ...) make their stream wait for it and hand back the event recorded
+// behind their own work, and the owner's next acquire_internal waits for those before it writes again.
+class RenderPassExternalLockInterface
+{
+public:
+	virtual ~RenderPassExternalLockInterface() = default;
+	virtual const char *get_ident() const { return "external-lock"; }
+
+	// consumer side (called by the graph while it records a pass)
+	Vulkan::Event external_acquire_event();
+	void external_release_event(Vulkan::Event event);
+	// External accesses are read-only; the reference records which queues touch the resource, the stream order
+	// plus the two calls above make that unnecessary here.  Kept so that builder code compiles unchanged.
+	void mark_access_in_queue(RenderGraphQueueFlagBits, VkPipelineStageFlags2, VkAccessFlags2) { foreign_access = true; }
+	bool has_foreign_access() const { return foreign_access; }
+
+protected:
+	// owner side (the derived class calls these around its own work on `stream`)
+	void acquire_internal(Vulkan::Device &device, Vulkan::Stream stream);
+	void release_internal(Vulkan::Device &device, Vulkan::Stream stream);
+
+private:
+	std::mutex lock;
+	Vulkan::Event produced = nullptr;            // recorded by release_internal
+	std::vector<Vulkan::Event> consumed;         // handed back by consumer passes since the last acquire_internal
+	bool foreign_access = false;
+};
+
+
 enum AttachmentInfoFlagBits
 {
 	ATTACHMENT_INFO_PERSISTENT_BIT = 1 << 0,
@@ -203,9 +236,13 @@ public:
 	explicit RenderBufferResource(unsigned index_) : RenderResource(RenderResource::Type::Buffer, index_) {}
 	void set_buffer_info(const BufferInfo &info_) { info = info_; }
 	const BufferInfo &get_buffer_info() const { return info; }
+	// a proxy has no memory (size 0): it exists for the ordering its writer / readers imply
+	void set_proxy(bool enable) { proxy = enable; }
+	bool is_proxy() const { return proxy; }
 
 private:
 	BufferInfo info;
+	bool proxy = false;
 };
 
 class RenderTextureResource : public RenderResource
@@ -241,6 +278,22 @@ public:
 	RenderBufferResource &add_transfer_output(const std::string &name, const BufferInfo &info);
 	RenderTextureResource &add_storage_texture_output(const std::string &name, const AttachmentInfo &info, const std::string &input = "");
 	void add_fake_resource_write_alias(const std::string &from, const std::string &to);
+	// Buffers a raster pass reads through fixed-function stages (render_graph.hpp:509-511): plain read dependencies here.
+	RenderBufferResource &add_vertex_buffer_input(const std::string &name) { return add_uniform_input(name); }
+	RenderBufferResource &add_index_buffer_input(const std::string &name) { return add_uniform_input(name); }
+	RenderBufferResource &add_indirect_buffer_input(const std::string &name) { return add_uniform_input(name); }
+	// Proxy resources (render_graph.hpp:513-514, render_graph.cpp:305-343): no memory, only ordering -- the writer of
+	// a proxy runs before its readers, across streams too.
+	void add_proxy_output(const std::string &name, VkPipelineStageFlags2 stages, VkAccessFlags2 access, const std::string &input = "");
+	void add_proxy_input(const std::string &name, VkPipelineStageFlags2 stages, VkAccessFlags2 access);
+	// render_graph.cpp:390-411: no-op unless RenderGraph::add_external_lock_interface registered `name`.
+	void add_external_lock(const std::string &name, VkPipelineStageFlags2 stages, VkAccessFlags2 access);
+	struct AccessedExternalLockInterface
+	{
+		RenderPassExternalLockInterface *iface;
+		VkPipelineStageFlags2 stages;
+	};
+	const std::vector<AccessedExternalLockInterface> &get_lock_interfaces() const { return lock_interfaces; }
 
 	const std::vector<RenderTextureResource *> &get_color_outputs() const { return color_outputs; }
 	const std::vector<RenderTextureResource *> &get_color_inputs() const { return color_inputs; }
@@ -323,6 +376,7 @@ private:
 	std::vector<RenderResource *> reads, writes;
 	std::vector<std::pair<RenderResource *, RenderResource *>> rmw_aliases; // (output, input it modifies in place)
 	std::vector<std::pair<RenderResource *, RenderResource *>> fake_aliases;
+	std::vector<AccessedExternalLockInterface> lock_interfaces;
 	friend class RenderGraph;
 };
 
@@ -390,6 +444,13 @@ public:
 	// pass being built (cmd's stream); wait_mark makes cmd's stream wait for the latest signal of that name (no-op
 	// before the first signal).  Used to phase the frame: the next lighting pass starts after this frame's
 	// full-machine bloom kernel, see host/post/hdr.cpp.
+	// render_graph.hpp:790-791 / render_graph.cpp:3771-3783
+	void add_external_lock_interface(const std::string &name, RenderPassExternalLockInterface *iface) { external_lock_interfaces[name] = iface; }
+	RenderPassExternalLockInterface *find_external_lock_interface(const std::string &name) const
+	{
+		auto itr = external_lock_interfaces.find(name);
+		return itr != external_lock_interfaces.end() ? itr->second : nullptr;
+	}
 	void signal_mark(const std::string &name, Vulkan::CommandBuffer &cmd);
 	void wait_mark(const std::string &name, Vulkan::CommandBuffer &cmd);
 	// Stream of the pass that writes `resource` (for host readbacks of a graph output).
@@ -453,6 +514,7 @@ private:
 		Vulkan::Stream stream = nullptr;
 	};
 	std::unordered_map<std::string, Mark> marks;
+	std::unordered_map<std::string, RenderPassExternalLockInterface *> external_lock_interfaces;
 	// one "pass done" event per pass per frame slot: a later frame re-recording the same event
 	// would turn "wait for frame N-2's reader" into "wait for frame N's", serialising the streams
 	enum { EventRing = 4 };
@@ -469,6 +531,7 @@ private:
 
 	RenderTextureResource &get_or_create_texture(const std::string &name);
 	RenderBufferResource &get_or_create_buffer(const std::string &name);
+	RenderBufferResource &get_proxy_resource(const std::string &name);
 	void traverse_dependencies(unsigned pass_index, std::vector<uint8_t> &state);
 	void build_physical_resources();
 	friend class RenderPass;

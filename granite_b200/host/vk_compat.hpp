@@ -26,6 +26,14 @@ constexpr VkBufferUsageFlags VK_BUFFER_USAGE_TRANSFER_DST_BIT = 0x2;
 constexpr VkBufferUsageFlags VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT = 0x10;
 constexpr VkBufferUsageFlags VK_BUFFER_USAGE_STORAGE_BUFFER_BIT = 0x20;
 constexpr VkImageUsageFlags VK_IMAGE_USAGE_SAMPLED_BIT = 0x4;
+// Stage / access masks the declaration surface takes (RenderPass::add_proxy_*, add_external_lock).  On this executor
+// a pass is a unit of stream order, so the values only have to be non-zero where the reference asserts that.
+constexpr VkPipelineStageFlags2 VK_PIPELINE_STAGE_2_PRE_RASTERIZATION_SHADERS_BIT = 0x4000000000ull;
+constexpr VkPipelineStageFlags2 VK_PIPELINE_STAGE_FRAGMENT_SHADER_BIT = 0x80ull;
+constexpr VkPipelineStageFlags2 VK_PIPELINE_STAGE_2_COMPUTE_SHADER_BIT = 0x800ull;
+constexpr VkAccessFlags2 VK_ACCESS_2_SHADER_SAMPLED_READ_BIT = 0x100000000ull;
+constexpr VkAccessFlags2 VK_ACCESS_2_SHADER_STORAGE_READ_BIT = 0x200000000ull;
+constexpr VkAccessFlags2 VK_ACCESS_2_SHADER_STORAGE_WRITE_BIT = 0x400000000ull;
 
 struct VkClearDepthStencilValue
 {

@@ -1,5 +1,7 @@
 // CPU-only checks of the RenderGraph declaration surface / bake logic (no device is touched:
 // bake() only needs one when a pass interface wants setup(device)).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -210,6 +212,111 @@ int main()
 			const mat4 &j = jitter.get_jitter_matrix();
 			CHECK(j[0][0] == 1.0f && j[1][1] == 1.0f && std::fabs(j[3][0]) <= 1.0f / 3840.0f + 1e-9f && std::fabs(j[3][1]) <= 1.0f / 2160.0f + 1e-9f);
 		}
+	}
+	// --- proxies order passes that share no memory; raster-stage buffer inputs are read dependencies ---
+	{
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo info;
+		info.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+		BufferInfo bi;
+		bi.size = 256;
+		auto &final_pass = graph.add_pass("final", RENDER_GRAPH_QUEUE_GRAPHICS_BIT); // declared first: order must come from the DAG
+		auto &prep = graph.add_pass("prep", RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT);
+		auto &geometry = graph.add_pass("geometry", RENDER_GRAPH_QUEUE_COMPUTE_BIT);
+		graph.add_pass("a", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("HDR-main", info);
+		prep.add_proxy_output("prep-done", VK_PIPELINE_STAGE_2_COMPUTE_SHADER_BIT, VK_ACCESS_2_SHADER_STORAGE_WRITE_BIT);
+		geometry.add_storage_output("vertices", bi);
+		geometry.add_storage_output("indices", bi);
+		geometry.add_storage_output("draws", bi);
+		final_pass.add_color_output("out", info);
+		final_pass.add_texture_input("HDR-main");
+		final_pass.add_proxy_input("prep-done", VK_PIPELINE_STAGE_FRAGMENT_SHADER_BIT, VK_ACCESS_2_SHADER_SAMPLED_READ_BIT);
+		final_pass.add_vertex_buffer_input("vertices");
+		final_pass.add_index_buffer_input("indices");
+		final_pass.add_indirect_buffer_input("draws");
+		CHECK(throws_logic_error([&] { final_pass.add_proxy_input("x", 0, 0); }));
+		graph.set_backbuffer_source("out");
+		graph.bake();
+		auto names = graph.get_baked_pass_names();
+		CHECK(names.size() == 4 && names.back() == "final");
+		auto has = [&](const char *n) { return std::find(names.begin(), names.end(), std::string(n)) != names.end(); };
+		CHECK(has("prep") && has("geometry") && has("a"));
+		CHECK(graph.get_buffer_resource("prep-done").is_proxy() && !graph.get_buffer_resource("vertices").is_proxy());
+	}
+
+	// --- external locks: a no-op until an interface is registered under the name (render_graph.cpp:390-411) ---
+	{
+		struct ShadowAtlas : RenderPassExternalLockInterface
+		{
+			const char *get_ident() const override { return "shadow-atlas"; }
+		} atlas;
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo info;
+		auto &lighting = graph.add_pass("lighting", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+		lighting.add_color_output("HDR-main", info);
+		lighting.add_external_lock("bindless-shadowmaps", VK_PIPELINE_STAGE_FRAGMENT_SHADER_BIT, VK_ACCESS_2_SHADER_SAMPLED_READ_BIT);
+		CHECK(lighting.get_lock_interfaces().empty() && graph.find_external_lock_interface("bindless-shadowmaps") == nullptr);
+		graph.add_external_lock_interface("bindless-shadowmaps", &atlas);
+		lighting.add_external_lock("bindless-shadowmaps", VK_PIPELINE_STAGE_FRAGMENT_SHADER_BIT, VK_ACCESS_2_SHADER_SAMPLED_READ_BIT);
+		lighting.add_external_lock("bindless-shadowmaps", VK_PIPELINE_STAGE_2_COMPUTE_SHADER_BIT, VK_ACCESS_2_SHADER_SAMPLED_READ_BIT);
+		CHECK(lighting.get_lock_interfaces().size() == 1 && lighting.get_lock_interfaces()[0].iface == &atlas);
+		CHECK(lighting.get_lock_interfaces()[0].stages == (VK_PIPELINE_STAGE_FRAGMENT_SHADER_BIT | VK_PIPELINE_STAGE_2_COMPUTE_SHADER_BIT));
+		CHECK(atlas.has_foreign_access() && atlas.external_acquire_event() == nullptr); // nothing produced yet: nothing to wait for
+		graph.reset();
+		CHECK(graph.find_external_lock_interface("bindless-shadowmaps") == nullptr);
+	}
+
+	// --- HDR10 output: lit scene + UI layer -> "pq10" (renderer/post/hdr.cpp:595-658) ---
+	{
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo hdr;
+		hdr.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+		graph.add_pass("lighting", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("HDR-main", hdr);
+		AttachmentInfo ui;
+		ui.format = VK_FORMAT_R8G8B8A8_UNORM;
+		auto &ui_pass = graph.add_pass("ui", RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
+		ui_pass.add_color_output("ui-temporary", ui);
+		ui_pass.add_texture_input("HDR-main");
+		VkHdrMetadataEXT rec709 = {};
+		rec709.displayPrimaryRed = { 0.640f, 0.330f };
+		rec709.displayPrimaryGreen = { 0.3f, 0.6f };
+		rec709.displayPrimaryBlue = { 0.150f, 0.060f };
+		rec709.whitePoint = { 0.3127f, 0.3290f };
+		rec709.maxContentLightLevel = 1000.0f;
+		setup_hdr10_pq_encoding(graph, "ui-output", "HDR-main", "ui-temporary", HDR10PQEncodingConfig{ 500.0f, 400.0f }, rec709);
+		graph.set_backbuffer_source("ui-output");
+		graph.bake();
+		CHECK(join(graph.get_baked_pass_names()) == "lighting,ui,pq10,");
+		auto out = graph.get_resource_dimensions(graph.get_texture_resource("ui-output"));
+		CHECK(out.format == VK_FORMAT_A2B10G10R10_UNORM_PACK32 && out.width == 3840 && out.height == 2160);
+		// Rec.709 -> Rec.709 is the identity; BT.2020 rows sum to 1 (white stays white)
+		mat4 ident = compute_rec709_to_display_primaries(rec709);
+		for (int c = 0; c < 4; c++)
+			for (int r = 0; r < 4; r++)
+				CHECK(std::fabs(ident[c][r] - (c == r ? 1.0f : 0.0f)) < 2e-7f);
+		VkHdrMetadataEXT bt2020 = rec709;
+		bt2020.displayPrimaryRed = { 0.708f, 0.292f };
+		bt2020.displayPrimaryGreen = { 0.170f, 0.797f };
+		bt2020.displayPrimaryBlue = { 0.131f, 0.046f };
+		mat4 m = compute_rec709_to_display_primaries(bt2020);
+		for (int r = 0; r < 3; r++)
+			CHECK(std::fabs(m[0][r] + m[1][r] + m[2][r] - 1.0f) < 1e-6f);
+		CHECK(m[0][0] > 0.62f && m[0][0] < 0.63f); // 0.6274: the familiar BT.709 -> BT.2020 coefficient
+	}
+
+	// --- queues map to streams: main, cluster build, tonemap / AA, bloom ---
+	{
+		CHECK(RenderGraph::queue_stream_index(RENDER_GRAPH_QUEUE_GRAPHICS_BIT) == 0 && RenderGraph::queue_stream_index(RENDER_GRAPH_QUEUE_COMPUTE_BIT) == 0);
+		CHECK(RenderGraph::queue_stream_index(RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT) == 1);
+		CHECK(RenderGraph::queue_stream_index(RENDER_GRAPH_QUEUE_ASYNC_GRAPHICS_BIT) == 2);
+		CHECK(RenderGraph::queue_stream_index(RENDER_GRAPH_QUEUE_ASYNC_POST_COMPUTE_BIT) == 3);
+		RenderGraph::set_async_post(true);
+		CHECK(RenderGraph::get_default_compute_queue() != RenderGraph::get_default_post_graphics_queue());
+		RenderGraph::set_async_post(false);
+		CHECK(RenderGraph::get_default_compute_queue() == RENDER_GRAPH_QUEUE_COMPUTE_BIT);
 	}
 	std::printf("render graph checks passed\n");
 	return 0;
