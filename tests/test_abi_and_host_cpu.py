@@ -159,6 +159,16 @@ def test_host_light_prep_is_byte_identical_to_oracle(built, oracle, n, spots):
     assert p.z_scale == 2.0 and p.z_max_index == 4095 and list(p.resolution_xy) == [128, 64] and p.num_lights_32 == (n + 31) // 32
 
 
+def test_hdr10_output_rejects_fxaa(built):
+    """FXAA reads the tonemapped 8-bit image; the HDR10 path (scene_viewer_application.cpp:1233-1288) has none."""
+    from granite_b200 import viewer
+
+    with pytest.raises(RuntimeError, match="FXAA"):
+        viewer.Viewer(640, 360, cuda_device=-1, post_aa=viewer.AA_FXAA, hdr10_output=True)
+    v = viewer.Viewer(640, 360, cuda_device=-1, post_aa=viewer.AA_TAA_HIGH, hdr10_output=True)  # host-only: accepted, nothing baked
+    v.close()
+
+
 def test_band_partition():
     from granite_b200 import viewer
 
