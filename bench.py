@@ -135,7 +135,7 @@ def _native_oracle():
     src_dir = os.path.dirname(os.path.abspath(oracle.__file__))
     out_dir = os.path.join(src_dir, "_build", "native")
     out = os.path.join(out_dir, "liboracle.so")
-    srcs = [os.path.join(src_dir, f) for f in ("oracle_host.c", "oracle_cluster.c", "oracle_lighting.c", "oracle_post.c")]
+    srcs = [os.path.join(src_dir, f) for f in ("oracle_host.c", "oracle_cluster.c", "oracle_lighting.c", "oracle_post.c", "oracle_smaa.c")]
     try:
         os.makedirs(out_dir, exist_ok=True)
         subprocess.run(["gcc", "-O3", "-march=native", "-std=c11", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-o", out,

@@ -169,4 +169,12 @@ float orc_srgb8_to_linear(uint32_t v);
 #ifdef __cplusplus
 }
 #endif
+/* SMAA (renderer/post/smaa.cpp:32-209, SMAA.hlsl): edge detection -> blending weights -> neighbourhood blending.
+ * quality = SMAA_QUALITY 0..3 (presets Low / Medium / High / Ultra).  area: 160x560 R8G8, search: 64x16 R8 (the
+ * reference's textures/smaa/{area,search}.gtx payloads). */
+void orc_smaa_edge_detection(const uint32_t *color_unorm, int w, int h, int quality, uint8_t *edges_rg8, int y0, int y1);
+void orc_smaa_blend_weights(const uint8_t *edges_rg8, int w, int h, const uint8_t *area_rg8, const uint8_t *search_r8, int quality,
+                            uint32_t *weights_rgba8, int y0, int y1);
+void orc_smaa_neighborhood_blend(const uint32_t *color_unorm, const uint32_t *weights_rgba8, int w, int h, uint32_t *out_srgb8, int y0, int y1);
+
 #endif

@@ -19,7 +19,7 @@ _REF_PATH = os.path.join(_HERE, "_ref", "libgranite_refmath.so")
 
 _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for k in (1, 2, 3, 4)]
 # post-processing shaders K7-K13 (ref_post_shim.cpp); ids as in oracle/Makefile POST_IDS
-_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14)
+_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
 # deferred-lighting fragment shaders K5 (clustering.frag) and K6 (directional.frag), ref_light_shim.cpp
 _REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6)}
@@ -552,6 +552,76 @@ def ref_pq10_encode(hdr, ui, primary16, hdr_pre=500.0, ui_pre=400.0, max_light=1
     y0, y1 = rows if rows else (0, h)
     ref_post_kernels()[14].refk14_pq10_encode(_p(_c(hdr, np.uint32)), _p(_c(ui, np.uint32)), w, h, _p(_c(primary16, np.float32)), _f(hdr_pre), _f(ui_pre),
                                               _f(max_light), _p(out), y0, y1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------- SMAA
+SMAA_MAX_SEARCH_STEPS = (4, 8, 16, 32)   # SMAA.hlsl:304-324, presets Low / Medium / High / Ultra (SMAA_QUALITY 0..3)
+SMAA_LUT_DIR = "/root/reference/assets/textures/smaa"
+
+
+def load_gtx(path):
+    """Granite's memory-mapped texture container (vulkan/texture/memory_mapped_texture.cpp:29-46): 64-byte header
+    (magic, type, VkFormat, width, height, depth, layers, levels, flags, payload size), then the texels."""
+    raw = open(path, "rb").read()
+    assert raw[:15] == b"GRANITE TEXFMT1"
+    hdr = np.frombuffer(raw[16:48], np.uint32)
+    fmt, w, h = int(hdr[1]), int(hdr[2]), int(hdr[3])
+    ch = {9: 1, 16: 2}[fmt]  # VK_FORMAT_R8_UNORM, VK_FORMAT_R8G8_UNORM
+    return np.frombuffer(raw[64:64 + w * h * ch], np.uint8).reshape(h, w, ch).copy()
+
+
+def smaa_luts():
+    """(area 560x160x2, search 16x64x1) from the reference's assets."""
+    return load_gtx(os.path.join(SMAA_LUT_DIR, "area.gtx")), load_gtx(os.path.join(SMAA_LUT_DIR, "search.gtx"))
+
+
+def smaa_edge(color_unorm, quality, rows=None):
+    h, w = color_unorm.shape
+    out = np.zeros((h, w, 2), np.uint8)
+    y0, y1 = rows if rows else (0, h)
+    lib().orc_smaa_edge_detection(_p(_c(color_unorm, np.uint32)), w, h, int(quality), _p(out), y0, y1)
+    return out
+
+
+def smaa_weights(edges, area, search, quality, rows=None):
+    h, w = edges.shape[:2]
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    lib().orc_smaa_blend_weights(_p(_c(edges, np.uint8)), w, h, _p(_c(area, np.uint8)), _p(_c(search, np.uint8)), int(quality), _p(out), y0, y1)
+    return out
+
+
+def smaa_blend(color_unorm, weights, rows=None):
+    h, w = color_unorm.shape
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    lib().orc_smaa_neighborhood_blend(_p(_c(color_unorm, np.uint32)), _p(_c(weights, np.uint32)), w, h, _p(out), y0, y1)
+    return out
+
+
+def ref_smaa_edge(color_unorm, quality, rows=None):
+    h, w = color_unorm.shape
+    out = np.zeros((h, w, 2), np.uint8)
+    y0, y1 = rows if rows else (0, h)
+    ref_post_kernels()[150 + quality].refk_smaa_edge(_p(_c(color_unorm, np.uint32)), w, h, _p(out), y0, y1)
+    return out
+
+
+def ref_smaa_weights(edges, area, search, quality, rows=None):
+    h, w = edges.shape[:2]
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    ref_post_kernels()[160 + quality].refk_smaa_weights(_p(_c(edges, np.uint8)), w, h, _p(_c(area, np.uint8)), _p(_c(search, np.uint8)),
+                                                        SMAA_MAX_SEARCH_STEPS[quality], _p(out), y0, y1)
+    return out
+
+
+def ref_smaa_blend(color_unorm, weights, quality, rows=None):
+    h, w = color_unorm.shape
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    ref_post_kernels()[170 + quality].refk_smaa_blend(_p(_c(color_unorm, np.uint32)), _p(_c(weights, np.uint32)), w, h, _p(out), y0, y1)
     return out
 
 

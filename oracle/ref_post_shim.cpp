@@ -65,6 +65,8 @@ enum ShimFormat
 	FMT_RGBA8_SRGB = 3,
 	FMT_D32F = 4,
 	FMT_RG16F = 5,
+	FMT_RG8_UNORM = 6,
+	FMT_R8_UNORM = 7,
 };
 
 // A texture view combined with a StockSampler.
@@ -118,6 +120,13 @@ struct sampler2D
 			const uint16_t *p = static_cast<const uint16_t *>(data) + 2 * i;
 			return glm::vec4(orc_f16_to_f32(p[0]), orc_f16_to_f32(p[1]), 0.0f, 1.0f);
 		}
+		case FMT_RG8_UNORM:
+		{
+			const uint8_t *p = static_cast<const uint8_t *>(data) + 2 * i;
+			return glm::vec4((float)p[0] / 255.0f, (float)p[1] / 255.0f, 0.0f, 1.0f);
+		}
+		case FMT_R8_UNORM:
+			return glm::vec4((float)static_cast<const uint8_t *>(data)[i] / 255.0f, 0.0f, 0.0f, 1.0f);
 		}
 		return glm::vec4(0.0f);
 	}
@@ -224,8 +233,28 @@ struct ShimMat4
 inline glm::vec4 operator*(const ShimMat4 &m, const glm::vec4 &v) { return ((m.c[0] * v.x + m.c[1] * v.y) + m.c[2] * v.z) + m.c[3] * v.w; }
 #define mat4 ShimMat4
 
+#if KERNEL >= 150
+// SMAA (SMAA.hlsl with SMAA_GLSL_4): mad(a, b, c) is GLSL fma().  GLM's fma is a * b + c with two roundings; a GPU
+// executes it fused, and so do oracle and product.  Non-template overloads win over GLM's.
+inline float fma(const float &a, const float &b, const float &c) { return std::fma(a, b, c); }
+inline glm::vec2 fma(const glm::vec2 &a, const glm::vec2 &b, const glm::vec2 &c) { return glm::vec2(std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)); }
+inline glm::vec3 fma(const glm::vec3 &a, const glm::vec3 &b, const glm::vec3 &c)
+{
+	return glm::vec3(std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y), std::fma(a.z, b.z, c.z));
+}
+inline glm::vec4 fma(const glm::vec4 &a, const glm::vec4 &b, const glm::vec4 &c)
+{
+	return glm::vec4(std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y), std::fma(a.z, b.z, c.z), std::fma(a.w, b.w, c.w));
+}
+// the edge-detection shader discards where it finds no edge: the attachment keeps its clear colour, 0 (smaa.cpp:131-135)
+#define discard return vec2(0.0f)
+#endif
+
 #include GEN_CPP
 #undef mat4
+#ifdef discard
+#undef discard
+#endif
 
 namespace
 {
@@ -519,5 +548,126 @@ void refk14_pq10_encode(const uint32_t *hdr, const uint32_t *ui, int w, int h, c
 		out[(size_t)y * w + x] = q(color.x) | (q(color.y) << 10) | (q(color.z) << 20) | (3u << 30);
 	});
 }
+#elif KERNEL >= 150 && KERNEL < 180
+// SMAA (renderer/post/smaa.cpp:32-209).  KERNEL = 150 + q: smaa_edge_detection.frag, 160 + q: smaa_blend_weight.frag
+// (SMAA_SUBPIXEL_MODE = 0), 170 + q: smaa_neighbor_blend.frag (SMAA_TARGET_SRGB = 1), q = SMAA_QUALITY 0..3.
+// The vertex stage (smaa_*.vert) only adds constant multiples of rt_metrics to the texture coordinate; the
+// interpolated values are those functions of the fragment's own coordinate, evaluated here with the same fma.
+static inline glm::vec4 mad4(const glm::vec4 &a, const glm::vec4 &b, const glm::vec4 &c) { return fma(a, b, c); }
+#if KERNEL < 160
+void refk_smaa_edge(const uint32_t *color_unorm, int w, int h, uint8_t *edges_rg8, int y0, int y1)
+{
+	sampler2D s = make_sampler(color_unorm, w, h, spirv_cross::FMT_RGBA8_UNORM);
+	Sh::Resources::Registers reg;
+	reg.rt_metrics = glm::vec4(1.0f / (float)w, 1.0f / (float)h, (float)w, (float)h);
+	glm::vec2 uv(0.0f), out(0.0f);
+	glm::vec4 o0(0.0f), o1(0.0f), o2(0.0f);
+	Runner r;
+	s.frag_uv = &uv;
+	s.frag_px = &r.pixel;
+	r.resource(0, 0, &s);
+	r.push(&reg, sizeof(reg));
+	spirv_cross_set_stage_input(r.sh, 0, &uv, sizeof(uv));
+	spirv_cross_set_stage_input(r.sh, 1, &o0, sizeof(o0));
+	spirv_cross_set_stage_input(r.sh, 2, &o1, sizeof(o1));
+	spirv_cross_set_stage_input(r.sh, 3, &o2, sizeof(o2));
+	spirv_cross_set_stage_output(r.sh, 0, &out, sizeof(out));
+	const glm::vec4 m = glm::vec4(reg.rt_metrics.x, reg.rt_metrics.y, reg.rt_metrics.x, reg.rt_metrics.y);
+	const float inv_w = 1.0f / (float)w, inv_h = 1.0f / (float)h;
+	for (int y = y0; y < y1; y++)
+		for (int x = 0; x < w; x++)
+		{
+			r.pixel = glm::ivec2(x, y);
+			uv = glm::vec2(((float)x + 0.5f) * inv_w, ((float)y + 0.5f) * inv_h);
+			const glm::vec4 t(uv.x, uv.y, uv.x, uv.y);
+			o0 = mad4(m, glm::vec4(-1.0f, 0.0f, 0.0f, -1.0f), t); // SMAAEdgeDetectionVS
+			o1 = mad4(m, glm::vec4(1.0f, 0.0f, 0.0f, 1.0f), t);
+			o2 = mad4(m, glm::vec4(-2.0f, 0.0f, 0.0f, -2.0f), t);
+			out = glm::vec2(0.0f);
+			r.itf->invoke(r.sh);
+			auto q = [](float c) -> uint8_t { c = c > 0.0f ? (c < 1.0f ? c : 1.0f) : 0.0f; return (uint8_t)std::floor(c * 255.0f + 0.5f); };
+			edges_rg8[2 * ((size_t)y * w + x) + 0] = q(out.x);
+			edges_rg8[2 * ((size_t)y * w + x) + 1] = q(out.y);
+		}
+}
+#elif KERNEL < 170
+void refk_smaa_weights(const uint8_t *edges_rg8, int w, int h, const uint8_t *area_rg8, const uint8_t *search_r8, int max_search_steps, uint32_t *weights_rgba8,
+                       int y0, int y1)
+{
+	sampler2D se = make_sampler(edges_rg8, w, h, spirv_cross::FMT_RG8_UNORM);
+	sampler2D sa = make_sampler(area_rg8, 160, 560, spirv_cross::FMT_RG8_UNORM);
+	sampler2D ss = make_sampler(search_r8, 64, 16, spirv_cross::FMT_R8_UNORM);
+	Sh::Resources::Registers reg;
+	reg.rt_metrics = glm::vec4(1.0f / (float)w, 1.0f / (float)h, (float)w, (float)h);
+	glm::vec2 uv(0.0f), pix(0.0f);
+	glm::vec4 o0(0.0f), o1(0.0f), o2(0.0f), out(0.0f);
+	Runner r;
+	se.frag_uv = &uv;
+	se.frag_px = &r.pixel;
+	r.resource(0, 0, &se);
+	r.resource(0, 1, &sa);
+	r.resource(0, 2, &ss);
+	r.push(&reg, sizeof(reg));
+	spirv_cross_set_stage_input(r.sh, 0, &uv, sizeof(uv));
+	spirv_cross_set_stage_input(r.sh, 1, &pix, sizeof(pix));
+	spirv_cross_set_stage_input(r.sh, 2, &o0, sizeof(o0));
+	spirv_cross_set_stage_input(r.sh, 3, &o1, sizeof(o1));
+	spirv_cross_set_stage_input(r.sh, 4, &o2, sizeof(o2));
+	spirv_cross_set_stage_output(r.sh, 0, &out, sizeof(out));
+	const glm::vec4 m = glm::vec4(reg.rt_metrics.x, reg.rt_metrics.y, reg.rt_metrics.x, reg.rt_metrics.y);
+	const glm::vec4 mxxyy = glm::vec4(reg.rt_metrics.x, reg.rt_metrics.x, reg.rt_metrics.y, reg.rt_metrics.y);
+	const float steps = (float)max_search_steps;
+	const float inv_w = 1.0f / (float)w, inv_h = 1.0f / (float)h;
+	for (int y = y0; y < y1; y++)
+		for (int x = 0; x < w; x++)
+		{
+			r.pixel = glm::ivec2(x, y);
+			uv = glm::vec2(((float)x + 0.5f) * inv_w, ((float)y + 0.5f) * inv_h);
+			const glm::vec4 t(uv.x, uv.y, uv.x, uv.y);
+			pix = uv * glm::vec2(reg.rt_metrics.z, reg.rt_metrics.w); // SMAABlendingWeightCalculationVS
+			o0 = mad4(m, glm::vec4(-0.25f, -0.125f, 1.25f, -0.125f), t);
+			o1 = mad4(m, glm::vec4(-0.125f, -0.25f, -0.125f, 1.25f), t);
+			o2 = mad4(mxxyy, glm::vec4(-2.0f, 2.0f, -2.0f, 2.0f) * steps, glm::vec4(o0.x, o0.z, o1.y, o1.w));
+			out = glm::vec4(0.0f);
+			r.itf->invoke(r.sh);
+			auto q = [](float c) -> uint32_t { c = c > 0.0f ? (c < 1.0f ? c : 1.0f) : 0.0f; return (uint32_t)std::floor(c * 255.0f + 0.5f); };
+			weights_rgba8[(size_t)y * w + x] = q(out.x) | (q(out.y) << 8) | (q(out.z) << 16) | (q(out.w) << 24);
+		}
+}
+#else
+void refk_smaa_blend(const uint32_t *color_unorm, const uint32_t *weights_rgba8, int w, int h, uint32_t *out_srgb8, int y0, int y1)
+{
+	sampler2D sc = make_sampler(color_unorm, w, h, spirv_cross::FMT_RGBA8_UNORM);
+	sampler2D sb = make_sampler(weights_rgba8, w, h, spirv_cross::FMT_RGBA8_UNORM);
+	Sh::Resources::Registers reg;
+	reg.rt_metrics = glm::vec4(1.0f / (float)w, 1.0f / (float)h, (float)w, (float)h);
+	glm::vec2 uv(0.0f);
+	glm::vec4 off(0.0f), out(0.0f);
+	Runner r;
+	sc.frag_uv = &uv;
+	sc.frag_px = &r.pixel;
+	sb.frag_uv = &uv;
+	sb.frag_px = &r.pixel;
+	r.resource(0, 0, &sc);
+	r.resource(0, 1, &sb);
+	r.push(&reg, sizeof(reg));
+	spirv_cross_set_stage_input(r.sh, 0, &uv, sizeof(uv));
+	spirv_cross_set_stage_input(r.sh, 1, &off, sizeof(off));
+	spirv_cross_set_stage_output(r.sh, 0, &out, sizeof(out));
+	const glm::vec4 m = glm::vec4(reg.rt_metrics.x, reg.rt_metrics.y, reg.rt_metrics.x, reg.rt_metrics.y);
+	const float inv_w = 1.0f / (float)w, inv_h = 1.0f / (float)h;
+	for (int y = y0; y < y1; y++)
+		for (int x = 0; x < w; x++)
+		{
+			r.pixel = glm::ivec2(x, y);
+			uv = glm::vec2(((float)x + 0.5f) * inv_w, ((float)y + 0.5f) * inv_h);
+			off = mad4(m, glm::vec4(1.0f, 0.0f, 0.0f, 1.0f), glm::vec4(uv.x, uv.y, uv.x, uv.y)); // SMAANeighborhoodBlendingVS
+			r.itf->invoke(r.sh);
+			// SMAA_TARGET_SRGB: the shader decoded to linear, the sRGB attachment encodes on store
+			auto a8 = [](float c) -> uint32_t { c = c > 0.0f ? (c < 1.0f ? c : 1.0f) : 0.0f; return (uint32_t)std::floor(c * 255.0f + 0.5f); };
+			out_srgb8[(size_t)y * w + x] = orc_linear_to_srgb8(out.x) | (orc_linear_to_srgb8(out.y) << 8) | (orc_linear_to_srgb8(out.z) << 16) | (a8(out.w) << 24);
+		}
+}
+#endif
 #endif
 }
