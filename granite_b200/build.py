@@ -22,6 +22,7 @@ UNITS = [
     ("grb_post.cu", ["-fmad=false"]),
     ("grb_post_tiles.cu", ["-fmad=false"]),
     ("grb_post_fast.cu", []),
+    ("grb_smaa.cu", ["-fmad=false"]),
     ("grb_lighting.cu", []),
 ]
 

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgranite_b200.so")
 
 # GrbFormat (== VkFormat values)
+FORMAT_R8_UNORM = 9
 FORMAT_R8G8_UNORM = 16
 FORMAT_R8G8B8A8_UNORM = 37
 FORMAT_R8G8B8A8_SRGB = 43
@@ -24,7 +25,7 @@ FORMAT_R16G16B16A16_SFLOAT = 97
 FORMAT_B10G11R11_UFLOAT = 122
 FORMAT_D32_SFLOAT = 126
 
-TEXEL_BYTES = {FORMAT_R8G8_UNORM: 2, FORMAT_R8G8B8A8_UNORM: 4, FORMAT_R8G8B8A8_SRGB: 4,
+TEXEL_BYTES = {FORMAT_R8_UNORM: 1, FORMAT_R8G8_UNORM: 2, FORMAT_R8G8B8A8_UNORM: 4, FORMAT_R8G8B8A8_SRGB: 4,
                FORMAT_A2B10G10R10_UNORM: 4, FORMAT_R16G16_SFLOAT: 4, FORMAT_R16G16B16A16_SFLOAT: 8,
                FORMAT_B10G11R11_UFLOAT: 4, FORMAT_D32_SFLOAT: 4}
 
@@ -85,7 +86,7 @@ ENTRY_POINTS = [
     "grb_cluster_build", "grb_deferred_lighting", "grb_deferred_lighting_blocks", "grb_deferred_lighting_scheduled", "grb_lighting_schedule_bytes", "grb_debug_cluster_indices", "grb_lighting_row_cost",
     "grb_bloom_threshold", "grb_bloom_threshold_downsample", "grb_bloom_threshold_downsample_to_peers", "grb_bloom_downsample", "grb_bloom_downsample_to_peers", "grb_peer_wait", "grb_bloom_upsample", "grb_bloom_upsample_exact",
     "grb_luminance", "grb_luminance_grid", "grb_luminance_finalize", "grb_bloom_tail", "grb_bloom_tail_ex", "grb_tonemap",
-    "grb_pq10_encode", "grb_fxaa", "grb_taa_resolve",
+    "grb_pq10_encode", "grb_smaa_edge_detection", "grb_smaa_blend_weights", "grb_smaa_neighborhood_blend", "grb_fxaa", "grb_taa_resolve",
 ]
 
 _lib = None
@@ -134,6 +135,9 @@ def lib() -> C.CDLL:
             "grb_bloom_tail_ex": [IMG, IMG, IMG, IMG, IMG, F, P, F, F, F, IMG, IMG, P, P],
             "grb_tonemap": [IMG, IMG, P, F, IMG, GrbRows, P],
             "grb_pq10_encode": [IMG, IMG, P, F, F, F, IMG, GrbRows, P],
+            "grb_smaa_edge_detection": [IMG, I, IMG, GrbRows, P],
+            "grb_smaa_blend_weights": [IMG, IMG, IMG, I, IMG, GrbRows, P],
+            "grb_smaa_neighborhood_blend": [IMG, IMG, IMG, GrbRows, P],
             "grb_fxaa": [IMG, IMG, GrbRows, P],
             "grb_taa_resolve": [IMG, IMG, IMG, IMG, P, I, IMG, IMG, GrbRows, P],
         }

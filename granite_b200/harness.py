@@ -222,6 +222,26 @@ def pq10_encode(hdr_t, ui_t, primary16, hdr_pre, ui_pre, max_light, out_t, rows=
                                           capi.stream_ptr()), "grb_pq10_encode")
 
 
+def smaa_edge_detection(color_t, quality, edges_t, rows=None):
+    """color_t: (H, W) int32 RGBA8 (read as UNORM); edges_t: (H, W, 2) uint8."""
+    ci, ei = capi.image(color_t, capi.FORMAT_R8G8B8A8_UNORM), capi.image(edges_t, capi.FORMAT_R8G8_UNORM)
+    capi.check(capi.lib().grb_smaa_edge_detection(C.byref(ci), int(quality), C.byref(ei), capi.rows(rows), capi.stream_ptr()), "grb_smaa_edge_detection")
+
+
+def smaa_blend_weights(edges_t, area_t, search_t, quality, weights_t, rows=None):
+    """area_t: (560, 160, 2) uint8, search_t: (16, 64) or (16, 64, 1) uint8, weights_t: (H, W) int32."""
+    ei, ai = capi.image(edges_t, capi.FORMAT_R8G8_UNORM), capi.image(area_t, capi.FORMAT_R8G8_UNORM)
+    si, wi = capi.image(search_t, capi.FORMAT_R8_UNORM), capi.image(weights_t, capi.FORMAT_R8G8B8A8_UNORM)
+    capi.check(capi.lib().grb_smaa_blend_weights(C.byref(ei), C.byref(ai), C.byref(si), int(quality), C.byref(wi), capi.rows(rows), capi.stream_ptr()),
+               "grb_smaa_blend_weights")
+
+
+def smaa_neighborhood_blend(color_t, weights_t, out_t, target_srgb=True, rows=None):
+    ci, wi = capi.image(color_t, capi.FORMAT_R8G8B8A8_UNORM), capi.image(weights_t, capi.FORMAT_R8G8B8A8_UNORM)
+    oi = capi.image(out_t, capi.FORMAT_R8G8B8A8_SRGB if target_srgb else capi.FORMAT_R8G8B8A8_UNORM)
+    capi.check(capi.lib().grb_smaa_neighborhood_blend(C.byref(ci), C.byref(wi), C.byref(oi), capi.rows(rows), capi.stream_ptr()), "grb_smaa_neighborhood_blend")
+
+
 def taa_resolve(hdr_t, depth_t, mv_t, history_t, reproj, quality, out_color_t, out_history_t, rows=None):
     hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
     oc = capi.image(out_color_t, capi.FORMAT_B10G11R11_UFLOAT)

@@ -49,6 +49,7 @@ typedef enum GrbResult
 typedef enum GrbFormat
 {
 	GRB_FORMAT_UNDEFINED = 0,
+	GRB_FORMAT_R8_UNORM = 9,
 	GRB_FORMAT_R8G8_UNORM = 16,
 	GRB_FORMAT_R8G8B8A8_UNORM = 37,
 	GRB_FORMAT_R8G8B8A8_SRGB = 43,
@@ -299,6 +300,19 @@ int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const float *lum
  * out: A2B10G10R10_UNORM_PACK32 holding ST.2084 (PQ) code values, alpha = 1. */
 int32_t grb_pq10_encode(const GrbImage *hdr, const GrbImage *ui, const float *primary_conversion16, float hdr_pre_exposure,
                         float ui_pre_exposure, float max_light_level, const GrbImage *out, GrbRows rows, void *stream);
+/* SMAA 1x (renderer/post/smaa.cpp:32-209; assets/shaders/post/SMAA.hlsl through smaa_edge_detection / smaa_blend_weight /
+ * smaa_neighbor_blend .vert + .frag).  quality = SMAA_QUALITY 0..3 = presets Low / Medium / High / Ultra (SMAA.hlsl:304-324).
+ * color: the tonemapped 8-bit image, read as UNORM whatever its format says (smaa.cpp:124 set_unorm_texture);
+ * edges: R8G8_UNORM; weights: R8G8B8A8_UNORM; area (160x560 R8G8_UNORM) and search (64x16 R8_UNORM) are the payloads
+ * of the reference's textures/smaa/{area,search}.gtx (SMAA's precomputed lookup tables), supplied by the caller;
+ * out: R8G8B8A8_SRGB (the blended colour is decoded to linear and encoded on store, SMAA_TARGET_SRGB) or _UNORM.
+ * The reference's depth mask between the first two passes (smaa.cpp:101-118) keeps every pixel (both passes emit depth
+ * 0 = the clear value), so there is nothing to emulate: pixels without an edge get zero weights from the second call. */
+int32_t grb_smaa_edge_detection(const GrbImage *color, int32_t quality, const GrbImage *edges, GrbRows rows, void *stream);
+int32_t grb_smaa_blend_weights(const GrbImage *edges, const GrbImage *area, const GrbImage *search, int32_t quality,
+                               const GrbImage *weights, GrbRows rows, void *stream);
+int32_t grb_smaa_neighborhood_blend(const GrbImage *color, const GrbImage *weights, const GrbImage *out, GrbRows rows, void *stream);
+
 /* K12 fxaa.frag; renderer/post/fxaa.cpp:41-55. in: 8-bit image viewed as UNORM; if out's
  * format is *_SRGB the shader's FXAA_TARGET_SRGB path applies. */
 int32_t grb_fxaa(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream);
