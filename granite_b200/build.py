@@ -67,7 +67,7 @@ HOST_DIR = os.path.join(HERE, "host")
 HOST_OUT = os.path.join(HERE, "libgranite_b200_host.so")
 HOST_SRCS = ["math.cpp", "frustum.cpp", "cuda_backend.cpp", "render_graph.cpp", "shard_plan.cpp", "render_context.cpp", "lights.cpp", "clusterer.cpp",
              "renderer.cpp", "nccl_collectives.cpp", "scene_viewer.cpp", "post/hdr.cpp", "post/fxaa.cpp",
-             "post/temporal.cpp", "post/aa.cpp"]
+             "post/temporal.cpp", "post/aa.cpp", "post/smaa.cpp"]
 CXX = os.environ.get("CXX", "g++")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 

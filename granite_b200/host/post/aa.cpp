@@ -4,6 +4,7 @@
 #include <stdexcept>
 
 #include "fxaa.hpp"
+#include "smaa.hpp"
 
 namespace Granite
 {
@@ -27,13 +28,25 @@ bool setup_before_post_chain_antialiasing(PostAAType type, RenderGraph &graph, T
 	}
 }
 
-bool setup_after_post_chain_antialiasing(PostAAType type, RenderGraph &graph, TemporalJitter &, float, const std::string &input,
-                                         const std::string &, const std::string &output)
+bool setup_after_post_chain_antialiasing(PostAAType type, RenderGraph &graph, TemporalJitter &jitter, float scaling_factor, const std::string &input,
+                                         const std::string &input_depth, const std::string &output)
 {
 	switch (type)
 	{
 	case PostAAType::FXAA:
 		setup_fxaa_postprocess(graph, input, output);
+		return true;
+	case PostAAType::SMAA_Low:
+		setup_smaa_postprocess(graph, jitter, scaling_factor, input, input_depth, output, SMAAPreset::Low);
+		return true;
+	case PostAAType::SMAA_Medium:
+		setup_smaa_postprocess(graph, jitter, scaling_factor, input, input_depth, output, SMAAPreset::Medium);
+		return true;
+	case PostAAType::SMAA_High:
+		setup_smaa_postprocess(graph, jitter, scaling_factor, input, input_depth, output, SMAAPreset::High);
+		return true;
+	case PostAAType::SMAA_Ultra:
+		setup_smaa_postprocess(graph, jitter, scaling_factor, input, input_depth, output, SMAAPreset::Ultra);
 		return true;
 	case PostAAType::None:
 	case PostAAType::TAA_Low:
@@ -41,7 +54,7 @@ bool setup_after_post_chain_antialiasing(PostAAType type, RenderGraph &graph, Te
 	case PostAAType::TAA_High:
 		return false;
 	default:
-		throw std::logic_error("PostAAType not supported by this executor (SMAA / FXAA_2Phase are outside the hot path).");
+		throw std::logic_error("PostAAType not supported by this executor (FXAA_2Phase and SMAA T2X are not built).");
 	}
 }
 } // namespace Granite

@@ -1,6 +1,6 @@
 // aa.hpp -- PostAAType and the two hooks the application calls around the HDR chain
-// (renderer/post/aa.hpp:33-63).  FXAA and the three TAA qualities are on the hot path; the
-// stale FXAA_2Phase / SMAA_T2X resolves and SMAA are not built.
+// (renderer/post/aa.hpp:33-63).  FXAA, the three TAA qualities and SMAA 1x (Low .. Ultra) are built; the
+// stale FXAA_2Phase and the SMAA_T2X resolve are not.
 #pragma once
 
 #include <string>
@@ -27,7 +27,8 @@ enum class PostAAType
 constexpr bool post_aa_type_is_supported(PostAAType type)
 {
 	return type == PostAAType::None || type == PostAAType::FXAA || type == PostAAType::TAA_Low || type == PostAAType::TAA_Medium ||
-	       type == PostAAType::TAA_High;
+	       type == PostAAType::TAA_High || type == PostAAType::SMAA_Low || type == PostAAType::SMAA_Medium || type == PostAAType::SMAA_High ||
+	       type == PostAAType::SMAA_Ultra;
 }
 
 // Returns true when a pass was added (the chain input then becomes `output`).

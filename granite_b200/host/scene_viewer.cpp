@@ -19,6 +19,7 @@
 #include "nccl_collectives.hpp"
 #include "post/aa.hpp"
 #include "post/fxaa.hpp"
+#include "post/smaa.hpp"
 #include "post/hdr.hpp"
 #include "renderer.hpp"
 
@@ -78,6 +79,7 @@ struct GrbhViewer
 		       config.post_aa == GRBH_AA_TAA_HIGH_PLUS_FXAA;
 	}
 	bool uses_fxaa() const { return config.post_aa == GRBH_AA_FXAA || config.post_aa == GRBH_AA_TAA_HIGH_PLUS_FXAA; }
+	bool uses_smaa() const { return config.post_aa >= GRBH_AA_SMAA_LOW && config.post_aa <= GRBH_AA_SMAA_ULTRA; }
 
 	// rows of the full-resolution inputs this rank must hold: its band + the halo the bloom
 	// threshold (and FXAA through the tonemap) reaches into
@@ -318,6 +320,14 @@ void GrbhViewer::bake_render_graph()
 			setup_fxaa_postprocess(graph, ui_source, "post-aa-output");
 			ui_source = "post-aa-output";
 		}
+		else if (uses_smaa())
+		{
+			const PostAAType type = config.post_aa == GRBH_AA_SMAA_LOW ? PostAAType::SMAA_Low :
+			                        (config.post_aa == GRBH_AA_SMAA_MEDIUM ? PostAAType::SMAA_Medium :
+			                                                                 (config.post_aa == GRBH_AA_SMAA_HIGH ? PostAAType::SMAA_High : PostAAType::SMAA_Ultra));
+			if (setup_after_post_chain_antialiasing(type, graph, jitter, 1.0f, ui_source, "depth-transient", "post-aa-output"))
+				ui_source = "post-aa-output";
+		}
 	}
 	output_name = ui_source;
 	graph.set_backbuffer_source(ui_source);
@@ -396,6 +406,8 @@ extern "C" int32_t grbh_viewer_create(const GrbhViewerConfig *config, GrbhViewer
 		return fail("grbh_viewer_create: bad config");
 	if (config->hdr10_output && (config->post_aa == GRBH_AA_FXAA || config->post_aa == GRBH_AA_TAA_HIGH_PLUS_FXAA))
 		return fail("grbh_viewer_create: FXAA reads the tonemapped 8-bit image; an HDR10 output has none (use TAA)");
+	if (config->hdr10_output && config->post_aa >= GRBH_AA_SMAA_LOW && config->post_aa <= GRBH_AA_SMAA_ULTRA)
+		return fail("grbh_viewer_create: SMAA reads the tonemapped 8-bit image; an HDR10 output has none (use TAA)");
 	GRBH_TRY
 	auto v = std::make_unique<GrbhViewer>();
 	v->config = *config;
@@ -427,6 +439,8 @@ extern "C" void grbh_viewer_destroy(GrbhViewer *viewer)
 	for (auto e : viewer->free_output_events)
 		cudaEventDestroy(e);
 	viewer->graph.reset();
+	if (viewer->device)
+		Granite::release_smaa_lookup_textures(*viewer->device); // device images: must go before the device does
 	delete viewer;
 }
 
@@ -490,6 +504,41 @@ extern "C" int32_t grbh_viewer_set_lights(GrbhViewer *v, const GrbhLights *l)
 			v->light_storage.push_back(std::move(s));
 		}
 		v->scene_lights.push_back(info);
+	}
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_set_smaa_lookup_textures(GrbhViewer *v, const uint8_t *area_rg8, const uint8_t *search_r8)
+{
+	if (!v || !area_rg8 || !search_r8)
+		return fail("grbh_viewer_set_smaa_lookup_textures: bad arguments");
+	if (!v->device)
+		return fail("grbh_viewer_set_smaa_lookup_textures: host-only viewer (no CUDA device)");
+	GRBH_TRY
+	if (!Granite::set_smaa_lookup_textures(*v->device, area_rg8, search_r8))
+		return fail("grbh_viewer_set_smaa_lookup_textures: upload failed");
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_load_gtx(const char *path, int32_t *format, int32_t *width, int32_t *height, uint8_t *texels, int64_t capacity)
+{
+	if (!path || !format || !width || !height)
+		return fail("grbh_load_gtx: bad arguments");
+	GRBH_TRY
+	Granite::GtxImage img;
+	std::string error;
+	if (!Granite::load_gtx(path, img, error))
+		return fail(error.c_str());
+	*format = (int32_t)img.format;
+	*width = (int32_t)img.width;
+	*height = (int32_t)img.height;
+	if (texels)
+	{
+		if (capacity < (int64_t)img.texels.size())
+			return fail("grbh_load_gtx: texel buffer too small");
+		std::memcpy(texels, img.texels.data(), img.texels.size());
 	}
 	return 0;
 	GRBH_CATCH

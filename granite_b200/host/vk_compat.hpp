@@ -7,6 +7,7 @@
 
 using VkFormat = int32_t;
 constexpr VkFormat VK_FORMAT_UNDEFINED = 0;
+constexpr VkFormat VK_FORMAT_R8_UNORM = 9;
 constexpr VkFormat VK_FORMAT_R8G8_UNORM = 16;
 constexpr VkFormat VK_FORMAT_R8G8B8A8_UNORM = 37;
 constexpr VkFormat VK_FORMAT_R8G8B8A8_SRGB = 43;
@@ -66,6 +67,8 @@ inline unsigned format_texel_size(VkFormat format)
 {
 	switch (format)
 	{
+	case VK_FORMAT_R8_UNORM:
+		return 1;
 	case VK_FORMAT_R8G8_UNORM:
 		return 2;
 	case VK_FORMAT_R16G16B16A16_SFLOAT:

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.path.join(_HERE, "libgranite_b200_host.so")
 
 AA_NONE, AA_FXAA, AA_TAA_LOW, AA_TAA_MEDIUM, AA_TAA_HIGH, AA_TAA_HIGH_PLUS_FXAA = 0, 1, 8, 9, 10, 100
+AA_SMAA_LOW, AA_SMAA_MEDIUM, AA_SMAA_HIGH, AA_SMAA_ULTRA = 3, 4, 5, 6
 
 
 class GrbhViewerConfig(C.Structure):
@@ -246,6 +247,13 @@ class Viewer:
         _check(lib().grbh_viewer_create(C.byref(cfg), C.byref(self._h)), "grbh_viewer_create")
         self._keep = []
 
+    def set_smaa_lookup_textures(self, area_rg8, search_r8):
+        """area: (560, 160, 2) uint8, search: (16, 64[, 1]) uint8 -- the payloads of the reference's area.gtx / search.gtx."""
+        a, s_ = np.ascontiguousarray(area_rg8, np.uint8), np.ascontiguousarray(search_r8, np.uint8)
+        assert a.size == 160 * 560 * 2 and s_.size == 64 * 16
+        _check(lib().grbh_viewer_set_smaa_lookup_textures(self._h, a.ctypes.data_as(C.c_void_p), s_.ctypes.data_as(C.c_void_p)),
+               "grbh_viewer_set_smaa_lookup_textures")
+
     def close(self):
         if self._h:
             lib().grbh_viewer_destroy(self._h)
@@ -422,6 +430,16 @@ class Viewer:
         n = _check(lib().grbh_viewer_collect_timeline(self._h, names, 64 * capacity, b, e, capacity), "grbh_viewer_collect_timeline")
         nm = [x for x in names.value.decode().split("\n") if x]
         return [(nm[i], b[i], e[i]) for i in range(min(n, len(nm), capacity))]
+
+
+def load_gtx(path):
+    """Granite's texture container (the reference's textures/smaa/*.gtx) -> (VkFormat, numpy (H, W, C) uint8) through the host library's reader."""
+    fmt, w, h = C.c_int32(), C.c_int32(), C.c_int32()
+    _check(lib().grbh_load_gtx(path.encode(), C.byref(fmt), C.byref(w), C.byref(h), None, C.c_int64(0)), "grbh_load_gtx")
+    ch = {capi.FORMAT_R8_UNORM: 1, capi.FORMAT_R8G8_UNORM: 2, capi.FORMAT_R8G8B8A8_UNORM: 4, capi.FORMAT_R8G8B8A8_SRGB: 4}[fmt.value]
+    out = np.zeros((h.value, w.value, ch), np.uint8)
+    _check(lib().grbh_load_gtx(path.encode(), C.byref(fmt), C.byref(w), C.byref(h), out.ctypes.data_as(C.c_void_p), C.c_int64(out.nbytes)), "grbh_load_gtx")
+    return fmt.value, out
 
 
 def rec709_to_display_primaries(primaries_xy8) -> np.ndarray:

@@ -27,6 +27,11 @@ typedef enum GrbhPostAA
 {
 	GRBH_AA_NONE = 0,
 	GRBH_AA_FXAA = 1,
+	/* SMAA 1x after the tonemap, presets Low .. Ultra; needs grbh_viewer_set_smaa_lookup_textures before the first frame */
+	GRBH_AA_SMAA_LOW = 3,
+	GRBH_AA_SMAA_MEDIUM = 4,
+	GRBH_AA_SMAA_HIGH = 5,
+	GRBH_AA_SMAA_ULTRA = 6,
 	GRBH_AA_TAA_LOW = 8,
 	GRBH_AA_TAA_MEDIUM = 9,
 	GRBH_AA_TAA_HIGH = 10,
@@ -88,6 +93,12 @@ int32_t grbh_viewer_set_camera(GrbhViewer *viewer, const float *projection16, co
 int32_t grbh_viewer_set_directional(GrbhViewer *viewer, const float *color3, const float *direction3);
 int32_t grbh_viewer_set_lights(GrbhViewer *viewer, const GrbhLights *lights);
 int32_t grbh_viewer_set_exposure(GrbhViewer *viewer, float exposure);
+
+/* The two lookup textures SMAA samples (the payloads of the reference's assets/textures/smaa/area.gtx: 160x560 R8G8_UNORM,
+ * and search.gtx: 64x16 R8_UNORM), uploaded once to the viewer's device.  grbh_load_gtx reads such a container from a
+ * file: returns the VkFormat and fills width / height; texels (capacity bytes) receives the level-0 payload. */
+int32_t grbh_viewer_set_smaa_lookup_textures(GrbhViewer *viewer, const uint8_t *area_rg8, const uint8_t *search_r8);
+int32_t grbh_load_gtx(const char *path, int32_t *format, int32_t *width, int32_t *height, uint8_t *texels, int64_t capacity);
 
 /* Rec.709 -> display primaries, the matrix setup_hdr10_pq_encoding pushes (renderer/post/hdr.cpp:580-593, 651).
  * primaries_xy8: red, green, blue, white chromaticities (VkHdrMetadataEXT order); out16: column-major mat4. */

@@ -4,12 +4,15 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../granite_b200/host/post/aa.hpp"
 #include "../../granite_b200/host/post/fxaa.hpp"
 #include "../../granite_b200/host/post/hdr.hpp"
+#include "../../granite_b200/host/post/smaa.hpp"
 #include "../../granite_b200/host/render_graph.hpp"
 
 using namespace Granite;
@@ -195,11 +198,13 @@ int main()
 
 	// --- PostAAType dispatch ---
 	{
-		CHECK(post_aa_type_is_supported(PostAAType::TAA_High) && !post_aa_type_is_supported(PostAAType::SMAA_Ultra));
+		CHECK(post_aa_type_is_supported(PostAAType::TAA_High) && post_aa_type_is_supported(PostAAType::SMAA_Ultra));
+		CHECK(!post_aa_type_is_supported(PostAAType::SMAA_Ultra_T2X) && !post_aa_type_is_supported(PostAAType::FXAA_2Phase));
 		RenderGraph graph;
 		graph.set_backbuffer_dimensions(dim);
 		TemporalJitter jitter;
-		CHECK(throws_logic_error([&] { setup_after_post_chain_antialiasing(PostAAType::SMAA_High, graph, jitter, 1.0f, "a", "d", "o"); }));
+		CHECK(throws_logic_error([&] { setup_after_post_chain_antialiasing(PostAAType::SMAA_Ultra_T2X, graph, jitter, 1.0f, "a", "d", "o"); }));
+		CHECK(throws_logic_error([&] { setup_after_post_chain_antialiasing(PostAAType::FXAA_2Phase, graph, jitter, 1.0f, "a", "d", "o"); }));
 		CHECK(!setup_before_post_chain_antialiasing(PostAAType::FXAA, graph, jitter, 1.0f, "a", "d", "mv", "o"));
 		CHECK(setup_before_post_chain_antialiasing(PostAAType::TAA_High, graph, jitter, 1.0f, "HDR-main", "depth", "mv", "HDR-resolved"));
 		CHECK(graph.find_pass("taa-resolve") != nullptr);
@@ -305,6 +310,55 @@ int main()
 		for (int r = 0; r < 3; r++)
 			CHECK(std::fabs(m[0][r] + m[1][r] + m[2][r] - 1.0f) < 1e-6f);
 		CHECK(m[0][0] > 0.62f && m[0][0] < 0.63f); // 0.6274: the familiar BT.709 -> BT.2020 coefficient
+	}
+
+	// --- SMAA: three passes behind the tonemap (renderer/post/smaa.cpp:32-209), formats and sizes of the intermediates ---
+	{
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo hdr;
+		hdr.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+		graph.add_pass("lighting", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("HDR-main", hdr);
+		FrameParameters frame;
+		setup_hdr_postprocess(graph, frame, "HDR-main", "tonemapped", HDROptions{});
+		TemporalJitter jitter;
+		CHECK(setup_after_post_chain_antialiasing(PostAAType::SMAA_High, graph, jitter, 1.0f, "tonemapped", "depth", "post-aa-output"));
+		graph.set_backbuffer_source("post-aa-output");
+		graph.bake();
+		CHECK(join(graph.get_baked_pass_names()) == "lighting,bloom-compute,tonemap,smaa-edge,smaa-weights,smaa-blend,");
+		auto e = graph.get_resource_dimensions(graph.get_texture_resource("smaa-edge"));
+		auto w = graph.get_resource_dimensions(graph.get_texture_resource("smaa-weights"));
+		auto o = graph.get_resource_dimensions(graph.get_texture_resource("post-aa-output"));
+		CHECK(e.format == VK_FORMAT_R8G8_UNORM && e.width == 3840 && e.height == 2160);
+		CHECK(w.format == VK_FORMAT_R8G8B8A8_UNORM && w.width == 3840);
+		CHECK(o.format == VK_FORMAT_R8G8B8A8_SRGB); // undefined format: the backbuffer's
+		CHECK(graph.get_texture_resource("tonemapped").get_attachment_info().flags & ATTACHMENT_INFO_UNORM_SRGB_ALIAS_BIT);
+		CHECK(jitter.get_jitter_type() == TemporalJitter::Type::None);
+	}
+	// --- the .gtx container the lookup textures come in (vulkan/texture/memory_mapped_texture.cpp:29-46) ---
+	{
+		std::vector<uint8_t> file(64 + 4 * 3 * 2, 0);
+		std::memcpy(file.data(), "GRANITE TEXFMT1", 16);
+		const uint32_t header[8] = { 1u, (uint32_t)VK_FORMAT_R8G8_UNORM, 4u, 3u, 1u, 1u, 1u, 0u };
+		std::memcpy(file.data() + 16, header, sizeof(header));
+		const uint64_t payload = 4 * 3 * 2;
+		std::memcpy(file.data() + 48, &payload, 8);
+		for (size_t i = 64; i < file.size(); i++)
+			file[i] = (uint8_t)(i - 64);
+		GtxImage img;
+		std::string err;
+		CHECK(parse_gtx(file.data(), file.size(), img, err));
+		CHECK(img.format == VK_FORMAT_R8G8_UNORM && img.width == 4 && img.height == 3 && img.texels.size() == 24 && img.texels[23] == 23);
+		CHECK(!parse_gtx(file.data(), 63, img, err) && !parse_gtx(file.data(), file.size() - 1, img, err));
+		file[0] = 'X';
+		CHECK(!parse_gtx(file.data(), file.size(), img, err));
+		// the reference's own files, where they exist
+		GtxImage area, search;
+		if (load_gtx("/root/reference/assets/textures/smaa/area.gtx", area, err) && load_gtx("/root/reference/assets/textures/smaa/search.gtx", search, err))
+		{
+			CHECK(area.format == VK_FORMAT_R8G8_UNORM && area.width == 160 && area.height == 560 && area.texels.size() == 160u * 560u * 2u);
+			CHECK(search.format == VK_FORMAT_R8_UNORM && search.width == 64 && search.height == 16 && search.texels.size() == 1024u);
+		}
 	}
 
 	// --- queues map to streams: main, cluster build, tonemap / AA, bloom ---

@@ -169,6 +169,21 @@ def test_hdr10_output_rejects_fxaa(built):
     v.close()
 
 
+def test_gtx_reader_reads_the_reference_lookup_textures(built, oracle):
+    """The host library's .gtx reader (host/post/smaa.cpp) against the Python reader the oracle tests use."""
+    from granite_b200 import capi, viewer
+
+    if not os.path.isdir(oracle.SMAA_LUT_DIR):
+        pytest.skip("the reference's assets are not on this machine")
+    area, search = oracle.smaa_luts()
+    fmt, a = viewer.load_gtx(os.path.join(oracle.SMAA_LUT_DIR, "area.gtx"))
+    assert fmt == capi.FORMAT_R8G8_UNORM and np.array_equal(a, area)
+    fmt, s = viewer.load_gtx(os.path.join(oracle.SMAA_LUT_DIR, "search.gtx"))
+    assert fmt == capi.FORMAT_R8_UNORM and np.array_equal(s, search)
+    with pytest.raises(RuntimeError):
+        viewer.load_gtx("/nonexistent.gtx")
+
+
 def test_band_partition():
     from granite_b200 import viewer
 

@@ -64,3 +64,34 @@ def test_cuda_smaa_vs_oracle(cuda, oracle, w, h):
     harness.smaa_neighborhood_blend(harness.to_dev(img), harness.to_dev(wg), band, target_srgb=True, rows=(16, h - 24))
     band = harness.to_host(band, np.uint32)
     assert np.array_equal(band[16:h - 24], out[16:h - 24]) and not band[:16].any() and not band[h - 24:].any()
+
+
+def test_viewer_frame_with_smaa(cuda, oracle):
+    """Whole frame through the host layer: lighting -> bloom -> tonemap -> smaa-edge / smaa-weights / smaa-blend
+    (host/post/smaa.cpp).  The three SMAA passes are checked on the tonemapped image the device itself produced."""
+    from granite_b200 import synth, viewer
+
+    f = np.load(os.path.join(GOLDEN, "refsmaa_160x96.npz"))
+    w, h = 640, 360
+    scene, lights = synth.make_scene(w, h), synth.make_lights(200, aspect=w / h)
+    v = viewer.Viewer(w, h, post_aa=viewer.AA_SMAA_HIGH)
+    v.set_camera(scene.projection, scene.view)
+    v.set_directional(scene.dir_color, scene.dir_direction)
+    v.set_lights(lights)
+    v.set_smaa_lookup_textures(f["area"], f["search"])
+    v.bake()
+    assert v.pass_names()[-3:] == ["smaa-edge", "smaa-weights", "smaa-blend"]
+    keep = [np.ascontiguousarray(a) for a in (scene.albedo, scene.normal, scene.pbr, scene.depth, scene.emissive)]
+    gb = viewer.Viewer.host_gbuffer(*keep)
+    for _ in range(2):
+        v.render_frame(gb)
+        out = np.zeros((h, w), np.uint32)
+        assert v.read_output(out) == (0, h)
+        ldr = v.download_image("tonemapped")
+        e = oracle.smaa_edge(ldr, 2)
+        assert np.array_equal(np.ascontiguousarray(v.download_image("smaa-edge")).view(np.uint8).reshape(h, w, 2), e)
+        wg = oracle.smaa_weights(e, f["area"], f["search"], 2)
+        assert np.array_equal(v.download_image("smaa-weights"), wg)
+        d = common.rgba8_channel_diff(out, oracle.smaa_blend(ldr, wg))
+        assert d.max() <= 1 and (d == 0).mean() > 0.995
+    v.close()
