@@ -22,6 +22,7 @@
 // B10G11R11 (6/5 mantissa bits), five orders of magnitude coarser than those rounding
 // differences.
 #include "grb_common.cuh"
+#include "grb_shadow.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -60,6 +61,10 @@ struct LightingParams
 	const uint32_t *bitmask;
 	const uint2 *cluster_range;
 	int y0, y1;
+	// shadowed positional lights (grb_deferred_lighting_shadowed only; grb_shadow.cuh)
+	const float *shadow_transforms;    // 16 floats per light: ClustererBindlessTransforms::shadow[index]
+	const uint16_t *const *shadow_maps; // per light: D16_UNORM, res^2 (spot) or 6 res^2 (point cube); null = no shadow
+	int shadow_res;
 };
 
 struct Surface
@@ -179,6 +184,9 @@ __global__ void __launch_bounds__(128) cluster_indices_kernel(const LightingPara
 
 constexpr int kWarpsPerCta = 4;
 
+// SHADOWS: POSITIONAL_LIGHTS_SHADOW (renderer.cpp:369,1126) -- each light's falloff is multiplied by the comparison
+// sample of its own shadow map (point.h:45-74, spot.h:51-77), taken only by the lanes the light reaches.
+template <bool SHADOWS>
 __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(const LightingParams p)
 {
 	__shared__ float s_srgb[256];
@@ -293,6 +301,17 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 				float cone_angle = -(L.x * l2.x + L.y * l2.y + L.z * l2.z);
 				float cone = __saturatef(fmaf(cone_angle, sb.x, sb.y));
 				falloff *= cone * cone;
+			}
+			if (SHADOWS)
+			{
+				const int index = i * 32 + bit;
+				const uint16_t *map = reinterpret_cast<const uint16_t *>(__ldg(reinterpret_cast<const unsigned long long *>(p.shadow_maps) + index));
+				if (map && near && falloff > 0.0f)
+				{
+					const float *m = p.shadow_transforms + 16 * (size_t)index;
+					falloff *= ((tm >> bit) & 1u) ? point_shadow_falloff(m, -l.x, -l.y, -l.z, map, p.shadow_res)
+					                              : spot_shadow_falloff(m, s.pos.x, s.pos.y, s.pos.z, map, p.shadow_res);
+				}
 			}
 			float NoL;
 			float3 b = brdf(s, L, NoL);
@@ -1377,7 +1396,7 @@ extern "C" int32_t grb_deferred_lighting(const GrbGBuffer *g, const GrbCamera *c
 }
 
 static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
-                                        const GrbImage *hdr, GrbRows rows, void *schedule, void *stream, bool blocks_only);
+                                        const GrbImage *hdr, GrbRows rows, void *schedule, void *stream, bool blocks_only, const GrbLightShadows *shadows = nullptr);
 
 extern "C" int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params,
                                                    const GrbClusterBuffers *buf, const GrbImage *hdr, GrbRows rows, void *schedule, void *stream)
@@ -1398,8 +1417,26 @@ extern "C" int32_t grb_deferred_lighting_blocks(const GrbGBuffer *g, const GrbCa
 	return launch_deferred_lighting(g, cam, params, buf, hdr, rows, nullptr, stream, true);
 }
 
+// Shadowed positional lights: the generic one-pixel-per-thread kernel with the comparison sampling of grb_shadow.cuh.
+// (The persistent two-pixel kernel carries no shadow path yet: DESIGN.md section 8.)
+extern "C" int32_t grb_deferred_lighting_shadowed(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
+                                                  const GrbLightShadows *shadows, const GrbImage *hdr, GrbRows rows, void *stream)
+{
+	if (!shadows)
+	{
+		set_last_error("grb_deferred_lighting_shadowed: null shadows (use grb_deferred_lighting for unshadowed lights)");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	if (params && params->num_lights > 0 && (!shadows->transforms || !shadows->maps || shadows->resolution <= 0 || shadows->resolution > 16384))
+	{
+		set_last_error("grb_deferred_lighting_shadowed: transforms / maps must be device arrays of num_lights entries, resolution in 1..16384");
+		return GRB_ERR_INVALID_ARGUMENT;
+	}
+	return launch_deferred_lighting(g, cam, params, buf, hdr, rows, nullptr, stream, true, shadows);
+}
+
 static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *cam, const GrbClusterParameters *params, const GrbClusterBuffers *buf,
-                                        const GrbImage *hdr, GrbRows rows, void *schedule, void *stream, bool blocks_only)
+                                        const GrbImage *hdr, GrbRows rows, void *schedule, void *stream, bool blocks_only, const GrbLightShadows *shadows)
 {
 	if (!g || !cam || !params || !buf || !hdr)
 	{
@@ -1472,11 +1509,14 @@ static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *ca
 	p.cluster_range = reinterpret_cast<const uint2 *>(buf->cluster_range);
 	p.y0 = rows.y0;
 	p.y1 = rows.y1;
+	p.shadow_transforms = shadows ? shadows->transforms : nullptr;
+	p.shadow_maps = shadows ? reinterpret_cast<const uint16_t *const *>(shadows->maps) : nullptr;
+	p.shadow_res = shadows ? shadows->resolution : 0;
 
 	// two pixels per thread (packed fp32) whenever rows can be addressed as aligned pixel pairs
 	static const bool force_1px = getenv("GRB_LIGHTING_1PX") != nullptr;
 	auto aligned8 = [](const void *ptr, int pitch_bytes) { return (reinterpret_cast<uintptr_t>(ptr) % 8) == 0 && (pitch_bytes % 8) == 0; };
-	const bool pairs = !force_1px && (w % 2) == 0 && aligned8(g->albedo.data, g->albedo.row_pitch) && aligned8(g->normal.data, g->normal.row_pitch) &&
+	const bool pairs = !shadows && !force_1px && (w % 2) == 0 && aligned8(g->albedo.data, g->albedo.row_pitch) && aligned8(g->normal.data, g->normal.row_pitch) &&
 	                   aligned8(g->depth.data, g->depth.row_pitch) && (reinterpret_cast<uintptr_t>(g->pbr.data) % 4) == 0 && (g->pbr.row_pitch % 4) == 0 &&
 	                   aligned8(hdr->data, hdr->row_pitch) && (!g->emissive.data || aligned8(g->emissive.data, g->emissive.row_pitch));
 	static const bool force_v2 = getenv("GRB_LIGHTING_V2") != nullptr;
@@ -1546,7 +1586,10 @@ static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *ca
 		return check_launch("grb_deferred_lighting");
 	}
 	dim3 grid((w + 8 * kWarpsPerCta - 1) / (8 * kWarpsPerCta), (rows.y1 - rows.y0 + 3) / 4, 1);
-	deferred_lighting_kernel<<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);
+	if (shadows)
+		deferred_lighting_kernel<true><<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);
+	else
+		deferred_lighting_kernel<false><<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);
 	return check_launch("grb_deferred_lighting");
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -36,10 +37,50 @@ static size_t packed_offset_model(size_t n) { return n * sizeof(PositionalFragme
 static size_t packed_offset_type_mask(size_t n) { return packed_offset_model(n) + n * sizeof(mat_affine); }
 static size_t packed_offset_z_ranges(size_t n) { return packed_offset_type_mask(n) + sizeof(uint32_t) * (ClustererMaxLightsBindless / 32); }
 static size_t packed_size(size_t n) { return packed_offset_z_ranges(n) + sizeof(uvec2) * (n ? n : 1); }
+// with shadows enabled two more arrays follow: [n x mat4 shadow transform][n x device pointer to the light's map]
+static size_t packed_offset_shadow_maps(size_t n) { return packed_size(n) + n * sizeof(mat4); }
+static size_t packed_size_with_shadows(size_t n) { return packed_offset_shadow_maps(n) + n * sizeof(void *); }
 
 size_t LightClusterer::transforms_offset_model() const { return packed_offset_model((size_t)parameters.num_lights); }
 size_t LightClusterer::transforms_offset_type_mask() const { return packed_offset_type_mask((size_t)parameters.num_lights); }
-size_t LightClusterer::transforms_size() const { return packed_size(ClustererMaxLightsBindless); }
+size_t LightClusterer::transforms_size() const
+{
+	return enable_shadows ? packed_size_with_shadows(ClustererMaxLightsBindless) : packed_size(ClustererMaxLightsBindless);
+}
+
+// clusterer.cpp:467-474: the spot light's own view (looking down its axis) and a projection that just covers the cone,
+// near = 0.5 % of the range, biased from clip space to texture coordinates
+mat4 LightClusterer::spot_shadow_transform(const PositionalFragmentInfo &light, float xy_range)
+{
+	const float range = std::tan(xy_range);
+	const mat4 view = mat4_cast(look_at_arbitrary_up(light.direction)) * translate(-light.position);
+	const mat4 proj = perspective(range * 2.0f, 1.0f, 0.005f / light.inv_radius, 1.0f / light.inv_radius);
+	return translate(vec3(0.5f, 0.5f, 0.0f)) * scale(vec3(0.5f, 0.5f, 1.0f)) * proj * view;
+}
+
+// clusterer.cpp:518-521 with math/transforms.cpp:223-224: the six faces share one 90-degree projection (mirrored in x);
+// the shader only needs the two rows that turn the distance along the major axis into the stored depth
+mat4 LightClusterer::point_shadow_transform(const PositionalFragmentInfo &light)
+{
+	const float pi = 3.1415926535897932384626433832795f; // muglm::pi<float>()
+	const mat4 proj = scale(vec3(-1.0f, 1.0f, 1.0f)) * perspective(0.5f * pi, 1.0f, 0.005f / light.inv_radius, 1.0f / light.inv_radius);
+	mat4 m(0.0f);
+	m[0] = vec4(proj[2].z, proj[2].w, proj[3].z, proj[3].w);
+	return m;
+}
+
+GrbLightShadows LightClusterer::get_light_shadows() const
+{
+	GrbLightShadows s = {};
+	if (!enable_shadows || !transforms_buffer)
+		return s;
+	auto *base = transforms_buffer->get<uint8_t>();
+	const size_t n = (size_t)parameters.num_lights;
+	s.transforms = reinterpret_cast<const float *>(base + packed_size(n));
+	s.maps = reinterpret_cast<const void *const *>(base + packed_offset_shadow_maps(n));
+	s.resolution = (int32_t)shadow_resolution;
+	return s;
+}
 
 void LightClusterer::add_render_passes(RenderGraph &graph)
 {
@@ -144,6 +185,8 @@ void LightClusterer::refresh_bindless_prepare(const RenderContext &ctx)
 	const auto &rp = ctx.get_render_parameters();
 	lights.clear();
 	model.clear();
+	shadow_transforms.clear();
+	shadow_maps.clear();
 	volume_index_range.clear();
 	type_mask.assign(ClustererMaxLightsBindless / 32, 0u);
 
@@ -200,6 +243,8 @@ void LightClusterer::refresh_bindless_prepare(const RenderContext &ctx)
 			auto &spot = static_cast<SpotLight &>(*l.light);
 			lights.push_back(spot.get_shader_info(l.transform));
 			model.push_back(spot.build_model_matrix(l.transform));
+			if (enable_shadows)
+				shadow_transforms.push_back(spot_shadow_transform(lights.back(), spot.get_xy_range()));
 		}
 		else
 		{
@@ -210,7 +255,11 @@ void LightClusterer::refresh_bindless_prepare(const RenderContext &ctx)
 			m[0] = vec4(lights.back().position, 1.0f / lights.back().inv_radius);
 			model.push_back(m);
 			type_mask[index >> 5] |= 1u << (index & 31u);
+			if (enable_shadows)
+				shadow_transforms.push_back(point_shadow_transform(lights.back()));
 		}
+		if (enable_shadows)
+			shadow_maps.push_back(l.light->get_shadow_map());
 		index++;
 	}
 
@@ -267,11 +316,13 @@ void LightClusterer::build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd)
 	const size_t model_bytes = n * sizeof(mat_affine);
 	const size_t mask_bytes = sizeof(uint32_t) * (ClustererMaxLightsBindless / 32);
 	const size_t range_bytes = volume_index_range.size() * sizeof(uvec2);
-	const size_t need = lights_bytes + model_bytes + mask_bytes + range_bytes;
+	const size_t shadow_bytes = enable_shadows ? n * (sizeof(mat4) + sizeof(void *)) : 0;
+	const size_t need = lights_bytes + model_bytes + mask_bytes + range_bytes + shadow_bytes;
 	auto stream = reinterpret_cast<cudaStream_t>(cmd.get_stream());
 	// Two pinned staging slots used alternately; a slot is reused only after the copies that
 	// read it have completed (its event), so frames pipeline without a host-device sync.
-	const size_t slot_size = ClustererMaxLightsBindless * (sizeof(PositionalFragmentInfo) + sizeof(mat_affine) + sizeof(uvec2)) + mask_bytes;
+	const size_t slot_size =
+	    ClustererMaxLightsBindless * (sizeof(PositionalFragmentInfo) + sizeof(mat_affine) + sizeof(uvec2) + sizeof(mat4) + sizeof(void *)) + mask_bytes;
 	if (!staging)
 	{
 		if (!Vulkan::cuda_ok(cudaMallocHost(&staging, slot_size * 2), "cudaMallocHost"))
@@ -301,6 +352,11 @@ void LightClusterer::build_cluster_bindless_gpu(Vulkan::CommandBuffer &cmd)
 	std::memcpy(s + lights_bytes, model.data(), model_bytes);
 	std::memcpy(s + lights_bytes + model_bytes, type_mask.data(), mask_bytes);
 	std::memcpy(s + lights_bytes + model_bytes + mask_bytes, volume_index_range.data(), range_bytes);
+	if (enable_shadows && n)
+	{
+		std::memcpy(s + packed_size(n), shadow_transforms.data(), n * sizeof(mat4));
+		std::memcpy(s + packed_offset_shadow_maps(n), shadow_maps.data(), n * sizeof(void *));
+	}
 
 	// the staging slot already has the packed device layout: one H2D copy
 	if (!Vulkan::cuda_ok(cudaMemcpyAsync(transforms_buffer->get_device_pointer(), s, need, cudaMemcpyHostToDevice, stream), "light upload"))

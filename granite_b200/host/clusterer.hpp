@@ -45,6 +45,20 @@ public:
 		lit_y1 = y1;
 		lit_height = height;
 	}
+	// Shadowed positional lights (clusterer.cpp:78-81,173-176): the lighting pass multiplies each light by the PCF
+	// comparison sample of its shadow map (PositionalLight::set_shadow_map).  RENDERING the maps is the caller's
+	// (clusterer.cpp:206-330 is rasterisation, outside the path); the clusterer computes the per-light shadow
+	// transforms (clusterer.cpp:467-474 spot, :518-521 point) and uploads them with the map pointers.
+	void set_enable_shadows(bool enable) { enable_shadows = enable; }
+	bool get_enable_shadows() const { return enable_shadows; }
+	void set_shadow_resolution(unsigned res) { shadow_resolution = res; }
+	unsigned get_shadow_resolution() const { return shadow_resolution; }
+	// ClustererBindlessTransforms::shadow[index] of a spot light (xy_range = SpotLight::get_xy_range) / a point light
+	static mat4 spot_shadow_transform(const PositionalFragmentInfo &light, float xy_range);
+	static mat4 point_shadow_transform(const PositionalFragmentInfo &light);
+	// The C-ABI view of the uploaded shadow data (null members while shadows are disabled).
+	GrbLightShadows get_light_shadows() const;
+	const std::vector<mat4> &get_shadow_transforms() const { return shadow_transforms; }
 	void set_max_spot_lights(unsigned) {}
 	void set_max_point_lights(unsigned) {}
 
@@ -91,6 +105,10 @@ private:
 	std::vector<mat_affine> model;
 	std::vector<uint32_t> type_mask;
 	std::vector<uvec2> volume_index_range;
+	bool enable_shadows = false;
+	unsigned shadow_resolution = 512;
+	std::vector<mat4> shadow_transforms;
+	std::vector<const void *> shadow_maps;
 	std::vector<unsigned> sort_order;
 	std::vector<float> sort_keys;
 	// pinned staging copy of {lights, model, type_mask, z ranges} for the async upload

@@ -38,6 +38,11 @@ public:
 	// local-space bounds the scene's visibility test transforms by the node transform
 	// (renderer/lights/lights.cpp:77-89 spot, :196-201 point; renderer/scene.cpp:1130)
 	const AABB &get_static_aabb() const { return aabb; }
+	// The light's shadow map (SpotLight / PointLight::set_shadow_info, renderer/lights/lights.cpp:91-95,222-226): device
+	// memory the CALLER rendered and owns -- D16_UNORM, resolution^2 texels for a spot light, 6 faces of resolution^2
+	// (+X -X +Y -Y +Z -Z) for a point light, resolution = LightClusterer::set_shadow_resolution.  Null: casts no shadow.
+	void set_shadow_map(const void *device_d16) { shadow_map = device_d16; }
+	const void *get_shadow_map() const { return shadow_map; }
 
 protected:
 	vec3 color = vec3(1.0f);
@@ -49,6 +54,7 @@ protected:
 
 private:
 	Type type;
+	const void *shadow_map = nullptr;
 };
 
 class PointLight : public PositionalLight
@@ -68,6 +74,7 @@ public:
 	void set_spot_parameters(float inner_cone, float outer_cone);
 	PositionalFragmentInfo get_shader_info(const mat_affine &transform) const;
 	mat_affine build_model_matrix(const mat_affine &transform) const;
+	float get_xy_range() const { return xy_range; }
 
 private:
 	float inner_cone = 0.4f;

@@ -91,4 +91,45 @@ uint16_t floatToHalf(float v)
 		h = 0x7c00u;
 	return (uint16_t)(sign | h);
 }
+
+quat rotate_vector(vec3 from, vec3 to)
+{
+	from = normalize(from);
+	to = normalize(to);
+	const float cos_angle = dot(from, to);
+	if (std::fabs(cos_angle) > 0.9999f)
+	{
+		if (cos_angle > 0.9999f)
+			return quat(1.0f, 0.0f, 0.0f, 0.0f);
+		// opposite vectors: half a turn about any axis perpendicular to `from`
+		vec3 axis = cross(vec3(1.0f, 0.0f, 0.0f), from);
+		if (dot(axis, axis) > 0.001f)
+			axis = normalize(axis);
+		else
+			axis = normalize(cross(vec3(0.0f, 1.0f, 0.0f), from));
+		return quat(0.0f, axis);
+	}
+	const vec3 axis = normalize(cross(from, to));
+	const vec3 half_vector = normalize(from + to);
+	const float cos_half = clamp(dot(half_vector, from), 0.0f, 1.0f);
+	const float sin_half = std::sqrt(1.0f - cos_half * cos_half);
+	return quat(cos_half, axis * sin_half);
+}
+
+quat look_at_arbitrary_up(const vec3 &direction)
+{
+	return rotate_vector(normalize(direction), vec3(0.0f, 0.0f, -1.0f));
+}
+
+mat4 mat4_cast(const quat &q)
+{
+	const float xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z;
+	const float xz = q.x * q.z, xy = q.x * q.y, yz = q.y * q.z;
+	const float wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
+	mat4 m(1.0f);
+	m[0] = vec4(1.0f - 2.0f * (yy + zz), 2.0f * (xy + wz), 2.0f * (xz - wy), 0.0f);
+	m[1] = vec4(2.0f * (xy - wz), 1.0f - 2.0f * (xx + zz), 2.0f * (yz + wx), 0.0f);
+	m[2] = vec4(2.0f * (xz + wy), 2.0f * (yz - wx), 1.0f - 2.0f * (xx + yy), 0.0f);
+	return m;
+}
 } // namespace muglm

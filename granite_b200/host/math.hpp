@@ -120,6 +120,21 @@ mat4 inverse(const mat4 &m);
 mat4 perspective(float fovy, float aspect, float z_near, float z_far);
 constexpr float InfiniteFarPlane = 3.402823466e+38f;
 
+// Rotations for the shadow views of the positional lights (math/muglm/muglm.hpp quat: w + (x, y, z)).
+struct quat
+{
+	float w = 1.0f, x = 0.0f, y = 0.0f, z = 0.0f;
+	quat() = default;
+	quat(float w_, const vec3 &v) : w(w_), x(v.x), y(v.y), z(v.z) {}
+	quat(float w_, float x_, float y_, float z_) : w(w_), x(x_), y(y_), z(z_) {}
+};
+// Shortest rotation taking `from` onto `to` (math/transforms.cpp:122-148), degenerate cases included.
+quat rotate_vector(vec3 from, vec3 to);
+// Rotation that turns `direction` onto the view axis -Z with whatever roll falls out (math/transforms.cpp:180-183).
+quat look_at_arbitrary_up(const vec3 &direction);
+// Rotation matrix of a unit quaternion (math/muglm/muglm.cpp:29-62).
+mat4 mat4_cast(const quat &q);
+
 // Rows of a 3x4 affine transform, like muglm::mat_affine (math/muglm/muglm.hpp:927-957).
 struct mat_affine
 {

@@ -57,7 +57,11 @@ void DeferredLightRenderer::render_light(Vulkan::CommandBuffer &cmd, const Rende
 	GrbImage hdr_img = hdr.as_grb();
 	// Row-sharded frames (rows != whole image, no schedule): the block form, so that the exchange-dependent
 	// post chain of the previous frame can interleave with this pass (see grb_deferred_lighting_blocks).
-	if (blocks_form)
+	// POSITIONAL_LIGHTS_SHADOW (renderer.cpp:1124-1131): the clusterer holds the shadow transforms and map pointers
+	const GrbLightShadows shadows = light->cluster->get_light_shadows();
+	if (shadows.maps)
+		cmd.check(grb_deferred_lighting_shadowed(&g, &cam, &params, &buffers, &shadows, &hdr_img, rows, cmd.get_stream_handle()), "grb_deferred_lighting_shadowed");
+	else if (blocks_form)
 		cmd.check(grb_deferred_lighting_blocks(&g, &cam, &params, &buffers, &hdr_img, rows, cmd.get_stream_handle()), "grb_deferred_lighting_blocks");
 	else
 		cmd.check(grb_deferred_lighting_scheduled(&g, &cam, &params, &buffers, &hdr_img, rows, schedule, cmd.get_stream_handle()), "grb_deferred_lighting");

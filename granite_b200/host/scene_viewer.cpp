@@ -125,6 +125,8 @@ void GrbhViewer::bake_render_graph()
 	cluster.set_scene_lights(&scene_lights);
 	cluster.set_base_render_context(&context);
 	cluster.set_async_compute(getenv("GRB_NO_ASYNC_CLUSTER") == nullptr);
+	cluster.set_enable_shadows(config.clustered_lights_shadows != 0);
+	cluster.set_shadow_resolution(config.clustered_lights_shadow_resolution > 0 ? (unsigned)config.clustered_lights_shadow_resolution : 512u);
 	if (bands.size() > 1)
 	{
 		const GrbRows lit = input_rows();
@@ -507,6 +509,36 @@ extern "C" int32_t grbh_viewer_set_lights(GrbhViewer *v, const GrbhLights *l)
 	}
 	return 0;
 	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_set_light_shadow_maps(GrbhViewer *v, const void *const *device_maps, int32_t count)
+{
+	if (!v || count < 0 || (count > 0 && !device_maps))
+		return fail("grbh_viewer_set_light_shadow_maps: bad arguments");
+	if ((size_t)count != v->scene_lights.size())
+		return fail("grbh_viewer_set_light_shadow_maps: one entry per light of the last grbh_viewer_set_lights call");
+	if (!v->config.clustered_lights_shadows)
+		return fail("grbh_viewer_set_light_shadow_maps: the viewer was created without clustered_lights_shadows");
+	for (int i = 0; i < count; i++)
+		v->scene_lights[(size_t)i].light->set_shadow_map(device_maps[i]);
+	return 0;
+}
+
+extern "C" int32_t grbh_viewer_get_shadow_transforms(GrbhViewer *v, float *out16_per_light, int32_t capacity)
+{
+	if (!v)
+		return fail("null viewer");
+	// host prep only (no GPU work), like grbh_viewer_get_light_prep
+	v->cluster.set_scene_lights(&v->scene_lights);
+	v->cluster.set_enable_shadows(true);
+	v->cluster.refresh(v->context);
+	v->cluster.set_enable_shadows(v->config.clustered_lights_shadows != 0);
+	const auto &t = v->cluster.get_shadow_transforms();
+	if ((int64_t)t.size() > capacity)
+		return fail("grbh_viewer_get_shadow_transforms: capacity too small");
+	if (out16_per_light && !t.empty())
+		std::memcpy(out16_per_light, t.data(), 64 * t.size());
+	return (int32_t)t.size();
 }
 
 extern "C" int32_t grbh_viewer_set_smaa_lookup_textures(GrbhViewer *v, const uint8_t *area_rg8, const uint8_t *search_r8)

@@ -22,7 +22,8 @@ class GrbhViewerConfig(C.Structure):
     _fields_ = [("cuda_device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("post_aa", C.c_int32),
                 ("hdr_bloom", C.c_int32), ("dynamic_exposure", C.c_int32), ("cluster_res", C.c_int32 * 3),
                 ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p), ("pipelined_io", C.c_int32),
-                ("hdr10_output", C.c_int32), ("hdr10_max_content_light_level", C.c_float)]
+                ("hdr10_output", C.c_int32), ("hdr10_max_content_light_level", C.c_float),
+                ("clustered_lights_shadows", C.c_int32), ("clustered_lights_shadow_resolution", C.c_int32)]
 
 
 class GrbhLights(C.Structure):
@@ -229,7 +230,8 @@ def shard_plan(width, height, bands, rank, fxaa=False) -> dict:
 
 class Viewer:
     def __init__(self, width, height, post_aa=AA_NONE, hdr_bloom=True, dynamic_exposure=True, cuda_device=0,
-                 cluster_res=(128, 64, 4096), timestamps=False, stream=None, pipelined_io=False, hdr10_output=False, hdr10_max_cll=1000.0):
+                 cluster_res=(128, 64, 4096), timestamps=False, stream=None, pipelined_io=False, hdr10_output=False, hdr10_max_cll=1000.0,
+                 light_shadows=False, shadow_resolution=512):
         cfg = GrbhViewerConfig()
         cfg.cuda_device = cuda_device
         cfg.width, cfg.height = width, height
@@ -242,6 +244,8 @@ class Viewer:
         cfg.pipelined_io = int(pipelined_io)
         cfg.hdr10_output = int(hdr10_output)
         cfg.hdr10_max_content_light_level = float(hdr10_max_cll)
+        cfg.clustered_lights_shadows = int(light_shadows)
+        cfg.clustered_lights_shadow_resolution = int(shadow_resolution)
         self.width, self.height = width, height
         self._h = C.c_void_p()
         _check(lib().grbh_viewer_create(C.byref(cfg), C.byref(self._h)), "grbh_viewer_create")
@@ -253,6 +257,19 @@ class Viewer:
         assert a.size == 160 * 560 * 2 and s_.size == 64 * 16
         _check(lib().grbh_viewer_set_smaa_lookup_textures(self._h, a.ctypes.data_as(C.c_void_p), s_.ctypes.data_as(C.c_void_p)),
                "grbh_viewer_set_smaa_lookup_textures")
+
+    def set_light_shadow_maps(self, device_pointers):
+        """One device pointer (int, 0 = no shadow) per light of the last set_lights call, in that order."""
+        arr = (C.c_void_p * len(device_pointers))(*[C.c_void_p(int(p) or None) for p in device_pointers])
+        _check(lib().grbh_viewer_set_light_shadow_maps(self._h, arr, len(device_pointers)), "grbh_viewer_set_light_shadow_maps")
+
+    def shadow_transforms(self, capacity=4096):
+        """(n, 16) float32: ClustererBindlessTransforms::shadow of the visible lights in cluster order (host prep only)."""
+        out = np.zeros((capacity, 16), np.float32)
+        n = lib().grbh_viewer_get_shadow_transforms(self._h, out.ctypes.data_as(C.c_void_p), capacity)
+        if n < 0:
+            raise capi.GrbError("grbh_viewer_get_shadow_transforms: " + (lib().grbh_last_error() or b"").decode())
+        return out[:n].copy()
 
     def close(self):
         if self._h:

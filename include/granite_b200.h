@@ -197,6 +197,27 @@ int32_t grb_deferred_lighting_scheduled(const GrbGBuffer *gbuffer, const GrbCame
                                         const GrbClusterBuffers *buffers, const GrbImage *hdr_inout, GrbRows rows, void *schedule,
                                         void *stream);
 
+/* ---- shadowed positional lights: clustering.frag with POSITIONAL_LIGHTS_SHADOW and the PCF sampler
+ * (renderer.cpp:369,1126; assets/shaders/lights/point.h:45-74, spot.h:51-77, pcf.h:98-99).  The shadow maps are
+ * INPUTS, as the G-buffer is: what LightClusterer::render_shadow (clusterer.cpp:206-330) rasterised, one D16_UNORM
+ * image per light (clusterer.cpp:397-407), bound bindlessly by update_bindless_descriptors (clusterer.cpp:1209-1252).
+ * Sampling follows StockSampler::LinearShadow (vulkan/device.cpp:1086-1088: GREATER_OR_EQUAL, linear, clamp to edge)
+ * as the Vulkan specification defines comparison filtering, cube maps with edge handling across faces. ---- */
+typedef struct GrbLightShadows
+{
+	/* num_lights x 16 floats, device: ClustererBindlessTransforms::shadow[index], column-major.  Spot light: bias *
+	 * projection * view (clusterer.cpp:467-474); point light: column 0 = (proj[2].zw, proj[3].zw) (clusterer.cpp:518-521). */
+	const float *transforms;
+	/* num_lights device pointers, device array: resolution^2 D16 texels for a spot light, 6 x resolution^2 (layers
+	 * +X -X +Y -Y +Z -Z) for a point light; a null entry = the light casts no shadow (its falloff stays 1). */
+	const void *const *maps;
+	int32_t resolution; /* LightClusterer::set_shadow_resolution (clusterer.cpp:78-81), 512 by default */
+} GrbLightShadows;
+/* The lighting pass with shadowed positional lights; every other argument as grb_deferred_lighting. */
+int32_t grb_deferred_lighting_shadowed(const GrbGBuffer *gbuffer, const GrbCamera *cam, const GrbClusterParameters *params,
+                                       const GrbClusterBuffers *buf, const GrbLightShadows *shadows, const GrbImage *hdr, GrbRows rows,
+                                       void *stream);
+
 /* Diagnostic: the (tile index, Z slice) the lighting kernel addresses for every pixel, -1 for sky
  * (clusterer_bindless.h:39-47).  Same device function as grb_deferred_lighting uses; exists so
  * the "bit-exact cluster indices" contract can be checked directly. */

@@ -56,6 +56,9 @@ typedef struct GrbhViewerConfig
 	                             * (and TAA-resolved) scene goes through a "ui" pass (cleared to 0,0,0,1: no widgets) and the
 	                             * "pq10" pass into an A2B10G10R10 image of ST.2084 codes, BT.2020 primaries, D65 */
 	float hdr10_max_content_light_level; /* VkHdrMetadataEXT::maxContentLightLevel in nits; <= 0: 1000 */
+	int32_t clustered_lights_shadows;           /* config "clusteredLightsShadows" (scene_viewer_application.cpp:214-215): the lighting
+	                                             * pass samples the per-light shadow maps of grbh_viewer_set_light_shadow_maps */
+	int32_t clustered_lights_shadow_resolution; /* "clusteredLightsShadowsResolution" (:216-217); <= 0: 512 */
 } GrbhViewerConfig;
 
 /* Raw light list as the application owns it (before the clusterer sorts/packs it). */
@@ -93,6 +96,13 @@ int32_t grbh_viewer_set_camera(GrbhViewer *viewer, const float *projection16, co
 int32_t grbh_viewer_set_directional(GrbhViewer *viewer, const float *color3, const float *direction3);
 int32_t grbh_viewer_set_lights(GrbhViewer *viewer, const GrbhLights *lights);
 int32_t grbh_viewer_set_exposure(GrbhViewer *viewer, float exposure);
+/* Shadow maps of the lights of the last grbh_viewer_set_lights call, in THAT order: `count` device pointers (host array),
+ * each D16_UNORM of resolution^2 texels (spot) or 6 x resolution^2 (point, faces +X -X +Y -Y +Z -Z); null = no shadow.
+ * The caller renders and owns them (the reference's LightClusterer::render_shadow is rasterisation, outside the path). */
+int32_t grbh_viewer_set_light_shadow_maps(GrbhViewer *viewer, const void *const *device_maps, int32_t count);
+/* ClustererBindlessTransforms::shadow[i] of the visible lights in cluster order, as the clusterer uploads them (host
+ * preparation only, no GPU work): capacity x 16 floats.  Returns the light count. */
+int32_t grbh_viewer_get_shadow_transforms(GrbhViewer *viewer, float *out16_per_light, int32_t capacity);
 
 /* The two lookup textures SMAA samples (the payloads of the reference's assets/textures/smaa/area.gtx: 160x560 R8G8_UNORM,
  * and search.gtx: 64x16 R8_UNORM), uploaded once to the viewer's device.  grbh_load_gtx reads such a container from a

@@ -9,6 +9,7 @@
 #ifndef ORACLE_H_
 #define ORACLE_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -79,6 +80,10 @@ void orc_cluster_params(const orc_camera_t *cam, int num_lights, int res_x, int 
 void orc_light_z_ranges(const orc_camera_t *cam, const orc_light_t *lights, const float *model_rows,
                         const uint32_t *type_mask, int num_lights, int res_z, uint32_t *z_ranges);
 
+/* ClustererBindlessTransforms::shadow[index] (clusterer.cpp:467-474 spot, :518-521 point), column-major mat4. */
+void orc_spot_shadow_transform(const orc_light_t *light, float xy_range, float *out16);
+void orc_point_shadow_transform(const orc_light_t *light, float *out16);
+
 /* ---- light visibility: renderer/scene.cpp:333-358 gather_positional_lights ---- */
 void orc_frustum_planes(const float *inv_view_projection16, float *planes24);                 /* math/frustum.cpp:109-156 */
 void orc_transform_aabb(const float *rows12, const float *lo3, const float *hi3, float *out_lo3, float *out_hi3); /* math/simd.hpp:386-419 */
@@ -120,6 +125,27 @@ void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, cons
                            const uint32_t *bitmask, const uint32_t *cluster_range,
                            uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
                            int32_t *out_light_count, int y0, int y1);
+
+/* Shadowed positional lights (POSITIONAL_LIGHTS_SHADOW with the PCF sampler; point.h:45-74, spot.h:51-77,
+ * pcf.h:98-99).  transforms: 16 floats per light = ClustererBindlessTransforms::shadow[index], column-major
+ * (spot: bias * proj * view, clusterer.cpp:467-474; point: column 0 = (proj[2].zw, proj[3].zw), clusterer.cpp:518-521).
+ * maps[index]: D16_UNORM, resolution^2 texels (spot) or 6 faces of resolution^2 in Vulkan layer order
+ * +X -X +Y -Y +Z -Z (point); NULL = the light casts no shadow. */
+typedef struct
+{
+	const float *transforms;
+	const uint16_t *const *maps;
+	int resolution;
+} orc_shadows_t;
+void orc_deferred_lighting_shadowed(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
+                                    const orc_light_t *lights, const uint32_t *type_mask,
+                                    const uint32_t *bitmask, const uint32_t *cluster_range, const orc_shadows_t *shadows,
+                                    uint32_t *hdr_out, int y0, int y1);
+/* the two comparison samplers on their own (Vulkan specification's filtering, fp32 weights) */
+float orc_shadow_sample_2d(const uint16_t *map, int res, float clip_x, float clip_y, float clip_z, float clip_w);
+float orc_shadow_sample_cube(const uint16_t *map, int res, float dx, float dy, float dz, float ref);
+/* texel (i, j) of cube face f, i or j possibly one step outside the face (-> the adjacent face); 0 at a corner */
+int orc_shadow_cube_texel(int res, int f, int i, int j, size_t *texel);
 
 /* One additive blend into a B10G11R11 attachment (renderer.cpp:1009-1011): dst = q(unpack(dst) + src) where
  * mask != 0.  Used by the tests that run the reference's own fragment shaders (oracle/_ref). */

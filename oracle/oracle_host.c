@@ -569,3 +569,101 @@ void orc_rec709_to_display_primaries(const float *primaries8, float *out9)
 		for (int r = 0; r < 3; r++)
 			out9[c * 3 + r] = (float)(inv[0 * 3 + r] * src[c * 3 + 0] + inv[1 * 3 + r] * src[c * 3 + 1] + inv[2 * 3 + r] * src[c * 3 + 2]);
 }
+
+/* ---- shadow transforms of the positional lights: ClustererBindlessTransforms::shadow[index] ---- */
+/* math/transforms.cpp:122-148 rotate_vector (muglm normalize = v * (1 / sqrt(dot))), :180-183 look_at_arbitrary_up;
+ * quaternion as (w, x, y, z) */
+static vec3 v3_cross(vec3 a, vec3 b)
+{
+	return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+static vec3 normalize_muglm(vec3 v)
+{
+	float inv = 1.0f / sqrtf(v3_dot(v, v));
+	return v3(v.x * inv, v.y * inv, v.z * inv);
+}
+
+static void rotate_vector(vec3 from, vec3 to, float *q)
+{
+	from = normalize_muglm(from);
+	to = normalize_muglm(to);
+	float cos_angle = v3_dot(from, to);
+	if (fabsf(cos_angle) > 0.9999f)
+	{
+		if (cos_angle > 0.9999f)
+		{
+			q[0] = 1.0f; q[1] = q[2] = q[3] = 0.0f;
+			return;
+		}
+		vec3 rotation = v3_cross(v3(1.0f, 0.0f, 0.0f), from);
+		if (v3_dot(rotation, rotation) > 0.001f)
+			rotation = normalize_muglm(rotation);
+		else
+			rotation = normalize_muglm(v3_cross(v3(0.0f, 1.0f, 0.0f), from));
+		q[0] = 0.0f; q[1] = rotation.x; q[2] = rotation.y; q[3] = rotation.z;
+		return;
+	}
+	vec3 rotation = normalize_muglm(v3_cross(from, to));
+	vec3 half_vector = normalize_muglm(v3_add(from, to));
+	float cos_half_range = f_clamp(v3_dot(half_vector, from), 0.0f, 1.0f);
+	float sin_half_angle = sqrtf(1.0f - cos_half_range * cos_half_range);
+	q[0] = cos_half_range; q[1] = rotation.x * sin_half_angle; q[2] = rotation.y * sin_half_angle; q[3] = rotation.z * sin_half_angle;
+}
+
+/* math/muglm/muglm.cpp:29-62 mat3_cast / mat4_cast, column-major 4x4 */
+static void mat4_cast(const float *q, float *m)
+{
+	float w = q[0], x = q[1], y = q[2], z = q[3];
+	float qxx = x * x, qyy = y * y, qzz = z * z, qxz = x * z, qxy = x * y, qyz = y * z, qwx = w * x, qwy = w * y, qwz = w * z;
+	for (int i = 0; i < 16; i++)
+		m[i] = 0.0f;
+	m[0] = 1.0f - 2.0f * (qyy + qzz); m[1] = 2.0f * (qxy + qwz); m[2] = 2.0f * (qxz - qwy);
+	m[4] = 2.0f * (qxy - qwz); m[5] = 1.0f - 2.0f * (qxx + qzz); m[6] = 2.0f * (qyz + qwx);
+	m[8] = 2.0f * (qxz + qwy); m[9] = 2.0f * (qyz - qwx); m[10] = 1.0f - 2.0f * (qxx + qyy);
+	m[15] = 1.0f;
+}
+
+static void mat4_translate(float x, float y, float z, float *m)
+{
+	for (int i = 0; i < 16; i++)
+		m[i] = (i % 5) == 0 ? 1.0f : 0.0f;
+	m[12] = x; m[13] = y; m[14] = z;
+}
+
+static void mat4_scale(float x, float y, float z, float *m)
+{
+	for (int i = 0; i < 16; i++)
+		m[i] = 0.0f;
+	m[0] = x; m[5] = y; m[10] = z; m[15] = 1.0f;
+}
+
+/* renderer/lights/clusterer.cpp:467-474 (gather_bindless_spot_shadow_renderables) */
+void orc_spot_shadow_transform(const orc_light_t *light, float xy_range, float *out16)
+{
+	float range = tanf(xy_range);
+	float q[4], rot[16], tr[16], view[16], proj[16], bias_t[16], bias_s[16], a[16], b[16];
+	vec3 dir = normalize_muglm(v3(light->direction[0], light->direction[1], light->direction[2]));
+	rotate_vector(dir, v3(0.0f, 0.0f, -1.0f), q);
+	mat4_cast(q, rot);
+	mat4_translate(-light->position[0], -light->position[1], -light->position[2], tr);
+	orc_mat4_mul(rot, tr, view);
+	orc_perspective(range * 2.0f, 1.0f, 0.005f / light->inv_radius, 1.0f / light->inv_radius, proj);
+	mat4_translate(0.5f, 0.5f, 0.0f, bias_t);
+	mat4_scale(0.5f, 0.5f, 1.0f, bias_s);
+	orc_mat4_mul(bias_t, bias_s, a); /* left to right: ((T * S) * proj) * view */
+	orc_mat4_mul(a, proj, b);
+	orc_mat4_mul(b, view, out16);
+}
+
+/* renderer/lights/clusterer.cpp:518-521 with math/transforms.cpp:223-224: column 0 = (proj[2].zw, proj[3].zw) */
+void orc_point_shadow_transform(const orc_light_t *light, float *out16)
+{
+	float flip[16], p[16], proj[16];
+	mat4_scale(-1.0f, 1.0f, 1.0f, flip);
+	orc_perspective(0.5f * 3.1415926535897932384626433832795f, 1.0f, 0.005f / light->inv_radius, 1.0f / light->inv_radius, p);
+	orc_mat4_mul(flip, p, proj);
+	for (int i = 0; i < 16; i++)
+		out16[i] = 0.0f;
+	out16[0] = proj[10]; out16[1] = proj[11]; out16[2] = proj[14]; out16[3] = proj[15];
+}

@@ -81,8 +81,141 @@ static vec3 brdf_terms(vec3 base_color, vec3 N, float metallic, float material_r
 	return v3_add(specref, diffuse);
 }
 
-/* point.h:33-81 compute_point_color (POSITIONAL_LIGHTS_SHADOW undefined => shadow_falloff = 1) */
-static vec3 compute_point_color(const orc_light_t *pt, vec3 world_pos, vec3 *light_dir)
+
+/* ---------------------------------------------------------------------------------------------
+ * Shadowed positional lights (POSITIONAL_LIGHTS_SHADOW, PCF; renderer.cpp:369,1126).
+ *
+ * The reference samples one D16_UNORM image per light (clusterer.cpp:397-407: 2-D for a spot light, a cube of
+ * 6 layers for a point light, shadow_resolution^2 each) through StockSampler::LinearShadow
+ * (vulkan/device.cpp:1086-1088,1118-1120,1146-1149): compare GREATER_OR_EQUAL, linear filter, clamp to edge.
+ * A texture unit's comparison filtering is specified by the Vulkan specification ("Texel Input Operations /
+ * Depth Compare Operation" then "Texel Filtering"), restated here in fp32:
+ *   - D_ref is clamped to [0, 1] (fixed-point depth format), each of the 2 x 2 texels gives 1.0 where
+ *     D_ref >= D_texel (D_texel = code / 65535), else 0.0;
+ *   - the four results are blended with the bilinear weights of (u, v) = (s W - 0.5, t H - 0.5) -- the oracle's
+ *     bilin_setup / bilin_mix, exact fp32 weights where hardware keeps 8 fractional bits;
+ *   - a 2-D image clamps texel indices to the edge; a cube map selects the face by the major axis (ties: z over
+ *     y over x) with the (s_c, t_c) table of the specification, and a footprint that leaves the face takes the
+ *     texel across the edge from the adjacent face ("Cube Map Edge Handling"); at a corner, where the fourth
+ *     texel does not exist, it is replaced by the average of the other three.
+ * A NULL map means "this light casts no shadow" (shadow_falloff = 1, the unshadowed shaders).
+ * --------------------------------------------------------------------------------------------- */
+static float shadow_compare(const uint16_t *map, size_t texel, float ref)
+{
+	return ref >= (float)map[texel] / 65535.0f ? 1.0f : 0.0f;
+}
+
+/* textureProjLod(sampler2DShadow, clip, 0.0): pcf.h:98-99 (SHADOW_MAP_PCF_KERNEL_WIDE undefined) */
+float orc_shadow_sample_2d(const uint16_t *map, int res, float clip_x, float clip_y, float clip_z, float clip_w)
+{
+	float s = clip_x / clip_w, t = clip_y / clip_w;
+	float ref = f_clamp(clip_z / clip_w, 0.0f, 1.0f);
+	if (!(ref == ref))
+		ref = 0.0f;
+	bilin_t b = bilin_setup(s, t, res, res);
+	int x0 = b.x0 < 0 ? 0 : (b.x0 > res - 1 ? res - 1 : b.x0), x1 = b.x1 < 0 ? 0 : (b.x1 > res - 1 ? res - 1 : b.x1);
+	int y0 = b.y0 < 0 ? 0 : (b.y0 > res - 1 ? res - 1 : b.y0), y1 = b.y1 < 0 ? 0 : (b.y1 > res - 1 ? res - 1 : b.y1);
+	float c00 = shadow_compare(map, (size_t)y0 * res + x0, ref), c10 = shadow_compare(map, (size_t)y0 * res + x1, ref);
+	float c01 = shadow_compare(map, (size_t)y1 * res + x0, ref), c11 = shadow_compare(map, (size_t)y1 * res + x1, ref);
+	return bilin_mix(c00, c10, c01, c11, b.a, b.b);
+}
+
+/* Texel (i, j) of cube face f, where i or j may be one step outside [0, res): the texel across that edge.
+ * Worked in doubled integer coordinates on the cube of half-size `res`: a texel centre of face f is the point
+ * with major-axis component +-res and in-face components 2 i + 1 - res (odd, |.| < res).  One step outside
+ * gives +-(res + 1): that axis becomes the major one (+-res) and the old major axis holds the edge texel of
+ * the neighbouring face, +-(res - 1).  Returns 0 at a corner (both outside). */
+int orc_shadow_cube_texel(int res, int f, int i, int j, size_t *texel)
+{
+	int a = 2 * i + 1 - res, b = 2 * j + 1 - res; /* s_c, t_c in doubled texel units */
+	int out_a = a < -res || a > res, out_b = b < -res || b > res;
+	if (out_a && out_b)
+		return 0;
+	/* face -> direction (x, y, z): inverse of the specification's table (s_c, t_c, m_a) */
+	int m = res, x, y, z;
+	switch (f)
+	{
+	case 0: x = m; y = -b; z = -a; break;  /* +X: s_c = -z, t_c = -y */
+	case 1: x = -m; y = -b; z = a; break;  /* -X: s_c = +z, t_c = -y */
+	case 2: x = a; y = m; z = b; break;    /* +Y: s_c = +x, t_c = +z */
+	case 3: x = a; y = -m; z = -b; break;  /* -Y: s_c = +x, t_c = -z */
+	case 4: x = a; y = -b; z = m; break;   /* +Z: s_c = +x, t_c = -y */
+	default: x = -a; y = -b; z = -m; break; /* -Z: s_c = -x, t_c = -y */
+	}
+	if (out_a || out_b)
+	{
+		int *v[3] = { &x, &y, &z };
+		for (int k = 0; k < 3; k++)
+		{
+			if (*v[k] == m || *v[k] == -m)
+				*v[k] = *v[k] > 0 ? res - 1 : -(res - 1); /* old major axis: edge texel of the neighbour */
+			else if (*v[k] > res || *v[k] < -res)
+				*v[k] = *v[k] > 0 ? res : -res; /* new major axis */
+		}
+		int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y;
+		int nf, sc, tc;
+		if (ax == res) { nf = x > 0 ? 0 : 1; sc = x > 0 ? -z : z; tc = -y; }
+		else if (ay == res) { nf = y > 0 ? 2 : 3; sc = x; tc = y > 0 ? z : -z; }
+		else { nf = z > 0 ? 4 : 5; sc = z > 0 ? x : -x; tc = -y; }
+		f = nf;
+		a = sc;
+		b = tc;
+	}
+	int ti = (a + res - 1) / 2, tj = (b + res - 1) / 2;
+	*texel = ((size_t)f * res + tj) * res + ti;
+	return 1;
+}
+
+/* texture(samplerCubeShadow, vec4(dir, ref)): point.h:56-71 */
+float orc_shadow_sample_cube(const uint16_t *map, int res, float dx, float dy, float dz, float ref)
+{
+	ref = f_clamp(ref, 0.0f, 1.0f);
+	if (!(ref == ref))
+		ref = 0.0f;
+	float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+	int face;
+	float sc, tc, ma;
+	if (az >= ax && az >= ay) { face = dz < 0.0f ? 5 : 4; sc = dz < 0.0f ? -dx : dx; tc = -dy; ma = az; }
+	else if (ay >= ax) { face = dy < 0.0f ? 3 : 2; sc = dx; tc = dy < 0.0f ? -dz : dz; ma = ay; }
+	else { face = dx < 0.0f ? 1 : 0; sc = dx < 0.0f ? dz : -dz; tc = -dy; ma = ax; }
+	float s = 0.5f * (sc / ma) + 0.5f, t = 0.5f * (tc / ma) + 0.5f;
+	bilin_t b = bilin_setup(s, t, res, res);
+	int xs[2] = { b.x0, b.x1 }, ys[2] = { b.y0, b.y1 };
+	for (int k = 0; k < 2; k++)
+	{
+		/* a face coordinate is within [0, 1] up to rounding: the footprint is at most one texel outside */
+		xs[k] = xs[k] < -1 ? -1 : (xs[k] > res ? res : xs[k]);
+		ys[k] = ys[k] < -1 ? -1 : (ys[k] > res ? res : ys[k]);
+	}
+	float c[4];
+	int have[4], n = 0;
+	float sum = 0.0f;
+	for (int k = 0; k < 4; k++)
+	{
+		size_t texel = 0;
+		have[k] = orc_shadow_cube_texel(res, face, xs[k & 1], ys[k >> 1], &texel);
+		c[k] = have[k] ? shadow_compare(map, texel, ref) : 0.0f;
+		if (have[k]) { sum += c[k]; n++; }
+	}
+	if (n == 3)
+		for (int k = 0; k < 4; k++)
+			if (!have[k])
+				c[k] = sum / 3.0f;
+	return bilin_mix(c[0], c[1], c[2], c[3], b.a, b.b);
+}
+
+/* mat4 * vec4(world_pos, 1): the association of the generated reference code (GLM: (c0 x + c1 y) + (c2 z + c3 w)) */
+static vec4 shadow_clip(const float *m, vec3 p)
+{
+	return v4((m[0] * p.x + m[4] * p.y) + (m[8] * p.z + m[12] * 1.0f), (m[1] * p.x + m[5] * p.y) + (m[9] * p.z + m[13] * 1.0f),
+	          (m[2] * p.x + m[6] * p.y) + (m[10] * p.z + m[14] * 1.0f), (m[3] * p.x + m[7] * p.y) + (m[11] * p.z + m[15] * 1.0f));
+}
+
+/* the light's shadow inputs for one evaluation; map == NULL => unshadowed */
+typedef struct { const float *transform; const uint16_t *map; int res; } light_shadow_t;
+
+/* point.h:33-81 compute_point_color */
+static vec3 compute_point_color(const orc_light_t *pt, vec3 world_pos, vec3 *light_dir, light_shadow_t sh)
 {
 	vec3 light_pos = v3(pt->position[0], pt->position[1], pt->position[2]);
 	vec3 full = v3_sub(world_pos, light_pos);
@@ -91,7 +224,15 @@ static vec3 compute_point_color(const orc_light_t *pt, vec3 world_pos, vec3 *lig
 	float static_falloff = 1.0f - f_smoothstep(0.9f, 1.0f, light_dist * pt->inv_radius);
 	if (static_falloff > 0.0f)
 	{
-		const float shadow_falloff = 1.0f;
+		float shadow_falloff = 1.0f;
+		if (sh.map)
+		{
+			/* point.h:46-49,67-71: reference depth of the cube face along the major axis */
+			float max_z = f_max(f_max(fabsf(full.x), fabsf(full.y)), fabsf(full.z));
+			const float *t = sh.transform; /* shadow[index][0] = (proj[2].zw, proj[3].zw), clusterer.cpp:521 */
+			float ref_x = t[2] - t[0] * max_z, ref_y = t[3] - t[1] * max_z;
+			shadow_falloff = orc_shadow_sample_cube(sh.map, sh.res, full.x, full.y, full.z, ref_x / ref_y);
+		}
 		float s = (shadow_falloff * static_falloff);
 		float d2 = (light_dist * light_dist);
 		/* point.color * (shadow*static) / (dist*dist): left-to-right */
@@ -101,7 +242,7 @@ static vec3 compute_point_color(const orc_light_t *pt, vec3 world_pos, vec3 *lig
 }
 
 /* spot.h:34-84 compute_spot_color */
-static vec3 compute_spot_color(const orc_light_t *sp, vec3 world_pos, vec3 *light_dir)
+static vec3 compute_spot_color(const orc_light_t *sp, vec3 world_pos, vec3 *light_dir, light_shadow_t sh)
 {
 	vec3 light_pos = v3(sp->position[0], sp->position[1], sp->position[2]);
 	vec3 primary = v3(sp->direction[0], sp->direction[1], sp->direction[2]);
@@ -116,7 +257,13 @@ static vec3 compute_spot_color(const orc_light_t *sp, vec3 world_pos, vec3 *ligh
 	cone_falloff *= 1.0f - f_smoothstep(0.9f, 1.0f, light_dist * sp->inv_radius);
 	if (cone_falloff > 0.0f)
 	{
-		const float shadow_falloff = 1.0f;
+		float shadow_falloff = 1.0f;
+		if (sh.map)
+		{
+			/* spot.h:67-77 + pcf.h:98-99 */
+			vec4 clip = shadow_clip(sh.transform, world_pos);
+			shadow_falloff = orc_shadow_sample_2d(sh.map, sh.res, clip.x, clip.y, clip.z, clip.w);
+		}
 		float k = (cone_falloff * shadow_falloff) / (light_dist * light_dist);
 		return v3(sp->color[0] * k, sp->color[1] * k, sp->color[2] * k);
 	}
@@ -125,10 +272,10 @@ static vec3 compute_spot_color(const orc_light_t *sp, vec3 world_pos, vec3 *ligh
 
 /* point.h:103-142 / spot.h:106-145 */
 static vec3 compute_positional_light(const orc_light_t *l, int is_point, vec3 base_color, vec3 N,
-                                     float metallic, float roughness, vec3 world_pos, vec3 camera_pos)
+                                     float metallic, float roughness, vec3 world_pos, vec3 camera_pos, light_shadow_t sh)
 {
 	vec3 light_dir;
-	vec3 color = is_point ? compute_point_color(l, world_pos, &light_dir) : compute_spot_color(l, world_pos, &light_dir);
+	vec3 color = is_point ? compute_point_color(l, world_pos, &light_dir, sh) : compute_spot_color(l, world_pos, &light_dir, sh);
 	if (color.x == 0.0f && color.y == 0.0f && color.z == 0.0f)
 		return v3(0.0f, 0.0f, 0.0f);
 	vec3 V = v3_normalize(v3_sub(camera_pos, world_pos));
@@ -148,11 +295,11 @@ static uint32_t cluster_mask_range(uint32_t mask, uint32_t rx, uint32_t ry, uint
 	return mask & range_mask;
 }
 
-void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
-                           const orc_light_t *lights, const uint32_t *type_mask,
-                           const uint32_t *bitmask, const uint32_t *cluster_range,
-                           uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
-                           int32_t *out_light_count, int y0, int y1)
+static void deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
+                              const orc_light_t *lights, const uint32_t *type_mask,
+                              const uint32_t *bitmask, const uint32_t *cluster_range,
+                              uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
+                              int32_t *out_light_count, int y0, int y1, const orc_shadows_t *shadows)
 {
 	const int W = g->width, H = g->height;
 	const float *ivp = cam->inv_view_projection;
@@ -250,7 +397,14 @@ void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, cons
 				{
 					int bit = __builtin_ctz(mask);
 					int index = 32 * i + bit;
-					vec3 c = compute_positional_light(&lights[index], (tm >> bit) & 1u, base_color, N, metallic, roughness, pos, camera_pos);
+					light_shadow_t sh = { 0, 0, 0 };
+					if (shadows && shadows->maps[index])
+					{
+						sh.transform = shadows->transforms + 16 * (size_t)index;
+						sh.map = shadows->maps[index];
+						sh.res = shadows->resolution;
+					}
+					vec3 c = compute_positional_light(&lights[index], (tm >> bit) & 1u, base_color, N, metallic, roughness, pos, camera_pos, sh);
 					result = v3_add(result, c);
 					count++;
 					mask &= ~(1u << bit);
@@ -261,6 +415,24 @@ void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, cons
 			hdr_out[idx] = pack_r11g11b10(v3_add(result, d));
 		}
 	}
+}
+
+void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
+                           const orc_light_t *lights, const uint32_t *type_mask,
+                           const uint32_t *bitmask, const uint32_t *cluster_range,
+                           uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
+                           int32_t *out_light_count, int y0, int y1)
+{
+	deferred_lighting(g, cam, p, lights, type_mask, bitmask, cluster_range, hdr_out, out_tile_index, out_z_index, out_light_count, y0, y1, 0);
+}
+
+/* the same pass with POSITIONAL_LIGHTS_SHADOW (clustering.frag through point.h:45-74, spot.h:51-77) */
+void orc_deferred_lighting_shadowed(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
+                                    const orc_light_t *lights, const uint32_t *type_mask,
+                                    const uint32_t *bitmask, const uint32_t *cluster_range, const orc_shadows_t *shadows,
+                                    uint32_t *hdr_out, int y0, int y1)
+{
+	deferred_lighting(g, cam, p, lights, type_mask, bitmask, cluster_range, hdr_out, 0, 0, 0, y0, y1, shadows);
 }
 
 /* renderer.cpp:1009-1011: additive blend, the attachment store quantises (oracle_math.h pack_r11g11b10) */

@@ -237,7 +237,54 @@ def prepare_lights(cam: Camera, lights, res=(128, 64, 4096), cutoff=1e10, cull=T
     z_ranges = np.zeros((max(n, 1), 2), np.uint32)
     L.orc_light_z_ranges(C.byref(cam), _p(recs), _p(model), _p(type_mask), n, res[2], _p(z_ranges))
     return SimpleNamespace(n=n, n32=n32, records=recs, model=model, type_mask=type_mask, params=params,
-                           z_ranges=z_ranges, res=res)
+                           z_ranges=z_ranges, res=res, outer_cone=np.asarray(lights.outer_cone, np.float32).copy())
+
+
+def spot_xy_range(outer_cone):
+    """SpotLight::set_spot_parameters (lights.cpp:82-86): tan of the outer half angle from its cosine, in fp32."""
+    oc = np.float32(outer_cone)
+    return np.float32(np.sqrt(np.float32(np.float32(1.0) - oc * oc)) / oc)
+
+
+def shadow_transforms(prep):
+    """ClustererBindlessTransforms::shadow of every light of prep (clusterer.cpp:467-474, 518-521): (n, 16) f32."""
+    L = lib()
+    out = np.zeros((max(prep.n, 1), 16), np.float32)
+    for i in range(prep.n):
+        rec = Light.from_buffer_copy(prep.records[i:i + 1].tobytes())
+        m = np.zeros(16, np.float32)
+        if (int(prep.type_mask[i >> 5]) >> (i & 31)) & 1:
+            L.orc_point_shadow_transform(C.byref(rec), _p(m))
+        else:
+            L.orc_spot_shadow_transform(C.byref(rec), _f(spot_xy_range(prep.outer_cone[i])), _p(m))
+        out[i] = m
+    return out[:prep.n] if prep.n else out[:0]
+
+
+class Shadows(C.Structure):
+    _fields_ = [("transforms", C.c_void_p), ("maps", C.c_void_p), ("resolution", C.c_int)]
+
+
+def deferred_lighting_shadowed(scene, cam: Camera, prep, clus, transforms, maps, resolution, rows=None):
+    """The lighting pass with POSITIONAL_LIGHTS_SHADOW.  maps: one uint16 array per light (res x res for a spot light,
+    6 x res x res for a point light) or None (no shadow)."""
+    H, W = scene.depth.shape
+    g = GBuffer()
+    g.width, g.height = W, H
+    keep = [_c(scene.albedo, np.uint32), _c(scene.normal, np.uint32), _c(scene.pbr, np.uint16),
+            _c(scene.depth, np.float32), _c(scene.emissive, np.uint32)]
+    g.albedo, g.normal, g.pbr, g.depth, g.emissive = [k.ctypes.data for k in keep]
+    g.dir_color = (C.c_float * 3)(*scene.dir_color)
+    g.dir_direction = (C.c_float * 3)(*scene.dir_direction)
+    hdr = np.zeros((H, W), np.uint32)
+    y0, y1 = rows if rows else (0, H)
+    t = _c(transforms, np.float32)
+    held = [None if m is None else _c(m, np.uint16) for m in maps]
+    table = (C.c_void_p * max(len(held), 1))(*[None if m is None else m.ctypes.data for m in held])
+    sh = Shadows(t.ctypes.data, C.cast(table, C.c_void_p), int(resolution))
+    lib().orc_deferred_lighting_shadowed(C.byref(g), C.byref(cam), C.byref(prep.params), _p(prep.records), _p(prep.type_mask),
+                                         _p(clus.bitmask), _p(clus.range), C.byref(sh), _p(hdr), y0, y1)
+    return hdr
 
 
 def cluster_build(cam: Camera, prep):

@@ -100,4 +100,23 @@ void ref_rec709_to_display_primaries(const float *primaries8, float *out9)
 	const mat3 m = xyz_to_display * srgb_to_xyz;
 	memcpy(out9, &m, 36);
 }
+// renderer/lights/clusterer.cpp:467-474: the statements of gather_bindless_spot_shadow_renderables, on the reference's math
+void ref_spot_shadow_transform(const float *direction3, const float *position3, float inv_radius, float xy_range, float *out16)
+{
+	vec3 direction(direction3[0], direction3[1], direction3[2]), position(position3[0], position3[1], position3[2]);
+	float range = tan(xy_range);
+	mat4 view = mat4_cast(Granite::look_at_arbitrary_up(direction)) * translate(-position);
+	mat4 proj = Granite::projection(range * 2.0f, 1.0f, 0.005f / inv_radius, 1.0f / inv_radius);
+	mat4 shadow = translate(vec3(0.5f, 0.5f, 0.0f)) * scale(vec3(0.5f, 0.5f, 1.0f)) * proj * view;
+	memcpy(out16, &shadow, 64);
+}
+
+// renderer/lights/clusterer.cpp:518-521 (gather_bindless_point_shadow_renderables)
+void ref_point_shadow_transform(const float *position3, float inv_radius, float *out4)
+{
+	mat4 view, proj;
+	Granite::compute_cube_render_transform(vec3(position3[0], position3[1], position3[2]), 0, proj, view, 0.005f / inv_radius, 1.0f / inv_radius);
+	vec4 r(proj[2].zw(), proj[3].zw());
+	memcpy(out4, &r, 16);
+}
 }
