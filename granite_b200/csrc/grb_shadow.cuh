@@ -6,7 +6,7 @@
 // CUDA has no comparison sampler and the maps are plain D16_UNORM arrays in HBM (one per light, caller-owned:
 // clusterer.cpp:397-407 creates a 2-D image per spot light and a 6-layer cube per point light), so the filter is
 // written out: 2 x 2 texels, each compared with the reference depth, blended with the bilinear weights.  Every
-// operation is a single IEEE fp32 op in the oracle's order (oracle/oracle_lighting.c orc_shadow_sample_2d / _cube,
+// operation is a single IEEE fp32 op in the oracle's order (oracle/oracle_lighting.c, the 2-D and cube samplers there,
 // which restates the Vulkan specification's filtering) -- a comparison flips on one ulp of the reference depth, so
 // the shadow term is held to the bit-exact bar, not to the lighting pass's one-code bar.  The functions are also
 // compiled for the CPU and compared with the oracle (tests/cpp/emulate_shadow.cpp).

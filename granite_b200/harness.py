@@ -130,6 +130,16 @@ def deferred_lighting(gb: GBufferDevice, cam: capi.GrbCamera, cluster: ClusterDe
                                                 C.byref(img), capi.rows(rows), capi.stream_ptr()), "grb_deferred_lighting")
 
 
+def deferred_lighting_shadowed(gb: GBufferDevice, cam: capi.GrbCamera, cluster: ClusterDevice, transforms: torch.Tensor, map_table: torch.Tensor,
+                              resolution: int, hdr: torch.Tensor, rows=None):
+    """Lighting with shadowed positional lights.  transforms: float32 (n, 16) device tensor (cluster order); map_table: int64 (n,)
+    device tensor of device pointers to each light's D16 map (0 = no shadow)."""
+    img = capi.image(hdr, capi.FORMAT_B10G11R11_UFLOAT)
+    sh = capi.GrbLightShadows(_ptr(transforms), _ptr(map_table), int(resolution))
+    capi.check(capi.lib().grb_deferred_lighting_shadowed(C.byref(gb.struct), C.byref(cam), C.byref(cluster.params), C.byref(cluster.buffers),
+                                                         C.byref(sh), C.byref(img), capi.rows(rows), capi.stream_ptr()), "grb_deferred_lighting_shadowed")
+
+
 def _img16(t):
     return capi.image(t, capi.FORMAT_R16G16B16A16_SFLOAT)
 
