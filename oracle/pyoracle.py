@@ -22,7 +22,7 @@ _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for 
 _REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
 # deferred-lighting fragment shaders K5 (clustering.frag) and K6 (directional.frag), ref_light_shim.cpp
-_REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6)}
+_REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6, 7)}
 
 
 def build(ref: bool = True) -> None:
@@ -396,10 +396,12 @@ def ref_light_kernels():
     return _ref_light
 
 
-def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None):
+def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None, shadows=None):
     """renderer.cpp:1004-1156 with the reference's own fragment shaders: the two draws' colours
     (fp32), then the two additive blends into B10G11R11 with DESIGN.md section 2's store rule:
-    q(q(emissive + directional) + clustered).  Returns (hdr, directional_rgb, clustered_rgb)."""
+    q(q(emissive + directional) + clustered).  Returns (hdr, directional_rgb, clustered_rgb).
+    shadows = (transforms (n, 16) f32, maps [uint16 array | None per light], resolution): clustering.frag compiled with
+    POSITIONAL_LIGHTS_SHADOW (ref_light_shim.cpp KERNEL=7)."""
     H, W = scene.depth.shape
     k = ref_light_kernels()
     y0, y1 = rows if rows else (0, H)
@@ -411,7 +413,14 @@ def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None):
     k[6].refk6_directional(W, H, _p(alb), _p(nrm), _p(pbr), _p(dep), _p(ivp), _p(cpos), _p(cfront), _p(_farr(list(scene.dir_color))),
                            _p(_farr(list(scene.dir_direction))), y0, y1, _p(d_rgb))
     P = prep.params
-    k[5].refk5_clustering(W, H, _p(alb), _p(nrm), _p(pbr), _p(dep), _p(ivp), _p(cpos), _p(_farr(list(P.camera_base))), _p(_farr(list(P.camera_front))),
+    if shadows is not None:
+        t = _c(shadows[0], np.float32)
+        held = [None if m is None else _c(m, np.uint16) for m in shadows[1]]
+        table = (C.c_void_p * max(len(held), 1))(*[None if m is None else m.ctypes.data for m in held])
+        clustering = lambda *a: k[7].refk7_clustering_shadowed(_p(t), table, int(shadows[2]), *a)  # noqa: E731
+    else:
+        clustering = k[5].refk5_clustering
+    clustering(W, H, _p(alb), _p(nrm), _p(pbr), _p(dep), _p(ivp), _p(cpos), _p(_farr(list(P.camera_base))), _p(_farr(list(P.camera_front))),
                           _p(_farr(list(P.xy_scale))), _p(np.array(list(P.resolution_xy), np.int32)), int(P.num_lights), int(P.num_lights_32),
                           int(P.z_max_index), _f(P.z_scale), _p(prep.records), _p(_c(prep.type_mask, np.uint32)), _p(_c(clus.bitmask, np.uint32)),
                           _p(_c(clus.range, np.uint32)), y0, y1, _p(c_rgb))

@@ -4,6 +4,11 @@
 //   KERNEL=5  assets/shaders/lights/clustering.frag  (K5: clustered point / spot lights)
 //   KERNEL=6  assets/shaders/lights/directional.frag (K6: directional light, VOLUMETRIC_DIFFUSE_FALLBACK,
 //             no shadows -- the variant renderer.cpp:1018-1105 selects for the viewer without shadow maps)
+//   KERNEL=7  clustering.frag with POSITIONAL_LIGHTS_SHADOW=1 (renderer.cpp:369,1126): shadowed point / spot lights
+//             through point.h:45-74, spot.h:51-77, pcf.h:98-99.  The shader's statements (clip transform, reference
+//             depth, the products around shadow_falloff) are the reference's; the two comparison samplers
+//             (sampler2DShadow / samplerCubeShadow behind StockSampler::LinearShadow) are a texture unit's job and
+//             are supplied here by the oracle's restatement of the Vulkan filtering rules.
 // GLSL where it lies under /root/reference -> SPIR-V (vendored glslang) -> C++ (vendored spirv-cross
 // `--cpp --vulkan-semantics`) -> #included here (GEN_CPP); see oracle/Makefile `ref-shaders`.  The
 // statements that run are the reference's: compute_cluster_light (clusterer_bindless.h:29-84),
@@ -51,6 +56,40 @@ struct sampler2D
 {
 	int unused;
 };
+#if KERNEL == 7
+// bindless shadow maps: one D16 image per light; a null map samples as 1.0 ("casts no shadow")
+struct texture2D
+{
+	const uint16_t *map;
+	int res;
+};
+struct textureCube
+{
+	const uint16_t *map;
+	int res;
+};
+struct sampler
+{
+	int unused;
+};
+struct sampler2DShadow
+{
+	texture2D t;
+	sampler2DShadow(const texture2D &t_, const sampler &) : t(t_) {}
+};
+struct samplerCubeShadow
+{
+	textureCube t;
+	samplerCubeShadow(const textureCube &t_, const sampler &) : t(t_) {}
+};
+template <typename T> inline T nonuniformEXT(const T &v) { return v; }
+extern "C" float orc_shadow_sample_2d(const uint16_t *map, int res, float clip_x, float clip_y, float clip_z, float clip_w);
+extern "C" float orc_shadow_sample_cube(const uint16_t *map, int res, float dx, float dy, float dz, float ref);
+// textureProjLod(sampler2DShadow, vec4(s, t, D_ref, q), lod): (s, t, D_ref) / q
+inline float textureProjLod(const sampler2DShadow &s, const glm::vec4 &p, float) { return s.t.map ? orc_shadow_sample_2d(s.t.map, s.t.res, p.x, p.y, p.z, p.w) : 1.0f; }
+// texture(samplerCubeShadow, vec4(direction, D_ref))
+inline float texture(const samplerCubeShadow &s, const glm::vec4 &p) { return s.t.map ? orc_shadow_sample_cube(s.t.map, s.t.res, p.x, p.y, p.z, p.w) : 1.0f; }
+#endif
 template <typename T> inline T subgroupMin(T v) { return v; }
 template <typename T> inline T subgroupMax(T v) { return v; }
 template <typename T> inline T subgroupOr(T v) { return v; }
@@ -67,6 +106,10 @@ namespace shim
 static const void *g_transforms = nullptr;
 static const void *g_bitmask = nullptr;
 static const void *g_range = nullptr;
+#if KERNEL == 7
+static const spirv_cross::texture2D *g_spot_atlas = nullptr;   // indexed by light (uSpotShadowAtlas[index])
+static const spirv_cross::textureCube *g_point_atlas = nullptr; // the same descriptors seen as cubes (uPointShadowAtlas[index])
+#endif
 struct BitmaskBlock
 {
 	uint32_t cluster_bitmask[1];
@@ -143,6 +186,10 @@ struct Runner
 		spirv_cross_set_stage_input(sh, 0, &f.vclip, sizeof(f.vclip));
 		spirv_cross_set_stage_output(sh, 0, &f.color, sizeof(f.color));
 		spirv_cross_set_builtin(sh, SPIRV_CROSS_BUILTIN_FRAG_COORD, &f.frag_coord, sizeof(f.frag_coord));
+#if KERNEL == 7
+		static spirv_cross::sampler linear_shadow_sampler = { 0 }; // LinearShadowSampler: behaviour lives in the sample functions
+		spirv_cross_set_uniform_constant(sh, 0, &linear_shadow_sampler, sizeof(linear_shadow_sampler));
+#endif
 	}
 	~Runner() { itf->destruct(sh); }
 	void resource(unsigned set, unsigned binding, void *ptr)
@@ -170,9 +217,15 @@ struct Runner
 } // namespace
 
 extern "C" {
-#if KERNEL == 5
+#if KERNEL == 5 || KERNEL == 7
 // renderer.cpp:1107-1156.  The cluster parameters are the oracle's orc_cluster_params_t fields.
-void refk5_clustering(int w, int h, const uint32_t *albedo, const uint32_t *normal, const uint16_t *pbr, const float *depth, const float *inv_view_projection16,
+#if KERNEL == 7
+// transforms16: num_lights x mat4 (ClustererBindlessTransforms::shadow); maps: num_lights pointers (null = no shadow)
+void refk7_clustering_shadowed(const float *transforms16, const uint16_t *const *maps, int shadow_res, int w, int h,
+#else
+void refk5_clustering(int w, int h,
+#endif
+                      const uint32_t *albedo, const uint32_t *normal, const uint16_t *pbr, const float *depth, const float *inv_view_projection16,
                       const float *camera_pos3, const float *camera_base3, const float *camera_front3, const float *xy_scale2, const int32_t *resolution_xy2,
                       int num_lights, int num_lights_32, int z_max_index, float z_scale, const void *lights48, const uint32_t *type_mask, const uint32_t *bitmask,
                       const uint32_t *cluster_range, int y0, int y1, float *out_rgb)
@@ -182,6 +235,18 @@ void refk5_clustering(int w, int h, const uint32_t *albedo, const uint32_t *norm
 	std::memset(static_cast<void *>(blob), 0, sizeof(*blob));
 	std::memcpy(blob->cluster_transforms.lights.data(), lights48, (size_t)num_lights * 48);
 	std::memcpy(blob->cluster_transforms.type_mask.data(), type_mask, (size_t)num_lights_32 * 4);
+#if KERNEL == 7
+	std::memcpy(static_cast<void *>(blob->cluster_transforms.shadow.data()), transforms16, (size_t)num_lights * 64);
+	auto *spot_atlas = new spirv_cross::texture2D[num_lights > 0 ? num_lights : 1];
+	auto *point_atlas = new spirv_cross::textureCube[num_lights > 0 ? num_lights : 1];
+	for (int i = 0; i < num_lights; i++)
+	{
+		spot_atlas[i].map = point_atlas[i].map = maps[i];
+		spot_atlas[i].res = point_atlas[i].res = shadow_res;
+	}
+	shim::g_spot_atlas = spot_atlas;
+	shim::g_point_atlas = point_atlas;
+#endif
 	shim::g_transforms = blob;
 	shim::g_bitmask = bitmask;
 	shim::g_range = cluster_range;
@@ -208,6 +273,10 @@ void refk5_clustering(int w, int h, const uint32_t *albedo, const uint32_t *norm
 		r.draw(g, inv_view_projection16, y0, y1, out_rgb);
 	}
 	delete blob;
+#if KERNEL == 7
+	delete[] spot_atlas;
+	delete[] point_atlas;
+#endif
 }
 #elif KERNEL == 6
 // renderer.cpp:1018-1105
