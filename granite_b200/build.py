@@ -23,6 +23,7 @@ UNITS = [
     ("grb_post_tiles.cu", ["-fmad=false"]),
     ("grb_post_fast.cu", []),
     ("grb_smaa.cu", ["-fmad=false"]),
+    ("grb_fsr.cu", ["-fmad=false"]),
     ("grb_lighting.cu", []),
 ]
 
@@ -38,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     hdrs = [os.path.join(CSRC, "grb_common.cuh"), os.path.join(HERE, "..", "include", "granite_b200.h"),
             os.path.abspath(__file__)]
-    hdrs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    hdrs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))]
     objs = []
     for src, extra in UNITS:
         s = os.path.join(CSRC, src)

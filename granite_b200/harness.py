@@ -252,6 +252,19 @@ def smaa_neighborhood_blend(color_t, weights_t, out_t, target_srgb=True, rows=No
     capi.check(capi.lib().grb_smaa_neighborhood_blend(C.byref(ci), C.byref(wi), C.byref(oi), capi.rows(rows), capi.stream_ptr()), "grb_smaa_neighborhood_blend")
 
 
+def fsr_upscale(color_t, out_t, target_srgb=False, rows=None):
+    """color_t: (h_in, w_in) int32 RGBA8; out_t: (h_out, w_out) int32 RGBA8 (UNORM when a sharpen pass follows)."""
+    ci = capi.image(color_t, capi.FORMAT_R8G8B8A8_UNORM)
+    oi = capi.image(out_t, capi.FORMAT_R8G8B8A8_SRGB if target_srgb else capi.FORMAT_R8G8B8A8_UNORM)
+    capi.check(capi.lib().grb_fsr_upscale(C.byref(ci), C.byref(oi), capi.rows(rows), capi.stream_ptr()), "grb_fsr_upscale")
+
+
+def fsr_sharpen(color_t, out_t, sharpness_stops=0.5, srgb=True, rows=None):
+    fmt = capi.FORMAT_R8G8B8A8_SRGB if srgb else capi.FORMAT_R8G8B8A8_UNORM
+    ci, oi = capi.image(color_t, capi.FORMAT_R8G8B8A8_UNORM), capi.image(out_t, fmt)
+    capi.check(capi.lib().grb_fsr_sharpen(C.byref(ci), C.byref(oi), C.c_float(sharpness_stops), capi.rows(rows), capi.stream_ptr()), "grb_fsr_sharpen")
+
+
 def taa_resolve(hdr_t, depth_t, mv_t, history_t, reproj, quality, out_color_t, out_history_t, rows=None):
     hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
     oc = capi.image(out_color_t, capi.FORMAT_B10G11R11_UFLOAT)

@@ -36,4 +36,8 @@ bool setup_before_post_chain_antialiasing(PostAAType type, RenderGraph &graph, T
                                           const std::string &input_depth, const std::string &input_mv, const std::string &output);
 bool setup_after_post_chain_antialiasing(PostAAType type, RenderGraph &graph, TemporalJitter &jitter, float scaling_factor, const std::string &input,
                                          const std::string &input_depth, const std::string &output);
+// FidelityFX FSR 1 from the (scaled-down) post-chain image to the swapchain size (renderer/post/aa.hpp:60,
+// aa.cpp:75-174): pass "<output>-scale" (edge-adaptive upscale) and, with use_sharpen, pass "<output>-sharpen"
+// (contrast-adaptive sharpening, 0.5 stops as the reference hard-codes).  `output` has the swapchain's size.
+bool setup_after_post_chain_upscaling(RenderGraph &graph, const std::string &input, const std::string &output, bool use_sharpen);
 } // namespace Granite

@@ -5,6 +5,8 @@
 // rasterises are uploaded from host memory by the "gbuffer" pass at the head of the graph.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -78,6 +80,11 @@ struct GrbhViewer
 		return config.post_aa == GRBH_AA_TAA_LOW || config.post_aa == GRBH_AA_TAA_MEDIUM || config.post_aa == GRBH_AA_TAA_HIGH ||
 		       config.post_aa == GRBH_AA_TAA_HIGH_PLUS_FXAA;
 	}
+	// "resolutionScale": the scene is rendered at ceil(scale * display size) (render_graph.cpp's relative-size rule)
+	bool upscales() const { return config.resolution_scale > 0.0f && config.resolution_scale < 1.0f; }
+	float scene_scale() const { return upscales() ? config.resolution_scale : 1.0f; }
+	int render_width() const { return upscales() ? std::max(int(std::ceil(config.resolution_scale * float(config.width))), 1) : config.width; }
+	int render_height() const { return upscales() ? std::max(int(std::ceil(config.resolution_scale * float(config.height))), 1) : config.height; }
 	bool uses_fxaa() const { return config.post_aa == GRBH_AA_FXAA || config.post_aa == GRBH_AA_TAA_HIGH_PLUS_FXAA; }
 	bool uses_smaa() const { return config.post_aa >= GRBH_AA_SMAA_LOW && config.post_aa <= GRBH_AA_SMAA_ULTRA; }
 
@@ -85,7 +92,7 @@ struct GrbhViewer
 	// threshold (and FXAA through the tonemap) reaches into
 	GrbRows input_rows() const
 	{
-		return compute_shard_plan((unsigned)config.width, (unsigned)config.height, bands, rank, uses_fxaa()).lighting;
+		return compute_shard_plan((unsigned)render_width(), (unsigned)render_height(), bands, rank, uses_fxaa()).lighting;
 	}
 
 	void upload_rows(Vulkan::CommandBuffer &cmd, RenderTextureResource *res, const void *host, unsigned texel)
@@ -94,7 +101,7 @@ struct GrbhViewer
 			return;
 		auto &view_ = graph.get_physical_texture_resource(*res);
 		GrbRows r = input_rows();
-		size_t pitch = (size_t)config.width * texel;
+		size_t pitch = (size_t)render_width() * texel;
 		auto *dst = static_cast<uint8_t *>(view_.get_image().get_device_pointer()) + (size_t)r.y0 * pitch;
 		auto *src = static_cast<const uint8_t *>(host) + (size_t)r.y0 * pitch;
 		Vulkan::cuda_ok(cudaMemcpyAsync(dst, src, pitch * (size_t)(r.y1 - r.y0), cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(cmd.get_stream())),
@@ -130,7 +137,7 @@ void GrbhViewer::bake_render_graph()
 	if (bands.size() > 1)
 	{
 		const GrbRows lit = input_rows();
-		cluster.set_lit_pixel_rows(lit.y0, lit.y1, config.height);
+		cluster.set_lit_pixel_rows(lit.y0, lit.y1, render_height());
 	}
 	else
 		cluster.set_lit_pixel_rows(0, 0, 0);
@@ -153,6 +160,10 @@ void GrbhViewer::bake_render_graph()
 
 	// pipelined I/O: uploads on the async-compute stream into ping-pong images, so the copy of the
 	// next frame's inputs overlaps this frame's lighting
+	// scene_viewer_application.cpp:758-761, 888-889: the scene attachments scale with "resolutionScale"; everything
+	// downstream is sized relative to them
+	for (auto *info : { &emissive, &albedo, &normal, &pbr, &depth })
+		info->size_x = info->size_y = scene_scale();
 	const bool pipelined = config.pipelined_io != 0;
 	if (pipelined)
 		for (auto *info : { &emissive, &albedo, &normal, &pbr, &depth })
@@ -189,7 +200,7 @@ void GrbhViewer::bake_render_graph()
 	lighting_pass.set_depth_stencil_input("depth-transient");
 	// work schedule of the lighting kernel: row costs of this frame order the next frame's rows
 	BufferInfo schedule_info;
-	schedule_info.size = (size_t)grb_lighting_schedule_bytes(config.height);
+	schedule_info.size = (size_t)grb_lighting_schedule_bytes(render_height());
 	schedule_info.usage = VK_BUFFER_USAGE_STORAGE_BUFFER_BIT;
 	auto &schedule = lighting_pass.add_storage_output("lighting-schedule", schedule_info);
 	auto light_iface = std::make_shared<DeferredLightingPass>(context, &cluster);
@@ -216,6 +227,7 @@ void GrbhViewer::bake_render_graph()
 		// add_mv_pass: the motion-vector image is an input of this path
 		AttachmentInfo mv;
 		mv.format = VK_FORMAT_R16G16_SFLOAT;
+		mv.size_x = mv.size_y = scene_scale();
 		if (pipelined)
 			mv.flags |= ATTACHMENT_INFO_PINGPONG_BIT;
 		auto &mv_pass = graph.add_pass("mv", pipelined ? RENDER_GRAPH_QUEUE_ASYNC_COMPUTE_BIT : RENDER_GRAPH_QUEUE_GRAPHICS_BIT);
@@ -331,6 +343,9 @@ void GrbhViewer::bake_render_graph()
 				ui_source = "post-aa-output";
 		}
 	}
+	// scene_viewer_application.cpp:1263-1268: FSR 1 from the scaled-down image to the swapchain size
+	if (upscales() && setup_after_post_chain_upscaling(graph, ui_source, "post-scale-output", config.resolution_scale_sharpen != 0))
+		ui_source = "post-scale-output";
 	output_name = ui_source;
 	graph.set_backbuffer_source(ui_source);
 	graph.bake();
@@ -410,6 +425,10 @@ extern "C" int32_t grbh_viewer_create(const GrbhViewerConfig *config, GrbhViewer
 		return fail("grbh_viewer_create: FXAA reads the tonemapped 8-bit image; an HDR10 output has none (use TAA)");
 	if (config->hdr10_output && config->post_aa >= GRBH_AA_SMAA_LOW && config->post_aa <= GRBH_AA_SMAA_ULTRA)
 		return fail("grbh_viewer_create: SMAA reads the tonemapped 8-bit image; an HDR10 output has none (use TAA)");
+	if (config->resolution_scale > 0.0f && config->resolution_scale < 1.0f && config->hdr10_output)
+		return fail("grbh_viewer_create: FSR 1 upscaling reads the tonemapped 8-bit image; an HDR10 output has none");
+	if (!(config->resolution_scale >= 0.0f && config->resolution_scale <= 1.0f))
+		return fail("grbh_viewer_create: resolution_scale must be within [0, 1] (0 or 1 = off)");
 	GRBH_TRY
 	auto v = std::make_unique<GrbhViewer>();
 	v->config = *config;
@@ -619,6 +638,8 @@ extern "C" int32_t grbh_viewer_set_row_shards(GrbhViewer *v, const GrbRows *band
 {
 	if (!v || count < 0 || (count && !bands) || (count && (rank < 0 || rank >= count)))
 		return fail("grbh_viewer_set_row_shards: bad arguments");
+	if (count > 1 && v->upscales())
+		return fail("grbh_viewer_set_row_shards: FSR 1 upscaling (resolution_scale < 1) is not row-sharded");
 	GRBH_TRY
 	v->bands.assign(bands, bands + count);
 	v->rank = (unsigned)rank;
@@ -864,6 +885,15 @@ extern "C" int32_t grbh_viewer_get_light_prep(GrbhViewer *v, GrbPositionalLight 
 	return n;
 }
 
+extern "C" int32_t grbh_viewer_get_render_size(GrbhViewer *v, int32_t *width, int32_t *height)
+{
+	if (!v || !width || !height)
+		return fail("grbh_viewer_get_render_size: null");
+	*width = v->render_width();
+	*height = v->render_height();
+	return 0;
+}
+
 extern "C" int32_t grbh_viewer_get_camera(GrbhViewer *v, GrbCamera *out, float *projection16, float *inv_projection16)
 {
 	if (!v || !out)
@@ -893,7 +923,7 @@ extern "C" int32_t grbh_viewer_measure_row_cost(GrbhViewer *v, uint32_t *out, in
 	if (v->graph.is_sharded())
 		return fail("grbh_viewer_measure_row_cost: the viewer must hold the whole frame (not row-sharded)");
 	GRBH_TRY
-	const int groups = ((int)v->config.height + 3) / 4;
+	const int groups = (v->render_height() + 3) / 4;
 	if (capacity < groups)
 		return fail("grbh_viewer_measure_row_cost: capacity too small");
 	v->device->wait_idle();

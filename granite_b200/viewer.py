@@ -23,7 +23,8 @@ class GrbhViewerConfig(C.Structure):
                 ("hdr_bloom", C.c_int32), ("dynamic_exposure", C.c_int32), ("cluster_res", C.c_int32 * 3),
                 ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p), ("pipelined_io", C.c_int32),
                 ("hdr10_output", C.c_int32), ("hdr10_max_content_light_level", C.c_float),
-                ("clustered_lights_shadows", C.c_int32), ("clustered_lights_shadow_resolution", C.c_int32)]
+                ("clustered_lights_shadows", C.c_int32), ("clustered_lights_shadow_resolution", C.c_int32),
+                ("resolution_scale", C.c_float), ("resolution_scale_sharpen", C.c_int32)]
 
 
 class GrbhLights(C.Structure):
@@ -231,7 +232,7 @@ def shard_plan(width, height, bands, rank, fxaa=False) -> dict:
 class Viewer:
     def __init__(self, width, height, post_aa=AA_NONE, hdr_bloom=True, dynamic_exposure=True, cuda_device=0,
                  cluster_res=(128, 64, 4096), timestamps=False, stream=None, pipelined_io=False, hdr10_output=False, hdr10_max_cll=1000.0,
-                 light_shadows=False, shadow_resolution=512):
+                 light_shadows=False, shadow_resolution=512, resolution_scale=0.0, resolution_scale_sharpen=True):
         cfg = GrbhViewerConfig()
         cfg.cuda_device = cuda_device
         cfg.width, cfg.height = width, height
@@ -246,6 +247,8 @@ class Viewer:
         cfg.hdr10_max_content_light_level = float(hdr10_max_cll)
         cfg.clustered_lights_shadows = int(light_shadows)
         cfg.clustered_lights_shadow_resolution = int(shadow_resolution)
+        cfg.resolution_scale = float(resolution_scale)  # < 1: width x height is the display size, FSR 1 upscales to it
+        cfg.resolution_scale_sharpen = int(resolution_scale_sharpen)
         self.width, self.height = width, height
         self._h = C.c_void_p()
         _check(lib().grbh_viewer_create(C.byref(cfg), C.byref(self._h)), "grbh_viewer_create")
@@ -257,6 +260,12 @@ class Viewer:
         assert a.size == 160 * 560 * 2 and s_.size == 64 * 16
         _check(lib().grbh_viewer_set_smaa_lookup_textures(self._h, a.ctypes.data_as(C.c_void_p), s_.ctypes.data_as(C.c_void_p)),
                "grbh_viewer_set_smaa_lookup_textures")
+
+    def render_size(self):
+        """(width, height) of the G-buffer the viewer expects (smaller than the display size when resolution_scale < 1)."""
+        w, h = C.c_int32(), C.c_int32()
+        _check(lib().grbh_viewer_get_render_size(self._h, C.byref(w), C.byref(h)), "grbh_viewer_get_render_size")
+        return w.value, h.value
 
     def set_light_shadow_maps(self, device_pointers):
         """One device pointer (int, 0 = no shadow) per light of the last set_lights call, in that order."""

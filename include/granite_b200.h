@@ -334,6 +334,19 @@ int32_t grb_smaa_blend_weights(const GrbImage *edges, const GrbImage *area, cons
                                const GrbImage *weights, GrbRows rows, void *stream);
 int32_t grb_smaa_neighborhood_blend(const GrbImage *color, const GrbImage *weights, const GrbImage *out, GrbRows rows, void *stream);
 
+/* FidelityFX FSR 1 after the post chain (renderer/post/aa.cpp:75-174 setup_after_post_chain_upscaling;
+ * assets/shaders/post/ffx-fsr/{upscale,sharpen}.frag over ffx_fsr1.h, 32-bit paths).
+ * grb_fsr_upscale = the "<output>-scale" pass (FsrEasuF): color is the low-resolution 8-bit image, read as UNORM whatever its
+ * format says (aa.cpp:90 set_unorm_texture); out has the display resolution -- R8G8B8A8_UNORM when a sharpen pass follows
+ * (TARGET_SRGB = 0), R8G8B8A8_SRGB when it is the last pass (TARGET_SRGB = 1: decode_srgb, the store encodes).  The EASU
+ * constants are FsrEasuCon of the two sizes (aa.cpp:33-61; grb_fsr_easu_constants returns them, 16 floats).
+ * grb_fsr_sharpen = the "<output>-sharpen" pass (FsrRcasF): color and out of one size; with an SRGB out the input is read
+ * through an sRGB view (aa.cpp:141-144) and the result encoded on store.  sharpness_stops as FsrRcasCon takes it
+ * (aa.cpp:63-73; the reference passes 0.5): the lobe is scaled by 2^-stops. */
+int32_t grb_fsr_easu_constants(int32_t in_width, int32_t in_height, int32_t out_width, int32_t out_height, float *con16);
+int32_t grb_fsr_upscale(const GrbImage *color, const GrbImage *out, GrbRows rows, void *stream);
+int32_t grb_fsr_sharpen(const GrbImage *color, const GrbImage *out, float sharpness_stops, GrbRows rows, void *stream);
+
 /* K12 fxaa.frag; renderer/post/fxaa.cpp:41-55. in: 8-bit image viewed as UNORM; if out's
  * format is *_SRGB the shader's FXAA_TARGET_SRGB path applies. */
 int32_t grb_fxaa(const GrbImage *in, const GrbImage *out, GrbRows rows, void *stream);

@@ -59,6 +59,11 @@ typedef struct GrbhViewerConfig
 	int32_t clustered_lights_shadows;           /* config "clusteredLightsShadows" (scene_viewer_application.cpp:214-215): the lighting
 	                                             * pass samples the per-light shadow maps of grbh_viewer_set_light_shadow_maps */
 	int32_t clustered_lights_shadow_resolution; /* "clusteredLightsShadowsResolution" (:216-217); <= 0: 512 */
+	float resolution_scale;          /* "resolutionScale" (scene_viewer_application.cpp:247-248): 0 or 1 = off.  < 1: width x height
+	                                  * is the DISPLAY size; the G-buffer the caller supplies (and every pass up to the post-chain
+	                                  * output) has ceil(scale * size) texels (:758-761, 888-889), and FSR 1 upscales the result
+	                                  * to the display size (:1263-1268).  Not with row sharding or HDR10 output. */
+	int32_t resolution_scale_sharpen; /* "resolutionScaleSharpen" (:249-250): the RCAS pass after the upscale */
 } GrbhViewerConfig;
 
 /* Raw light list as the application owns it (before the clusterer sorts/packs it). */
@@ -162,6 +167,8 @@ int32_t grbh_viewer_get_camera(GrbhViewer *viewer, GrbCamera *out, float *projec
  * (renderer/post/temporal.cpp:239-243: unjittered history matrices). */
 int32_t grbh_viewer_get_taa_reprojection(GrbhViewer *viewer, float *out16);
 /* Names of the baked passes, '\n' separated. Returns the length needed. */
+/* Size of the G-buffer the viewer expects (= width x height unless resolution_scale < 1). */
+int32_t grbh_viewer_get_render_size(GrbhViewer *viewer, int32_t *width, int32_t *height);
 int32_t grbh_viewer_get_pass_names(GrbhViewer *viewer, char *buffer, int32_t capacity);
 /* Per-pass GPU time of the frames since the last call (needs config.timestamps):
  * writes up to `capacity` (name, total ms, count) triples. Returns the number of passes. */

@@ -203,4 +203,13 @@ void orc_smaa_blend_weights(const uint8_t *edges_rg8, int w, int h, const uint8_
                             uint32_t *weights_rgba8, int y0, int y1);
 void orc_smaa_neighborhood_blend(const uint32_t *color_unorm, const uint32_t *weights_rgba8, int w, int h, uint32_t *out_srgb8, int y0, int y1);
 
+/* ---- FSR 1 after the post chain: renderer/post/aa.cpp:34-174, assets/shaders/post/ffx-fsr/{upscale,sharpen}.frag,
+ * ffx_fsr1.h (32-bit paths) ---- */
+void orc_fsr_easu_constants(int w_in, int h_in, int w_out, int h_out, float *con16);  /* aa.cpp:33-61 */
+void orc_fsr_rcas_constants(float sharpness, float *con4);                             /* aa.cpp:63-73 */
+/* upscale.frag: src is the sRGB image read as UNORM; target_srgb = 1 stores decode_srgb(colour) into an sRGB target */
+void orc_fsr_easu(const uint32_t *src_unorm, int w_in, int h_in, const float *con16, uint32_t *dst, int w_out, int h_out, int target_srgb, int y0, int y1);
+/* sharpen.frag: srgb = 1 reads through an sRGB view (linear values) and stores into an sRGB target */
+void orc_fsr_rcas(const uint32_t *src, int w, int h, const float *con4, uint32_t *dst, int srgb, int y0, int y1);
+
 #endif

@@ -19,7 +19,7 @@ _REF_PATH = os.path.join(_HERE, "_ref", "libgranite_refmath.so")
 
 _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for k in (1, 2, 3, 4)]
 # post-processing shaders K7-K13 (ref_post_shim.cpp); ids as in oracle/Makefile POST_IDS
-_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173)
+_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173, 24, 25, 26)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
 # deferred-lighting fragment shaders K5 (clustering.frag) and K6 (directional.frag), ref_light_shim.cpp
 _REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6, 7)}
@@ -705,3 +705,57 @@ def hdr_chain(hdr, lum3, d3_history, frame_time=1.0 / 60.0, exposure=1.0, dynami
     u0 = bloom_upsample(u1, sz[1])
     ldr = tonemap(hdr, u0, lum_out, exposure)
     return SimpleNamespace(t=t, d0=d0, d1=d1, d2=d2, d3=d3, u2=u2, u1=u1, u0=u0, lum=lum_out, ldr=ldr)
+
+
+# ---------------- FSR 1 (renderer/post/aa.cpp:34-174) ----------------
+def fsr_easu_constants(w_in, h_in, w_out, h_out):
+    con = np.zeros(16, np.float32)
+    lib().orc_fsr_easu_constants(int(w_in), int(h_in), int(w_out), int(h_out), _p(con))
+    return con
+
+
+def fsr_rcas_constants(sharpness_stops=0.5):
+    con = np.zeros(4, np.float32)
+    lib().orc_fsr_rcas_constants(_f(sharpness_stops), _p(con))
+    return con
+
+
+def fsr_upscale(img, out_wh, target_srgb=False, rows=None):
+    """upscale.frag: img (h, w) uint32 RGBA8 read as UNORM -> (h_out, w_out) uint32."""
+    h, w = img.shape
+    wo, ho = out_wh
+    out = np.zeros((ho, wo), np.uint32)
+    y0, y1 = rows if rows else (0, ho)
+    lib().orc_fsr_easu(_p(_c(img, np.uint32)), w, h, _p(fsr_easu_constants(w, h, wo, ho)), _p(out), wo, ho, int(target_srgb), y0, y1)
+    return out
+
+
+def fsr_sharpen(img, sharpness_stops=0.5, srgb=True, rows=None):
+    """sharpen.frag: srgb = the target is an sRGB attachment (input read through an sRGB view)."""
+    h, w = img.shape
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    lib().orc_fsr_rcas(_p(_c(img, np.uint32)), w, h, _p(fsr_rcas_constants(sharpness_stops)), _p(out), int(srgb), y0, y1)
+    return out
+
+
+def ref_fsr_upscale(img, out_wh, target_srgb=False, rows=None):
+    """The reference's upscale.frag on the CPU (oracle/_ref/libgranite_ref_p24 / p25)."""
+    k = ref_post_kernels()
+    h, w = img.shape
+    wo, ho = out_wh
+    out = np.zeros((ho, wo), np.uint32)
+    y0, y1 = rows if rows else (0, ho)
+    fn = k[25].refk25_fsr_upscale_srgb if target_srgb else k[24].refk24_fsr_upscale_unorm
+    fn(_p(_c(img, np.uint32)), w, h, _p(fsr_easu_constants(w, h, wo, ho)), _p(out), wo, ho, y0, y1)
+    return out
+
+
+def ref_fsr_sharpen(img, sharpness_stops=0.5, srgb=True, rows=None):
+    """The reference's sharpen.frag on the CPU (oracle/_ref/libgranite_ref_p26)."""
+    k = ref_post_kernels()
+    h, w = img.shape
+    out = np.zeros((h, w), np.uint32)
+    y0, y1 = rows if rows else (0, h)
+    k[26].refk26_fsr_sharpen(_p(_c(img, np.uint32)), w, h, _p(fsr_rcas_constants(sharpness_stops)), int(srgb), _p(out), y0, y1)
+    return out

@@ -250,6 +250,14 @@ inline glm::vec4 fma(const glm::vec4 &a, const glm::vec4 &b, const glm::vec4 &c)
 #define discard return vec2(0.0f)
 #endif
 
+#if KERNEL == 24 || KERNEL == 25 || KERNEL == 26
+// FSR 1: scalar min / max as a GPU executes them (FMNMX / v_max_f32 return the non-NaN operand, IEEE minNum / maxNum);
+// GLM's (x < y) ? y : x would keep a NaN first operand.  RCAS meets one by design: a channel that is 0 over the whole
+// ring gives hitMin = 0 * (1 / 0), and max(-hitMin, hitMax) must fall through to hitMax (ffx_fsr1.h:753-755).
+inline float max(const float &a, const float &b) { return std::fmax(a, b); }
+inline float min(const float &a, const float &b) { return std::fmin(a, b); }
+#endif
+
 #include GEN_CPP
 #undef mat4
 #ifdef discard
@@ -290,7 +298,7 @@ struct Runner
 	// `emit(x, y)` is called after every invocation.
 	glm::ivec2 pixel = glm::ivec2(0);
 	template <typename F>
-	void raster(int w, int h, int y0, int y1, glm::vec2 *uv_slot, F &&emit)
+	void raster(int w, int h, int y0, int y1, glm::vec2 *uv_slot, F &&emit, glm::vec2 *pixel_uv_slot = nullptr)
 	{
 		glm::vec4 frag(0.0f);
 		spirv_cross_set_builtin(sh, SPIRV_CROSS_BUILTIN_FRAG_COORD, &frag, sizeof(frag));
@@ -302,6 +310,8 @@ struct Runner
 				pixel = glm::ivec2(x, y);
 				if (uv_slot)
 					*uv_slot = glm::vec2(((float)x + 0.5f) * inv_w, ((float)y + 0.5f) * inv_h);
+				if (pixel_uv_slot) // ffx-fsr/{upscale,sharpen}.vert: vUV = (0.5 * Position + 0.5) * out_resolution
+					*pixel_uv_slot = glm::vec2((float)x + 0.5f, (float)y + 0.5f);
 				itf->invoke(sh);
 				emit(x, y);
 			}
@@ -669,5 +679,63 @@ void refk_smaa_blend(const uint32_t *color_unorm, const uint32_t *weights_rgba8,
 		}
 }
 #endif
+#elif KERNEL == 24 || KERNEL == 25
+// aa.cpp:75-118 "<output>-scale": upscale.frag, FP16 = 0; KERNEL 25 = sRGB target (TARGET_SRGB = 1).  vUV is the
+// output pixel position (upscale.vert:19: (0.5 * Position + 0.5) * out_resolution), con16 = FsrEasuCon (aa.cpp:33-61).
+void
+#if KERNEL == 24
+refk24_fsr_upscale_unorm
+#else
+refk25_fsr_upscale_srgb
+#endif
+(const uint32_t *in, int w_in, int h_in, const float *con16, uint32_t *out, int w, int h, int y0, int y1)
+{
+	sampler2D s = make_sampler(in, w_in, h_in, spirv_cross::FMT_RGBA8_UNORM, false); // set_unorm_texture + NearestClamp
+	Sh::Resources::Params params;
+	std::memcpy(&params, con16, sizeof(params));
+	glm::vec2 uv(0.0f);
+	glm::vec4 color(0.0f);
+	Runner r;
+	r.resource(0, 0, &s);
+	r.resource(1, 0, &params);
+	spirv_cross_set_stage_input(r.sh, 0, &uv, sizeof(uv));
+	spirv_cross_set_stage_output(r.sh, 0, &color, sizeof(color));
+	r.raster(w, h, y0, y1, nullptr, [&](int x, int y) {
+		auto q = [](float c) -> uint32_t {
+#if KERNEL == 25
+			return orc_linear_to_srgb8(c);
+#else
+			c = c > 0.0f ? (c < 1.0f ? c : 1.0f) : 0.0f;
+			return (uint32_t)std::floor(c * 255.0f + 0.5f);
+#endif
+		};
+		out[(size_t)y * w + x] = q(color.x) | (q(color.y) << 8) | (q(color.z) << 16) | 0xff000000u;
+	}, &uv);
+}
+#elif KERNEL == 26
+// aa.cpp:120-171 "<output>-sharpen": sharpen.frag.  srgb != 0: sRGB backbuffer, the input is bound through an sRGB view.
+void refk26_fsr_sharpen(const uint32_t *in, int w, int h, const float *con4, int srgb, uint32_t *out, int y0, int y1)
+{
+	sampler2D s = make_sampler(in, w, h, srgb ? spirv_cross::FMT_RGBA8_SRGB : spirv_cross::FMT_RGBA8_UNORM, false);
+	Sh::Resources::UBO ubo;
+	std::memcpy(&ubo.param0, con4, 16);
+	ubo.range = glm::ivec4(0, 0, w - 1, h - 1); // aa.cpp:154-157
+	glm::vec2 uv(0.0f);
+	glm::vec4 color(0.0f);
+	Runner r;
+	r.resource(0, 0, &s);
+	r.resource(1, 0, &ubo);
+	spirv_cross_set_stage_input(r.sh, 0, &uv, sizeof(uv));
+	spirv_cross_set_stage_output(r.sh, 0, &color, sizeof(color));
+	r.raster(w, h, y0, y1, nullptr, [&](int x, int y) {
+		auto q = [srgb](float c) -> uint32_t {
+			if (srgb)
+				return orc_linear_to_srgb8(c);
+			c = c > 0.0f ? (c < 1.0f ? c : 1.0f) : 0.0f;
+			return (uint32_t)std::floor(c * 255.0f + 0.5f);
+		};
+		out[(size_t)y * w + x] = q(color.x) | (q(color.y) << 8) | (q(color.z) << 16) | 0xff000000u;
+	}, &uv);
+}
 #endif
 }

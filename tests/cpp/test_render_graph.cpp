@@ -335,6 +335,46 @@ int main()
 		CHECK(graph.get_texture_resource("tonemapped").get_attachment_info().flags & ATTACHMENT_INFO_UNORM_SRGB_ALIAS_BIT);
 		CHECK(jitter.get_jitter_type() == TemporalJitter::Type::None);
 	}
+	// --- FSR 1 behind a scaled-down scene (renderer/post/aa.cpp:75-174): "resolutionScale" 0.75 of a 4K swapchain ---
+	{
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo hdr;
+		hdr.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+		hdr.size_x = hdr.size_y = 0.75f;
+		graph.add_pass("lighting", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("HDR-main", hdr);
+		FrameParameters frame;
+		setup_hdr_postprocess(graph, frame, "HDR-main", "tonemapped", HDROptions{});
+		CHECK(setup_after_post_chain_upscaling(graph, "tonemapped", "post-scale-output", true));
+		graph.set_backbuffer_source("post-scale-output");
+		graph.bake();
+		CHECK(join(graph.get_baked_pass_names()) == "lighting,bloom-compute,tonemap,post-scale-output-scale,post-scale-output-sharpen,");
+		auto t = graph.get_resource_dimensions(graph.get_texture_resource("tonemapped"));
+		auto u = graph.get_resource_dimensions(graph.get_texture_resource("post-scale-output-scale"));
+		auto o = graph.get_resource_dimensions(graph.get_texture_resource("post-scale-output"));
+		CHECK(t.width == 2880 && t.height == 1620);
+		CHECK(u.format == VK_FORMAT_R8G8B8A8_UNORM && u.width == 3840 && u.height == 2160);
+		CHECK(o.format == VK_FORMAT_R8G8B8A8_SRGB && o.width == 3840 && o.height == 2160);
+		CHECK(graph.get_texture_resource("tonemapped").get_attachment_info().flags & ATTACHMENT_INFO_UNORM_SRGB_ALIAS_BIT);
+	}
+	{
+		// without the sharpen pass the upscale writes `output` itself, as R8G8B8A8_UNORM (aa.cpp:80-84)
+		RenderGraph graph;
+		graph.set_backbuffer_dimensions(dim);
+		AttachmentInfo hdr;
+		hdr.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+		hdr.size_x = hdr.size_y = 0.5f;
+		graph.add_pass("lighting", RENDER_GRAPH_QUEUE_GRAPHICS_BIT).add_color_output("HDR-main", hdr);
+		FrameParameters frame;
+		setup_hdr_postprocess(graph, frame, "HDR-main", "tonemapped", HDROptions{});
+		CHECK(setup_after_post_chain_upscaling(graph, "tonemapped", "post-scale-output", false));
+		graph.set_backbuffer_source("post-scale-output");
+		graph.bake();
+		CHECK(join(graph.get_baked_pass_names()) == "lighting,bloom-compute,tonemap,post-scale-output-scale,");
+		auto o = graph.get_resource_dimensions(graph.get_texture_resource("post-scale-output"));
+		CHECK(o.format == VK_FORMAT_R8G8B8A8_UNORM && o.width == 3840 && o.height == 2160);
+	}
+
 	// --- the .gtx container the lookup textures come in (vulkan/texture/memory_mapped_texture.cpp:29-46) ---
 	{
 		std::vector<uint8_t> file(64 + 4 * 3 * 2, 0);
