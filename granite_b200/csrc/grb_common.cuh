@@ -276,4 +276,17 @@ GRB_DEV float3 fetch_hdr_clamped(const View<const uint32_t> &im, int x, int y)
 	return unpack_r11g11b10(__ldg(&im.at(iclamp(x, 0, im.w - 1), iclamp(y, 0, im.h - 1))));
 }
 
+// The HDR image in its other storage format, R16G16B16A16_SFLOAT ("renderTargetFp16", scene_viewer_application.cpp:
+// 880-884): the kernels that read HDR-main are templated on the texel type and decode through these overloads.
+GRB_DEV float3 hdr_texel(const View<const uint32_t> &im, int x, int y) { return unpack_r11g11b10(__ldg(&im.at(x, y))); }
+GRB_DEV float3 hdr_texel(const View<const uint2> &im, int x, int y)
+{
+	const float4 t = unpack_rgba16f(__ldg(&im.at(x, y)));
+	return make_float3(t.x, t.y, t.z);
+}
+GRB_DEV float3 fetch_hdr_clamped(const View<const uint2> &im, int x, int y)
+{
+	return hdr_texel(im, iclamp(x, 0, im.w - 1), iclamp(y, 0, im.h - 1));
+}
+
 } // namespace grb

@@ -65,6 +65,10 @@ struct LightingParams
 	const float *shadow_transforms;    // 16 floats per light: ClustererBindlessTransforms::shadow[index]
 	const uint16_t *const *shadow_maps; // per light: D16_UNORM, res^2 (spot) or 6 res^2 (point cube); null = no shadow
 	int shadow_res;
+	// "renderTargetFp16" (scene_viewer_application.cpp:880-884): HDR-main / emissive as R16G16B16A16_SFLOAT; the generic
+	// kernel's HDR16 form reads and writes these instead of hdr / emissive
+	View<uint2> hdr16;
+	View<const uint2> emissive16;
 };
 
 struct Surface
@@ -186,7 +190,9 @@ constexpr int kWarpsPerCta = 4;
 
 // SHADOWS: POSITIONAL_LIGHTS_SHADOW (renderer.cpp:369,1126) -- each light's falloff is multiplied by the comparison
 // sample of its own shadow map (point.h:45-74, spot.h:51-77), taken only by the lanes the light reaches.
-template <bool SHADOWS>
+// HDR16: the blend destination is R16G16B16A16_SFLOAT -- each of the two additive blends rounds to fp16 (RNE), alpha
+// passes through (the shaders write RGB only).
+template <bool SHADOWS, bool HDR16 = false>
 __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(const LightingParams p)
 {
 	__shared__ float s_srgb[256];
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int x = (blockIdx.x * kWarpsPerCta + warp) * 8 + (lane & 7);
 	const int y = p.y0 + blockIdx.y * 4 + (lane >> 3);
-	const bool inside = x < p.hdr.w && y < p.y1;
+	const bool inside = x < p.depth.w && y < p.y1;
 
 	float depth = 0.0f;
 	if (inside)
@@ -207,6 +213,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 
 	Surface s;
 	uint32_t dst = 0u;
+	float3 dst16 = make_float3(0.f, 0.f, 0.f); // HDR16: the destination's RGB as the fp16 values it holds
+	uint32_t alpha16 = 0u;
 	uint32_t rx = 0xffffffffu, ry = 0u;
 	int cluster_base = 0;
 	float3 base_color = make_float3(0.f, 0.f, 0.f);
@@ -215,7 +223,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		const uint32_t a8 = __ldg(&p.albedo.at(x, y));
 		const uint32_t n10 = __ldg(&p.normal.at(x, y));
 		const uint32_t mr = __ldg(&p.pbr.at(x, y));
-		dst = __ldg(&p.emissive.at(x, y));
+		if (HDR16)
+		{
+			const uint2 t = __ldg(&p.emissive16.at(x, y));
+			const float4 f = unpack_rgba16f(t);
+			dst16 = make_float3(f.x, f.y, f.z);
+			alpha16 = t.y & 0xffff0000u;
+		}
+		else
+			dst = __ldg(&p.emissive.at(x, y));
 
 		base_color = make_float3(s_srgb[a8 & 0xffu], s_srgb[(a8 >> 8) & 0xffu], s_srgb[(a8 >> 16) & 0xffu]);
 		// UNORM decode: these feed only the BRDF (not the bit-exact indices), a multiply by the
@@ -256,9 +272,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		// ---- draw 1: directional.frag (LIGHTING_NO_AMBIENT, no shadows, VOLUMETRIC_DIFFUSE_FALLBACK) ----
 		float NoL;
 		float3 b = brdf(s, p.dir_dir, NoL);
-		float3 e = unpack_r11g11b10(dst);
-		dst = pack_r11g11b10(e.x + p.dir_color.x * NoL * b.x + base_color.x * 0.05f, e.y + p.dir_color.y * NoL * b.y + base_color.y * 0.05f,
-		                     e.z + p.dir_color.z * NoL * b.z + base_color.z * 0.05f);
+		if (HDR16)
+			dst16 = make_float3(h2f(f2h(dst16.x + p.dir_color.x * NoL * b.x + base_color.x * 0.05f)), h2f(f2h(dst16.y + p.dir_color.y * NoL * b.y + base_color.y * 0.05f)),
+			                    h2f(f2h(dst16.z + p.dir_color.z * NoL * b.z + base_color.z * 0.05f)));
+		else
+		{
+			float3 e = unpack_r11g11b10(dst);
+			dst = pack_r11g11b10(e.x + p.dir_color.x * NoL * b.x + base_color.x * 0.05f, e.y + p.dir_color.y * NoL * b.y + base_color.y * 0.05f,
+			                     e.z + p.dir_color.z * NoL * b.z + base_color.z * 0.05f);
+		}
 	}
 
 	// ---- draw 2: clustering.frag, warp-uniform walk over the union of the lanes' masks ----
@@ -325,6 +347,19 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 		}
 	}
 
+	if (HDR16)
+	{
+		if (lit)
+		{
+			uint2 t;
+			t.x = (uint32_t)f2h(dst16.x + acc.x) | ((uint32_t)f2h(dst16.y + acc.y) << 16);
+			t.y = (uint32_t)f2h(dst16.z + acc.z) | alpha16;
+			p.hdr16.at(x, y) = t;
+		}
+		else if (inside && p.emissive16.p != p.hdr16.p)
+			p.hdr16.at(x, y) = __ldg(&p.emissive16.at(x, y)); // sky keeps the attachment value
+		return;
+	}
 	if (lit)
 	{
 		float3 e = unpack_r11g11b10(dst);
@@ -1443,11 +1478,12 @@ static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *ca
 		set_last_error("grb_deferred_lighting: null argument");
 		return GRB_ERR_INVALID_ARGUMENT;
 	}
+	const bool hdr16 = image_ok(hdr, GRB_FORMAT_R16G16B16A16_SFLOAT, 8); // "renderTargetFp16"
 	if (!image_ok(&g->albedo, GRB_FORMAT_R8G8B8A8_SRGB, 4) || !image_ok(&g->normal, GRB_FORMAT_A2B10G10R10_UNORM_PACK32, 4) ||
 	    !image_ok(&g->pbr, GRB_FORMAT_R8G8_UNORM, 2) || !image_ok(&g->depth, GRB_FORMAT_D32_SFLOAT, 4) ||
-	    !image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4))
+	    (!hdr16 && !image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4)))
 	{
-		set_last_error("grb_deferred_lighting: G-buffer must be R8G8B8A8_SRGB / A2B10G10R10_UNORM / R8G8_UNORM / D32_SFLOAT, hdr B10G11R11_UFLOAT");
+		set_last_error("grb_deferred_lighting: G-buffer must be R8G8B8A8_SRGB / A2B10G10R10_UNORM / R8G8_UNORM / D32_SFLOAT, hdr B10G11R11_UFLOAT or R16G16B16A16_SFLOAT");
 		return GRB_ERR_UNSUPPORTED_FORMAT;
 	}
 	const int w = hdr->width, h = hdr->height;
@@ -1477,17 +1513,22 @@ static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *ca
 	p.pbr = view_of<const uint16_t>(&g->pbr);
 	p.depth = view_of<const float>(&g->depth);
 	p.hdr = view_of<uint32_t>(hdr);
+	p.hdr16 = view_of<uint2>(hdr);
 	if (g->emissive.data)
 	{
-		if (!image_ok(&g->emissive, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || g->emissive.width != w || g->emissive.height != h)
+		if (!image_ok(&g->emissive, hdr->format, hdr16 ? 8 : 4) || g->emissive.width != w || g->emissive.height != h)
 		{
-			set_last_error("grb_deferred_lighting: emissive must be B10G11R11_UFLOAT of the G-buffer's size");
+			set_last_error("grb_deferred_lighting: emissive must have hdr's format (B10G11R11_UFLOAT or R16G16B16A16_SFLOAT) and the G-buffer's size");
 			return GRB_ERR_UNSUPPORTED_FORMAT;
 		}
 		p.emissive = view_of<const uint32_t>(&g->emissive);
+		p.emissive16 = view_of<const uint2>(&g->emissive);
 	}
 	else
+	{
 		p.emissive = view_of<const uint32_t>(hdr);
+		p.emissive16 = view_of<const uint2>(hdr);
+	}
 	for (int i = 0; i < 16; i++)
 		p.ivp[i] = cam->inv_view_projection[i];
 	p.camera_pos = make_float3(cam->camera_position[0], cam->camera_position[1], cam->camera_position[2]);
@@ -1516,7 +1557,7 @@ static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *ca
 	// two pixels per thread (packed fp32) whenever rows can be addressed as aligned pixel pairs
 	static const bool force_1px = getenv("GRB_LIGHTING_1PX") != nullptr;
 	auto aligned8 = [](const void *ptr, int pitch_bytes) { return (reinterpret_cast<uintptr_t>(ptr) % 8) == 0 && (pitch_bytes % 8) == 0; };
-	const bool pairs = !shadows && !force_1px && (w % 2) == 0 && aligned8(g->albedo.data, g->albedo.row_pitch) && aligned8(g->normal.data, g->normal.row_pitch) &&
+	const bool pairs = !shadows && !hdr16 && !force_1px && (w % 2) == 0 && aligned8(g->albedo.data, g->albedo.row_pitch) && aligned8(g->normal.data, g->normal.row_pitch) &&
 	                   aligned8(g->depth.data, g->depth.row_pitch) && (reinterpret_cast<uintptr_t>(g->pbr.data) % 4) == 0 && (g->pbr.row_pitch % 4) == 0 &&
 	                   aligned8(hdr->data, hdr->row_pitch) && (!g->emissive.data || aligned8(g->emissive.data, g->emissive.row_pitch));
 	static const bool force_v2 = getenv("GRB_LIGHTING_V2") != nullptr;
@@ -1586,7 +1627,11 @@ static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *ca
 		return check_launch("grb_deferred_lighting");
 	}
 	dim3 grid((w + 8 * kWarpsPerCta - 1) / (8 * kWarpsPerCta), (rows.y1 - rows.y0 + 3) / 4, 1);
-	if (shadows)
+	if (hdr16 && shadows)
+		deferred_lighting_kernel<true, true><<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);
+	else if (hdr16)
+		deferred_lighting_kernel<false, true><<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);
+	else if (shadows)
 		deferred_lighting_kernel<true><<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);
 	else
 		deferred_lighting_kernel<false><<<grid, 32 * kWarpsPerCta, 0, as_stream(stream)>>>(p);

@@ -26,8 +26,8 @@ inline dim3 grid_for(int w, int rows) { return dim3((w + kBlockX - 1) / kBlockX,
 
 // ------------------------------------------------------------------------------- K7
 // bloom_threshold: out(x,y) = f(bilinear HDR at the output texel centre).
-template <bool DynamicExposure>
-__global__ void __launch_bounds__(kBlockX *kBlockY) bloom_threshold_kernel(View<const uint32_t> hdr, const float *__restrict__ lum,
+template <bool DynamicExposure, typename HdrTexel = uint32_t>
+__global__ void __launch_bounds__(kBlockX *kBlockY) bloom_threshold_kernel(View<const HdrTexel> hdr, const float *__restrict__ lum,
                                                                           View<uint2> out, int y0, int y1, float inv_w, float inv_h)
 {
 	int x = blockIdx.x * kBlockX + threadIdx.x;
@@ -37,10 +37,10 @@ __global__ void __launch_bounds__(kBlockX *kBlockY) bloom_threshold_kernel(View<
 	float u = ((float)x + 0.5f) * inv_w;
 	float v = ((float)y + 0.5f) * inv_h;
 	Bilin s = bilin_setup(u, v, hdr.w, hdr.h);
-	float3 t00 = unpack_r11g11b10(__ldg(&hdr.at(s.x0, s.y0)));
-	float3 t10 = unpack_r11g11b10(__ldg(&hdr.at(s.x1, s.y0)));
-	float3 t01 = unpack_r11g11b10(__ldg(&hdr.at(s.x0, s.y1)));
-	float3 t11 = unpack_r11g11b10(__ldg(&hdr.at(s.x1, s.y1)));
+	float3 t00 = hdr_texel(hdr, s.x0, s.y0);
+	float3 t10 = hdr_texel(hdr, s.x1, s.y0);
+	float3 t01 = hdr_texel(hdr, s.x0, s.y1);
+	float3 t11 = hdr_texel(hdr, s.x1, s.y1);
 	float3 c = make_float3(bilin_mix(t00.x, t10.x, t01.x, t11.x, s.a, s.b), bilin_mix(t00.y, t10.y, t01.y, t11.y, s.a, s.b),
 	                       bilin_mix(t00.z, t10.z, t01.z, t11.z, s.a, s.b));
 	float luminance = fmax_(fmax_(c.x, c.y), c.z) + 0.0001f;
@@ -328,15 +328,15 @@ __device__ __forceinline__ float uncharted2(float x)
 	return ((x * (A * x + CB) + DE) / (x * (A * x + B) + DF)) - EF;
 }
 
-template <bool DynamicExposure, bool SrgbTarget>
-__global__ void __launch_bounds__(kBlockX *kBlockY) tonemap_kernel(View<const uint32_t> hdr, View<const uint2> bloom, const float *__restrict__ lum,
+template <bool DynamicExposure, bool SrgbTarget, typename HdrTexel = uint32_t>
+__global__ void __launch_bounds__(kBlockX *kBlockY) tonemap_kernel(View<const HdrTexel> hdr, View<const uint2> bloom, const float *__restrict__ lum,
                                                                   float exposure, View<uint32_t> out, int y0, int y1, float inv_w, float inv_h)
 {
 	int x = blockIdx.x * kBlockX + threadIdx.x;
 	int y = y0 + blockIdx.y * kBlockY + threadIdx.y;
 	if (x >= out.w || y >= y1)
 		return;
-	float3 c = unpack_r11g11b10(__ldg(&hdr.at(x, y)));
+	float3 c = hdr_texel(hdr, x, y);
 	float u = ((float)x + 0.5f) * inv_w;
 	float v = ((float)y + 0.5f) * inv_h;
 	float4 b = sample_rgba16f(bloom, u, v);
@@ -554,13 +554,15 @@ __device__ __forceinline__ float3 clamp_box(float3 color, float3 lo, float3 hi)
 	return color;
 }
 
-struct TaaInputs
+template <typename HdrTexel>
+struct TaaInputsT
 {
-	View<const uint32_t> hdr;
+	View<const HdrTexel> hdr;
 	View<const float> depth;
 	View<const uint32_t> mv; // RG16F packed
 	View<const uint2> history;
 };
+using TaaInputs = TaaInputsT<uint32_t>;
 
 __device__ __forceinline__ float3 sample_rgb16f(const View<const uint2> &im, float u, float v)
 {
@@ -614,8 +616,8 @@ struct Mat4
 	float m[16];
 };
 
-template <int Quality, bool History>
-__global__ void __launch_bounds__(kBlockX *kBlockY) taa_kernel(TaaInputs in, Mat4 reproj, View<uint32_t> out_color, View<uint2> out_history, int y0,
+template <int Quality, bool History, typename HdrTexel = uint32_t>
+__global__ void __launch_bounds__(kBlockX *kBlockY) taa_kernel(TaaInputsT<HdrTexel> in, Mat4 reproj, View<uint32_t> out_color, View<uint2> out_history, int y0,
                                                               int y1, float4 rt)
 {
 	int x = blockIdx.x * kBlockX + threadIdx.x;
@@ -909,9 +911,10 @@ using namespace grb;
 
 extern "C" int32_t grb_bloom_threshold(const GrbImage *hdr, const float *luminance, const GrbImage *out, GrbRows rows, void *stream)
 {
-	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !image_ok(out, GRB_FORMAT_R16G16B16A16_SFLOAT, 8))
+	const bool hdr16 = image_ok(hdr, GRB_FORMAT_R16G16B16A16_SFLOAT, 8); // "renderTargetFp16"
+	if ((!hdr16 && !image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4)) || !image_ok(out, GRB_FORMAT_R16G16B16A16_SFLOAT, 8))
 	{
-		set_last_error("grb_bloom_threshold: hdr must be B10G11R11_UFLOAT and out R16G16B16A16_SFLOAT");
+		set_last_error("grb_bloom_threshold: hdr must be B10G11R11_UFLOAT or R16G16B16A16_SFLOAT and out R16G16B16A16_SFLOAT");
 		return GRB_ERR_UNSUPPORTED_FORMAT;
 	}
 	rows = full_rows(rows, out->height);
@@ -920,6 +923,14 @@ extern "C" int32_t grb_bloom_threshold(const GrbImage *hdr, const float *luminan
 	auto o = view_of<uint2>(out);
 	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
 	float inv_w = 1.0f / (float)out->width, inv_h = 1.0f / (float)out->height; // hdr.cpp:140-141
+	if (hdr16)
+	{
+		if (luminance)
+			bloom_threshold_kernel<true, uint2><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint2>(hdr), luminance, o, rows.y0, rows.y1, inv_w, inv_h);
+		else
+			bloom_threshold_kernel<false, uint2><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint2>(hdr), nullptr, o, rows.y0, rows.y1, inv_w, inv_h);
+		return check_launch("grb_bloom_threshold");
+	}
 	if (luminance)
 		bloom_threshold_kernel<true><<<grid, block, 0, as_stream(stream)>>>(view_of<const uint32_t>(hdr), luminance, o, rows.y0, rows.y1, inv_w, inv_h);
 	else
@@ -1090,11 +1101,12 @@ extern "C" int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const
                                GrbRows rows, void *stream)
 {
 	bool srgb = out && out->format == GRB_FORMAT_R8G8B8A8_SRGB;
-	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !image_ok(bloom, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) ||
+	const bool hdr16 = image_ok(hdr, GRB_FORMAT_R16G16B16A16_SFLOAT, 8); // "renderTargetFp16"
+	if ((!hdr16 && !image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4)) || !image_ok(bloom, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) ||
 	    !(image_ok(out, GRB_FORMAT_R8G8B8A8_SRGB, 4) || image_ok(out, GRB_FORMAT_R8G8B8A8_UNORM, 4)) || out->width != hdr->width ||
 	    out->height != hdr->height)
 	{
-		set_last_error("grb_tonemap: hdr B10G11R11_UFLOAT, bloom R16G16B16A16_SFLOAT, out R8G8B8A8_{SRGB,UNORM} of hdr's size");
+		set_last_error("grb_tonemap: hdr B10G11R11_UFLOAT or R16G16B16A16_SFLOAT, bloom R16G16B16A16_SFLOAT, out R8G8B8A8_{SRGB,UNORM} of hdr's size");
 		return GRB_ERR_UNSUPPORTED_FORMAT;
 	}
 	rows = full_rows(rows, out->height);
@@ -1102,10 +1114,24 @@ extern "C" int32_t grb_tonemap(const GrbImage *hdr, const GrbImage *bloom, const
 		return GRB_OK;
 	dim3 grid = grid_for(out->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
 	float inv_w = 1.0f / (float)out->width, inv_h = 1.0f / (float)out->height;
-	auto h = view_of<const uint32_t>(hdr);
 	auto b = view_of<const uint2>(bloom);
 	auto o = view_of<uint32_t>(out);
 	cudaStream_t s = as_stream(stream);
+	if (hdr16)
+	{
+		// the generic one-pixel kernel with the fp16 texel decode (the tile and 4-pixel forms read B10G11R11 only)
+		auto h16 = view_of<const uint2>(hdr);
+		if (luminance && srgb)
+			tonemap_kernel<true, true, uint2><<<grid, block, 0, s>>>(h16, b, luminance, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+		else if (luminance)
+			tonemap_kernel<true, false, uint2><<<grid, block, 0, s>>>(h16, b, luminance, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+		else if (srgb)
+			tonemap_kernel<false, true, uint2><<<grid, block, 0, s>>>(h16, b, nullptr, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+		else
+			tonemap_kernel<false, false, uint2><<<grid, block, 0, s>>>(h16, b, nullptr, dynamic_exposure, o, rows.y0, rows.y1, inv_w, inv_h);
+		return check_launch("grb_tonemap");
+	}
+	auto h = view_of<const uint32_t>(hdr);
 	{
 		int32_t rc = GRB_OK;
 		if (launch_tonemap_fast(hdr, bloom, luminance, dynamic_exposure, out, rows, s, &rc))
@@ -1166,11 +1192,12 @@ extern "C" int32_t grb_fxaa(const GrbImage *in, const GrbImage *out, GrbRows row
 extern "C" int32_t grb_taa_resolve(const GrbImage *hdr, const GrbImage *depth, const GrbImage *mv, const GrbImage *history, const float *reproj16,
                                    int32_t quality, const GrbImage *out_color, const GrbImage *out_history, GrbRows rows, void *stream)
 {
-	if (!image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) || !image_ok(out_color, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) ||
+	const bool hdr16 = image_ok(hdr, GRB_FORMAT_R16G16B16A16_SFLOAT, 8); // "renderTargetFp16": the resolve's own output stays B10G11R11 (temporal.cpp:209-212)
+	if ((!hdr16 && !image_ok(hdr, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4)) || !image_ok(out_color, GRB_FORMAT_B10G11R11_UFLOAT_PACK32, 4) ||
 	    !image_ok(out_history, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || out_color->width != hdr->width || out_color->height != hdr->height ||
 	    out_history->width != hdr->width || out_history->height != hdr->height)
 	{
-		set_last_error("grb_taa_resolve: hdr/out_color B10G11R11_UFLOAT, out_history R16G16B16A16_SFLOAT, equal sizes");
+		set_last_error("grb_taa_resolve: hdr B10G11R11_UFLOAT or R16G16B16A16_SFLOAT, out_color B10G11R11_UFLOAT, out_history R16G16B16A16_SFLOAT, equal sizes");
 		return GRB_ERR_UNSUPPORTED_FORMAT;
 	}
 	if (history && (!image_ok(history, GRB_FORMAT_R16G16B16A16_SFLOAT, 8) || !image_ok(depth, GRB_FORMAT_D32_SFLOAT, 4) ||
@@ -1189,7 +1216,7 @@ extern "C" int32_t grb_taa_resolve(const GrbImage *hdr, const GrbImage *depth, c
 	rows = full_rows(rows, hdr->height);
 	if (rows.y1 <= rows.y0)
 		return GRB_OK;
-	if (history && quality == 2)
+	if (history && quality == 2 && !hdr16)
 	{
 		int32_t rc = GRB_OK;
 		if (launch_taa_fast(hdr, depth, mv, history, reproj16, out_color, out_history, rows, as_stream(stream), &rc))
@@ -1211,6 +1238,25 @@ extern "C" int32_t grb_taa_resolve(const GrbImage *hdr, const GrbImage *depth, c
 	float4 rt = make_float4(1.0f / (float)hdr->width, 1.0f / (float)hdr->height, (float)hdr->width, (float)hdr->height); // temporal.cpp:245-248
 	dim3 grid = grid_for(hdr->width, rows.y1 - rows.y0), block(kBlockX, kBlockY);
 	cudaStream_t s = as_stream(stream);
+	if (hdr16)
+	{
+		TaaInputsT<uint2> in16{};
+		in16.hdr = view_of<const uint2>(hdr);
+		in16.depth = in.depth;
+		in16.mv = in.mv;
+		in16.history = in.history;
+#define GRB_LAUNCH16(Q, H) taa_kernel<Q, H, uint2><<<grid, block, 0, s>>>(in16, m, oc, oh, rows.y0, rows.y1, rt)
+		if (!history)
+			GRB_LAUNCH16(0, false);
+		else if (quality == 0)
+			GRB_LAUNCH16(0, true);
+		else if (quality == 1)
+			GRB_LAUNCH16(1, true);
+		else
+			GRB_LAUNCH16(2, true);
+#undef GRB_LAUNCH16
+		return check_launch("grb_taa_resolve");
+	}
 #define GRB_LAUNCH(Q, H) taa_kernel<Q, H><<<grid, block, 0, s>>>(in, m, oc, oh, rows.y0, rows.y1, rt)
 	if (!history)
 		GRB_LAUNCH(0, false);

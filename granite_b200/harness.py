@@ -113,14 +113,19 @@ class GBufferDevice:
         self.struct = g
 
 
+def _hdr_img(t):
+    """HDR-main / emissive: an (H, W) int32 tensor is B10G11R11_UFLOAT, an (H, W, 4) int16 tensor R16G16B16A16_SFLOAT ("renderTargetFp16")."""
+    return capi.image(t, capi.FORMAT_R16G16B16A16_SFLOAT if t.dim() == 3 else capi.FORMAT_B10G11R11_UFLOAT)
+
+
 def lighting_schedule(height: int) -> torch.Tensor:
     """Zero-initialised schedule buffer for grb_deferred_lighting_scheduled (kept across frames)."""
     return torch.zeros(int(capi.lib().grb_lighting_schedule_bytes(height)) // 4, dtype=torch.int32, device="cuda")
 
 
 def deferred_lighting(gb: GBufferDevice, cam: capi.GrbCamera, cluster: ClusterDevice, hdr: torch.Tensor, rows=None, schedule=None):
-    """hdr: int32 (H, W) tensor holding the emissive / HDR-main attachment; updated in place."""
-    img = capi.image(hdr, capi.FORMAT_B10G11R11_UFLOAT)
+    """hdr: int32 (H, W) tensor (or int16 (H, W, 4): RGBA16F) holding the emissive / HDR-main attachment; updated in place."""
+    img = _hdr_img(hdr)
     if schedule is not None:
         capi.check(capi.lib().grb_deferred_lighting_scheduled(C.byref(gb.struct), C.byref(cam), C.byref(cluster.params), C.byref(cluster.buffers),
                                                               C.byref(img), capi.rows(rows), _ptr(schedule), capi.stream_ptr()),
@@ -134,7 +139,7 @@ def deferred_lighting_shadowed(gb: GBufferDevice, cam: capi.GrbCamera, cluster: 
                               resolution: int, hdr: torch.Tensor, rows=None):
     """Lighting with shadowed positional lights.  transforms: float32 (n, 16) device tensor (cluster order); map_table: int64 (n,)
     device tensor of device pointers to each light's D16 map (0 = no shadow)."""
-    img = capi.image(hdr, capi.FORMAT_B10G11R11_UFLOAT)
+    img = _hdr_img(hdr)
     sh = capi.GrbLightShadows(_ptr(transforms), _ptr(map_table), int(resolution))
     capi.check(capi.lib().grb_deferred_lighting_shadowed(C.byref(gb.struct), C.byref(cam), C.byref(cluster.params), C.byref(cluster.buffers),
                                                          C.byref(sh), C.byref(img), capi.rows(rows), capi.stream_ptr()), "grb_deferred_lighting_shadowed")
@@ -149,14 +154,14 @@ def new_rgba16f(w, h):
 
 
 def bloom_threshold(hdr_t, lum_t, out_t, rows=None):
-    hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
+    hi = _hdr_img(hdr_t)
     oi = _img16(out_t)
     capi.check(capi.lib().grb_bloom_threshold(C.byref(hi), _ptr(lum_t), C.byref(oi), capi.rows(rows), capi.stream_ptr()), "grb_bloom_threshold")
 
 
 def bloom_threshold_downsample(hdr_t, lum_t, d0_t, threshold_t=None, rows=None):
     """Fused K7 + first K8 (TMA tiles); raises GrbError when the shape is not eligible."""
-    hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
+    hi = _hdr_img(hdr_t)
     oi = _img16(d0_t)
     ti = C.byref(_img16(threshold_t)) if threshold_t is not None else None
     capi.check(capi.lib().grb_bloom_threshold_downsample(C.byref(hi), _ptr(lum_t), ti, C.byref(oi), capi.rows(rows), capi.stream_ptr()),
@@ -210,7 +215,7 @@ def luminance_finalize(grid_t, size_x, size_y, lum_t, lerp, lo=-3.0, hi=2.0):
 
 
 def tonemap(hdr_t, bloom_t, lum_t, out_t, exposure=1.0, srgb=True, rows=None):
-    hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
+    hi = _hdr_img(hdr_t)
     bi = _img16(bloom_t)
     oi = capi.image(out_t, capi.FORMAT_R8G8B8A8_SRGB if srgb else capi.FORMAT_R8G8B8A8_UNORM)
     capi.check(capi.lib().grb_tonemap(C.byref(hi), C.byref(bi), _ptr(lum_t), C.c_float(exposure), C.byref(oi), capi.rows(rows), capi.stream_ptr()),
@@ -224,7 +229,7 @@ def fxaa(in_t, out_t, target_srgb=True, rows=None):
 
 
 def pq10_encode(hdr_t, ui_t, primary16, hdr_pre, ui_pre, max_light, out_t, rows=None):
-    hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
+    hi = _hdr_img(hdr_t)
     ui = capi.image(ui_t, capi.FORMAT_R8G8B8A8_UNORM)
     oi = capi.image(out_t, capi.FORMAT_A2B10G10R10_UNORM)
     m = (C.c_float * 16)(*np.asarray(primary16, np.float32).reshape(-1).tolist())
@@ -266,7 +271,7 @@ def fsr_sharpen(color_t, out_t, sharpness_stops=0.5, srgb=True, rows=None):
 
 
 def taa_resolve(hdr_t, depth_t, mv_t, history_t, reproj, quality, out_color_t, out_history_t, rows=None):
-    hi = capi.image(hdr_t, capi.FORMAT_B10G11R11_UFLOAT)
+    hi = _hdr_img(hdr_t)
     oc = capi.image(out_color_t, capi.FORMAT_B10G11R11_UFLOAT)
     oh = _img16(out_history_t)
     di = C.byref(capi.image(depth_t, capi.FORMAT_D32_SFLOAT)) if depth_t is not None else None

@@ -152,7 +152,7 @@ void GrbhViewer::bake_render_graph()
 
 	// ---- add_main_pass_deferred ----
 	AttachmentInfo emissive, albedo, normal, pbr, depth;
-	emissive.format = VK_FORMAT_B10G11R11_UFLOAT_PACK32;
+	emissive.format = config.render_target_fp16 ? VK_FORMAT_R16G16B16A16_SFLOAT : VK_FORMAT_B10G11R11_UFLOAT_PACK32; // scene_viewer_application.cpp:882-884
 	albedo.format = VK_FORMAT_R8G8B8A8_SRGB;
 	normal.format = VK_FORMAT_A2B10G10R10_UNORM_PACK32;
 	pbr.format = VK_FORMAT_R8G8_UNORM;
@@ -177,7 +177,7 @@ void GrbhViewer::bake_render_graph()
 	gbuffer.set_build_render_pass([this](Vulkan::CommandBuffer &cmd) {
 		if (!pending_upload)
 			return; // inputs already resident from an earlier frame
-		upload_rows(cmd, res_emissive, pending_upload->emissive, 4);
+		upload_rows(cmd, res_emissive, pending_upload->emissive, config.render_target_fp16 ? 8 : 4);
 		upload_rows(cmd, res_albedo, pending_upload->albedo, 4);
 		upload_rows(cmd, res_normal, pending_upload->normal, 4);
 		upload_rows(cmd, res_pbr, pending_upload->pbr, 2);
@@ -427,6 +427,8 @@ extern "C" int32_t grbh_viewer_create(const GrbhViewerConfig *config, GrbhViewer
 		return fail("grbh_viewer_create: SMAA reads the tonemapped 8-bit image; an HDR10 output has none (use TAA)");
 	if (config->resolution_scale > 0.0f && config->resolution_scale < 1.0f && config->hdr10_output)
 		return fail("grbh_viewer_create: FSR 1 upscaling reads the tonemapped 8-bit image; an HDR10 output has none");
+	if (config->render_target_fp16 && config->hdr10_output)
+		return fail("grbh_viewer_create: the HDR10 / PQ encoder reads a B10G11R11 scene image; render_target_fp16 is not supported with it");
 	if (!(config->resolution_scale >= 0.0f && config->resolution_scale <= 1.0f))
 		return fail("grbh_viewer_create: resolution_scale must be within [0, 1] (0 or 1 = off)");
 	GRBH_TRY

@@ -24,7 +24,7 @@ class GrbhViewerConfig(C.Structure):
                 ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p), ("pipelined_io", C.c_int32),
                 ("hdr10_output", C.c_int32), ("hdr10_max_content_light_level", C.c_float),
                 ("clustered_lights_shadows", C.c_int32), ("clustered_lights_shadow_resolution", C.c_int32),
-                ("resolution_scale", C.c_float), ("resolution_scale_sharpen", C.c_int32)]
+                ("resolution_scale", C.c_float), ("resolution_scale_sharpen", C.c_int32), ("render_target_fp16", C.c_int32)]
 
 
 class GrbhLights(C.Structure):
@@ -232,7 +232,8 @@ def shard_plan(width, height, bands, rank, fxaa=False) -> dict:
 class Viewer:
     def __init__(self, width, height, post_aa=AA_NONE, hdr_bloom=True, dynamic_exposure=True, cuda_device=0,
                  cluster_res=(128, 64, 4096), timestamps=False, stream=None, pipelined_io=False, hdr10_output=False, hdr10_max_cll=1000.0,
-                 light_shadows=False, shadow_resolution=512, resolution_scale=0.0, resolution_scale_sharpen=True):
+                 light_shadows=False, shadow_resolution=512, resolution_scale=0.0, resolution_scale_sharpen=True,
+                 render_target_fp16=False):
         cfg = GrbhViewerConfig()
         cfg.cuda_device = cuda_device
         cfg.width, cfg.height = width, height
@@ -249,6 +250,7 @@ class Viewer:
         cfg.clustered_lights_shadow_resolution = int(shadow_resolution)
         cfg.resolution_scale = float(resolution_scale)  # < 1: width x height is the display size, FSR 1 upscales to it
         cfg.resolution_scale_sharpen = int(resolution_scale_sharpen)
+        cfg.render_target_fp16 = int(render_target_fp16)  # emissive / HDR-main as RGBA16F: host_gbuffer's emissive is (H, W, 4) uint16
         self.width, self.height = width, height
         self._h = C.c_void_p()
         _check(lib().grbh_viewer_create(C.byref(cfg), C.byref(self._h)), "grbh_viewer_create")

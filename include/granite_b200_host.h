@@ -64,6 +64,9 @@ typedef struct GrbhViewerConfig
 	                                  * output) has ceil(scale * size) texels (:758-761, 888-889), and FSR 1 upscales the result
 	                                  * to the display size (:1263-1268).  Not with row sharding or HDR10 output. */
 	int32_t resolution_scale_sharpen; /* "resolutionScaleSharpen" (:249-250): the RCAS pass after the upscale */
+	int32_t render_target_fp16;       /* "renderTargetFp16" (:235-236, 880-884): emissive / HDR-main are R16G16B16A16_SFLOAT (8 bytes per
+	                                   * texel -- GrbhHostGBuffer::emissive then points at RGBA16F texels); lighting, bloom threshold,
+	                                   * tonemap and TAA read / write that format (TAA's own output stays B10G11R11).  Not with HDR10. */
 } GrbhViewerConfig;
 
 /* Raw light list as the application owns it (before the clusterer sorts/packs it). */

@@ -141,6 +141,12 @@ void orc_deferred_lighting_shadowed(const orc_gbuffer_t *g, const orc_camera_t *
                                     const orc_light_t *lights, const uint32_t *type_mask,
                                     const uint32_t *bitmask, const uint32_t *cluster_range, const orc_shadows_t *shadows,
                                     uint32_t *hdr_out, int y0, int y1);
+/* The same pass for an R16G16B16A16_SFLOAT HDR target ("renderTargetFp16", scene_viewer_application.cpp:880-884):
+ * g->emissive points at RGBA16F texels; each blend rounds to fp16 (RNE); alpha passes through.  shadows may be NULL. */
+void orc_deferred_lighting_fp16(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
+                                const orc_light_t *lights, const uint32_t *type_mask,
+                                const uint32_t *bitmask, const uint32_t *cluster_range, const orc_shadows_t *shadows,
+                                uint16_t *hdr_out_rgba16f, int y0, int y1);
 /* the two comparison samplers on their own (Vulkan specification's filtering, fp32 weights) */
 float orc_shadow_sample_2d(const uint16_t *map, int res, float clip_x, float clip_y, float clip_z, float clip_w);
 float orc_shadow_sample_cube(const uint16_t *map, int res, float dx, float dy, float dz, float ref);
@@ -150,6 +156,7 @@ int orc_shadow_cube_texel(int res, int f, int i, int j, size_t *texel);
 /* One additive blend into a B10G11R11 attachment (renderer.cpp:1009-1011): dst = q(unpack(dst) + src) where
  * mask != 0.  Used by the tests that run the reference's own fragment shaders (oracle/_ref). */
 void orc_blend_add_r11g11b10(uint32_t *dst, const float *src_rgb, const uint8_t *mask, int64_t count);
+void orc_blend_add_rgba16f(uint16_t *dst, const float *src_rgb, const uint8_t *mask, int64_t count);
 
 /* ---- HDR chain ---- */
 /* K7 bloom_threshold.comp:23-45.  lum3: {avg_log, avg_lin, avg_inv_lin} or NULL (DYNAMIC_EXPOSURE=0). */
@@ -173,6 +180,15 @@ void orc_fxaa(const uint32_t *in, int w, int h, int target_srgb, uint32_t *out, 
 void orc_taa_resolve(const uint32_t *hdr, const float *depth, const uint16_t *mv, const uint16_t *history,
                      int w, int h, const float *reproj16, int quality,
                      uint32_t *out_color, uint16_t *out_history, int y0, int y1);
+
+/* K7 / K11 / K13 reading an R16G16B16A16_SFLOAT HDR image ("renderTargetFp16": HDR-main is RGBA16F; TAA's own output stays
+ * B10G11R11, temporal.cpp:209-212).  Same functions, the HDR texel decode differs. */
+void orc_bloom_threshold_fp16(const uint16_t *hdr_rgba16f, int w_in, int h_in, const float *lum3, uint16_t *out, int w, int h);
+void orc_tonemap_fp16(const uint16_t *hdr_rgba16f, int w, int h, const uint16_t *bloom, int bw, int bh,
+                      const float *lum3, float exposure, uint32_t *out, int y0, int y1);
+void orc_taa_resolve_fp16(const uint16_t *hdr_rgba16f, const float *depth, const uint16_t *mv, const uint16_t *history,
+                          int w, int h, const float *reproj16, int quality,
+                          uint32_t *out_color, uint16_t *out_history, int y0, int y1);
 
 /* K14 pq10_encode.frag:20-52 + hdr.cpp:595-658 (setup_hdr10_pq_encoding): HDR10 / ST.2084 output encoding.
  * hdr: B10G11R11 linear scene colour; ui: R8G8B8A8_UNORM (alpha = how much of the scene shows through);

@@ -299,8 +299,12 @@ static void deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, c
                               const orc_light_t *lights, const uint32_t *type_mask,
                               const uint32_t *bitmask, const uint32_t *cluster_range,
                               uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
-                              int32_t *out_light_count, int y0, int y1, const orc_shadows_t *shadows)
+                              int32_t *out_light_count, int y0, int y1, const orc_shadows_t *shadows, int hdr_fp16)
 {
+	/* hdr_fp16 ("renderTargetFp16", scene_viewer_application.cpp:880-884): emissive / HDR-main are R16G16B16A16_SFLOAT;
+	 * each of the two additive blends then rounds to fp16 (RNE), alpha passes through (the shaders write RGB only). */
+	const uint16_t *emissive16 = (const uint16_t *)(const void *)g->emissive;
+	uint16_t *hdr_out16 = (uint16_t *)(void *)hdr_out;
 	const int W = g->width, H = g->height;
 	const float *ivp = cam->inv_view_projection;
 	const vec3 camera_pos = v3(cam->camera_position[0], cam->camera_position[1], cam->camera_position[2]);
@@ -316,13 +320,24 @@ static void deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, c
 		{
 			size_t idx = (size_t)y * W + x;
 			float depth = g->depth[idx];
-			uint32_t dst = g->emissive[idx];
+			uint32_t dst = hdr_fp16 ? 0u : g->emissive[idx];
+			vec3 dst16 = v3(0.0f, 0.0f, 0.0f);
+			if (hdr_fp16)
+			{
+				dst16 = v3(f16_to_f32(emissive16[4 * idx]), f16_to_f32(emissive16[4 * idx + 1]), f16_to_f32(emissive16[4 * idx + 2]));
+				hdr_out16[4 * idx + 3] = emissive16[4 * idx + 3];
+			}
 			if (out_tile_index) out_tile_index[idx] = -1;
 			if (out_z_index) out_z_index[idx] = -1;
 			if (out_light_count) out_light_count[idx] = 0;
 			if (depth == 0.0f)
 			{
-				hdr_out[idx] = dst; /* depth test NOT_EQUAL fails: sky keeps the attachment value */
+				/* depth test NOT_EQUAL fails: sky keeps the attachment value */
+				if (hdr_fp16)
+					for (int c = 0; c < 3; c++)
+						hdr_out16[4 * idx + c] = emissive16[4 * idx + c];
+				else
+					hdr_out[idx] = dst;
 				continue;
 			}
 
@@ -358,8 +373,14 @@ static void deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, c
 			const float base_ambient = 1.0f;
 			(void)ambient_a; /* material_ambient_factor only feeds the !LIGHTING_NO_AMBIENT branch */
 			lit = v3_add(lit, v3(base_ambient * base_color.x * 0.05f, base_ambient * base_color.y * 0.05f, base_ambient * base_color.z * 0.05f));
-			vec3 d = unpack_r11g11b10(dst);
-			dst = pack_r11g11b10(v3_add(lit, d));
+			vec3 d = hdr_fp16 ? dst16 : unpack_r11g11b10(dst);
+			if (hdr_fp16)
+			{
+				vec3 sum = v3_add(lit, d);
+				dst16 = v3(f16_to_f32(f32_to_f16_rne(sum.x)), f16_to_f32(f32_to_f16_rne(sum.y)), f16_to_f32(f32_to_f16_rne(sum.z)));
+			}
+			else
+				dst = pack_r11g11b10(v3_add(lit, d));
 
 			/* ---- draw 2: clustering.frag + clusterer_bindless.h:29-84 ---- */
 			vec3 result = v3(0.0f, 0.0f, 0.0f);
@@ -411,8 +432,18 @@ static void deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, c
 				}
 			}
 			if (out_light_count) out_light_count[idx] = count;
-			d = unpack_r11g11b10(dst);
-			hdr_out[idx] = pack_r11g11b10(v3_add(result, d));
+			if (hdr_fp16)
+			{
+				vec3 sum = v3_add(result, dst16);
+				hdr_out16[4 * idx] = f32_to_f16_rne(sum.x);
+				hdr_out16[4 * idx + 1] = f32_to_f16_rne(sum.y);
+				hdr_out16[4 * idx + 2] = f32_to_f16_rne(sum.z);
+			}
+			else
+			{
+				d = unpack_r11g11b10(dst);
+				hdr_out[idx] = pack_r11g11b10(v3_add(result, d));
+			}
 		}
 	}
 }
@@ -423,7 +454,7 @@ void orc_deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, cons
                            uint32_t *hdr_out, int32_t *out_tile_index, int32_t *out_z_index,
                            int32_t *out_light_count, int y0, int y1)
 {
-	deferred_lighting(g, cam, p, lights, type_mask, bitmask, cluster_range, hdr_out, out_tile_index, out_z_index, out_light_count, y0, y1, 0);
+	deferred_lighting(g, cam, p, lights, type_mask, bitmask, cluster_range, hdr_out, out_tile_index, out_z_index, out_light_count, y0, y1, 0, 0);
 }
 
 /* the same pass with POSITIONAL_LIGHTS_SHADOW (clustering.frag through point.h:45-74, spot.h:51-77) */
@@ -432,7 +463,17 @@ void orc_deferred_lighting_shadowed(const orc_gbuffer_t *g, const orc_camera_t *
                                     const uint32_t *bitmask, const uint32_t *cluster_range, const orc_shadows_t *shadows,
                                     uint32_t *hdr_out, int y0, int y1)
 {
-	deferred_lighting(g, cam, p, lights, type_mask, bitmask, cluster_range, hdr_out, 0, 0, 0, y0, y1, shadows);
+	deferred_lighting(g, cam, p, lights, type_mask, bitmask, cluster_range, hdr_out, 0, 0, 0, y0, y1, shadows, 0);
+}
+
+/* "renderTargetFp16": g->emissive points at R16G16B16A16_SFLOAT texels (4 x uint16 per pixel), hdr_out likewise;
+ * shadows may be NULL */
+void orc_deferred_lighting_fp16(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
+                                const orc_light_t *lights, const uint32_t *type_mask,
+                                const uint32_t *bitmask, const uint32_t *cluster_range, const orc_shadows_t *shadows,
+                                uint16_t *hdr_out_rgba16f, int y0, int y1)
+{
+	deferred_lighting(g, cam, p, lights, type_mask, bitmask, cluster_range, (uint32_t *)(void *)hdr_out_rgba16f, 0, 0, 0, y0, y1, shadows, 1);
 }
 
 /* renderer.cpp:1009-1011: additive blend, the attachment store quantises (oracle_math.h pack_r11g11b10) */
@@ -444,5 +485,17 @@ void orc_blend_add_r11g11b10(uint32_t *dst, const float *src_rgb, const uint8_t 
 			continue;
 		vec3 d = unpack_r11g11b10(dst[i]);
 		dst[i] = pack_r11g11b10(v3(d.x + src_rgb[3 * i + 0], d.y + src_rgb[3 * i + 1], d.z + src_rgb[3 * i + 2]));
+	}
+}
+
+/* the same blend into an R16G16B16A16_SFLOAT attachment: RGB = fp16_rne(decode(dst) + src), alpha untouched */
+void orc_blend_add_rgba16f(uint16_t *dst, const float *src_rgb, const uint8_t *mask, int64_t count)
+{
+	for (int64_t i = 0; i < count; i++)
+	{
+		if (!mask[i])
+			continue;
+		for (int c = 0; c < 3; c++)
+			dst[4 * i + c] = f32_to_f16_rne(f16_to_f32(dst[4 * i + c]) + src_rgb[3 * i + c]);
 	}
 }

@@ -16,10 +16,20 @@
 #include "oracle_math.h"
 
 /* ---- K7: bloom_threshold.comp:23-45 ---- */
+/* Storage format of the HDR image K7 / K11 / K13 read: 0 = B10G11R11_UFLOAT (default), 1 = R16G16B16A16_SFLOAT
+ * ("renderTargetFp16").  Set by the *_fp16 entry points around the shared implementation (test infrastructure: one call
+ * at a time). */
+static int g_hdr_fp16 = 0;
+
 static vec3 fetch_hdr(const uint32_t *hdr, int w, int h, int x, int y)
 {
 	x = x < 0 ? 0 : (x > w - 1 ? w - 1 : x);
 	y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
+	if (g_hdr_fp16)
+	{
+		const uint16_t *t = (const uint16_t *)(const void *)hdr + 4 * ((size_t)y * w + x);
+		return v3(f16_to_f32(t[0]), f16_to_f32(t[1]), f16_to_f32(t[2]));
+	}
 	return unpack_r11g11b10(hdr[(size_t)y * w + x]);
 }
 
@@ -572,4 +582,28 @@ void orc_pq10_encode(const uint32_t *hdr, const uint32_t *ui, int w, int h, cons
 			}
 			out[i] = unorm10(k[0]) | (unorm10(k[1]) << 10) | (unorm10(k[2]) << 20) | (3u << 30);
 		}
+}
+
+/* ---- "renderTargetFp16": the same three passes over an RGBA16F HDR image ---- */
+void orc_bloom_threshold_fp16(const uint16_t *hdr_rgba16f, int w_in, int h_in, const float *lum3, uint16_t *out, int w, int h)
+{
+	g_hdr_fp16 = 1;
+	orc_bloom_threshold((const uint32_t *)(const void *)hdr_rgba16f, w_in, h_in, lum3, out, w, h);
+	g_hdr_fp16 = 0;
+}
+
+void orc_tonemap_fp16(const uint16_t *hdr_rgba16f, int w, int h, const uint16_t *bloom, int bw, int bh, const float *lum3, float exposure,
+                      uint32_t *out, int y0, int y1)
+{
+	g_hdr_fp16 = 1;
+	orc_tonemap((const uint32_t *)(const void *)hdr_rgba16f, w, h, bloom, bw, bh, lum3, exposure, out, y0, y1);
+	g_hdr_fp16 = 0;
+}
+
+void orc_taa_resolve_fp16(const uint16_t *hdr_rgba16f, const float *depth, const uint16_t *mv, const uint16_t *history, int w, int h,
+                          const float *reproj16, int quality, uint32_t *out_color, uint16_t *out_history, int y0, int y1)
+{
+	g_hdr_fp16 = 1;
+	orc_taa_resolve((const uint32_t *)(const void *)hdr_rgba16f, depth, mv, history, w, h, reproj16, quality, out_color, out_history, y0, y1);
+	g_hdr_fp16 = 0;
 }

@@ -384,6 +384,30 @@ def deferred_lighting(scene, cam: Camera, prep, clus, rows=None, want_indices=Fa
     return hdr
 
 
+def deferred_lighting_fp16(scene, cam: Camera, prep, clus, emissive16, rows=None, shadows=None):
+    """The lighting pass into an R16G16B16A16_SFLOAT HDR-main ("renderTargetFp16").  emissive16: (H, W, 4) uint16.
+    shadows = (transforms, maps, resolution) or None.  Returns (H, W, 4) uint16."""
+    H, W = scene.depth.shape
+    g = GBuffer()
+    g.width, g.height = W, H
+    keep = [_c(scene.albedo, np.uint32), _c(scene.normal, np.uint32), _c(scene.pbr, np.uint16),
+            _c(scene.depth, np.float32), _c(emissive16, np.uint16)]
+    g.albedo, g.normal, g.pbr, g.depth, g.emissive = [k.ctypes.data for k in keep]
+    g.dir_color = (C.c_float * 3)(*scene.dir_color)
+    g.dir_direction = (C.c_float * 3)(*scene.dir_direction)
+    hdr = np.zeros((H, W, 4), np.uint16)
+    y0, y1 = rows if rows else (0, H)
+    sh = None
+    if shadows is not None:
+        t = _c(shadows[0], np.float32)
+        held = [None if m is None else _c(m, np.uint16) for m in shadows[1]]
+        table = (C.c_void_p * max(len(held), 1))(*[None if m is None else m.ctypes.data for m in held])
+        sh = C.byref(Shadows(t.ctypes.data, C.cast(table, C.c_void_p), int(shadows[2])))
+    lib().orc_deferred_lighting_fp16(C.byref(g), C.byref(cam), C.byref(prep.params), _p(prep.records), _p(prep.type_mask),
+                                     _p(clus.bitmask), _p(clus.range), sh, _p(hdr), y0, y1)
+    return hdr
+
+
 _ref_light = None
 
 
@@ -396,7 +420,7 @@ def ref_light_kernels():
     return _ref_light
 
 
-def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None, shadows=None):
+def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None, shadows=None, emissive16=None):
     """renderer.cpp:1004-1156 with the reference's own fragment shaders: the two draws' colours
     (fp32), then the two additive blends into B10G11R11 with DESIGN.md section 2's store rule:
     q(q(emissive + directional) + clustered).  Returns (hdr, directional_rgb, clustered_rgb).
@@ -426,10 +450,16 @@ def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None, shadows=Non
                           _p(_c(clus.range, np.uint32)), y0, y1, _p(c_rgb))
     L = lib()
     L.orc_blend_add_r11g11b10.restype = None
-    hdr = _c(scene.emissive, np.uint32).copy()
+    L.orc_blend_add_rgba16f.restype = None
     lit = dep != 0.0
     lit[:y0] = False
     lit[y1:] = False
+    if emissive16 is not None:  # R16G16B16A16_SFLOAT HDR-main: each blend rounds to fp16
+        hdr = _c(emissive16, np.uint16).copy()
+        for rgb in (d_rgb, c_rgb):
+            L.orc_blend_add_rgba16f(_p(hdr), _p(np.ascontiguousarray(rgb)), _p(np.ascontiguousarray(lit, dtype=np.uint8)), H * W)
+        return hdr, d_rgb, c_rgb
+    hdr = _c(scene.emissive, np.uint32).copy()
     for rgb in (d_rgb, c_rgb):
         L.orc_blend_add_r11g11b10(_p(hdr), _p(np.ascontiguousarray(rgb)), _p(np.ascontiguousarray(lit, dtype=np.uint8)), hdr.size)
     return hdr, d_rgb, c_rgb
@@ -437,11 +467,14 @@ def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None, shadows=Non
 
 # ---------------- HDR chain ----------------
 def bloom_threshold(hdr, lum3, out_wh):
-    h_in, w_in = hdr.shape
+    h_in, w_in = hdr.shape[:2]
     w, h = out_wh
     out = np.zeros((h, w, 4), np.uint16)
     l3 = None if lum3 is None else _c(lum3, np.float32)
-    lib().orc_bloom_threshold(_p(_c(hdr, np.uint32)), w_in, h_in, _p(l3), _p(out), w, h)
+    if hdr.ndim == 3:  # R16G16B16A16_SFLOAT HDR image ("renderTargetFp16")
+        lib().orc_bloom_threshold_fp16(_p(_c(hdr, np.uint16)), w_in, h_in, _p(l3), _p(out), w, h)
+    else:
+        lib().orc_bloom_threshold(_p(_c(hdr, np.uint32)), w_in, h_in, _p(l3), _p(out), w, h)
     return out
 
 
@@ -471,12 +504,15 @@ def luminance(d3, lum3, lerp, lo=-3.0, hi=2.0, want_grid=False):
 
 
 def tonemap(hdr, bloom, lum3, exposure=1.0, rows=None):
-    h, w = hdr.shape
+    h, w = hdr.shape[:2]
     bh, bw = bloom.shape[:2]
     out = np.zeros((h, w), np.uint32)
     l3 = None if lum3 is None else _c(lum3, np.float32)
     y0, y1 = rows if rows else (0, h)
-    lib().orc_tonemap(_p(_c(hdr, np.uint32)), w, h, _p(_c(bloom, np.uint16)), bw, bh, _p(l3), _f(exposure), _p(out), y0, y1)
+    if hdr.ndim == 3:
+        lib().orc_tonemap_fp16(_p(_c(hdr, np.uint16)), w, h, _p(_c(bloom, np.uint16)), bw, bh, _p(l3), _f(exposure), _p(out), y0, y1)
+    else:
+        lib().orc_tonemap(_p(_c(hdr, np.uint32)), w, h, _p(_c(bloom, np.uint16)), bw, bh, _p(l3), _f(exposure), _p(out), y0, y1)
     return out
 
 
@@ -489,22 +525,32 @@ def fxaa(img, target_srgb=True, rows=None):
 
 
 def taa_resolve(hdr, depth, mv, history, reproj, quality=2, rows=None):
-    h, w = hdr.shape
+    h, w = hdr.shape[:2]
     out_c = np.zeros((h, w), np.uint32)
     out_h = np.zeros((h, w, 4), np.uint16)
     hist = None if history is None else _c(history, np.uint16)
     y0, y1 = rows if rows else (0, h)
-    lib().orc_taa_resolve(_p(_c(hdr, np.uint32)), _p(_c(depth, np.float32)), _p(_c(mv, np.uint16)), _p(hist), w, h,
-                          _p(_c(reproj, np.float32)), int(quality), _p(out_c), _p(out_h), y0, y1)
+    fn, dt = (lib().orc_taa_resolve_fp16, np.uint16) if hdr.ndim == 3 else (lib().orc_taa_resolve, np.uint32)
+    fn(_p(_c(hdr, dt)), _p(_c(depth, np.float32)), _p(_c(mv, np.uint16)), _p(hist), w, h,
+       _p(_c(reproj, np.float32)), int(quality), _p(out_c), _p(out_h), y0, y1)
     return out_c, out_h
 
 
 # ---------------- the reference's own post shaders on the CPU (oracle/_ref) ----------------
+def _hdr_arg(k, hdr):
+    """The shim's HDR sampler reads B10G11R11 (2-D uint32 array) or, for a (H, W, 4) uint16 array, RGBA16F."""
+    k.refk_set_hdr_fp16(1 if hdr.ndim == 3 else 0)
+    return _c(hdr, np.uint16 if hdr.ndim == 3 else np.uint32)
+
+
 def ref_bloom_threshold(hdr, lum3, out_wh):
-    h_in, w_in = hdr.shape
+    h_in, w_in = hdr.shape[:2]
     w, h = out_wh
     out = np.zeros((h, w, 4), np.uint16)
-    ref_post_kernels()[7].refk7_bloom_threshold(_p(_c(hdr, np.uint32)), w_in, h_in, _p(_c(lum3, np.float32)), _p(out), w, h)
+    k = ref_post_kernels()[7]
+    a = _hdr_arg(k, hdr)
+    k.refk7_bloom_threshold(_p(a), w_in, h_in, _p(_c(lum3, np.float32)), _p(out), w, h)
+    k.refk_set_hdr_fp16(0)
     return out
 
 
@@ -536,12 +582,14 @@ def ref_luminance(d3, lum3, lerp, lo=-3.0, hi=2.0):
 
 
 def ref_tonemap(hdr, bloom, lum3, exposure=1.0, rows=None):
-    h, w = hdr.shape
+    h, w = hdr.shape[:2]
     bh, bw = bloom.shape[:2]
     out = np.zeros((h, w), np.uint32)
     y0, y1 = rows if rows else (0, h)
-    ref_post_kernels()[11].refk11_tonemap(_p(_c(hdr, np.uint32)), w, h, _p(_c(bloom, np.uint16)), bw, bh, _p(_c(lum3, np.float32)), _f(exposure),
-                                          _p(out), y0, y1)
+    k = ref_post_kernels()[11]
+    a = _hdr_arg(k, hdr)
+    k.refk11_tonemap(_p(a), w, h, _p(_c(bloom, np.uint16)), bw, bh, _p(_c(lum3, np.float32)), _f(exposure), _p(out), y0, y1)
+    k.refk_set_hdr_fp16(0)
     return out
 
 
@@ -555,17 +603,20 @@ def ref_fxaa(img, target_srgb=True, rows=None):
 
 
 def ref_taa_resolve(hdr, depth, mv, history, reproj, quality=2, rows=None):
-    h, w = hdr.shape
+    h, w = hdr.shape[:2]
     out_c = np.zeros((h, w), np.uint32)
     out_h = np.zeros((h, w, 4), np.uint16)
     y0, y1 = rows if rows else (0, h)
     k = ref_post_kernels()
     if history is None:
-        fn = k[43].refk13_taa_nohistory
+        kk, fn = k[43], k[43].refk13_taa_nohistory
     else:
+        kk = {0: k[23], 1: k[33], 2: k[13]}[int(quality)]
         fn = {0: k[23].refk13_taa_q0, 1: k[33].refk13_taa_q1, 2: k[13].refk13_taa_q2}[int(quality)]
-    fn(_p(_c(hdr, np.uint32)), _p(_c(depth, np.float32)), _p(_c(mv, np.uint16)), None if history is None else _p(_c(history, np.uint16)), w, h,
+    hdr = _hdr_arg(kk, hdr)
+    fn(_p(hdr), _p(_c(depth, np.float32)), _p(_c(mv, np.uint16)), None if history is None else _p(_c(history, np.uint16)), w, h,
        _p(_c(reproj, np.float32)), _p(out_c), _p(out_h), y0, y1)
+    kk.refk_set_hdr_fp16(0)
     return out_c, out_h
 
 
@@ -688,8 +739,9 @@ def pyramid_sizes(w, h):
 
 
 def hdr_chain(hdr, lum3, d3_history, frame_time=1.0 / 60.0, exposure=1.0, dynamic_exposure=True):
-    """One frame of setup_hdr_postprocess_compute (renderer/post/hdr.cpp:354-379) + tonemap."""
-    h, w = hdr.shape
+    """One frame of setup_hdr_postprocess_compute (renderer/post/hdr.cpp:354-379) + tonemap.  hdr: (H, W) uint32 B10G11R11 or
+    (H, W, 4) uint16 RGBA16F."""
+    h, w = hdr.shape[:2]
     sz = pyramid_sizes(w, h)
     lerp_d3 = np.float32(1.0 - 0.001 ** frame_time)   # hdr.cpp:182 (double math, then float)
     lerp_lum = np.float32(1.0 - 0.5 ** frame_time)    # hdr.cpp:93

@@ -318,8 +318,14 @@ struct Runner
 	}
 };
 
+// "renderTargetFp16": the HDR image K7 / K11 / K13 sample is R16G16B16A16_SFLOAT instead of B10G11R11 (set by the tests
+// around a call; the pointer the entry points declare as uint32_t then addresses 8-byte texels)
+static int g_hdr_fp16 = 0;
+
 sampler2D make_sampler(const void *data, int w, int h, int format, bool linear = true)
 {
+	if (format == spirv_cross::FMT_R11G11B10 && g_hdr_fp16)
+		format = spirv_cross::FMT_RGBA16F;
 	sampler2D s;
 	s.data = data;
 	s.w = w;
@@ -331,6 +337,7 @@ sampler2D make_sampler(const void *data, int w, int h, int format, bool linear =
 } // namespace
 
 extern "C" {
+void refk_set_hdr_fp16(int enable) { g_hdr_fp16 = enable; }
 #if KERNEL == 7
 // hdr.cpp:115-144: dispatch ceil(w/8) x ceil(h/8), inv_output_size = 1 / out size
 void refk7_bloom_threshold(const uint32_t *hdr, int w_in, int h_in, const float *lum3, uint16_t *out, int w, int h)

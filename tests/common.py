@@ -161,3 +161,13 @@ def make_shadow_maps(prep, resolution, seed=0x5AD0, skip_every=7):
         m = np.repeat(np.repeat(coarse, 4, axis=1), 4, axis=2)[:, :resolution, :resolution]
         maps.append(np.ascontiguousarray(m if is_point else m[0]))
     return maps
+
+
+def random_hdr_f16(rng, w, h, scale=4.0, hot=0.002):
+    """Random R16G16B16A16_SFLOAT HDR image ("renderTargetFp16"), a few very bright texels, alpha 1: (h, w, 4) uint16."""
+    rgb = (rng.random((h, w, 3)) ** 3 * scale).astype(np.float32)
+    m = rng.random((h, w)) < hot
+    rgb[m] = rng.uniform(10.0, 200.0, size=(int(m.sum()), 3)).astype(np.float32)
+    img = np.ones((h, w, 4), np.float16)
+    img[..., :3] = rgb
+    return np.ascontiguousarray(img).view(np.uint16)
