@@ -177,7 +177,12 @@ typedef struct GrbGBuffer
 } GrbGBuffer;
 
 /* hdr: B10G11R11_UFLOAT; read-modify-write when gbuffer->emissive.data is NULL ("HDR-main"
- * aliases "emissive", scene_viewer_application.cpp:956-963), write-only otherwise. */
+ * aliases "emissive", scene_viewer_application.cpp:956-963), write-only otherwise.
+ * "renderTargetFp16" (scene_viewer_application.cpp:880-884): hdr (and emissive) may be R16G16B16A16_SFLOAT instead -- each of
+ * the two additive blends then rounds to fp16 (RNE) and alpha passes through; the pass runs on the generic one-pixel kernel.
+ * grb_bloom_threshold, grb_tonemap and grb_taa_resolve accept an R16G16B16A16_SFLOAT hdr likewise (TAA's own output stays
+ * B10G11R11, temporal.cpp:209-212); the fused / tile forms (grb_bloom_threshold_downsample*) take B10G11R11 only and
+ * return GRB_ERR_UNSUPPORTED_FORMAT, on which the caller issues the unfused pair. */
 int32_t grb_deferred_lighting(const GrbGBuffer *gbuffer, const GrbCamera *cam,
                               const GrbClusterParameters *params, const GrbClusterBuffers *buf,
                               const GrbImage *hdr, GrbRows rows, void *stream);
