@@ -24,6 +24,7 @@ UNITS = [
     ("grb_post_fast.cu", []),
     ("grb_smaa.cu", ["-fmad=false"]),
     ("grb_fsr.cu", ["-fmad=false"]),
+    ("grb_decal.cu", ["-fmad=false"]),
     ("grb_lighting.cu", []),
 ]
 

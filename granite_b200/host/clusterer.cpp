@@ -5,7 +5,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <numeric>
+#include <utility>
 #include <stdexcept>
 
 namespace Granite
@@ -111,7 +113,22 @@ void LightClusterer::add_render_passes_bindless(RenderGraph &graph)
 	att.size = sizeof(vec4) * 6 * ClustererMaxLightsBindless;
 	res_spots = &pass.add_storage_output("cluster-transformed-spot", att);
 
-	pass.set_build_render_pass([this](Vulkan::CommandBuffer &cmd) { build_cluster_bindless_gpu(cmd); });
+	if (enable_volumetric_decals)
+	{
+		// clusterer.cpp:1585-1592: the decals' own bitmask and Z-range buffers, same grid
+		att.size = resolution_x * resolution_y * (MaxDecalsBindless / 8);
+		res_bitmask_decal = &pass.add_storage_output("cluster-bitmask-decal", att);
+		att.size = resolution_z * sizeof(ivec2);
+		res_range_decal = &pass.add_storage_output("cluster-range-decal", att);
+		// per-frame inputs and scratch: [n x mat4 mvp][n x vec4 screen box][max(n,1) x uvec2 Z range]
+		att.size = MaxDecalsBindless * (sizeof(mat4) + sizeof(vec4) + sizeof(uvec2));
+		res_decal_scratch = &pass.add_transfer_output("cluster-decal-transforms", att);
+	}
+
+	pass.set_build_render_pass([this](Vulkan::CommandBuffer &cmd) {
+		build_cluster_bindless_gpu(cmd);
+		build_decal_clusters_gpu(cmd);
+	});
 }
 
 // renderer/lights/clusterer.cpp:83-93
@@ -132,6 +149,9 @@ void LightClusterer::setup_render_pass_resources(RenderGraph &graph)
 	transforms_buffer = graph.maybe_get_physical_buffer_resource(res_transforms);
 	cull_buffer = graph.maybe_get_physical_buffer_resource(res_cull);
 	spot_buffer = graph.maybe_get_physical_buffer_resource(res_spots);
+	bitmask_decal_buffer = res_bitmask_decal ? graph.maybe_get_physical_buffer_resource(res_bitmask_decal) : nullptr;
+	range_decal_buffer = res_range_decal ? graph.maybe_get_physical_buffer_resource(res_range_decal) : nullptr;
+	decal_scratch_buffer = res_decal_scratch ? graph.maybe_get_physical_buffer_resource(res_decal_scratch) : nullptr;
 }
 
 GrbClusterBuffers LightClusterer::get_cluster_buffers() const
@@ -176,6 +196,90 @@ void LightClusterer::refresh(const RenderContext &ctx)
 {
 	context = &ctx;
 	refresh_bindless_prepare(ctx);
+	refresh_decals(ctx);
+}
+
+// clusterer.cpp:1348-1369: view-depth range of the decal's unit cube
+vec2 LightClusterer::decal_z_range(const RenderContext &ctx, const mat_affine &transform)
+{
+	const auto &rp = ctx.get_render_parameters();
+	float lo = std::numeric_limits<float>::infinity(), hi = -std::numeric_limits<float>::infinity();
+	for (unsigned i = 0; i < 8; i++)
+	{
+		const vec4 corner((i & 1) ? 0.5f : -0.5f, (i & 2) ? 0.5f : -0.5f, (i & 4) ? 0.5f : -0.5f, 1.0f);
+		// SIMD::mul(vec4, mat_affine, vec4): one dot product per row, added pairwise as DPPS does
+		vec3 world;
+		float *w = &world.x;
+		for (int r = 0; r < 3; r++)
+			w[r] = (transform[r].x * corner.x + transform[r].y * corner.y) + (transform[r].z * corner.z + transform[r].w * corner.w);
+		const float z = dot(world - rp.camera_position, rp.camera_front);
+		lo = std::min(lo, z);
+		hi = std::max(hi, z);
+	}
+	return vec2(lo, hi);
+}
+
+// The visible decals front to back (clusterer.cpp:1124-1131, 1167-1171), their mvps (clusterer.cpp:1406-1410) and Z-slice
+// ranges (clusterer.cpp:1371-1389).
+void LightClusterer::refresh_decals(const RenderContext &ctx)
+{
+	decal_mvps.clear();
+	decal_index_range.clear();
+	if (!enable_volumetric_decals)
+		return;
+	const auto &rp = ctx.get_render_parameters();
+	std::vector<std::pair<float, unsigned>> order;
+	if (scene_decals)
+	{
+		const Frustum &frustum = ctx.get_visibility_frustum();
+		const AABB unit(vec3(-0.5f), vec3(0.5f));
+		for (unsigned i = 0; i < (unsigned)scene_decals->size(); i++)
+		{
+			const AABB world = unit.transform((*scene_decals)[i]);
+			if (frustum_culling && !frustum.intersects_fast(world))
+				continue;
+			order.emplace_back(dot(rp.camera_front, world.get_center()), i);
+		}
+		std::stable_sort(order.begin(), order.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+	}
+	if (order.size() > MaxDecalsBindless)
+		order.resize(MaxDecalsBindless);
+	for (auto &o : order)
+	{
+		const mat_affine &t = (*scene_decals)[o.second];
+		const mat4 world(vec4(t[0].x, t[1].x, t[2].x, 0.0f), vec4(t[0].y, t[1].y, t[2].y, 0.0f), vec4(t[0].z, t[1].z, t[2].z, 0.0f),
+		                 vec4(t[0].w, t[1].w, t[2].w, 1.0f)); // mat_affine::to_mat4
+		decal_mvps.push_back(rp.view_projection * world);
+		decal_index_range.push_back(compute_uint_range(decal_z_range(ctx, t)));
+	}
+	// the Z-range kernel still runs with one empty entry so that the range buffer is cleared (clusterer.cpp:1384-1386)
+	if (decal_index_range.empty())
+		decal_index_range.push_back(uvec2(~0u, 0u));
+}
+
+// update_bindless_mask_buffer_decal_gpu + update_bindless_range_buffer_decal_gpu (clusterer.cpp:1570-1572)
+void LightClusterer::build_decal_clusters_gpu(Vulkan::CommandBuffer &cmd)
+{
+	if (!enable_volumetric_decals || !decal_scratch_buffer || !bitmask_decal_buffer || !range_decal_buffer)
+		return;
+	const size_t n = decal_mvps.size();
+	auto *base = decal_scratch_buffer->get<uint8_t>();
+	auto *d_mvps = reinterpret_cast<float *>(base);
+	auto *d_boxes = reinterpret_cast<float *>(base + MaxDecalsBindless * sizeof(mat4));
+	auto *d_ranges = reinterpret_cast<uint32_t *>(base + MaxDecalsBindless * (sizeof(mat4) + sizeof(vec4)));
+	auto stream = reinterpret_cast<cudaStream_t>(cmd.get_stream());
+	// pageable copies: the runtime stages them before returning, so the vectors may change right after
+	if (n)
+		Vulkan::cuda_ok(cudaMemcpyAsync(d_mvps, decal_mvps.data(), n * sizeof(mat4), cudaMemcpyHostToDevice, stream), "decal upload");
+	Vulkan::cuda_ok(cudaMemcpyAsync(d_ranges, decal_index_range.data(), decal_index_range.size() * sizeof(uvec2), cudaMemcpyHostToDevice, stream),
+	                "decal range upload");
+	cmd.check(grb_cluster_decal_binning(&parameters, d_mvps, (int32_t)n, d_boxes, bitmask_decal_buffer->get<uint32_t>(), cmd.get_stream_handle()),
+	          "grb_cluster_decal_binning");
+	GrbClusterBuffers buf = {};
+	buf.z_ranges = d_ranges;
+	buf.cluster_range = range_decal_buffer->get<uint32_t>();
+	buf.resolution_z = (int32_t)resolution_z;
+	cmd.check(grb_cluster_z_range(&buf, (int32_t)decal_index_range.size(), cmd.get_stream_handle()), "grb_cluster_z_range(decals)");
 }
 
 // renderer/threaded_scene.cpp:137-150 (front-to-back order), clusterer.cpp:656-698 (scan),

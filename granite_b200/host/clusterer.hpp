@@ -59,6 +59,24 @@ public:
 	// The C-ABI view of the uploaded shadow data (null members while shadows are disabled).
 	GrbLightShadows get_light_shadows() const;
 	const std::vector<mat4> &get_shadow_transforms() const { return shadow_transforms; }
+	// Volumetric decals (clusterer.cpp:148-156, 1348-1461): binned over the same tile grid and Z slices as the lights, into
+	// "cluster-bitmask-decal" / "cluster-range-decal".  The scene's decals are their world transforms (unit cubes in decal
+	// space; replaces Scene::gather_visible_volumetric_decals): culled against the frustum, sorted by view depth of their
+	// centre, at most MaxDecalsBindless.  Sampling the decal textures is the material pass's job, outside the path.
+	enum
+	{
+		MaxDecalsBindless = 4096
+	};
+	void set_enable_volumetric_decals(bool enable) { enable_volumetric_decals = enable; }
+	bool clusterer_has_volumetric_decals() const { return enable_volumetric_decals; }
+	void set_scene_decals(const std::vector<mat_affine> *world_transforms) { scene_decals = world_transforms; }
+	const Vulkan::Buffer *get_cluster_bitmask_decal_buffer() const { return bitmask_decal_buffer; }
+	const Vulkan::Buffer *get_cluster_range_decal_buffer() const { return range_decal_buffer; }
+	unsigned get_active_decal_count() const { return (unsigned)decal_mvps.size(); }
+	// CPU copies of what is uploaded (parity tests): view_projection * world per visible decal, and the Z-slice ranges
+	const std::vector<mat4> &get_decal_mvps() const { return decal_mvps; }
+	const std::vector<uvec2> &get_decal_z_ranges() const { return decal_index_range; }
+	static vec2 decal_z_range(const RenderContext &context, const mat_affine &transform);
 	void set_max_spot_lights(unsigned) {}
 	void set_max_point_lights(unsigned) {}
 
@@ -109,6 +127,14 @@ private:
 	unsigned shadow_resolution = 512;
 	std::vector<mat4> shadow_transforms;
 	std::vector<const void *> shadow_maps;
+	bool enable_volumetric_decals = false;
+	const std::vector<mat_affine> *scene_decals = nullptr;
+	std::vector<mat4> decal_mvps;
+	std::vector<uvec2> decal_index_range;
+	RenderBufferResource *res_bitmask_decal = nullptr, *res_range_decal = nullptr, *res_decal_scratch = nullptr;
+	const Vulkan::Buffer *bitmask_decal_buffer = nullptr, *range_decal_buffer = nullptr, *decal_scratch_buffer = nullptr;
+	void refresh_decals(const RenderContext &ctx);
+	void build_decal_clusters_gpu(Vulkan::CommandBuffer &cmd);
 	std::vector<unsigned> sort_order;
 	std::vector<float> sort_keys;
 	// pinned staging copy of {lights, model, type_mask, z ranges} for the async upload

@@ -16,6 +16,7 @@ public:
 	AABB(vec3 minimum_, vec3 maximum_) : minimum(minimum_), maximum(maximum_) {}
 	const vec3 &get_minimum() const { return minimum; }
 	const vec3 &get_maximum() const { return maximum; }
+	vec3 get_center() const { return minimum + (maximum - minimum) * 0.5f; } // math/aabb.hpp
 	// math/simd.hpp:386-419 SIMD::transform_aabb(output, aabb, mat_affine)
 	AABB transform(const mat_affine &m) const;
 

@@ -61,6 +61,7 @@ struct GrbhViewer
 
 	std::vector<std::unique_ptr<PositionalLight>> light_storage;
 	PositionalLightList scene_lights;
+	std::vector<mat_affine> scene_decals;
 
 	mat4 projection = mat4(1.0f), view = mat4(1.0f);
 	bool baked = false;
@@ -132,6 +133,8 @@ void GrbhViewer::bake_render_graph()
 	cluster.set_scene_lights(&scene_lights);
 	cluster.set_base_render_context(&context);
 	cluster.set_async_compute(getenv("GRB_NO_ASYNC_CLUSTER") == nullptr);
+	cluster.set_enable_volumetric_decals(config.volumetric_decals != 0);
+	cluster.set_scene_decals(&scene_decals);
 	cluster.set_enable_shadows(config.clustered_lights_shadows != 0);
 	cluster.set_shadow_resolution(config.clustered_lights_shadow_resolution > 0 ? (unsigned)config.clustered_lights_shadow_resolution : 512u);
 	if (bands.size() > 1)
@@ -885,6 +888,44 @@ extern "C" int32_t grbh_viewer_get_light_prep(GrbhViewer *v, GrbPositionalLight 
 	if (z_ranges)
 		std::memcpy(z_ranges, v->cluster.get_z_ranges().data(), sizeof(uint32_t) * 2 * v->cluster.get_z_ranges().size());
 	return n;
+}
+
+extern "C" int32_t grbh_viewer_set_decals(GrbhViewer *v, const float *world_rows12, int32_t count)
+{
+	if (!v || count < 0 || (count > 0 && !world_rows12))
+		return fail("grbh_viewer_set_decals: bad arguments");
+	GRBH_TRY
+	v->scene_decals.clear();
+	for (int i = 0; i < count; i++)
+	{
+		const float *r = world_rows12 + 12 * (size_t)i;
+		v->scene_decals.push_back(mat_affine(vec4(r[0], r[1], r[2], r[3]), vec4(r[4], r[5], r[6], r[7]), vec4(r[8], r[9], r[10], r[11])));
+	}
+	return 0;
+	GRBH_CATCH
+}
+
+extern "C" int32_t grbh_viewer_get_decal_prep(GrbhViewer *v, float *mvps16, uint32_t *z_ranges2, int32_t capacity)
+{
+	if (!v)
+		return fail("null viewer");
+	GRBH_TRY
+	if (v->config.cluster_res[0])
+		v->cluster.set_resolution((unsigned)v->config.cluster_res[0], (unsigned)v->config.cluster_res[1], (unsigned)v->config.cluster_res[2]);
+	v->cluster.set_scene_lights(&v->scene_lights);
+	v->cluster.set_scene_decals(&v->scene_decals);
+	v->cluster.set_enable_volumetric_decals(true);
+	v->cluster.refresh(v->context);
+	v->cluster.set_enable_volumetric_decals(v->config.volumetric_decals != 0);
+	const int n = (int)v->cluster.get_active_decal_count();
+	if (n > capacity)
+		return fail("grbh_viewer_get_decal_prep: capacity too small");
+	if (mvps16 && n)
+		std::memcpy(mvps16, v->cluster.get_decal_mvps().data(), 64 * (size_t)n);
+	if (z_ranges2 && n)
+		std::memcpy(z_ranges2, v->cluster.get_decal_z_ranges().data(), 8 * (size_t)n);
+	return n;
+	GRBH_CATCH
 }
 
 extern "C" int32_t grbh_viewer_get_render_size(GrbhViewer *v, int32_t *width, int32_t *height)

@@ -24,7 +24,7 @@ class GrbhViewerConfig(C.Structure):
                 ("timestamps", C.c_int32), ("cuda_stream", C.c_void_p), ("pipelined_io", C.c_int32),
                 ("hdr10_output", C.c_int32), ("hdr10_max_content_light_level", C.c_float),
                 ("clustered_lights_shadows", C.c_int32), ("clustered_lights_shadow_resolution", C.c_int32),
-                ("resolution_scale", C.c_float), ("resolution_scale_sharpen", C.c_int32), ("render_target_fp16", C.c_int32)]
+                ("resolution_scale", C.c_float), ("resolution_scale_sharpen", C.c_int32), ("render_target_fp16", C.c_int32), ("volumetric_decals", C.c_int32)]
 
 
 class GrbhLights(C.Structure):
@@ -233,7 +233,7 @@ class Viewer:
     def __init__(self, width, height, post_aa=AA_NONE, hdr_bloom=True, dynamic_exposure=True, cuda_device=0,
                  cluster_res=(128, 64, 4096), timestamps=False, stream=None, pipelined_io=False, hdr10_output=False, hdr10_max_cll=1000.0,
                  light_shadows=False, shadow_resolution=512, resolution_scale=0.0, resolution_scale_sharpen=True,
-                 render_target_fp16=False):
+                 render_target_fp16=False, volumetric_decals=False):
         cfg = GrbhViewerConfig()
         cfg.cuda_device = cuda_device
         cfg.width, cfg.height = width, height
@@ -250,6 +250,7 @@ class Viewer:
         cfg.clustered_lights_shadow_resolution = int(shadow_resolution)
         cfg.resolution_scale = float(resolution_scale)  # < 1: width x height is the display size, FSR 1 upscales to it
         cfg.resolution_scale_sharpen = int(resolution_scale_sharpen)
+        cfg.volumetric_decals = int(volumetric_decals)
         cfg.render_target_fp16 = int(render_target_fp16)  # emissive / HDR-main as RGBA16F: host_gbuffer's emissive is (H, W, 4) uint16
         self.width, self.height = width, height
         self._h = C.c_void_p()
@@ -262,6 +263,18 @@ class Viewer:
         assert a.size == 160 * 560 * 2 and s_.size == 64 * 16
         _check(lib().grbh_viewer_set_smaa_lookup_textures(self._h, a.ctypes.data_as(C.c_void_p), s_.ctypes.data_as(C.c_void_p)),
                "grbh_viewer_set_smaa_lookup_textures")
+
+    def set_decals(self, world_rows):
+        """(n, 12) float32: world transforms (mat_affine rows) of the scene's volumetric decals (unit cubes in decal space)."""
+        w = np.ascontiguousarray(world_rows, np.float32).reshape(-1, 12)
+        self._keep.append(w)
+        _check(lib().grbh_viewer_set_decals(self._h, w.ctypes.data_as(C.c_void_p), len(w)), "grbh_viewer_set_decals")
+
+    def decal_prep(self, capacity=4096):
+        """Host prep of the decal binning: ((n, 16) f32 mvps, (n, 2) u32 Z-slice ranges) of the visible decals, front to back."""
+        m, z = np.zeros((capacity, 16), np.float32), np.zeros((capacity, 2), np.uint32)
+        n = _check(lib().grbh_viewer_get_decal_prep(self._h, m.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), capacity), "grbh_viewer_get_decal_prep")
+        return m[:n].copy(), z[:n].copy()
 
     def render_size(self):
         """(width, height) of the G-buffer the viewer expects (smaller than the display size when resolution_scale < 1)."""

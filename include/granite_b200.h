@@ -160,6 +160,15 @@ int32_t grb_cluster_z_range(const GrbClusterBuffers *buf, int32_t num_ranges, vo
 int32_t grb_cluster_build(const GrbCamera *cam, const GrbClusterParameters *params,
                           const GrbClusterBuffers *buf, void *stream);
 
+/* Volumetric-decal binning over the clusterer's tile grid: LightClusterer::update_bindless_mask_buffer_decal_gpu
+ * (clusterer.cpp:1391-1461) + clusterer_bindless_binning_decal.comp.  mvps: num_decals x mat4 (column-major, device) =
+ * view_projection * decal world transform (clusterer.cpp:1406-1410); boxes: scratch, num_decals x 4 floats (the decals'
+ * screen-space bounding boxes); bitmask: resolution_x * resolution_y * ((num_decals + 31) / 32) words,
+ * [(tile_y * resolution_x + tile_x) * num_decals_32 + decal / 32].  The decals' Z-slice ranges go through
+ * grb_cluster_z_range like the lights' (clusterer.cpp:1371-1389).  num_decals == 0: nothing is launched. */
+int32_t grb_cluster_decal_binning(const GrbClusterParameters *params, const float *mvps, int32_t num_decals, float *boxes, uint32_t *bitmask,
+                                  void *stream);
+
 /* ---- deferred lighting: replaces DeferredLightRenderer::render_light
  * (renderer/renderer.cpp:1004-1156): directional.frag + clustering.frag, both additively
  * blended into HDR-main, sky (depth == 0) skipped. ---- */

@@ -67,6 +67,8 @@ typedef struct GrbhViewerConfig
 	int32_t render_target_fp16;       /* "renderTargetFp16" (:235-236, 880-884): emissive / HDR-main are R16G16B16A16_SFLOAT (8 bytes per
 	                                   * texel -- GrbhHostGBuffer::emissive then points at RGBA16F texels); lighting, bloom threshold,
 	                                   * tonemap and TAA read / write that format (TAA's own output stays B10G11R11).  Not with HDR10. */
+	int32_t volumetric_decals;        /* LightClusterer::set_enable_volumetric_decals (clusterer.cpp:153-156): the decals of
+	                                   * grbh_viewer_set_decals are binned into "cluster-bitmask-decal" / "cluster-range-decal" */
 } GrbhViewerConfig;
 
 /* Raw light list as the application owns it (before the clusterer sorts/packs it). */
@@ -170,6 +172,11 @@ int32_t grbh_viewer_get_camera(GrbhViewer *viewer, GrbCamera *out, float *projec
  * (renderer/post/temporal.cpp:239-243: unjittered history matrices). */
 int32_t grbh_viewer_get_taa_reprojection(GrbhViewer *viewer, float *out16);
 /* Names of the baked passes, '\n' separated. Returns the length needed. */
+/* The scene's volumetric decals: `count` world transforms, 12 floats each (mat_affine rows) of unit cubes in decal space. */
+int32_t grbh_viewer_set_decals(GrbhViewer *viewer, const float *world_rows12, int32_t count);
+/* Host preparation of the decal binning (no GPU work): the visible decals front to back -- view_projection * world
+ * (capacity x 16 floats) and their Z-slice ranges (capacity x 2 words).  Returns the count. */
+int32_t grbh_viewer_get_decal_prep(GrbhViewer *viewer, float *mvps16, uint32_t *z_ranges2, int32_t capacity);
 /* Size of the G-buffer the viewer expects (= width x height unless resolution_scale < 1). */
 int32_t grbh_viewer_get_render_size(GrbhViewer *viewer, int32_t *width, int32_t *height);
 int32_t grbh_viewer_get_pass_names(GrbhViewer *viewer, char *buffer, int32_t capacity);

@@ -103,6 +103,13 @@ void orc_binning(const orc_cluster_params_t *p, const uint32_t *type_mask, const
 /* K4 clusterer_bindless_z_range.comp:20-51. out: res_z uvec2. */
 void orc_z_range(const uint32_t *z_ranges, int num_ranges, int res_z, uint32_t *cluster_range);
 
+/* ---- volumetric-decal binning: clusterer_bindless_binning_decal.comp, SUBGROUPS = 0 ---- */
+void orc_decal_mvp(const float *view_projection16, const float *world_rows12, float *out16);      /* clusterer.cpp:1408-1409 */
+void orc_decal_z_range(const orc_camera_t *cam, const float *world_rows12, float *lo_hi2);       /* clusterer.cpp:1348-1369 */
+void orc_decal_screen_bb(const float *mvp16, float *bb4);                                         /* .comp:39-70 */
+/* bitmask: res_x * res_y * ((num_decals + 31) / 32) words */
+void orc_decal_binning(int res_x, int res_y, const float *inv_resolution_xy2, int num_decals, const float *mvps16, uint32_t *bitmask);
+
 /* ---- deferred lighting (K6 directional + K5 clustered, two additive blends) ---- */
 typedef struct
 {

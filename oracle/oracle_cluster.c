@@ -4,6 +4,8 @@
  * (bitmask, ranges) are the bit-exact contract.  See oracle_math.h for arithmetic rules.
  */
 #include "oracle.h"
+
+#include <stdlib.h>
 #include "oracle_math.h"
 
 /* ---- K1: clusterer_bindless_spot_transform.comp:33-73 ---- */
@@ -440,4 +442,78 @@ void orc_z_range(const uint32_t *z_ranges, int num_ranges, int res_z, uint32_t *
 		cluster_range[2 * zi] = z_lo;
 		cluster_range[2 * zi + 1] = z_hi;
 	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Volumetric-decal binning: clusterer_bindless_binning_decal.comp (SUBGROUPS = 0 path, :118-141) over the same
+ * (resolution_x x resolution_y) tile grid as the lights, one bit per decal and tile.  Host side
+ * LightClusterer::update_bindless_mask_buffer_decal_gpu (clusterer.cpp:1391-1461): mvp[i] = view_projection * world.
+ * --------------------------------------------------------------------------------------------- */
+/* compute_decal_screen_bb, :39-70.  mat4 * vec4 as the generated reference code evaluates it (GLM: pairwise);
+ * min / max keep the accumulated value when the projected coordinate is NaN (GLM's (y < x) ? y : x). */
+void orc_decal_screen_bb(const float *m, float *bb4)
+{
+	float bb[4] = { 1.0f, 1.0f, -1.0f, -1.0f };
+	float lo_w = 1.0f, hi_w = -1.0f;
+	float corner[8][4];
+	for (int r = 0; r < 4; r++)
+		corner[0][r] = (m[r] * -0.5f + m[4 + r] * -0.5f) + (m[8 + r] * -0.5f + m[12 + r] * 1.0f);
+	for (int r = 0; r < 4; r++)
+	{
+		corner[1][r] = corner[0][r] + m[r];
+		corner[2][r] = corner[0][r] + m[4 + r];
+		corner[3][r] = corner[1][r] + m[4 + r];
+		corner[4][r] = corner[0][r] + m[8 + r];
+		corner[5][r] = corner[1][r] + m[8 + r];
+		corner[6][r] = corner[2][r] + m[8 + r];
+		corner[7][r] = corner[3][r] + m[8 + r];
+	}
+	for (int i = 0; i < 8; i++)
+	{
+		const float w = corner[i][3];
+		lo_w = w < lo_w ? w : lo_w;
+		hi_w = hi_w < w ? w : hi_w;
+		const float px = corner[i][0] / w, py = corner[i][1] / w;
+		bb[0] = px < bb[0] ? px : bb[0];
+		bb[1] = py < bb[1] ? py : bb[1];
+		bb[2] = bb[2] < px ? px : bb[2];
+		bb[3] = bb[3] < py ? py : bb[3];
+	}
+	if (hi_w <= 0.0f)
+		bb[0] = bb[1] = bb[2] = bb[3] = -10.0f;
+	else if (lo_w <= 0.0f)
+	{
+		bb[0] = bb[1] = -1.0f;
+		bb[2] = bb[3] = 1.0f;
+	}
+	for (int i = 0; i < 4; i++)
+		bb4[i] = bb[i];
+}
+
+/* main(), SUBGROUPS = 0: bitmask[(y * res_x + x) * num_decals_32 + chunk], bit = decal & 31 */
+void orc_decal_binning(int res_x, int res_y, const float *inv_resolution_xy2, int num_decals, const float *mvps16, uint32_t *bitmask)
+{
+	const int n32 = (num_decals + 31) / 32;
+	const float stride_x = 2.0f * inv_resolution_xy2[0], stride_y = 2.0f * inv_resolution_xy2[1];
+	float *bbs = (float *)malloc(sizeof(float) * 4 * (size_t)(num_decals > 0 ? num_decals : 1));
+	for (int i = 0; i < num_decals; i++)
+		orc_decal_screen_bb(mvps16 + 16 * (size_t)i, bbs + 4 * (size_t)i);
+#pragma omp parallel for schedule(static)
+	for (int y = 0; y < res_y; y++)
+		for (int x = 0; x < res_x; x++)
+		{
+			const float u = 2.0f * (float)x * inv_resolution_xy2[0] - 1.0f, v = 2.0f * (float)y * inv_resolution_xy2[1] - 1.0f;
+			for (int c = 0; c < n32; c++)
+			{
+				uint32_t mask = 0u;
+				for (int b = 0; b < 32 && 32 * c + b < num_decals; b++)
+				{
+					const float *bb = bbs + 4 * (size_t)(32 * c + b);
+					if (u + stride_x > bb[0] && v + stride_y > bb[1] && u < bb[2] && v < bb[3]) /* test_decal, :28-31 */
+						mask |= 1u << b;
+				}
+				bitmask[((size_t)y * res_x + x) * n32 + c] = mask;
+			}
+		}
+	free(bbs);
 }

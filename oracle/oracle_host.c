@@ -667,3 +667,42 @@ void orc_point_shadow_transform(const orc_light_t *light, float *out16)
 		out16[i] = 0.0f;
 	out16[0] = proj[10]; out16[1] = proj[11]; out16[2] = proj[14]; out16[3] = proj[15];
 }
+
+/* ---- volumetric decals: host side of the decal binning (clusterer.cpp:1348-1412) ---- */
+/* mvp = view_projection * to_mat4(world) (clusterer.cpp:1408-1409); world: 3 rows of 4 (mat_affine) */
+void orc_decal_mvp(const float *view_projection16, const float *world_rows12, float *out16)
+{
+	float w[16];
+	for (int c = 0; c < 4; c++)
+	{
+		w[4 * c + 0] = world_rows12[c];
+		w[4 * c + 1] = world_rows12[4 + c];
+		w[4 * c + 2] = world_rows12[8 + c];
+		w[4 * c + 3] = c == 3 ? 1.0f : 0.0f;
+	}
+	orc_mat4_mul(view_projection16, w, out16);
+}
+
+/* decal_z_range (clusterer.cpp:1348-1369): view-depth range of the unit cube's eight corners, corner i of an AABB =
+ * (i & 1 ? hi : lo, i & 2 ? hi : lo, i & 4 ? hi : lo) (math/aabb.cpp get_corner) */
+void orc_decal_z_range(const orc_camera_t *cam, const float *world_rows12, float *lo_hi2)
+{
+	float lo = INFINITY, hi = -INFINITY;
+	for (int i = 0; i < 8; i++)
+	{
+		const float t[4] = { (i & 1) ? 0.5f : -0.5f, (i & 2) ? 0.5f : -0.5f, (i & 4) ? 0.5f : -0.5f, 1.0f };
+		float wpos[3];
+		for (int r = 0; r < 3; r++)
+		{
+			const float *row = world_rows12 + 4 * r;
+			/* SIMD::mul(vec4, mat_affine, vec4) (math/simd.hpp:107-119): one DPPS per row = (p0 + p1) + (p2 + p3) */
+			wpos[r] = (row[0] * t[0] + row[1] * t[1]) + (row[2] * t[2] + row[3] * t[3]);
+		}
+		const float z = (wpos[0] - cam->camera_position[0]) * cam->camera_front[0] + (wpos[1] - cam->camera_position[1]) * cam->camera_front[1] +
+		                (wpos[2] - cam->camera_position[2]) * cam->camera_front[2];
+		lo = z < lo ? z : lo;
+		hi = z > hi ? z : hi;
+	}
+	lo_hi2[0] = lo;
+	lo_hi2[1] = hi;
+}

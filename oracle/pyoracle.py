@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libgranite_refmath.so")
 
 
-_REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for k in (1, 2, 3, 4)]
+_REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for k in (1, 2, 3, 4, 5)]
 # post-processing shaders K7-K13 (ref_post_shim.cpp); ids as in oracle/Makefile POST_IDS
 _REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173, 24, 25, 26)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
@@ -122,7 +122,7 @@ def ref_kernels():
     (oracle/_ref/libgranite_ref_k*.so, see ref_shader_shim.cpp), or None when they were not built."""
     global _ref_kernels
     if _ref_kernels is None and all(os.path.exists(p) for p in _REF_KERNEL_PATHS):
-        _ref_kernels = {k: C.CDLL(p) for k, p in zip((1, 2, 3, 4), _REF_KERNEL_PATHS)}
+        _ref_kernels = {k: C.CDLL(p) for k, p in zip((1, 2, 3, 4, 5), _REF_KERNEL_PATHS)}
     return _ref_kernels
 
 
@@ -810,4 +810,43 @@ def ref_fsr_sharpen(img, sharpness_stops=0.5, srgb=True, rows=None):
     out = np.zeros((h, w), np.uint32)
     y0, y1 = rows if rows else (0, h)
     k[26].refk26_fsr_sharpen(_p(_c(img, np.uint32)), w, h, _p(fsr_rcas_constants(sharpness_stops)), int(srgb), _p(out), y0, y1)
+    return out
+
+
+# ---------------- volumetric-decal binning (clusterer.cpp:1348-1461) ----------------
+def decal_mvps(cam: Camera, world_rows):
+    """world_rows: (n, 12) f32 mat_affine rows -> (n, 16) f32 view_projection * world."""
+    w = _c(world_rows, np.float32).reshape(-1, 12)
+    out = np.zeros((len(w), 16), np.float32)
+    vp = _farr(list(cam.view_projection))
+    for i in range(len(w)):
+        lib().orc_decal_mvp(_p(vp), _p(w[i]), _p(out[i]))
+    return out
+
+
+def decal_z_ranges(cam: Camera, world_rows):
+    w = _c(world_rows, np.float32).reshape(-1, 12)
+    out = np.zeros((len(w), 2), np.float32)
+    for i in range(len(w)):
+        lib().orc_decal_z_range(C.byref(cam), _p(w[i]), _p(out[i]))
+    return out
+
+
+def decal_binning(res_xy, mvps):
+    rx, ry = res_xy
+    m = _c(mvps, np.float32).reshape(-1, 16)
+    n = len(m)
+    inv = np.array([1.0 / rx, 1.0 / ry], np.float32)
+    out = np.zeros((ry, rx, max((n + 31) // 32, 1)), np.uint32)
+    lib().orc_decal_binning(rx, ry, _p(inv), n, _p(m), _p(out))
+    return out
+
+
+def ref_decal_binning(res_xy, mvps):
+    """The reference's clusterer_bindless_binning_decal.comp (SUBGROUPS=0) on the CPU."""
+    rx, ry = res_xy
+    m = _c(mvps, np.float32).reshape(-1, 16)
+    n = len(m)
+    out = np.zeros((ry, rx, max((n + 31) // 32, 1)), np.uint32)
+    ref_kernels()[5].refk5_decal_binning(_p(np.array([rx, ry], np.int32)), _p(np.array([1.0 / rx, 1.0 / ry], np.float32)), n, _p(m), _p(out))
     return out

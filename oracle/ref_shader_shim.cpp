@@ -80,7 +80,7 @@ struct Runner
 	}
 };
 
-#if KERNEL != 4
+#if KERNEL != 4 && KERNEL != 5
 // ClustererBindlessTransforms (assets/shaders/lights/clusterer_data.h:46-53) filled from the packed
 // host arrays: 48-byte light records, mat_affine rows, type mask.
 std::vector<unsigned char> make_transforms(const void *lights48, const float *model_rows12, const uint32_t *type_mask, int n)
@@ -192,6 +192,23 @@ void refk3_binning(const float *clip_scale4, const int32_t *resolution_xy2, cons
 				id = glm::uvec3((unsigned)c, (unsigned)tx, (unsigned)ty);
 				r.itf->invoke(r.sh);
 			}
+}
+#elif KERNEL == 5
+// clusterer_bindless_binning_decal.comp, SUBGROUPS=0 path: dispatch (num_decals_32, resolution_x, resolution_y), one
+// 32-thread workgroup per (chunk, tile) (clusterer.cpp:1454-1457).  mvps16: num_decals column-major mat4.
+void refk5_decal_binning(const int32_t *resolution_xy2, const float *inv_resolution_xy2, int num_decals, const float *mvps16, uint32_t *out_bitmask)
+{
+	Sh::Resources::ClustererParameters ubo;
+	std::memset(&ubo, 0, sizeof(ubo));
+	ubo.parameters.resolution_xy = glm::ivec2(resolution_xy2[0], resolution_xy2[1]);
+	ubo.parameters.inv_resolution_xy = glm::vec2(inv_resolution_xy2[0], inv_resolution_xy2[1]);
+	ubo.parameters.num_decals = num_decals;
+	ubo.parameters.num_decals_32 = (num_decals + 31) / 32;
+	Runner r;
+	r.resource(2, 0, const_cast<float *>(mvps16));
+	r.resource(1, 0, &ubo);
+	r.resource(0, 0, out_bitmask);
+	r.dispatch((unsigned)((num_decals + 31) / 32), (unsigned)resolution_xy2[0], (unsigned)resolution_xy2[1]);
 }
 #elif KERNEL == 4
 // naive form = the specification; dispatch res_z / 64 (clusterer.cpp:1286-1300)
