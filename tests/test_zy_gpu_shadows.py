@@ -91,10 +91,16 @@ def test_viewer_frame_with_shadowed_lights(cuda, oracle):
     v.set_directional(scene.dir_color, scene.dir_direction)
     v.set_lights(lights)
     cam, prep = common.build_case_for_viewer(oracle, v, scene, lights)
-    assert prep.n == len(lights.color), "every light of this case is visible, so input order == cluster order"
+    # the synthetic lights come sorted front to back, so cluster order = input order minus the culled ones
+    keep = oracle.visible_lights(cam, lights)
+    assert int(keep.sum()) == prep.n
     maps = common.make_shadow_maps(prep, res)
     held = [None if m is None else torch.from_numpy(np.ascontiguousarray(m).view(np.int16)).cuda() for m in maps]
-    v.set_light_shadow_maps([0 if t is None else t.data_ptr() for t in held])
+    by_input, k = [], 0
+    for visible in keep:
+        by_input.append(0 if (not visible or held[k] is None) else held[k].data_ptr())
+        k += 1 if visible else 0
+    v.set_light_shadow_maps(by_input)
     v.bake()
     keep = [np.ascontiguousarray(a) for a in (scene.albedo, scene.normal, scene.pbr, scene.depth, scene.emissive)]
     v.render_frame(viewer.Viewer.host_gbuffer(*keep))
