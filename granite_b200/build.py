@@ -25,6 +25,7 @@ UNITS = [
     ("grb_smaa.cu", ["-fmad=false"]),
     ("grb_fsr.cu", ["-fmad=false"]),
     ("grb_decal.cu", ["-fmad=false"]),
+    ("grb_fog.cu", ["-fmad=false"]),
     ("grb_lighting.cu", []),
 ]
 

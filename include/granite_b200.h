@@ -169,6 +169,13 @@ int32_t grb_cluster_build(const GrbCamera *cam, const GrbClusterParameters *para
 int32_t grb_cluster_decal_binning(const GrbClusterParameters *params, const float *mvps, int32_t num_decals, float *boxes, uint32_t *bitmask,
                                   void *stream);
 
+/* Volumetric fog, accumulation pass: VolumetricFog::build_fog (renderer/lights/volumetric_fog.cpp:236-254) + fog_accumulate.comp.
+ * light_density / fog: device pointers to R16G16B16A16_SFLOAT volumes of width x height x depth texels (x fastest, then y, then
+ * slices), distinct and 8-byte aligned; light_density = (in-scattered light rgb, optical depth) per froxel, as the reference's
+ * "volumetric-fog-inscatter" image holds it; fog = (light accumulated front to back, transmittance).  The first pass
+ * (fog_light_density.comp) is not built: the caller supplies the density volume. */
+int32_t grb_fog_accumulate(const void *light_density, int32_t width, int32_t height, int32_t depth, void *fog, void *stream);
+
 /* ---- deferred lighting: replaces DeferredLightRenderer::render_light
  * (renderer/renderer.cpp:1004-1156): directional.frag + clustering.frag, both additively
  * blended into HDR-main, sky (depth == 0) skipped. ---- */

@@ -235,4 +235,8 @@ void orc_fsr_easu(const uint32_t *src_unorm, int w_in, int h_in, const float *co
 /* sharpen.frag: srgb = 1 reads through an sRGB view (linear values) and stores into an sRGB target */
 void orc_fsr_rcas(const uint32_t *src, int w, int h, const float *con4, uint32_t *dst, int srgb, int y0, int y1);
 
+/* ---- volumetric fog, accumulation pass: fog_accumulate.comp + VolumetricFog::build_fog (volumetric_fog.cpp:236-254).
+ * light / fog: R16G16B16A16_SFLOAT volumes of w x h x d texels, x fastest ---- */
+void orc_fog_accumulate(const uint16_t *light_rgba16f, int w, int h, int d, uint16_t *fog_rgba16f);
+
 #endif

@@ -19,7 +19,7 @@ _REF_PATH = os.path.join(_HERE, "_ref", "libgranite_refmath.so")
 
 _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for k in (1, 2, 3, 4, 5)]
 # post-processing shaders K7-K13 (ref_post_shim.cpp); ids as in oracle/Makefile POST_IDS
-_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173, 24, 25, 26)
+_REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173, 24, 25, 26, 27)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
 # deferred-lighting fragment shaders K5 (clustering.frag) and K6 (directional.frag), ref_light_shim.cpp
 _REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6, 7)}
@@ -849,4 +849,21 @@ def ref_decal_binning(res_xy, mvps):
     n = len(m)
     out = np.zeros((ry, rx, max((n + 31) // 32, 1)), np.uint32)
     ref_kernels()[5].refk5_decal_binning(_p(np.array([rx, ry], np.int32)), _p(np.array([1.0 / rx, 1.0 / ry], np.float32)), n, _p(m), _p(out))
+    return out
+
+
+# ---------------- volumetric fog, accumulation pass (volumetric_fog.cpp:236-254) ----------------
+def fog_accumulate(light):
+    """light: (d, h, w, 4) uint16 RGBA16F froxel grid (rgb in-scattered light, a optical depth) -> fog, same shape."""
+    d, h, w = light.shape[:3]
+    out = np.zeros((d, h, w, 4), np.uint16)
+    lib().orc_fog_accumulate(_p(_c(light, np.uint16)), w, h, d, _p(out))
+    return out
+
+
+def ref_fog_accumulate(light):
+    """The reference's fog_accumulate.comp on the CPU (oracle/_ref/libgranite_ref_p27)."""
+    d, h, w = light.shape[:3]
+    out = np.zeros((d, h, w, 4), np.uint16)
+    ref_post_kernels()[27].refk27_fog_accumulate(_p(_c(light, np.uint16)), w, h, d, _p(out))
     return out

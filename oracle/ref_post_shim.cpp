@@ -190,6 +190,38 @@ inline glm::vec4 textureGather(const sampler2D &s, const glm::vec2 &uv, int comp
 inline glm::ivec2 textureSize(const sampler2D &s, int) { return glm::ivec2(s.w, s.h); }
 typedef sampler2D texture2D; // separate images are only ever texelFetch'ed
 
+// RGBA16F volumes (fog_accumulate.comp): a NearestClamp sampler3D -- nearest texel of the normalised coordinate, integer
+// offset, clamp to edge -- and a storage image3D
+struct sampler3D
+{
+	const uint16_t *data = nullptr;
+	int w = 0, h = 0, d = 0;
+};
+inline glm::vec4 textureLodOffset(const sampler3D &s, const glm::vec3 &uvw, float, const glm::ivec3 &off)
+{
+	int x = (int)std::floor(uvw.x * (float)s.w) + off.x, y = (int)std::floor(uvw.y * (float)s.h) + off.y, z = (int)std::floor(uvw.z * (float)s.d) + off.z;
+	x = x < 0 ? 0 : (x > s.w - 1 ? s.w - 1 : x);
+	y = y < 0 ? 0 : (y > s.h - 1 ? s.h - 1 : y);
+	z = z < 0 ? 0 : (z > s.d - 1 ? s.d - 1 : z);
+	const uint16_t *t = s.data + 4 * (((size_t)z * s.h + y) * s.w + x);
+	return glm::vec4(orc_f16_to_f32(t[0]), orc_f16_to_f32(t[1]), orc_f16_to_f32(t[2]), orc_f16_to_f32(t[3]));
+}
+struct image3D
+{
+	uint16_t *data = nullptr;
+	int w = 0, h = 0, d = 0;
+};
+inline void imageStore(image3D &im, const glm::ivec3 &p, const glm::vec4 &v)
+{
+	if (p.x < 0 || p.y < 0 || p.z < 0 || p.x >= im.w || p.y >= im.h || p.z >= im.d)
+		return;
+	uint16_t *o = im.data + 4 * (((size_t)p.z * im.h + p.y) * im.w + p.x);
+	o[0] = orc_f32_to_f16(v.x);
+	o[1] = orc_f32_to_f16(v.y);
+	o[2] = orc_f32_to_f16(v.z);
+	o[3] = orc_f32_to_f16(v.w);
+}
+
 // rgba16f storage image
 struct image2D
 {
@@ -743,6 +775,29 @@ void refk26_fsr_sharpen(const uint32_t *in, int w, int h, const float *con4, int
 		};
 		out[(size_t)y * w + x] = q(color.x) | (q(color.y) << 8) | (q(color.z) << 16) | 0xff000000u;
 	}, &uv);
+}
+#elif KERNEL == 27
+// volumetric_fog.cpp:236-254: fog_accumulate.comp, dispatch ceil(w / 8) x ceil(h / 8) x 1, the shader loops over the slices
+void refk27_fog_accumulate(const uint16_t *light, int w, int h, int d, uint16_t *fog)
+{
+	spirv_cross::sampler3D s;
+	s.data = light;
+	s.w = w;
+	s.h = h;
+	s.d = d;
+	spirv_cross::image3D o;
+	o.data = fog;
+	o.w = w;
+	o.h = h;
+	o.d = d;
+	Sh::Resources::Registers reg;
+	reg.inv_resolution = glm::vec3(1.0f / (float)w, 1.0f / (float)h, 1.0f / (float)d);
+	reg.count = glm::uvec3((unsigned)w, (unsigned)h, (unsigned)d);
+	Runner r;
+	r.resource(0, 1, &s);
+	r.resource(0, 0, &o);
+	r.push(&reg, sizeof(reg));
+	r.dispatch((unsigned)((w + 7) / 8), (unsigned)((h + 7) / 8));
 }
 #endif
 }

@@ -114,3 +114,12 @@ def test_post_passes_reject_unknown_hdr_formats(lib):
     assert lib.grb_taa_resolve(C.byref(bad), None, None, None, None, 2, C.byref(oc), C.byref(oh), rows, None) == ERR_FORMAT
     hdr16 = _image(capi, np.zeros((h, w, 4), np.uint16), capi.FORMAT_R16G16B16A16_SFLOAT)
     assert lib.grb_taa_resolve(C.byref(hdr16), None, None, None, None, 3, C.byref(oc), C.byref(oh), rows, None) == ERR_ARG  # quality 0..2
+
+
+def test_fog_accumulate_argument_checks(lib):
+    a, b = np.zeros(64, np.uint16), np.zeros(64, np.uint16)
+    pa, pb = a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)
+    assert lib.grb_fog_accumulate(None, 2, 2, 2, pb, None) == ERR_ARG
+    assert lib.grb_fog_accumulate(pa, 0, 2, 2, pb, None) == ERR_ARG
+    assert lib.grb_fog_accumulate(pa, 2, 2, 2, pa, None) == ERR_ARG and "distinct" in _msg(lib)
+    assert lib.grb_fog_accumulate(C.c_void_p(a.ctypes.data + 2), 2, 2, 2, pb, None) == ERR_ARG  # misaligned
