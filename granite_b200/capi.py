@@ -81,7 +81,7 @@ class GrbGBuffer(C.Structure):
 
 
 class GrbLightShadows(C.Structure):
-    _fields_ = [("transforms", C.c_void_p), ("maps", C.c_void_p), ("resolution", C.c_int32)]
+    _fields_ = [("transforms", C.c_void_p), ("maps", C.c_void_p), ("resolution", C.c_int32), ("pcf_wide", C.c_int32)]
 
 
 ENTRY_POINTS = [

@@ -65,6 +65,7 @@ struct LightingParams
 	const float *shadow_transforms;    // 16 floats per light: ClustererBindlessTransforms::shadow[index]
 	const uint16_t *const *shadow_maps; // per light: D16_UNORM, res^2 (spot) or 6 res^2 (point cube); null = no shadow
 	int shadow_res;
+	int shadow_pcf_wide; // SHADOW_MAP_PCF_KERNEL_WIDE: spot lights use the 6 x 6 kernel
 	// "renderTargetFp16" (scene_viewer_application.cpp:880-884): HDR-main / emissive as R16G16B16A16_SFLOAT; the generic
 	// kernel's HDR16 form reads and writes these instead of hdr / emissive
 	View<uint2> hdr16;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) deferred_lighting_kernel(co
 				{
 					const float *m = p.shadow_transforms + 16 * (size_t)index;
 					falloff *= ((tm >> bit) & 1u) ? point_shadow_falloff(m, -l.x, -l.y, -l.z, map, p.shadow_res)
-					                              : spot_shadow_falloff(m, s.pos.x, s.pos.y, s.pos.z, map, p.shadow_res);
+					                              : spot_shadow_falloff(m, s.pos.x, s.pos.y, s.pos.z, map, p.shadow_res, p.shadow_pcf_wide != 0);
 				}
 			}
 			float NoL;
@@ -1553,6 +1554,7 @@ static int32_t launch_deferred_lighting(const GrbGBuffer *g, const GrbCamera *ca
 	p.shadow_transforms = shadows ? shadows->transforms : nullptr;
 	p.shadow_maps = shadows ? reinterpret_cast<const uint16_t *const *>(shadows->maps) : nullptr;
 	p.shadow_res = shadows ? shadows->resolution : 0;
+	p.shadow_pcf_wide = shadows ? shadows->pcf_wide : 0;
 
 	// two pixels per thread (packed fp32) whenever rows can be addressed as aligned pixel pairs
 	static const bool force_1px = getenv("GRB_LIGHTING_1PX") != nullptr;

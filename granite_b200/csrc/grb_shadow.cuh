@@ -14,6 +14,8 @@
 
 #include <stdint.h>
 
+#define GRB_SHADOW_DEV __device__ __forceinline__
+
 namespace grb
 {
 struct ShadowBilin
@@ -71,6 +73,53 @@ __device__ __forceinline__ float shadow_sample_2d(const uint16_t *map, int res, 
 	const size_t r0 = (size_t)y0 * res, r1 = (size_t)y1 * res;
 	return shadow_mix(shadow_compare(map, r0 + x0, ref), shadow_compare(map, r0 + x1, ref), shadow_compare(map, r1 + x0, ref),
 	                  shadow_compare(map, r1 + x1, ref), q.a, q.b);
+}
+
+// SHADOW_MAP_PCF_KERNEL_WIDE (pcf.h:7-80): 6 x 6 texels from the shader's nine comparison gathers (which sit on texel
+// corners: exact footprints), weights exp2(-0.375 d^2) (1 - d^2 / 9) per axis, normalised; sums in the shader's order
+GRB_SHADOW_DEV float pcf_wide_weight(float p)
+{
+	const float p2 = __fmul_rn(p, p);
+	return __fmul_rn(exp2f(__fmul_rn(p2, -0.375f)), __fsub_rn(1.0f, __fdiv_rn(p2, 9.0f)));
+}
+
+GRB_SHADOW_DEV float shadow_sample_2d_wide(const uint16_t *map, int res, float cx, float cy, float cz, float cw)
+{
+	const float u = __fdiv_rn(cx, cw), v = __fdiv_rn(cy, cw);
+	const float ref = shadow_ref_clamp(__fdiv_rn(cz, cw));
+	const float fres = (float)res;
+	const float ix = __fsub_rn(__fmul_rn(u, fres), 1.5f), iy = __fsub_rn(__fmul_rn(v, fres), 1.5f);
+	const float flx = floorf(ix), fly = floorf(iy);
+	const float fx = __fsub_rn(ix, flx), fy = __fsub_rn(iy, fly);
+	const ShadowBilin q = shadow_bilin(__fdiv_rn(flx, fres), __fdiv_rn(fly, fres), res); // origin of the first gather's footprint
+	float H[6], V[6];
+	const float off[6] = { 2.0f, 1.0f, 0.0f, -1.0f, -2.0f, -3.0f };
+#pragma unroll
+	for (int i = 0; i < 6; i++)
+	{
+		H[i] = pcf_wide_weight(__fadd_rn(fx, off[i]));
+		V[i] = pcf_wide_weight(__fadd_rn(fy, off[i]));
+	}
+	float var = 0.0f, total_w = 0.0f;
+#pragma unroll
+	for (int gy = 0; gy < 3; gy++)
+	{
+		const int p = 2 * gy;
+		const size_t r0 = (size_t)min(max(q.y0 + p, 0), res - 1) * res, r1 = (size_t)min(max(q.y0 + p + 1, 0), res - 1) * res;
+#pragma unroll
+		for (int gx = 0; gx < 3; gx++)
+		{
+			const int a = 2 * gx;
+			const int x0 = min(max(q.x0 + a, 0), res - 1), x1 = min(max(q.x0 + a + 1, 0), res - 1);
+			// gather components x = (a, p + 1), y = (a + 1, p + 1), z = (a + 1, p), w = (a, p)
+			const float kx = __fmul_rn(H[a], V[p + 1]), ky = __fmul_rn(H[a + 1], V[p + 1]), kz = __fmul_rn(H[a + 1], V[p]), kw = __fmul_rn(H[a], V[p]);
+			const float c_x = shadow_compare(map, r1 + x0, ref), c_y = shadow_compare(map, r1 + x1, ref), c_z = shadow_compare(map, r0 + x1, ref),
+			            c_w = shadow_compare(map, r0 + x0, ref);
+			var = __fadd_rn(var, __fadd_rn(__fadd_rn(__fmul_rn(c_x, kx), __fmul_rn(c_y, ky)), __fadd_rn(__fmul_rn(c_z, kz), __fmul_rn(c_w, kw))));
+			total_w = __fadd_rn(total_w, __fadd_rn(__fadd_rn(kx, kz), __fadd_rn(ky, kw)));
+		}
+	}
+	return __fdiv_rn(var, total_w);
 }
 
 // Texel (i, j) of face f with i or j possibly one step outside [0, res): the texel across that edge of the cube
@@ -186,14 +235,14 @@ __device__ __forceinline__ float shadow_sample_cube(const uint16_t *map, int res
 
 // spot.h:67-77: clip = shadow[index] * vec4(world_pos, 1) -- (c0 x + c1 y) + (c2 z + c3), the association of the
 // reference code as spirv-cross / GLM evaluates it -- then the projective comparison sample
-__device__ __forceinline__ float spot_shadow_falloff(const float *m, float px, float py, float pz, const uint16_t *map, int res)
+__device__ __forceinline__ float spot_shadow_falloff(const float *m, float px, float py, float pz, const uint16_t *map, int res, bool pcf_wide = false)
 {
 	float c[4];
 #pragma unroll
 	for (int r = 0; r < 4; r++)
 		c[r] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(m + r), px), __fmul_rn(__ldg(m + 4 + r), py)),
 		                 __fadd_rn(__fmul_rn(__ldg(m + 8 + r), pz), __ldg(m + 12 + r)));
-	return shadow_sample_2d(map, res, c[0], c[1], c[2], c[3]);
+	return pcf_wide ? shadow_sample_2d_wide(map, res, c[0], c[1], c[2], c[3]) : shadow_sample_2d(map, res, c[0], c[1], c[2], c[3]);
 }
 
 // point.h:46-49,67-71: full = world_pos - light_pos; the cube face's depth along its major axis from

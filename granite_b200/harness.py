@@ -136,11 +136,11 @@ def deferred_lighting(gb: GBufferDevice, cam: capi.GrbCamera, cluster: ClusterDe
 
 
 def deferred_lighting_shadowed(gb: GBufferDevice, cam: capi.GrbCamera, cluster: ClusterDevice, transforms: torch.Tensor, map_table: torch.Tensor,
-                              resolution: int, hdr: torch.Tensor, rows=None):
+                              resolution: int, hdr: torch.Tensor, rows=None, pcf_wide=False):
     """Lighting with shadowed positional lights.  transforms: float32 (n, 16) device tensor (cluster order); map_table: int64 (n,)
     device tensor of device pointers to each light's D16 map (0 = no shadow)."""
     img = _hdr_img(hdr)
-    sh = capi.GrbLightShadows(_ptr(transforms), _ptr(map_table), int(resolution))
+    sh = capi.GrbLightShadows(_ptr(transforms), _ptr(map_table), int(resolution), int(pcf_wide))
     capi.check(capi.lib().grb_deferred_lighting_shadowed(C.byref(gb.struct), C.byref(cam), C.byref(cluster.params), C.byref(cluster.buffers),
                                                          C.byref(sh), C.byref(img), capi.rows(rows), capi.stream_ptr()), "grb_deferred_lighting_shadowed")
 

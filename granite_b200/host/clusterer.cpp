@@ -81,6 +81,7 @@ GrbLightShadows LightClusterer::get_light_shadows() const
 	s.transforms = reinterpret_cast<const float *>(base + packed_size(n));
 	s.maps = reinterpret_cast<const void *const *>(base + packed_offset_shadow_maps(n));
 	s.resolution = (int32_t)shadow_resolution;
+	s.pcf_wide = shadow_pcf_wide ? 1 : 0;
 	return s;
 }
 

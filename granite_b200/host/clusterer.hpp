@@ -53,6 +53,8 @@ public:
 	bool get_enable_shadows() const { return enable_shadows; }
 	void set_shadow_resolution(unsigned res) { shadow_resolution = res; }
 	unsigned get_shadow_resolution() const { return shadow_resolution; }
+	// config "PCFKernelWide" (scene_viewer_application.cpp:208-217 -> Renderer::SHADOW_PCF_KERNEL_WIDE_BIT)
+	void set_shadow_pcf_kernel_wide(bool enable) { shadow_pcf_wide = enable; }
 	// ClustererBindlessTransforms::shadow[index] of a spot light (xy_range = SpotLight::get_xy_range) / a point light
 	static mat4 spot_shadow_transform(const PositionalFragmentInfo &light, float xy_range);
 	static mat4 point_shadow_transform(const PositionalFragmentInfo &light);
@@ -125,6 +127,7 @@ private:
 	std::vector<uvec2> volume_index_range;
 	bool enable_shadows = false;
 	unsigned shadow_resolution = 512;
+	bool shadow_pcf_wide = false;
 	std::vector<mat4> shadow_transforms;
 	std::vector<const void *> shadow_maps;
 	bool enable_volumetric_decals = false;

@@ -233,6 +233,8 @@ typedef struct GrbLightShadows
 	 * +X -X +Y -Y +Z -Z) for a point light; a null entry = the light casts no shadow (its falloff stays 1). */
 	const void *const *maps;
 	int32_t resolution; /* LightClusterer::set_shadow_resolution (clusterer.cpp:78-81), 512 by default */
+	int32_t pcf_wide;   /* != 0: SHADOW_MAP_PCF_KERNEL_WIDE (config "PCFKernelWide", renderer.cpp:380-381): spot lights filter with the
+	                     * 6 x 6 kernel of pcf.h:7-80 instead of the sampler's 2 x 2; point lights keep the cube sampler */
 } GrbLightShadows;
 /* The lighting pass with shadowed positional lights; every other argument as grb_deferred_lighting. */
 int32_t grb_deferred_lighting_shadowed(const GrbGBuffer *gbuffer, const GrbCamera *cam, const GrbClusterParameters *params,

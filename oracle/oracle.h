@@ -143,6 +143,7 @@ typedef struct
 	const float *transforms;
 	const uint16_t *const *maps;
 	int resolution;
+	int pcf_wide; /* SHADOW_MAP_PCF_KERNEL_WIDE: spot lights filter with the 6 x 6 kernel of pcf.h:7-80 (point lights are unaffected) */
 } orc_shadows_t;
 void orc_deferred_lighting_shadowed(const orc_gbuffer_t *g, const orc_camera_t *cam, const orc_cluster_params_t *p,
                                     const orc_light_t *lights, const uint32_t *type_mask,
@@ -157,6 +158,7 @@ void orc_deferred_lighting_fp16(const orc_gbuffer_t *g, const orc_camera_t *cam,
 /* the two comparison samplers on their own (Vulkan specification's filtering, fp32 weights) */
 float orc_shadow_sample_2d(const uint16_t *map, int res, float clip_x, float clip_y, float clip_z, float clip_w);
 float orc_shadow_sample_cube(const uint16_t *map, int res, float dx, float dy, float dz, float ref);
+float orc_shadow_sample_2d_wide(const uint16_t *map, int res, float clip_x, float clip_y, float clip_z, float clip_w); /* pcf.h:7-80 */
 /* texel (i, j) of cube face f, i or j possibly one step outside the face (-> the adjacent face); 0 at a corner */
 int orc_shadow_cube_texel(int res, int f, int i, int j, size_t *texel);
 

@@ -120,6 +120,57 @@ float orc_shadow_sample_2d(const uint16_t *map, int res, float clip_x, float cli
 	return bilin_mix(c00, c10, c01, c11, b.a, b.b);
 }
 
+/* SHADOW_MAP_PCF_KERNEL_WIDE (renderer.cpp:380-381, pcf.h:7-80): a 6 x 6 texel kernel from nine comparison gathers, weights
+ * exp2(-0.375 d^2) (1 - d^2 / 9) per axis, normalised.  The gathers sit on texel corners (floor(uv res - 1.5) / res), so
+ * their footprints are exact whatever the sampler's precision: texel (c, r) of the window = (fx - 1 + c, fy - 1 + r),
+ * clamped to the edge.  Sums in the order of the shader's statements (dot and the weight sum as GLM / the macro write
+ * them), so that the pin compares like with like; exp2 is libm's. */
+static float pcf_wide_weight(float p)
+{
+	float p2 = p * p;
+	return exp2f(p2 * -0.375f) * (1.0f - p2 / 9.0f);
+}
+
+float orc_shadow_sample_2d_wide(const uint16_t *map, int res, float clip_x, float clip_y, float clip_z, float clip_w)
+{
+	float u = clip_x / clip_w, v = clip_y / clip_w;
+	float ref = f_clamp(clip_z / clip_w, 0.0f, 1.0f);
+	if (!(ref == ref))
+		ref = 0.0f;
+	const float fres = (float)res;
+	float ix = u * fres - 1.5f, iy = v * fres - 1.5f;
+	float flx = floorf(ix), fly = floorf(iy);
+	const float fx = ix - flx, fy = iy - fly;
+	/* footprint origin of textureGather at floored / res: floor(floored / res * res - 0.5) = floored - 1 */
+	bilin_t b = bilin_setup(flx / fres, fly / fres, res, res);
+	float H[6], V[6];
+	const float off[6] = { 2.0f, 1.0f, 0.0f, -1.0f, -2.0f, -3.0f };
+	for (int i = 0; i < 6; i++)
+	{
+		H[i] = pcf_wide_weight(fx + off[i]);
+		V[i] = pcf_wide_weight(fy + off[i]);
+	}
+	float c[6][6];
+	for (int r = 0; r < 6; r++)
+		for (int q = 0; q < 6; q++)
+		{
+			int x = b.x0 + q, y = b.y0 + r;
+			x = x < 0 ? 0 : (x > res - 1 ? res - 1 : x);
+			y = y < 0 ? 0 : (y > res - 1 ? res - 1 : y);
+			c[r][q] = shadow_compare(map, (size_t)y * res + x, ref);
+		}
+	float var = 0.0f, total_w = 0.0f;
+	for (int gy = 0; gy < 3; gy++)
+		for (int gx = 0; gx < 3; gx++)
+		{
+			const int a = 2 * gx, p = 2 * gy; /* gather components: x = (a, p + 1), y = (a + 1, p + 1), z = (a + 1, p), w = (a, p) */
+			const float kx = H[a] * V[p + 1], ky = H[a + 1] * V[p + 1], kz = H[a + 1] * V[p], kw = H[a] * V[p];
+			var += (c[p + 1][a] * kx + c[p + 1][a + 1] * ky) + (c[p][a + 1] * kz + c[p][a] * kw);
+			total_w += (kx + kz) + (ky + kw);
+		}
+	return var / total_w;
+}
+
 /* Texel (i, j) of cube face f, where i or j may be one step outside [0, res): the texel across that edge.
  * Worked in doubled integer coordinates on the cube of half-size `res`: a texel centre of face f is the point
  * with major-axis component +-res and in-face components 2 i + 1 - res (odd, |.| < res).  One step outside
@@ -212,7 +263,7 @@ static vec4 shadow_clip(const float *m, vec3 p)
 }
 
 /* the light's shadow inputs for one evaluation; map == NULL => unshadowed */
-typedef struct { const float *transform; const uint16_t *map; int res; } light_shadow_t;
+typedef struct { const float *transform; const uint16_t *map; int res; int wide; } light_shadow_t;
 
 /* point.h:33-81 compute_point_color */
 static vec3 compute_point_color(const orc_light_t *pt, vec3 world_pos, vec3 *light_dir, light_shadow_t sh)
@@ -262,7 +313,8 @@ static vec3 compute_spot_color(const orc_light_t *sp, vec3 world_pos, vec3 *ligh
 		{
 			/* spot.h:67-77 + pcf.h:98-99 */
 			vec4 clip = shadow_clip(sh.transform, world_pos);
-			shadow_falloff = orc_shadow_sample_2d(sh.map, sh.res, clip.x, clip.y, clip.z, clip.w);
+			shadow_falloff = sh.wide ? orc_shadow_sample_2d_wide(sh.map, sh.res, clip.x, clip.y, clip.z, clip.w)
+			                         : orc_shadow_sample_2d(sh.map, sh.res, clip.x, clip.y, clip.z, clip.w);
 		}
 		float k = (cone_falloff * shadow_falloff) / (light_dist * light_dist);
 		return v3(sp->color[0] * k, sp->color[1] * k, sp->color[2] * k);
@@ -418,12 +470,13 @@ static void deferred_lighting(const orc_gbuffer_t *g, const orc_camera_t *cam, c
 				{
 					int bit = __builtin_ctz(mask);
 					int index = 32 * i + bit;
-					light_shadow_t sh = { 0, 0, 0 };
+					light_shadow_t sh = { 0, 0, 0, 0 };
 					if (shadows && shadows->maps[index])
 					{
 						sh.transform = shadows->transforms + 16 * (size_t)index;
 						sh.map = shadows->maps[index];
 						sh.res = shadows->resolution;
+						sh.wide = shadows->pcf_wide;
 					}
 					vec3 c = compute_positional_light(&lights[index], (tm >> bit) & 1u, base_color, N, metallic, roughness, pos, camera_pos, sh);
 					result = v3_add(result, c);

@@ -22,7 +22,7 @@ _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for 
 _REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173, 24, 25, 26, 27)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
 # deferred-lighting fragment shaders K5 (clustering.frag) and K6 (directional.frag), ref_light_shim.cpp
-_REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6, 7)}
+_REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6, 7, 8)}
 
 
 def build(ref: bool = True) -> None:
@@ -262,10 +262,10 @@ def shadow_transforms(prep):
 
 
 class Shadows(C.Structure):
-    _fields_ = [("transforms", C.c_void_p), ("maps", C.c_void_p), ("resolution", C.c_int)]
+    _fields_ = [("transforms", C.c_void_p), ("maps", C.c_void_p), ("resolution", C.c_int), ("pcf_wide", C.c_int)]
 
 
-def deferred_lighting_shadowed(scene, cam: Camera, prep, clus, transforms, maps, resolution, rows=None):
+def deferred_lighting_shadowed(scene, cam: Camera, prep, clus, transforms, maps, resolution, rows=None, pcf_wide=False):
     """The lighting pass with POSITIONAL_LIGHTS_SHADOW.  maps: one uint16 array per light (res x res for a spot light,
     6 x res x res for a point light) or None (no shadow)."""
     H, W = scene.depth.shape
@@ -281,7 +281,7 @@ def deferred_lighting_shadowed(scene, cam: Camera, prep, clus, transforms, maps,
     t = _c(transforms, np.float32)
     held = [None if m is None else _c(m, np.uint16) for m in maps]
     table = (C.c_void_p * max(len(held), 1))(*[None if m is None else m.ctypes.data for m in held])
-    sh = Shadows(t.ctypes.data, C.cast(table, C.c_void_p), int(resolution))
+    sh = Shadows(t.ctypes.data, C.cast(table, C.c_void_p), int(resolution), int(pcf_wide))
     lib().orc_deferred_lighting_shadowed(C.byref(g), C.byref(cam), C.byref(prep.params), _p(prep.records), _p(prep.type_mask),
                                          _p(clus.bitmask), _p(clus.range), C.byref(sh), _p(hdr), y0, y1)
     return hdr
@@ -402,7 +402,7 @@ def deferred_lighting_fp16(scene, cam: Camera, prep, clus, emissive16, rows=None
         t = _c(shadows[0], np.float32)
         held = [None if m is None else _c(m, np.uint16) for m in shadows[1]]
         table = (C.c_void_p * max(len(held), 1))(*[None if m is None else m.ctypes.data for m in held])
-        sh = C.byref(Shadows(t.ctypes.data, C.cast(table, C.c_void_p), int(shadows[2])))
+        sh = C.byref(Shadows(t.ctypes.data, C.cast(table, C.c_void_p), int(shadows[2]), int(shadows[3]) if len(shadows) > 3 else 0))
     lib().orc_deferred_lighting_fp16(C.byref(g), C.byref(cam), C.byref(prep.params), _p(prep.records), _p(prep.type_mask),
                                      _p(clus.bitmask), _p(clus.range), sh, _p(hdr), y0, y1)
     return hdr
@@ -441,7 +441,10 @@ def ref_deferred_lighting(scene, cam: Camera, prep, clus, rows=None, shadows=Non
         t = _c(shadows[0], np.float32)
         held = [None if m is None else _c(m, np.uint16) for m in shadows[1]]
         table = (C.c_void_p * max(len(held), 1))(*[None if m is None else m.ctypes.data for m in held])
-        clustering = lambda *a: k[7].refk7_clustering_shadowed(_p(t), table, int(shadows[2]), *a)  # noqa: E731
+        if len(shadows) > 3 and shadows[3]:  # SHADOW_MAP_PCF_KERNEL_WIDE
+            clustering = lambda *a: k[8].refk8_clustering_shadowed_pcf_wide(_p(t), table, int(shadows[2]), *a)  # noqa: E731
+        else:
+            clustering = lambda *a: k[7].refk7_clustering_shadowed(_p(t), table, int(shadows[2]), *a)  # noqa: E731
     else:
         clustering = k[5].refk5_clustering
     clustering(W, H, _p(alb), _p(nrm), _p(pbr), _p(dep), _p(ivp), _p(cpos), _p(_farr(list(P.camera_base))), _p(_farr(list(P.camera_front))),

@@ -56,7 +56,7 @@ struct sampler2D
 {
 	int unused;
 };
-#if KERNEL == 7
+#if KERNEL == 7 || KERNEL == 8
 // bindless shadow maps: one D16 image per light; a null map samples as 1.0 ("casts no shadow")
 struct texture2D
 {
@@ -89,6 +89,26 @@ extern "C" float orc_shadow_sample_cube(const uint16_t *map, int res, float dx, 
 inline float textureProjLod(const sampler2DShadow &s, const glm::vec4 &p, float) { return s.t.map ? orc_shadow_sample_2d(s.t.map, s.t.res, p.x, p.y, p.z, p.w) : 1.0f; }
 // texture(samplerCubeShadow, vec4(direction, D_ref))
 inline float texture(const samplerCubeShadow &s, const glm::vec4 &p) { return s.t.map ? orc_shadow_sample_cube(s.t.map, s.t.res, p.x, p.y, p.z, p.w) : 1.0f; }
+// KERNEL 8 (SHADOW_MAP_PCF_KERNEL_WIDE, pcf.h:7-80): textureSize and the comparison gathers -- four texels of the bilinear
+// footprint at uv (+ an integer offset), each compared GREATER_OR_EQUAL with the clamped reference; components
+// x = (i0, j1), y = (i1, j1), z = (i1, j0), w = (i0, j0); clamp to edge.  A null map compares as lit.
+inline glm::ivec2 textureSize(const texture2D &t, int) { return glm::ivec2(t.res, t.res); }
+inline glm::vec4 textureGatherOffset(const sampler2DShadow &s, const glm::vec2 &uv, float ref, const glm::ivec2 &off)
+{
+	if (!s.t.map)
+		return glm::vec4(1.0f);
+	const int res = s.t.res;
+	ref = ref > 0.0f ? (ref < 1.0f ? ref : 1.0f) : 0.0f;
+	const float fx = uv.x * (float)res - 0.5f, fy = uv.y * (float)res - 0.5f;
+	const int x0 = (int)std::floor(fx) + off.x, y0 = (int)std::floor(fy) + off.y;
+	auto cmp = [&](int x, int y) -> float {
+		x = x < 0 ? 0 : (x > res - 1 ? res - 1 : x);
+		y = y < 0 ? 0 : (y > res - 1 ? res - 1 : y);
+		return ref >= (float)s.t.map[(size_t)y * res + x] / 65535.0f ? 1.0f : 0.0f;
+	};
+	return glm::vec4(cmp(x0, y0 + 1), cmp(x0 + 1, y0 + 1), cmp(x0 + 1, y0), cmp(x0, y0));
+}
+inline glm::vec4 textureGather(const sampler2DShadow &s, const glm::vec2 &uv, float ref) { return textureGatherOffset(s, uv, ref, glm::ivec2(0)); }
 #endif
 template <typename T> inline T subgroupMin(T v) { return v; }
 template <typename T> inline T subgroupMax(T v) { return v; }
@@ -106,7 +126,7 @@ namespace shim
 static const void *g_transforms = nullptr;
 static const void *g_bitmask = nullptr;
 static const void *g_range = nullptr;
-#if KERNEL == 7
+#if KERNEL == 7 || KERNEL == 8
 static const spirv_cross::texture2D *g_spot_atlas = nullptr;   // indexed by light (uSpotShadowAtlas[index])
 static const spirv_cross::textureCube *g_point_atlas = nullptr; // the same descriptors seen as cubes (uPointShadowAtlas[index])
 #endif
@@ -186,7 +206,7 @@ struct Runner
 		spirv_cross_set_stage_input(sh, 0, &f.vclip, sizeof(f.vclip));
 		spirv_cross_set_stage_output(sh, 0, &f.color, sizeof(f.color));
 		spirv_cross_set_builtin(sh, SPIRV_CROSS_BUILTIN_FRAG_COORD, &f.frag_coord, sizeof(f.frag_coord));
-#if KERNEL == 7
+#if KERNEL == 7 || KERNEL == 8
 		static spirv_cross::sampler linear_shadow_sampler = { 0 }; // LinearShadowSampler: behaviour lives in the sample functions
 		spirv_cross_set_uniform_constant(sh, 0, &linear_shadow_sampler, sizeof(linear_shadow_sampler));
 #endif
@@ -217,11 +237,16 @@ struct Runner
 } // namespace
 
 extern "C" {
-#if KERNEL == 5 || KERNEL == 7
+#if KERNEL == 5 || KERNEL == 7 || KERNEL == 8
 // renderer.cpp:1107-1156.  The cluster parameters are the oracle's orc_cluster_params_t fields.
-#if KERNEL == 7
+#if KERNEL == 7 || KERNEL == 8
 // transforms16: num_lights x mat4 (ClustererBindlessTransforms::shadow); maps: num_lights pointers (null = no shadow)
-void refk7_clustering_shadowed(const float *transforms16, const uint16_t *const *maps, int shadow_res, int w, int h,
+#if KERNEL == 8
+void refk8_clustering_shadowed_pcf_wide(
+#else
+void refk7_clustering_shadowed(
+#endif
+                      const float *transforms16, const uint16_t *const *maps, int shadow_res, int w, int h,
 #else
 void refk5_clustering(int w, int h,
 #endif
@@ -235,7 +260,7 @@ void refk5_clustering(int w, int h,
 	std::memset(static_cast<void *>(blob), 0, sizeof(*blob));
 	std::memcpy(blob->cluster_transforms.lights.data(), lights48, (size_t)num_lights * 48);
 	std::memcpy(blob->cluster_transforms.type_mask.data(), type_mask, (size_t)num_lights_32 * 4);
-#if KERNEL == 7
+#if KERNEL == 7 || KERNEL == 8
 	std::memcpy(static_cast<void *>(blob->cluster_transforms.shadow.data()), transforms16, (size_t)num_lights * 64);
 	auto *spot_atlas = new spirv_cross::texture2D[num_lights > 0 ? num_lights : 1];
 	auto *point_atlas = new spirv_cross::textureCube[num_lights > 0 ? num_lights : 1];
@@ -273,7 +298,7 @@ void refk5_clustering(int w, int h,
 		r.draw(g, inv_view_projection16, y0, y1, out_rgb);
 	}
 	delete blob;
-#if KERNEL == 7
+#if KERNEL == 7 || KERNEL == 8
 	delete[] spot_atlas;
 	delete[] point_atlas;
 #endif

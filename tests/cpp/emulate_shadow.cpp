@@ -27,3 +27,9 @@ extern "C" void emu_point_shadow_falloff(const float *transform16, const float *
 	for (int i = 0; i < n; i++)
 		out[i] = grb::point_shadow_falloff(transform16, full3[3 * i], full3[3 * i + 1], full3[3 * i + 2], map, res);
 }
+
+extern "C" void emu_shadow_2d_wide(const uint16_t *map, int res, const float *clip4, int n, float *out)
+{
+	for (int i = 0; i < n; i++)
+		out[i] = grb::shadow_sample_2d_wide(map, res, clip4[4 * i], clip4[4 * i + 1], clip4[4 * i + 2], clip4[4 * i + 3]);
+}

@@ -53,3 +53,19 @@ def test_oracle_reproduces_reference_shadow_fixture(oracle):
     scene, cam, prep, clus, transforms, maps = shadow_case(oracle, 160, 96, 300, 0.25, 32)
     assert np.array_equal(scene.depth, f["depth"]) and np.array_equal(transforms, f["transforms"]), "synthetic case changed: regenerate the fixture"
     compare(oracle.deferred_lighting_shadowed(scene, cam, prep, clus, transforms, maps, 32), f["ref_hdr"], "shadowed image vs fixture")
+
+
+@pytest.mark.parametrize("w,h,n,spots,res", [pytest.param(160, 96, 300, 0.5, 32, id="160x96-300-50pct-spots-res32"),
+                                             pytest.param(192, 108, 200, 1.0, 64, id="192x108-200-spots-res64")])
+def test_oracle_wide_pcf_equals_reference_shader(oracle, w, h, n, spots, res):
+    """SHADOW_MAP_PCF_KERNEL_WIDE (config "PCFKernelWide"): spot lights filter with the 6 x 6 kernel of pcf.h:7-80."""
+    oracle.build()
+    k = oracle.ref_light_kernels()
+    if k is None or 8 not in k:
+        pytest.skip("oracle/_ref lighting shaders not built (no /root/reference on this machine)")
+    scene, cam, prep, clus, transforms, maps = shadow_case(oracle, w, h, n, spots, res)
+    mine = oracle.deferred_lighting_shadowed(scene, cam, prep, clus, transforms, maps, res, pcf_wide=True)
+    ref, _, c_rgb = oracle.ref_deferred_lighting(scene, cam, prep, clus, shadows=(transforms, maps, res, True))
+    compare(mine, ref, "wide-PCF lit image")
+    narrow = oracle.deferred_lighting_shadowed(scene, cam, prep, clus, transforms, maps, res)
+    assert (mine != narrow).mean() > 0.0005, "the wide kernel must change the spot lights' penumbrae"

@@ -219,3 +219,46 @@ def test_spot_shadow_transform_degenerate_directions(oracle):
             r = np.zeros(16, np.float32)
             ref.ref_spot_shadow_transform(_p(np.array(rec.direction[:], np.float32)), _p(np.array(rec.position[:], np.float32)), C.c_float(0.125), C.c_float(0.6), _p(r))
             assert np.array_equal(r.view(np.uint32), m.view(np.uint32)), d
+
+
+# ---- SHADOW_MAP_PCF_KERNEL_WIDE (pcf.h:7-80): the 6 x 6 kernel of the spot lights ----
+@pytest.mark.parametrize("res", [8, 33, 512])
+def test_shadow_2d_wide_source_equals_oracle(emu, oracle, res):
+    lib = oracle.lib()
+    lib.orc_shadow_sample_2d_wide.restype = C.c_float
+    lib.orc_shadow_sample_2d_wide.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4
+    rng = np.random.default_rng(res + 77)
+    m = rng.integers(0, 65536, (res, res), dtype=np.uint16)
+    n = 3000
+    clip = np.empty((n, 4), np.float32)
+    clip[:, 3] = rng.uniform(0.2, 30.0, n)
+    for c in range(3):
+        clip[:, c] = rng.uniform(-0.1, 1.1, n) * clip[:, 3]
+    clip[:4] = [[0, 0, 0.5, 1], [1, 1, 0.5, 1], [0.5, 0.5, 2, 1], [0.5 / res, 0.5 / res, 0.3, 1]]
+    out = np.zeros(n, np.float32)
+    emu.emu_shadow_2d_wide(_p(m), res, _p(clip), n, _p(out))
+    ref = np.array([lib.orc_shadow_sample_2d_wide(_p(m), res, *[float(v) for v in c]) for c in clip], np.float32)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    assert np.isfinite(ref).all() and (ref >= 0).all() and (ref <= 1.000001).all() and ((ref > 0.05) & (ref < 0.95)).mean() > 0.3
+
+
+def test_shadow_2d_wide_is_a_normalised_blur_of_the_comparison(oracle):
+    """All texels lit -> 1, none -> 0; across a straight shadow edge the wide kernel ramps over about five texels where
+    the sampler's 2 x 2 filter ramps over one."""
+    lib = oracle.lib()
+    for f in (lib.orc_shadow_sample_2d_wide, lib.orc_shadow_sample_2d):
+        f.restype = C.c_float
+        f.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4
+    res = 64
+    lit = np.zeros((res, res), np.uint16)
+    assert lib.orc_shadow_sample_2d_wide(_p(lit), res, 0.37, 0.61, 0.5, 1.0) == 1.0
+    dark = np.full((res, res), 65535, np.uint16)
+    assert lib.orc_shadow_sample_2d_wide(_p(dark), res, 0.37, 0.61, 0.5, 1.0) == 0.0
+    edge = np.zeros((res, res), np.uint16)
+    edge[:, 32:] = 65535
+    xs = np.linspace(24, 40, 161) / res
+    wide = np.array([lib.orc_shadow_sample_2d_wide(_p(edge), res, float(x), 0.5, 0.5, 1.0) for x in xs])
+    narrow = np.array([lib.orc_shadow_sample_2d(_p(edge), res, float(x), 0.5, 0.5, 1.0) for x in xs])
+    assert (np.diff(wide) <= 1e-6).all() and wide[0] == 1.0 and wide[-1] == 0.0
+    ramp = lambda v: ((v > 0.02) & (v < 0.98)).sum() / 10.0  # texels
+    assert 3.5 < ramp(wide) < 6.0 and 0.8 < ramp(narrow) < 1.2, (ramp(wide), ramp(narrow))

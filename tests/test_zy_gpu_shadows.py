@@ -27,7 +27,7 @@ def _device_shadows(transforms, maps):
     return t, table, held
 
 
-def _gpu_shadowed(cuda, oracle, scene, cam, prep, transforms, maps, res, rows=None):
+def _gpu_shadowed(cuda, oracle, scene, cam, prep, transforms, maps, res, rows=None, pcf_wide=False):
     import torch
 
     from granite_b200 import harness
@@ -37,7 +37,7 @@ def _gpu_shadowed(cuda, oracle, scene, cam, prep, transforms, maps, res, rows=No
     gb = harness.GBufferDevice(scene)
     hdr = gb.emissive.clone()
     t, table, held = _device_shadows(transforms, maps)
-    harness.deferred_lighting_shadowed(gb, gcam, dev, t, table, res, hdr, rows=rows)
+    harness.deferred_lighting_shadowed(gb, gcam, dev, t, table, res, hdr, rows=rows, pcf_wide=pcf_wide)
     torch.cuda.synchronize()
     return harness.to_host(hdr, np.uint32)
 
@@ -68,6 +68,13 @@ def test_cuda_shadowed_lighting_vs_oracle(cuda, oracle, w, h, n, spots, res):
     a = _gpu_shadowed(cuda, oracle, scene, cam, prep, transforms, maps, res, rows=(0, cut))
     b = _gpu_shadowed(cuda, oracle, scene, cam, prep, transforms, maps, res, rows=(cut, h))
     assert np.array_equal(a[:cut], got[:cut]) and np.array_equal(b[cut:], got[cut:])
+
+
+def test_cuda_wide_pcf_vs_oracle(cuda, oracle):
+    """SHADOW_MAP_PCF_KERNEL_WIDE: the 6 x 6 kernel of the spot lights (its exp2 is CUDA's on hardware: lighting bar)."""
+    scene, cam, prep, clus, transforms, maps = shadow_case(oracle, 320, 180, 300, 0.6, 64)
+    ref = oracle.deferred_lighting_shadowed(scene, cam, prep, clus, transforms, maps, 64, pcf_wide=True)
+    _compare(_gpu_shadowed(cuda, oracle, scene, cam, prep, transforms, maps, 64, pcf_wide=True), ref, 0.97)
 
 
 def test_cuda_shadowed_lighting_vs_reference_shader_fixture(cuda, oracle):
