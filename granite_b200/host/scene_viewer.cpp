@@ -240,7 +240,7 @@ void GrbhViewer::bake_render_graph()
 				upload_rows(cmd, res_mv, pending_upload->mv, 4);
 		});
 	}
-	bool resolved = setup_before_post_chain_antialiasing(before, graph, jitter, 1.0f, light_output, "depth-transient", "mv-main", "HDR-resolved");
+	bool resolved = setup_before_post_chain_antialiasing(before, graph, jitter, scene_scale(), light_output, "depth-transient", "mv-main", "HDR-resolved");
 	if (resolved && async_post)
 		graph.get_texture_resource("HDR-resolved").get_attachment_info().flags |= ATTACHMENT_INFO_PINGPONG_BIT;
 
@@ -342,7 +342,7 @@ void GrbhViewer::bake_render_graph()
 			const PostAAType type = config.post_aa == GRBH_AA_SMAA_LOW ? PostAAType::SMAA_Low :
 			                        (config.post_aa == GRBH_AA_SMAA_MEDIUM ? PostAAType::SMAA_Medium :
 			                                                                 (config.post_aa == GRBH_AA_SMAA_HIGH ? PostAAType::SMAA_High : PostAAType::SMAA_Ultra));
-			if (setup_after_post_chain_antialiasing(type, graph, jitter, 1.0f, ui_source, "depth-transient", "post-aa-output"))
+			if (setup_after_post_chain_antialiasing(type, graph, jitter, scene_scale(), ui_source, "depth-transient", "post-aa-output"))
 				ui_source = "post-aa-output";
 		}
 	}
