@@ -172,8 +172,26 @@ int32_t grb_cluster_decal_binning(const GrbClusterParameters *params, const floa
 /* Volumetric fog, accumulation pass: VolumetricFog::build_fog (renderer/lights/volumetric_fog.cpp:236-254) + fog_accumulate.comp.
  * light_density / fog: device pointers to R16G16B16A16_SFLOAT volumes of width x height x depth texels (x fastest, then y, then
  * slices), distinct and 8-byte aligned; light_density = (in-scattered light rgb, optical depth) per froxel, as the reference's
- * "volumetric-fog-inscatter" image holds it; fog = (light accumulated front to back, transmittance).  The first pass
- * (fog_light_density.comp) is not built: the caller supplies the density volume. */
+ * "volumetric-fog-inscatter" image holds it (grb_fog_light_density below, or the caller's own); fog = (light accumulated front to
+ * back, transmittance). */
+/* Volumetric fog, light-density pass: VolumetricFog::build_light_density (volumetric_fog.cpp:142-228) + fog_light_density.comp in
+ * its base variant: constant medium (no FOG_REGIONS), no TEMPORAL_REPROJECTION (the first frame of the reference), no
+ * FLOOR_LIGHTING, unshadowed directional and clustered positional lights.  projection16 / inv_projection16: the camera's
+ * (z_transform and xy_scale come from them, :161-168); slice_extents: depth floats (compute_slice_extents, :115-126);
+ * dither_lut: N layers of 128 x 128 R8G8B8A8_UNORM texels (build_dither_lut, :356-395), layer fog->dither_offset is read;
+ * light_density: depth x height x width R16G16B16A16_SFLOAT, 8-byte aligned = (in-scattered light, fog albedo). */
+typedef struct GrbFogParameters
+{
+	int32_t width, height, depth; /* VolumetricFog::set_resolution */
+	int32_t dither_offset;
+	float slice_z_log2_scale;     /* 1 / log2(1 + z_range) (:87-91) */
+	float density_mod;            /* set_fog_density */
+	float in_scatter_strength;    /* inscatter_mod */
+} GrbFogParameters;
+int32_t grb_fog_light_density(const GrbFogParameters *fog, const GrbCamera *cam, const float *projection16, const float *inv_projection16,
+                              const GrbClusterParameters *params, const GrbClusterBuffers *buf, const float *directional_color3,
+                              const float *directional_direction3, const float *slice_extents, const void *dither_lut, void *light_density,
+                              void *stream);
 int32_t grb_fog_accumulate(const void *light_density, int32_t width, int32_t height, int32_t depth, void *fog, void *stream);
 
 /* ---- deferred lighting: replaces DeferredLightRenderer::render_light

@@ -237,6 +237,22 @@ void orc_fsr_easu(const uint32_t *src_unorm, int w_in, int h_in, const float *co
 /* sharpen.frag: srgb = 1 reads through an sRGB view (linear values) and stores into an sRGB target */
 void orc_fsr_rcas(const uint32_t *src, int w, int h, const float *con4, uint32_t *dst, int srgb, int y0, int y1);
 
+/* ---- volumetric fog, light-density pass: fog_light_density.comp, base variant (no fog regions, no temporal reprojection,
+ * no floor lighting, no shadows); VolumetricFog::build_light_density (volumetric_fog.cpp:142-228) ---- */
+typedef struct
+{
+	int width, height, depth;   /* VolumetricFog::set_resolution; the reference's default is 160 x 92 x 64 */
+	int dither_offset;          /* layer of the 128 x 128 x N dither LUT */
+	float slice_z_log2_scale;   /* 1 / log2(1 + z_range) (volumetric_fog.cpp:87-91) */
+	float density_mod;          /* set_fog_density */
+	float in_scatter_strength;  /* inscatter_mod */
+} orc_fog_params_t;
+void orc_fog_slice_extents(int depth, float slice_z_log2_scale, float *out);
+/* out: depth x height x width RGBA16F = (in-scattered light, fog albedo); dither_lut_rgba8: N x 128 x 128 texels (R8G8B8A8_UNORM) */
+void orc_fog_light_density(const orc_fog_params_t *f, const orc_camera_t *cam, const orc_cluster_params_t *p, const orc_light_t *lights,
+                           const uint32_t *type_mask, const uint32_t *bitmask, const uint32_t *cluster_range, const float *dir_color3,
+                           const float *dir_direction3, const float *slice_extents, const uint32_t *dither_lut_rgba8, uint16_t *out_rgba16f);
+
 /* ---- volumetric fog, accumulation pass: fog_accumulate.comp + VolumetricFog::build_fog (volumetric_fog.cpp:236-254).
  * light / fog: R16G16B16A16_SFLOAT volumes of w x h x d texels, x fastest ---- */
 void orc_fog_accumulate(const uint16_t *light_rgba16f, int w, int h, int d, uint16_t *fog_rgba16f);

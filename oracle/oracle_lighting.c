@@ -552,3 +552,118 @@ void orc_blend_add_rgba16f(uint16_t *dst, const float *src_rgb, const uint8_t *m
 			dst[4 * i + c] = f32_to_f16_rne(f16_to_f32(dst[4 * i + c]) + src_rgb[3 * i + c]);
 	}
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Volumetric fog, first pass: fog_light_density.comp (VolumetricFog::build_light_density, renderer/lights/
+ * volumetric_fog.cpp:142-228) in its base variant -- no fog regions (density 0.1), no temporal reprojection (the first
+ * frame), no floor lighting, unshadowed directional light, clustered positional lights without shadows.  Per froxel:
+ * dithered position -> world position, fog albedo, in-scattered light (directional + compute_cluster_scatter_light,
+ * clusterer_bindless.h:158-203) -> RGBA16F.  mat4 * vec4 pairwise, as the generated reference code evaluates it.
+ * --------------------------------------------------------------------------------------------- */
+static vec4 m4_mul_v4_pairwise(const float *m, vec4 v)
+{
+	return v4((m[0] * v.x + m[4] * v.y) + (m[8] * v.z + m[12] * v.w), (m[1] * v.x + m[5] * v.y) + (m[9] * v.z + m[13] * v.w),
+	          (m[2] * v.x + m[6] * v.y) + (m[10] * v.z + m[14] * v.w), (m[3] * v.x + m[7] * v.y) + (m[11] * v.z + m[15] * v.w));
+}
+
+/* clusterer_bindless.h:158-203 with point.h:83-89 / spot.h:86-92 (a subgroup of one: the pixel's own mask) */
+static vec3 cluster_scatter_light(const orc_cluster_params_t *p, const orc_light_t *lights, const uint32_t *type_mask, const uint32_t *bitmask,
+                                  const uint32_t *cluster_range, vec3 world_pos, vec3 camera_pos)
+{
+	vec3 result = v3(0.0f, 0.0f, 0.0f);
+	vec4 clip = m4_mul_v4_pairwise(p->transform, v4(world_pos.x, world_pos.y, world_pos.z, 1.0f));
+	if (clip.w <= 0.0f)
+		return result;
+	float cxf = (clip.x * p->xy_scale[0]) / clip.w, cyf = (clip.y * p->xy_scale[1]) / clip.w;
+	int cx = cxf >= 2147483520.0f ? 2147483647 : (cxf <= -2147483648.0f ? (-2147483647 - 1) : (cxf != cxf ? 0 : (int)cxf));
+	int cy = cyf >= 2147483520.0f ? 2147483647 : (cyf <= -2147483648.0f ? (-2147483647 - 1) : (cyf != cyf ? 0 : (int)cyf));
+	cx = cx < 0 ? 0 : (cx > p->resolution_xy[0] - 1 ? p->resolution_xy[0] - 1 : cx);
+	cy = cy < 0 ? 0 : (cy > p->resolution_xy[1] - 1 ? p->resolution_xy[1] - 1 : cy);
+	const int cluster_base = (cy * p->resolution_xy[0] + cx) * p->num_lights_32;
+	vec3 cbase = v3(p->camera_base[0], p->camera_base[1], p->camera_base[2]), cfront = v3(p->camera_front[0], p->camera_front[1], p->camera_front[2]);
+	float zs = v3_dot(v3_sub(world_pos, cbase), cfront) * p->z_scale;
+	int z_index = zs >= 2147483520.0f ? 2147483647 : (zs <= -2147483648.0f ? (-2147483647 - 1) : (zs != zs ? 0 : (int)zs));
+	z_index = z_index < 0 ? 0 : (z_index > p->z_max_index ? p->z_max_index : z_index);
+	uint32_t rx = cluster_range[2 * z_index], ry = cluster_range[2 * z_index + 1];
+	for (int i = (int)(rx >> 5u); i <= (int)(ry >> 5u) && i < p->num_lights_32; i++)
+	{
+		uint32_t mask = cluster_mask_range(bitmask[cluster_base + i], rx, ry, 32u * (uint32_t)i);
+		const uint32_t tm = type_mask[i];
+		while (mask != 0u)
+		{
+			const int bit = __builtin_ctz(mask);
+			const orc_light_t *l = &lights[32 * i + bit];
+			const light_shadow_t none = { 0, 0, 0, 0 };
+			vec3 light_dir;
+			vec3 color = ((tm >> bit) & 1u) ? compute_point_color(l, world_pos, &light_dir, none) : compute_spot_color(l, world_pos, &light_dir, none);
+			float VoL = v3_dot(v3_normalize(v3_sub(camera_pos, world_pos)), v3_normalize(v3_sub(v3(l->position[0], l->position[1], l->position[2]), world_pos)));
+			float phase = 0.55f - 0.45f * VoL;
+			result = v3_add(result, v3(color.x * phase, color.y * phase, color.z * phase));
+			mask &= ~(1u << bit);
+		}
+	}
+	return result;
+}
+
+void orc_fog_light_density(const orc_fog_params_t *f, const orc_camera_t *cam, const orc_cluster_params_t *p, const orc_light_t *lights,
+                           const uint32_t *type_mask, const uint32_t *bitmask, const uint32_t *cluster_range, const float *dir_color3,
+                           const float *dir_direction3, const float *slice_extents, const uint32_t *dither_lut_rgba8, uint16_t *out_rgba16f)
+{
+	const int W = f->width, H = f->height, D = f->depth;
+	const float inv_x = 1.0f / (float)W, inv_y = 1.0f / (float)H, inv_z = 1.0f / (float)D; /* volumetric_fog.cpp:165 */
+	const vec3 camera_pos = v3(cam->camera_position[0], cam->camera_position[1], cam->camera_position[2]);
+	const vec3 dir = v3(dir_direction3[0], dir_direction3[1], dir_direction3[2]);
+	/* z_transform = (projection[2].zw, projection[3].zw); xy_scale = (inv_projection[0].x, inv_projection[1].y) (:161-168) */
+	const float zt[4] = { cam->projection[10], cam->projection[11], cam->projection[14], cam->projection[15] };
+	const float xy_scale[2] = { cam->inv_projection[0], cam->inv_projection[5] };
+#pragma omp parallel for schedule(dynamic, 2)
+	for (int z = 0; z < D; z++)
+		for (int y = 0; y < H; y++)
+			for (int x = 0; x < W; x++)
+			{
+				float u = ((float)x + 0.5f) * inv_x, v = ((float)y + 0.5f) * inv_y, w = ((float)z + 0.5f) * inv_z;
+				const uint32_t dl = dither_lut_rgba8[((size_t)f->dither_offset * 128 + (size_t)(y & 127)) * 128 + (size_t)(x & 127)];
+				float dx = (float)(dl & 255u) / 255.0f, dy = (float)((dl >> 8) & 255u) / 255.0f, dz = (float)((dl >> 16) & 255u) / 255.0f;
+				dx -= 0.5f;
+				dy -= 0.5f;
+				dz = -dz;
+				u += dx * inv_x;
+				v += dy * inv_y;
+				w += dz * inv_z;
+				u = f_clamp(u, 0.0f, 1.0f);
+				v = f_clamp(v, 0.0f, 1.0f);
+				w = f_clamp(w, 0.001f, 1.0f);
+				/* get_world_position */
+				const float world_z = exp2f(w / f->slice_z_log2_scale) - 1.0f;
+				const float zw_x = zt[2] - zt[0] * world_z, zw_y = zt[3] - zt[1] * world_z;
+				const float clip_z = zw_x / zw_y;
+				const vec4 clip = m4_mul_v4_pairwise(cam->inv_view_projection, v4(u * 2.0f - 1.0f, v * 2.0f - 1.0f, clip_z, 1.0f));
+				const vec3 pos = v3(clip.x / clip.w, clip.y / clip.w, clip.z / clip.w);
+				/* get_fog_albedo * compute_fog_density (no regions: 0.1) */
+				const float lx = (u * 2.0f - 1.0f) * xy_scale[0], ly = (v * 2.0f - 1.0f) * xy_scale[1];
+				const float length_mod = sqrtf(1.0f * 1.0f + lx * lx + ly * ly);
+				float albedo = f->density_mod * slice_extents[z] * length_mod;
+				albedo = albedo * 0.1f;
+				/* compute_scatter_lighting (lighting_scatter.h:13-38) */
+				const float VoL = v3_dot(v3_normalize(v3_sub(camera_pos, pos)), dir);
+				const float phase = (0.55f - 0.45f * VoL) * 1.0f;
+				vec3 s = v3(dir_color3[0] * phase, dir_color3[1] * phase, dir_color3[2] * phase);
+				s = v3_add(s, cluster_scatter_light(p, lights, type_mask, bitmask, cluster_range, pos, camera_pos));
+				uint16_t *o = out_rgba16f + 4 * (((size_t)z * H + y) * W + x);
+				o[0] = f32_to_f16_rne(f->in_scatter_strength * s.x);
+				o[1] = f32_to_f16_rne(f->in_scatter_strength * s.y);
+				o[2] = f32_to_f16_rne(f->in_scatter_strength * s.z);
+				o[3] = f32_to_f16_rne(albedo);
+			}
+}
+
+/* VolumetricFog::compute_slice_extents (volumetric_fog.cpp:115-126) */
+void orc_fog_slice_extents(int depth, float slice_z_log2_scale, float *out)
+{
+	for (int z = 0; z < depth; z++)
+	{
+		float end_z = exp2f(((float)z + 1.0f) / ((float)depth * slice_z_log2_scale)) - 1.0f;
+		float start_z = exp2f((float)z / ((float)depth * slice_z_log2_scale)) - 1.0f;
+		out[z] = end_z - start_z;
+	}
+}

@@ -870,3 +870,31 @@ def ref_fog_accumulate(light):
     out = np.zeros((d, h, w, 4), np.uint16)
     ref_post_kernels()[27].refk27_fog_accumulate(_p(_c(light, np.uint16)), w, h, d, _p(out))
     return out
+
+
+# ---------------- volumetric fog, light-density pass (volumetric_fog.cpp:115-228), base variant ----------------
+class FogParams(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("depth", C.c_int), ("dither_offset", C.c_int),
+                ("slice_z_log2_scale", C.c_float), ("density_mod", C.c_float), ("in_scatter_strength", C.c_float)]
+
+
+def fog_params(w, h, d, z_range=80.0, density=0.5, in_scatter=1.0, dither_offset=0):
+    """slice_z_log2_scale = 1 / log2(1 + z_range), in fp32 (volumetric_fog.cpp:87-91)."""
+    s = np.float32(1.0) / np.float32(np.log2(np.float32(1.0) + np.float32(z_range)))
+    return FogParams(int(w), int(h), int(d), int(dither_offset), float(s), float(density), float(in_scatter))
+
+
+def fog_slice_extents(fp: FogParams):
+    out = np.zeros(fp.depth, np.float32)
+    lib().orc_fog_slice_extents(fp.depth, _f(fp.slice_z_log2_scale), _p(out))
+    return out
+
+
+def fog_light_density(fp: FogParams, cam: Camera, prep, clus, dir_color, dir_direction, dither_lut):
+    """dither_lut: (layers, 128, 128) uint32 RGBA8.  Returns (d, h, w, 4) uint16 RGBA16F."""
+    out = np.zeros((fp.depth, fp.height, fp.width, 4), np.uint16)
+    ext = fog_slice_extents(fp)
+    lib().orc_fog_light_density(C.byref(fp), C.byref(cam), C.byref(prep.params), _p(prep.records), _p(prep.type_mask), _p(_c(clus.bitmask, np.uint32)),
+                                _p(_c(clus.range, np.uint32)), _p(_farr(list(dir_color))), _p(_farr(list(dir_direction))), _p(ext),
+                                _p(_c(dither_lut, np.uint32)), _p(out))
+    return out

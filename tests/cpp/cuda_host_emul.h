@@ -44,3 +44,6 @@ template <typename T>
 static inline T __ldg(const T *p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }

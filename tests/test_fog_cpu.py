@@ -84,3 +84,73 @@ def test_fog_accumulate_physics(oracle):
     uni[..., 3] = 0.125
     t = _f16(oracle.fog_accumulate(uni.view(np.uint16)))[:, h // 2, w // 2, 3]
     assert np.allclose(t, np.exp2(-0.125 * np.arange(1, d + 1)), rtol=2e-3)
+
+
+# ---- light-density pass (fog_light_density.comp, base variant) ----
+def fog_case(oracle, w=40, h=23, d=16, n=300, spots=0.25):
+    from tests import common
+
+    cam, lights, prep = common.build_lights_case(oracle, 16.0 / 9.0, n, spots)
+    clus = oracle.cluster_build(cam, prep)
+    fp = oracle.fog_params(w, h, d, z_range=80.0, density=0.5, in_scatter=1.25, dither_offset=1)
+    lut = np.random.default_rng(17).integers(0, 2 ** 32, (3, 128, 128), dtype=np.uint64).astype(np.uint32)
+    return cam, prep, clus, fp, lut
+
+
+DIR_COLOR, DIR_DIRECTION = (6.0, 5.5, 4.5), tuple(np.array([0.3, 0.8, 0.5]) / np.linalg.norm([0.3, 0.8, 0.5]))
+
+
+def test_fog_density_kernel_source_equals_oracle(emu, oracle):
+    from granite_b200 import capi
+
+    cam, prep, clus, fp, lut = fog_case(oracle)
+    ref = oracle.fog_light_density(fp, cam, prep, clus, DIR_COLOR, DIR_DIRECTION, lut)
+    g = capi.GrbFogParameters(fp.width, fp.height, fp.depth, fp.dither_offset, fp.slice_z_log2_scale, fp.density_mod, fp.in_scatter_strength)
+    gcam = capi.GrbCamera()
+    for name in ("view", "view_projection", "inv_view_projection", "camera_position", "camera_front"):
+        getattr(gcam, name)[:] = list(getattr(cam, name))
+    gp = capi.GrbClusterParameters()
+    for name, _t in capi.GrbClusterParameters._fields_:
+        v = getattr(prep.params, name)
+        if hasattr(v, "__len__"):
+            getattr(gp, name)[:] = list(v)
+        else:
+            setattr(gp, name, v)
+    keep = [np.ascontiguousarray(prep.records), np.ascontiguousarray(prep.type_mask, np.uint32), np.ascontiguousarray(clus.bitmask, np.uint32),
+            np.ascontiguousarray(clus.range, np.uint32)]
+    buf = capi.GrbClusterBuffers()
+    buf.lights, buf.type_mask, buf.bitmask, buf.cluster_range = [k.ctypes.data for k in keep]
+    ext = oracle.fog_slice_extents(fp)
+    proj, inv_proj = np.array(list(cam.projection), np.float32), np.array(list(cam.inv_projection), np.float32)
+    dc, dd = np.array(DIR_COLOR, np.float32), np.array(DIR_DIRECTION, np.float32)
+    got = np.zeros_like(ref)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    emu.emu_fog_light_density(C.byref(g), C.byref(gcam), p(proj), p(inv_proj), C.byref(gp), C.byref(buf), p(dc), p(dd), p(ext), p(lut), p(got))
+    assert np.array_equal(got, ref)
+    from tests import common
+
+    cam0, _, prep0 = common.build_lights_case(oracle, 16.0 / 9.0, 0)
+    dark = oracle.fog_light_density(fp, cam0, prep0, oracle.cluster_build(cam0, prep0), DIR_COLOR, DIR_DIRECTION, lut)
+    reached = (ref[..., :3] != dark[..., :3]).any(-1).mean()  # froxels a positional light adds to
+    print(f"positional lights reach {reached:.4f} of the froxels")
+    assert 0.003 < reached < 0.98 and np.isfinite(_f16(ref)).all() and np.array_equal(ref[..., 3], dark[..., 3])
+
+
+def test_fog_density_properties(oracle):
+    """No positional lights: in-scatter = strength * colour * (0.55 - 0.45 VoL) within the phase function's range; the albedo
+    grows with the slice thickness along z and with the ray's obliquity towards the screen corners."""
+    from tests import common
+
+    cam, lights, prep = common.build_lights_case(oracle, 16.0 / 9.0, 0)
+    clus = oracle.cluster_build(cam, prep)
+    fp = oracle.fog_params(32, 18, 12, in_scatter=2.0)
+    lut = np.full((1, 128, 128), 0x00007F7F, np.uint32)  # dither (0.498 - 0.5, 0.498 - 0.5, 0): practically none
+    out = _f16(oracle.fog_light_density(fp, cam, prep, clus, DIR_COLOR, DIR_DIRECTION, lut))
+    for c in range(3):
+        lo, hi = 2.0 * DIR_COLOR[c] * 0.1, 2.0 * DIR_COLOR[c] * 1.0
+        assert (out[..., c] >= lo * 0.999).all() and (out[..., c] <= hi * 1.001).all()
+    a = out[..., 3]
+    assert (np.diff(a[:, 9, 16]) > 0).all(), "slices get thicker with distance"
+    assert a[5, 0, 0] > a[5, 9, 16] and a[5, 17, 31] > a[5, 9, 16], "oblique rays cross more medium"
+    ext = oracle.fog_slice_extents(fp)
+    assert abs(ext.sum() - 80.0) < 1e-2, "the slices tile [0, z_range]"
