@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(128) fog_light_density_kernel(FogDensityArgs a
 	// fog albedo
 	const float lx = (u * 2.0f - 1.0f) * a.xy_scale[0], ly = (v * 2.0f - 1.0f) * a.xy_scale[1];
 	const float length_mod = sqrtf(1.0f * 1.0f + lx * lx + ly * ly);
-	float albedo = a.density_mod * __ldg(a.slice_extents + z) * length_mod;
+	// the shader indexes the extents with gl_GlobalInvocationID.z, which for its 64 x 1 x 1 workgroup (remapped to 4 x 4 x 4
+	// froxels) is the workgroup's z = z / 4: four slices share one extent.  Reproduced as the reference behaves.
+	float albedo = a.density_mod * __ldg(a.slice_extents + (z >> 2)) * length_mod;
 	albedo = albedo * 0.1f;
 	// directional in-scatter
 	const float3 cam = make_float3(a.camera_pos[0], a.camera_pos[1], a.camera_pos[2]);

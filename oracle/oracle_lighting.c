@@ -642,7 +642,10 @@ void orc_fog_light_density(const orc_fog_params_t *f, const orc_camera_t *cam, c
 				/* get_fog_albedo * compute_fog_density (no regions: 0.1) */
 				const float lx = (u * 2.0f - 1.0f) * xy_scale[0], ly = (v * 2.0f - 1.0f) * xy_scale[1];
 				const float length_mod = sqrtf(1.0f * 1.0f + lx * lx + ly * ly);
-				float albedo = f->density_mod * slice_extents[z] * length_mod;
+				/* texelFetch(uSliceExtents, int(gl_GlobalInvocationID.z)): the workgroup is 64 x 1 x 1 threads remapped to a 4 x 4 x 4
+				 * box (.comp:207-215), so gl_GlobalInvocationID.z is the WORKGROUP's z index = z / 4, not the froxel's slice:
+				 * four consecutive slices share the extent of slice z / 4.  Reproduced as the reference behaves. */
+				float albedo = f->density_mod * slice_extents[z >> 2] * length_mod;
 				albedo = albedo * 0.1f;
 				/* compute_scatter_lighting (lighting_scatter.h:13-38) */
 				const float VoL = v3_dot(v3_normalize(v3_sub(camera_pos, pos)), dir);

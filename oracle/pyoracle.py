@@ -22,7 +22,7 @@ _REF_KERNEL_PATHS = [os.path.join(_HERE, "_ref", f"libgranite_ref_k{k}.so") for 
 _REF_POST_IDS = (7, 8, 18, 9, 10, 11, 12, 22, 13, 23, 33, 43, 14, 150, 151, 152, 153, 160, 161, 162, 163, 170, 171, 172, 173, 24, 25, 26, 27)
 _REF_POST_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_p{k}.so") for k in _REF_POST_IDS}
 # deferred-lighting fragment shaders K5 (clustering.frag) and K6 (directional.frag), ref_light_shim.cpp
-_REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6, 7, 8)}
+_REF_LIGHT_PATHS = {k: os.path.join(_HERE, "_ref", f"libgranite_ref_l{k}.so") for k in (5, 6, 7, 8, 9)}
 
 
 def build(ref: bool = True) -> None:
@@ -897,4 +897,20 @@ def fog_light_density(fp: FogParams, cam: Camera, prep, clus, dir_color, dir_dir
     lib().orc_fog_light_density(C.byref(fp), C.byref(cam), C.byref(prep.params), _p(prep.records), _p(prep.type_mask), _p(_c(clus.bitmask, np.uint32)),
                                 _p(_c(clus.range, np.uint32)), _p(_farr(list(dir_color))), _p(_farr(list(dir_direction))), _p(ext),
                                 _p(_c(dither_lut, np.uint32)), _p(out))
+    return out
+
+
+def ref_fog_light_density(fp: FogParams, cam: Camera, prep, clus, dir_color, dir_direction, dither_lut):
+    """The reference's fog_light_density.comp (base variant) on the CPU (oracle/_ref/libgranite_ref_l9)."""
+    out = np.zeros((fp.depth, fp.height, fp.width, 4), np.uint16)
+    ext = fog_slice_extents(fp)
+    P = prep.params
+    ref_light_kernels()[9].refk9_fog_light_density(
+        fp.width, fp.height, fp.depth, fp.dither_offset, _f(fp.slice_z_log2_scale), _f(fp.density_mod), _f(fp.in_scatter_strength),
+        _p(_farr(list(cam.inv_view_projection))), _p(_farr(list(cam.projection))), _p(_farr(list(cam.inv_projection))),
+        _p(_farr(list(cam.camera_position))), _p(_farr(list(cam.camera_front))), _p(_farr(list(dir_color))), _p(_farr(list(dir_direction))),
+        _p(_farr(list(P.transform))), _p(_farr(list(P.camera_base))), _p(_farr(list(P.camera_front))), _p(_farr(list(P.xy_scale))),
+        _p(np.array(list(P.resolution_xy), np.int32)), int(P.num_lights), int(P.num_lights_32), int(P.z_max_index), _f(P.z_scale),
+        _p(prep.records), _p(_c(prep.type_mask, np.uint32)), _p(_c(clus.bitmask, np.uint32)), _p(_c(clus.range, np.uint32)), _p(ext),
+        _p(_c(dither_lut, np.uint32)), _p(out))
     return out

@@ -110,6 +110,40 @@ inline glm::vec4 textureGatherOffset(const sampler2DShadow &s, const glm::vec2 &
 }
 inline glm::vec4 textureGather(const sampler2DShadow &s, const glm::vec2 &uv, float ref) { return textureGatherOffset(s, uv, ref, glm::ivec2(0)); }
 #endif
+#if KERNEL == 9
+// fog_light_density.comp: a texel buffer of floats, an array texture of RGBA8 texels, an RGBA16F storage volume
+extern "C" uint16_t orc_f32_to_f16(float f);
+struct samplerBuffer
+{
+	const float *data;
+};
+inline glm::vec4 texelFetch(const samplerBuffer &b, int i) { return glm::vec4(b.data[i], 0.0f, 0.0f, 1.0f); }
+struct texture2DArray
+{
+	const uint32_t *data; // layers x 128 x 128, R8G8B8A8_UNORM
+	int w, h;
+};
+inline glm::vec4 texelFetch(const texture2DArray &t, const glm::ivec3 &p, int)
+{
+	const uint32_t v = t.data[((size_t)p.z * t.h + p.y) * t.w + p.x];
+	return glm::vec4((float)(v & 255u) / 255.0f, (float)((v >> 8) & 255u) / 255.0f, (float)((v >> 16) & 255u) / 255.0f, (float)(v >> 24) / 255.0f);
+}
+struct image3D
+{
+	uint16_t *data;
+	int w, h, d;
+};
+inline void imageStore(image3D &im, const glm::ivec3 &p, const glm::vec4 &v)
+{
+	if (p.x < 0 || p.y < 0 || p.z < 0 || p.x >= im.w || p.y >= im.h || p.z >= im.d)
+		return;
+	uint16_t *o = im.data + 4 * (((size_t)p.z * im.h + p.y) * im.w + p.x);
+	o[0] = orc_f32_to_f16(v.x);
+	o[1] = orc_f32_to_f16(v.y);
+	o[2] = orc_f32_to_f16(v.z);
+	o[3] = orc_f32_to_f16(v.w);
+}
+#endif
 template <typename T> inline T subgroupMin(T v) { return v; }
 template <typename T> inline T subgroupMax(T v) { return v; }
 template <typename T> inline T subgroupOr(T v) { return v; }
@@ -150,6 +184,7 @@ struct TransformsBlock
 
 #include GEN_CPP
 
+#if KERNEL != 9
 namespace
 {
 using Sh = Impl::Shader;
@@ -235,6 +270,7 @@ struct Runner
 	}
 };
 } // namespace
+#endif
 
 extern "C" {
 #if KERNEL == 5 || KERNEL == 7 || KERNEL == 8
@@ -320,6 +356,84 @@ void refk6_directional(int w, int h, const uint32_t *albedo, const uint32_t *nor
 	Runner r;
 	spirv_cross_set_push_constant(r.sh, &reg, sizeof(reg));
 	r.draw(g, inv_view_projection16, y0, y1, out_rgb);
+}
+#elif KERNEL == 9
+// volumetric_fog.cpp:142-228: fog_light_density.comp (base variant), dispatch ceil(w / 4) x ceil(h / 4) x ceil(d / 4) groups of 64
+void refk9_fog_light_density(int w, int h, int d, int dither_offset, float slice_z_log2_scale, float density_mod, float in_scatter_strength,
+                             const float *inv_view_projection16, const float *projection16, const float *inv_projection16, const float *camera_pos3,
+                             const float *camera_front3, const float *dir_color3, const float *dir_direction3, const float *cluster_transform16,
+                             const float *camera_base3, const float *cluster_front3, const float *xy_scale2, const int32_t *resolution_xy2, int num_lights,
+                             int num_lights_32, int z_max_index, float z_scale, const void *lights48, const uint32_t *type_mask, const uint32_t *bitmask,
+                             const uint32_t *cluster_range, const float *slice_extents, const uint32_t *dither_lut, uint16_t *out)
+{
+	using Sh = Impl::Shader;
+	auto *blob = new shim::TransformsBlock<Sh>();
+	std::memset(static_cast<void *>(blob), 0, sizeof(*blob));
+	std::memcpy(blob->cluster_transforms.lights.data(), lights48, (size_t)num_lights * 48);
+	std::memcpy(blob->cluster_transforms.type_mask.data(), type_mask, (size_t)num_lights_32 * 4);
+	shim::g_transforms = blob;
+	shim::g_bitmask = bitmask;
+	shim::g_range = cluster_range;
+	Sh::Resources::ClusterParameters ubo;
+	std::memset(static_cast<void *>(&ubo), 0, sizeof(ubo));
+	std::memcpy(&ubo.cluster.transform, cluster_transform16, 64);
+	ubo.cluster.camera_base = glm::vec3(camera_base3[0], camera_base3[1], camera_base3[2]);
+	ubo.cluster.camera_front = glm::vec3(cluster_front3[0], cluster_front3[1], cluster_front3[2]);
+	ubo.cluster.xy_scale = glm::vec2(xy_scale2[0], xy_scale2[1]);
+	ubo.cluster.resolution_xy = glm::ivec2(resolution_xy2[0], resolution_xy2[1]);
+	ubo.cluster.num_lights = num_lights;
+	ubo.cluster.num_lights_32 = num_lights_32;
+	ubo.cluster.z_max_index = z_max_index;
+	ubo.cluster.z_scale = z_scale;
+	Sh::Resources::Registers reg;
+	std::memset(static_cast<void *>(&reg), 0, sizeof(reg));
+	std::memcpy(&reg.inv_view_projection, inv_view_projection16, 64);
+	reg.z_transform = glm::vec4(projection16[10], projection16[11], projection16[14], projection16[15]); // :161-162
+	reg.count = glm::uvec3((unsigned)w, (unsigned)h, (unsigned)d);
+	reg.dither_offset = dither_offset;
+	reg.inv_resolution = glm::vec3(1.0f / (float)w, 1.0f / (float)h, 1.0f / (float)d);
+	reg.in_scatter_strength = in_scatter_strength;
+	reg.xy_scale = glm::vec2(inv_projection16[0], inv_projection16[5]); // :167-168
+	reg.slice_z_log2_scale = slice_z_log2_scale;
+	reg.density_mod = density_mod;
+	Sh::Resources::RenderParameters render_ubo; // ("global" and "registers" are macros of the generated code)
+	std::memset(static_cast<void *>(&render_ubo), 0, sizeof(render_ubo));
+	render_ubo.camera_position = glm::vec3(camera_pos3[0], camera_pos3[1], camera_pos3[2]);
+	render_ubo.camera_front = glm::vec3(camera_front3[0], camera_front3[1], camera_front3[2]);
+	Sh::Resources::LightingParameters lighting;
+	std::memset(static_cast<void *>(&lighting), 0, sizeof(lighting));
+	lighting.directional.color = glm::vec3(dir_color3[0], dir_color3[1], dir_color3[2]);
+	lighting.directional.direction = glm::vec3(dir_direction3[0], dir_direction3[1], dir_direction3[2]);
+	spirv_cross::samplerBuffer extents = { slice_extents };
+	spirv_cross::texture2DArray lut = { dither_lut, 128, 128 };
+	spirv_cross::image3D image = { out, w, h, d };
+	spirv_cross::sampler2D brdf = { 0 };
+	const spirv_cross_interface *itf = spirv_cross_get_interface();
+	spirv_cross_shader_t *sh = itf->construct();
+	auto bind = [&](unsigned set, unsigned binding, void *ptr) {
+		void *p = ptr;
+		spirv_cross_set_resource(sh, set, binding, &p, sizeof(p));
+	};
+	bind(0, 8, &ubo);
+	bind(3, 0, &reg);
+	bind(0, 0, &render_ubo);
+	bind(0, 1, &lighting);
+	bind(2, 1, &extents);
+	bind(2, 2, &lut);
+	bind(2, 0, &image);
+	bind(0, 4, &brdf);
+	glm::uvec3 num((unsigned)((w + 3) / 4), (unsigned)((h + 3) / 4), (unsigned)((d + 3) / 4)), id(0);
+	spirv_cross_set_builtin(sh, SPIRV_CROSS_BUILTIN_NUM_WORK_GROUPS, &num, sizeof(num));
+	spirv_cross_set_builtin(sh, SPIRV_CROSS_BUILTIN_WORK_GROUP_ID, &id, sizeof(id));
+	for (unsigned z = 0; z < num.z; z++)
+		for (unsigned y = 0; y < num.y; y++)
+			for (unsigned x = 0; x < num.x; x++)
+			{
+				id = glm::uvec3(x, y, z);
+				itf->invoke(sh);
+			}
+	itf->destruct(sh);
+	delete blob;
 }
 #endif
 }

@@ -123,3 +123,21 @@ def test_fog_accumulate_argument_checks(lib):
     assert lib.grb_fog_accumulate(pa, 0, 2, 2, pb, None) == ERR_ARG
     assert lib.grb_fog_accumulate(pa, 2, 2, 2, pa, None) == ERR_ARG and "distinct" in _msg(lib)
     assert lib.grb_fog_accumulate(C.c_void_p(a.ctypes.data + 2), 2, 2, 2, pb, None) == ERR_ARG  # misaligned
+
+
+def test_fog_light_density_argument_checks(lib):
+    from granite_b200 import capi
+
+    g = capi.GrbFogParameters(8, 4, 4, 0, 0.157, 0.5, 1.0)
+    cam, params, bufs = capi.GrbCamera(), capi.GrbClusterParameters(), capi.GrbClusterBuffers()
+    m, v3, buf = np.zeros(16, np.float32), np.zeros(3, np.float32), np.zeros(1024, np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    args = lambda fog, out: (C.byref(fog), C.byref(cam), p(m), p(m), C.byref(params), C.byref(bufs), p(v3), p(v3), p(m), p(buf), out, None)  # noqa: E731
+    assert lib.grb_fog_light_density(*args(g, None)) == ERR_ARG
+    assert lib.grb_fog_light_density(*args(g, p(buf))) == ERR_ARG and "cluster" in _msg(lib)  # cluster_range is null
+    bad = capi.GrbFogParameters(8, 4, 0, 0, 0.157, 0.5, 1.0)
+    assert lib.grb_fog_light_density(*args(bad, p(buf))) == ERR_ARG
+    bad = capi.GrbFogParameters(8, 4, 4, -1, 0.157, 0.5, 1.0)
+    assert lib.grb_fog_light_density(*args(bad, p(buf))) == ERR_ARG
+    bad = capi.GrbFogParameters(8, 4, 4, 0, 0.0, 0.5, 1.0)
+    assert lib.grb_fog_light_density(*args(bad, p(buf))) == ERR_ARG

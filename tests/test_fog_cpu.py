@@ -150,7 +150,23 @@ def test_fog_density_properties(oracle):
         lo, hi = 2.0 * DIR_COLOR[c] * 0.1, 2.0 * DIR_COLOR[c] * 1.0
         assert (out[..., c] >= lo * 0.999).all() and (out[..., c] <= hi * 1.001).all()
     a = out[..., 3]
-    assert (np.diff(a[:, 9, 16]) > 0).all(), "slices get thicker with distance"
+    assert (np.diff(a[::4, 9, 16]) > 0).all(), "slices get thicker with distance (the shader reads one extent per group of four slices)"
     assert a[5, 0, 0] > a[5, 9, 16] and a[5, 17, 31] > a[5, 9, 16], "oblique rays cross more medium"
     ext = oracle.fog_slice_extents(fp)
     assert abs(ext.sum() - 80.0) < 1e-2, "the slices tile [0, z_range]"
+
+
+@pytest.mark.parametrize("n,spots", [(300, 0.25), (64, 1.0), (0, 0.0)])
+def test_oracle_fog_density_equals_reference_shader(oracle, n, spots):
+    """fog_light_density.comp compiled as the forward renderer compiles it for an unshadowed scene (STAGE_COMPUTE,
+    RENDERER_FORWARD, POSITIONAL_LIGHTS, CLUSTERER_BINDLESS; no FOG_REGIONS / TEMPORAL_REPROJECTION / FLOOR_LIGHTING) and run on
+    the CPU.  exp2 / sqrt are libm's here and GLM's there: stored fp16 values within one code."""
+    oracle.build()
+    k = oracle.ref_light_kernels()
+    if k is None or 9 not in k:
+        pytest.skip("oracle/_ref shaders not built (no /root/reference on this machine)")
+    cam, prep, clus, fp, lut = fog_case(oracle, n=n, spots=spots)
+    mine = oracle.fog_light_density(fp, cam, prep, clus, DIR_COLOR, DIR_DIRECTION, lut)
+    ref = oracle.ref_fog_light_density(fp, cam, prep, clus, DIR_COLOR, DIR_DIRECTION, lut)
+    diff = np.abs(mine.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff == 0).mean() > 0.995, (int(diff.max()), float((diff == 0).mean()))
